@@ -1,0 +1,104 @@
+"""ctypes binding of libdm_b200.so (see include/dm_b200.h).
+
+There is no fallback: if the library is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+from .build import LIB_PATH
+
+c_void_p, c_int, c_float, c_ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("layout", c_int), ("m", c_int), ("n", c_int), ("k", c_int),
+        ("a", c_void_p), ("lda", c_ll), ("b", c_void_p), ("ldb", c_ll),
+        ("d", c_void_p), ("ldd_m", c_ll), ("ldd_n", c_ll),
+        ("d_f32", c_int), ("accumulate", c_int), ("bias", c_void_p),
+        ("m_store", c_int), ("n_store", c_int), ("splits", c_int),
+    ]
+
+
+class ConvGeom(C.Structure):
+    _fields_ = [("batch", c_int), ("hs", c_int), ("ws", c_int), ("cs", c_int),
+                ("hb", c_int), ("wb", c_int), ("cb", c_int), ("stride", c_int)]
+
+
+GEMM_NT, GEMM_NN, GEMM_TN = 0, 1, 2
+
+# name -> argtypes (all return int except the first three)
+_SIGS = {
+    "dm_gemm_bf16": [C.POINTER(GemmDesc), c_void_p],
+    "dm_conv_down": [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "dm_conv_up": [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+    "dm_conv_wgrad": [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_void_p],
+    "dm_debug_last_plan": [C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int)],
+    "dm_bn_stats": [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p],
+    "dm_bn_finalize": [c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float,
+                       c_void_p, c_void_p, c_void_p],
+    "dm_bn_apply_act": [c_void_p, c_int, c_ll, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p],
+    "dm_bn_backward": [c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_int, c_float, c_void_p,
+                       c_void_p, c_void_p, c_void_p, c_void_p],
+    "dm_bias_act": [c_void_p, c_ll, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p],
+    "dm_act_backward": [c_void_p, c_void_p, c_ll, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p],
+    "dm_colsum": [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p],
+    "dm_im2col3": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "dm_nhwc3_to_nchw": [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p],
+    "dm_tanh_backward": [c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p],
+    "dm_transpose_bf16": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
+    "dm_pack_conv_weights": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "dm_cast_bf16": [c_void_p, c_ll, c_void_p, c_void_p],
+    "dm_reparam_forward": [c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_void_p],
+    "dm_reparam_backward": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_void_p,
+                            c_void_p, c_void_p],
+    "dm_head_forward": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "dm_head_backward": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                         c_void_p, c_void_p],
+    "dm_mse_sum": [c_void_p, c_void_p, c_ll, c_float, c_void_p, c_float, c_int, c_void_p, c_void_p],
+    "dm_kl": [c_void_p, c_void_p, c_ll, c_float, c_void_p, c_int, c_void_p, c_void_p, c_void_p],
+    "dm_bce_const": [c_void_p, c_int, c_float, c_float, c_float, c_void_p, c_int, c_void_p, c_void_p, c_void_p],
+    "dm_adam_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float, c_int,
+                     c_float, c_void_p, c_void_p],
+}
+
+#: every symbol include/dm_b200.h declares
+EXPORTED = ["dm_last_error", "dm_version", "dm_launch_count", *list(_SIGS)]
+
+_lib = None
+
+
+def load():
+    """Load libdm_b200.so, building it first if the source tree is newer. Raises if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = Path(os.environ.get("DM_B200_LIB", LIB_PATH))
+    if not path.exists() or os.environ.get("DM_B200_REBUILD"):
+        from .build import build
+
+        path = build()
+    lib = C.CDLL(str(path))
+    lib.dm_last_error.restype = C.c_char_p
+    lib.dm_last_error.argtypes = []
+    lib.dm_version.restype = c_int
+    lib.dm_launch_count.restype = c_ll
+    for name, args in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = c_int
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().dm_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(load().dm_launch_count())

@@ -1,0 +1,850 @@
+// HBM-bound kernels of the training step: layout conversion, BatchNorm (training mode) forward/backward
+// with folded ReLU / LeakyReLU, bias+activation, reparameterisation, the N=1 discriminator head, loss
+// reductions.  All are vectorised (8 channels = 16 B of bf16 per thread per access), channel-innermost
+// (NHWC) so a warp touches contiguous memory, and reduce with per-thread accumulators -> shared memory ->
+// one atomicAdd per (block, channel).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <atomic>
+#include <cstdint>
+
+#include "../../include/dm_b200.h"
+#include "dm_common.h"
+
+namespace dm {
+extern std::atomic<long long> g_launch_count;
+
+#define DM_LAUNCHED(name)                                   \
+  do {                                                      \
+    g_launch_count.fetch_add(1, std::memory_order_relaxed); \
+    return check_launch(name);                              \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------ helpers
+struct alignas(16) bf16x8 {
+  __nv_bfloat162 v[4];
+};
+
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&f)[8]);
+template <>
+__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[8]) {
+  bf16x8 x = *reinterpret_cast<const bf16x8*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(x.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&f)[8]) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  float4 b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+  f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
+  bf16x8 x;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  *reinterpret_cast<bf16x8*>(p) = x;
+}
+__device__ __forceinline__ void store8(float* p, const float (&f)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+}
+
+__device__ __forceinline__ float act_fwd(float z, int act, float slope) {
+  if (act == 1) return z > 0.f ? z : 0.f;
+  if (act == 2) return z > 0.f ? z : z * slope;
+  return z;
+}
+__device__ __forceinline__ float act_grad(float z, int act, float slope) {
+  if (act == 1) return z > 0.f ? 1.f : 0.f;
+  if (act == 2) return z > 0.f ? 1.f : slope;
+  return 1.f;
+}
+
+// Thread layout shared by all [rows, C] channel-innermost kernels: TX threads cover TX*8 channels,
+// TY = 256/TX rows in flight; grid.x tiles channels, grid.y tiles rows.
+struct RowLayout {
+  int tx, ty, gx, gy;
+  long long rows_per_block;
+};
+static RowLayout make_row_layout(long long rows, int c) {
+  RowLayout l;
+  int cv = c / 8;
+  l.tx = 1;
+  while (l.tx < cv && l.tx < 256) l.tx <<= 1;
+  if (l.tx > cv) l.tx >>= 1;  // cv not a power of two: fall back to the largest pow2 below (never for this model)
+  if (l.tx < 1) l.tx = 1;
+  l.ty = 256 / l.tx;
+  l.gx = (cv + l.tx - 1) / l.tx;
+  long long want = std::max<long long>(1, (148ll * 8) / l.gx);  // ~8 blocks per SM overall
+  long long rpb = (rows + want - 1) / want;
+  rpb = std::max<long long>(l.ty, (rpb + l.ty - 1) / l.ty * l.ty);
+  l.rows_per_block = rpb;
+  l.gy = static_cast<int>((rows + rpb - 1) / rpb);
+  return l;
+}
+
+// ------------------------------------------------------------------------------------------ BN statistics
+// sums[0][c] += sum_r y[r][c], sums[1][c] += sum_r y[r][c]^2      (sums must be zeroed by the caller)
+template <typename T, int NACC, typename F>
+__device__ __forceinline__ void rows_reduce(long long rows, int c, long long rows_per_block, float* out, F&& body) {
+  extern __shared__ float red[];  // [ty][tx*8*NACC]
+  const int tx = blockDim.x, ty = blockDim.y;
+  const int cv = blockIdx.x * tx + threadIdx.x;
+  const bool live = cv * 8 < c;
+  float acc[NACC][8];
+#pragma unroll
+  for (int a = 0; a < NACC; ++a)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[a][i] = 0.f;
+  const long long r0 = blockIdx.y * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  if (live)
+    for (long long r = r0 + threadIdx.y; r < r1; r += ty) body(r, cv * 8, acc);
+  float* mine = red + (threadIdx.y * tx + threadIdx.x) * (8 * NACC);
+#pragma unroll
+  for (int a = 0; a < NACC; ++a)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mine[a * 8 + i] = acc[a][i];
+  __syncthreads();
+  // column reduction over ty: thread (x, y) sums entries j = y, y+ty.. of the 8*NACC values
+  for (int j = threadIdx.y; j < 8 * NACC; j += ty) {
+    float s = 0.f;
+    for (int y = 0; y < ty; ++y) s += red[(y * tx + threadIdx.x) * (8 * NACC) + j];
+    if (live) atomicAdd(out + (j / 8) * c + cv * 8 + (j % 8), s);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ y, long long rows, int c,
+                                                       long long rows_per_block, float* __restrict__ sums) {
+  rows_reduce<T, 2>(rows, c, rows_per_block, sums, [&](long long r, int ch, float(&acc)[2][8]) {
+    float f[8];
+    load8(y + r * c + ch, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[0][i] += f[i];
+      acc[1][i] += f[i] * f[i];
+    }
+  });
+}
+
+// Per-channel finalize: normalisation constants + running-stat update (momentum, unbiased running var),
+// matching torch.nn.BatchNorm{1,2}d in training mode (models/model.py:451-457,462,468,492,496-504,390-399).
+__global__ void bn_finalize_kernel(const float* __restrict__ sums, long long rows, int c,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   long long* __restrict__ num_batches_tracked, float momentum, float eps,
+                                   float* __restrict__ scale_shift, float* __restrict__ mean_invstd) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch == 0 && num_batches_tracked) *num_batches_tracked += 1;
+  if (ch >= c) return;
+  const double n = static_cast<double>(rows);
+  const double mean = sums[ch] / n;
+  double var = sums[c + ch] / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float sc = gamma[ch] * invstd;
+  scale_shift[ch] = sc;
+  scale_shift[c + ch] = beta[ch] - static_cast<float>(mean) * sc;
+  mean_invstd[ch] = static_cast<float>(mean);
+  mean_invstd[c + ch] = invstd;
+  if (running_mean) {
+    const double unbiased = rows > 1 ? var * n / (n - 1.0) : var;
+    running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * static_cast<float>(mean);
+    running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * static_cast<float>(unbiased);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_apply_act_kernel(const T* __restrict__ y, long long rows, int c,
+                                                           long long rows_per_block,
+                                                           const float* __restrict__ scale_shift, int act,
+                                                           float slope, __nv_bfloat16* __restrict__ out) {
+  const int cv = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cv * 8 >= c) return;
+  float sc[8], sh[8];
+  load8(scale_shift + cv * 8, sc);
+  load8(scale_shift + c + cv * 8, sh);
+  const long long r0 = blockIdx.y * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+    float f[8];
+    load8(y + r * c + cv * 8, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = act_fwd(f[i] * sc[i] + sh[i], act, slope);
+    store8(out + r * c + cv * 8, f);
+  }
+}
+
+// Backward pass 1: sums[0][c] = sum dz, sums[1][c] = sum dz * xhat, dz = dout * act'(z)
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout,
+                                                            const T* __restrict__ y, long long rows, int c,
+                                                            long long rows_per_block,
+                                                            const float* __restrict__ scale_shift,
+                                                            const float* __restrict__ mean_invstd, int act,
+                                                            float slope, float* __restrict__ sums) {
+  const int cv0 = blockIdx.x * blockDim.x + threadIdx.x;
+  float sc[8], sh[8], mu[8], is[8];
+  if (cv0 * 8 < c) {
+    load8(scale_shift + cv0 * 8, sc);
+    load8(scale_shift + c + cv0 * 8, sh);
+    load8(mean_invstd + cv0 * 8, mu);
+    load8(mean_invstd + c + cv0 * 8, is);
+  }
+  rows_reduce<T, 2>(rows, c, rows_per_block, sums, [&](long long r, int ch, float(&acc)[2][8]) {
+    float f[8], g[8];
+    load8(y + r * c + ch, f);
+    load8(dout + r * c + ch, g);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float dz = g[i] * act_grad(f[i] * sc[i] + sh[i], act, slope);
+      acc[0][i] += dz;
+      acc[1][i] += dz * (f[i] - mu[i]) * is[i];
+    }
+  });
+}
+
+// Backward pass 2: dy = gamma * invstd * (dz - mean(dz) - xhat * mean(dz * xhat))
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout,
+                                                           const T* __restrict__ y, long long rows, int c,
+                                                           long long rows_per_block,
+                                                           const float* __restrict__ scale_shift,
+                                                           const float* __restrict__ mean_invstd,
+                                                           const float* __restrict__ sums, int act, float slope,
+                                                           __nv_bfloat16* __restrict__ dy) {
+  const int cv = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cv * 8 >= c) return;
+  float sc[8], sh[8], mu[8], is[8], s0[8], s1[8];
+  load8(scale_shift + cv * 8, sc);
+  load8(scale_shift + c + cv * 8, sh);
+  load8(mean_invstd + cv * 8, mu);
+  load8(mean_invstd + c + cv * 8, is);
+  load8(sums + cv * 8, s0);
+  load8(sums + c + cv * 8, s1);
+  const float inv_n = 1.f / static_cast<float>(rows);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    s0[i] *= inv_n;
+    s1[i] *= inv_n;
+  }
+  const long long r0 = blockIdx.y * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+    float f[8], g[8];
+    load8(y + r * c + cv * 8, f);
+    load8(dout + r * c + cv * 8, g);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float dz = g[i] * act_grad(f[i] * sc[i] + sh[i], act, slope);
+      const float xh = (f[i] - mu[i]) * is[i];
+      g[i] = sc[i] * (dz - s0[i] - xh * s1[i]);  // sc = gamma * invstd
+    }
+    store8(dy + r * c + cv * 8, g);
+  }
+}
+
+// dgamma += sums[1], dbeta += sums[0]  (accumulating, like autograd's AccumulateGrad)
+__global__ void bn_param_grad_kernel(const float* __restrict__ sums, int c, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  dgamma[ch] += sums[c + ch];
+  dbeta[ch] += sums[ch];
+}
+
+// ------------------------------------------------------------------------------------------ bias + activation
+// out = act(acc + bias); writes fp32 and/or bf16 copies.  Backward: dpre = dout * act'(pre) (+ column sums).
+__global__ void __launch_bounds__(256) bias_act_kernel(const float* __restrict__ acc, long long rows, int c,
+                                                       long long rows_per_block, const float* __restrict__ bias,
+                                                       int act, float slope, float* __restrict__ out_f32,
+                                                       __nv_bfloat16* __restrict__ out_bf16) {
+  const int cv = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cv * 8 >= c) return;
+  float b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = 0.f;
+  if (bias) load8(bias + cv * 8, b);
+  const long long r0 = blockIdx.y * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+    float f[8];
+    load8(acc + r * c + cv * 8, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = act_fwd(f[i] + b[i], act, slope);
+    if (out_f32) store8(out_f32 + r * c + cv * 8, f);
+    if (out_bf16) store8(out_bf16 + r * c + cv * 8, f);
+  }
+}
+
+// dpre[r][c] = dout[r][c] * act'(out[r][c]) (sign of out == sign of pre for relu/leaky); colsum[c] += sum_r dpre
+__global__ void __launch_bounds__(256) act_bwd_colsum_kernel(const float* __restrict__ dout,
+                                                             const float* __restrict__ out, long long rows, int c,
+                                                             long long rows_per_block, int act, float slope,
+                                                             __nv_bfloat16* __restrict__ dpre,
+                                                             float* __restrict__ colsum) {
+  rows_reduce<float, 1>(rows, c, rows_per_block, colsum, [&](long long r, int ch, float(&acc)[1][8]) {
+    float g[8], o[8];
+    load8(dout + r * c + ch, g);
+    load8(out + r * c + ch, o);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      g[i] *= act_grad(o[i], act, slope);
+      acc[0][i] += g[i];
+    }
+    store8(dpre + r * c + ch, g);
+  });
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long rows, int c,
+                                                     long long rows_per_block, float* __restrict__ colsum) {
+  rows_reduce<T, 1>(rows, c, rows_per_block, colsum, [&](long long r, int ch, float(&acc)[1][8]) {
+    float f[8];
+    load8(x + r * c + ch, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[0][i] += f[i];
+  });
+}
+
+// ------------------------------------------------------------------------------------------ layout kernels
+// fp32 NCHW 3-channel image -> bf16 im2col matrix [batch*oh*ow, 128]; column = c*25 + kh*5 + kw (75 valid)
+__global__ void __launch_bounds__(256) im2col3_kernel(const float* __restrict__ x, int batch, int h, int w,
+                                                      int stride, __nv_bfloat16* __restrict__ col) {
+  const int oh = h / stride, ow = w / stride;
+  const long long total = static_cast<long long>(batch) * oh * ow * 16;  // 16 groups of 8 columns per pixel
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int grp = static_cast<int>(idx & 15);
+    const long long pix = idx >> 4;
+    const int x0 = static_cast<int>(pix % ow);
+    const int y0 = static_cast<int>((pix / ow) % oh);
+    const int n = static_cast<int>(pix / (static_cast<long long>(ow) * oh));
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = grp * 8 + i;
+      float v = 0.f;
+      if (k < 75) {
+        const int ch = k / 25, t = k - ch * 25, kh = t / 5, kw = t - kh * 5;
+        const int iy = y0 * stride + kh - 2, ix = x0 * stride + kw - 2;
+        if (iy >= 0 && iy < h && ix >= 0 && ix < w) v = __ldg(x + ((static_cast<long long>(n) * 3 + ch) * h + iy) * w + ix);
+      }
+      f[i] = v;
+    }
+    store8(col + pix * 128 + grp * 8, f);
+  }
+}
+
+// fp32 NHWC(3) -> fp32 NCHW, optionally through tanh (decoder output, models/model.py:509,565)
+__global__ void __launch_bounds__(256) nhwc3_to_nchw_kernel(const float* __restrict__ src, long long batch, int hw,
+                                                            int apply_tanh, float* __restrict__ dst) {
+  const long long total = batch * hw;
+  for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < total;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = p / hw;
+    const int q = static_cast<int>(p - n * hw);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      float v = src[p * 3 + ch];
+      if (apply_tanh) v = tanhf(v);
+      dst[(n * 3 + ch) * hw + q] = v;
+    }
+  }
+}
+
+// dy = dout * (1 - out^2), all fp32 NCHW; bias_grad[c] += sum over batch and pixels of dy
+__global__ void __launch_bounds__(256) tanh_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                                                       long long batch, int hw, float* __restrict__ dy,
+                                                       float* __restrict__ bias_grad) {
+  __shared__ float red[3][8];
+  float acc[3] = {0.f, 0.f, 0.f};
+  const long long total = batch * 3 * hw;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float o = out[i];
+    const float g = dout[i] * (1.f - o * o);
+    dy[i] = g;
+    const int ch = static_cast<int>((i / hw) % 3);
+    acc[0] += ch == 0 ? g : 0.f;
+    acc[1] += ch == 1 ? g : 0.f;
+    acc[2] += ch == 2 ? g : 0.f;
+  }
+  if (bias_grad == nullptr) return;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    float v = acc[ch];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[ch][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float v = 0.f;
+    for (int wv = 0; wv < 8; ++wv) v += red[threadIdx.x][wv];
+    atomicAdd(bias_grad + threadIdx.x, v);
+  }
+}
+
+// bf16 [b][r][c] -> [b][c][r] through a 32x32 (+1 pad) shared-memory tile
+__global__ void __launch_bounds__(256) transpose_kernel(const __nv_bfloat16* __restrict__ src, int rows, int cols,
+                                                        __nv_bfloat16* __restrict__ dst) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  const long long base = static_cast<long long>(blockIdx.z) * rows * cols;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[j][threadIdx.x] = src[base + static_cast<long long>(r) * cols + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) dst[base + static_cast<long long>(c) * rows + r] = tile[threadIdx.x][j];
+  }
+}
+
+// fp32 [cs][cb][25] -> bf16 down [25][cs][cb], up [25][cb_pad][cs] (zero rows for cb >= cb), col [cs][128]
+__global__ void __launch_bounds__(256) pack_conv_kernel(const float* __restrict__ w, int cs, int cb, int cb_pad,
+                                                        __nv_bfloat16* __restrict__ w_down,
+                                                        __nv_bfloat16* __restrict__ w_up,
+                                                        __nv_bfloat16* __restrict__ w_col) {
+  const long long n_down = 25ll * cs * cb, n_up = 25ll * cb_pad * cs, n_col = w_col ? 128ll * cs : 0;
+  const long long total = (w_down ? n_down : 0) + (w_up ? n_up : 0) + n_col;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long j = i;
+    if (w_down) {
+      if (j < n_down) {
+        const int b = static_cast<int>(j % cb), s = static_cast<int>((j / cb) % cs), t = static_cast<int>(j / (static_cast<long long>(cb) * cs));
+        w_down[j] = __float2bfloat16_rn(w[(static_cast<long long>(s) * cb + b) * 25 + t]);
+        continue;
+      }
+      j -= n_down;
+    }
+    if (w_up) {
+      if (j < n_up) {
+        const int s = static_cast<int>(j % cs), b = static_cast<int>((j / cs) % cb_pad), t = static_cast<int>(j / (static_cast<long long>(cs) * cb_pad));
+        w_up[j] = __float2bfloat16_rn(b < cb ? w[(static_cast<long long>(s) * cb + b) * 25 + t] : 0.f);
+        continue;
+      }
+      j -= n_up;
+    }
+    {
+      const int k = static_cast<int>(j % 128), s = static_cast<int>(j / 128);
+      w_col[j] = __float2bfloat16_rn(k < cb * 25 ? w[static_cast<long long>(s) * cb * 25 + k] : 0.f);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src, long long n,
+                                                        __nv_bfloat16* __restrict__ dst) {
+  const long long nv = n / 8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nv;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float f[8];
+    load8(src + i * 8, f);
+    store8(dst + i * 8, f);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < n - nv * 8) dst[nv * 8 + threadIdx.x] = __float2bfloat16_rn(src[nv * 8 + threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------ small heads
+// z = mu + eps * exp(0.5 * logvar)   (models/model.py:532-535); writes fp32 and bf16 copies
+__global__ void reparam_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ logvar,
+                                   const float* __restrict__ eps, long long n, float* __restrict__ z_f32,
+                                   __nv_bfloat16* __restrict__ z_bf16) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const float z = mu[i] + eps[i] * expf(0.5f * logvar[i]);
+  if (z_f32) z_f32[i] = z;
+  if (z_bf16) z_bf16[i] = __float2bfloat16_rn(z);
+}
+// dmu = dz (+ dmu_ext), dlogvar = dz * eps * 0.5 * exp(0.5 logvar) (+ dlogvar_ext); bf16 copies for the GEMMs
+__global__ void reparam_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ logvar,
+                                   const float* __restrict__ eps, const float* __restrict__ dmu_ext,
+                                   const float* __restrict__ dlogvar_ext, long long n,
+                                   __nv_bfloat16* __restrict__ dmu, __nv_bfloat16* __restrict__ dlogvar,
+                                   float* __restrict__ dmu_f32, float* __restrict__ dlogvar_f32) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const float g = dz ? dz[i] : 0.f;
+  float a = g, b = g * eps[i] * 0.5f * expf(0.5f * logvar[i]);
+  if (dmu_ext) a += dmu_ext[i];
+  if (dlogvar_ext) b += dlogvar_ext[i];
+  dmu[i] = __float2bfloat16_rn(a);
+  dlogvar[i] = __float2bfloat16_rn(b);
+  if (dmu_f32) dmu_f32[i] = a;
+  if (dlogvar_f32) dlogvar_f32[i] = b;
+}
+
+// Discriminator head Linear(k,1)+Sigmoid (models/model.py:406-408): one warp per row
+__global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__ feat, int rows, int k,
+                                                       const float* __restrict__ w, const float* __restrict__ b,
+                                                       float* __restrict__ prob) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float s = 0.f;
+  for (int i = (threadIdx.x & 31) * 4; i < k; i += 128) {
+    const float4 a = *reinterpret_cast<const float4*>(feat + static_cast<long long>(row) * k + i);
+    const float4 ww = __ldg(reinterpret_cast<const float4*>(w + i));
+    s += a.x * ww.x + a.y * ww.y + a.z * ww.z + a.w * ww.w;
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) prob[row] = 1.f / (1.f + expf(-(s + b[0])));
+}
+// dlogit = dprob * p * (1-p); dfeat[r][:] = dfeat_ext[r][:] + dlogit[r] * w;  dw += sum_r dlogit[r] feat[r][:]; db += sum dlogit
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ dprob, const float* __restrict__ prob,
+                                                       const float* __restrict__ feat, const float* __restrict__ dfeat_ext,
+                                                       int rows, int k, const float* __restrict__ w,
+                                                       float* __restrict__ dfeat, float* __restrict__ dw,
+                                                       float* __restrict__ db) {
+  // one block per 256 columns; loops over rows
+  const int col = blockIdx.x * 256 + threadIdx.x;
+  float accw = 0.f, accb = 0.f;
+  const float wv = col < k ? w[col] : 0.f;
+  for (int r = 0; r < rows; ++r) {
+    const float p = prob[r];
+    const float dl = dprob[r] * p * (1.f - p);
+    accb += dl;
+    if (col < k) {
+      const long long o = static_cast<long long>(r) * k + col;
+      dfeat[o] = (dfeat_ext ? dfeat_ext[o] : 0.f) + dl * wv;
+      accw += dl * feat[o];
+    }
+  }
+  if (col < k && dw) dw[col] += accw;
+  if (col == 0 && db) db[0] += accb;
+}
+
+// ------------------------------------------------------------------------------------------ loss reductions
+template <int NT>
+__device__ __forceinline__ float block_sum(float v) {
+  __shared__ float red[NT / 32];
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+  if (threadIdx.x < NT / 32) s = red[threadIdx.x];
+  if (threadIdx.x < 32)
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __syncthreads();
+  return s;
+}
+
+// loss[0] += wloss * sum (a-b)^2 ; if grad: grad (+)= wgrad * 2 (a-b)      (F.mse_loss(reduction='sum'),
+// experiments/new_betavaegan.py:67-75; new_vae.py:40)
+__global__ void __launch_bounds__(256) mse_sum_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                      long long n, float wloss, float* __restrict__ loss,
+                                                      float wgrad, int grad_accumulate, float* __restrict__ grad) {
+  float acc = 0.f;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float d = a[i] - b[i];
+    acc += d * d;
+    if (grad) grad[i] = (grad_accumulate ? grad[i] : 0.f) + wgrad * 2.f * d;
+  }
+  const float s = block_sum<256>(acc);
+  if (threadIdx.x == 0 && loss) atomicAdd(loss, wloss * s);
+}
+
+// KL = -0.5 sum(1 + logvar - mu^2 - exp(logvar)) (new_betavaegan.py:64-65); loss += w * KL;
+// dmu (+)= w * mu, dlogvar (+)= w * 0.5 (exp(logvar) - 1)
+__global__ void __launch_bounds__(256) kl_kernel(const float* __restrict__ mu, const float* __restrict__ logvar,
+                                                 long long n, float w, float* __restrict__ loss,
+                                                 int grad_accumulate, float* __restrict__ dmu,
+                                                 float* __restrict__ dlogvar) {
+  float acc = 0.f;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float m = mu[i], lv = logvar[i], e = expf(lv);
+    acc += -0.5f * (1.f + lv - m * m - e);
+    if (dmu) dmu[i] = (grad_accumulate ? dmu[i] : 0.f) + w * m;
+    if (dlogvar) dlogvar[i] = (grad_accumulate ? dlogvar[i] : 0.f) + w * 0.5f * (e - 1.f);
+  }
+  const float s = block_sum<256>(acc);
+  if (threadIdx.x == 0 && loss) atomicAdd(loss, w * s);
+}
+
+// nn.BCELoss(mean) against a constant target t (new_betavaegan.py:53,97-101): loss += w * mean(-(t log p + (1-t) log(1-p)))
+// with log clamped at -100; dprob (+)= w/n_total * (-(t/p) + (1-t)/(1-p)) with the clamp's zero-gradient region respected;
+// stat[0] += sum p (for D_x logging)
+__global__ void __launch_bounds__(256) bce_const_kernel(const float* __restrict__ p, int n, float n_total, float target,
+                                                        float w, float* __restrict__ loss, int grad_accumulate,
+                                                        float* __restrict__ dprob, float* __restrict__ stat) {
+  float acc = 0.f, accp = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float q = p[i];
+    const float lp = fmaxf(logf(q), -100.f), l1p = fmaxf(logf(1.f - q), -100.f);
+    acc += -(target * lp + (1.f - target) * l1p);
+    accp += q;
+    if (dprob) {
+      // torch: grad = (p - t) / max((1-p) p, 1e-12) / n
+      const float g = (q - target) / fmaxf((1.f - q) * q, 1e-12f) * (w / n_total);
+      dprob[i] = (grad_accumulate ? dprob[i] : 0.f) + g;
+    }
+  }
+  const float s = block_sum<256>(acc);
+  const float sp = block_sum<256>(accp);
+  if (threadIdx.x == 0) {
+    if (loss) atomicAdd(loss, w * s / n_total);
+    if (stat) atomicAdd(stat, sp);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ Adam
+// torch.optim.Adam (betas, eps, no weight decay, no amsgrad; experiments/new_betavaegan.py:49-50) on a flat buffer,
+// optionally refreshing the bf16 shadow copy the GEMMs read.  28 B/param (+2 B shadow).
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v, long long n, float lr,
+                                                   float beta1, float beta2, float eps, float bc1, float bc2_sqrt,
+                                                   float grad_scale, __nv_bfloat16* __restrict__ shadow) {
+  const long long nv = n / 4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nv;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float* pf = &pp.x; float* gf = &gg.x; float* mf = &mm.x; float* vf = &vv.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gr = gf[j] * grad_scale;
+      mf[j] = beta1 * mf[j] + (1.f - beta1) * gr;
+      vf[j] = beta2 * vf[j] + (1.f - beta2) * gr * gr;
+      const float denom = sqrtf(vf[j]) / bc2_sqrt + eps;
+      pf[j] -= (lr / bc1) * (mf[j] / denom);
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (shadow) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(pp.x, pp.y), hi = __floats2bfloat162_rn(pp.z, pp.w);
+      reinterpret_cast<uint2*>(shadow)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    }
+  }
+  // tail (n not a multiple of 4)
+  const long long t = nv * 4 + threadIdx.x;
+  if (blockIdx.x == 0 && t < n) {
+    const float gr = g[t] * grad_scale;
+    m[t] = beta1 * m[t] + (1.f - beta1) * gr;
+    v[t] = beta2 * v[t] + (1.f - beta2) * gr * gr;
+    p[t] -= (lr / bc1) * (m[t] / (sqrtf(v[t]) / bc2_sqrt + eps));
+    if (shadow) shadow[t] = __float2bfloat16_rn(p[t]);
+  }
+}
+
+static int grid_for(long long work_items, int threads = 256, int max_blocks = 148 * 16) {
+  long long b = (work_items + threads - 1) / threads;
+  return static_cast<int>(std::max<long long>(1, std::min<long long>(b, max_blocks)));
+}
+
+}  // namespace dm
+
+using namespace dm;
+typedef __nv_bfloat16 bf16;
+
+#define DM_CHECK_C8(c, who) DM_REQUIRE((c) % 8 == 0, who ": channel count %d must be a multiple of 8", (c))
+
+extern "C" int dm_bn_stats(const void* y, int y_f32, long long rows, int c, float* sums, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  DM_CHECK_C8(c, "dm_bn_stats");
+  cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(float) * 2 * c, s);
+  if (e != cudaSuccess) return set_error((int)e, "dm_bn_stats memset: %s", cudaGetErrorString(e));
+  RowLayout l = make_row_layout(rows, c);
+  const size_t sm = sizeof(float) * 256 * 16;
+  if (y_f32)
+    bn_stats_kernel<float><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s>>>(static_cast<const float*>(y), rows, c, l.rows_per_block, sums);
+  else
+    bn_stats_kernel<bf16><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s>>>(static_cast<const bf16*>(y), rows, c, l.rows_per_block, sums);
+  DM_LAUNCHED("dm_bn_stats");
+}
+
+extern "C" int dm_bn_finalize(const float* sums, long long rows, int c, const float* gamma, const float* beta,
+                              float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
+                              float eps, float* scale_shift, float* mean_invstd, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  bn_finalize_kernel<<<(c + 255) / 256, 256, 0, s>>>(sums, rows, c, gamma, beta, running_mean, running_var,
+                                                     num_batches_tracked, momentum, eps, scale_shift, mean_invstd);
+  DM_LAUNCHED("dm_bn_finalize");
+}
+
+extern "C" int dm_bn_apply_act(const void* y, int y_f32, long long rows, int c, const float* scale_shift, int act,
+                               float slope, void* out_bf16, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  DM_CHECK_C8(c, "dm_bn_apply_act");
+  RowLayout l = make_row_layout(rows, c);
+  if (y_f32)
+    bn_apply_act_kernel<float><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), 0, s>>>(static_cast<const float*>(y), rows, c, l.rows_per_block, scale_shift, act, slope, static_cast<bf16*>(out_bf16));
+  else
+    bn_apply_act_kernel<bf16><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), 0, s>>>(static_cast<const bf16*>(y), rows, c, l.rows_per_block, scale_shift, act, slope, static_cast<bf16*>(out_bf16));
+  DM_LAUNCHED("dm_bn_apply_act");
+}
+
+extern "C" int dm_bn_backward(const void* dout_bf16, const void* y, int y_f32, long long rows, int c,
+                              const float* scale_shift, const float* mean_invstd, int act, float slope, float* sums,
+                              void* dy_bf16, float* dgamma, float* dbeta, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  DM_CHECK_C8(c, "dm_bn_backward");
+  cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(float) * 2 * c, s);
+  if (e != cudaSuccess) return set_error((int)e, "dm_bn_backward memset: %s", cudaGetErrorString(e));
+  RowLayout l = make_row_layout(rows, c);
+  const size_t sm = sizeof(float) * 256 * 16;
+  const bf16* d = static_cast<const bf16*>(dout_bf16);
+  if (y_f32) {
+    bn_bwd_reduce_kernel<float><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s>>>(d, static_cast<const float*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, act, slope, sums);
+    bn_bwd_apply_kernel<float><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), 0, s>>>(d, static_cast<const float*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, sums, act, slope, static_cast<bf16*>(dy_bf16));
+  } else {
+    bn_bwd_reduce_kernel<bf16><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s>>>(d, static_cast<const bf16*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, act, slope, sums);
+    bn_bwd_apply_kernel<bf16><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), 0, s>>>(d, static_cast<const bf16*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, sums, act, slope, static_cast<bf16*>(dy_bf16));
+  }
+  g_launch_count.fetch_add(2, std::memory_order_relaxed);
+  if (dgamma && dbeta) {
+    bn_param_grad_kernel<<<(c + 255) / 256, 256, 0, s>>>(sums, c, dgamma, dbeta);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  }
+  return check_launch("dm_bn_backward");
+}
+
+extern "C" int dm_bias_act(const float* acc, long long rows, int c, const float* bias, int act, float slope,
+                           float* out_f32, void* out_bf16, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  DM_CHECK_C8(c, "dm_bias_act");
+  RowLayout l = make_row_layout(rows, c);
+  bias_act_kernel<<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), 0, s>>>(acc, rows, c, l.rows_per_block, bias, act, slope, out_f32, static_cast<bf16*>(out_bf16));
+  DM_LAUNCHED("dm_bias_act");
+}
+
+extern "C" int dm_act_backward(const float* dout, const float* out, long long rows, int c, int act, float slope,
+                               void* dpre_bf16, float* colsum, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  DM_CHECK_C8(c, "dm_act_backward");
+  RowLayout l = make_row_layout(rows, c);
+  act_bwd_colsum_kernel<<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), sizeof(float) * 256 * 8, s>>>(dout, out, rows, c, l.rows_per_block, act, slope, static_cast<bf16*>(dpre_bf16), colsum);
+  DM_LAUNCHED("dm_act_backward");
+}
+
+extern "C" int dm_colsum(const void* x, int x_f32, long long rows, int c, float* colsum, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  DM_CHECK_C8(c, "dm_colsum");
+  RowLayout l = make_row_layout(rows, c);
+  const size_t sm = sizeof(float) * 256 * 8;
+  if (x_f32)
+    colsum_kernel<float><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s>>>(static_cast<const float*>(x), rows, c, l.rows_per_block, colsum);
+  else
+    colsum_kernel<bf16><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s>>>(static_cast<const bf16*>(x), rows, c, l.rows_per_block, colsum);
+  DM_LAUNCHED("dm_colsum");
+}
+
+extern "C" int dm_im2col3(const float* x_nchw, int batch, int h, int w, int stride, void* col_bf16, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  DM_REQUIRE(stride == 1 || stride == 2, "dm_im2col3: stride must be 1 or 2");
+  const long long items = static_cast<long long>(batch) * (h / stride) * (w / stride) * 16;
+  im2col3_kernel<<<grid_for(items, 256, 148 * 32), 256, 0, s>>>(x_nchw, batch, h, w, stride, static_cast<bf16*>(col_bf16));
+  DM_LAUNCHED("dm_im2col3");
+}
+
+extern "C" int dm_nhwc3_to_nchw(const float* src, long long batch, int hw, int apply_tanh, float* dst, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  nhwc3_to_nchw_kernel<<<grid_for(batch * hw), 256, 0, s>>>(src, batch, hw, apply_tanh, dst);
+  DM_LAUNCHED("dm_nhwc3_to_nchw");
+}
+
+extern "C" int dm_tanh_backward(const float* dout, const float* out, long long batch, int hw, float* dy,
+                                float* bias_grad, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  tanh_bwd_kernel<<<grid_for(batch * 3 * hw, 256, 148 * 4), 256, 0, s>>>(dout, out, batch, hw, dy, bias_grad);
+  DM_LAUNCHED("dm_tanh_backward");
+}
+
+extern "C" int dm_transpose_bf16(const void* src, int batch, int rows, int cols, void* dst, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  transpose_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32, batch), dim3(32, 8), 0, s>>>(static_cast<const bf16*>(src), rows, cols, static_cast<bf16*>(dst));
+  DM_LAUNCHED("dm_transpose_bf16");
+}
+
+extern "C" int dm_pack_conv_weights(const float* w, int cs, int cb, void* w_down, void* w_up, void* w_col,
+                                    void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  DM_REQUIRE(w_col == nullptr || cb * 25 <= 128, "dm_pack_conv_weights: col form needs cb*25 <= 128");
+  const int cb_pad = std::max(16, (cb + 15) / 16 * 16);
+  const long long total = 25ll * cs * cb + 25ll * cb_pad * cs + 128ll * cs;
+  pack_conv_kernel<<<grid_for(total), 256, 0, s>>>(w, cs, cb, cb_pad, static_cast<bf16*>(w_down), static_cast<bf16*>(w_up), static_cast<bf16*>(w_col));
+  DM_LAUNCHED("dm_pack_conv_weights");
+}
+
+extern "C" int dm_cast_bf16(const float* src, long long n, void* dst, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  DM_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0, "dm_cast_bf16: pointers must be 16-byte aligned");
+  cast_bf16_kernel<<<grid_for(n / 8 + 1), 256, 0, s>>>(src, n, static_cast<bf16*>(dst));
+  DM_LAUNCHED("dm_cast_bf16");
+}
+
+extern "C" int dm_reparam_forward(const float* mu, const float* logvar, const float* eps, long long n, float* z_f32,
+                                  void* z_bf16, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  reparam_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(mu, logvar, eps, n, z_f32, static_cast<bf16*>(z_bf16));
+  DM_LAUNCHED("dm_reparam_forward");
+}
+
+extern "C" int dm_reparam_backward(const float* dz, const float* logvar, const float* eps, const float* dmu_ext,
+                                   const float* dlogvar_ext, long long n, void* dmu_bf16, void* dlogvar_bf16,
+                                   float* dmu_f32, float* dlogvar_f32, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  reparam_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dz, logvar, eps, dmu_ext, dlogvar_ext, n, static_cast<bf16*>(dmu_bf16), static_cast<bf16*>(dlogvar_bf16), dmu_f32, dlogvar_f32);
+  DM_LAUNCHED("dm_reparam_backward");
+}
+
+extern "C" int dm_head_forward(const float* feat, int rows, int k, const float* w, const float* b, float* prob,
+                               void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  DM_REQUIRE(k % 4 == 0, "dm_head_forward: k must be a multiple of 4");
+  head_fwd_kernel<<<(rows + 7) / 8, 256, 0, s>>>(feat, rows, k, w, b, prob);
+  DM_LAUNCHED("dm_head_forward");
+}
+
+extern "C" int dm_head_backward(const float* dprob, const float* prob, const float* feat, const float* dfeat_ext,
+                                int rows, int k, const float* w, float* dfeat, float* dw, float* db, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  head_bwd_kernel<<<(k + 255) / 256, 256, 0, s>>>(dprob, prob, feat, dfeat_ext, rows, k, w, dfeat, dw, db);
+  DM_LAUNCHED("dm_head_backward");
+}
+
+extern "C" int dm_mse_sum(const float* a, const float* b, long long n, float wloss, float* loss, float wgrad,
+                          int grad_accumulate, float* grad, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  mse_sum_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, s>>>(a, b, n, wloss, loss, wgrad, grad_accumulate, grad);
+  DM_LAUNCHED("dm_mse_sum");
+}
+
+extern "C" int dm_kl(const float* mu, const float* logvar, long long n, float w, float* loss, int grad_accumulate,
+                     float* dmu, float* dlogvar, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  kl_kernel<<<grid_for(n, 256, 148), 256, 0, s>>>(mu, logvar, n, w, loss, grad_accumulate, dmu, dlogvar);
+  DM_LAUNCHED("dm_kl");
+}
+
+extern "C" int dm_bce_const(const float* p, int n, float n_total, float target, float w, float* loss,
+                            int grad_accumulate, float* dprob, float* stat, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  bce_const_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(p, n, n_total, target, w, loss, grad_accumulate, dprob, stat);
+  DM_LAUNCHED("dm_bce_const");
+}
+
+extern "C" int dm_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                            float beta2, float eps, int step, float grad_scale, void* shadow_bf16, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  DM_REQUIRE(step >= 1, "dm_adam_step: step must be >= 1");
+  const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
+  const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
+  adam_kernel<<<grid_for(n / 4 + 1, 256, 148 * 8), 256, 0, s>>>(p, g, m, v, n, lr, beta1, beta2, eps, static_cast<float>(bc1), static_cast<float>(sqrt(bc2)), grad_scale, static_cast<bf16*>(shadow_bf16));
+  DM_LAUNCHED("dm_adam_step");
+}

@@ -1,0 +1,738 @@
+// Tap-GEMM: one tcgen05/TMEM/TMA kernel behind every dense contraction of the training step.
+//
+//   D[128 x BN tile] = sum over k-blocks  A_kb * B_kb^T      (bf16 x bf16 -> fp32 in TMEM)
+//
+// MODE_FWD   : M = rows of a pixel tile (or plain matrix rows); the K loop walks (filter tap, channel
+//              chunk).  The A k-block of tap (kh,kw) is ONE 5-D TMA box of the NHWC activation tensor,
+//              shifted by the tap; padding comes from TMA out-of-bounds zero fill, stride 2 from a
+//              parity-split view (c,w,p,h,n) = (2C, W/2, 2, H/2, B) of the same memory.  Implicit GEMM:
+//              no im2col buffer exists.  B = packed weights [tap][N][K] (K-major) or [K][N] (MN-major).
+// MODE_WGRAD : M and N are channels, the K loop walks pixel tiles (K = batch*h*w).  Both operands are
+//              MN-major boxes of NHWC tensors (channels contiguous), B shifted by one fixed tap.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 =
+// epilogue (TMEM -> registers -> global).  smem ring of `stages` k-blocks guarded by full/empty mbarriers.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/dm_b200.h"
+#include "dm_common.h"
+#include "dm_ptx.cuh"
+
+namespace dm {
+
+extern std::atomic<long long> g_launch_count;
+
+struct Tap {
+  int16_t dc;      // offset along dim 0 (channels / parity-merged channels)
+  int8_t dw, dp, dh;
+  uint8_t wt;      // weight tap index (B coordinate 2 in MODE_FWD)
+  int16_t nvalid;  // MODE_WGRAD: valid columns of this tap unit
+  int32_t out_off; // MODE_WGRAD: element offset of this tap unit in the output
+};
+
+enum { MODE_FWD = 0, MODE_WGRAD = 1 };
+
+struct alignas(64) GemmParams {
+  CUtensorMap map_a;
+  CUtensorMap map_b;
+  int mode;
+  int a_mn, b_mn;  // 0 = K-major, 1 = MN-major
+  int kc;          // K elements per k-block: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B, K-major only)
+  int bn;          // N tile (multiple of 16, <= 256)
+  int stages;
+  int tmem_cols;
+  int num_splits;
+  int num_n_tiles;
+  int cpt;     // MODE_FWD: channel chunks per tap
+  int num_kb;  // MODE_WGRAD: total pixel-tile k-blocks
+  // pixel-tile decode: tile j -> (w0, h0, n0); used for the M tile (FWD) or the K tile (WGRAD)
+  int tw_step, tpi, th_step, tn_step;
+  int bw, bh;  // FWD row r -> w = w0 + r % bw, h = h0 + (r / bw) % bh, n = n0 + r / (bw*bh)
+  int phase_tap_start[5];
+  Tap taps[28];
+  void* out;
+  const float* bias;
+  int out_f32, out_atomic;
+  // FWD epilogue: element offset of row (w,h,n) and column j
+  long long os_w, os_h, os_n, os_col;
+  long long phase_out_off[4];
+  int w_lim, n_lim;  // row validity
+  int n_valid;       // global column validity
+  // WGRAD epilogue: off = m*os_m + (n % nmod)*os_n1 + (n / nmod)*os_n2 + tap.out_off
+  long long os_m, os_n1, os_n2;
+  int nmod;
+  int m_valid;
+};
+
+constexpr int kThreads = 192;
+constexpr int kAtomBytes = 8192;  // one MN-major atom: 64 k-rows x 128 B
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int a_bytes = p.a_mn ? 2 * kAtomBytes : 128 * p.kc * 2;
+  const int b_bytes = p.b_mn ? (p.bn >> 6) * kAtomBytes : p.bn * p.kc * 2;
+  const int stage_bytes = a_bytes + b_bytes;
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full_bar = empty_bar + p.stages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  // ---- which tile / k-range does this CTA own
+  const int m_tile = blockIdx.x;
+  int n_tile, phase = 0, split, total_kb, tap_begin = 0, unit_tap = 0;
+  if (p.mode == MODE_FWD) {
+    n_tile = blockIdx.y;
+    phase = blockIdx.z / p.num_splits;
+    split = blockIdx.z - phase * p.num_splits;
+    tap_begin = p.phase_tap_start[phase];
+    total_kb = (p.phase_tap_start[phase + 1] - tap_begin) * p.cpt;
+  } else {
+    unit_tap = blockIdx.y / p.num_n_tiles;
+    n_tile = blockIdx.y - unit_tap * p.num_n_tiles;
+    split = blockIdx.z;
+    total_kb = p.num_kb;
+  }
+  const int kb_per_split = (total_kb + p.num_splits - 1) / p.num_splits;
+  const int kb0 = split * kb_per_split;
+  const int kb1 = min(total_kb, kb0 + kb_per_split);
+  const bool has_work = kb0 < kb1;
+
+  // ---- one-time setup
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.map_a);
+    tma_prefetch_desc(&p.map_b);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < p.stages; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      mbar_init(tmem_full_bar, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr_smem, static_cast<uint32_t>(p.tmem_cols));
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // =========================================================== TMA producer (one thread)
+    if (lane == 0 && has_work) {
+      int stage = 0;
+      uint32_t parity = 0;
+      if (p.mode == MODE_FWD) {
+        const int w0 = m_tile * p.tw_step;
+        const int h0 = (m_tile % p.tpi) * p.th_step;
+        const int n0 = (m_tile / p.tpi) * p.tn_step;
+        const int ncol0 = n_tile * p.bn;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          const int t = kb / p.cpt;
+          const int chunk = kb - t * p.cpt;
+          const Tap tap = p.taps[tap_begin + t];
+          uint8_t* sa = smem + stage * stage_bytes;
+          uint8_t* sb = sa + a_bytes;
+          mbar_wait(&empty_bar[stage], parity ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
+          tma_load_5d(sa, &p.map_a, &full_bar[stage], tap.dc + chunk * p.kc, w0 + tap.dw, tap.dp, h0 + tap.dh,
+                      n0);
+          if (!p.b_mn) {
+            tma_load_3d(sb, &p.map_b, &full_bar[stage], chunk * p.kc, ncol0, tap.wt);
+          } else {
+            for (int a = 0; a < (p.bn >> 6); ++a)
+              tma_load_3d(sb + a * kAtomBytes, &p.map_b, &full_bar[stage], ncol0 + a * 64, chunk * 64, tap.wt);
+          }
+          if (++stage == p.stages) {
+            stage = 0;
+            parity ^= 1u;
+          }
+        }
+      } else {
+        const Tap tap = p.taps[unit_tap];
+        const int mch0 = m_tile * 128;
+        const int nch0 = n_tile * p.bn;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          const int w0 = kb * p.tw_step;
+          const int h0 = (kb % p.tpi) * p.th_step;
+          const int n0 = (kb / p.tpi) * p.tn_step;
+          uint8_t* sa = smem + stage * stage_bytes;
+          uint8_t* sb = sa + a_bytes;
+          mbar_wait(&empty_bar[stage], parity ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
+          for (int a = 0; a < 2; ++a)
+            tma_load_5d(sa + a * kAtomBytes, &p.map_a, &full_bar[stage], mch0 + a * 64, w0, 0, h0, n0);
+          for (int a = 0; a < (p.bn >> 6); ++a)
+            tma_load_5d(sb + a * kAtomBytes, &p.map_b, &full_bar[stage], nch0 + a * 64 + tap.dc, w0 + tap.dw,
+                        tap.dp, h0 + tap.dh, n0);
+          if (++stage == p.stages) {
+            stage = 0;
+            parity ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================================================== MMA issuer (one thread)
+    if (lane == 0 && has_work) {
+      const uint32_t idesc = make_idesc_bf16(128u, static_cast<uint32_t>(p.bn), p.a_mn, p.b_mn);
+      const uint32_t k_layout = (p.kc == 64) ? 2u : 4u;          // SWIZZLE_128B : SWIZZLE_64B
+      const uint32_t k_sbo = static_cast<uint32_t>(8 * p.kc * 2);  // 8 rows of one swizzle atom
+      const uint32_t a_step = p.a_mn ? 2048u : 32u;              // bytes per UMMA_K (16 elements of K)
+      const uint32_t b_step = p.b_mn ? 2048u : 32u;
+      int stage = 0;
+      uint32_t parity = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], parity);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
+        const uint32_t b_addr = a_addr + static_cast<uint32_t>(a_bytes);
+        const int nk = p.kc >> 4;
+#pragma unroll 4
+        for (int k = 0; k < nk; ++k) {
+          const uint64_t da = p.a_mn ? make_smem_desc(a_addr + k * a_step, kAtomBytes, 1024u, 2u)
+                                     : make_smem_desc(a_addr + k * a_step, 0u, k_sbo, k_layout);
+          const uint64_t db = p.b_mn ? make_smem_desc(b_addr + k * b_step, kAtomBytes, 1024u, 2u)
+                                     : make_smem_desc(b_addr + k * b_step, 0u, k_sbo, k_layout);
+          umma_bf16(tmem_base, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above retire
+        if (++stage == p.stages) {
+          stage = 0;
+          parity ^= 1u;
+        }
+      }
+      umma_commit(tmem_full_bar);  // accumulator complete -> epilogue
+    }
+  } else if (has_work) {
+    // =========================================================== epilogue (4 warps, 128 TMEM lanes)
+    const int q = warp & 3;       // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;  // row of the 128-row tile
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    float* outf = reinterpret_cast<float*>(p.out);
+    __nv_bfloat16* outh = reinterpret_cast<__nv_bfloat16*>(p.out);
+
+    if (p.mode == MODE_FWD) {
+      const int w = m_tile * p.tw_step + r % p.bw;
+      const int h = (m_tile % p.tpi) * p.th_step + (r / p.bw) % p.bh;
+      const int n = (m_tile / p.tpi) * p.tn_step + r / (p.bw * p.bh);
+      const bool row_ok = (w < p.w_lim) && (n < p.n_lim);
+      const long long row_off = w * p.os_w + h * p.os_h + n * p.os_n + p.phase_out_off[phase];
+      const bool add_bias = (p.bias != nullptr) && (split == 0);
+      for (int c0 = 0; c0 < p.bn; c0 += 32) {
+        uint32_t v[32];
+        __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the divergent stores
+        tmem_ld_32x32(lane_addr + static_cast<uint32_t>(c0), v);
+        tmem_ld_wait();
+        const int ng = n_tile * p.bn + c0;  // first global column of this chunk
+        if (!row_ok || ng >= p.n_valid) continue;
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          f[i] = __uint_as_float(v[i]);
+          if (add_bias && ng + i < p.n_valid) f[i] += __ldg(p.bias + ng + i);
+        }
+        const bool full_chunk = (ng + 32 <= p.n_valid) && (c0 + 32 <= p.bn) && (p.os_col == 1);
+        if (p.out_atomic) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < p.bn && ng + i < p.n_valid) atomicAdd(outf + row_off + (ng + i) * p.os_col, f[i]);
+        } else if (p.out_f32) {
+          if (full_chunk && ((row_off + ng) & 3) == 0) {
+            float4* dst = reinterpret_cast<float4*>(outf + row_off + ng);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c0 + i < p.bn && ng + i < p.n_valid) outf[row_off + (ng + i) * p.os_col] = f[i];
+          }
+        } else {
+          if (full_chunk && ((row_off + ng) & 7) == 0) {
+            uint4* dst = reinterpret_cast<uint4*>(outh + row_off + ng);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              dst[i] = make_uint4(pack_bf16x2(f[8 * i], f[8 * i + 1]), pack_bf16x2(f[8 * i + 2], f[8 * i + 3]),
+                                  pack_bf16x2(f[8 * i + 4], f[8 * i + 5]), pack_bf16x2(f[8 * i + 6], f[8 * i + 7]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c0 + i < p.bn && ng + i < p.n_valid)
+                outh[row_off + (ng + i) * p.os_col] = __float2bfloat16_rn(f[i]);
+          }
+        }
+      }
+    } else {
+      const Tap tap = p.taps[unit_tap];
+      const int m = m_tile * 128 + r;
+      const bool row_ok = m < p.m_valid;
+      for (int c0 = 0; c0 < p.bn; c0 += 32) {
+        uint32_t v[32];
+        __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the divergent stores
+        tmem_ld_32x32(lane_addr + static_cast<uint32_t>(c0), v);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int nl = n_tile * p.bn + c0 + i;  // column within this tap unit
+          if (c0 + i < p.bn && nl < tap.nvalid) {
+            const long long off = m * p.os_m + (nl % p.nmod) * p.os_n1 + (nl / p.nmod) * p.os_n2 + tap.out_off;
+            atomicAdd(outf + off, __uint_as_float(v[i]));
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+}
+
+// ================================================================================ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+// rank-`rank` bf16 tensor map; dims/box innermost first; strides in BYTES for dims 1..rank-1.
+static int encode_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides,
+                      const uint32_t* box, int swizzle_bytes) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(-2, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides[i];
+  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                               : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(ptr), gdim,
+                  gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    return set_error(static_cast<int>(r),
+                     "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu %llu] box [%u %u %u %u %u]",
+                     static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                     (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+                     (unsigned long long)(rank > 4 ? dims[4] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0,
+                     rank > 3 ? box[3] : 0, rank > 4 ? box[4] : 0);
+  }
+  return 0;
+}
+
+// NHWC bf16 activation [b,h,w,c] as the 5-D view (c, w, p, h, n); stride 2 -> parity-split view.
+static int encode_act_map(CUtensorMap* m, const void* ptr, int b, int h, int w, int c, int stride, const uint32_t* box,
+                          int swizzle_bytes) {
+  uint64_t dims[5], str[4];
+  const uint64_t e = 2;
+  if (stride == 1) {
+    dims[0] = c; dims[1] = w; dims[2] = 1; dims[3] = h; dims[4] = b;
+    str[0] = c * e; str[1] = (uint64_t)w * c * e; str[2] = (uint64_t)w * c * e; str[3] = (uint64_t)h * w * c * e;
+  } else {
+    dims[0] = 2 * c; dims[1] = w / 2; dims[2] = 2; dims[3] = h / 2; dims[4] = b;
+    str[0] = 2 * c * e; str[1] = (uint64_t)w * c * e; str[2] = 2ull * w * c * e; str[3] = (uint64_t)h * w * c * e;
+  }
+  return encode_map(m, ptr, 5, dims, str, box, swizzle_bytes);
+}
+
+// Row-major bf16 matrix [rows, cols] (leading dimension ld) as the 5-D view (c=cols, w=rows, 1, 1, 1).
+static int encode_mat_map5(CUtensorMap* m, const void* ptr, long long rows, long long cols, long long ld,
+                           uint32_t box_c, uint32_t box_r, int swizzle_bytes) {
+  uint64_t dims[5] = {(uint64_t)cols, (uint64_t)rows, 1, 1, 1};
+  const uint64_t rs = (uint64_t)ld * 2;
+  uint64_t str[4] = {rs, rs * rows, rs * rows, rs * rows};
+  uint32_t box[5] = {box_c, box_r, 1, 1, 1};
+  return encode_map(m, ptr, 5, dims, str, box, swizzle_bytes);
+}
+
+// bf16 [t][rows][cols] as 3-D (cols, rows, t)
+static int encode_w_map3(CUtensorMap* m, const void* ptr, long long t, long long rows, long long cols, long long ld,
+                         uint32_t box_c, uint32_t box_r, int swizzle_bytes) {
+  uint64_t dims[3] = {(uint64_t)cols, (uint64_t)rows, (uint64_t)t};
+  uint64_t str[2] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * rows};
+  uint32_t box[3] = {box_c, box_r, 1};
+  return encode_map(m, ptr, 3, dims, str, box, swizzle_bytes);
+}
+
+static int g_last_grid[3] = {0, 0, 0};
+static int g_last_smem = 0, g_last_stages = 0;
+
+static int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return s ? atoi(s) : dflt;
+}
+
+static int pow2_cols(int n) {
+  int c = 32;
+  while (c < n) c <<= 1;
+  return c;
+}
+
+static int launch(GemmParams& p, dim3 grid, cudaStream_t stream) {
+  const int a_bytes = p.a_mn ? 2 * kAtomBytes : 128 * p.kc * 2;
+  const int b_bytes = p.b_mn ? (p.bn >> 6) * kAtomBytes : p.bn * p.kc * 2;
+  const int stage_bytes = a_bytes + b_bytes;
+  // two CTAs per SM when a stage is small; deeper ring otherwise
+  const int budget = stage_bytes <= 32768 ? env_int("DM_SMEM_BUDGET_SMALL", 98304) : env_int("DM_SMEM_BUDGET_BIG", 196608);
+  int stages = std::max(2, std::min(8, budget / stage_bytes));
+  p.stages = stages;
+  p.tmem_cols = pow2_cols(p.bn);
+  const int smem = stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(dm_tapgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  if (attr_err != cudaSuccess) return set_error((int)attr_err, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+  g_last_grid[0] = grid.x; g_last_grid[1] = grid.y; g_last_grid[2] = grid.z;
+  g_last_smem = smem; g_last_stages = stages;
+  dm_tapgemm_kernel<<<grid, kThreads, smem, stream>>>(p);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return check_launch("dm_tapgemm_kernel");
+}
+
+// pixel tile of P pixels on an (h, w) grid: full-width rows
+struct PixTile {
+  int bw, bh, bimg, tpi, th_step, tn_step, tiles;
+};
+static bool make_pix_tile(int P, int batch, int h, int w, PixTile* t) {
+  if (w <= 0 || h <= 0 || P % w != 0) return false;
+  t->bw = w;
+  if (w * h >= P) {
+    t->bh = P / w;
+    if (h % t->bh != 0) return false;
+    t->bimg = 1;
+    t->tpi = h / t->bh;
+    t->th_step = t->bh;
+    t->tn_step = 1;
+    t->tiles = batch * t->tpi;
+  } else {
+    if (P % (w * h) != 0) return false;
+    t->bh = h;
+    t->bimg = P / (w * h);
+    t->tpi = 1;
+    t->th_step = 0;
+    t->tn_step = t->bimg;
+    t->tiles = (batch + t->bimg - 1) / t->bimg;
+  }
+  return true;
+}
+
+static void init_params(GemmParams& p) {
+  memset(&p, 0, sizeof(p));
+  p.num_splits = 1;
+  p.num_n_tiles = 1;
+  p.cpt = 1;
+  p.nmod = 1 << 30;
+  p.os_col = 1;
+  p.tpi = 1 << 30;
+}
+
+static int pick_bn(int n, int cap) {
+  // largest multiple of 16 <= cap that divides n rounded up to 16
+  int n16 = (n + 15) / 16 * 16;
+  if (n16 <= cap) return n16;
+  for (int b = cap; b >= 16; b -= 16)
+    if (n16 % b == 0) return b;
+  return cap;
+}
+
+}  // namespace dm
+
+using namespace dm;
+
+extern "C" int dm_debug_last_plan(int* grid_xyz, int* smem_bytes, int* stages) {
+  if (grid_xyz) { grid_xyz[0] = g_last_grid[0]; grid_xyz[1] = g_last_grid[1]; grid_xyz[2] = g_last_grid[2]; }
+  if (smem_bytes) *smem_bytes = g_last_smem;
+  if (stages) *stages = g_last_stages;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ dense GEMM
+extern "C" int dm_gemm_bf16(const dm_gemm_desc* g, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DM_REQUIRE(g != nullptr, "dm_gemm_bf16: null descriptor");
+  DM_REQUIRE(g->m > 0 && g->n > 0 && g->k > 0, "dm_gemm_bf16: bad shape %d %d %d", g->m, g->n, g->k);
+  DM_REQUIRE(g->lda % 8 == 0 && g->ldb % 8 == 0, "dm_gemm_bf16: lda/ldb must be multiples of 8 elements");
+  DM_REQUIRE((reinterpret_cast<uintptr_t>(g->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(g->b) & 15) == 0,
+             "dm_gemm_bf16: operands must be 16-byte aligned");
+  const int splits = std::max(1, g->splits);
+  DM_REQUIRE(splits == 1 || (g->accumulate && g->d_f32), "dm_gemm_bf16: split-K needs fp32 accumulate output");
+  DM_REQUIRE(!g->accumulate || g->d_f32, "dm_gemm_bf16: accumulate needs fp32 output");
+  GemmParams p;
+  init_params(p);
+  p.out = g->d;
+  p.bias = g->bias;
+  p.out_f32 = g->d_f32;
+  p.out_atomic = g->accumulate;
+  p.num_splits = splits;
+  const int m_store = g->m_store > 0 ? g->m_store : g->m;
+  const int n_store = g->n_store > 0 ? g->n_store : g->n;
+  dim3 grid;
+  int rc;
+  if (g->layout == DM_GEMM_NT || g->layout == DM_GEMM_NN) {
+    p.mode = MODE_FWD;
+    p.a_mn = 0;
+    p.b_mn = (g->layout == DM_GEMM_NN);
+    p.kc = (g->k % 64 == 0 || p.b_mn) ? 64 : 32;
+    if (!p.b_mn && g->k < 64 && g->k % 32 == 0) p.kc = 32;
+    DM_REQUIRE(g->k % p.kc == 0 || g->k > p.kc, "dm_gemm_bf16: unsupported k %d", g->k);
+    p.bn = p.b_mn ? (g->n >= 128 ? 128 : 64) : pick_bn(g->n, env_int("DM_BN_CAP", 128));
+    p.cpt = (g->k + p.kc - 1) / p.kc;
+    p.phase_tap_start[0] = 0;
+    p.phase_tap_start[1] = 1;
+    p.tw_step = 128; p.tpi = 1 << 30; p.th_step = 0; p.tn_step = 0;
+    p.bw = 128; p.bh = 1;
+    p.os_w = g->ldd_m; p.os_col = g->ldd_n;
+    p.w_lim = m_store; p.n_lim = 1; p.n_valid = n_store;
+    rc = encode_mat_map5(&p.map_a, g->a, g->m, g->k, g->lda, p.kc, 128, p.kc * 2);
+    if (rc) return rc;
+    if (!p.b_mn)
+      rc = encode_w_map3(&p.map_b, g->b, 1, g->n, g->k, g->ldb, p.kc, p.bn, p.kc * 2);
+    else
+      rc = encode_w_map3(&p.map_b, g->b, 1, g->k, g->n, g->ldb, 64, 64, 128);
+    if (rc) return rc;
+    p.num_n_tiles = (g->n + p.bn - 1) / p.bn;
+    DM_REQUIRE(splits <= p.cpt, "dm_gemm_bf16: splits %d > k-blocks %d", splits, p.cpt);
+    grid = dim3((g->m + 127) / 128, p.num_n_tiles, splits);
+  } else if (g->layout == DM_GEMM_TN) {
+    DM_REQUIRE(g->d_f32 && g->accumulate, "dm_gemm_bf16: TN (weight-gradient) output is fp32 accumulate");
+    DM_REQUIRE(g->bias == nullptr, "dm_gemm_bf16: TN has no bias");
+    p.mode = MODE_WGRAD;
+    p.a_mn = 1; p.b_mn = 1; p.kc = 64;
+    p.bn = g->n >= 256 ? env_int("DM_BN_WGRAD", 256) : (g->n >= 128 ? 128 : 64);
+    p.num_kb = (g->k + 63) / 64;
+    p.tw_step = 64; p.tpi = 1 << 30; p.th_step = 0; p.tn_step = 0;
+    p.taps[0].nvalid = static_cast<int16_t>(std::min(n_store, 32767));
+    p.os_m = g->ldd_m; p.os_n1 = g->ldd_n; p.os_n2 = 0; p.nmod = 1 << 30;
+    p.m_valid = m_store;
+    // A stored [k][m]: (c = m, w = k rows); B stored [k][n]
+    rc = encode_mat_map5(&p.map_a, g->a, g->k, g->m, g->lda, 64, 64, 128);
+    if (rc) return rc;
+    rc = encode_mat_map5(&p.map_b, g->b, g->k, g->n, g->ldb, 64, 64, 128);
+    if (rc) return rc;
+    p.num_n_tiles = (g->n + p.bn - 1) / p.bn;
+    if (n_store > 32767) p.taps[0].nvalid = 32767;  // columns are bounded by n_tiles*bn anyway
+    DM_REQUIRE(g->n <= 32767 || g->n % p.bn == 0, "dm_gemm_bf16: TN n too large for masked store");
+    DM_REQUIRE(splits <= p.num_kb, "dm_gemm_bf16: splits %d > k-blocks %d", splits, p.num_kb);
+    grid = dim3((g->m + 127) / 128, p.num_n_tiles, splits);
+  } else {
+    return set_error(-1, "dm_gemm_bf16: unknown layout %d", g->layout);
+  }
+  return launch(p, grid, stream);
+}
+
+// ------------------------------------------------------------------------------------------ convolutions
+static int check_geom(const dm_conv_geom* g, const char* who) {
+  DM_REQUIRE(g != nullptr, "%s: null geometry", who);
+  DM_REQUIRE(g->stride == 1 || g->stride == 2, "%s: stride must be 1 or 2", who);
+  DM_REQUIRE(g->hb == g->hs * g->stride && g->wb == g->ws * g->stride, "%s: big side must be stride x small side", who);
+  DM_REQUIRE(g->batch > 0 && g->cs > 0 && g->cb > 0, "%s: bad sizes", who);
+  return 0;
+}
+
+// taps of `small = conv(big)` in the (c,w,p,h,n) view of big
+static void down_taps(const dm_conv_geom* g, Tap* taps) {
+  for (int kh = 0; kh < 5; ++kh)
+    for (int kw = 0; kw < 5; ++kw) {
+      Tap& t = taps[kh * 5 + kw];
+      memset(&t, 0, sizeof(t));
+      t.wt = static_cast<uint8_t>(kh * 5 + kw);
+      if (g->stride == 1) {
+        t.dh = static_cast<int8_t>(kh - 2);
+        t.dw = static_cast<int8_t>(kw - 2);
+      } else {
+        const int eh = kh - 2, ew = kw - 2;
+        const int ah = (eh >= 0) ? eh / 2 : -((-eh + 1) / 2);
+        const int aw = (ew >= 0) ? ew / 2 : -((-ew + 1) / 2);
+        t.dh = static_cast<int8_t>(ah);
+        t.dp = static_cast<int8_t>(eh - 2 * ah);
+        t.dw = static_cast<int8_t>(aw);
+        t.dc = static_cast<int16_t>((ew - 2 * aw) * g->cb);
+      }
+    }
+}
+
+extern "C" int dm_conv_down(const dm_conv_geom* g, const void* big, const void* w_down, const float* bias,
+                            void* out_small, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (int rc = check_geom(g, "dm_conv_down")) return rc;
+  DM_REQUIRE(g->cb % 32 == 0, "dm_conv_down: cb %d must be a multiple of 32", g->cb);
+  DM_REQUIRE(g->cs % 16 == 0, "dm_conv_down: cs %d must be a multiple of 16", g->cs);
+  PixTile pt;
+  DM_REQUIRE(make_pix_tile(128, g->batch, g->hs, g->ws, &pt), "dm_conv_down: unsupported grid %dx%d", g->hs, g->ws);
+  GemmParams p;
+  init_params(p);
+  p.mode = MODE_FWD;
+  p.kc = (g->cb % 64 == 0) ? 64 : 32;
+  p.bn = pick_bn(g->cs, env_int("DM_BN_CAP", 128));
+  p.cpt = g->cb / p.kc;
+  p.phase_tap_start[0] = 0;
+  p.phase_tap_start[1] = 25;
+  down_taps(g, p.taps);
+  p.tw_step = 0; p.tpi = pt.tpi; p.th_step = pt.th_step; p.tn_step = pt.tn_step;
+  p.bw = pt.bw; p.bh = pt.bh;
+  p.out = out_small; p.bias = bias; p.out_f32 = 0; p.out_atomic = 0;
+  p.os_w = g->cs; p.os_h = (long long)g->ws * g->cs; p.os_n = (long long)g->hs * g->ws * g->cs; p.os_col = 1;
+  p.w_lim = g->ws; p.n_lim = g->batch; p.n_valid = g->cs;
+  uint32_t box[5] = {(uint32_t)p.kc, (uint32_t)pt.bw, 1, (uint32_t)pt.bh, (uint32_t)pt.bimg};
+  if (int rc = encode_act_map(&p.map_a, big, g->batch, g->hb, g->wb, g->cb, g->stride, box, p.kc * 2)) return rc;
+  if (int rc = encode_w_map3(&p.map_b, w_down, 25, g->cs, g->cb, g->cb, p.kc, p.bn, p.kc * 2)) return rc;
+  p.num_n_tiles = (g->cs + p.bn - 1) / p.bn;
+  return launch(p, dim3(pt.tiles, p.num_n_tiles, 1), stream);
+}
+
+extern "C" int dm_conv_up(const dm_conv_geom* g, const void* small, const void* w_up, const float* bias, void* out_big,
+                          int out_f32, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (int rc = check_geom(g, "dm_conv_up")) return rc;
+  DM_REQUIRE(g->cs % 32 == 0, "dm_conv_up: cs %d must be a multiple of 32", g->cs);
+  const int cb_pad = std::max(16, (g->cb + 15) / 16 * 16);
+  PixTile pt;
+  DM_REQUIRE(make_pix_tile(128, g->batch, g->hs, g->ws, &pt), "dm_conv_up: unsupported grid %dx%d", g->hs, g->ws);
+  GemmParams p;
+  init_params(p);
+  p.mode = MODE_FWD;
+  p.kc = (g->cs % 64 == 0) ? 64 : 32;
+  p.bn = pick_bn(cb_pad, env_int("DM_BN_CAP", 128));
+  p.cpt = g->cs / p.kc;
+  int nphase = 0, nt = 0;
+  if (g->stride == 1) {
+    p.phase_tap_start[0] = 0;
+    for (int kh = 0; kh < 5; ++kh)
+      for (int kw = 0; kw < 5; ++kw) {
+        Tap& t = p.taps[nt++];
+        t.dh = static_cast<int8_t>(2 - kh);
+        t.dw = static_cast<int8_t>(2 - kw);
+        t.wt = static_cast<uint8_t>(kh * 5 + kw);
+      }
+    p.phase_tap_start[1] = nt;
+    p.phase_out_off[0] = 0;
+    nphase = 1;
+    p.os_w = g->cb; p.os_h = (long long)g->wb * g->cb;
+  } else {
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw) {
+        p.phase_tap_start[nphase] = nt;
+        for (int kh = ph; kh < 5; kh += 2)
+          for (int kw = pw; kw < 5; kw += 2) {
+            Tap& t = p.taps[nt++];
+            t.dh = static_cast<int8_t>((ph + 2 - kh) / 2);
+            t.dw = static_cast<int8_t>((pw + 2 - kw) / 2);
+            t.wt = static_cast<uint8_t>(kh * 5 + kw);
+          }
+        p.phase_out_off[nphase] = ((long long)ph * g->wb + pw) * g->cb;
+        ++nphase;
+      }
+    p.phase_tap_start[nphase] = nt;
+    p.os_w = 2ll * g->cb; p.os_h = 2ll * g->wb * g->cb;
+  }
+  p.os_n = (long long)g->hb * g->wb * g->cb; p.os_col = 1;
+  p.tw_step = 0; p.tpi = pt.tpi; p.th_step = pt.th_step; p.tn_step = pt.tn_step;
+  p.bw = pt.bw; p.bh = pt.bh;
+  p.out = out_big; p.bias = bias; p.out_f32 = out_f32; p.out_atomic = 0;
+  p.w_lim = g->ws; p.n_lim = g->batch; p.n_valid = g->cb;
+  uint32_t box[5] = {(uint32_t)p.kc, (uint32_t)pt.bw, 1, (uint32_t)pt.bh, (uint32_t)pt.bimg};
+  if (int rc = encode_act_map(&p.map_a, small, g->batch, g->hs, g->ws, g->cs, 1, box, p.kc * 2)) return rc;
+  if (int rc = encode_w_map3(&p.map_b, w_up, 25, cb_pad, g->cs, g->cs, p.kc, p.bn, p.kc * 2)) return rc;
+  p.num_n_tiles = (cb_pad + p.bn - 1) / p.bn;
+  return launch(p, dim3(pt.tiles, p.num_n_tiles, nphase), stream);
+}
+
+extern "C" int dm_conv_wgrad(const dm_conv_geom* g, const void* small, const void* big, float* dw, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (int rc = check_geom(g, "dm_conv_wgrad")) return rc;
+  DM_REQUIRE(g->cs % 128 == 0, "dm_conv_wgrad: cs %d must be a multiple of 128", g->cs);
+  const bool pair = (g->cb == 32 && g->stride == 2);
+  DM_REQUIRE(g->cb % 64 == 0 || pair, "dm_conv_wgrad: cb %d must be a multiple of 64 (or 32 with stride 2)", g->cb);
+  PixTile pt;
+  DM_REQUIRE(make_pix_tile(64, g->batch, g->hs, g->ws, &pt), "dm_conv_wgrad: unsupported grid %dx%d", g->hs, g->ws);
+  GemmParams p;
+  init_params(p);
+  p.mode = MODE_WGRAD;
+  p.a_mn = 1; p.b_mn = 1; p.kc = 64;
+  p.num_kb = pt.tiles;
+  p.tw_step = 0; p.tpi = pt.tpi; p.th_step = pt.th_step; p.tn_step = pt.tn_step;
+  p.out = dw; p.out_f32 = 1; p.out_atomic = 1;
+  p.os_m = (long long)g->cb * 25;
+  p.m_valid = g->cs;
+  int units = 0;
+  if (!pair) {
+    p.bn = g->cb >= 256 ? env_int("DM_BN_WGRAD", 256) : (g->cb >= 128 ? 128 : 64);
+    p.num_n_tiles = g->cb / p.bn;
+    down_taps(g, p.taps);
+    for (int t = 0; t < 25; ++t) {
+      p.taps[t].nvalid = static_cast<int16_t>(g->cb);
+      p.taps[t].out_off = t;
+    }
+    p.os_n1 = 25; p.os_n2 = 0; p.nmod = 1 << 30;
+    units = 25;
+  } else {
+    // cb == 32, stride 2: one 64-wide box covers both w-parities = filter columns (2aw+2, 2aw+3)
+    p.bn = 64;
+    p.num_n_tiles = 1;
+    for (int kh = 0; kh < 5; ++kh)
+      for (int aw = -1; aw <= 1; ++aw) {
+        Tap& t = p.taps[units++];
+        const int eh = kh - 2;
+        const int ah = (eh >= 0) ? eh / 2 : -((-eh + 1) / 2);
+        t.dc = 0;
+        t.dw = static_cast<int8_t>(aw);
+        t.dh = static_cast<int8_t>(ah);
+        t.dp = static_cast<int8_t>(eh - 2 * ah);
+        t.nvalid = static_cast<int16_t>(aw == 1 ? 32 : 64);
+        t.out_off = kh * 5 + 2 * aw + 2;
+      }
+    p.os_n1 = 25; p.os_n2 = 1; p.nmod = 32;
+  }
+  uint32_t boxa[5] = {64, (uint32_t)pt.bw, 1, (uint32_t)pt.bh, (uint32_t)pt.bimg};
+  if (int rc = encode_act_map(&p.map_a, small, g->batch, g->hs, g->ws, g->cs, 1, boxa, 128)) return rc;
+  if (int rc = encode_act_map(&p.map_b, big, g->batch, g->hb, g->wb, g->cb, g->stride, boxa, 128)) return rc;
+  // split K so that the grid covers the machine a few times over
+  const int base_ctas = (g->cs / 128) * p.num_n_tiles * units;
+  int splits = env_int("DM_WGRAD_SPLITS", 0);
+  if (splits <= 0) splits = std::max(1, std::min(p.num_kb, (2 * 148 + base_ctas - 1) / base_ctas));
+  splits = std::min(splits, p.num_kb);
+  p.num_splits = splits;
+  return launch(p, dim3(g->cs / 128, p.num_n_tiles * units, splits), stream);
+}

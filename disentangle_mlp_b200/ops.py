@@ -1,0 +1,241 @@
+"""Tensor-level wrappers around the C ABI (include/dm_b200.h).
+
+Every function takes CUDA torch tensors, passes raw device pointers plus the current stream to
+libdm_b200.so and returns torch tensors.  torch is used for memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import GEMM_NN, GEMM_NT, GEMM_TN, ConvGeom, GemmDesc
+
+ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t) -> int | None:
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "dm ops need contiguous CUDA tensors"
+    return t.data_ptr()
+
+
+def geom(batch, hs, ws, cs, cb, stride) -> ConvGeom:
+    return ConvGeom(batch, hs, ws, cs, hs * stride, ws * stride, cb, stride)
+
+
+# ------------------------------------------------------------------------------------------ GEMM-class
+def gemm(layout, a, b, m, n, k, *, out=None, out_dtype=F32, accumulate=False, bias=None, splits=1,
+         lda=None, ldb=None, ldd_m=None, ldd_n=1, m_store=0, n_store=0):
+    """D = op(A) op(B) with bf16 operands; see dm_gemm_desc."""
+    assert a.dtype == BF16 and b.dtype == BF16
+    if out is None:
+        out = (torch.zeros if accumulate else torch.empty)((m_store or m, n_store or n), dtype=out_dtype,
+                                                            device=a.device)
+    if lda is None:
+        lda = a.stride(0)
+    if ldb is None:
+        ldb = b.stride(0)
+    if ldd_m is None:
+        ldd_m = out.stride(0) if out.dim() >= 2 else 1
+    d = GemmDesc(layout, m, n, k, _p(a), lda, _p(b), ldb, _p(out), ldd_m, ldd_n, int(out.dtype == F32),
+                 int(accumulate), _p(bias), m_store, n_store, splits)
+    _lib.check(_lib.load().dm_gemm_bf16(C.byref(d), _stream()), "dm_gemm_bf16")
+    return out
+
+
+def conv_down(g: ConvGeom, big, w_down, bias=None, out=None):
+    if out is None:
+        out = torch.empty((g.batch, g.hs, g.ws, g.cs), dtype=BF16, device=big.device)
+    _lib.check(_lib.load().dm_conv_down(C.byref(g), _p(big), _p(w_down), _p(bias), _p(out), _stream()),
+               "dm_conv_down")
+    return out
+
+
+def conv_up(g: ConvGeom, small, w_up, bias=None, out=None, out_f32=False):
+    if out is None:
+        out = torch.empty((g.batch, g.hb, g.wb, g.cb), dtype=F32 if out_f32 else BF16, device=small.device)
+    _lib.check(_lib.load().dm_conv_up(C.byref(g), _p(small), _p(w_up), _p(bias), _p(out), int(out.dtype == F32),
+                                      _stream()), "dm_conv_up")
+    return out
+
+
+def conv_wgrad(g: ConvGeom, small, big, dw):
+    """dw[cs][cb][5][5] (fp32) += small^T * shifted(big)"""
+    assert dw.dtype == F32
+    _lib.check(_lib.load().dm_conv_wgrad(C.byref(g), _p(small), _p(big), _p(dw), _stream()), "dm_conv_wgrad")
+    return dw
+
+
+def last_plan():
+    grid = (C.c_int * 3)()
+    smem, stages = C.c_int(), C.c_int()
+    _lib.load().dm_debug_last_plan(grid, C.byref(smem), C.byref(stages))
+    return tuple(grid), smem.value, stages.value
+
+
+def pack_conv_weights(w, cs, cb, want_down=True, want_up=True, want_col=False):
+    """fp32 [cs][cb][5][5] -> (w_down [25][cs][cb], w_up [25][cb_pad][cs], w_col [cs][128]) bf16"""
+    dev = w.device
+    cb_pad = max(16, (cb + 15) // 16 * 16)
+    w_down = torch.empty((25, cs, cb), dtype=BF16, device=dev) if want_down else None
+    w_up = torch.empty((25, cb_pad, cs), dtype=BF16, device=dev) if want_up else None
+    w_col = torch.empty((cs, 128), dtype=BF16, device=dev) if want_col else None
+    _lib.check(_lib.load().dm_pack_conv_weights(_p(w), cs, cb, _p(w_down), _p(w_up), _p(w_col), _stream()),
+               "dm_pack_conv_weights")
+    return w_down, w_up, w_col
+
+
+# ------------------------------------------------------------------------------------------ HBM-bound
+def bn_stats(y, rows, c, sums=None):
+    if sums is None:
+        sums = torch.empty((2, c), dtype=F32, device=y.device)
+    _lib.check(_lib.load().dm_bn_stats(_p(y), int(y.dtype == F32), rows, c, _p(sums), _stream()), "dm_bn_stats")
+    return sums
+
+
+def bn_finalize(sums, rows, c, gamma, beta, running_mean, running_var, nbt, momentum=0.1, eps=1e-5):
+    scale_shift = torch.empty((2, c), dtype=F32, device=sums.device)
+    mean_invstd = torch.empty((2, c), dtype=F32, device=sums.device)
+    _lib.check(_lib.load().dm_bn_finalize(_p(sums), rows, c, _p(gamma), _p(beta), _p(running_mean), _p(running_var),
+                                          _p(nbt), momentum, eps, _p(scale_shift), _p(mean_invstd), _stream()),
+               "dm_bn_finalize")
+    return scale_shift, mean_invstd
+
+
+def bn_apply_act(y, rows, c, scale_shift, act, slope=0.2, out=None):
+    if out is None:
+        out = torch.empty(y.shape, dtype=BF16, device=y.device)
+    _lib.check(_lib.load().dm_bn_apply_act(_p(y), int(y.dtype == F32), rows, c, _p(scale_shift), act, slope, _p(out),
+                                           _stream()), "dm_bn_apply_act")
+    return out
+
+
+def bn_backward(dout, y, rows, c, scale_shift, mean_invstd, act, slope=0.2, dgamma=None, dbeta=None):
+    assert dout.dtype == BF16
+    dy = torch.empty(y.shape, dtype=BF16, device=y.device)
+    sums = torch.empty((2, c), dtype=F32, device=y.device)
+    _lib.check(_lib.load().dm_bn_backward(_p(dout), _p(y), int(y.dtype == F32), rows, c, _p(scale_shift),
+                                          _p(mean_invstd), act, slope, _p(sums), _p(dy), _p(dgamma), _p(dbeta),
+                                          _stream()), "dm_bn_backward")
+    return dy, sums
+
+
+def bias_act(acc, rows, c, bias, act, slope=0.2, want_f32=True, want_bf16=True):
+    out_f32 = torch.empty((rows, c), dtype=F32, device=acc.device) if want_f32 else None
+    out_bf16 = torch.empty((rows, c), dtype=BF16, device=acc.device) if want_bf16 else None
+    _lib.check(_lib.load().dm_bias_act(_p(acc), rows, c, _p(bias), act, slope, _p(out_f32), _p(out_bf16), _stream()),
+               "dm_bias_act")
+    return out_f32, out_bf16
+
+
+def act_backward(dout, out, rows, c, act, slope, colsum):
+    dpre = torch.empty((rows, c), dtype=BF16, device=dout.device)
+    _lib.check(_lib.load().dm_act_backward(_p(dout), _p(out), rows, c, act, slope, _p(dpre), _p(colsum), _stream()),
+               "dm_act_backward")
+    return dpre
+
+
+def colsum(x, rows, c, out):
+    _lib.check(_lib.load().dm_colsum(_p(x), int(x.dtype == F32), rows, c, _p(out), _stream()), "dm_colsum")
+    return out
+
+
+def im2col3(x_nchw, stride, out=None):
+    b, ch, h, w = x_nchw.shape
+    assert ch == 3 and x_nchw.dtype == F32
+    if out is None:
+        out = torch.empty((b * (h // stride) * (w // stride), 128), dtype=BF16, device=x_nchw.device)
+    _lib.check(_lib.load().dm_im2col3(_p(x_nchw), b, h, w, stride, _p(out), _stream()), "dm_im2col3")
+    return out
+
+
+def nhwc3_to_nchw(src, batch, h, w, apply_tanh):
+    dst = torch.empty((batch, 3, h, w), dtype=F32, device=src.device)
+    _lib.check(_lib.load().dm_nhwc3_to_nchw(_p(src), batch, h * w, int(apply_tanh), _p(dst), _stream()),
+               "dm_nhwc3_to_nchw")
+    return dst
+
+
+def tanh_backward(dout, out, bias_grad=None):
+    b, ch, h, w = out.shape
+    dy = torch.empty_like(out)
+    _lib.check(_lib.load().dm_tanh_backward(_p(dout), _p(out), b, h * w, _p(dy), _p(bias_grad), _stream()),
+               "dm_tanh_backward")
+    return dy
+
+
+def transpose(src, batch, rows, cols):
+    dst = torch.empty((batch, cols, rows), dtype=BF16, device=src.device)
+    _lib.check(_lib.load().dm_transpose_bf16(_p(src), batch, rows, cols, _p(dst), _stream()), "dm_transpose_bf16")
+    return dst
+
+
+def cast_bf16(src, dst=None):
+    if dst is None:
+        dst = torch.empty(src.shape, dtype=BF16, device=src.device)
+    _lib.check(_lib.load().dm_cast_bf16(_p(src), src.numel(), _p(dst), _stream()), "dm_cast_bf16")
+    return dst
+
+
+def reparam_forward(mu, logvar, eps):
+    z = torch.empty_like(mu)
+    zb = torch.empty(mu.shape, dtype=BF16, device=mu.device)
+    _lib.check(_lib.load().dm_reparam_forward(_p(mu), _p(logvar), _p(eps), mu.numel(), _p(z), _p(zb), _stream()),
+               "dm_reparam_forward")
+    return z, zb
+
+
+def reparam_backward(dz, logvar, eps, dmu_ext=None, dlogvar_ext=None):
+    dmu = torch.empty(logvar.shape, dtype=BF16, device=logvar.device)
+    dlv = torch.empty(logvar.shape, dtype=BF16, device=logvar.device)
+    dmu32 = torch.empty_like(logvar)
+    dlv32 = torch.empty_like(logvar)
+    _lib.check(_lib.load().dm_reparam_backward(_p(dz), _p(logvar), _p(eps), _p(dmu_ext), _p(dlogvar_ext),
+                                               logvar.numel(), _p(dmu), _p(dlv), _p(dmu32), _p(dlv32), _stream()),
+               "dm_reparam_backward")
+    return dmu, dlv, dmu32, dlv32
+
+
+def head_forward(feat, w, b):
+    rows, k = feat.shape
+    prob = torch.empty((rows,), dtype=F32, device=feat.device)
+    _lib.check(_lib.load().dm_head_forward(_p(feat), rows, k, _p(w), _p(b), _p(prob), _stream()), "dm_head_forward")
+    return prob
+
+
+def head_backward(dprob, prob, feat, dfeat_ext, w, dw, db):
+    rows, k = feat.shape
+    dfeat = torch.empty_like(feat)
+    _lib.check(_lib.load().dm_head_backward(_p(dprob), _p(prob), _p(feat), _p(dfeat_ext), rows, k, _p(w), _p(dfeat),
+                                            _p(dw), _p(db), _stream()), "dm_head_backward")
+    return dfeat
+
+
+def mse_sum(a, b, loss, wloss=1.0, grad=None, wgrad=1.0, accumulate=False):
+    _lib.check(_lib.load().dm_mse_sum(_p(a), _p(b), a.numel(), wloss, _p(loss), wgrad, int(accumulate), _p(grad),
+                                      _stream()), "dm_mse_sum")
+
+
+def kl(mu, logvar, loss, w=1.0, dmu=None, dlogvar=None, accumulate=False):
+    _lib.check(_lib.load().dm_kl(_p(mu), _p(logvar), mu.numel(), w, _p(loss), int(accumulate), _p(dmu), _p(dlogvar),
+                                 _stream()), "dm_kl")
+
+
+def bce_const(p, target, loss, w=1.0, n_total=None, dprob=None, accumulate=False, stat=None):
+    n = p.numel()
+    _lib.check(_lib.load().dm_bce_const(_p(p), n, float(n_total or n), float(target), w, _p(loss), int(accumulate),
+                                        _p(dprob), _p(stat), _stream()), "dm_bce_const")
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0, shadow=None):
+    _lib.check(_lib.load().dm_adam_step(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, step,
+                                        grad_scale, _p(shadow), _stream()), "dm_adam_step")

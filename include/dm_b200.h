@@ -1,0 +1,165 @@
+/*
+ * dm_b200.h — C ABI of libdm_b200.so: the B200 (sm_100a) kernels behind the VAE / GAN / beta-VAE-GAN
+ * training step of RicoFio/disentangle_mlp.
+ *
+ * The reference has no native layer: its hot path calls torch.nn library ops.  Each entry point below
+ * replaces the ATen op(s) that a line of the reference invokes (cited as file:line, relative to the
+ * reference checkout).  All pointers are DEVICE pointers borrowed for the duration of the call; every
+ * function enqueues work on `stream` (a cudaStream_t passed as void*) and returns without synchronising.
+ * Return value: 0 on success, non-zero on argument / launch error (see dm_last_error()).
+ *
+ * Data conventions
+ *   - activations between layers: bf16, NHWC ("pixel-major": [batch, h, w, c]); matrices row-major
+ *   - parameters / gradients / optimizer state: fp32 in the reference's own layouts
+ *       Conv2d.weight [Co,Ci,5,5], ConvTranspose2d.weight [Ci,Co,5,5], Linear.weight [out,in]
+ *   - "small"/"big": the low-/high-resolution side of a 5x5, pad-2 (transposed) convolution:
+ *       Conv2d:          big = input,  small = output, weight [Cs=Co][Cb=Ci][5][5]
+ *       ConvTranspose2d: small = input, big = output,  weight [Cs=Ci][Cb=Co][5][5]
+ *     so one weight layout [Cs][Cb][25] serves both (models/model.py:449-457, 495-507, 388-398).
+ */
+#ifndef DM_B200_H_
+#define DM_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* dm_last_error(void);
+int dm_version(void);
+/* Number of kernels launched through this library since load (bench.py's gpu_launches). */
+long long dm_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * GEMM-class ops (tcgen05 + TMEM + TMA).  bf16 operands, fp32 accumulation.
+ * ---------------------------------------------------------------------------------------------- */
+
+enum { DM_GEMM_NT = 0, /* D[m,n] = sum_k A[m,k] B[n,k]   (nn.Linear forward,  model.py:460-471,490,402-408) */
+       DM_GEMM_NN = 1, /* D[m,n] = sum_k A[m,k] B[k,n]   (nn.Linear backward wrt input)                     */
+       DM_GEMM_TN = 2  /* D[m,n] = sum_k A[k,m] B[k,n]   (nn.Linear backward wrt weight)                    */ };
+
+typedef struct dm_gemm_desc {
+  int layout;        /* DM_GEMM_* */
+  int m, n, k;
+  const void* a;     /* bf16 */
+  long long lda;     /* leading dimension (elements) of A as stored */
+  const void* b;     /* bf16 */
+  long long ldb;
+  void* d;           /* fp32 or bf16 */
+  long long ldd_m;   /* element stride of D along m */
+  long long ldd_n;   /* element stride of D along n (1 = row-major) */
+  int d_f32;         /* 1: D is fp32, 0: bf16 */
+  int accumulate;    /* 1: atomically add into D (fp32 only); required when splits > 1 */
+  const float* bias; /* optional per-n bias (NT/NN only), added once */
+  int m_store;       /* rows of D actually stored (0 = m) */
+  int n_store;       /* columns of D actually stored (0 = n) */
+  int splits;        /* split-K factor (>= 1) */
+} dm_gemm_desc;
+
+int dm_gemm_bf16(const dm_gemm_desc* g, void* stream);
+
+typedef struct dm_conv_geom {
+  int batch;
+  int hs, ws, cs; /* small side */
+  int hb, wb, cb; /* big side; hb = hs*stride, wb = ws*stride */
+  int stride;     /* 1 or 2 */
+} dm_conv_geom;
+
+/* small[b,hs,ws,cs] = sum_{kh,kw,cb} big[b, s*h+kh-2, s*w+kw-2, cb] * W[cs][cb][kh][kw]  (+ bias[cs])
+ * = nn.Conv2d forward (model.py:449-457, 388-398) and nn.ConvTranspose2d input-gradient.
+ * w_down: bf16 [25][cs][cb] (dm_pack_conv_weights).  Requires cb % 32 == 0, cs % 16 == 0. */
+int dm_conv_down(const dm_conv_geom* g, const void* big, const void* w_down, const float* bias,
+                 void* out_small, void* stream);
+
+/* big[b, s*h+kh-2, s*w+kw-2, cb] += small[b,h,w,cs] * W[cs][cb][kh][kw]   (+ bias[cb])
+ * = nn.ConvTranspose2d forward with output_padding = stride-1 (model.py:495-507, 555-563) and
+ *   nn.Conv2d input-gradient.  w_up: bf16 [25][cb_pad][cs], cb_pad = max(cb,16) rounded up to 16.
+ * out_big: bf16 NHWC [b,hb,wb,cb] or, when out_f32, fp32 NHWC (used for the 3-channel image side). */
+int dm_conv_up(const dm_conv_geom* g, const void* small, const void* w_up, const float* bias,
+               void* out_big, int out_f32, void* stream);
+
+/* dw[cs][cb][kh][kw] += sum_{b,h,w} small[b,h,w,cs] * big[b, s*h+kh-2, s*w+kw-2, cb]   (fp32, atomic)
+ * = weight gradient of nn.Conv2d (small = grad_output, big = input) and of nn.ConvTranspose2d
+ *   (small = input, big = grad_output).  Requires cs % 128 == 0 and cb % 64 == 0, or cb == 32 with stride 2. */
+int dm_conv_wgrad(const dm_conv_geom* g, const void* small, const void* big, float* dw, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * HBM-bound ops.  "rows x c" = channel-innermost matrix view of an NHWC activation (rows = b*h*w) or of a
+ * Linear output (rows = batch).  act: 0 none, 1 ReLU, 2 LeakyReLU(slope).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* nn.BatchNorm1d/2d, training mode (model.py:451,454,457,462,468,492,496,500,504,390,393,396,399):
+ *   dm_bn_stats    : sums[0][c] = sum_r y, sums[1][c] = sum_r y^2   (sums is zeroed inside)
+ *   dm_bn_finalize : scale = gamma*invstd, shift = beta - mean*scale; running stats updated with
+ *                    `momentum` and the unbiased variance; num_batches_tracked += 1 (may be NULL)
+ *   dm_bn_apply_act: out = act(y*scale + shift)   (the ReLU / LeakyReLU(0.2) that follows every BN)
+ *   dm_bn_backward : dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)), dz = dout*act'(z);
+ *                    dgamma += sum dz*xhat, dbeta += sum dz (skipped when NULL); sums = [2][c] scratch */
+int dm_bn_stats(const void* y, int y_f32, long long rows, int c, float* sums, void* stream);
+int dm_bn_finalize(const float* sums, long long rows, int c, const float* gamma, const float* beta,
+                   float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
+                   float eps, float* scale_shift, float* mean_invstd, void* stream);
+int dm_bn_apply_act(const void* y, int y_f32, long long rows, int c, const float* scale_shift, int act,
+                    float slope, void* out_bf16, void* stream);
+int dm_bn_backward(const void* dout_bf16, const void* y, int y_f32, long long rows, int c,
+                   const float* scale_shift, const float* mean_invstd, int act, float slope, float* sums,
+                   void* dy_bf16, float* dgamma, float* dbeta, void* stream);
+
+/* out = act(acc + bias) after a split-K Linear (model.py:402-404); fp32 and/or bf16 outputs (NULL = skip). */
+int dm_bias_act(const float* acc, long long rows, int c, const float* bias, int act, float slope,
+                float* out_f32, void* out_bf16, void* stream);
+/* dpre = dout * act'(out) as bf16; colsum[c] += sum_r dpre (the Linear bias gradient). */
+int dm_act_backward(const float* dout, const float* out, long long rows, int c, int act, float slope,
+                    void* dpre_bf16, float* colsum, void* stream);
+/* colsum[c] += sum_r x[r][c] */
+int dm_colsum(const void* x, int x_f32, long long rows, int c, float* colsum, void* stream);
+
+/* fp32 NCHW [b,3,h,w] image -> bf16 im2col matrix [b*(h/s)*(w/s), 128], column c*25+kh*5+kw (75 valid):
+ * the A operand of the two 3-channel convolutions (model.py:449, 389) and of deconv4's input-gradient. */
+int dm_im2col3(const float* x_nchw, int batch, int h, int w, int stride, void* col_bf16, void* stream);
+/* fp32 NHWC(3) -> fp32 NCHW, optionally through nn.Tanh (model.py:509,565). */
+int dm_nhwc3_to_nchw(const float* src, long long batch, int hw, int apply_tanh, float* dst, void* stream);
+/* dy = dout*(1-out^2) (fp32 NCHW); bias_grad[3] += per-channel sums of dy (deconv4.bias gradient). */
+int dm_tanh_backward(const float* dout, const float* out, long long batch, int hw, float* dy,
+                     float* bias_grad, void* stream);
+/* bf16 [batch][rows][cols] -> [batch][cols][rows]: NHWC <-> the NCHW flatten order that the 16384-wide
+ * Linear layers are defined on (model.py:516-517, 540-543, 412-413). */
+int dm_transpose_bf16(const void* src, int batch, int rows, int cols, void* dst, void* stream);
+/* fp32 weight [cs][cb][5][5] -> bf16 operand packs: w_down [25][cs][cb], w_up [25][cb_pad][cs],
+ * w_col [cs][128] (only when cb*25 <= 128).  Any output may be NULL. */
+int dm_pack_conv_weights(const float* w, int cs, int cb, void* w_down, void* w_up, void* w_col, void* stream);
+int dm_cast_bf16(const float* src, long long n, void* dst, void* stream);
+
+/* z = mu + eps*exp(0.5*logvar) (model.py:532-535) and its backward (+ externally supplied dmu/dlogvar). */
+int dm_reparam_forward(const float* mu, const float* logvar, const float* eps, long long n, float* z_f32,
+                       void* z_bf16, void* stream);
+int dm_reparam_backward(const float* dz, const float* logvar, const float* eps, const float* dmu_ext,
+                        const float* dlogvar_ext, long long n, void* dmu_bf16, void* dlogvar_bf16,
+                        float* dmu_f32, float* dlogvar_f32, void* stream);
+
+/* Discriminator head Linear(k,1)+Sigmoid (model.py:406-408) and its backward. */
+int dm_head_forward(const float* feat, int rows, int k, const float* w, const float* b, float* prob,
+                    void* stream);
+int dm_head_backward(const float* dprob, const float* prob, const float* feat, const float* dfeat_ext,
+                     int rows, int k, const float* w, float* dfeat, float* dw, float* db, void* stream);
+
+/* Loss reductions (experiments/new_betavaegan.py:53,64-75; new_vae.py:39-48).  `loss` is a device scalar
+ * that is atomically accumulated; gradients are written (or accumulated) when the pointer is non-NULL. */
+int dm_mse_sum(const float* a, const float* b, long long n, float wloss, float* loss, float wgrad,
+               int grad_accumulate, float* grad, void* stream);
+int dm_kl(const float* mu, const float* logvar, long long n, float w, float* loss, int grad_accumulate,
+          float* dmu, float* dlogvar, void* stream);
+int dm_bce_const(const float* p, int n, float n_total, float target, float w, float* loss,
+                 int grad_accumulate, float* dprob, float* stat, void* stream);
+
+/* torch.optim.Adam step on a flat fp32 buffer (new_betavaegan.py:49-50,123,164,193); `step` is the
+ * 1-based step count; g is multiplied by grad_scale first; shadow_bf16 (may be NULL) receives bf16(p). */
+int dm_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                 float beta2, float eps, int step, float grad_scale, void* shadow_bf16, void* stream);
+
+/* Test hook: direct access to the tile plan of a GEMM-class call (tile counts, smem bytes). */
+int dm_debug_last_plan(int* grid_xyz, int* smem_bytes, int* stages);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DM_B200_H_ */
