@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""Benchmark of the VAE-GAN / beta-VAE-GAN training step (BASELINE.json metric: train img/s per step, 64x64).
+
+    python bench.py --gpus 1 --steps K --warmup W                      # this repo's CUDA path (default)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...                               # the reference's CPU step (oracle port)
+
+N=1 workload = BASELINE.json configs[1]: VAE-GAN baseline (beta=1, Dis_l feature loss), 64x64, batch 64 on one
+B200.  N>1: the same per-GPU batch on every rank (weak scaling; configs[2] is 64/GPU x 8), gradients
+SUM-allreduced over NCCL before each of the three Adam steps.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GFLOP_PER_IMG = {"betavaegan": 20.01, "gan": 9.95, "vae": 3.64}  # algorithmic minimum, SURVEY.md §8d
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"bf16_sustained": d.get("bf16_tflops_sustained"), "bf16_burst": d.get("bf16_tflops"),
+                "hbm_gbs": d.get("hbm_gbs"), "src": "measured"}
+    return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm_gbs": 6650.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_oracle_step(workload, batch, threads):
+    """The reference's CPU training step (oracle port: stock torch.nn fp32 on the host cores)."""
+    import numpy as np
+    import torch
+
+    from oracle import nets, steps
+
+    torch.set_num_threads(threads)
+    torch.manual_seed(999)
+    np.random.seed(999)
+    opt = steps.make_opt()
+    x = steps.synthetic_batch(batch, 1234)
+    if workload == "betavaegan":
+        eg, d = nets.VAE(opt), nets.Discriminator_celeba(opt)
+        eg.apply(nets.weights_init)
+        d.apply(nets.weights_init)
+        oeg, od = torch.optim.Adam(eg.parameters(), lr=1e-3), torch.optim.Adam(d.parameters(), lr=1e-3)
+
+        def step():
+            real, fake = steps.draw_labels()
+            return steps.betavaegan_step(eg, d, oeg, od, x, 1.0, real, fake)
+    elif workload == "gan":
+        g, d = nets.Generator_celeba(opt), nets.Discriminator_celeba(opt)
+        g.apply(nets.weights_init)
+        d.apply(nets.weights_init)
+        og, od = torch.optim.Adam(g.parameters(), lr=3e-4), torch.optim.Adam(d.parameters(), lr=3e-4)
+
+        def step():
+            real, fake = steps.draw_labels()
+            return steps.gan_step(g, d, og, od, x, real, fake)
+    else:
+        m = nets.VAE(opt)
+        m.apply(nets.weights_init)
+        o = torch.optim.Adam(m.parameters(), lr=3e-4)
+
+        def step():
+            return steps.vae_step(m, o, x)
+    return step
+
+
+def time_cpu(workload, batch, threads, warmup, steps_n):
+    step = build_oracle_step(workload, batch, threads)
+    for _ in range(warmup):
+        step()
+    ts = []
+    for _ in range(steps_n):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    ts.sort()
+    med = ts[len(ts) // 2]
+    return batch / med, med
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the step on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    # bounded sample: per-step batch sized so that (warmup + steps) steps end within a few minutes
+    total = args.steps + args.warmup
+    batch = 64 if total <= 12 else (16 if total <= 60 else 8)
+    t0 = time.perf_counter()
+    ips, med = time_cpu(args.workload, batch, threads, args.warmup, args.steps)
+    line = {
+        "impl": "reference", "metric": "train_img_per_s", "value": round(ips, 3), "unit": "img/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(med * 1e3, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 64),
+        "cpu_baseline": {"value": round(ips, 3), "unit": "img/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} timed steps (median) of the same step at batch {batch} on the host "
+                                   f"cores, oracle/steps.py restating experiments/new_betavaegan.py:93-193; "
+                                   f"wall {time.perf_counter() - t0:.0f}s"},
+        "e2e": {"value": round(ips, 3), "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, per_gpu_batch):
+    names = {"betavaegan": f"VAE-GAN baseline (Larsen, Dis_l loss; experiments/new_betavaegan.py step, beta={args.beta:g})",
+             "gan": "GAN (experiments/new_gan.py step)", "vae": "VAE (experiments/new_vae.py step)"}
+    return {"workload": names[args.workload] + f", 64x64x3, batch {per_gpu_batch}/GPU",
+            "per_gpu_batch": per_gpu_batch, "global_batch": per_gpu_batch * args.gpus, "beta": args.beta,
+            "parallelism": f"dp{args.gpus}",
+            "l2": "no explicit flush: every step streams ~2 GB of parameters + Adam state, far beyond the 126 MB L2",
+            "gflop_per_img_algorithmic": GFLOP_PER_IMG[args.workload]}
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from disentangle_mlp_b200 import _lib, ops
+    from disentangle_mlp_b200 import model as dm
+    from disentangle_mlp_b200 import trainer as tr
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    b = args.batch
+    torch.manual_seed(999)
+    np.random.seed(999)  # identical label stream on every rank
+    opt = dm.default_opt()
+    if args.workload == "betavaegan":
+        eg, d = dm.VAE(opt), dm.Discriminator_celeba(opt)
+        eg.apply(dm.weights_init)
+        d.apply(dm.weights_init)
+        T = tr.BetaVAEGANTrainer(eg.to(dev), d.to(dev), beta=args.beta, lr=1e-3)
+        key = "recon_enc"
+    elif args.workload == "gan":
+        g, d = dm.Generator_celeba(opt), dm.Discriminator_celeba(opt)
+        g.apply(dm.weights_init)
+        d.apply(dm.weights_init)
+        T = tr.GANTrainer(g.to(dev), d.to(dev), lr=3e-4)
+        key = "errG"
+    else:
+        m = dm.VAE(opt)
+        m.apply(dm.weights_init)
+        T = tr.VAETrainer(m.to(dev), lr=3e-4)
+        key = "loss"
+
+    # synthetic CelebA-shaped inputs, U[-1,1]; a pool of distinct batches, per-rank seed
+    npool = 8
+    gen = torch.Generator().manual_seed(1234 + rank)
+    host_pool = [(torch.rand(b, 3, 64, 64, generator=gen) * 2 - 1).pin_memory() for _ in range(npool)]
+    dev_pool = [h.to(dev) for h in host_pool]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, nsteps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(nsteps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    def step_resident(i):
+        T.step(dev_pool[i % npool])
+
+    sink = []
+
+    def step_e2e(i):
+        x = host_pool[i % npool].to(dev, non_blocking=True)  # H2D from pinned memory inside the timed region
+        m = T.step(x)
+        sink.append(float(m[key]))  # D2H read of the step's loss
+
+    for i in range(max(3, args.warmup)):
+        step_resident(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # roofline pass: same workload, per-launch CUDA events around every GEMM-class kernel
+    ops.profile_enable(True)
+    ops.profile_read()
+    t_prof = timed(step_resident, args.steps)
+    gemm_ms, gemm_flops, gemm_n = ops.profile_read()
+    ops.profile_enable(False)
+
+    if rank == 0:
+        peaks = load_peaks()
+        gbatch = b * world
+        ips = gbatch * args.steps / (ms / 1e3)
+        ips_e2e = gbatch * args.steps / (ms_e2e / 1e3)
+        ach = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+        peak = peaks["bf16_sustained"]
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            cb = 64
+            t0 = time.perf_counter()
+            cips, cmed = time_cpu(args.workload, cb, threads, 1, 3)
+            cpu = {"value": round(cips, 3), "unit": "img/s", "cores": threads, "kind": "port",
+                   "sample": f"3 timed steps (median {cmed:.2f}s) + 1 warm-up of the same step at batch {cb}, "
+                             f"oracle/steps.py on the host cores, {time.perf_counter() - t0:.0f}s wall"}
+        line = {
+            "metric": "train_img_per_s", "value": round(ips, 2), "unit": "img/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms / args.steps, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(args, b),
+            "clocks": clocks,
+            "e2e": {"value": round(ips_e2e, 2), "unit": "img/s", "h2d_bytes_per_step": b * 3 * 64 * 64 * 4,
+                    "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 4)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "dm_tapgemm_kernel (all GEMM-class launches of the step)",
+                         "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s",
+                         "frac": round(ach / peak, 4) if peak else None, "traffic": None,
+                         "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['src']})",
+                         "launches_per_step": gemm_n / args.steps, "gemm_ms_per_step": round(gemm_ms / args.steps, 4),
+                         "gemm_share_of_step": round(gemm_ms / t_prof, 4),
+                         "step_frac_of_peak": round(ips / world * GFLOP_PER_IMG[args.workload] / 1e3 / peak, 4)},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="betavaegan", choices=["betavaegan", "gan", "vae"])
+    ap.add_argument("--beta", type=float, default=1.0)
+    ap.add_argument("--batch", type=int, default=64, help="per-GPU batch")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

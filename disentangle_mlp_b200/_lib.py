@@ -19,7 +19,7 @@ class GemmDesc(C.Structure):
         ("a", c_void_p), ("lda", c_ll), ("b", c_void_p), ("ldb", c_ll),
         ("d", c_void_p), ("ldd_m", c_ll), ("ldd_n", c_ll),
         ("d_f32", c_int), ("accumulate", c_int), ("bias", c_void_p),
-        ("m_store", c_int), ("n_store", c_int), ("splits", c_int),
+        ("m_store", c_int), ("n_store", c_int), ("splits", c_int), ("k_alg", c_int),
     ]
 
 
@@ -36,6 +36,8 @@ _SIGS = {
     "dm_conv_down": [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "dm_conv_up": [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "dm_conv_wgrad": [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_void_p],
+    "dm_profile_enable": [c_int],
+    "dm_profile_read": [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(c_ll)],
     "dm_debug_last_plan": [C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int)],
     "dm_bn_stats": [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p],
     "dm_bn_finalize": [c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float,
@@ -94,10 +96,20 @@ def load():
     return lib
 
 
+_DEBUG_SYNC = bool(os.environ.get("DM_DEBUG_SYNC"))
+
+
 def check(rc: int, what: str) -> None:
     if rc != 0:
         msg = load().dm_last_error().decode(errors="replace")
         raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+    if _DEBUG_SYNC:  # debugging aid: surface asynchronous faults at the call that caused them
+        import torch
+
+        try:
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            raise RuntimeError(f"{what}: device fault after launch: {e}") from e
 
 
 def launch_count() -> int:

@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "../../include/dm_b200.h"
 #include "dm_common.h"
@@ -397,6 +398,17 @@ static int encode_w_map3(CUtensorMap* m, const void* ptr, long long t, long long
 static int g_last_grid[3] = {0, 0, 0};
 static int g_last_smem = 0, g_last_stages = 0;
 
+// Optional per-launch timing of the GEMM-class kernel (bench.py's roofline): CUDA event pairs around every
+// launch on the launching stream, read back (after a device sync) by dm_profile_read().
+struct ProfRec {
+  cudaEvent_t e0, e1;
+  double flops;
+};
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<ProfRec> g_prof_pool;
+
 static int env_int(const char* name, int dflt) {
   const char* s = getenv(name);
   return s ? atoi(s) : dflt;
@@ -408,7 +420,7 @@ static int pow2_cols(int n) {
   return c;
 }
 
-static int launch(GemmParams& p, dim3 grid, cudaStream_t stream) {
+static int launch(GemmParams& p, dim3 grid, cudaStream_t stream, double flops) {
   const int a_bytes = p.a_mn ? 2 * kAtomBytes : 128 * p.kc * 2;
   const int b_bytes = p.b_mn ? (p.bn >> 6) * kAtomBytes : p.bn * p.kc * 2;
   const int stage_bytes = a_bytes + b_bytes;
@@ -426,7 +438,29 @@ static int launch(GemmParams& p, dim3 grid, cudaStream_t stream) {
   if (attr_err != cudaSuccess) return set_error((int)attr_err, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
   g_last_grid[0] = grid.x; g_last_grid[1] = grid.y; g_last_grid[2] = grid.z;
   g_last_smem = smem; g_last_stages = stages;
+  ProfRec rec;
+  bool prof = false;
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    prof = g_prof_on;
+    if (prof) {
+      if (!g_prof_pool.empty()) {
+        rec = g_prof_pool.back();
+        g_prof_pool.pop_back();
+      } else {
+        cudaEventCreate(&rec.e0);
+        cudaEventCreate(&rec.e1);
+      }
+      rec.flops = flops;
+    }
+  }
+  if (prof) cudaEventRecord(rec.e0, stream);
   dm_tapgemm_kernel<<<grid, kThreads, smem, stream>>>(p);
+  if (prof) {
+    cudaEventRecord(rec.e1, stream);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(rec);
+  }
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return check_launch("dm_tapgemm_kernel");
 }
@@ -480,6 +514,32 @@ static int pick_bn(int n, int cap) {
 }  // namespace dm
 
 using namespace dm;
+
+extern "C" int dm_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = on != 0;
+  return 0;
+}
+
+// Sum of per-launch durations (ms), algorithmic FLOPs and launch count of the GEMM-class kernel since the
+// last read; synchronises the device.  Any output may be NULL.
+extern "C" int dm_profile_read(double* total_ms, double* total_flops, long long* launches) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return set_error((int)e, "dm_profile_read: %s", cudaGetErrorString(e));
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  double ms = 0.0, fl = 0.0;
+  for (auto& r : g_prof) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) ms += t;
+    fl += r.flops;
+    g_prof_pool.push_back(r);
+  }
+  if (total_ms) *total_ms = ms;
+  if (total_flops) *total_flops = fl;
+  if (launches) *launches = static_cast<long long>(g_prof.size());
+  g_prof.clear();
+  return 0;
+}
 
 extern "C" int dm_debug_last_plan(int* grid_xyz, int* smem_bytes, int* stages) {
   if (grid_xyz) { grid_xyz[0] = g_last_grid[0]; grid_xyz[1] = g_last_grid[1]; grid_xyz[2] = g_last_grid[2]; }
@@ -559,7 +619,8 @@ extern "C" int dm_gemm_bf16(const dm_gemm_desc* g, void* stream_) {
   } else {
     return set_error(-1, "dm_gemm_bf16: unknown layout %d", g->layout);
   }
-  return launch(p, grid, stream);
+  const double k_alg = g->k_alg > 0 ? g->k_alg : g->k;
+  return launch(p, grid, stream, 2.0 * m_store * n_store * k_alg);
 }
 
 // ------------------------------------------------------------------------------------------ convolutions
@@ -619,7 +680,7 @@ extern "C" int dm_conv_down(const dm_conv_geom* g, const void* big, const void* 
   if (int rc = encode_act_map(&p.map_a, big, g->batch, g->hb, g->wb, g->cb, g->stride, box, p.kc * 2)) return rc;
   if (int rc = encode_w_map3(&p.map_b, w_down, 25, g->cs, g->cb, g->cb, p.kc, p.bn, p.kc * 2)) return rc;
   p.num_n_tiles = (g->cs + p.bn - 1) / p.bn;
-  return launch(p, dim3(pt.tiles, p.num_n_tiles, 1), stream);
+  return launch(p, dim3(pt.tiles, p.num_n_tiles, 1), stream, 50.0 * g->batch * g->hs * g->ws * g->cs * g->cb);
 }
 
 extern "C" int dm_conv_up(const dm_conv_geom* g, const void* small, const void* w_up, const float* bias, void* out_big,
@@ -676,7 +737,7 @@ extern "C" int dm_conv_up(const dm_conv_geom* g, const void* small, const void* 
   if (int rc = encode_act_map(&p.map_a, small, g->batch, g->hs, g->ws, g->cs, 1, box, p.kc * 2)) return rc;
   if (int rc = encode_w_map3(&p.map_b, w_up, 25, cb_pad, g->cs, g->cs, p.kc, p.bn, p.kc * 2)) return rc;
   p.num_n_tiles = (cb_pad + p.bn - 1) / p.bn;
-  return launch(p, dim3(pt.tiles, p.num_n_tiles, nphase), stream);
+  return launch(p, dim3(pt.tiles, p.num_n_tiles, nphase), stream, 50.0 * g->batch * g->hs * g->ws * g->cs * g->cb);
 }
 
 extern "C" int dm_conv_wgrad(const dm_conv_geom* g, const void* small, const void* big, float* dw, void* stream_) {
@@ -734,5 +795,6 @@ extern "C" int dm_conv_wgrad(const dm_conv_geom* g, const void* small, const voi
   if (splits <= 0) splits = std::max(1, std::min(p.num_kb, (2 * 148 + base_ctas - 1) / base_ctas));
   splits = std::min(splits, p.num_kb);
   p.num_splits = splits;
-  return launch(p, dim3(g->cs / 128, p.num_n_tiles * units, splits), stream);
+  return launch(p, dim3(g->cs / 128, p.num_n_tiles * units, splits), stream,
+                50.0 * g->batch * g->hs * g->ws * g->cs * g->cb);
 }

@@ -1,0 +1,357 @@
+"""Forward / backward schedules of the three networks as explicit sequences of libdm_b200 kernel calls.
+
+No autograd in here: each `*_forward` returns its outputs plus a `Saved` record, each `*_backward` consumes
+that record and ACCUMULATES parameter gradients into the fp32 tensors it is handed (zero them first for a
+fresh gradient).  model.py wraps these in torch.autograd.Function for the reference training loops;
+steps.py calls them directly for the fused steps.
+
+Layouts: activations bf16 NHWC; the 16384-wide Linear layers are defined on the NCHW flatten order
+(model.py:516-517, 540-543, 412-413), so one small bf16 transpose sits on either side of them.
+Parameters are addressed by their reference state_dict names.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from types import SimpleNamespace
+
+import torch
+
+from . import ops
+from .ops import ACT_LEAKY, ACT_RELU, BF16, F32, GEMM_NN, GEMM_NT, GEMM_TN
+
+BN_EPS, BN_MOMENTUM, LEAKY = 1e-5, 0.1, 0.2
+
+
+# ------------------------------------------------------------------------------------------ operand cache
+class OperandCache:
+    """bf16 GEMM operands derived from the fp32 master parameters; rebuilt when a parameter's version
+    counter or storage changes (optimizer step, load_state_dict, weights_init), or after invalidate()."""
+
+    def __init__(self):
+        self._c = {}
+        self.static = False  # True: never rebuild implicitly (CUDA-graph mode); refresh() does it in place
+
+    def get(self, key, param, builder):
+        ent = self._c.get(key)
+        ver = (param.data_ptr(), param._version)
+        if ent is not None and (self.static or ent[0] == ver):
+            return ent[1]
+        val = builder(param.detach())
+        self._c[key] = (ver, val)
+        return val
+
+    def invalidate(self):
+        self._c.clear()
+
+
+def _lin_w(cache, name, p):
+    """bf16 copy of a Linear weight: a view of the optimizer's bf16 shadow when there is one, else a cast."""
+    views = getattr(cache, "lin_views", None)
+    if views is not None:
+        return views[name + ".weight"]
+    return cache.get(("lin", name), p, lambda w: ops.cast_bf16(w.contiguous()))
+
+
+def _conv_pack(cache, name, p, cs, cb):
+    """(w_down [25][cs][cb], w_up [25][cb_pad][cs], w_col [cs][128] or None)"""
+    return cache.get(("conv", name), p, lambda w: ops.pack_conv_weights(w.contiguous(), cs, cb, True, True, cb * 25 <= 128))
+
+
+# ------------------------------------------------------------------------------------------ BatchNorm helper
+@dataclass
+class BNState:
+    y: torch.Tensor          # pre-normalisation tensor (bf16 or fp32), viewed as [rows, c]
+    rows: int
+    c: int
+    scale_shift: torch.Tensor
+    mean_invstd: torch.Tensor
+    act: int
+
+
+def bn_act_forward(y, rows, c, P, B, prefix, act, training=True):
+    """BatchNorm (batch statistics, running-stat update) + activation. P: params, B: buffers."""
+    gamma, beta = P[prefix + ".weight"], P[prefix + ".bias"]
+    rm, rv, nbt = B[prefix + ".running_mean"], B[prefix + ".running_var"], B[prefix + ".num_batches_tracked"]
+    if training:
+        sums = ops.bn_stats(y, rows, c)
+        ss, mi = ops.bn_finalize(sums, rows, c, gamma.detach(), beta.detach(), rm, rv, nbt, BN_MOMENTUM, BN_EPS)
+    else:  # inference statistics (the reference scripts never call .eval(); kept for completeness)
+        invstd = torch.rsqrt(rv + BN_EPS)
+        sc = gamma.detach() * invstd
+        ss = torch.stack([sc, beta.detach() - rm * sc]).contiguous()
+        mi = torch.stack([rm, invstd]).contiguous()
+    out = ops.bn_apply_act(y, rows, c, ss, act, LEAKY)
+    return out, BNState(y, rows, c, ss, mi, act)
+
+
+def bn_act_backward(dout, st: BNState, G, prefix):
+    """Returns dy (bf16); accumulates dgamma / dbeta into G when present."""
+    dg = G.get(prefix + ".weight") if G is not None else None
+    db = G.get(prefix + ".bias") if G is not None else None
+    dy, _ = ops.bn_backward(dout, st.y, st.rows, st.c, st.scale_shift, st.mean_invstd, st.act, LEAKY, dg, db)
+    return dy
+
+
+def _splits_for(m_tiles, n_tiles, kblocks, target=296):
+    s = max(1, min(kblocks, target // max(1, m_tiles * n_tiles)))
+    return s
+
+
+def linear_forward(x_bf16, w_bf16, bias, batch, n_out, k_in, out_dtype=F32):
+    """y[batch, n_out] = x @ w^T + bias, fp32 accumulate; split-K (atomic fp32) when the grid would be tiny."""
+    n_tiles = (n_out + 127) // 128
+    m_tiles = (batch + 127) // 128
+    splits = _splits_for(m_tiles, n_tiles, k_in // 64 if k_in >= 64 else 1)
+    if out_dtype != F32:
+        splits = 1
+    return ops.gemm(GEMM_NT, x_bf16, w_bf16, batch, n_out, k_in, out_dtype=out_dtype, accumulate=splits > 1,
+                    bias=bias, splits=splits)
+
+
+def linear_dgrad(dy_bf16, w_bf16, batch, n_out, k_in, out_dtype=BF16, out=None):
+    """dx[batch, k_in] = dy[batch, n_out] @ w[n_out, k_in]"""
+    n_tiles = (k_in + 127) // 128
+    m_tiles = (batch + 127) // 128
+    splits = _splits_for(m_tiles, n_tiles, max(1, n_out // 64)) if (out_dtype == F32) else 1
+    acc = splits > 1 or out is not None
+    return ops.gemm(GEMM_NN, dy_bf16, w_bf16, batch, k_in, n_out, out=out, out_dtype=out_dtype, accumulate=acc,
+                    splits=splits)
+
+
+def linear_wgrad(dy_bf16, x_bf16, batch, n_out, k_in, dw):
+    """dw[n_out, k_in] += dy^T @ x"""
+    ops.gemm(GEMM_TN, dy_bf16, x_bf16, n_out, k_in, batch, out=dw, accumulate=True)
+
+
+def col_conv_forward(col, w_col, bias, rows, cs):
+    """3-channel convolution as a GEMM over the im2col matrix: raw[rows, cs] (bf16)."""
+    return ops.gemm(GEMM_NT, col, w_col, rows, cs, 128, out_dtype=BF16, bias=bias, k_alg=75)
+
+
+def col_conv_wgrad(col, dy, rows, cs, dw):
+    """dw[cs][3][5][5] (viewed [cs][75]) += dy^T @ col ; computed as D[k, cs] = col^T dy with a transposed store."""
+    splits = max(1, min(rows // 64, 296))
+    ops.gemm(GEMM_TN, col, dy.view(rows, cs), 128, cs, rows, out=dw, accumulate=True, splits=splits, ldd_m=1, ldd_n=75, m_store=75,
+             n_store=cs)
+
+
+# ------------------------------------------------------------------------------------------ Discriminator
+def discriminator_forward(x, P, B, cache: OperandCache, training=True, col=None):
+    """Discriminator_celeba.forward (model.py:410-416). x: fp32 NCHW [b,3,64,64]. Returns prob [b], feat [b,2048]."""
+    b = x.shape[0]
+    S = SimpleNamespace(b=b)
+    S.col = ops.im2col3(x, 1) if col is None else col
+    _, _, wc1 = _conv_pack(cache, "convs.0", P["convs.0.weight"], 32, 3)
+    raw1 = col_conv_forward(S.col, wc1, P["convs.0.bias"].detach(), b * 4096, 32)
+    S.a1, S.bn1 = bn_act_forward(raw1, b * 4096, 32, P, B, "convs.1", ACT_LEAKY, training)
+    g2 = ops.geom(b, 32, 32, 128, 32, 2)
+    wd2, _, _ = _conv_pack(cache, "convs.3", P["convs.3.weight"], 128, 32)
+    raw2 = ops.conv_down(g2, S.a1, wd2, P["convs.3.bias"].detach())
+    S.a2, S.bn2 = bn_act_forward(raw2, b * 1024, 128, P, B, "convs.4", ACT_LEAKY, training)
+    g3 = ops.geom(b, 16, 16, 256, 128, 2)
+    wd3, _, _ = _conv_pack(cache, "convs.6", P["convs.6.weight"], 256, 128)
+    raw3 = ops.conv_down(g3, S.a2, wd3, P["convs.6.bias"].detach())
+    S.a3, S.bn3 = bn_act_forward(raw3, b * 256, 256, P, B, "convs.7", ACT_LEAKY, training)
+    g4 = ops.geom(b, 8, 8, 256, 256, 2)
+    wd4, _, _ = _conv_pack(cache, "convs.9", P["convs.9.weight"], 256, 256)
+    raw4 = ops.conv_down(g4, S.a3, wd4, P["convs.9.bias"].detach())
+    a4, S.bn4 = bn_act_forward(raw4, b * 64, 256, P, B, "convs.10", ACT_LEAKY, training)
+    S.flat = ops.transpose(a4, b, 64, 256)  # NHWC [b,64,256] -> NCHW flatten order [b,256*64]
+    wl = _lin_w(cache, "lth_features.0", P["lth_features.0.weight"])
+    acc = linear_forward(S.flat, wl, None, b, 2048, 16384)
+    S.feat, _ = ops.bias_act(acc, b, 2048, P["lth_features.0.bias"].detach(), ACT_LEAKY, LEAKY, True, False)
+    S.prob = ops.head_forward(S.feat, P["sigmoid_output.0.weight"].detach().contiguous(),
+                              P["sigmoid_output.0.bias"].detach())
+    return S.prob, S.feat, S
+
+
+def discriminator_backward(S, dprob, dfeat, P, G, cache: OperandCache, need_dx=True, need_wgrad=True):
+    """Backward of discriminator_forward. dprob [b] / dfeat [b,2048] fp32 (either may be None).
+    G: dict name -> fp32 grad tensor (accumulated) or None. Returns dx fp32 NCHW or None."""
+    b = S.b
+    dev = S.feat.device
+    if dprob is None:
+        dprob = torch.zeros(b, dtype=F32, device=dev)
+    wg = G if need_wgrad else None
+    wo = P["sigmoid_output.0.weight"].detach().contiguous()
+    dfeat_t = ops.head_backward(dprob.contiguous(), S.prob, S.feat, None if dfeat is None else dfeat.contiguous(), wo,
+                                wg["sigmoid_output.0.weight"] if wg else None,
+                                wg["sigmoid_output.0.bias"] if wg else None)
+    colsum = wg["lth_features.0.bias"] if wg else torch.zeros(2048, dtype=F32, device=dev)
+    dpre = ops.act_backward(dfeat_t, S.feat, b, 2048, ACT_LEAKY, LEAKY, colsum)
+    wl = _lin_w(cache, "lth_features.0", P["lth_features.0.weight"])
+    if wg:
+        linear_wgrad(dpre, S.flat, b, 2048, 16384, wg["lth_features.0.weight"])
+    dflat = linear_dgrad(dpre, wl, b, 2048, 16384)
+    da4 = ops.transpose(dflat, b, 256, 64)  # back to NHWC [b,64,256]
+    # conv 4
+    dr4 = bn_act_backward(da4, S.bn4, wg, "convs.10")
+    g4 = ops.geom(b, 8, 8, 256, 256, 2)
+    _, wu4, _ = _conv_pack(cache, "convs.9", P["convs.9.weight"], 256, 256)
+    if wg:
+        ops.conv_wgrad(g4, dr4, S.a3, wg["convs.9.weight"])
+    da3 = ops.conv_up(g4, dr4, wu4)
+    # conv 3
+    dr3 = bn_act_backward(da3, S.bn3, wg, "convs.7")
+    g3 = ops.geom(b, 16, 16, 256, 128, 2)
+    _, wu3, _ = _conv_pack(cache, "convs.6", P["convs.6.weight"], 256, 128)
+    if wg:
+        ops.conv_wgrad(g3, dr3, S.a2, wg["convs.6.weight"])
+    da2 = ops.conv_up(g3, dr3, wu3)
+    # conv 2
+    dr2 = bn_act_backward(da2, S.bn2, wg, "convs.4")
+    g2 = ops.geom(b, 32, 32, 128, 32, 2)
+    _, wu2, _ = _conv_pack(cache, "convs.3", P["convs.3.weight"], 128, 32)
+    if wg:
+        ops.conv_wgrad(g2, dr2, S.a1, wg["convs.3.weight"])
+    da1 = ops.conv_up(g2, dr2, wu2)
+    # conv 1 (3 input channels: im2col GEMM)
+    dr1 = bn_act_backward(da1, S.bn1, wg, "convs.1")
+    if wg:
+        col_conv_wgrad(S.col, dr1, b * 4096, 32, wg["convs.0.weight"])
+    if not need_dx:
+        return None
+    g1 = ops.geom(b, 64, 64, 32, 3, 1)
+    _, wu1, _ = _conv_pack(cache, "convs.0", P["convs.0.weight"], 32, 3)
+    dx_nhwc = ops.conv_up(g1, dr1, wu1, out_f32=True)
+    return ops.nhwc3_to_nchw(dx_nhwc, b, 64, 64, False)
+
+
+# ------------------------------------------------------------------------------------------ Encoder
+def encoder_forward(x, P, B, cache: OperandCache, training=True, col=None):
+    """VAE.encode (model.py:511-522). Returns mu, logvar fp32 [b,128]."""
+    b = x.shape[0]
+    S = SimpleNamespace(b=b)
+    S.col = ops.im2col3(x, 2) if col is None else col
+    _, _, wc1 = _conv_pack(cache, "features.0", P["features.0.weight"], 64, 3)
+    raw1 = col_conv_forward(S.col, wc1, P["features.0.bias"].detach(), b * 1024, 64)
+    S.a1, S.bn1 = bn_act_forward(raw1, b * 1024, 64, P, B, "features.1", ACT_RELU, training)
+    g2 = ops.geom(b, 16, 16, 128, 64, 2)
+    wd2, _, _ = _conv_pack(cache, "features.3", P["features.3.weight"], 128, 64)
+    raw2 = ops.conv_down(g2, S.a1, wd2, P["features.3.bias"].detach())
+    S.a2, S.bn2 = bn_act_forward(raw2, b * 256, 128, P, B, "features.4", ACT_RELU, training)
+    g3 = ops.geom(b, 8, 8, 256, 128, 2)
+    wd3, _, _ = _conv_pack(cache, "features.6", P["features.6.weight"], 256, 128)
+    raw3 = ops.conv_down(g3, S.a2, wd3, P["features.6.bias"].detach())
+    a3, S.bn3 = bn_act_forward(raw3, b * 64, 256, P, B, "features.7", ACT_RELU, training)
+    S.flat = ops.transpose(a3, b, 64, 256)
+    outs = []
+    S.heads = {}
+    for head in ("x_to_mu", "x_to_logvar"):
+        w0 = _lin_w(cache, head + ".0", P[head + ".0.weight"])
+        acc = linear_forward(S.flat, w0, P[head + ".0.bias"].detach(), b, 2048, 16384)
+        h1, bn = bn_act_forward(acc, b, 2048, P, B, head + ".1", ACT_RELU, training)
+        w3 = _lin_w(cache, head + ".3", P[head + ".3.weight"])
+        out = linear_forward(h1, w3, P[head + ".3.bias"].detach(), b, 128, 2048)
+        S.heads[head] = SimpleNamespace(h1=h1, bn=bn)
+        outs.append(out)
+    return outs[0], outs[1], S
+
+
+def encoder_backward(S, dmu, dlogvar, P, G, cache: OperandCache, need_wgrad=True):
+    """dmu / dlogvar: fp32 [b,128] gradients w.r.t. the encoder outputs."""
+    b = S.b
+    dev = S.flat.device
+    wg = G if need_wgrad else None
+    dflat = torch.zeros((b, 16384), dtype=F32, device=dev)
+    for head, d in (("x_to_mu", dmu), ("x_to_logvar", dlogvar)):
+        H = S.heads[head]
+        if d is None:
+            d = torch.zeros((b, 128), dtype=F32, device=dev)
+        d = d.contiguous()
+        d16 = ops.cast_bf16(d)
+        if wg:
+            ops.colsum(d, b, 128, wg[head + ".3.bias"])
+            linear_wgrad(d16, H.h1, b, 128, 2048, wg[head + ".3.weight"])
+        w3 = _lin_w(cache, head + ".3", P[head + ".3.weight"])
+        dh1 = linear_dgrad(d16, w3, b, 128, 2048)
+        dacc = bn_act_backward(dh1, H.bn, wg, head + ".1")
+        w0 = _lin_w(cache, head + ".0", P[head + ".0.weight"])
+        if wg:
+            linear_wgrad(dacc, S.flat, b, 2048, 16384, wg[head + ".0.weight"])
+        linear_dgrad(dacc, w0, b, 2048, 16384, out_dtype=F32, out=dflat)
+    da3 = ops.transpose(ops.cast_bf16(dflat), b, 256, 64)
+    dr3 = bn_act_backward(da3, S.bn3, wg, "features.7")
+    g3 = ops.geom(b, 8, 8, 256, 128, 2)
+    _, wu3, _ = _conv_pack(cache, "features.6", P["features.6.weight"], 256, 128)
+    if wg:
+        ops.conv_wgrad(g3, dr3, S.a2, wg["features.6.weight"])
+    da2 = ops.conv_up(g3, dr3, wu3)
+    dr2 = bn_act_backward(da2, S.bn2, wg, "features.4")
+    g2 = ops.geom(b, 16, 16, 128, 64, 2)
+    _, wu2, _ = _conv_pack(cache, "features.3", P["features.3.weight"], 128, 64)
+    if wg:
+        ops.conv_wgrad(g2, dr2, S.a1, wg["features.3.weight"])
+    da1 = ops.conv_up(g2, dr2, wu2)
+    dr1 = bn_act_backward(da1, S.bn1, wg, "features.1")
+    if wg:
+        col_conv_wgrad(S.col, dr1, b * 1024, 64, wg["features.0.weight"])
+    return None  # the encoder input is data: no input gradient on this path
+
+
+# ------------------------------------------------------------------------------------------ Decoder
+def decoder_forward(code, P, B, cache: OperandCache, training=True):
+    """VAE.decode / Generator_celeba.forward (model.py:537-566, 363-378). code: fp32 or bf16 [b,128].
+    Returns recon fp32 NCHW [b,3,64,64]."""
+    b = code.shape[0]
+    S = SimpleNamespace(b=b)
+    S.code16 = code if code.dtype == BF16 else ops.cast_bf16(code.contiguous())
+    wp = _lin_w(cache, "preprocess.0", P["preprocess.0.weight"])
+    acc = linear_forward(S.code16, wp, P["preprocess.0.bias"].detach(), b, 16384, 128)
+    h, S.bn0 = bn_act_forward(acc, b, 16384, P, B, "preprocess.1", ACT_RELU, training)
+    S.h0 = ops.transpose(h, b, 256, 64)  # NCHW flatten order -> NHWC [b,8,8,256]
+    g1 = ops.geom(b, 8, 8, 256, 256, 2)
+    _, wu1, _ = _conv_pack(cache, "deconv1", P["deconv1.weight"], 256, 256)
+    raw1 = ops.conv_up(g1, S.h0, wu1, P["deconv1.bias"].detach())
+    S.a1, S.bn1 = bn_act_forward(raw1, b * 256, 256, P, B, "act1.0", ACT_RELU, training)
+    g2 = ops.geom(b, 16, 16, 256, 128, 2)
+    _, wu2, _ = _conv_pack(cache, "deconv2", P["deconv2.weight"], 256, 128)
+    raw2 = ops.conv_up(g2, S.a1, wu2, P["deconv2.bias"].detach())
+    S.a2, S.bn2 = bn_act_forward(raw2, b * 1024, 128, P, B, "act2.0", ACT_RELU, training)
+    g3 = ops.geom(b, 32, 32, 128, 32, 2)
+    _, wu3, _ = _conv_pack(cache, "deconv3", P["deconv3.weight"], 128, 32)
+    raw3 = ops.conv_up(g3, S.a2, wu3, P["deconv3.bias"].detach())
+    S.a3, S.bn3 = bn_act_forward(raw3, b * 4096, 32, P, B, "act3.0", ACT_RELU, training)
+    g4 = ops.geom(b, 64, 64, 32, 3, 1)
+    _, wu4, _ = _conv_pack(cache, "deconv4", P["deconv4.weight"], 32, 3)
+    y4 = ops.conv_up(g4, S.a3, wu4, P["deconv4.bias"].detach(), out_f32=True)  # fp32 NHWC(3)
+    S.recon = ops.nhwc3_to_nchw(y4, b, 64, 64, True)
+    return S.recon, S
+
+
+def decoder_backward(S, drecon, P, G, cache: OperandCache, need_dcode=True, need_wgrad=True):
+    """drecon: fp32 NCHW gradient w.r.t. the decoder output. Returns dcode fp32 [b,128] or None."""
+    b = S.b
+    wg = G if need_wgrad else None
+    dy4 = ops.tanh_backward(drecon.contiguous(), S.recon, wg["deconv4.bias"] if wg else None)  # fp32 NCHW
+    col4 = ops.im2col3(dy4, 1)  # [b*4096, 128]
+    if wg:
+        col_conv_wgrad(col4, S.a3, b * 4096, 32, wg["deconv4.weight"])
+    _, _, wc4 = _conv_pack(cache, "deconv4", P["deconv4.weight"], 32, 3)
+    da3 = col_conv_forward(col4, wc4, None, b * 4096, 32)  # ConvT input-gradient = conv of dy with the same weights
+    dr3 = bn_act_backward(da3, S.bn3, wg, "act3.0")
+    g3 = ops.geom(b, 32, 32, 128, 32, 2)
+    wd3, _, _ = _conv_pack(cache, "deconv3", P["deconv3.weight"], 128, 32)
+    if wg:
+        ops.conv_wgrad(g3, S.a2, dr3, wg["deconv3.weight"])
+    da2 = ops.conv_down(g3, dr3, wd3)
+    dr2 = bn_act_backward(da2, S.bn2, wg, "act2.0")
+    g2 = ops.geom(b, 16, 16, 256, 128, 2)
+    wd2, _, _ = _conv_pack(cache, "deconv2", P["deconv2.weight"], 256, 128)
+    if wg:
+        ops.conv_wgrad(g2, S.a1, dr2, wg["deconv2.weight"])
+    da1 = ops.conv_down(g2, dr2, wd2)
+    dr1 = bn_act_backward(da1, S.bn1, wg, "act1.0")
+    g1 = ops.geom(b, 8, 8, 256, 256, 2)
+    wd1, _, _ = _conv_pack(cache, "deconv1", P["deconv1.weight"], 256, 256)
+    if wg:
+        ops.conv_wgrad(g1, S.h0, dr1, wg["deconv1.weight"])
+    dh0 = ops.conv_down(g1, dr1, wd1)  # NHWC [b,8,8,256]
+    dh = ops.transpose(dh0, b, 64, 256)  # -> [b, 256*64] flatten order
+    dacc = bn_act_backward(dh, S.bn0, wg, "preprocess.1")
+    if wg:
+        linear_wgrad(dacc, S.code16, b, 16384, 128, wg["preprocess.0.weight"])
+    if not need_dcode:
+        return None
+    wp = _lin_w(cache, "preprocess.0", P["preprocess.0.weight"])
+    return linear_dgrad(dacc, wp, b, 16384, 128, out_dtype=F32)

@@ -34,7 +34,7 @@ def geom(batch, hs, ws, cs, cb, stride) -> ConvGeom:
 
 # ------------------------------------------------------------------------------------------ GEMM-class
 def gemm(layout, a, b, m, n, k, *, out=None, out_dtype=F32, accumulate=False, bias=None, splits=1,
-         lda=None, ldb=None, ldd_m=None, ldd_n=1, m_store=0, n_store=0):
+         lda=None, ldb=None, ldd_m=None, ldd_n=1, m_store=0, n_store=0, k_alg=0):
     """D = op(A) op(B) with bf16 operands; see dm_gemm_desc."""
     assert a.dtype == BF16 and b.dtype == BF16
     if out is None:
@@ -47,7 +47,7 @@ def gemm(layout, a, b, m, n, k, *, out=None, out_dtype=F32, accumulate=False, bi
     if ldd_m is None:
         ldd_m = out.stride(0) if out.dim() >= 2 else 1
     d = GemmDesc(layout, m, n, k, _p(a), lda, _p(b), ldb, _p(out), ldd_m, ldd_n, int(out.dtype == F32),
-                 int(accumulate), _p(bias), m_store, n_store, splits)
+                 int(accumulate), _p(bias), m_store, n_store, splits, k_alg)
     _lib.check(_lib.load().dm_gemm_bf16(C.byref(d), _stream()), "dm_gemm_bf16")
     return out
 
@@ -73,6 +73,17 @@ def conv_wgrad(g: ConvGeom, small, big, dw):
     assert dw.dtype == F32
     _lib.check(_lib.load().dm_conv_wgrad(C.byref(g), _p(small), _p(big), _p(dw), _stream()), "dm_conv_wgrad")
     return dw
+
+
+def profile_enable(on: bool):
+    _lib.load().dm_profile_enable(int(on))
+
+
+def profile_read():
+    """(total GEMM-kernel ms, algorithmic FLOPs, launches) since the previous read; synchronises."""
+    ms, fl, n = C.c_double(), C.c_double(), C.c_longlong()
+    _lib.check(_lib.load().dm_profile_read(C.byref(ms), C.byref(fl), C.byref(n)), "dm_profile_read")
+    return ms.value, fl.value, n.value
 
 
 def last_plan():

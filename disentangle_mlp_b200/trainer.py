@@ -1,0 +1,327 @@
+"""Fused training steps: one iteration of the reference's three loops, scheduled as kernel calls.
+
+  VAETrainer.step          <- experiments/new_vae.py:53-60
+  GANTrainer.step          <- experiments/new_gan.py:84-128
+  BetaVAEGANTrainer.step   <- experiments/new_betavaegan.py:93-193
+
+Semantics kept from the reference: same update order (D, then EG "decoder" phase, then
+EG "encoder" phase), both EG Adam steps update every encoder and decoder parameter, `fake` is generated
+before the D update and re-scored after it, one (real, fake) label pair per step, BatchNorm always in
+training mode with running stats updated on every forward (D 5x, encoder 2x, decoder 3x per step), BCE is a
+mean over the batch, MSE / Dis_l / KL are sums.
+What is NOT repeated: the reference walks the same graphs with six separate `.backward()` calls and computes
+discriminator weight gradients in the EG phases that the next `netD.zero_grad()` throws away
+(new_betavaegan.py:95,157-163); here each phase runs one backward per graph and skips the discarded wgrads.
+The resulting parameter updates are the same sums of the same terms.
+
+Data parallel (one process per GPU): gradients are SUM-allreduced before each Adam step; the BCE terms are
+scaled by 1/world_size so that the sum reproduces the reference's mean over the global batch; BatchNorm
+statistics stay per rank (as under the reference's nn.DataParallel).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import engine, ops
+from .ops import BF16, F32
+
+ALIGN = 64  # elements; keeps every parameter's bf16 shadow 128-byte aligned for TMA
+
+
+class FlatParams:
+    """Re-homes a module's parameters into ONE flat fp32 buffer (parameters become views), with matching
+    flat gradient / Adam-moment buffers and a bf16 shadow that the GEMMs read."""
+
+    def __init__(self, module: torch.nn.Module, lr, betas=(0.9, 0.999), eps=1e-8):
+        named = list(module.named_parameters())
+        self.names = [n for n, _ in named]
+        dev = named[0][1].device
+        assert dev.type == "cuda", "FlatParams needs the module on a CUDA device"
+        self.offsets, off = {}, 0
+        for n, p in named:
+            self.offsets[n] = off
+            off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+        self.total = off
+        self.flat = torch.zeros(off, dtype=F32, device=dev)
+        self.grad = torch.zeros(off, dtype=F32, device=dev)
+        self.m = torch.zeros(off, dtype=F32, device=dev)
+        self.v = torch.zeros(off, dtype=F32, device=dev)
+        self.shadow = torch.zeros(off, dtype=BF16, device=dev)
+        self.P, self.G, self.W16 = {}, {}, {}
+        for n, p in named:
+            o, k = self.offsets[n], p.numel()
+            self.flat[o:o + k].copy_(p.data.reshape(-1))
+            p.data = self.flat[o:o + k].view(p.shape)
+            self.P[n] = p
+            self.G[n] = self.grad[o:o + k].view(p.shape)
+            self.W16[n] = self.shadow[o:o + k].view(p.shape)
+        self.module = module
+        self.buffers = dict(module.named_buffers())
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.step_count = 0
+        self.cache = engine.OperandCache()
+        self.cache.lin_views = self.W16
+        self.params_changed()
+
+    def params_changed(self):
+        """Call after the fp32 parameters were modified outside adam() (init, load_state_dict)."""
+        ops.cast_bf16(self.flat, self.shadow)
+        self.cache.invalidate()
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def adam(self, grad_scale=1.0):
+        self.step_count += 1
+        ops.adam_step(self.flat, self.grad, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps,
+                      self.step_count, grad_scale, self.shadow)
+        self.cache.invalidate()  # conv operand packs are rebuilt lazily from the updated fp32 weights
+
+    def optimizer_state_dict(self):
+        """torch.optim.Adam-compatible state (exp_avg / exp_avg_sq / step per parameter)."""
+        state = {}
+        for i, n in enumerate(self.names):
+            o, k = self.offsets[n], self.P[n].numel()
+            state[i] = {"step": torch.tensor(float(self.step_count)),
+                        "exp_avg": self.m[o:o + k].view(self.P[n].shape).clone(),
+                        "exp_avg_sq": self.v[o:o + k].view(self.P[n].shape).clone()}
+        group = {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": 0, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "decoupled_weight_decay": False, "params": list(range(len(self.names)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_optimizer_state_dict(self, sd):
+        steps = set()
+        for i, n in enumerate(self.names):
+            st = sd["state"].get(i)
+            if st is None:
+                continue
+            o, k = self.offsets[n], self.P[n].numel()
+            self.m[o:o + k].copy_(st["exp_avg"].reshape(-1))
+            self.v[o:o + k].copy_(st["exp_avg_sq"].reshape(-1))
+            steps.add(int(st["step"]))
+        if steps:
+            assert len(steps) == 1, "per-parameter step counts differ; not representable"
+            self.step_count = steps.pop()
+        g = sd["param_groups"][0]
+        self.lr, self.betas, self.eps = g["lr"], tuple(g["betas"]), g["eps"]
+
+
+class _Dist:
+    """Gradient all-reduce (SUM) over torch.distributed; a no-op for world size 1."""
+
+    def __init__(self):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.on = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.world = dist.get_world_size() if self.on else 1
+        self.pending = []
+        self.comm_stream = torch.cuda.Stream() if self.on else None
+
+    def allreduce_async(self, flat, lo=0, hi=None):
+        """Enqueue a SUM all-reduce of flat[lo:hi] on the side stream, ordered after the work already queued
+        on the current stream."""
+        if not self.on:
+            return
+        hi = flat.numel() if hi is None else hi
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(ev)
+            self.dist.all_reduce(flat[lo:hi], op=self.dist.ReduceOp.SUM)
+        self.pending.append(None)
+
+    def wait(self):
+        if self.on and self.pending:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+            self.pending.clear()
+
+
+def _scalar(dev):
+    return torch.zeros((), dtype=F32, device=dev)
+
+
+class _Base:
+    def __init__(self):
+        self.dist = _Dist()
+        self.metrics = {}
+
+    @staticmethod
+    def draw_labels():
+        """One (real, fake) label pair per step from numpy's global RNG (new_betavaegan.py:89-90)."""
+        fake = float(np.random.choice(a=[0.1, 0.9], p=[0.95, 0.05]))
+        real = float(np.random.choice(a=[0.1, 0.9], p=[0.05, 0.95]))
+        return real, fake
+
+    def _bce(self, prob, target, loss, stat=None):
+        """Mean BCE over the GLOBAL batch and its gradient w.r.t. prob."""
+        b = prob.numel()
+        dprob = torch.empty_like(prob)
+        ops.bce_const(prob, target, loss, 1.0, n_total=b * self.dist.world, dprob=dprob, stat=stat)
+        return dprob
+
+
+class VAETrainer(_Base):
+    """One step of experiments/new_vae.py:53-60 (loss = MSE-sum + KL-sum, :39-48)."""
+
+    def __init__(self, model, lr=3e-3, beta=1.0):
+        super().__init__()
+        self.model = model
+        self.fp = FlatParams(model, lr)
+        self.beta = beta
+
+    def step(self, data, eps=None):
+        fp, dev = self.fp, data.device
+        b = data.shape[0]
+        loss = _scalar(dev)
+        fp.zero_grad()
+        mu, logvar, Se = engine.encoder_forward(data, fp.P, fp.buffers, fp.cache, True)
+        if eps is None:
+            eps = torch.randn_like(mu)
+        _, z16 = ops.reparam_forward(mu, logvar, eps)
+        recon, Sg = engine.decoder_forward(z16, fp.P, fp.buffers, fp.cache, True)
+        drecon = torch.empty_like(recon)
+        ops.mse_sum(recon, data, loss, 1.0, drecon, 1.0)
+        dmu_kl, dlv_kl = torch.empty_like(mu), torch.empty_like(mu)
+        ops.kl(mu, logvar, loss, self.beta, dmu_kl, dlv_kl)
+        dz = engine.decoder_backward(Sg, drecon, fp.P, fp.G, fp.cache, True, True)
+        _, _, dmu, dlv = ops.reparam_backward(dz, logvar, eps, dmu_kl, dlv_kl)
+        engine.encoder_backward(Se, dmu, dlv, fp.P, fp.G, fp.cache, True)
+        self.dist.allreduce_async(fp.grad)
+        self.dist.wait()
+        fp.adam()
+        self.metrics = {"loss": loss}
+        return self.metrics
+
+
+class GANTrainer(_Base):
+    """One step of experiments/new_gan.py:84-128."""
+
+    def __init__(self, netG, netD, lr=3e-3):
+        super().__init__()
+        self.netG, self.netD = netG, netD
+        self.fg = FlatParams(netG, lr)
+        self.fd = FlatParams(netD, lr)
+
+    def step(self, data, real_label=None, fake_label=None, noise=None):
+        fg, fd, dev = self.fg, self.fd, data.device
+        b = data.shape[0]
+        if real_label is None:
+            real_label, fake_label = self.draw_labels()
+        errD, errG, sum_dx, sum_dgz1, sum_dgz2 = (_scalar(dev) for _ in range(5))
+        # ---- (1) discriminator: real batch, then detached fake batch (:84-113)
+        fd.zero_grad()
+        prob_r, _, S1 = engine.discriminator_forward(data, fd.P, fd.buffers, fd.cache, True)
+        d1 = self._bce(prob_r, real_label, errD, sum_dx)
+        if noise is None:
+            noise = torch.randn(b, 128, device=dev)
+        fake, Sg = engine.decoder_forward(noise, fg.P, fg.buffers, fg.cache, True)
+        prob_f, _, S2 = engine.discriminator_forward(fake, fd.P, fd.buffers, fd.cache, True)
+        d2 = self._bce(prob_f, fake_label, errD, sum_dgz1)
+        engine.discriminator_backward(S1, d1, None, fd.P, fd.G, fd.cache, False, True)
+        engine.discriminator_backward(S2, d2, None, fd.P, fd.G, fd.cache, False, True)
+        self.dist.allreduce_async(fd.grad)
+        self.dist.wait()
+        fd.adam()
+        # ---- (2) generator: re-score the same fake batch with the updated D (:118-128)
+        fg.zero_grad()
+        prob_g, _, S3 = engine.discriminator_forward(fake, fd.P, fd.buffers, fd.cache, True)
+        d3 = self._bce(prob_g, real_label, errG, sum_dgz2)
+        dfake = engine.discriminator_backward(S3, d3, None, fd.P, None, fd.cache, True, False)
+        engine.decoder_backward(Sg, dfake, fg.P, fg.G, fg.cache, False, True)
+        self.dist.allreduce_async(fg.grad)
+        self.dist.wait()
+        fg.adam()
+        self.metrics = {"errD": errD, "errG": errG, "D_x": sum_dx / b, "D_G_z1": sum_dgz1 / b, "D_G_z2": sum_dgz2 / b}
+        return self.metrics
+
+
+class BetaVAEGANTrainer(_Base):
+    """One step of experiments/new_betavaegan.py:93-193 (beta multiplies only the KL term, :64-65)."""
+
+    def __init__(self, netEG, netD, beta, lr=1e-3):
+        super().__init__()
+        self.netEG, self.netD = netEG, netD
+        self.feg = FlatParams(netEG, lr)
+        self.fd = FlatParams(netD, lr)
+        self.beta = float(beta)
+
+    def step(self, data, real_label=None, fake_label=None, noise=None, eps_dec=None, eps_enc=None):
+        feg, fd, dev = self.feg, self.fd, data.device
+        b = data.shape[0]
+        if real_label is None:
+            real_label, fake_label = self.draw_labels()
+        (errD_real, errD_fake, sum_dx, errG_fake, errG_recon, sim_loss, loss_dec, kld, loss_enc) = (
+            _scalar(dev) for _ in range(9))
+        col_d = ops.im2col3(data, 1)  # the D-side and encoder-side im2col of `data` are reused within the step
+        col_e = ops.im2col3(data, 2)
+
+        # ================= discriminator phase (:95-123)
+        fd.zero_grad()
+        prob_r, _, S1 = engine.discriminator_forward(data, fd.P, fd.buffers, fd.cache, True, col=col_d)
+        d1 = self._bce(prob_r, real_label, errD_real, sum_dx)
+        if noise is None:
+            noise = torch.randn(b, 128, device=dev)
+        fake, Sg1 = engine.decoder_forward(noise, feg.P, feg.buffers, feg.cache, True)
+        prob_f, _, S2 = engine.discriminator_forward(fake, fd.P, fd.buffers, fd.cache, True)
+        d2 = self._bce(prob_f, fake_label, errD_fake)
+        engine.discriminator_backward(S1, d1, None, fd.P, fd.G, fd.cache, False, True)
+        engine.discriminator_backward(S2, d2, None, fd.P, fd.G, fd.cache, False, True)
+        del S1, S2
+        self.dist.allreduce_async(fd.grad)
+        self.dist.wait()
+        fd.adam()
+
+        # ================= "decoder" phase (:127-164): gradient of
+        #   BCE(D(fake), real) + BCE(D(recon), real) + 0.5*||Dis_l(recon) - Dis_l(x)||^2 + ||recon - x||^2
+        # w.r.t. ALL encoder and decoder parameters, D frozen at its updated value
+        feg.zero_grad()
+        _, sim_real, S3 = engine.discriminator_forward(data, fd.P, fd.buffers, fd.cache, True, col=col_d)
+        del S3  # sim_real's path into D only produces discarded D gradients (:95)
+        mu, logvar, Se = engine.encoder_forward(data, feg.P, feg.buffers, feg.cache, True, col=col_e)
+        if eps_dec is None:
+            eps_dec = torch.randn_like(mu)
+        _, z16 = ops.reparam_forward(mu, logvar, eps_dec)
+        recon, Sg2 = engine.decoder_forward(z16, feg.P, feg.buffers, feg.cache, True)
+        prob_f2, _, S4 = engine.discriminator_forward(fake, fd.P, fd.buffers, fd.cache, True)
+        prob_rc, sim_recon, S5 = engine.discriminator_forward(recon, fd.P, fd.buffers, fd.cache, True)
+        d4 = self._bce(prob_f2, real_label, errG_fake)
+        d5 = self._bce(prob_rc, real_label, errG_recon)
+        dsim = torch.empty_like(sim_recon)
+        ops.mse_sum(sim_recon, sim_real, sim_loss, 0.5, dsim, 0.5)
+        dfake = engine.discriminator_backward(S4, d4, None, fd.P, None, fd.cache, True, False)
+        engine.decoder_backward(Sg1, dfake, feg.P, feg.G, feg.cache, False, True)
+        del S4, Sg1
+        drecon = engine.discriminator_backward(S5, d5, dsim, fd.P, None, fd.cache, True, False)
+        ops.mse_sum(recon, data, loss_dec, 1.0, drecon, 1.0, accumulate=True)
+        dz = engine.decoder_backward(Sg2, drecon, feg.P, feg.G, feg.cache, True, True)
+        _, _, dmu, dlv = ops.reparam_backward(dz, logvar, eps_dec)
+        engine.encoder_backward(Se, dmu, dlv, feg.P, feg.G, feg.cache, True)
+        del S5, Sg2, Se
+        self.dist.allreduce_async(feg.grad)
+        self.dist.wait()
+        feg.adam()
+
+        # ================= "encoder" phase (:167-193): gradient of beta*KL + ||recon - x||^2, fresh forward
+        feg.zero_grad()
+        mu, logvar, Se = engine.encoder_forward(data, feg.P, feg.buffers, feg.cache, True, col=col_e)
+        if eps_enc is None:
+            eps_enc = torch.randn_like(mu)
+        _, z16 = ops.reparam_forward(mu, logvar, eps_enc)
+        recon, Sg3 = engine.decoder_forward(z16, feg.P, feg.buffers, feg.cache, True)
+        drecon = torch.empty_like(recon)
+        ops.mse_sum(recon, data, loss_enc, 1.0, drecon, 1.0)
+        dmu_kl, dlv_kl = torch.empty_like(mu), torch.empty_like(mu)
+        ops.kl(mu, logvar, kld, self.beta, dmu_kl, dlv_kl)
+        dz = engine.decoder_backward(Sg3, drecon, feg.P, feg.G, feg.cache, True, True)
+        _, _, dmu, dlv = ops.reparam_backward(dz, logvar, eps_enc, dmu_kl, dlv_kl)
+        engine.encoder_backward(Se, dmu, dlv, feg.P, feg.G, feg.cache, True)
+        self.dist.allreduce_async(feg.grad)
+        self.dist.wait()
+        feg.adam()
+        self.metrics = {"errD_real": errD_real, "errD_fake": errD_fake, "D_x": sum_dx / b, "errG_fake": errG_fake,
+                        "errG_recon": errG_recon, "sim": sim_loss, "recon_dec": loss_dec, "kld": kld,
+                        "recon_enc": loss_enc}
+        return self.metrics

@@ -53,6 +53,7 @@ typedef struct dm_gemm_desc {
   int m_store;       /* rows of D actually stored (0 = m) */
   int n_store;       /* columns of D actually stored (0 = n) */
   int splits;        /* split-K factor (>= 1) */
+  int k_alg;         /* algorithmic K for FLOP accounting when k is zero-padded (0 = k) */
 } dm_gemm_desc;
 
 int dm_gemm_bf16(const dm_gemm_desc* g, void* stream);
@@ -155,6 +156,12 @@ int dm_bce_const(const float* p, int n, float n_total, float target, float w, fl
  * 1-based step count; g is multiplied by grad_scale first; shadow_bf16 (may be NULL) receives bf16(p). */
 int dm_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
                  float beta2, float eps, int step, float grad_scale, void* shadow_bf16, void* stream);
+
+/* Per-launch CUDA-event timing of the GEMM-class kernel (bench.py roofline). dm_profile_read synchronises the
+ * device and returns the summed launch durations, algorithmic FLOPs (2*M*N*K; convolutions: 2*25*b*hs*ws*cs*cb)
+ * and launch count since the previous read. */
+int dm_profile_enable(int on);
+int dm_profile_read(double* total_ms, double* total_flops, long long* launches);
 
 /* Test hook: direct access to the tile plan of a GEMM-class call (tile counts, smem bytes). */
 int dm_debug_last_plan(int* grid_xyz, int* smem_bytes, int* stages);
