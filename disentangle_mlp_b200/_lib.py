@@ -63,7 +63,7 @@ _SIGS = {
     "dm_mse_sum": [c_void_p, c_void_p, c_ll, c_float, c_void_p, c_float, c_int, c_void_p, c_void_p],
     "dm_kl": [c_void_p, c_void_p, c_ll, c_float, c_void_p, c_int, c_void_p, c_void_p, c_void_p],
     "dm_bce_const": [c_void_p, c_int, c_float, c_float, c_float, c_void_p, c_int, c_void_p, c_void_p, c_void_p],
-    "dm_adam_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float, c_int,
+    "dm_adam_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, C.c_double, C.c_double, C.c_double, C.c_double, c_int,
                      c_float, c_void_p, c_void_p],
 }
 

@@ -604,9 +604,9 @@ __global__ void __launch_bounds__(256) bce_const_kernel(const float* __restrict_
 // torch.optim.Adam (betas, eps, no weight decay, no amsgrad; experiments/new_betavaegan.py:49-50) on a flat buffer,
 // optionally refreshing the bf16 shadow copy the GEMMs read.  28 B/param (+2 B shadow).
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
-                                                   float* __restrict__ m, float* __restrict__ v, long long n, float lr,
-                                                   float beta1, float beta2, float eps, float bc1, float bc2_sqrt,
-                                                   float grad_scale, __nv_bfloat16* __restrict__ shadow) {
+                                                   float* __restrict__ m, float* __restrict__ v, long long n,
+                                                   float step_size, float beta1, float beta2, float omb1, float omb2,
+                                                   float eps, float bc2_sqrt, float grad_scale, __nv_bfloat16* __restrict__ shadow) {
   const long long nv = n / 4;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nv;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -618,10 +618,10 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float gr = gf[j] * grad_scale;
-      mf[j] = beta1 * mf[j] + (1.f - beta1) * gr;
-      vf[j] = beta2 * vf[j] + (1.f - beta2) * gr * gr;
+      mf[j] = beta1 * mf[j] + omb1 * gr;
+      vf[j] = beta2 * vf[j] + omb2 * gr * gr;
       const float denom = sqrtf(vf[j]) / bc2_sqrt + eps;
-      pf[j] -= (lr / bc1) * (mf[j] / denom);
+      pf[j] -= step_size * (mf[j] / denom);
     }
     reinterpret_cast<float4*>(p)[i] = pp;
     reinterpret_cast<float4*>(m)[i] = mm;
@@ -635,9 +635,9 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   const long long t = nv * 4 + threadIdx.x;
   if (blockIdx.x == 0 && t < n) {
     const float gr = g[t] * grad_scale;
-    m[t] = beta1 * m[t] + (1.f - beta1) * gr;
-    v[t] = beta2 * v[t] + (1.f - beta2) * gr * gr;
-    p[t] -= (lr / bc1) * (m[t] / (sqrtf(v[t]) / bc2_sqrt + eps));
+    m[t] = beta1 * m[t] + omb1 * gr;
+    v[t] = beta2 * v[t] + omb2 * gr * gr;
+    p[t] -= step_size * (m[t] / (sqrtf(v[t]) / bc2_sqrt + eps));
     if (shadow) shadow[t] = __float2bfloat16_rn(p[t]);
   }
 }
@@ -839,12 +839,16 @@ extern "C" int dm_bce_const(const float* p, int n, float n_total, float target, 
   DM_LAUNCHED("dm_bce_const");
 }
 
-extern "C" int dm_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
-                            float beta2, float eps, int step, float grad_scale, void* shadow_bf16, void* stream_) {
+extern "C" int dm_adam_step(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1,
+                            double beta2, double eps, int step, float grad_scale, void* shadow_bf16, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   DM_REQUIRE(step >= 1, "dm_adam_step: step must be >= 1");
-  const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
-  const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
-  adam_kernel<<<grid_for(n / 4 + 1, 256, 148 * 8), 256, 0, s>>>(p, g, m, v, n, lr, beta1, beta2, eps, static_cast<float>(bc1), static_cast<float>(sqrt(bc2)), grad_scale, static_cast<bf16*>(shadow_bf16));
+  // scalar arithmetic in double, then rounded to float once -- as torch.optim.Adam does with Python floats
+  const double bc1 = 1.0 - pow(beta1, step);
+  const double bc2 = 1.0 - pow(beta2, step);
+  adam_kernel<<<grid_for(n / 4 + 1, 256, 148 * 8), 256, 0, s>>>(
+      p, g, m, v, n, static_cast<float>(lr / bc1), static_cast<float>(beta1), static_cast<float>(beta2),
+      static_cast<float>(1.0 - beta1), static_cast<float>(1.0 - beta2), static_cast<float>(eps),
+      static_cast<float>(sqrt(bc2)), grad_scale, static_cast<bf16*>(shadow_bf16));
   DM_LAUNCHED("dm_adam_step");
 }

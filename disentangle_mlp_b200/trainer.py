@@ -108,8 +108,12 @@ class FlatParams:
         self.lr, self.betas, self.eps = g["lr"], tuple(g["betas"]), g["eps"]
 
 
-class _Dist:
-    """Gradient all-reduce (SUM) over torch.distributed; a no-op for world size 1."""
+class GradReducer:
+    """Gradient all-reduce (SUM) over torch.distributed in bucket slices; a no-op for world size 1.
+
+    CUDA tensors: each bucket is enqueued on a side stream, ordered after the work already queued on the
+    current stream, so NCCL overlaps whatever the current stream does next; wait() joins the side stream.
+    CPU tensors (gloo, used by the CPU tests): asynchronous work handles."""
 
     def __init__(self):
         import torch.distributed as dist
@@ -117,26 +121,47 @@ class _Dist:
         self.dist = dist
         self.on = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self.world = dist.get_world_size() if self.on else 1
-        self.pending = []
-        self.comm_stream = torch.cuda.Stream() if self.on else None
+        self.comm_stream = None
+        self.handles = []
+        self.cuda_pending = False
+
+    def bce_scale(self):
+        """nn.BCELoss is a MEAN over the global batch: each rank scales its local mean by 1/world so that the
+        SUM all-reduce of gradients reproduces it; the sum-reduced losses (MSE, Dis_l, KL) need no scaling."""
+        return 1.0 / self.world
+
+    @staticmethod
+    def buckets(n, bucket_elems=8 << 20):
+        lo = 0
+        while lo < n:
+            hi = min(n, lo + bucket_elems)
+            yield lo, hi
+            lo = hi
 
     def allreduce_async(self, flat, lo=0, hi=None):
-        """Enqueue a SUM all-reduce of flat[lo:hi] on the side stream, ordered after the work already queued
-        on the current stream."""
         if not self.on:
             return
         hi = flat.numel() if hi is None else hi
-        ev = torch.cuda.Event()
-        ev.record()
-        with torch.cuda.stream(self.comm_stream):
-            self.comm_stream.wait_event(ev)
-            self.dist.all_reduce(flat[lo:hi], op=self.dist.ReduceOp.SUM)
-        self.pending.append(None)
+        view = flat[lo:hi]
+        if flat.is_cuda:
+            if self.comm_stream is None:
+                self.comm_stream = torch.cuda.Stream()
+            ev = torch.cuda.Event()
+            ev.record()
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(ev)
+                self.dist.all_reduce(view, op=self.dist.ReduceOp.SUM)
+            self.cuda_pending = True
+        else:
+            self.handles.append(self.dist.all_reduce(view, op=self.dist.ReduceOp.SUM, async_op=True))
 
     def wait(self):
-        if self.on and self.pending:
+        for h in self.handles:
+            h.wait()
+        self.handles.clear()
+        if self.cuda_pending:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
-            self.pending.clear()
+            self.cuda_pending = False
 
 
 def _scalar(dev):
@@ -145,7 +170,7 @@ def _scalar(dev):
 
 class _Base:
     def __init__(self):
-        self.dist = _Dist()
+        self.dist = GradReducer()
         self.metrics = {}
 
     @staticmethod

@@ -154,8 +154,8 @@ int dm_bce_const(const float* p, int n, float n_total, float target, float w, fl
 
 /* torch.optim.Adam step on a flat fp32 buffer (new_betavaegan.py:49-50,123,164,193); `step` is the
  * 1-based step count; g is multiplied by grad_scale first; shadow_bf16 (may be NULL) receives bf16(p). */
-int dm_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
-                 float beta2, float eps, int step, float grad_scale, void* shadow_bf16, void* stream);
+int dm_adam_step(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1,
+                 double beta2, double eps, int step, float grad_scale, void* shadow_bf16, void* stream);
 
 /* Per-launch CUDA-event timing of the GEMM-class kernel (bench.py roofline). dm_profile_read synchronises the
  * device and returns the summed launch durations, algorithmic FLOPs (2*M*N*K; convolutions: 2*25*b*hs*ws*cs*cb)

@@ -1,0 +1,70 @@
+"""CPU: libdm_b200.so builds for sm_100a, loads, and exports every symbol include/dm_b200.h declares."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from disentangle_mlp_b200 import _lib, build
+
+    build.build()
+    return _lib.load()
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "dm_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dm_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(lib):
+    names = header_functions()
+    assert len(names) >= 30
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_binding_table_matches_header():
+    from disentangle_mlp_b200 import _lib
+
+    assert sorted(_lib.EXPORTED) == header_functions()
+
+
+def test_version_and_error_string(lib):
+    assert lib.dm_version() == 100
+    assert isinstance(lib.dm_last_error(), bytes)
+    assert lib.dm_launch_count() >= 0
+
+
+def test_struct_layouts_match_c():
+    from disentangle_mlp_b200 import _lib
+
+    # dm_gemm_desc: 4 ints, (ptr, ll) x2, ptr, 2 ll, 2 ints, ptr, 4 ints  -> natural alignment, no surprises
+    assert ctypes.sizeof(_lib.GemmDesc) == 16 + 16 + 16 + 24 + 8 + 8 + 16
+    assert ctypes.sizeof(_lib.ConvGeom) == 32
+
+
+def test_argument_errors_do_not_need_a_gpu(lib):
+    from disentangle_mlp_b200 import _lib
+
+    g = _lib.ConvGeom(4, 8, 8, 256, 17, 16, 256, 2)  # hb != hs*stride
+    rc = lib.dm_conv_down(ctypes.byref(g), None, None, None, None, None)
+    assert rc != 0 and b"stride x small" in lib.dm_last_error()
+    d = _lib.GemmDesc(layout=7, m=1, n=1, k=1, lda=8, ldb=8)
+    assert lib.dm_gemm_bf16(ctypes.byref(d), None) != 0
+
+
+def test_sass_is_blackwell_native():
+    from disentangle_mlp_b200.build import LIB_PATH
+
+    out = subprocess.run(["cuobjdump", "-sass", str(LIB_PATH)], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in out, "tcgen05.mma missing from SASS"
+    assert "UTMALDG" in out, "TMA loads missing from SASS"
+    assert "LDTM" in out, "tcgen05.ld missing from SASS"
+    assert "sm_100a" in out or "sm_100" in out

@@ -1,0 +1,163 @@
+"""GPU: the HBM-bound kernels through the C ABI against torch fp32 on the same inputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from disentangle_mlp_b200 import ops as o
+
+    return o
+
+
+@pytest.mark.parametrize("rows,c,dtype,act", [(8 * 4096, 32, torch.bfloat16, 2), (4096, 256, torch.bfloat16, 1),
+                                             (16, 2048, torch.float32, 1), (16, 16384, torch.float32, 1),
+                                             (1000, 64, torch.bfloat16, 0)])
+def test_batchnorm_forward_backward(ops, rows, c, dtype, act):
+    torch.manual_seed(0)
+    y = (torch.randn(rows, c, device="cuda") * 1.7 + 0.3).to(dtype)
+    gamma = torch.randn(c, device="cuda") * 0.1 + 1
+    beta = torch.randn(c, device="cuda") * 0.1
+    rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    nbt = torch.zeros((), dtype=torch.long, device="cuda")
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    sums = ops.bn_stats(y, rows, c)
+    ss, mi = ops.bn_finalize(sums, rows, c, gamma, beta, rm, rv, nbt)
+    out = ops.bn_apply_act(y, rows, c, ss, act, 0.2)
+    yr = y.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    z = F.batch_norm(yr, rm_ref, rv_ref, gr, br, training=True, momentum=0.1, eps=1e-5)
+    ref = {0: z, 1: F.relu(z), 2: F.leaky_relu(z, 0.2)}[act]
+    assert rel(out, ref) < 4e-3  # bf16 output rounding
+    assert rel(rm, rm_ref) < 1e-4 and rel(rv, rv_ref) < 1e-4 and int(nbt) == 1
+    dout = torch.randn(rows, c, device="cuda").bfloat16()
+    ref.backward(dout.float())
+    dg, db = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
+    dy, _ = ops.bn_backward(dout, y, rows, c, ss, mi, act, 0.2, dg, db)
+    assert rel(dy, yr.grad) < 6e-3
+    assert rel(dg, gr.grad) < 2e-3 and rel(db, br.grad) < 2e-3
+
+
+@pytest.mark.parametrize("stride", [1, 2])
+def test_im2col3(ops, stride):
+    x = torch.rand(3, 3, 64, 64, device="cuda") * 2 - 1
+    col = ops.im2col3(x, stride)
+    ref = F.unfold(x, 5, padding=2, stride=stride).transpose(1, 2).reshape(-1, 75)
+    assert torch.equal(col[:, :75].float(), ref.bfloat16().float())
+    assert float(col[:, 75:].abs().max()) == 0.0
+
+
+def test_layout_kernels(ops):
+    x = torch.randn(5, 64, 256, device="cuda").bfloat16()
+    assert torch.equal(ops.transpose(x, 5, 64, 256), x.transpose(1, 2).contiguous())
+    y = torch.randn(4, 64, 64, 3, device="cuda")
+    assert torch.equal(ops.nhwc3_to_nchw(y, 4, 64, 64, False), y.permute(0, 3, 1, 2).contiguous())
+    assert rel(ops.nhwc3_to_nchw(y, 4, 64, 64, True), torch.tanh(y).permute(0, 3, 1, 2)) < 1e-6
+    out = torch.tanh(y).permute(0, 3, 1, 2).contiguous()
+    dout = torch.randn_like(out)
+    bg = torch.zeros(3, device="cuda")
+    dy = ops.tanh_backward(dout, out, bg)
+    ref = dout * (1 - out * out)
+    assert rel(dy, ref) < 1e-6 and rel(bg, ref.sum((0, 2, 3))) < 1e-4
+
+
+def test_pack_conv_weights(ops):
+    w = torch.randn(64, 3, 5, 5, device="cuda")
+    wd, wu, wc = ops.pack_conv_weights(w, 64, 3, True, True, True)
+    wb = w.bfloat16()
+    assert torch.equal(wd, wb.reshape(64, 3, 25).permute(2, 0, 1).contiguous())
+    assert torch.equal(wu[:, :3, :], wb.reshape(64, 3, 25).permute(2, 1, 0).contiguous())
+    assert float(wu[:, 3:, :].float().abs().max()) == 0.0
+    assert torch.equal(wc[:, :75], wb.reshape(64, 75)) and float(wc[:, 75:].float().abs().max()) == 0.0
+
+
+def test_bias_act_and_backward(ops):
+    acc = torch.randn(32, 2048, device="cuda")
+    bias = torch.randn(2048, device="cuda")
+    o32, o16 = ops.bias_act(acc, 32, 2048, bias, 2, 0.2)
+    ref = F.leaky_relu(acc + bias, 0.2)
+    assert rel(o32, ref) < 1e-6 and rel(o16, ref) < 4e-3
+    dout = torch.randn_like(acc)
+    cs = torch.zeros(2048, device="cuda")
+    dpre = ops.act_backward(dout, o32, 32, 2048, 2, 0.2, cs)
+    refd = dout * torch.where(ref > 0, 1.0, 0.2)
+    assert rel(dpre, refd) < 4e-3 and rel(cs, refd.sum(0)) < 1e-4
+
+
+def test_head_and_reparam(ops):
+    feat = torch.randn(16, 2048, device="cuda")
+    w = (torch.randn(1, 2048, device="cuda") * 0.02).requires_grad_(True)
+    b = torch.zeros(1, device="cuda").requires_grad_(True)
+    fr = feat.clone().requires_grad_(True)
+    pref = torch.sigmoid(F.linear(fr, w, b)).squeeze()
+    prob = ops.head_forward(feat, w.detach(), b.detach())
+    assert rel(prob, pref) < 1e-5
+    dprob = torch.randn(16, device="cuda")
+    dfe = torch.randn(16, 2048, device="cuda")
+    (pref * dprob).sum().backward()
+    dw, db = torch.zeros_like(w), torch.zeros_like(b)
+    dfeat = ops.head_backward(dprob, prob, feat, dfe, w.detach(), dw, db)
+    assert rel(dfeat, fr.grad + dfe) < 1e-4 and rel(dw, w.grad) < 1e-4 and rel(db, b.grad) < 1e-4
+    mu, lv, eps = (torch.randn(16, 128, device="cuda") for _ in range(3))
+    z, z16 = ops.reparam_forward(mu, lv, eps)
+    assert rel(z, mu + eps * torch.exp(0.5 * lv)) < 1e-6 and rel(z16, z) < 4e-3
+    dz = torch.randn_like(mu)
+    _, _, dmu, dlv = ops.reparam_backward(dz, lv, eps)
+    assert rel(dmu, dz) < 1e-6 and rel(dlv, dz * eps * 0.5 * torch.exp(0.5 * lv)) < 1e-6
+
+
+def test_losses(ops):
+    a, b = torch.randn(8, 3, 64, 64, device="cuda"), torch.randn(8, 3, 64, 64, device="cuda")
+    loss = torch.zeros((), device="cuda")
+    g = torch.empty_like(a)
+    ops.mse_sum(a, b, loss, 0.5, g, 0.5)
+    assert abs(float(loss) - 0.5 * float(F.mse_loss(a, b, reduction="sum"))) < 1e-3 * float(loss)
+    assert rel(g, a - b) < 1e-6
+    mu, lv = torch.randn(8, 128, device="cuda"), torch.randn(8, 128, device="cuda")
+    loss.zero_()
+    dmu, dlv = torch.empty_like(mu), torch.empty_like(mu)
+    ops.kl(mu, lv, loss, 25.0, dmu, dlv)
+    mr, lr = mu.clone().requires_grad_(True), lv.clone().requires_grad_(True)
+    ref = 25.0 * (-0.5 * torch.sum(1 + lr - mr.pow(2) - lr.exp()))
+    ref.backward()
+    assert abs(float(loss) - float(ref)) < 1e-4 * abs(float(ref))
+    assert rel(dmu, mr.grad) < 1e-6 and rel(dlv, lr.grad) < 1e-6
+    for target in (0.9, 0.1):
+        p = torch.rand(64, device="cuda") * 0.98 + 0.01
+        p[0], p[1] = 1.0, 0.0  # saturated outputs: log clamped at -100 (nn.BCELoss)
+        pr = p.clone().requires_grad_(True)
+        refl = F.binary_cross_entropy(pr, torch.full((64,), target, device="cuda"))
+        refl.backward()
+        loss.zero_()
+        dp = torch.empty_like(p)
+        stat = torch.zeros((), device="cuda")
+        ops.bce_const(p, target, loss, dprob=dp, stat=stat)
+        assert abs(float(loss) - float(refl)) < 1e-5 * abs(float(refl))
+        assert rel(dp, pr.grad) < 1e-5 and abs(float(stat) - float(p.sum())) < 1e-3
+
+
+def test_adam_matches_torch(ops):
+    torch.manual_seed(0)
+    n = 100003
+    p = torch.randn(n, device="cuda")
+    ref = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-3)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    shadow = torch.empty(n, dtype=torch.bfloat16, device="cuda")
+    for step in range(1, 6):
+        g = torch.randn(n, device="cuda")
+        ref.grad = g.clone()
+        opt.step()
+        ops.adam_step(p, g, m, v, 1e-3, 0.9, 0.999, 1e-8, step, 1.0, shadow)
+    assert rel(p, ref.detach()) < 1e-6
+    assert torch.equal(shadow, p.bfloat16())
+    st = opt.state[ref]
+    assert rel(m, st["exp_avg"]) < 1e-6 and rel(v, st["exp_avg_sq"]) < 1e-6

@@ -1,0 +1,52 @@
+"""GPU: every mode of the tcgen05 tap-GEMM kernel through the C ABI against torch (fp32 math on the same bf16
+inputs).  Tolerances: fp32 outputs 1e-4 relative-L2 (accumulation order only), bf16 outputs 4e-3 (one bf16
+rounding of the result: 2^-9 per element)."""
+import os
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+import probe_gemm  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+BF16_OUT = {"nt_bf16out", "nt_k128_n32", "nn_64x16384x2048"}
+
+
+@pytest.mark.parametrize("name", list(probe_gemm.CASES))
+def test_case(name):
+    rel, _ = probe_gemm.CASES[name]()
+    bf16_out = name in BF16_OUT or (name.startswith(("down_", "up_")) and "f32" not in name)
+    assert rel < (4e-3 if bf16_out else 1e-4), (name, rel)
+
+
+def test_full_size_layers_linearity_and_batch_independence():
+    """Full BASELINE sizes (batch 128): conv(x1 + x2) == conv(x1) + conv(x2) on bf16-exact inputs, and the
+    result for image i does not depend on the other images in the batch."""
+    import torch
+
+    from disentangle_mlp_b200 import ops
+
+    torch.manual_seed(1)
+    b = 128
+    g = ops.geom(b, 16, 16, 256, 128, 2)
+    x1 = torch.randint(-4, 5, (b, 32, 32, 128), device="cuda").float()
+    x2 = torch.randint(-4, 5, (b, 32, 32, 128), device="cuda").float()
+    # integers up to |8| and weights with few mantissa bits keep every product and partial sum exact in fp32
+    wq = (torch.randint(-3, 4, (256, 128, 5, 5), device="cuda").float() / 8)
+    wd, wu, _ = ops.pack_conv_weights(wq, 256, 128)
+    y1 = ops.conv_down(g, x1.bfloat16(), wd).float()
+    y2 = ops.conv_down(g, x2.bfloat16(), wd).float()
+    y12 = ops.conv_down(g, (x1 + x2).bfloat16(), wd).float()
+    assert torch.equal(y12, (y1 + y2).bfloat16().float()) or (y12 - (y1 + y2)).abs().max() <= 2 ** -7 * y12.abs().max()
+    g1 = ops.geom(2, 16, 16, 256, 128, 2)
+    ysub = ops.conv_down(g1, x1[5:7].bfloat16().contiguous(), wd).float()
+    assert torch.equal(ysub, y1[5:7])
+    # transposed convolution is the adjoint: <conv_down(x), s> == <x, conv_up(s)> (exact integers)
+    s = torch.randint(-2, 3, (b, 16, 16, 256), device="cuda").float()
+    up = ops.conv_up(g, s.bfloat16(), wu, out_f32=True)
+    y = ops.conv_down(g, x1.bfloat16(), wd).double()
+    lhs, rhs = (y * s.double()).sum(), (x1.double() * up.double()).sum()
+    # y carries one bf16 rounding (2^-9 relative per element); the sums cancel, so bound by the sum of magnitudes
+    assert abs(float(lhs - rhs)) <= 2 ** -8 * float((y.abs() * s.abs().double()).sum())

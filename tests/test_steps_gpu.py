@@ -1,0 +1,105 @@
+"""GPU: the fused trainers (disentangle_mlp_b200/trainer.py) against the oracle's restated reference steps on
+identical weights, data, noise, eps and labels."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def params_rel(mine, ref):
+    a = torch.cat([p.detach().flatten().cpu() for p in mine.parameters()])
+    b = torch.cat([p.detach().flatten() for p in ref.parameters()])
+    return float((a - b).norm() / b.norm())
+
+
+@pytest.fixture(scope="module")
+def mods():
+    from disentangle_mlp_b200 import model as dm
+    from disentangle_mlp_b200 import trainer as tr
+    from oracle import nets, steps
+
+    return dm, tr, nets, steps
+
+
+def test_vae_trainer_tracks_oracle(mods):
+    dm, tr, nets, steps = mods
+    b, opt = 16, steps.make_opt()
+    x = steps.synthetic_batch(b, 1234)
+    torch.manual_seed(999)
+    ref = nets.VAE(opt)
+    ref.apply(nets.weights_init)
+    mine = dm.VAE(opt).cuda()
+    mine.load_state_dict(ref.state_dict())
+    o = torch.optim.Adam(ref.parameters(), lr=3e-4)
+    T = tr.VAETrainer(mine, lr=3e-4)
+    for s in range(5):
+        eps = torch.randn(b, 128, generator=torch.Generator().manual_seed(90 + s))
+        r = steps.vae_step(ref, o, x, eps)
+        m = float(T.step(x.cuda(), eps.cuda())["loss"])
+        assert abs(m - r["loss"]) <= 1e-2 * r["loss"], (s, m, r["loss"])
+    assert params_rel(mine, ref) < 3e-2
+    assert int(mine.features[1].num_batches_tracked) == 5
+
+
+def test_gan_trainer_tracks_oracle(mods):
+    dm, tr, nets, steps = mods
+    b, opt = 16, steps.make_opt()
+    x = steps.synthetic_batch(b, 1234)
+    torch.manual_seed(999)
+    rG, rD = nets.Generator_celeba(opt), nets.Discriminator_celeba(opt)
+    rG.apply(nets.weights_init)
+    rD.apply(nets.weights_init)
+    mG, mD = dm.Generator_celeba(opt).cuda(), dm.Discriminator_celeba(opt).cuda()
+    mG.load_state_dict(rG.state_dict())
+    mD.load_state_dict(rD.state_dict())
+    oG, oD = torch.optim.Adam(rG.parameters(), lr=3e-4), torch.optim.Adam(rD.parameters(), lr=3e-4)
+    T = tr.GANTrainer(mG, mD, lr=3e-4)
+    np.random.seed(999)
+    for s in range(3):
+        real, fake = steps.draw_labels()
+        noise = torch.randn(b, 128, generator=torch.Generator().manual_seed(70 + s))
+        r = steps.gan_step(rG, rD, oG, oD, x, real, fake, noise)
+        m = {k: float(v) for k, v in T.step(x.cuda(), real, fake, noise.cuda()).items()}
+        assert abs(m["errD"] - r["errD"]) <= 3e-2 * abs(r["errD"]), (s, m, r)
+        assert abs(m["errG"] - r["errG"]) <= 3e-2 * abs(r["errG"]), (s, m, r)
+    assert params_rel(mG, rG) < 2e-2 and params_rel(mD, rD) < 5e-2
+    assert int(mD.convs[1].num_batches_tracked) == 9  # three D forwards per step
+
+
+def test_betavaegan_trainer_first_step_and_counters(mods):
+    dm, tr, nets, steps = mods
+    b, opt = 16, steps.make_opt()
+    x = steps.synthetic_batch(b, 1234)
+    torch.manual_seed(999)
+    rEG, rD = nets.VAE(opt), nets.Discriminator_celeba(opt)
+    rEG.apply(nets.weights_init)
+    rD.apply(nets.weights_init)
+    mEG, mD = dm.VAE(opt).cuda(), dm.Discriminator_celeba(opt).cuda()
+    mEG.load_state_dict(rEG.state_dict())
+    mD.load_state_dict(rD.state_dict())
+    oEG, oD = torch.optim.Adam(rEG.parameters(), lr=1e-3), torch.optim.Adam(rD.parameters(), lr=1e-3)
+    T = tr.BetaVAEGANTrainer(mEG, mD, beta=25.0, lr=1e-3)
+    g = torch.Generator().manual_seed(50)
+    noise, e1, e2 = (torch.randn(b, 128, generator=g) for _ in range(3))
+    r = steps.betavaegan_step(rEG, rD, oEG, oD, x, 25.0, 0.9, 0.1, noise, e1, e2)
+    m = {k: float(v) for k, v in T.step(x.cuda(), 0.9, 0.1, noise.cuda(), e1.cuda(), e2.cuda()).items()}
+    # quantities computed before any parameter update: pure bf16 forward error
+    for k in ("errD_real", "errD_fake", "D_x"):
+        assert abs(m[k] - r[k]) <= 5e-3 * abs(r[k]), (k, m[k], r[k])
+    # after the D update / the first EG update (Adam's first step is lr*sign(g): sensitive to tiny gradients)
+    for k, tol in (("errG_fake", 2e-2), ("errG_recon", 2e-2), ("sim", 5e-2), ("recon_dec", 2e-2), ("kld", 0.15),
+                   ("recon_enc", 5e-2)):
+        assert abs(m[k] - r[k]) <= tol * abs(r[k]), (k, m[k], r[k])
+    # update order / counts: D stepped once, EG twice; BN running stats D 5x, encoder 2x, decoder 3x
+    assert T.fd.step_count == 1 and T.feg.step_count == 2
+    assert int(mD.convs[1].num_batches_tracked) == 5
+    assert int(mEG.features[1].num_batches_tracked) == 2 and int(mEG.act1[0].num_batches_tracked) == 3
+    # every encoder AND decoder parameter moved in the EG updates; Adam state interchange
+    sd = T.feg.optimizer_state_dict()
+    assert len(sd["state"]) == 42 and all(float(s["exp_avg_sq"].sum()) >= 0 for s in sd["state"].values())
+    ref_sd = oEG.state_dict()
+    assert list(sd["param_groups"][0]["params"]) == list(ref_sd["param_groups"][0]["params"])
+    moved = [n for n, p in mEG.named_parameters() if not n.endswith(".bias") or "act" in n or ".1." in n]
+    init = dict(nets.VAE(opt).named_parameters())
+    assert params_rel(mEG, rEG) < 0.1 and params_rel(mD, rD) < 0.1
