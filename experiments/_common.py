@@ -1,0 +1,74 @@
+"""Shared glue of the three training scripts: flags (a subset of the reference's EnvSetter flags with the same
+names and defaults, utils/envsetter.py:13-55), torchrun set-up, a synthetic CelebA-shaped loader, checkpoints."""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def parse(desc):
+    p = argparse.ArgumentParser(description=desc)
+    p.add_argument("--name", required=True)
+    p.add_argument("--seed", type=int, default=999)
+    p.add_argument("--batch_size_train", type=int, default=256, help="GLOBAL batch (split across ranks)")
+    p.add_argument("--n_z", type=int, nargs=3, default=[256, 8, 8])
+    p.add_argument("--n_hidden", type=int, default=128)
+    p.add_argument("--input_channels", type=int, default=3)
+    p.add_argument("--lr", type=float, default=3e-3)
+    p.add_argument("--beta", type=float, default=50)
+    p.add_argument("--epochs", type=int, default=30)
+    p.add_argument("--steps_per_epoch", type=int, default=100, help="synthetic data: steps per epoch")
+    p.add_argument("--log_interval", type=int, default=10)
+    p.add_argument("--model_path", default=None, help="directory for model_<epoch>.tar checkpoints")
+    p.add_argument("--load_path", default=None)
+    p.add_argument("--data_path", default=None, help="optional uint8 [N,64,64,3] .npy shard; default synthetic U[-1,1]")
+    return p.parse_args()
+
+
+def setup_dist():
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("no CUDA device: these scripts have no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return world, rank, torch.device("cuda", local)
+
+
+class Loader:
+    """Per-rank shard of a CelebA-shaped stream in [-1, 1] (dataloader/dataset.py:37-50 after Normalize(.5,.5))."""
+
+    def __init__(self, opt, world, rank, dev):
+        self.b = opt.batch_size_train // world
+        self.steps, self.dev = opt.steps_per_epoch, dev
+        self.gen = torch.Generator().manual_seed(1234 + rank)
+        self.data = None
+        if opt.data_path:
+            arr = np.load(opt.data_path, mmap_mode="r")
+            self.data = arr[rank::world]
+            self.steps = len(self.data) // self.b
+        self.dataset_len = self.steps * self.b * world
+
+    def __len__(self):
+        return self.steps
+
+    def __iter__(self):
+        for i in range(self.steps):
+            if self.data is None:
+                x = torch.rand(self.b, 3, 64, 64, generator=self.gen) * 2 - 1
+            else:
+                u8 = torch.from_numpy(np.ascontiguousarray(self.data[i * self.b:(i + 1) * self.b]))
+                x = (u8.permute(0, 3, 1, 2).float() / 255.0 - 0.5) / 0.5
+            yield x.pin_memory().to(self.dev, non_blocking=True)

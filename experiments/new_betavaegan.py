@@ -1,0 +1,60 @@
+"""beta-VAE-GAN training on the B200 kernels — counterpart of the reference's experiments/new_betavaegan.py.
+Same models, losses, update order and checkpoint keys (:222-228); the loop body is
+disentangle_mlp_b200.trainer.BetaVAEGANTrainer.step.  lr is hard-coded to 1e-3 as in the reference (:49-50).
+
+    python experiments/new_betavaegan.py --name run --beta 25 --batch_size_train 64
+    torchrun --nproc-per-node 8 experiments/new_betavaegan.py --name run --beta 25 --batch_size_train 512
+"""
+import os
+
+import numpy as np
+import torch
+
+from _common import Loader, parse, setup_dist
+
+from disentangle_mlp_b200 import model as dm
+from disentangle_mlp_b200.trainer import BetaVAEGANTrainer
+
+
+def main():
+    opt = parse("vaegan")
+    world, rank, dev = setup_dist()
+    torch.manual_seed(opt.seed)
+    np.random.seed(opt.seed)  # the label stream must be identical on every rank
+    netEG, netD = dm.VAE(opt).to(dev), dm.Discriminator_celeba(opt).to(dev)
+    netEG.apply(dm.weights_init)
+    netD.apply(dm.weights_init)
+    T = BetaVAEGANTrainer(netEG, netD, beta=opt.beta, lr=1e-3)
+    start = 0
+    if opt.load_path:
+        ck = torch.load(opt.load_path, map_location=dev)
+        netEG.load_state_dict(ck["encoder_decoder_model"])
+        netD.load_state_dict({k.removeprefix("module."): v for k, v in ck["discriminator_model"].items()})
+        T.feg.load_optimizer_state_dict(ck["encoder_decoder_optimizer"])
+        T.fd.load_optimizer_state_dict(ck["discriminator_optimizer"])
+        T.feg.params_changed()
+        T.fd.params_changed()
+        start = ck["epoch"]
+    loader = Loader(opt, world, rank, dev)
+    for epoch in range(start, opt.epochs):
+        sums = None
+        for i, data in enumerate(loader):
+            m = T.step(data)
+            vals = torch.stack([m["recon_enc"], m["recon_dec"], m["D_x"]])
+            sums = vals if sums is None else sums + vals  # accumulated on the device: no per-step host sync
+            if rank == 0 and i % opt.log_interval == 0:
+                print(f"epoch {epoch} step {i}: " + " ".join(f"{k}={float(v):.4f}" for k, v in m.items()), flush=True)
+        enc, dec, dx = (float(v) / loader.dataset_len * world for v in sums)
+        if rank == 0:
+            print(f"====> Epoch: {epoch} Avg Encoder Loss: {enc:.4f} Avg Decoder Loss: {dec:.4f} Dx: {dx:.4f}")
+            if opt.model_path:
+                os.makedirs(opt.model_path, exist_ok=True)
+                torch.save({"epoch": epoch + 1, "encoder_decoder_model": netEG.state_dict(),
+                            "discriminator_model": {"module." + k: v for k, v in netD.state_dict().items()},
+                            "encoder_decoder_optimizer": T.feg.optimizer_state_dict(),
+                            "discriminator_optimizer": T.fd.optimizer_state_dict()},
+                           os.path.join(opt.model_path, f"model_{epoch + 1}.tar"))
+
+
+if __name__ == "__main__":
+    main()
