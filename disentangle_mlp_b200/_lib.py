@@ -35,19 +35,21 @@ _SIGS = {
     "dm_gemm_bf16": [C.POINTER(GemmDesc), c_void_p],
     "dm_conv_down": [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "dm_conv_up": [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
-    "dm_conv_wgrad": [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_void_p],
+    "dm_conv_wgrad": [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+    "dm_unpack_conv_grad": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "dm_profile_enable": [c_int],
     "dm_profile_read": [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(c_ll)],
     "dm_debug_last_plan": [C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int)],
+    "dm_bn_parts": [c_ll, c_int],
     "dm_bn_stats": [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p],
-    "dm_bn_finalize": [c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float,
-                       c_void_p, c_void_p, c_void_p],
+    "dm_bn_finalize": [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+                       c_float, c_void_p, c_void_p, c_void_p],
     "dm_bn_apply_act": [c_void_p, c_int, c_ll, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p],
     "dm_bn_backward": [c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_int, c_float, c_void_p,
-                       c_void_p, c_void_p, c_void_p, c_void_p],
+                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "dm_bias_act": [c_void_p, c_ll, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p],
-    "dm_act_backward": [c_void_p, c_void_p, c_ll, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p],
-    "dm_colsum": [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p],
+    "dm_act_backward": [c_void_p, c_void_p, c_ll, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p],
+    "dm_colsum": [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p],
     "dm_im2col3": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "dm_nhwc3_to_nchw": [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p],
     "dm_tanh_backward": [c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p],

@@ -84,7 +84,7 @@ static RowLayout make_row_layout(long long rows, int c) {
   if (l.tx < 1) l.tx = 1;
   l.ty = 256 / l.tx;
   l.gx = (cv + l.tx - 1) / l.tx;
-  long long want = std::max<long long>(1, (148ll * 8) / l.gx);  // ~8 blocks per SM overall
+  long long want = std::max<long long>(1, (148ll * 2) / l.gx);  // ~2 fat blocks per SM: few partial vectors
   long long rpb = (rows + want - 1) / want;
   rpb = std::max<long long>(l.ty, (rpb + l.ty - 1) / l.ty * l.ty);
   l.rows_per_block = rpb;
@@ -93,7 +93,8 @@ static RowLayout make_row_layout(long long rows, int c) {
 }
 
 // ------------------------------------------------------------------------------------------ BN statistics
-// sums[0][c] += sum_r y[r][c], sums[1][c] += sum_r y[r][c]^2      (sums must be zeroed by the caller)
+// Row reduction skeleton: every block reduces its row range and writes ONE partial vector
+//   out[(blockIdx.y * NACC + a) * c + channel]        (no atomics: the consumer sums the gridDim.y partials)
 template <typename T, int NACC, typename F>
 __device__ __forceinline__ void rows_reduce(long long rows, int c, long long rows_per_block, float* out, F&& body) {
   extern __shared__ float red[];  // [ty][tx*8*NACC]
@@ -107,19 +108,50 @@ __device__ __forceinline__ void rows_reduce(long long rows, int c, long long row
     for (int i = 0; i < 8; ++i) acc[a][i] = 0.f;
   const long long r0 = blockIdx.y * rows_per_block;
   const long long r1 = min(rows, r0 + rows_per_block);
-  if (live)
+  if (live) {
+#pragma unroll 2
     for (long long r = r0 + threadIdx.y; r < r1; r += ty) body(r, cv * 8, acc);
+  }
   float* mine = red + (threadIdx.y * tx + threadIdx.x) * (8 * NACC);
 #pragma unroll
   for (int a = 0; a < NACC; ++a)
 #pragma unroll
     for (int i = 0; i < 8; ++i) mine[a * 8 + i] = acc[a][i];
   __syncthreads();
-  // column reduction over ty: thread (x, y) sums entries j = y, y+ty.. of the 8*NACC values
   for (int j = threadIdx.y; j < 8 * NACC; j += ty) {
     float s = 0.f;
     for (int y = 0; y < ty; ++y) s += red[(y * tx + threadIdx.x) * (8 * NACC) + j];
-    if (live) atomicAdd(out + (j / 8) * c + cv * 8 + (j % 8), s);
+    if (live) out[(static_cast<long long>(blockIdx.y) * NACC + (j / 8)) * c + cv * 8 + (j % 8)] = s;
+  }
+}
+
+// Block-cooperative sum over partial vectors: blockDim = (32, 32); thread (x, y) accumulates partials
+// y, y+32, ... of element i = blockIdx.x*32 + x for NV consecutive groups (stride `gstride` elements), then the
+// 32 y-lanes are reduced through shared memory.  Result valid in threads with y == 0.
+template <int NV>
+__device__ __forceinline__ void sum_partials_block(const float* __restrict__ partials, int nparts, long long n,
+                                                   int i, bool live, int gstride, float (&out)[NV]) {
+  __shared__ float red[NV][32][33];
+  float acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) acc[v] = 0.f;
+  if (live) {
+#pragma unroll 4
+    for (int p = threadIdx.y; p < nparts; p += 32) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) acc[v] += partials[static_cast<long long>(p) * n + v * gstride + i];
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) red[v][threadIdx.y][threadIdx.x] = acc[v];
+  __syncthreads();
+  if (threadIdx.y == 0) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      float s = 0.f;
+      for (int y = 0; y < 32; ++y) s += red[v][y][threadIdx.x];
+      out[v] = s;
+    }
   }
 }
 
@@ -139,17 +171,22 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ y, 
 
 // Per-channel finalize: normalisation constants + running-stat update (momentum, unbiased running var),
 // matching torch.nn.BatchNorm{1,2}d in training mode (models/model.py:451-457,462,468,492,496-504,390-399).
-__global__ void bn_finalize_kernel(const float* __restrict__ sums, long long rows, int c,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   float* __restrict__ running_mean, float* __restrict__ running_var,
-                                   long long* __restrict__ num_batches_tracked, float momentum, float eps,
-                                   float* __restrict__ scale_shift, float* __restrict__ mean_invstd) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ partials, int nparts, long long rows,
+                                                            int c, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float* __restrict__ running_mean,
+                                                            float* __restrict__ running_var,
+                                                            long long* __restrict__ num_batches_tracked, float momentum,
+                                                            float eps, float* __restrict__ scale_shift,
+                                                            float* __restrict__ mean_invstd) {
+  const int ch = blockIdx.x * 32 + threadIdx.x;
+  float sum[2];
+  sum_partials_block<2>(partials, nparts, 2ll * c, ch, ch < c, c, sum);
+  if (threadIdx.y != 0) return;
   if (ch == 0 && num_batches_tracked) *num_batches_tracked += 1;
   if (ch >= c) return;
   const double n = static_cast<double>(rows);
-  const double mean = sums[ch] / n;
-  double var = sums[c + ch] / n - mean * mean;
+  const double mean = sum[0] / n;
+  double var = sum[1] / n - mean * mean;
   if (var < 0.0) var = 0.0;
   const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
   const float sc = gamma[ch] * invstd;
@@ -254,13 +291,29 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
   }
 }
 
-// dgamma += sums[1], dbeta += sums[0]  (accumulating, like autograd's AccumulateGrad)
-__global__ void bn_param_grad_kernel(const float* __restrict__ sums, int c, float* __restrict__ dgamma,
-                                     float* __restrict__ dbeta) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
-  dgamma[ch] += sums[c + ch];
-  dbeta[ch] += sums[ch];
+// sums[0][c] = sum dz, sums[1][c] = sum dz*xhat from the block partials; dgamma += sums[1], dbeta += sums[0]
+// (accumulating, like autograd's AccumulateGrad)
+__global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __restrict__ partials, int nparts, int c,
+                                                                float* __restrict__ sums, float* __restrict__ dgamma,
+                                                                float* __restrict__ dbeta) {
+  const int ch = blockIdx.x * 32 + threadIdx.x;
+  float sum[2];
+  sum_partials_block<2>(partials, nparts, 2ll * c, ch, ch < c, c, sum);
+  if (threadIdx.y != 0 || ch >= c) return;
+  sums[ch] = sum[0];
+  sums[c + ch] = sum[1];
+  if (dgamma) dgamma[ch] += sum[1];
+  if (dbeta) dbeta[ch] += sum[0];
+}
+
+// out[i] (+)= sum_p partials[p][i]
+__global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __restrict__ partials, int nparts, int n,
+                                                                int accumulate, float* __restrict__ out) {
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  float sum[1];
+  sum_partials_block<1>(partials, nparts, n, i, i < n, 0, sum);
+  if (threadIdx.y != 0 || i >= n) return;
+  out[i] = accumulate ? out[i] + sum[0] : sum[0];
 }
 
 // ------------------------------------------------------------------------------------------ bias + activation
@@ -441,6 +494,32 @@ __global__ void __launch_bounds__(256) pack_conv_kernel(const float* __restrict_
     {
       const int k = static_cast<int>(j % 128), s = static_cast<int>(j / 128);
       w_col[j] = __float2bfloat16_rn(k < cb * 25 ? w[static_cast<long long>(s) * cb * 25 + k] : 0.f);
+    }
+  }
+}
+
+// tap-major packed conv gradient [25][n] -> master layout [n][25] (n = cs*cb); dw (+)= ; the packed buffer is
+// re-zeroed so that the next backward pass can accumulate into it again
+__global__ void __launch_bounds__(256) unpack_conv_grad_kernel(float* __restrict__ packed, long long n, int accumulate,
+                                                               float* __restrict__ dw) {
+  constexpr int W = 128;  // elements of n per block
+  __shared__ float tile[25][W + 1];
+  const long long i0 = static_cast<long long>(blockIdx.x) * W;
+  for (int j = threadIdx.x; j < 25 * W; j += 256) {
+    const int t = j / W, ii = j - t * W;
+    float v = 0.f;
+    if (i0 + ii < n) {
+      v = packed[t * n + i0 + ii];
+      packed[t * n + i0 + ii] = 0.f;
+    }
+    tile[t][ii] = v;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < 25 * W; j += 256) {
+    const int ii = j / 25, t = j - ii * 25;
+    if (i0 + ii < n) {
+      float* dst = dw + (i0 + ii) * 25 + t;
+      *dst = accumulate ? *dst + tile[t][ii] : tile[t][ii];
     }
   }
 }
@@ -654,25 +733,26 @@ typedef __nv_bfloat16 bf16;
 
 #define DM_CHECK_C8(c, who) DM_REQUIRE((c) % 8 == 0, who ": channel count %d must be a multiple of 8", (c))
 
-extern "C" int dm_bn_stats(const void* y, int y_f32, long long rows, int c, float* sums, void* stream_) {
+extern "C" int dm_bn_parts(long long rows, int c) { return make_row_layout(rows, c).gy; }
+
+extern "C" int dm_bn_stats(const void* y, int y_f32, long long rows, int c, float* partials, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   DM_CHECK_C8(c, "dm_bn_stats");
-  cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(float) * 2 * c, s);
-  if (e != cudaSuccess) return set_error((int)e, "dm_bn_stats memset: %s", cudaGetErrorString(e));
   RowLayout l = make_row_layout(rows, c);
   const size_t sm = sizeof(float) * 256 * 16;
   if (y_f32)
-    bn_stats_kernel<float><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s>>>(static_cast<const float*>(y), rows, c, l.rows_per_block, sums);
+    bn_stats_kernel<float><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s>>>(static_cast<const float*>(y), rows, c, l.rows_per_block, partials);
   else
-    bn_stats_kernel<bf16><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s>>>(static_cast<const bf16*>(y), rows, c, l.rows_per_block, sums);
+    bn_stats_kernel<bf16><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s>>>(static_cast<const bf16*>(y), rows, c, l.rows_per_block, partials);
   DM_LAUNCHED("dm_bn_stats");
 }
 
-extern "C" int dm_bn_finalize(const float* sums, long long rows, int c, const float* gamma, const float* beta,
-                              float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
-                              float eps, float* scale_shift, float* mean_invstd, void* stream_) {
+extern "C" int dm_bn_finalize(const float* partials, int nparts, long long rows, int c, const float* gamma,
+                              const float* beta, float* running_mean, float* running_var,
+                              long long* num_batches_tracked, float momentum, float eps, float* scale_shift,
+                              float* mean_invstd, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-  bn_finalize_kernel<<<(c + 255) / 256, 256, 0, s>>>(sums, rows, c, gamma, beta, running_mean, running_var,
+  bn_finalize_kernel<<<(c + 31) / 32, dim3(32, 32), 0, s>>>(partials, nparts, rows, c, gamma, beta, running_mean, running_var,
                                                      num_batches_tracked, momentum, eps, scale_shift, mean_invstd);
   DM_LAUNCHED("dm_bn_finalize");
 }
@@ -690,27 +770,23 @@ extern "C" int dm_bn_apply_act(const void* y, int y_f32, long long rows, int c, 
 }
 
 extern "C" int dm_bn_backward(const void* dout_bf16, const void* y, int y_f32, long long rows, int c,
-                              const float* scale_shift, const float* mean_invstd, int act, float slope, float* sums,
-                              void* dy_bf16, float* dgamma, float* dbeta, void* stream_) {
+                              const float* scale_shift, const float* mean_invstd, int act, float slope,
+                              float* partials, float* sums, void* dy_bf16, float* dgamma, float* dbeta, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   DM_CHECK_C8(c, "dm_bn_backward");
-  cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(float) * 2 * c, s);
-  if (e != cudaSuccess) return set_error((int)e, "dm_bn_backward memset: %s", cudaGetErrorString(e));
   RowLayout l = make_row_layout(rows, c);
   const size_t sm = sizeof(float) * 256 * 16;
   const bf16* d = static_cast<const bf16*>(dout_bf16);
-  if (y_f32) {
-    bn_bwd_reduce_kernel<float><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s>>>(d, static_cast<const float*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, act, slope, sums);
+  if (y_f32)
+    bn_bwd_reduce_kernel<float><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s>>>(d, static_cast<const float*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, act, slope, partials);
+  else
+    bn_bwd_reduce_kernel<bf16><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s>>>(d, static_cast<const bf16*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, act, slope, partials);
+  bn_bwd_finalize_kernel<<<(c + 31) / 32, dim3(32, 32), 0, s>>>(partials, l.gy, c, sums, dgamma, dbeta);
+  if (y_f32)
     bn_bwd_apply_kernel<float><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), 0, s>>>(d, static_cast<const float*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, sums, act, slope, static_cast<bf16*>(dy_bf16));
-  } else {
-    bn_bwd_reduce_kernel<bf16><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s>>>(d, static_cast<const bf16*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, act, slope, sums);
+  else
     bn_bwd_apply_kernel<bf16><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), 0, s>>>(d, static_cast<const bf16*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, sums, act, slope, static_cast<bf16*>(dy_bf16));
-  }
-  g_launch_count.fetch_add(2, std::memory_order_relaxed);
-  if (dgamma && dbeta) {
-    bn_param_grad_kernel<<<(c + 255) / 256, 256, 0, s>>>(sums, c, dgamma, dbeta);
-    g_launch_count.fetch_add(1, std::memory_order_relaxed);
-  }
+  g_launch_count.fetch_add(3, std::memory_order_relaxed);
   return check_launch("dm_bn_backward");
 }
 
@@ -724,24 +800,31 @@ extern "C" int dm_bias_act(const float* acc, long long rows, int c, const float*
 }
 
 extern "C" int dm_act_backward(const float* dout, const float* out, long long rows, int c, int act, float slope,
-                               void* dpre_bf16, float* colsum, void* stream_) {
+                               void* dpre_bf16, float* partials, float* colsum, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   DM_CHECK_C8(c, "dm_act_backward");
   RowLayout l = make_row_layout(rows, c);
-  act_bwd_colsum_kernel<<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), sizeof(float) * 256 * 8, s>>>(dout, out, rows, c, l.rows_per_block, act, slope, static_cast<bf16*>(dpre_bf16), colsum);
-  DM_LAUNCHED("dm_act_backward");
+  act_bwd_colsum_kernel<<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), sizeof(float) * 256 * 8, s>>>(dout, out, rows, c, l.rows_per_block, act, slope, static_cast<bf16*>(dpre_bf16), partials);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  if (colsum) {
+    reduce_partials_kernel<<<(c + 31) / 32, dim3(32, 32), 0, s>>>(partials, l.gy, c, 1, colsum);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  }
+  return check_launch("dm_act_backward");
 }
 
-extern "C" int dm_colsum(const void* x, int x_f32, long long rows, int c, float* colsum, void* stream_) {
+extern "C" int dm_colsum(const void* x, int x_f32, long long rows, int c, float* partials, float* colsum, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   DM_CHECK_C8(c, "dm_colsum");
   RowLayout l = make_row_layout(rows, c);
   const size_t sm = sizeof(float) * 256 * 8;
   if (x_f32)
-    colsum_kernel<float><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s>>>(static_cast<const float*>(x), rows, c, l.rows_per_block, colsum);
+    colsum_kernel<float><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s>>>(static_cast<const float*>(x), rows, c, l.rows_per_block, partials);
   else
-    colsum_kernel<bf16><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s>>>(static_cast<const bf16*>(x), rows, c, l.rows_per_block, colsum);
-  DM_LAUNCHED("dm_colsum");
+    colsum_kernel<bf16><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s>>>(static_cast<const bf16*>(x), rows, c, l.rows_per_block, partials);
+  reduce_partials_kernel<<<(c + 31) / 32, dim3(32, 32), 0, s>>>(partials, l.gy, c, 1, colsum);
+  g_launch_count.fetch_add(2, std::memory_order_relaxed);
+  return check_launch("dm_colsum");
 }
 
 extern "C" int dm_im2col3(const float* x_nchw, int batch, int h, int w, int stride, void* col_bf16, void* stream_) {
@@ -779,6 +862,13 @@ extern "C" int dm_pack_conv_weights(const float* w, int cs, int cb, void* w_down
   const long long total = 25ll * cs * cb + 25ll * cb_pad * cs + 128ll * cs;
   pack_conv_kernel<<<grid_for(total), 256, 0, s>>>(w, cs, cb, cb_pad, static_cast<bf16*>(w_down), static_cast<bf16*>(w_up), static_cast<bf16*>(w_col));
   DM_LAUNCHED("dm_pack_conv_weights");
+}
+
+extern "C" int dm_unpack_conv_grad(float* packed, int cs, int cb, int accumulate, float* dw, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  const long long n = static_cast<long long>(cs) * cb;
+  unpack_conv_grad_kernel<<<static_cast<unsigned>((n + 127) / 128), 256, 0, s>>>(packed, n, accumulate, dw);
+  DM_LAUNCHED("dm_unpack_conv_grad");
 }
 
 extern "C" int dm_cast_bf16(const float* src, long long n, void* dst, void* stream_) {

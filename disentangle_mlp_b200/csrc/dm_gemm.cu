@@ -37,6 +37,8 @@ struct Tap {
   int8_t dw, dp, dh;
   uint8_t wt;      // weight tap index (B coordinate 2 in MODE_FWD)
   int16_t nvalid;  // MODE_WGRAD: valid columns of this tap unit
+  int16_t mvalid;  // MODE_WGRAD: valid rows of this tap unit
+  int16_t pad_;
   int32_t out_off; // MODE_WGRAD: element offset of this tap unit in the output
 };
 
@@ -52,7 +54,10 @@ struct alignas(64) GemmParams {
   int stages;
   int tmem_cols;
   int num_splits;
-  int num_n_tiles;
+  int num_m_tiles, num_n_tiles;
+  int num_units;    // MODE_WGRAD: tap units
+  int total_tiles;  // persistent: CTAs grid-stride over [0, total_tiles)
+  int acc_stride;   // TMEM columns between the two accumulator buffers
   int cpt;     // MODE_FWD: channel chunks per tap
   int num_kb;  // MODE_WGRAD: total pixel-tile k-blocks
   // pixel-tile decode: tile j -> (w0, h0, n0); used for the M tile (FWD) or the K tile (WGRAD)
@@ -68,10 +73,12 @@ struct alignas(64) GemmParams {
   long long phase_out_off[4];
   int w_lim, n_lim;  // row validity
   int n_valid;       // global column validity
-  // WGRAD epilogue: off = m*os_m + (n % nmod)*os_n1 + (n / nmod)*os_n2 + tap.out_off
-  long long os_m, os_n1, os_n2;
-  int nmod;
+  // WGRAD epilogue: off = (m % mmod)*os_m + (m / mmod)*os_m2 + (n % nmod)*os_n1 + (n / nmod)*os_n2 + tap.out_off
+  long long os_m, os_m2, os_n1, os_n2;
+  int mmod, nmod;
   int m_valid;
+  int wgrad_direct;    // host-only: conv wgrad writes the parameter layout directly
+  int wgrad_tap_on_a;  // MODE_WGRAD: the tap shift applies to operand A (conv wgrad) instead of B
 };
 
 constexpr int kThreads = 192;
@@ -80,6 +87,44 @@ constexpr int kAtomBytes = 8192;  // one MN-major atom: 64 k-rows x 128 B
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// One unit of work: a 128 x BN output tile and the k-block range that feeds it.
+struct TileWork {
+  int m_tile, n_tile, phase, split, unit_tap, tap_begin, kb0, kb1;
+};
+
+__device__ __forceinline__ TileWork decode_tile(const GemmParams& p, int t) {
+  TileWork w;
+  int total_kb;
+  if (p.mode == MODE_FWD) {
+    // order: m fastest, then n, then (phase, split): concurrently resident CTAs share one weight tile in L2
+    w.m_tile = t % p.num_m_tiles;
+    int r = t / p.num_m_tiles;
+    w.n_tile = r % p.num_n_tiles;
+    const int z = r / p.num_n_tiles;
+    w.phase = z / p.num_splits;
+    w.split = z - w.phase * p.num_splits;
+    w.unit_tap = 0;
+    w.tap_begin = p.phase_tap_start[w.phase];
+    total_kb = (p.phase_tap_start[w.phase + 1] - w.tap_begin) * p.cpt;
+  } else {
+    // order: (tap unit, n) fastest, then m, then split: concurrent CTAs share the pixel tiles, write disjoint outputs
+    const int units_n = p.num_units * p.num_n_tiles;
+    const int u = t % units_n;
+    const int r = t / units_n;
+    w.unit_tap = u / p.num_n_tiles;
+    w.n_tile = u - w.unit_tap * p.num_n_tiles;
+    w.m_tile = r % p.num_m_tiles;
+    w.split = r / p.num_m_tiles;
+    w.phase = 0;
+    w.tap_begin = 0;
+    total_kb = p.num_kb;
+  }
+  const int kb_per_split = (total_kb + p.num_splits - 1) / p.num_splits;
+  w.kb0 = w.split * kb_per_split;
+  w.kb1 = min(total_kb, w.kb0 + kb_per_split);
+  return w;
 }
 
 __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_constant__ GemmParams p) {
@@ -95,28 +140,9 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
 
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
-  uint64_t* tmem_full_bar = empty_bar + p.stages;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-
-  // ---- which tile / k-range does this CTA own
-  const int m_tile = blockIdx.x;
-  int n_tile, phase = 0, split, total_kb, tap_begin = 0, unit_tap = 0;
-  if (p.mode == MODE_FWD) {
-    n_tile = blockIdx.y;
-    phase = blockIdx.z / p.num_splits;
-    split = blockIdx.z - phase * p.num_splits;
-    tap_begin = p.phase_tap_start[phase];
-    total_kb = (p.phase_tap_start[phase + 1] - tap_begin) * p.cpt;
-  } else {
-    unit_tap = blockIdx.y / p.num_n_tiles;
-    n_tile = blockIdx.y - unit_tap * p.num_n_tiles;
-    split = blockIdx.z;
-    total_kb = p.num_kb;
-  }
-  const int kb_per_split = (total_kb + p.num_splits - 1) / p.num_splits;
-  const int kb0 = split * kb_per_split;
-  const int kb1 = min(total_kb, kb0 + kb_per_split);
-  const bool has_work = kb0 < kb1;
+  uint64_t* tmem_full_bar = empty_bar + p.stages;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   // ---- one-time setup
   if (warp == 0 && lane == 0) {
@@ -129,7 +155,10 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
         mbar_init(&full_bar[s], 1);
         mbar_init(&empty_bar[s], 1);
       }
-      mbar_init(tmem_full_bar, 1);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&tmem_full_bar[b], 1);
+        mbar_init(&tmem_empty_bar[b], 128);  // every epilogue thread arrives
+      }
       fence_mbar_init();
     }
     __syncwarp();
@@ -142,170 +171,224 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
 
   if (warp == 0) {
     // =========================================================== TMA producer (one thread)
-    if (lane == 0 && has_work) {
+    if (lane == 0) {
       int stage = 0;
       uint32_t parity = 0;
-      if (p.mode == MODE_FWD) {
-        const int w0 = m_tile * p.tw_step;
-        const int h0 = (m_tile % p.tpi) * p.th_step;
-        const int n0 = (m_tile / p.tpi) * p.tn_step;
-        const int ncol0 = n_tile * p.bn;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          const int t = kb / p.cpt;
-          const int chunk = kb - t * p.cpt;
-          const Tap tap = p.taps[tap_begin + t];
-          uint8_t* sa = smem + stage * stage_bytes;
-          uint8_t* sb = sa + a_bytes;
-          mbar_wait(&empty_bar[stage], parity ^ 1u);
-          mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
-          tma_load_5d(sa, &p.map_a, &full_bar[stage], tap.dc + chunk * p.kc, w0 + tap.dw, tap.dp, h0 + tap.dh,
-                      n0);
-          if (!p.b_mn) {
-            tma_load_3d(sb, &p.map_b, &full_bar[stage], chunk * p.kc, ncol0, tap.wt);
-          } else {
-            for (int a = 0; a < (p.bn >> 6); ++a)
-              tma_load_3d(sb + a * kAtomBytes, &p.map_b, &full_bar[stage], ncol0 + a * 64, chunk * 64, tap.wt);
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileWork w = decode_tile(p, t);
+        if (w.kb0 >= w.kb1) continue;
+        if (p.mode == MODE_FWD) {
+          const int w0 = w.m_tile * p.tw_step;
+          const int h0 = (w.m_tile % p.tpi) * p.th_step;
+          const int n0 = (w.m_tile / p.tpi) * p.tn_step;
+          const int ncol0 = w.n_tile * p.bn;
+          for (int kb = w.kb0; kb < w.kb1; ++kb) {
+            const int tt = kb / p.cpt;
+            const int chunk = kb - tt * p.cpt;
+            const Tap tap = p.taps[w.tap_begin + tt];
+            uint8_t* sa = smem + stage * stage_bytes;
+            uint8_t* sb = sa + a_bytes;
+            mbar_wait(&empty_bar[stage], parity ^ 1u);
+            mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
+            tma_load_5d(sa, &p.map_a, &full_bar[stage], tap.dc + chunk * p.kc, w0 + tap.dw, tap.dp, h0 + tap.dh,
+                        n0);
+            if (!p.b_mn) {
+              tma_load_3d(sb, &p.map_b, &full_bar[stage], chunk * p.kc, ncol0, tap.wt);
+            } else {
+              for (int a = 0; a < (p.bn >> 6); ++a)
+                tma_load_3d(sb + a * kAtomBytes, &p.map_b, &full_bar[stage], ncol0 + a * 64, chunk * 64, tap.wt);
+            }
+            if (++stage == p.stages) {
+              stage = 0;
+              parity ^= 1u;
+            }
           }
-          if (++stage == p.stages) {
-            stage = 0;
-            parity ^= 1u;
-          }
-        }
-      } else {
-        const Tap tap = p.taps[unit_tap];
-        const int mch0 = m_tile * 128;
-        const int nch0 = n_tile * p.bn;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          const int w0 = kb * p.tw_step;
-          const int h0 = (kb % p.tpi) * p.th_step;
-          const int n0 = (kb / p.tpi) * p.tn_step;
-          uint8_t* sa = smem + stage * stage_bytes;
-          uint8_t* sb = sa + a_bytes;
-          mbar_wait(&empty_bar[stage], parity ^ 1u);
-          mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
-          for (int a = 0; a < 2; ++a)
-            tma_load_5d(sa + a * kAtomBytes, &p.map_a, &full_bar[stage], mch0 + a * 64, w0, 0, h0, n0);
-          for (int a = 0; a < (p.bn >> 6); ++a)
-            tma_load_5d(sb + a * kAtomBytes, &p.map_b, &full_bar[stage], nch0 + a * 64 + tap.dc, w0 + tap.dw,
-                        tap.dp, h0 + tap.dh, n0);
-          if (++stage == p.stages) {
-            stage = 0;
-            parity ^= 1u;
+        } else {
+          const Tap tap = p.taps[w.unit_tap];
+          const int mch0 = w.m_tile * 128;
+          const int nch0 = w.n_tile * p.bn;
+          for (int kb = w.kb0; kb < w.kb1; ++kb) {
+            const int w0 = kb * p.tw_step;
+            const int h0 = (kb % p.tpi) * p.th_step;
+            const int n0 = (kb / p.tpi) * p.tn_step;
+            uint8_t* sa = smem + stage * stage_bytes;
+            uint8_t* sb = sa + a_bytes;
+            mbar_wait(&empty_bar[stage], parity ^ 1u);
+            mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
+            if (p.wgrad_tap_on_a) {
+              for (int a = 0; a < 2; ++a)
+                tma_load_5d(sa + a * kAtomBytes, &p.map_a, &full_bar[stage], mch0 + a * 64 + tap.dc, w0 + tap.dw,
+                            tap.dp, h0 + tap.dh, n0);
+              for (int a = 0; a < (p.bn >> 6); ++a)
+                tma_load_5d(sb + a * kAtomBytes, &p.map_b, &full_bar[stage], nch0 + a * 64, w0, 0, h0, n0);
+            } else {
+              for (int a = 0; a < 2; ++a)
+                tma_load_5d(sa + a * kAtomBytes, &p.map_a, &full_bar[stage], mch0 + a * 64, w0, 0, h0, n0);
+              for (int a = 0; a < (p.bn >> 6); ++a)
+                tma_load_5d(sb + a * kAtomBytes, &p.map_b, &full_bar[stage], nch0 + a * 64 + tap.dc, w0 + tap.dw,
+                            tap.dp, h0 + tap.dh, n0);
+            }
+            if (++stage == p.stages) {
+              stage = 0;
+              parity ^= 1u;
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
     // =========================================================== MMA issuer (one thread)
-    if (lane == 0 && has_work) {
+    if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128u, static_cast<uint32_t>(p.bn), p.a_mn, p.b_mn);
       const uint32_t k_layout = (p.kc == 64) ? 2u : 4u;          // SWIZZLE_128B : SWIZZLE_64B
       const uint32_t k_sbo = static_cast<uint32_t>(8 * p.kc * 2);  // 8 rows of one swizzle atom
       const uint32_t a_step = p.a_mn ? 2048u : 32u;              // bytes per UMMA_K (16 elements of K)
       const uint32_t b_step = p.b_mn ? 2048u : 32u;
+      const int nk = p.kc >> 4;
       int stage = 0;
       uint32_t parity = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&full_bar[stage], parity);
+      int it = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileWork w = decode_tile(p, t);
+        if (w.kb0 >= w.kb1) continue;
+        const int buf = it & 1;
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * p.acc_stride);
+        mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
-        const uint32_t b_addr = a_addr + static_cast<uint32_t>(a_bytes);
-        const int nk = p.kc >> 4;
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
+          mbar_wait(&full_bar[stage], parity);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
+          const uint32_t b_addr = a_addr + static_cast<uint32_t>(a_bytes);
 #pragma unroll 4
-        for (int k = 0; k < nk; ++k) {
-          const uint64_t da = p.a_mn ? make_smem_desc(a_addr + k * a_step, kAtomBytes, 1024u, 2u)
-                                     : make_smem_desc(a_addr + k * a_step, 0u, k_sbo, k_layout);
-          const uint64_t db = p.b_mn ? make_smem_desc(b_addr + k * b_step, kAtomBytes, 1024u, 2u)
-                                     : make_smem_desc(b_addr + k * b_step, 0u, k_sbo, k_layout);
-          umma_bf16(tmem_base, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < nk; ++k) {
+            const uint64_t da = p.a_mn ? make_smem_desc(a_addr + k * a_step, kAtomBytes, 1024u, 2u)
+                                       : make_smem_desc(a_addr + k * a_step, 0u, k_sbo, k_layout);
+            const uint64_t db = p.b_mn ? make_smem_desc(b_addr + k * b_step, kAtomBytes, 1024u, 2u)
+                                       : make_smem_desc(b_addr + k * b_step, 0u, k_sbo, k_layout);
+            umma_bf16(tmem_d, da, db, idesc, (kb > w.kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above retire
+          if (++stage == p.stages) {
+            stage = 0;
+            parity ^= 1u;
+          }
         }
-        umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above retire
-        if (++stage == p.stages) {
-          stage = 0;
-          parity ^= 1u;
-        }
+        umma_commit(&tmem_full_bar[buf]);  // accumulator complete -> epilogue
+        ++it;
       }
-      umma_commit(tmem_full_bar);  // accumulator complete -> epilogue
     }
-  } else if (has_work) {
+  } else {
     // =========================================================== epilogue (4 warps, 128 TMEM lanes)
     const int q = warp & 3;       // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;  // row of the 128-row tile
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     float* outf = reinterpret_cast<float*>(p.out);
     __nv_bfloat16* outh = reinterpret_cast<__nv_bfloat16*>(p.out);
+    int it = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const TileWork w = decode_tile(p, t);
+      if (w.kb0 >= w.kb1) continue;
+      const int buf = it & 1;
+      mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * p.acc_stride);
+      const int m_tile = w.m_tile, n_tile = w.n_tile;
 
-    if (p.mode == MODE_FWD) {
-      const int w = m_tile * p.tw_step + r % p.bw;
-      const int h = (m_tile % p.tpi) * p.th_step + (r / p.bw) % p.bh;
-      const int n = (m_tile / p.tpi) * p.tn_step + r / (p.bw * p.bh);
-      const bool row_ok = (w < p.w_lim) && (n < p.n_lim);
-      const long long row_off = w * p.os_w + h * p.os_h + n * p.os_n + p.phase_out_off[phase];
-      const bool add_bias = (p.bias != nullptr) && (split == 0);
-      for (int c0 = 0; c0 < p.bn; c0 += 32) {
-        uint32_t v[32];
-        __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the divergent stores
-        tmem_ld_32x32(lane_addr + static_cast<uint32_t>(c0), v);
-        tmem_ld_wait();
-        const int ng = n_tile * p.bn + c0;  // first global column of this chunk
-        if (!row_ok || ng >= p.n_valid) continue;
-        float f[32];
+      if (p.mode == MODE_FWD) {
+        const int wx = m_tile * p.tw_step + r % p.bw;
+        const int h = (m_tile % p.tpi) * p.th_step + (r / p.bw) % p.bh;
+        const int n = (m_tile / p.tpi) * p.tn_step + r / (p.bw * p.bh);
+        const bool row_ok = (wx < p.w_lim) && (n < p.n_lim);
+        const long long row_off = wx * p.os_w + h * p.os_h + n * p.os_n + p.phase_out_off[w.phase];
+        const bool add_bias = (p.bias != nullptr) && (w.split == 0);
+        for (int c0 = 0; c0 < p.bn; c0 += 32) {
+          uint32_t v[32];
+          __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the divergent stores
+          tmem_ld_32x32(lane_addr + static_cast<uint32_t>(c0), v);
+          tmem_ld_wait();
+          const int ng = n_tile * p.bn + c0;  // first global column of this chunk
+          if (!row_ok || ng >= p.n_valid) continue;
+          float f[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          f[i] = __uint_as_float(v[i]);
-          if (add_bias && ng + i < p.n_valid) f[i] += __ldg(p.bias + ng + i);
-        }
-        const bool full_chunk = (ng + 32 <= p.n_valid) && (c0 + 32 <= p.bn) && (p.os_col == 1);
-        if (p.out_atomic) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c0 + i < p.bn && ng + i < p.n_valid) atomicAdd(outf + row_off + (ng + i) * p.os_col, f[i]);
-        } else if (p.out_f32) {
-          if (full_chunk && ((row_off + ng) & 3) == 0) {
-            float4* dst = reinterpret_cast<float4*>(outf + row_off + ng);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c0 + i < p.bn && ng + i < p.n_valid) outf[row_off + (ng + i) * p.os_col] = f[i];
+          for (int i = 0; i < 32; ++i) {
+            f[i] = __uint_as_float(v[i]);
+            if (add_bias && ng + i < p.n_valid) f[i] += __ldg(p.bias + ng + i);
           }
-        } else {
-          if (full_chunk && ((row_off + ng) & 7) == 0) {
-            uint4* dst = reinterpret_cast<uint4*>(outh + row_off + ng);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              dst[i] = make_uint4(pack_bf16x2(f[8 * i], f[8 * i + 1]), pack_bf16x2(f[8 * i + 2], f[8 * i + 3]),
-                                  pack_bf16x2(f[8 * i + 4], f[8 * i + 5]), pack_bf16x2(f[8 * i + 6], f[8 * i + 7]));
-          } else {
+          const bool full_chunk = (ng + 32 <= p.n_valid) && (c0 + 32 <= p.bn) && (p.os_col == 1);
+          if (p.out_atomic) {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (c0 + i < p.bn && ng + i < p.n_valid)
-                outh[row_off + (ng + i) * p.os_col] = __float2bfloat16_rn(f[i]);
+              if (c0 + i < p.bn && ng + i < p.n_valid) atomicAdd(outf + row_off + (ng + i) * p.os_col, f[i]);
+          } else if (p.out_f32) {
+            if (full_chunk && ((row_off + ng) & 3) == 0) {
+              float4* dst = reinterpret_cast<float4*>(outf + row_off + ng);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (c0 + i < p.bn && ng + i < p.n_valid) outf[row_off + (ng + i) * p.os_col] = f[i];
+            }
+          } else {
+            if (full_chunk && ((row_off + ng) & 7) == 0) {
+              uint4* dst = reinterpret_cast<uint4*>(outh + row_off + ng);
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                dst[i] = make_uint4(pack_bf16x2(f[8 * i], f[8 * i + 1]), pack_bf16x2(f[8 * i + 2], f[8 * i + 3]),
+                                    pack_bf16x2(f[8 * i + 4], f[8 * i + 5]), pack_bf16x2(f[8 * i + 6], f[8 * i + 7]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (c0 + i < p.bn && ng + i < p.n_valid)
+                  outh[row_off + (ng + i) * p.os_col] = __float2bfloat16_rn(f[i]);
+            }
+          }
+        }
+      } else {
+        const Tap tap = p.taps[w.unit_tap];
+        const int m = m_tile * 128 + r;
+        const bool row_ok = (m < p.m_valid) && (m < tap.mvalid);
+        const long long row_off = (m % p.mmod) * p.os_m + (m / p.mmod) * p.os_m2 + tap.out_off;
+        const bool simple_n = p.nmod >= (1 << 30);  // column offset is affine: no div/mod per element
+        const int ncols = min(p.bn, static_cast<int>(tap.nvalid) - n_tile * p.bn);
+        for (int c0 = 0; c0 < p.bn; c0 += 32) {
+          uint32_t v[32];
+          __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the divergent stores
+          tmem_ld_32x32(lane_addr + static_cast<uint32_t>(c0), v);
+          tmem_ld_wait();
+          if (!row_ok || c0 >= ncols) continue;
+          if (simple_n) {
+            float* dst = outf + row_off + static_cast<long long>(n_tile * p.bn + c0) * p.os_n1;
+            const int lim = min(32, ncols - c0);
+            if (p.out_atomic) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < lim) atomicAdd(dst + i * p.os_n1, __uint_as_float(v[i]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < lim) dst[i * p.os_n1] = __uint_as_float(v[i]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int nl = n_tile * p.bn + c0 + i;  // column within this tap unit
+              if (c0 + i < ncols) {
+                const long long off = row_off + (nl % p.nmod) * p.os_n1 + (nl / p.nmod) * p.os_n2;
+                if (p.out_atomic)
+                  atomicAdd(outf + off, __uint_as_float(v[i]));
+                else
+                  outf[off] = __uint_as_float(v[i]);
+              }
+            }
           }
         }
       }
-    } else {
-      const Tap tap = p.taps[unit_tap];
-      const int m = m_tile * 128 + r;
-      const bool row_ok = m < p.m_valid;
-      for (int c0 = 0; c0 < p.bn; c0 += 32) {
-        uint32_t v[32];
-        __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the divergent stores
-        tmem_ld_32x32(lane_addr + static_cast<uint32_t>(c0), v);
-        tmem_ld_wait();
-        if (!row_ok) continue;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int nl = n_tile * p.bn + c0 + i;  // column within this tap unit
-          if (c0 + i < p.bn && nl < tap.nvalid) {
-            const long long off = m * p.os_m + (nl % p.nmod) * p.os_n1 + (nl / p.nmod) * p.os_n2 + tap.out_off;
-            atomicAdd(outf + off, __uint_as_float(v[i]));
-          }
-        }
-      }
+      // this thread's TMEM reads of the accumulator are complete: hand the buffer back to the MMA issuer
+      __syncwarp();
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[buf]);
+      ++it;
     }
   }
 
@@ -420,22 +503,47 @@ static int pow2_cols(int n) {
   return c;
 }
 
-static int launch(GemmParams& p, dim3 grid, cudaStream_t stream, double flops) {
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+// `grid` = logical tile space: x = m tiles, y = n tiles (FWD) or n tiles * tap units (WGRAD), z = phases*splits
+// (FWD) or splits (WGRAD).  The kernel is persistent: min(tiles, SMs * CTAs/SM) CTAs grid-stride over the tiles,
+// each with a double-buffered TMEM accumulator so that a tile's epilogue overlaps the next tile's main loop.
+static int launch(GemmParams& p, dim3 grid, cudaStream_t stream, double flops, int kb_per_cta = 1 << 30) {
   const int a_bytes = p.a_mn ? 2 * kAtomBytes : 128 * p.kc * 2;
   const int b_bytes = p.b_mn ? (p.bn >> 6) * kAtomBytes : p.bn * p.kc * 2;
   const int stage_bytes = a_bytes + b_bytes;
-  // two CTAs per SM when a stage is small; deeper ring otherwise
-  const int budget = stage_bytes <= 32768 ? env_int("DM_SMEM_BUDGET_SMALL", 98304) : env_int("DM_SMEM_BUDGET_BIG", 196608);
+  p.num_m_tiles = grid.x;
+  if (p.mode == MODE_WGRAD) p.num_units = grid.y / p.num_n_tiles;
+  p.total_tiles = static_cast<int>(grid.x * grid.y * grid.z);
+  p.acc_stride = (p.bn + 31) / 32 * 32;
+  p.tmem_cols = pow2_cols(2 * p.acc_stride);
+  const int sms = num_sms();
+  // two CTAs per SM only if both their TMEM (2 x <=256 columns) and their smem rings fit
+  const bool two_per_sm = p.tmem_cols <= 256 && stage_bytes <= 32768 && env_int("DM_ONE_CTA", 0) == 0;
+  const int budget = two_per_sm ? env_int("DM_SMEM_BUDGET_SMALL", 98304) : env_int("DM_SMEM_BUDGET_BIG", 196608);
+  const int tiles_per_cta = (p.total_tiles + sms * (two_per_sm ? 2 : 1) - 1) / (sms * (two_per_sm ? 2 : 1));
+  const long long kb_stream = static_cast<long long>(std::min(kb_per_cta, 1 << 20)) * tiles_per_cta;
   int stages = std::max(2, std::min(8, budget / stage_bytes));
+  stages = static_cast<int>(std::max<long long>(1, std::min<long long>(stages, kb_stream)));
   p.stages = stages;
-  p.tmem_cols = pow2_cols(p.bn);
-  const int smem = stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
+  int smem = stages * stage_bytes + (2 * stages + 4) * 8 + 16 + 1024;
+  // TMEM is 512 columns per SM: keep co-residency at <= 512 / tmem_cols CTAs by padding the smem request
+  smem = std::max(smem, (two_per_sm ? 80 : 120) * 1024);
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
     attr_err = cudaFuncSetAttribute(dm_tapgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (attr_err != cudaSuccess) return set_error((int)attr_err, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+  const int ctas = std::min(p.total_tiles, sms * (two_per_sm ? 2 : 1));
   g_last_grid[0] = grid.x; g_last_grid[1] = grid.y; g_last_grid[2] = grid.z;
   g_last_smem = smem; g_last_stages = stages;
   ProfRec rec;
@@ -455,7 +563,7 @@ static int launch(GemmParams& p, dim3 grid, cudaStream_t stream, double flops) {
     }
   }
   if (prof) cudaEventRecord(rec.e0, stream);
-  dm_tapgemm_kernel<<<grid, kThreads, smem, stream>>>(p);
+  dm_tapgemm_kernel<<<ctas, kThreads, smem, stream>>>(p);
   if (prof) {
     cudaEventRecord(rec.e1, stream);
     std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -498,6 +606,7 @@ static void init_params(GemmParams& p) {
   p.num_n_tiles = 1;
   p.cpt = 1;
   p.nmod = 1 << 30;
+  p.mmod = 1 << 30;
   p.os_col = 1;
   p.tpi = 1 << 30;
 }
@@ -596,7 +705,7 @@ extern "C" int dm_gemm_bf16(const dm_gemm_desc* g, void* stream_) {
     DM_REQUIRE(splits <= p.cpt, "dm_gemm_bf16: splits %d > k-blocks %d", splits, p.cpt);
     grid = dim3((g->m + 127) / 128, p.num_n_tiles, splits);
   } else if (g->layout == DM_GEMM_TN) {
-    DM_REQUIRE(g->d_f32 && g->accumulate, "dm_gemm_bf16: TN (weight-gradient) output is fp32 accumulate");
+    DM_REQUIRE(g->d_f32, "dm_gemm_bf16: TN (weight-gradient) output is fp32");
     DM_REQUIRE(g->bias == nullptr, "dm_gemm_bf16: TN has no bias");
     p.mode = MODE_WGRAD;
     p.a_mn = 1; p.b_mn = 1; p.kc = 64;
@@ -604,6 +713,7 @@ extern "C" int dm_gemm_bf16(const dm_gemm_desc* g, void* stream_) {
     p.num_kb = (g->k + 63) / 64;
     p.tw_step = 64; p.tpi = 1 << 30; p.th_step = 0; p.tn_step = 0;
     p.taps[0].nvalid = static_cast<int16_t>(std::min(n_store, 32767));
+    p.taps[0].mvalid = 32767;
     p.os_m = g->ldd_m; p.os_n1 = g->ldd_n; p.os_n2 = 0; p.nmod = 1 << 30;
     p.m_valid = m_store;
     // A stored [k][m]: (c = m, w = k rows); B stored [k][n]
@@ -620,7 +730,8 @@ extern "C" int dm_gemm_bf16(const dm_gemm_desc* g, void* stream_) {
     return set_error(-1, "dm_gemm_bf16: unknown layout %d", g->layout);
   }
   const double k_alg = g->k_alg > 0 ? g->k_alg : g->k;
-  return launch(p, grid, stream, 2.0 * m_store * n_store * k_alg);
+  const int kb_total = (p.mode == MODE_FWD) ? p.cpt : p.num_kb;
+  return launch(p, grid, stream, 2.0 * m_store * n_store * k_alg, (kb_total + splits - 1) / splits);
 }
 
 // ------------------------------------------------------------------------------------------ convolutions
@@ -740,38 +851,48 @@ extern "C" int dm_conv_up(const dm_conv_geom* g, const void* small, const void* 
   return launch(p, dim3(pt.tiles, p.num_n_tiles, nphase), stream, 50.0 * g->batch * g->hs * g->ws * g->cs * g->cb);
 }
 
-extern "C" int dm_conv_wgrad(const dm_conv_geom* g, const void* small, const void* big, float* dw, void* stream_) {
+extern "C" int dm_conv_wgrad(const dm_conv_geom* g, const void* small, const void* big, float* dw_packed,
+                             int direct_layout, void* stream_) {
+  // D_t[m = cb][n = cs] = sum_pixels big_tap_t[pix][cb] * small[pix][cs], accumulated into the tap-major packed
+  // gradient dw_packed[25][cs][cb]: a warp's 32 rows (cb) are contiguous floats -> coalesced reductions.
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = check_geom(g, "dm_conv_wgrad")) return rc;
-  DM_REQUIRE(g->cs % 128 == 0, "dm_conv_wgrad: cs %d must be a multiple of 128", g->cs);
+  DM_REQUIRE(g->cs % 64 == 0, "dm_conv_wgrad: cs %d must be a multiple of 64", g->cs);
   const bool pair = (g->cb == 32 && g->stride == 2);
   DM_REQUIRE(g->cb % 64 == 0 || pair, "dm_conv_wgrad: cb %d must be a multiple of 64 (or 32 with stride 2)", g->cb);
   PixTile pt;
   DM_REQUIRE(make_pix_tile(64, g->batch, g->hs, g->ws, &pt), "dm_conv_wgrad: unsupported grid %dx%d", g->hs, g->ws);
   GemmParams p;
   init_params(p);
+  p.wgrad_direct = direct_layout;
   p.mode = MODE_WGRAD;
   p.a_mn = 1; p.b_mn = 1; p.kc = 64;
   p.num_kb = pt.tiles;
   p.tw_step = 0; p.tpi = pt.tpi; p.th_step = pt.th_step; p.tn_step = pt.tn_step;
-  p.out = dw; p.out_f32 = 1; p.out_atomic = 1;
-  p.os_m = (long long)g->cb * 25;
-  p.m_valid = g->cs;
-  int units = 0;
+  p.out = dw_packed; p.out_f32 = 1; p.out_atomic = 1;
+  p.bn = g->cs >= 256 ? env_int("DM_BN_WGRAD", 256) : (g->cs >= 128 ? 128 : 64);
+  p.num_n_tiles = g->cs / p.bn;
+  // direct = 1: accumulate straight into the parameter layout dw[cs][cb][25] (scattered 4-byte reductions, no
+  // unpack pass); direct = 0: tap-major packed layout [25][cs][cb] (coalesced reductions + dm_unpack_conv_grad)
+  const bool direct = p.wgrad_direct != 0;
+  p.os_n1 = direct ? (long long)g->cb * 25 : g->cb; p.os_n2 = 0; p.nmod = 1 << 30;
+  const long long tap_stride = direct ? 1 : (long long)g->cs * g->cb;
+  const long long m_stride = direct ? 25 : 1;
+  int units = 0, m_tiles = 1;
   if (!pair) {
-    p.bn = g->cb >= 256 ? env_int("DM_BN_WGRAD", 256) : (g->cb >= 128 ? 128 : 64);
-    p.num_n_tiles = g->cb / p.bn;
+    m_tiles = (g->cb + 127) / 128;
     down_taps(g, p.taps);
     for (int t = 0; t < 25; ++t) {
-      p.taps[t].nvalid = static_cast<int16_t>(g->cb);
-      p.taps[t].out_off = t;
+      p.taps[t].nvalid = static_cast<int16_t>(g->cs);
+      p.taps[t].mvalid = static_cast<int16_t>(g->cb);
+      p.taps[t].out_off = static_cast<int32_t>(t * tap_stride);
     }
-    p.os_n1 = 25; p.os_n2 = 0; p.nmod = 1 << 30;
+    p.os_m = m_stride; p.os_m2 = 0; p.mmod = 1 << 30;
+    p.m_valid = g->cb;
     units = 25;
   } else {
-    // cb == 32, stride 2: one 64-wide box covers both w-parities = filter columns (2aw+2, 2aw+3)
-    p.bn = 64;
-    p.num_n_tiles = 1;
+    // cb == 32, stride 2: one 64-wide box covers both w-parities = filter columns (2aw+2, 2aw+3):
+    // row m -> (pw = m / 32, cb = m % 32), tap = kh*5 + 2aw+2 + pw
     for (int kh = 0; kh < 5; ++kh)
       for (int aw = -1; aw <= 1; ++aw) {
         Tap& t = p.taps[units++];
@@ -781,20 +902,23 @@ extern "C" int dm_conv_wgrad(const dm_conv_geom* g, const void* small, const voi
         t.dw = static_cast<int8_t>(aw);
         t.dh = static_cast<int8_t>(ah);
         t.dp = static_cast<int8_t>(eh - 2 * ah);
-        t.nvalid = static_cast<int16_t>(aw == 1 ? 32 : 64);
-        t.out_off = kh * 5 + 2 * aw + 2;
+        t.nvalid = static_cast<int16_t>(g->cs);
+        t.mvalid = static_cast<int16_t>(aw == 1 ? 32 : 64);
+        t.out_off = static_cast<int32_t>((kh * 5 + 2 * aw + 2) * tap_stride);
       }
-    p.os_n1 = 25; p.os_n2 = 1; p.nmod = 32;
+    p.os_m = m_stride; p.mmod = 32; p.os_m2 = tap_stride;
+    p.m_valid = 64;
   }
   uint32_t boxa[5] = {64, (uint32_t)pt.bw, 1, (uint32_t)pt.bh, (uint32_t)pt.bimg};
-  if (int rc = encode_act_map(&p.map_a, small, g->batch, g->hs, g->ws, g->cs, 1, boxa, 128)) return rc;
-  if (int rc = encode_act_map(&p.map_b, big, g->batch, g->hb, g->wb, g->cb, g->stride, boxa, 128)) return rc;
-  // split K so that the grid covers the machine a few times over
-  const int base_ctas = (g->cs / 128) * p.num_n_tiles * units;
+  // operand roles: A = big (tap-shifted, M = cb), B = small (N = cs)
+  if (int rc = encode_act_map(&p.map_a, big, g->batch, g->hb, g->wb, g->cb, g->stride, boxa, 128)) return rc;
+  if (int rc = encode_act_map(&p.map_b, small, g->batch, g->hs, g->ws, g->cs, 1, boxa, 128)) return rc;
+  p.wgrad_tap_on_a = 1;
+  const int base_ctas = m_tiles * p.num_n_tiles * units;
   int splits = env_int("DM_WGRAD_SPLITS", 0);
-  if (splits <= 0) splits = std::max(1, std::min(p.num_kb, (2 * 148 + base_ctas - 1) / base_ctas));
+  if (splits <= 0) splits = std::max(1, std::min(p.num_kb, (env_int("DM_WGRAD_CTAS", 296) + base_ctas - 1) / base_ctas));
   splits = std::min(splits, p.num_kb);
   p.num_splits = splits;
-  return launch(p, dim3(g->cs / 128, p.num_n_tiles * units, splits), stream,
-                50.0 * g->batch * g->hs * g->ws * g->cs * g->cb);
+  return launch(p, dim3(m_tiles, p.num_n_tiles * units, splits), stream,
+                50.0 * g->batch * g->hs * g->ws * g->cs * g->cb, (p.num_kb + splits - 1) / splits);
 }

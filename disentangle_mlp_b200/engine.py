@@ -29,6 +29,7 @@ class OperandCache:
 
     def __init__(self):
         self._c = {}
+        self.wgrad_scratch = {}  # (weight name, device) -> zeroed [25][cs][cb] fp32 packed-gradient scratch
         self.static = False  # True: never rebuild implicitly (CUDA-graph mode); refresh() does it in place
 
     def get(self, key, param, builder):
@@ -118,9 +119,22 @@ def linear_dgrad(dy_bf16, w_bf16, batch, n_out, k_in, out_dtype=BF16, out=None):
                     splits=splits)
 
 
-def linear_wgrad(dy_bf16, x_bf16, batch, n_out, k_in, dw):
-    """dw[n_out, k_in] += dy^T @ x"""
-    ops.gemm(GEMM_TN, dy_bf16, x_bf16, n_out, k_in, batch, out=dw, accumulate=True)
+def linear_wgrad(dy_bf16, x_bf16, batch, n_out, k_in, dw, overwrite=False):
+    """dw[n_out, k_in] (+)= dy^T @ x.  Computed as D[m = in-feature, n = out-feature] so that a warp's 32 rows are
+    contiguous floats of dw (coalesced); `overwrite` stores instead of accumulating (dw need not be zeroed)."""
+    ops.gemm(GEMM_TN, x_bf16, dy_bf16, k_in, n_out, batch, out=dw, accumulate=not overwrite, ldd_m=1, ldd_n=k_in)
+
+
+def conv_wgrad(g, small, big, dw, cache, name):
+    """Conv / ConvT weight gradient through the tap-major packed scratch (persistent per weight, kept zeroed)."""
+    if ops.WGRAD_DIRECT:
+        ops.conv_wgrad(g, small, big, dw)
+        return
+    ws = cache.wgrad_scratch
+    key = (name, dw.device)
+    if key not in ws:
+        ws[key] = torch.zeros((25, g.cs, g.cb), dtype=F32, device=dw.device)
+    ops.conv_wgrad(g, small, big, dw, ws[key])
 
 
 def col_conv_forward(col, w_col, bias, rows, cs):
@@ -165,7 +179,8 @@ def discriminator_forward(x, P, B, cache: OperandCache, training=True, col=None)
     return S.prob, S.feat, S
 
 
-def discriminator_backward(S, dprob, dfeat, P, G, cache: OperandCache, need_dx=True, need_wgrad=True):
+def discriminator_backward(S, dprob, dfeat, P, G, cache: OperandCache, need_dx=True, need_wgrad=True,
+                           overwrite_big=False):
     """Backward of discriminator_forward. dprob [b] / dfeat [b,2048] fp32 (either may be None).
     G: dict name -> fp32 grad tensor (accumulated) or None. Returns dx fp32 NCHW or None."""
     b = S.b
@@ -177,11 +192,11 @@ def discriminator_backward(S, dprob, dfeat, P, G, cache: OperandCache, need_dx=T
     dfeat_t = ops.head_backward(dprob.contiguous(), S.prob, S.feat, None if dfeat is None else dfeat.contiguous(), wo,
                                 wg["sigmoid_output.0.weight"] if wg else None,
                                 wg["sigmoid_output.0.bias"] if wg else None)
-    colsum = wg["lth_features.0.bias"] if wg else torch.zeros(2048, dtype=F32, device=dev)
+    colsum = wg["lth_features.0.bias"] if wg else None
     dpre = ops.act_backward(dfeat_t, S.feat, b, 2048, ACT_LEAKY, LEAKY, colsum)
     wl = _lin_w(cache, "lth_features.0", P["lth_features.0.weight"])
     if wg:
-        linear_wgrad(dpre, S.flat, b, 2048, 16384, wg["lth_features.0.weight"])
+        linear_wgrad(dpre, S.flat, b, 2048, 16384, wg["lth_features.0.weight"], overwrite_big)
     dflat = linear_dgrad(dpre, wl, b, 2048, 16384)
     da4 = ops.transpose(dflat, b, 256, 64)  # back to NHWC [b,64,256]
     # conv 4
@@ -189,21 +204,21 @@ def discriminator_backward(S, dprob, dfeat, P, G, cache: OperandCache, need_dx=T
     g4 = ops.geom(b, 8, 8, 256, 256, 2)
     _, wu4, _ = _conv_pack(cache, "convs.9", P["convs.9.weight"], 256, 256)
     if wg:
-        ops.conv_wgrad(g4, dr4, S.a3, wg["convs.9.weight"])
+        conv_wgrad(g4, dr4, S.a3, wg["convs.9.weight"], cache, "convs.9")
     da3 = ops.conv_up(g4, dr4, wu4)
     # conv 3
     dr3 = bn_act_backward(da3, S.bn3, wg, "convs.7")
     g3 = ops.geom(b, 16, 16, 256, 128, 2)
     _, wu3, _ = _conv_pack(cache, "convs.6", P["convs.6.weight"], 256, 128)
     if wg:
-        ops.conv_wgrad(g3, dr3, S.a2, wg["convs.6.weight"])
+        conv_wgrad(g3, dr3, S.a2, wg["convs.6.weight"], cache, "convs.6")
     da2 = ops.conv_up(g3, dr3, wu3)
     # conv 2
     dr2 = bn_act_backward(da2, S.bn2, wg, "convs.4")
     g2 = ops.geom(b, 32, 32, 128, 32, 2)
     _, wu2, _ = _conv_pack(cache, "convs.3", P["convs.3.weight"], 128, 32)
     if wg:
-        ops.conv_wgrad(g2, dr2, S.a1, wg["convs.3.weight"])
+        conv_wgrad(g2, dr2, S.a1, wg["convs.3.weight"], cache, "convs.3")
     da1 = ops.conv_up(g2, dr2, wu2)
     # conv 1 (3 input channels: im2col GEMM)
     dr1 = bn_act_backward(da1, S.bn1, wg, "convs.1")
@@ -248,7 +263,7 @@ def encoder_forward(x, P, B, cache: OperandCache, training=True, col=None):
     return outs[0], outs[1], S
 
 
-def encoder_backward(S, dmu, dlogvar, P, G, cache: OperandCache, need_wgrad=True):
+def encoder_backward(S, dmu, dlogvar, P, G, cache: OperandCache, need_wgrad=True, overwrite_big=False):
     """dmu / dlogvar: fp32 [b,128] gradients w.r.t. the encoder outputs."""
     b = S.b
     dev = S.flat.device
@@ -268,20 +283,20 @@ def encoder_backward(S, dmu, dlogvar, P, G, cache: OperandCache, need_wgrad=True
         dacc = bn_act_backward(dh1, H.bn, wg, head + ".1")
         w0 = _lin_w(cache, head + ".0", P[head + ".0.weight"])
         if wg:
-            linear_wgrad(dacc, S.flat, b, 2048, 16384, wg[head + ".0.weight"])
+            linear_wgrad(dacc, S.flat, b, 2048, 16384, wg[head + ".0.weight"], overwrite_big)
         linear_dgrad(dacc, w0, b, 2048, 16384, out_dtype=F32, out=dflat)
     da3 = ops.transpose(ops.cast_bf16(dflat), b, 256, 64)
     dr3 = bn_act_backward(da3, S.bn3, wg, "features.7")
     g3 = ops.geom(b, 8, 8, 256, 128, 2)
     _, wu3, _ = _conv_pack(cache, "features.6", P["features.6.weight"], 256, 128)
     if wg:
-        ops.conv_wgrad(g3, dr3, S.a2, wg["features.6.weight"])
+        conv_wgrad(g3, dr3, S.a2, wg["features.6.weight"], cache, "features.6")
     da2 = ops.conv_up(g3, dr3, wu3)
     dr2 = bn_act_backward(da2, S.bn2, wg, "features.4")
     g2 = ops.geom(b, 16, 16, 128, 64, 2)
     _, wu2, _ = _conv_pack(cache, "features.3", P["features.3.weight"], 128, 64)
     if wg:
-        ops.conv_wgrad(g2, dr2, S.a1, wg["features.3.weight"])
+        conv_wgrad(g2, dr2, S.a1, wg["features.3.weight"], cache, "features.3")
     da1 = ops.conv_up(g2, dr2, wu2)
     dr1 = bn_act_backward(da1, S.bn1, wg, "features.1")
     if wg:
@@ -319,7 +334,7 @@ def decoder_forward(code, P, B, cache: OperandCache, training=True):
     return S.recon, S
 
 
-def decoder_backward(S, drecon, P, G, cache: OperandCache, need_dcode=True, need_wgrad=True):
+def decoder_backward(S, drecon, P, G, cache: OperandCache, need_dcode=True, need_wgrad=True, overwrite_big=False):
     """drecon: fp32 NCHW gradient w.r.t. the decoder output. Returns dcode fp32 [b,128] or None."""
     b = S.b
     wg = G if need_wgrad else None
@@ -333,24 +348,24 @@ def decoder_backward(S, drecon, P, G, cache: OperandCache, need_dcode=True, need
     g3 = ops.geom(b, 32, 32, 128, 32, 2)
     wd3, _, _ = _conv_pack(cache, "deconv3", P["deconv3.weight"], 128, 32)
     if wg:
-        ops.conv_wgrad(g3, S.a2, dr3, wg["deconv3.weight"])
+        conv_wgrad(g3, S.a2, dr3, wg["deconv3.weight"], cache, "deconv3")
     da2 = ops.conv_down(g3, dr3, wd3)
     dr2 = bn_act_backward(da2, S.bn2, wg, "act2.0")
     g2 = ops.geom(b, 16, 16, 256, 128, 2)
     wd2, _, _ = _conv_pack(cache, "deconv2", P["deconv2.weight"], 256, 128)
     if wg:
-        ops.conv_wgrad(g2, S.a1, dr2, wg["deconv2.weight"])
+        conv_wgrad(g2, S.a1, dr2, wg["deconv2.weight"], cache, "deconv2")
     da1 = ops.conv_down(g2, dr2, wd2)
     dr1 = bn_act_backward(da1, S.bn1, wg, "act1.0")
     g1 = ops.geom(b, 8, 8, 256, 256, 2)
     wd1, _, _ = _conv_pack(cache, "deconv1", P["deconv1.weight"], 256, 256)
     if wg:
-        ops.conv_wgrad(g1, S.h0, dr1, wg["deconv1.weight"])
+        conv_wgrad(g1, S.h0, dr1, wg["deconv1.weight"], cache, "deconv1")
     dh0 = ops.conv_down(g1, dr1, wd1)  # NHWC [b,8,8,256]
     dh = ops.transpose(dh0, b, 64, 256)  # -> [b, 256*64] flatten order
     dacc = bn_act_backward(dh, S.bn0, wg, "preprocess.1")
     if wg:
-        linear_wgrad(dacc, S.code16, b, 16384, 128, wg["preprocess.0.weight"])
+        linear_wgrad(dacc, S.code16, b, 16384, 128, wg["preprocess.0.weight"], overwrite_big)
     if not need_dcode:
         return None
     wp = _lin_w(cache, "preprocess.0", P["preprocess.0.weight"])

@@ -6,6 +6,7 @@ libdm_b200.so and returns torch tensors.  torch is used for memory and streams o
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -68,11 +69,34 @@ def conv_up(g: ConvGeom, small, w_up, bias=None, out=None, out_f32=False):
     return out
 
 
-def conv_wgrad(g: ConvGeom, small, big, dw):
-    """dw[cs][cb][5][5] (fp32) += small^T * shifted(big)"""
-    assert dw.dtype == F32
-    _lib.check(_lib.load().dm_conv_wgrad(C.byref(g), _p(small), _p(big), _p(dw), _stream()), "dm_conv_wgrad")
+WGRAD_DIRECT = os.environ.get("DM_WGRAD_DIRECT", "1") != "0"
+
+
+def conv_wgrad_packed(g: ConvGeom, small, big, dw_packed):
+    """dw_packed[25][cs][cb] (fp32, tap-major) += small^T * shifted(big)"""
+    assert dw_packed.dtype == F32 and dw_packed.numel() == 25 * g.cs * g.cb
+    _lib.check(_lib.load().dm_conv_wgrad(C.byref(g), _p(small), _p(big), _p(dw_packed), 0, _stream()), "dm_conv_wgrad")
+    return dw_packed
+
+
+def unpack_conv_grad(dw_packed, cs, cb, dw, accumulate=True):
+    """dw[cs][cb][5][5] (+)= dw_packed; dw_packed is re-zeroed."""
+    _lib.check(_lib.load().dm_unpack_conv_grad(_p(dw_packed), cs, cb, int(accumulate), _p(dw), _stream()),
+               "dm_unpack_conv_grad")
     return dw
+
+
+def conv_wgrad(g: ConvGeom, small, big, dw, packed=None, direct=None):
+    """dw[cs][cb][5][5] (fp32) += small^T * shifted(big).
+    direct: reduce straight into dw; otherwise through `packed` = zeroed [25][cs][cb] scratch (kept zeroed)."""
+    if WGRAD_DIRECT if direct is None else direct:
+        assert dw.dtype == F32 and dw.numel() == 25 * g.cs * g.cb
+        _lib.check(_lib.load().dm_conv_wgrad(C.byref(g), _p(small), _p(big), _p(dw), 1, _stream()), "dm_conv_wgrad")
+        return dw
+    if packed is None:
+        packed = torch.zeros((25, g.cs, g.cb), dtype=F32, device=dw.device)
+    conv_wgrad_packed(g, small, big, packed)
+    return unpack_conv_grad(packed, g.cs, g.cb, dw, True)
 
 
 def profile_enable(on: bool):
@@ -106,19 +130,23 @@ def pack_conv_weights(w, cs, cb, want_down=True, want_up=True, want_col=False):
 
 
 # ------------------------------------------------------------------------------------------ HBM-bound
-def bn_stats(y, rows, c, sums=None):
-    if sums is None:
-        sums = torch.empty((2, c), dtype=F32, device=y.device)
-    _lib.check(_lib.load().dm_bn_stats(_p(y), int(y.dtype == F32), rows, c, _p(sums), _stream()), "dm_bn_stats")
-    return sums
+def bn_parts(rows, c) -> int:
+    return int(_lib.load().dm_bn_parts(rows, c))
 
 
-def bn_finalize(sums, rows, c, gamma, beta, running_mean, running_var, nbt, momentum=0.1, eps=1e-5):
-    scale_shift = torch.empty((2, c), dtype=F32, device=sums.device)
-    mean_invstd = torch.empty((2, c), dtype=F32, device=sums.device)
-    _lib.check(_lib.load().dm_bn_finalize(_p(sums), rows, c, _p(gamma), _p(beta), _p(running_mean), _p(running_var),
-                                          _p(nbt), momentum, eps, _p(scale_shift), _p(mean_invstd), _stream()),
-               "dm_bn_finalize")
+def bn_stats(y, rows, c):
+    """Per-block partial sums [parts][2][c] of y and y^2 (summed by bn_finalize)."""
+    partials = torch.empty((bn_parts(rows, c), 2, c), dtype=F32, device=y.device)
+    _lib.check(_lib.load().dm_bn_stats(_p(y), int(y.dtype == F32), rows, c, _p(partials), _stream()), "dm_bn_stats")
+    return partials
+
+
+def bn_finalize(partials, rows, c, gamma, beta, running_mean, running_var, nbt, momentum=0.1, eps=1e-5):
+    scale_shift = torch.empty((2, c), dtype=F32, device=partials.device)
+    mean_invstd = torch.empty((2, c), dtype=F32, device=partials.device)
+    _lib.check(_lib.load().dm_bn_finalize(_p(partials), partials.shape[0], rows, c, _p(gamma), _p(beta),
+                                          _p(running_mean), _p(running_var), _p(nbt), momentum, eps, _p(scale_shift),
+                                          _p(mean_invstd), _stream()), "dm_bn_finalize")
     return scale_shift, mean_invstd
 
 
@@ -133,10 +161,11 @@ def bn_apply_act(y, rows, c, scale_shift, act, slope=0.2, out=None):
 def bn_backward(dout, y, rows, c, scale_shift, mean_invstd, act, slope=0.2, dgamma=None, dbeta=None):
     assert dout.dtype == BF16
     dy = torch.empty(y.shape, dtype=BF16, device=y.device)
+    partials = torch.empty((bn_parts(rows, c), 2, c), dtype=F32, device=y.device)
     sums = torch.empty((2, c), dtype=F32, device=y.device)
     _lib.check(_lib.load().dm_bn_backward(_p(dout), _p(y), int(y.dtype == F32), rows, c, _p(scale_shift),
-                                          _p(mean_invstd), act, slope, _p(sums), _p(dy), _p(dgamma), _p(dbeta),
-                                          _stream()), "dm_bn_backward")
+                                          _p(mean_invstd), act, slope, _p(partials), _p(sums), _p(dy), _p(dgamma),
+                                          _p(dbeta), _stream()), "dm_bn_backward")
     return dy, sums
 
 
@@ -150,13 +179,15 @@ def bias_act(acc, rows, c, bias, act, slope=0.2, want_f32=True, want_bf16=True):
 
 def act_backward(dout, out, rows, c, act, slope, colsum):
     dpre = torch.empty((rows, c), dtype=BF16, device=dout.device)
-    _lib.check(_lib.load().dm_act_backward(_p(dout), _p(out), rows, c, act, slope, _p(dpre), _p(colsum), _stream()),
-               "dm_act_backward")
+    partials = torch.empty((bn_parts(rows, c), c), dtype=F32, device=dout.device)
+    _lib.check(_lib.load().dm_act_backward(_p(dout), _p(out), rows, c, act, slope, _p(dpre), _p(partials), _p(colsum),
+                                           _stream()), "dm_act_backward")
     return dpre
 
 
 def colsum(x, rows, c, out):
-    _lib.check(_lib.load().dm_colsum(_p(x), int(x.dtype == F32), rows, c, _p(out), _stream()), "dm_colsum")
+    partials = torch.empty((bn_parts(rows, c), c), dtype=F32, device=x.device)
+    _lib.check(_lib.load().dm_colsum(_p(x), int(x.dtype == F32), rows, c, _p(partials), _p(out), _stream()), "dm_colsum")
     return out
 
 

@@ -27,6 +27,7 @@ from . import engine, ops
 from .ops import BF16, F32
 
 ALIGN = 64  # elements; keeps every parameter's bf16 shadow 128-byte aligned for TMA
+BIG_LINEAR = ("lth_features.0.weight", "x_to_mu.0.weight", "x_to_logvar.0.weight", "preprocess.0.weight")
 
 
 class FlatParams:
@@ -62,6 +63,16 @@ class FlatParams:
         self.step_count = 0
         self.cache = engine.OperandCache()
         self.cache.lin_views = self.W16
+        # the big Linear weight gradients are written in "overwrite" mode by the first backward of a phase, so
+        # zero_grad() only clears the rest of the flat gradient (8 % of it)
+        big = sorted((self.offsets[n], self.offsets[n] + self.P[n].numel()) for n in self.names if n in BIG_LINEAR)
+        self._zero_ranges, lo = [], 0
+        for a, b in big:
+            if a > lo:
+                self._zero_ranges.append((lo, a))
+            lo = b
+        if lo < self.total:
+            self._zero_ranges.append((lo, self.total))
         self.params_changed()
 
     def params_changed(self):
@@ -70,7 +81,8 @@ class FlatParams:
         self.cache.invalidate()
 
     def zero_grad(self):
-        self.grad.zero_()
+        for lo, hi in self._zero_ranges:
+            self.grad[lo:hi].zero_()
 
     def adam(self, grad_scale=1.0):
         self.step_count += 1
@@ -211,9 +223,9 @@ class VAETrainer(_Base):
         ops.mse_sum(recon, data, loss, 1.0, drecon, 1.0)
         dmu_kl, dlv_kl = torch.empty_like(mu), torch.empty_like(mu)
         ops.kl(mu, logvar, loss, self.beta, dmu_kl, dlv_kl)
-        dz = engine.decoder_backward(Sg, drecon, fp.P, fp.G, fp.cache, True, True)
+        dz = engine.decoder_backward(Sg, drecon, fp.P, fp.G, fp.cache, True, True, overwrite_big=True)
         _, _, dmu, dlv = ops.reparam_backward(dz, logvar, eps, dmu_kl, dlv_kl)
-        engine.encoder_backward(Se, dmu, dlv, fp.P, fp.G, fp.cache, True)
+        engine.encoder_backward(Se, dmu, dlv, fp.P, fp.G, fp.cache, True, overwrite_big=True)
         self.dist.allreduce_async(fp.grad)
         self.dist.wait()
         fp.adam()
@@ -245,7 +257,7 @@ class GANTrainer(_Base):
         fake, Sg = engine.decoder_forward(noise, fg.P, fg.buffers, fg.cache, True)
         prob_f, _, S2 = engine.discriminator_forward(fake, fd.P, fd.buffers, fd.cache, True)
         d2 = self._bce(prob_f, fake_label, errD, sum_dgz1)
-        engine.discriminator_backward(S1, d1, None, fd.P, fd.G, fd.cache, False, True)
+        engine.discriminator_backward(S1, d1, None, fd.P, fd.G, fd.cache, False, True, overwrite_big=True)
         engine.discriminator_backward(S2, d2, None, fd.P, fd.G, fd.cache, False, True)
         self.dist.allreduce_async(fd.grad)
         self.dist.wait()
@@ -255,7 +267,7 @@ class GANTrainer(_Base):
         prob_g, _, S3 = engine.discriminator_forward(fake, fd.P, fd.buffers, fd.cache, True)
         d3 = self._bce(prob_g, real_label, errG, sum_dgz2)
         dfake = engine.discriminator_backward(S3, d3, None, fd.P, None, fd.cache, True, False)
-        engine.decoder_backward(Sg, dfake, fg.P, fg.G, fg.cache, False, True)
+        engine.decoder_backward(Sg, dfake, fg.P, fg.G, fg.cache, False, True, overwrite_big=True)
         self.dist.allreduce_async(fg.grad)
         self.dist.wait()
         fg.adam()
@@ -292,7 +304,7 @@ class BetaVAEGANTrainer(_Base):
         fake, Sg1 = engine.decoder_forward(noise, feg.P, feg.buffers, feg.cache, True)
         prob_f, _, S2 = engine.discriminator_forward(fake, fd.P, fd.buffers, fd.cache, True)
         d2 = self._bce(prob_f, fake_label, errD_fake)
-        engine.discriminator_backward(S1, d1, None, fd.P, fd.G, fd.cache, False, True)
+        engine.discriminator_backward(S1, d1, None, fd.P, fd.G, fd.cache, False, True, overwrite_big=True)
         engine.discriminator_backward(S2, d2, None, fd.P, fd.G, fd.cache, False, True)
         del S1, S2
         self.dist.allreduce_async(fd.grad)
@@ -317,13 +329,13 @@ class BetaVAEGANTrainer(_Base):
         dsim = torch.empty_like(sim_recon)
         ops.mse_sum(sim_recon, sim_real, sim_loss, 0.5, dsim, 0.5)
         dfake = engine.discriminator_backward(S4, d4, None, fd.P, None, fd.cache, True, False)
-        engine.decoder_backward(Sg1, dfake, feg.P, feg.G, feg.cache, False, True)
+        engine.decoder_backward(Sg1, dfake, feg.P, feg.G, feg.cache, False, True, overwrite_big=True)
         del S4, Sg1
         drecon = engine.discriminator_backward(S5, d5, dsim, fd.P, None, fd.cache, True, False)
         ops.mse_sum(recon, data, loss_dec, 1.0, drecon, 1.0, accumulate=True)
         dz = engine.decoder_backward(Sg2, drecon, feg.P, feg.G, feg.cache, True, True)
         _, _, dmu, dlv = ops.reparam_backward(dz, logvar, eps_dec)
-        engine.encoder_backward(Se, dmu, dlv, feg.P, feg.G, feg.cache, True)
+        engine.encoder_backward(Se, dmu, dlv, feg.P, feg.G, feg.cache, True, overwrite_big=True)
         del S5, Sg2, Se
         self.dist.allreduce_async(feg.grad)
         self.dist.wait()
@@ -340,9 +352,9 @@ class BetaVAEGANTrainer(_Base):
         ops.mse_sum(recon, data, loss_enc, 1.0, drecon, 1.0)
         dmu_kl, dlv_kl = torch.empty_like(mu), torch.empty_like(mu)
         ops.kl(mu, logvar, kld, self.beta, dmu_kl, dlv_kl)
-        dz = engine.decoder_backward(Sg3, drecon, feg.P, feg.G, feg.cache, True, True)
+        dz = engine.decoder_backward(Sg3, drecon, feg.P, feg.G, feg.cache, True, True, overwrite_big=True)
         _, _, dmu, dlv = ops.reparam_backward(dz, logvar, eps_enc, dmu_kl, dlv_kl)
-        engine.encoder_backward(Se, dmu, dlv, feg.P, feg.G, feg.cache, True)
+        engine.encoder_backward(Se, dmu, dlv, feg.P, feg.G, feg.cache, True, overwrite_big=True)
         self.dist.allreduce_async(feg.grad)
         self.dist.wait()
         feg.adam()

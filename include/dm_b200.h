@@ -78,41 +78,51 @@ int dm_conv_down(const dm_conv_geom* g, const void* big, const void* w_down, con
 int dm_conv_up(const dm_conv_geom* g, const void* small, const void* w_up, const float* bias,
                void* out_big, int out_f32, void* stream);
 
-/* dw[cs][cb][kh][kw] += sum_{b,h,w} small[b,h,w,cs] * big[b, s*h+kh-2, s*w+kw-2, cb]   (fp32, atomic)
- * = weight gradient of nn.Conv2d (small = grad_output, big = input) and of nn.ConvTranspose2d
- *   (small = input, big = grad_output).  Requires cs % 128 == 0 and cb % 64 == 0, or cb == 32 with stride 2. */
-int dm_conv_wgrad(const dm_conv_geom* g, const void* small, const void* big, float* dw, void* stream);
+/* Weight gradient of nn.Conv2d (small = grad_output, big = input) and of nn.ConvTranspose2d (small = input,
+ * big = grad_output), fp32, accumulated atomically:
+ *   direct_layout = 1: dw[cs][cb][kh][kw]          += sum_{b,h,w} small[b,h,w,cs] * big[b, s*h+kh-2, s*w+kw-2, cb]
+ *   direct_layout = 0: dw_packed[kh*5+kw][cs][cb]  += (same sum)   tap-major packed layout, coalesced reductions;
+ *                      dm_unpack_conv_grad then moves it into the parameter layout.
+ * Requires cs % 64 == 0 and cb % 64 == 0, or cb == 32 with stride 2. */
+int dm_conv_wgrad(const dm_conv_geom* g, const void* small, const void* big, float* dw, int direct_layout,
+                  void* stream);
+/* dw[cs][cb][5][5] (+)= dw_packed[25][cs][cb]; dw_packed is zeroed for the next accumulation. */
+int dm_unpack_conv_grad(float* dw_packed, int cs, int cb, int accumulate, float* dw, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * HBM-bound ops.  "rows x c" = channel-innermost matrix view of an NHWC activation (rows = b*h*w) or of a
  * Linear output (rows = batch).  act: 0 none, 1 ReLU, 2 LeakyReLU(slope).
  * ---------------------------------------------------------------------------------------------- */
 
-/* nn.BatchNorm1d/2d, training mode (model.py:451,454,457,462,468,492,496,500,504,390,393,396,399):
- *   dm_bn_stats    : sums[0][c] = sum_r y, sums[1][c] = sum_r y^2   (sums is zeroed inside)
+/* nn.BatchNorm1d/2d, training mode (model.py:451,454,457,462,468,492,496,500,504,390,393,396,399).
+ * Reductions over rows are two-level: every thread block writes one partial vector, the consumer kernel sums
+ * them (no same-address atomics).  dm_bn_parts(rows, c) = number of partial vectors = leading dimension of the
+ * caller-provided `partials` scratch ([parts][2][c] floats; [parts][c] for dm_act_backward / dm_colsum).
+ *   dm_bn_stats    : partials[p][0][c] = sum_r y, partials[p][1][c] = sum_r y^2 over block p's rows
  *   dm_bn_finalize : scale = gamma*invstd, shift = beta - mean*scale; running stats updated with
  *                    `momentum` and the unbiased variance; num_batches_tracked += 1 (may be NULL)
  *   dm_bn_apply_act: out = act(y*scale + shift)   (the ReLU / LeakyReLU(0.2) that follows every BN)
  *   dm_bn_backward : dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)), dz = dout*act'(z);
- *                    dgamma += sum dz*xhat, dbeta += sum dz (skipped when NULL); sums = [2][c] scratch */
-int dm_bn_stats(const void* y, int y_f32, long long rows, int c, float* sums, void* stream);
-int dm_bn_finalize(const float* sums, long long rows, int c, const float* gamma, const float* beta,
+ *                    sums[2][c] = (sum dz, sum dz*xhat); dgamma += sums[1], dbeta += sums[0] (skipped when NULL) */
+int dm_bn_parts(long long rows, int c);
+int dm_bn_stats(const void* y, int y_f32, long long rows, int c, float* partials, void* stream);
+int dm_bn_finalize(const float* partials, int nparts, long long rows, int c, const float* gamma, const float* beta,
                    float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
                    float eps, float* scale_shift, float* mean_invstd, void* stream);
 int dm_bn_apply_act(const void* y, int y_f32, long long rows, int c, const float* scale_shift, int act,
                     float slope, void* out_bf16, void* stream);
 int dm_bn_backward(const void* dout_bf16, const void* y, int y_f32, long long rows, int c,
-                   const float* scale_shift, const float* mean_invstd, int act, float slope, float* sums,
-                   void* dy_bf16, float* dgamma, float* dbeta, void* stream);
+                   const float* scale_shift, const float* mean_invstd, int act, float slope, float* partials,
+                   float* sums, void* dy_bf16, float* dgamma, float* dbeta, void* stream);
 
 /* out = act(acc + bias) after a split-K Linear (model.py:402-404); fp32 and/or bf16 outputs (NULL = skip). */
 int dm_bias_act(const float* acc, long long rows, int c, const float* bias, int act, float slope,
                 float* out_f32, void* out_bf16, void* stream);
-/* dpre = dout * act'(out) as bf16; colsum[c] += sum_r dpre (the Linear bias gradient). */
+/* dpre = dout * act'(out) as bf16; colsum[c] += sum_r dpre (the Linear bias gradient; NULL = skip). */
 int dm_act_backward(const float* dout, const float* out, long long rows, int c, int act, float slope,
-                    void* dpre_bf16, float* colsum, void* stream);
+                    void* dpre_bf16, float* partials, float* colsum, void* stream);
 /* colsum[c] += sum_r x[r][c] */
-int dm_colsum(const void* x, int x_f32, long long rows, int c, float* colsum, void* stream);
+int dm_colsum(const void* x, int x_f32, long long rows, int c, float* partials, float* colsum, void* stream);
 
 /* fp32 NCHW [b,3,h,w] image -> bf16 im2col matrix [b*(h/s)*(w/s), 128], column c*25+kh*5+kw (75 valid):
  * the A operand of the two 3-channel convolutions (model.py:449, 389) and of deconv4's input-gradient. */

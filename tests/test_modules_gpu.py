@@ -133,7 +133,7 @@ def check_linear_layer(ops, lin, inp, out, tag, dgrad_ref="own"):
     dy16 = out.grad.detach().cuda().bfloat16().contiguous()
     dx = ops.gemm(ops.GEMM_NN, dy16, w16, b, k, n)
     dw = torch.zeros(n, k, device="cuda")
-    ops.gemm(ops.GEMM_TN, dy16, x16, n, k, b, out=dw, accumulate=True)
+    ops.gemm(ops.GEMM_TN, x16, dy16, k, n, b, out=dw, accumulate=False, ldd_m=1, ldd_n=k)  # as engine.linear_wgrad
     errs = {"fwd": rel(y, out), "wgrad": rel(dw, lin.weight.grad)}
     if dgrad_ref == "own":  # (the two latent heads share their input: its oracle gradient is the SUM of both)
         errs["dgrad"] = rel(dx, inp.grad)

@@ -46,7 +46,7 @@ def case_gemm(layout, m, n, k, splits=1, out_bf16=False, bias=False, n_store=0, 
     bias_t = torch.randn(n, device=dev) if bias else None
     if bias:
         ref = ref + bias_t
-    acc = splits > 1 or layout == "tn"
+    acc = splits > 1
     out = ops.gemm(lay, a, b, m, n, k, out_dtype=torch.bfloat16 if out_bf16 else torch.float32, accumulate=acc,
                    bias=bias_t, splits=splits, m_store=m_store, n_store=n_store)
     torch.cuda.synchronize()
@@ -98,7 +98,7 @@ def case_conv_up(batch, hs, ws, cs, cb, stride, bias=True, out_f32=False):
     return rel_err(out, ref.permute(0, 2, 3, 1))
 
 
-def case_conv_wgrad(batch, hs, ws, cs, cb, stride):
+def case_conv_wgrad(batch, hs, ws, cs, cb, stride, direct=True):
     import torch
 
     from disentangle_mlp_b200 import ops
@@ -106,7 +106,7 @@ def case_conv_wgrad(batch, hs, ws, cs, cb, stride):
     w, small, big = conv_refs(batch, hs, ws, cs, cb, stride)
     g = ops.geom(batch, hs, ws, cs, cb, stride)
     dw = torch.zeros(cs, cb, 5, 5, device="cuda")
-    ops.conv_wgrad(g, small, big, dw)
+    ops.conv_wgrad(g, small, big, dw, direct=direct)
     torch.cuda.synchronize()
     ref = torch.nn.grad.conv2d_weight(big.float().permute(0, 3, 1, 2), (cs, cb, 5, 5),
                                       small.float().permute(0, 3, 1, 2), stride=stride, padding=2)
@@ -131,6 +131,8 @@ CASES = {
     "tn_128x128x64": lambda: case_gemm("tn", 128, 128, 64),
     "tn_128x256x128": lambda: case_gemm("tn", 128, 256, 128),
     "tn_2048x1024x64": lambda: case_gemm("tn", 2048, 1024, 64),
+    "tn_acc_splitk": lambda: case_gemm("tn", 256, 256, 1024, splits=4),
+    "tn_n32_oob_box": lambda: case_gemm("tn", 128, 32, 4096, splits=8, m_store=75),
     "tn_col": lambda: case_gemm("tn", 128, 64, 8192, splits=16, m_store=75, n_store=32),
     # convolutions
     "down_s1_c64": lambda: case_conv_down(2, 16, 16, 128, 64, 1),
@@ -146,6 +148,9 @@ CASES = {
     "wgrad_s2": lambda: case_conv_wgrad(2, 16, 16, 256, 128, 2),
     "wgrad_s2_8x8": lambda: case_conv_wgrad(4, 8, 8, 256, 256, 2),
     "wgrad_s2_c32_pair": lambda: case_conv_wgrad(2, 32, 32, 128, 32, 2),
+    "wgrad_s2_cb64": lambda: case_conv_wgrad(2, 16, 16, 128, 64, 2),
+    "wgrad_packed_s2": lambda: case_conv_wgrad(2, 16, 16, 256, 128, 2, direct=False),
+    "wgrad_packed_pair": lambda: case_conv_wgrad(2, 32, 32, 128, 32, 2, direct=False),
 }
 
 
