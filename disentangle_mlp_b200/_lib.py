@@ -38,6 +38,7 @@ _SIGS = {
     "dm_conv_wgrad": [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "dm_unpack_conv_grad": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "dm_profile_enable": [c_int],
+    "dm_profile_dump": [C.c_char_p],
     "dm_profile_read": [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(c_ll)],
     "dm_debug_last_plan": [C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int)],
     "dm_bn_parts": [c_ll, c_int],
@@ -64,9 +65,9 @@ _SIGS = {
                          c_void_p, c_void_p],
     "dm_mse_sum": [c_void_p, c_void_p, c_ll, c_float, c_void_p, c_float, c_int, c_void_p, c_void_p],
     "dm_kl": [c_void_p, c_void_p, c_ll, c_float, c_void_p, c_int, c_void_p, c_void_p, c_void_p],
-    "dm_bce_const": [c_void_p, c_int, c_float, c_float, c_float, c_void_p, c_int, c_void_p, c_void_p, c_void_p],
+    "dm_bce_const": [c_void_p, c_int, c_float, c_float, c_void_p, c_float, c_void_p, c_int, c_void_p, c_void_p, c_void_p],
     "dm_adam_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, C.c_double, C.c_double, C.c_double, C.c_double, c_int,
-                     c_float, c_void_p, c_void_p],
+                     c_void_p, c_float, c_void_p, c_void_p],
 }
 
 #: every symbol include/dm_b200.h declares

@@ -657,8 +657,10 @@ __global__ void __launch_bounds__(256) kl_kernel(const float* __restrict__ mu, c
 // with log clamped at -100; dprob (+)= w/n_total * (-(t/p) + (1-t)/(1-p)) with the clamp's zero-gradient region respected;
 // stat[0] += sum p (for D_x logging)
 __global__ void __launch_bounds__(256) bce_const_kernel(const float* __restrict__ p, int n, float n_total, float target,
-                                                        float w, float* __restrict__ loss, int grad_accumulate,
+                                                        const float* __restrict__ target_dev, float w,
+                                                        float* __restrict__ loss, int grad_accumulate,
                                                         float* __restrict__ dprob, float* __restrict__ stat) {
+  if (target_dev) target = *target_dev;  // CUDA-graph mode: the per-step label lives in device memory
   float acc = 0.f, accp = 0.f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float q = p[i];
@@ -682,10 +684,25 @@ __global__ void __launch_bounds__(256) bce_const_kernel(const float* __restrict_
 // ------------------------------------------------------------------------------------------ Adam
 // torch.optim.Adam (betas, eps, no weight decay, no amsgrad; experiments/new_betavaegan.py:49-50) on a flat buffer,
 // optionally refreshing the bf16 shadow copy the GEMMs read.  28 B/param (+2 B shadow).
+__global__ void adam_count_kernel(int* step) { *step += 1; }
+
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, long long n,
                                                    float step_size, float beta1, float beta2, float omb1, float omb2,
-                                                   float eps, float bc2_sqrt, float grad_scale, __nv_bfloat16* __restrict__ shadow) {
+                                                   float eps, float bc2_sqrt, float grad_scale, __nv_bfloat16* __restrict__ shadow,
+                                                   const int* __restrict__ step_dev, double lr_d, double beta1_d,
+                                                   double beta2_d) {
+  if (step_dev) {  // CUDA-graph mode: bias corrections from the device-side step counter (same double arithmetic)
+    __shared__ float sh[2];
+    if (threadIdx.x == 0) {
+      const int st = *step_dev;
+      sh[0] = static_cast<float>(lr_d / (1.0 - pow(beta1_d, static_cast<double>(st))));
+      sh[1] = static_cast<float>(sqrt(1.0 - pow(beta2_d, static_cast<double>(st))));
+    }
+    __syncthreads();
+    step_size = sh[0];
+    bc2_sqrt = sh[1];
+  }
   const long long nv = n / 4;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nv;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -922,23 +939,32 @@ extern "C" int dm_kl(const float* mu, const float* logvar, long long n, float w,
   DM_LAUNCHED("dm_kl");
 }
 
-extern "C" int dm_bce_const(const float* p, int n, float n_total, float target, float w, float* loss,
-                            int grad_accumulate, float* dprob, float* stat, void* stream_) {
+extern "C" int dm_bce_const(const float* p, int n, float n_total, float target, const float* target_dev, float w,
+                            float* loss, int grad_accumulate, float* dprob, float* stat, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-  bce_const_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(p, n, n_total, target, w, loss, grad_accumulate, dprob, stat);
+  bce_const_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(p, n, n_total, target, target_dev, w, loss, grad_accumulate, dprob, stat);
   DM_LAUNCHED("dm_bce_const");
 }
 
 extern "C" int dm_adam_step(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1,
-                            double beta2, double eps, int step, float grad_scale, void* shadow_bf16, void* stream_) {
+                            double beta2, double eps, int step, int* step_dev, float grad_scale, void* shadow_bf16,
+                            void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-  DM_REQUIRE(step >= 1, "dm_adam_step: step must be >= 1");
+  DM_REQUIRE(step >= 1 || step_dev != nullptr, "dm_adam_step: step must be >= 1 (or a device counter given)");
   // scalar arithmetic in double, then rounded to float once -- as torch.optim.Adam does with Python floats
-  const double bc1 = 1.0 - pow(beta1, step);
-  const double bc2 = 1.0 - pow(beta2, step);
+  float step_size = 0.f, bc2s = 1.f;
+  if (step_dev) {
+    adam_count_kernel<<<1, 1, 0, s>>>(step_dev);  // *step_dev += 1, then the update reads it
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  } else {
+    const double bc1 = 1.0 - pow(beta1, step);
+    const double bc2 = 1.0 - pow(beta2, step);
+    step_size = static_cast<float>(lr / bc1);
+    bc2s = static_cast<float>(sqrt(bc2));
+  }
   adam_kernel<<<grid_for(n / 4 + 1, 256, 148 * 8), 256, 0, s>>>(
-      p, g, m, v, n, static_cast<float>(lr / bc1), static_cast<float>(beta1), static_cast<float>(beta2),
-      static_cast<float>(1.0 - beta1), static_cast<float>(1.0 - beta2), static_cast<float>(eps),
-      static_cast<float>(sqrt(bc2)), grad_scale, static_cast<bf16*>(shadow_bf16));
+      p, g, m, v, n, step_size, static_cast<float>(beta1), static_cast<float>(beta2),
+      static_cast<float>(1.0 - beta1), static_cast<float>(1.0 - beta2), static_cast<float>(eps), bc2s, grad_scale,
+      static_cast<bf16*>(shadow_bf16), step_dev, lr, beta1, beta2);
   DM_LAUNCHED("dm_adam_step");
 }

@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -486,6 +487,7 @@ static int g_last_smem = 0, g_last_stages = 0;
 struct ProfRec {
   cudaEvent_t e0, e1;
   double flops;
+  int gx, gy, gz, mode, bn, kc, stages, ctas, a_mn, b_mn;
 };
 static std::mutex g_prof_mu;
 static bool g_prof_on = false;
@@ -560,6 +562,8 @@ static int launch(GemmParams& p, dim3 grid, cudaStream_t stream, double flops, i
         cudaEventCreate(&rec.e1);
       }
       rec.flops = flops;
+      rec.gx = grid.x; rec.gy = grid.y; rec.gz = grid.z; rec.mode = p.mode; rec.bn = p.bn; rec.kc = p.kc;
+      rec.stages = stages; rec.ctas = ctas; rec.a_mn = p.a_mn; rec.b_mn = p.b_mn;
     }
   }
   if (prof) cudaEventRecord(rec.e0, stream);
@@ -647,6 +651,28 @@ extern "C" int dm_profile_read(double* total_ms, double* total_flops, long long*
   if (total_flops) *total_flops = fl;
   if (launches) *launches = static_cast<long long>(g_prof.size());
   g_prof.clear();
+  return 0;
+}
+
+// Write one CSV row per profiled GEMM-class launch (logical tile grid, tile shape, duration, algorithmic FLOPs)
+// and clear the record list; synchronises the device.
+extern "C" int dm_profile_dump(const char* path) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return set_error((int)e, "dm_profile_dump: %s", cudaGetErrorString(e));
+  FILE* f = fopen(path, "w");
+  if (!f) return set_error(-1, "dm_profile_dump: cannot open %s", path);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  fprintf(f, "idx,mode,a_mn,b_mn,tiles_m,tiles_n,tiles_z,bn,kc,stages,ctas,us,gflop\n");
+  int i = 0;
+  for (auto& r : g_prof) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.e0, r.e1);
+    fprintf(f, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.3f,%.4f\n", i++, r.mode, r.a_mn, r.b_mn, r.gx, r.gy, r.gz, r.bn,
+            r.kc, r.stages, r.ctas, t * 1e3, r.flops * 1e-9);
+    g_prof_pool.push_back(r);
+  }
+  g_prof.clear();
+  fclose(f);
   return 0;
 }
 

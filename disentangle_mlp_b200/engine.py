@@ -55,6 +55,9 @@ def _lin_w(cache, name, p):
 
 def _conv_pack(cache, name, p, cs, cb):
     """(w_down [25][cs][cb], w_up [25][cb_pad][cs], w_col [cs][128] or None)"""
+    static = getattr(cache, "static_packs", None)
+    if static is not None:  # fused trainers: persistent buffers refreshed in place after every optimizer step
+        return static[name]
     return cache.get(("conv", name), p, lambda w: ops.pack_conv_weights(w.contiguous(), cs, cb, True, True, cb * 25 <= 128))
 
 

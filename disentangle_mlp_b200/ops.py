@@ -117,13 +117,17 @@ def last_plan():
     return tuple(grid), smem.value, stages.value
 
 
-def pack_conv_weights(w, cs, cb, want_down=True, want_up=True, want_col=False):
-    """fp32 [cs][cb][5][5] -> (w_down [25][cs][cb], w_up [25][cb_pad][cs], w_col [cs][128]) bf16"""
+def pack_conv_weights(w, cs, cb, want_down=True, want_up=True, want_col=False, out=None):
+    """fp32 [cs][cb][5][5] -> (w_down [25][cs][cb], w_up [25][cb_pad][cs], w_col [cs][128]) bf16.
+    out: a previously returned tuple to refresh in place."""
     dev = w.device
     cb_pad = max(16, (cb + 15) // 16 * 16)
-    w_down = torch.empty((25, cs, cb), dtype=BF16, device=dev) if want_down else None
-    w_up = torch.empty((25, cb_pad, cs), dtype=BF16, device=dev) if want_up else None
-    w_col = torch.empty((cs, 128), dtype=BF16, device=dev) if want_col else None
+    if out is not None:
+        w_down, w_up, w_col = out
+    else:
+        w_down = torch.empty((25, cs, cb), dtype=BF16, device=dev) if want_down else None
+        w_up = torch.empty((25, cb_pad, cs), dtype=BF16, device=dev) if want_up else None
+        w_col = torch.empty((cs, 128), dtype=BF16, device=dev) if want_col else None
     _lib.check(_lib.load().dm_pack_conv_weights(_p(w), cs, cb, _p(w_down), _p(w_up), _p(w_col), _stream()),
                "dm_pack_conv_weights")
     return w_down, w_up, w_col
@@ -273,11 +277,15 @@ def kl(mu, logvar, loss, w=1.0, dmu=None, dlogvar=None, accumulate=False):
 
 
 def bce_const(p, target, loss, w=1.0, n_total=None, dprob=None, accumulate=False, stat=None):
+    """`target`: python float, or a 1-element CUDA tensor (read on the device: CUDA-graph replay)."""
     n = p.numel()
-    _lib.check(_lib.load().dm_bce_const(_p(p), n, float(n_total or n), float(target), w, _p(loss), int(accumulate),
-                                        _p(dprob), _p(stat), _stream()), "dm_bce_const")
+    tdev = target if isinstance(target, torch.Tensor) else None
+    _lib.check(_lib.load().dm_bce_const(_p(p), n, float(n_total or n), 0.0 if tdev is not None else float(target),
+                                        _p(tdev), w, _p(loss), int(accumulate), _p(dprob), _p(stat), _stream()),
+               "dm_bce_const")
 
 
-def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0, shadow=None):
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0, shadow=None, step_dev=None):
+    """step_dev: int32 CUDA tensor holding the step count; incremented on the device and used instead of `step`."""
     _lib.check(_lib.load().dm_adam_step(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, step,
-                                        grad_scale, _p(shadow), _stream()), "dm_adam_step")
+                                        _p(step_dev), grad_scale, _p(shadow), _stream()), "dm_adam_step")

@@ -61,8 +61,16 @@ class FlatParams:
         self.buffers = dict(module.named_buffers())
         self.lr, self.betas, self.eps = lr, betas, eps
         self.step_count = 0
+        self.step_dev = torch.zeros((), dtype=torch.int32, device=dev)  # the kernels' copy of step_count
         self.cache = engine.OperandCache()
         self.cache.lin_views = self.W16
+        # persistent bf16 operand packs of the conv / deconv weights ([cs][cb][5][5]), refreshed IN PLACE after every
+        # update: no lazily rebuilt state, so a captured CUDA graph always reads current operands
+        self.cache.static_packs = {}
+        for n, p in named:
+            if p.dim() == 4:
+                cs, cb = p.shape[0], p.shape[1]
+                self.cache.static_packs[n[:-len(".weight")]] = ops.pack_conv_weights(p.detach(), cs, cb, True, True, cb * 25 <= 128)
         # the big Linear weight gradients are written in "overwrite" mode by the first backward of a phase, so
         # zero_grad() only clears the rest of the flat gradient (8 % of it)
         big = sorted((self.offsets[n], self.offsets[n] + self.P[n].numel()) for n in self.names if n in BIG_LINEAR)
@@ -75,20 +83,41 @@ class FlatParams:
             self._zero_ranges.append((lo, self.total))
         self.params_changed()
 
+    def refresh_packs(self):
+        for name, packs in self.cache.static_packs.items():
+            p = self.P[name + ".weight"]
+            ops.pack_conv_weights(p.detach(), p.shape[0], p.shape[1], out=packs)
+
     def params_changed(self):
         """Call after the fp32 parameters were modified outside adam() (init, load_state_dict)."""
         ops.cast_bf16(self.flat, self.shadow)
-        self.cache.invalidate()
+        self.refresh_packs()
 
     def zero_grad(self):
         for lo, hi in self._zero_ranges:
             self.grad[lo:hi].zero_()
 
     def adam(self, grad_scale=1.0):
+        """One Adam update; the step count lives on the device (incremented by the kernel) so that the call can be
+        replayed from a CUDA graph; the host mirror `step_count` is kept for the optimizer state dict."""
         self.step_count += 1
         ops.adam_step(self.flat, self.grad, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps,
-                      self.step_count, grad_scale, self.shadow)
-        self.cache.invalidate()  # conv operand packs are rebuilt lazily from the updated fp32 weights
+                      0, grad_scale, self.shadow, step_dev=self.step_dev)
+        self.refresh_packs()  # bf16 conv operand packs follow the updated fp32 weights
+
+    def snapshot(self):
+        return {"flat": self.flat.clone(), "m": self.m.clone(), "v": self.v.clone(), "step": self.step_count,
+                "buffers": {k: b.clone() for k, b in self.buffers.items()}}
+
+    def restore(self, snap):
+        self.flat.copy_(snap["flat"])
+        self.m.copy_(snap["m"])
+        self.v.copy_(snap["v"])
+        self.step_count = snap["step"]
+        self.step_dev.fill_(snap["step"])
+        for k, b in self.buffers.items():
+            b.copy_(snap["buffers"][k])
+        self.params_changed()
 
     def optimizer_state_dict(self):
         """torch.optim.Adam-compatible state (exp_avg / exp_avg_sq / step per parameter)."""
@@ -116,6 +145,7 @@ class FlatParams:
         if steps:
             assert len(steps) == 1, "per-parameter step counts differ; not representable"
             self.step_count = steps.pop()
+            self.step_dev.fill_(self.step_count)
         g = sd["param_groups"][0]
         self.lr, self.betas, self.eps = g["lr"], tuple(g["betas"]), g["eps"]
 
@@ -181,9 +211,19 @@ def _scalar(dev):
 
 
 class _Base:
+    """Common trainer plumbing: label stream, BCE helper, optional whole-step CUDA-graph capture.
+
+    Graph mode (`enable_graph(batch)`; world size 1): the step's ~480 kernel launches are captured once into a
+    torch.cuda.CUDAGraph and replayed; the batch is copied into a static device buffer, the per-step labels and
+    the Adam step counters are read from device memory, noise / eps come from torch's graph-safe CUDA generator."""
+
     def __init__(self):
         self.dist = GradReducer()
         self.metrics = {}
+        self._graph = None
+
+    def flat_params(self):
+        raise NotImplementedError
 
     @staticmethod
     def draw_labels():
@@ -193,11 +233,61 @@ class _Base:
         return real, fake
 
     def _bce(self, prob, target, loss, stat=None):
-        """Mean BCE over the GLOBAL batch and its gradient w.r.t. prob."""
+        """Mean BCE over the GLOBAL batch and its gradient w.r.t. prob. target: float or 1-element CUDA tensor."""
         b = prob.numel()
         dprob = torch.empty_like(prob)
         ops.bce_const(prob, target, loss, 1.0, n_total=b * self.dist.world, dprob=dprob, stat=stat)
         return dprob
+
+    # ------------------------------------------------------------------ CUDA graph
+    def enable_graph(self, batch):
+        if self.dist.on:
+            raise RuntimeError("whole-step graph capture is implemented for world size 1 only")
+        fps = self.flat_params()
+        dev = fps[0].flat.device
+        self._gx = torch.zeros(batch, 3, 64, 64, device=dev)
+        self._glabels = torch.zeros(2, device=dev)
+        self._glabels_host = torch.zeros(2).pin_memory()
+        # random inputs of the step (noise / eps), drawn OUTSIDE the graph in the reference's order (SURVEY Q5)
+        self._grands = [torch.zeros(batch, 128, device=dev) for _ in range(self.n_rands)]
+        snaps = [fp.snapshot() for fp in fps]
+        rng = torch.cuda.get_rng_state(dev)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm-up outside capture: lazy inits (func attributes, driver entry points)
+            self._glabels.copy_(torch.tensor([0.9, 0.1]))
+            self._gx.uniform_(-1, 1)
+            for _ in range(2):
+                self._step_impl(self._gx, self._glabels[0:1], self._glabels[1:2], *self._grands)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        counts0 = [fp.step_count for fp in fps]
+        from . import _lib
+
+        l0 = _lib.launch_count()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._gmetrics = self._step_impl(self._gx, self._glabels[0:1], self._glabels[1:2], *self._grands)
+        self.graph_launches_per_step = _lib.launch_count() - l0  # libdm_b200 kernels captured in one step
+        self._adams_per_step = [fp.step_count - c for fp, c in zip(fps, counts0)]
+        for fp, s in zip(fps, snaps):  # undo the warm-up / capture-time bookkeeping: training state as before
+            fp.restore(s)
+        torch.cuda.set_rng_state(rng, dev)
+        torch.cuda.synchronize()
+
+    def _graph_step(self, data, real_label, fake_label):
+        if real_label is None:
+            real_label, fake_label = self.draw_labels()
+        self._glabels_host[0], self._glabels_host[1] = real_label, fake_label
+        self._glabels.copy_(self._glabels_host, non_blocking=True)
+        self._gx.copy_(data, non_blocking=True)
+        for r in self._grands:
+            r.normal_()
+        self._graph.replay()
+        for fp, n in zip(self.flat_params(), self._adams_per_step):
+            fp.step_count += n
+        self.metrics = self._gmetrics
+        return self.metrics
 
 
 class VAETrainer(_Base):
@@ -209,7 +299,17 @@ class VAETrainer(_Base):
         self.fp = FlatParams(model, lr)
         self.beta = beta
 
+    n_rands = 1  # eps
+
+    def flat_params(self):
+        return [self.fp]
+
     def step(self, data, eps=None):
+        if self._graph is not None and eps is None:
+            return self._graph_step(data, 0.0, 0.0)
+        return self._step_impl(data, None, None, eps=eps)
+
+    def _step_impl(self, data, real_label=None, fake_label=None, eps=None):
         fp, dev = self.fp, data.device
         b = data.shape[0]
         loss = _scalar(dev)
@@ -242,11 +342,21 @@ class GANTrainer(_Base):
         self.fg = FlatParams(netG, lr)
         self.fd = FlatParams(netD, lr)
 
+    n_rands = 1  # noise
+
+    def flat_params(self):
+        return [self.fg, self.fd]
+
     def step(self, data, real_label=None, fake_label=None, noise=None):
-        fg, fd, dev = self.fg, self.fd, data.device
-        b = data.shape[0]
+        if self._graph is not None and noise is None:
+            return self._graph_step(data, real_label, fake_label)
         if real_label is None:
             real_label, fake_label = self.draw_labels()
+        return self._step_impl(data, real_label, fake_label, noise=noise)
+
+    def _step_impl(self, data, real_label, fake_label, noise=None):
+        fg, fd, dev = self.fg, self.fd, data.device
+        b = data.shape[0]
         errD, errG, sum_dx, sum_dgz1, sum_dgz2 = (_scalar(dev) for _ in range(5))
         # ---- (1) discriminator: real batch, then detached fake batch (:84-113)
         fd.zero_grad()
@@ -285,11 +395,21 @@ class BetaVAEGANTrainer(_Base):
         self.fd = FlatParams(netD, lr)
         self.beta = float(beta)
 
+    n_rands = 3  # noise, eps of the decoder phase, eps of the encoder phase
+
+    def flat_params(self):
+        return [self.feg, self.fd]
+
     def step(self, data, real_label=None, fake_label=None, noise=None, eps_dec=None, eps_enc=None):
-        feg, fd, dev = self.feg, self.fd, data.device
-        b = data.shape[0]
+        if self._graph is not None and noise is None and eps_dec is None and eps_enc is None:
+            return self._graph_step(data, real_label, fake_label)
         if real_label is None:
             real_label, fake_label = self.draw_labels()
+        return self._step_impl(data, real_label, fake_label, noise, eps_dec, eps_enc)
+
+    def _step_impl(self, data, real_label, fake_label, noise=None, eps_dec=None, eps_enc=None):
+        feg, fd, dev = self.feg, self.fd, data.device
+        b = data.shape[0]
         (errD_real, errD_fake, sum_dx, errG_fake, errG_recon, sim_loss, loss_dec, kld, loss_enc) = (
             _scalar(dev) for _ in range(9))
         col_d = ops.im2col3(data, 1)  # the D-side and encoder-side im2col of `data` are reused within the step

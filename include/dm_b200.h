@@ -159,19 +159,25 @@ int dm_mse_sum(const float* a, const float* b, long long n, float wloss, float* 
                int grad_accumulate, float* grad, void* stream);
 int dm_kl(const float* mu, const float* logvar, long long n, float w, float* loss, int grad_accumulate,
           float* dmu, float* dlogvar, void* stream);
-int dm_bce_const(const float* p, int n, float n_total, float target, float w, float* loss,
+/* target_dev (may be NULL): read the label from device memory instead of `target` (CUDA-graph replay). */
+int dm_bce_const(const float* p, int n, float n_total, float target, const float* target_dev, float w, float* loss,
                  int grad_accumulate, float* dprob, float* stat, void* stream);
 
 /* torch.optim.Adam step on a flat fp32 buffer (new_betavaegan.py:49-50,123,164,193); `step` is the
- * 1-based step count; g is multiplied by grad_scale first; shadow_bf16 (may be NULL) receives bf16(p). */
+ * 1-based step count; g is multiplied by grad_scale first; shadow_bf16 (may be NULL) receives bf16(p).
+ * step_dev (may be NULL): device-side step counter, incremented and then used instead of `step` (CUDA-graph
+ * replay: the bias corrections change every step). */
 int dm_adam_step(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1,
-                 double beta2, double eps, int step, float grad_scale, void* shadow_bf16, void* stream);
+                 double beta2, double eps, int step, int* step_dev, float grad_scale, void* shadow_bf16,
+                 void* stream);
 
 /* Per-launch CUDA-event timing of the GEMM-class kernel (bench.py roofline). dm_profile_read synchronises the
  * device and returns the summed launch durations, algorithmic FLOPs (2*M*N*K; convolutions: 2*25*b*hs*ws*cs*cb)
  * and launch count since the previous read. */
 int dm_profile_enable(int on);
 int dm_profile_read(double* total_ms, double* total_flops, long long* launches);
+/* One CSV row per profiled launch (tile grid, tile shape, us, GFLOP); clears the records; synchronises. */
+int dm_profile_dump(const char* path);
 
 /* Test hook: direct access to the tile plan of a GEMM-class call (tile counts, smem bytes). */
 int dm_debug_last_plan(int* grid_xyz, int* smem_bytes, int* stages);

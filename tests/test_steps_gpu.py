@@ -103,3 +103,41 @@ def test_betavaegan_trainer_first_step_and_counters(mods):
     moved = [n for n, p in mEG.named_parameters() if not n.endswith(".bias") or "act" in n or ".1." in n]
     init = dict(nets.VAE(opt).named_parameters())
     assert params_rel(mEG, rEG) < 0.1 and params_rel(mD, rD) < 0.1
+
+
+def test_cuda_graph_step_matches_eager(mods):
+    """The captured-and-replayed step must do exactly what the eagerly launched step does (same kernels, same
+    order, same random draws).  Quantities computed before the first parameter update agree to fp32 round-off;
+    later ones only to the level two eager runs agree with each other (fp32 atomics reorder sums, and Adam's first
+    steps are ~lr*sign(g), so noise-level gradient components flip)."""
+    dm, tr, nets, steps = mods
+    b, opt = 8, steps.make_opt()
+    x = steps.synthetic_batch(b, 4321).cuda()
+    outs = []
+    for graph in (False, True):
+        torch.manual_seed(7)
+        eg, d = dm.VAE(opt), dm.Discriminator_celeba(opt)
+        eg.apply(dm.weights_init)
+        d.apply(dm.weights_init)
+        T = tr.BetaVAEGANTrainer(eg.cuda(), d.cuda(), beta=25.0, lr=1e-4)
+        if graph:
+            T.enable_graph(b)
+            assert T.feg.step_count == 0 and int(T.feg.step_dev) == 0 and int(d.convs[1].num_batches_tracked) == 0
+        torch.manual_seed(11)
+        first = {k: float(v) for k, v in T.step(x, 0.9, 0.1).items()}
+        for s in range(2):
+            T.step(x, 0.9, 0.1)
+        outs.append((torch.cat([p.detach().flatten() for p in eg.parameters()]).clone(),
+                     torch.cat([p.detach().flatten() for p in d.parameters()]).clone(),
+                     first, T.feg.step_count, int(T.feg.step_dev), T.fd.step_count,
+                     int(d.convs[1].num_batches_tracked)))
+    (eg0, d0, m0, c0, cd0, dd0, n0), (eg1, d1, m1, c1, cd1, dd1, n1) = outs
+    assert c0 == c1 == cd0 == cd1 == 6 and dd0 == dd1 == 3 and n0 == n1 == 15
+    for k in ("errD_real", "errD_fake", "D_x"):
+        assert abs(m0[k] - m1[k]) <= 1e-5 * abs(m0[k]), (k, m0[k], m1[k])
+    for k in ("errG_fake", "errG_recon", "sim", "recon_dec"):
+        assert abs(m0[k] - m1[k]) <= 2e-3 * abs(m0[k]), (k, m0[k], m1[k])
+    for k in ("kld", "recon_enc"):
+        assert abs(m0[k] - m1[k]) <= 3e-2 * abs(m0[k]), (k, m0[k], m1[k])
+    assert float((eg0 - eg1).norm() / eg0.norm()) < 1e-2
+    assert float((d0 - d1).norm() / d0.norm()) < 1e-2
