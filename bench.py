@@ -215,9 +215,19 @@ def run_ours(args):
         T = tr.VAETrainer(m.to(dev), lr=3e-4)
         key = "loss"
 
-    if world == 1 and not args.no_graph:
-        T.enable_graph(b)  # whole-step CUDA graph: one launch per step instead of ~480
+    if not args.no_graph:
+        # whole-step CUDA graph: one launch per step instead of ~480 (for world > 1 the NCCL all-reduces are captured
+        # too; if that fails on this stack the trainer keeps launching eagerly)
+        try:
+            T.enable_graph(b)
+        except Exception as e:  # noqa: BLE001
+            if world == 1:
+                raise
+            T._graph = None
+            if rank == 0:
+                print(f"[bench] graph capture with NCCL failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
 
+    torch.manual_seed(999 + 7919 * (rank + 1))  # identical initial weights above, per-rank noise / eps streams below
     # synthetic CelebA-shaped inputs, U[-1,1]; a pool of distinct batches, per-rank seed
     npool = 8
     gen = torch.Generator().manual_seed(1234 + rank)
@@ -317,7 +327,13 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # leave without tearing down NCCL communicators that a captured CUDA graph still references (observed to hang
+        # at interpreter exit): everything has been printed and synchronised, so exit hard on every rank
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -183,7 +183,7 @@ def discriminator_forward(x, P, B, cache: OperandCache, training=True, col=None)
 
 
 def discriminator_backward(S, dprob, dfeat, P, G, cache: OperandCache, need_dx=True, need_wgrad=True,
-                           overwrite_big=False):
+                           overwrite_big=False, grad_ready=None):
     """Backward of discriminator_forward. dprob [b] / dfeat [b,2048] fp32 (either may be None).
     G: dict name -> fp32 grad tensor (accumulated) or None. Returns dx fp32 NCHW or None."""
     b = S.b
@@ -200,6 +200,8 @@ def discriminator_backward(S, dprob, dfeat, P, G, cache: OperandCache, need_dx=T
     wl = _lin_w(cache, "lth_features.0", P["lth_features.0.weight"])
     if wg:
         linear_wgrad(dpre, S.flat, b, 2048, 16384, wg["lth_features.0.weight"], overwrite_big)
+        if grad_ready:  # the 33.5 M-element gradient is final: its all-reduce can overlap the conv backward below
+            grad_ready("lth_features.0.weight")
     dflat = linear_dgrad(dpre, wl, b, 2048, 16384)
     da4 = ops.transpose(dflat, b, 256, 64)  # back to NHWC [b,64,256]
     # conv 4
@@ -266,7 +268,8 @@ def encoder_forward(x, P, B, cache: OperandCache, training=True, col=None):
     return outs[0], outs[1], S
 
 
-def encoder_backward(S, dmu, dlogvar, P, G, cache: OperandCache, need_wgrad=True, overwrite_big=False):
+def encoder_backward(S, dmu, dlogvar, P, G, cache: OperandCache, need_wgrad=True, overwrite_big=False,
+                     grad_ready=None):
     """dmu / dlogvar: fp32 [b,128] gradients w.r.t. the encoder outputs."""
     b = S.b
     dev = S.flat.device
@@ -287,6 +290,8 @@ def encoder_backward(S, dmu, dlogvar, P, G, cache: OperandCache, need_wgrad=True
         w0 = _lin_w(cache, head + ".0", P[head + ".0.weight"])
         if wg:
             linear_wgrad(dacc, S.flat, b, 2048, 16384, wg[head + ".0.weight"], overwrite_big)
+            if grad_ready:
+                grad_ready(head + ".0.weight")
         linear_dgrad(dacc, w0, b, 2048, 16384, out_dtype=F32, out=dflat)
     da3 = ops.transpose(ops.cast_bf16(dflat), b, 256, 64)
     dr3 = bn_act_backward(da3, S.bn3, wg, "features.7")

@@ -20,6 +20,8 @@ statistics stay per rank (as under the reference's nn.DataParallel).
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -28,6 +30,7 @@ from .ops import BF16, F32
 
 ALIGN = 64  # elements; keeps every parameter's bf16 shadow 128-byte aligned for TMA
 BIG_LINEAR = ("lth_features.0.weight", "x_to_mu.0.weight", "x_to_logvar.0.weight", "preprocess.0.weight")
+EARLY_BUCKETS = ("lth_features.0.weight", "x_to_mu.0.weight", "x_to_logvar.0.weight")  # all-reduced as soon as final
 
 
 class FlatParams:
@@ -81,7 +84,25 @@ class FlatParams:
             lo = b
         if lo < self.total:
             self._zero_ranges.append((lo, self.total))
+        # data parallel: the three 33.5 M-element gradients are all-reduced early, the remainder at phase end
+        early = sorted((self.offsets[n], self.offsets[n] + self.P[n].numel()) for n in self.names if n in EARLY_BUCKETS)
+        self._late_ranges, lo = [], 0
+        for a, b in early:
+            if a > lo:
+                self._late_ranges.append((lo, a))
+            lo = b
+        if lo < self.total:
+            self._late_ranges.append((lo, self.total))
         self.params_changed()
+
+    def reduce_early(self, reducer, name):
+        o = self.offsets[name]
+        reducer.allreduce_async(self.grad, o, o + self.P[name].numel())
+
+    def reduce_rest_and_wait(self, reducer):
+        for lo, hi in self._late_ranges:
+            reducer.allreduce_async(self.grad, lo, hi)
+        reducer.wait()
 
     def refresh_packs(self):
         for name, packs in self.cache.static_packs.items():
@@ -239,10 +260,16 @@ class _Base:
         ops.bce_const(prob, target, loss, 1.0, n_total=b * self.dist.world, dprob=dprob, stat=stat)
         return dprob
 
+    def _early(self, fp):
+        """grad_ready hook: all-reduce a big gradient bucket as soon as the backward pass has finished writing it."""
+        if not self.dist.on:
+            return None
+        return lambda name: fp.reduce_early(self.dist, name)
+
     # ------------------------------------------------------------------ CUDA graph
     def enable_graph(self, batch):
-        if self.dist.on:
-            raise RuntimeError("whole-step graph capture is implemented for world size 1 only")
+        if self.dist.on and os.environ.get("DM_GRAPH_DDP", "1") == "0":
+            raise RuntimeError("graph capture with collectives disabled (DM_GRAPH_DDP=0)")
         fps = self.flat_params()
         dev = fps[0].flat.device
         self._gx = torch.zeros(batch, 3, 64, 64, device=dev)
@@ -325,9 +352,9 @@ class VAETrainer(_Base):
         ops.kl(mu, logvar, loss, self.beta, dmu_kl, dlv_kl)
         dz = engine.decoder_backward(Sg, drecon, fp.P, fp.G, fp.cache, True, True, overwrite_big=True)
         _, _, dmu, dlv = ops.reparam_backward(dz, logvar, eps, dmu_kl, dlv_kl)
-        engine.encoder_backward(Se, dmu, dlv, fp.P, fp.G, fp.cache, True, overwrite_big=True)
-        self.dist.allreduce_async(fp.grad)
-        self.dist.wait()
+        engine.encoder_backward(Se, dmu, dlv, fp.P, fp.G, fp.cache, True, overwrite_big=True,
+                                grad_ready=self._early(fp))
+        fp.reduce_rest_and_wait(self.dist)
         fp.adam()
         self.metrics = {"loss": loss}
         return self.metrics
@@ -368,9 +395,9 @@ class GANTrainer(_Base):
         prob_f, _, S2 = engine.discriminator_forward(fake, fd.P, fd.buffers, fd.cache, True)
         d2 = self._bce(prob_f, fake_label, errD, sum_dgz1)
         engine.discriminator_backward(S1, d1, None, fd.P, fd.G, fd.cache, False, True, overwrite_big=True)
-        engine.discriminator_backward(S2, d2, None, fd.P, fd.G, fd.cache, False, True)
-        self.dist.allreduce_async(fd.grad)
-        self.dist.wait()
+        engine.discriminator_backward(S2, d2, None, fd.P, fd.G, fd.cache, False, True,
+                                      grad_ready=self._early(fd))
+        fd.reduce_rest_and_wait(self.dist)
         fd.adam()
         # ---- (2) generator: re-score the same fake batch with the updated D (:118-128)
         fg.zero_grad()
@@ -378,8 +405,7 @@ class GANTrainer(_Base):
         d3 = self._bce(prob_g, real_label, errG, sum_dgz2)
         dfake = engine.discriminator_backward(S3, d3, None, fd.P, None, fd.cache, True, False)
         engine.decoder_backward(Sg, dfake, fg.P, fg.G, fg.cache, False, True, overwrite_big=True)
-        self.dist.allreduce_async(fg.grad)
-        self.dist.wait()
+        fg.reduce_rest_and_wait(self.dist)
         fg.adam()
         self.metrics = {"errD": errD, "errG": errG, "D_x": sum_dx / b, "D_G_z1": sum_dgz1 / b, "D_G_z2": sum_dgz2 / b}
         return self.metrics
@@ -425,10 +451,10 @@ class BetaVAEGANTrainer(_Base):
         prob_f, _, S2 = engine.discriminator_forward(fake, fd.P, fd.buffers, fd.cache, True)
         d2 = self._bce(prob_f, fake_label, errD_fake)
         engine.discriminator_backward(S1, d1, None, fd.P, fd.G, fd.cache, False, True, overwrite_big=True)
-        engine.discriminator_backward(S2, d2, None, fd.P, fd.G, fd.cache, False, True)
+        engine.discriminator_backward(S2, d2, None, fd.P, fd.G, fd.cache, False, True,
+                                      grad_ready=self._early(fd))
         del S1, S2
-        self.dist.allreduce_async(fd.grad)
-        self.dist.wait()
+        fd.reduce_rest_and_wait(self.dist)
         fd.adam()
 
         # ================= "decoder" phase (:127-164): gradient of
@@ -455,10 +481,10 @@ class BetaVAEGANTrainer(_Base):
         ops.mse_sum(recon, data, loss_dec, 1.0, drecon, 1.0, accumulate=True)
         dz = engine.decoder_backward(Sg2, drecon, feg.P, feg.G, feg.cache, True, True)
         _, _, dmu, dlv = ops.reparam_backward(dz, logvar, eps_dec)
-        engine.encoder_backward(Se, dmu, dlv, feg.P, feg.G, feg.cache, True, overwrite_big=True)
+        engine.encoder_backward(Se, dmu, dlv, feg.P, feg.G, feg.cache, True, overwrite_big=True,
+                                grad_ready=self._early(feg))
         del S5, Sg2, Se
-        self.dist.allreduce_async(feg.grad)
-        self.dist.wait()
+        feg.reduce_rest_and_wait(self.dist)
         feg.adam()
 
         # ================= "encoder" phase (:167-193): gradient of beta*KL + ||recon - x||^2, fresh forward
@@ -474,9 +500,9 @@ class BetaVAEGANTrainer(_Base):
         ops.kl(mu, logvar, kld, self.beta, dmu_kl, dlv_kl)
         dz = engine.decoder_backward(Sg3, drecon, feg.P, feg.G, feg.cache, True, True, overwrite_big=True)
         _, _, dmu, dlv = ops.reparam_backward(dz, logvar, eps_enc, dmu_kl, dlv_kl)
-        engine.encoder_backward(Se, dmu, dlv, feg.P, feg.G, feg.cache, True, overwrite_big=True)
-        self.dist.allreduce_async(feg.grad)
-        self.dist.wait()
+        engine.encoder_backward(Se, dmu, dlv, feg.P, feg.G, feg.cache, True, overwrite_big=True,
+                                grad_ready=self._early(feg))
+        feg.reduce_rest_and_wait(self.dist)
         feg.adam()
         self.metrics = {"errD_real": errD_real, "errD_fake": errD_fake, "D_x": sum_dx / b, "errG_fake": errG_fake,
                         "errG_recon": errG_recon, "sim": sim_loss, "recon_dec": loss_dec, "kld": kld,

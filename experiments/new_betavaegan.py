@@ -35,6 +35,7 @@ def main():
         T.feg.params_changed()
         T.fd.params_changed()
         start = ck["epoch"]
+    torch.manual_seed(opt.seed + 7919 * (rank + 1))  # same initial weights on every rank, different noise / eps
     loader = Loader(opt, world, rank, dev)
     for epoch in range(start, opt.epochs):
         sums = None

@@ -20,6 +20,7 @@ def main():
     netG.apply(dm.weights_init)
     netD.apply(dm.weights_init)
     T = GANTrainer(netG, netD, lr=opt.lr)
+    torch.manual_seed(opt.seed + 7919 * (rank + 1))  # same initial weights on every rank, different noise / eps
     loader = Loader(opt, world, rank, dev)
     for epoch in range(opt.epochs):
         for i, data in enumerate(loader):

@@ -17,6 +17,7 @@ def main():
     model = dm.VAE(opt).to(dev)
     model.apply(dm.weights_init)
     T = VAETrainer(model, lr=opt.lr)
+    torch.manual_seed(opt.seed + 7919 * (rank + 1))  # same initial weights on every rank, different noise / eps
     loader = Loader(opt, world, rank, dev)
     for epoch in range(opt.epochs):
         total = None
