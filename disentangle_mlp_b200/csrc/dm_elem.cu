@@ -371,15 +371,16 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, lo
 }
 
 // ------------------------------------------------------------------------------------------ layout kernels
-// fp32 NCHW 3-channel image -> bf16 im2col matrix [batch*oh*ow, 128]; column = c*25 + kh*5 + kw (75 valid)
+// fp32 NCHW 3-channel image -> bf16 im2col matrix [batch*oh*ow, 80]; column = c*25 + kh*5 + kw (75 valid, 5 zero).
+// The GEMMs read it with K boxes of 32/64 columns: columns >= 80 are TMA out-of-bounds zero fill, never stored.
 __global__ void __launch_bounds__(256) im2col3_kernel(const float* __restrict__ x, int batch, int h, int w,
                                                       int stride, __nv_bfloat16* __restrict__ col) {
   const int oh = h / stride, ow = w / stride;
-  const long long total = static_cast<long long>(batch) * oh * ow * 16;  // 16 groups of 8 columns per pixel
+  const long long total = static_cast<long long>(batch) * oh * ow * 10;  // 10 groups of 8 columns per pixel
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int grp = static_cast<int>(idx & 15);
-    const long long pix = idx >> 4;
+    const int grp = static_cast<int>(idx % 10);
+    const long long pix = idx / 10;
     const int x0 = static_cast<int>(pix % ow);
     const int y0 = static_cast<int>((pix / ow) % oh);
     const int n = static_cast<int>(pix / (static_cast<long long>(ow) * oh));
@@ -395,7 +396,7 @@ __global__ void __launch_bounds__(256) im2col3_kernel(const float* __restrict__ 
       }
       f[i] = v;
     }
-    store8(col + pix * 128 + grp * 8, f);
+    store8(col + pix * 80 + grp * 8, f);
   }
 }
 
@@ -847,7 +848,7 @@ extern "C" int dm_colsum(const void* x, int x_f32, long long rows, int c, float*
 extern "C" int dm_im2col3(const float* x_nchw, int batch, int h, int w, int stride, void* col_bf16, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   DM_REQUIRE(stride == 1 || stride == 2, "dm_im2col3: stride must be 1 or 2");
-  const long long items = static_cast<long long>(batch) * (h / stride) * (w / stride) * 16;
+  const long long items = static_cast<long long>(batch) * (h / stride) * (w / stride) * 10;
   im2col3_kernel<<<grid_for(items, 256, 148 * 32), 256, 0, s>>>(x_nchw, batch, h, w, stride, static_cast<bf16*>(col_bf16));
   DM_LAUNCHED("dm_im2col3");
 }

@@ -72,27 +72,49 @@ class BNState:
     act: int
 
 
-def bn_act_forward(y, rows, c, P, B, prefix, act, training=True):
-    """BatchNorm (batch statistics, running-stat update) + activation. P: params, B: buffers."""
+def bn_act_forward(y, rows, c, P, B, prefix, act, training=True, groups=1):
+    """BatchNorm (batch statistics, running-stat update) + activation. P: params, B: buffers.
+
+    groups > 1: `y` holds `groups` independent batches stacked along rows (several forward passes of the same
+    network pushed through each GEMM together); statistics, normalisation and the running-stat updates are done
+    per group, in order -- exactly what separate forward calls would do.  Returns (out, [BNState per group])."""
     gamma, beta = P[prefix + ".weight"], P[prefix + ".bias"]
     rm, rv, nbt = B[prefix + ".running_mean"], B[prefix + ".running_var"], B[prefix + ".num_batches_tracked"]
-    if training:
-        sums = ops.bn_stats(y, rows, c)
-        ss, mi = ops.bn_finalize(sums, rows, c, gamma.detach(), beta.detach(), rm, rv, nbt, BN_MOMENTUM, BN_EPS)
-    else:  # inference statistics (the reference scripts never call .eval(); kept for completeness)
-        invstd = torch.rsqrt(rv + BN_EPS)
-        sc = gamma.detach() * invstd
-        ss = torch.stack([sc, beta.detach() - rm * sc]).contiguous()
-        mi = torch.stack([rm, invstd]).contiguous()
-    out = ops.bn_apply_act(y, rows, c, ss, act, LEAKY)
-    return out, BNState(y, rows, c, ss, mi, act)
+    rg = rows // groups
+    y2 = y.view(rows, c)
+    out = torch.empty(y.shape, dtype=BF16, device=y.device)
+    o2 = out.view(rows, c)
+    states = []
+    for g in range(groups):
+        ys = y2[g * rg:(g + 1) * rg]
+        if training:
+            partials = ops.bn_stats(ys, rg, c)
+            ss, mi = ops.bn_finalize(partials, rg, c, gamma.detach(), beta.detach(), rm, rv, nbt, BN_MOMENTUM, BN_EPS)
+        else:  # inference statistics (the reference scripts never call .eval(); kept for completeness)
+            invstd = torch.rsqrt(rv + BN_EPS)
+            sc = gamma.detach() * invstd
+            ss = torch.stack([sc, beta.detach() - rm * sc]).contiguous()
+            mi = torch.stack([rm, invstd]).contiguous()
+        ops.bn_apply_act(ys, rg, c, ss, act, LEAKY, out=o2[g * rg:(g + 1) * rg])
+        states.append(BNState(ys, rg, c, ss, mi, act))
+    return out, states
 
 
-def bn_act_backward(dout, st: BNState, G, prefix):
-    """Returns dy (bf16); accumulates dgamma / dbeta into G when present."""
+def bn_act_backward(dout, states, G, prefix):
+    """Backward of bn_act_forward over the given per-group states (dout rows stacked in the same order).
+    Returns dy (bf16); accumulates dgamma / dbeta into G when present."""
     dg = G.get(prefix + ".weight") if G is not None else None
     db = G.get(prefix + ".bias") if G is not None else None
-    dy, _ = ops.bn_backward(dout, st.y, st.rows, st.c, st.scale_shift, st.mean_invstd, st.act, LEAKY, dg, db)
+    c = states[0].c
+    rows = sum(st.rows for st in states)
+    d2 = dout.view(rows, c)
+    dy = torch.empty(dout.shape, dtype=BF16, device=dout.device)
+    y2 = dy.view(rows, c)
+    r0 = 0
+    for st in states:
+        ops.bn_backward(d2[r0:r0 + st.rows], st.y, st.rows, st.c, st.scale_shift, st.mean_invstd, st.act, LEAKY, dg, db,
+                        out=y2[r0:r0 + st.rows])
+        r0 += st.rows
     return dy
 
 
@@ -142,37 +164,39 @@ def conv_wgrad(g, small, big, dw, cache, name):
 
 def col_conv_forward(col, w_col, bias, rows, cs):
     """3-channel convolution as a GEMM over the im2col matrix: raw[rows, cs] (bf16)."""
-    return ops.gemm(GEMM_NT, col, w_col, rows, cs, 128, out_dtype=BF16, bias=bias, k_alg=75)
+    return ops.gemm(GEMM_NT, col, w_col, rows, cs, ops.COL_K, out_dtype=BF16, bias=bias, k_alg=75)
 
 
 def col_conv_wgrad(col, dy, rows, cs, dw):
     """dw[cs][3][5][5] (viewed [cs][75]) += dy^T @ col ; computed as D[k, cs] = col^T dy with a transposed store."""
     splits = max(1, min(rows // 64, 296))
-    ops.gemm(GEMM_TN, col, dy.view(rows, cs), 128, cs, rows, out=dw, accumulate=True, splits=splits, ldd_m=1, ldd_n=75, m_store=75,
+    ops.gemm(GEMM_TN, col, dy.view(rows, cs), ops.COL_K, cs, rows, out=dw, accumulate=True, splits=splits, ldd_m=1, ldd_n=75, m_store=75,
              n_store=cs)
 
 
 # ------------------------------------------------------------------------------------------ Discriminator
-def discriminator_forward(x, P, B, cache: OperandCache, training=True, col=None):
-    """Discriminator_celeba.forward (model.py:410-416). x: fp32 NCHW [b,3,64,64]. Returns prob [b], feat [b,2048]."""
+def discriminator_forward(x, P, B, cache: OperandCache, training=True, col=None, groups=1):
+    """Discriminator_celeba.forward (model.py:410-416). x: fp32 NCHW [b,3,64,64]. Returns prob [b], feat [b,2048].
+    groups > 1: x stacks `groups` separate batches (e.g. real | fake); every GEMM processes them together while
+    BatchNorm treats each group as its own forward pass (see bn_act_forward)."""
     b = x.shape[0]
-    S = SimpleNamespace(b=b)
+    S = SimpleNamespace(b=b, groups=groups)
     S.col = ops.im2col3(x, 1) if col is None else col
     _, _, wc1 = _conv_pack(cache, "convs.0", P["convs.0.weight"], 32, 3)
     raw1 = col_conv_forward(S.col, wc1, P["convs.0.bias"].detach(), b * 4096, 32)
-    S.a1, S.bn1 = bn_act_forward(raw1, b * 4096, 32, P, B, "convs.1", ACT_LEAKY, training)
+    S.a1, S.bn1 = bn_act_forward(raw1, b * 4096, 32, P, B, "convs.1", ACT_LEAKY, training, groups)
     g2 = ops.geom(b, 32, 32, 128, 32, 2)
     wd2, _, _ = _conv_pack(cache, "convs.3", P["convs.3.weight"], 128, 32)
     raw2 = ops.conv_down(g2, S.a1, wd2, P["convs.3.bias"].detach())
-    S.a2, S.bn2 = bn_act_forward(raw2, b * 1024, 128, P, B, "convs.4", ACT_LEAKY, training)
+    S.a2, S.bn2 = bn_act_forward(raw2, b * 1024, 128, P, B, "convs.4", ACT_LEAKY, training, groups)
     g3 = ops.geom(b, 16, 16, 256, 128, 2)
     wd3, _, _ = _conv_pack(cache, "convs.6", P["convs.6.weight"], 256, 128)
     raw3 = ops.conv_down(g3, S.a2, wd3, P["convs.6.bias"].detach())
-    S.a3, S.bn3 = bn_act_forward(raw3, b * 256, 256, P, B, "convs.7", ACT_LEAKY, training)
+    S.a3, S.bn3 = bn_act_forward(raw3, b * 256, 256, P, B, "convs.7", ACT_LEAKY, training, groups)
     g4 = ops.geom(b, 8, 8, 256, 256, 2)
     wd4, _, _ = _conv_pack(cache, "convs.9", P["convs.9.weight"], 256, 256)
     raw4 = ops.conv_down(g4, S.a3, wd4, P["convs.9.bias"].detach())
-    a4, S.bn4 = bn_act_forward(raw4, b * 64, 256, P, B, "convs.10", ACT_LEAKY, training)
+    a4, S.bn4 = bn_act_forward(raw4, b * 64, 256, P, B, "convs.10", ACT_LEAKY, training, groups)
     S.flat = ops.transpose(a4, b, 64, 256)  # NHWC [b,64,256] -> NCHW flatten order [b,256*64]
     wl = _lin_w(cache, "lth_features.0", P["lth_features.0.weight"])
     acc = linear_forward(S.flat, wl, None, b, 2048, 16384)
@@ -182,10 +206,27 @@ def discriminator_forward(x, P, B, cache: OperandCache, training=True, col=None)
     return S.prob, S.feat, S
 
 
+def _slice_disc(S, g0, g1):
+    """View of a discriminator forward record restricted to groups [g0, g1) (batch-major tensors: contiguous)."""
+    if g0 == 0 and g1 == S.groups:
+        return S
+    bg = S.b // S.groups
+    i0, i1 = g0 * bg, g1 * bg
+    V = SimpleNamespace(b=i1 - i0, groups=g1 - g0)
+    V.col = S.col[i0 * 4096:i1 * 4096]
+    V.a1, V.a2, V.a3 = S.a1[i0:i1], S.a2[i0:i1], S.a3[i0:i1]
+    V.flat, V.feat, V.prob = S.flat[i0:i1], S.feat[i0:i1], S.prob[i0:i1]
+    V.bn1, V.bn2, V.bn3, V.bn4 = S.bn1[g0:g1], S.bn2[g0:g1], S.bn3[g0:g1], S.bn4[g0:g1]
+    return V
+
+
 def discriminator_backward(S, dprob, dfeat, P, G, cache: OperandCache, need_dx=True, need_wgrad=True,
-                           overwrite_big=False, grad_ready=None):
+                           overwrite_big=False, grad_ready=None, group_range=None):
     """Backward of discriminator_forward. dprob [b] / dfeat [b,2048] fp32 (either may be None).
-    G: dict name -> fp32 grad tensor (accumulated) or None. Returns dx fp32 NCHW or None."""
+    G: dict name -> fp32 grad tensor (accumulated) or None. Returns dx fp32 NCHW or None.
+    group_range=(g0, g1): back-propagate only through those groups of a grouped forward (b = their images)."""
+    if group_range is not None:
+        S = _slice_disc(S, *group_range)
     b = S.b
     dev = S.feat.device
     if dprob is None:

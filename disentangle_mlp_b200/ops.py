@@ -14,6 +14,7 @@ from . import _lib
 from ._lib import GEMM_NN, GEMM_NT, GEMM_TN, ConvGeom, GemmDesc
 
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+COL_K = 80  # stored columns of the 3-channel im2col matrix (75 valid); the GEMM's K boxes zero-fill beyond
 BF16 = torch.bfloat16
 F32 = torch.float32
 
@@ -162,9 +163,9 @@ def bn_apply_act(y, rows, c, scale_shift, act, slope=0.2, out=None):
     return out
 
 
-def bn_backward(dout, y, rows, c, scale_shift, mean_invstd, act, slope=0.2, dgamma=None, dbeta=None):
+def bn_backward(dout, y, rows, c, scale_shift, mean_invstd, act, slope=0.2, dgamma=None, dbeta=None, out=None):
     assert dout.dtype == BF16
-    dy = torch.empty(y.shape, dtype=BF16, device=y.device)
+    dy = torch.empty(y.shape, dtype=BF16, device=y.device) if out is None else out
     partials = torch.empty((bn_parts(rows, c), 2, c), dtype=F32, device=y.device)
     sums = torch.empty((2, c), dtype=F32, device=y.device)
     _lib.check(_lib.load().dm_bn_backward(_p(dout), _p(y), int(y.dtype == F32), rows, c, _p(scale_shift),
@@ -199,7 +200,7 @@ def im2col3(x_nchw, stride, out=None):
     b, ch, h, w = x_nchw.shape
     assert ch == 3 and x_nchw.dtype == F32
     if out is None:
-        out = torch.empty((b * (h // stride) * (w // stride), 128), dtype=BF16, device=x_nchw.device)
+        out = torch.empty((b * (h // stride) * (w // stride), COL_K), dtype=BF16, device=x_nchw.device)
     _lib.check(_lib.load().dm_im2col3(_p(x_nchw), b, h, w, stride, _p(out), _stream()), "dm_im2col3")
     return out
 

@@ -385,18 +385,20 @@ class GANTrainer(_Base):
         fg, fd, dev = self.fg, self.fd, data.device
         b = data.shape[0]
         errD, errG, sum_dx, sum_dgz1, sum_dgz2 = (_scalar(dev) for _ in range(5))
-        # ---- (1) discriminator: real batch, then detached fake batch (:84-113)
+        # ---- (1) discriminator: real batch, then detached fake batch (:84-113).  Both forward passes go through every
+        # GEMM together (stacked along the batch); BatchNorm statistics / running stats stay per pass, real first.
         fd.zero_grad()
-        prob_r, _, S1 = engine.discriminator_forward(data, fd.P, fd.buffers, fd.cache, True)
-        d1 = self._bce(prob_r, real_label, errD, sum_dx)
         if noise is None:
             noise = torch.randn(b, 128, device=dev)
         fake, Sg = engine.decoder_forward(noise, fg.P, fg.buffers, fg.cache, True)
-        prob_f, _, S2 = engine.discriminator_forward(fake, fd.P, fd.buffers, fd.cache, True)
-        d2 = self._bce(prob_f, fake_label, errD, sum_dgz1)
-        engine.discriminator_backward(S1, d1, None, fd.P, fd.G, fd.cache, False, True, overwrite_big=True)
-        engine.discriminator_backward(S2, d2, None, fd.P, fd.G, fd.cache, False, True,
+        prob, _, S12 = engine.discriminator_forward(torch.cat([data, fake]), fd.P, fd.buffers, fd.cache, True, groups=2)
+        dprob = torch.empty_like(prob)
+        nt = b * self.dist.world
+        ops.bce_const(prob[:b], real_label, errD, 1.0, n_total=nt, dprob=dprob[:b], stat=sum_dx)
+        ops.bce_const(prob[b:], fake_label, errD, 1.0, n_total=nt, dprob=dprob[b:], stat=sum_dgz1)
+        engine.discriminator_backward(S12, dprob, None, fd.P, fd.G, fd.cache, False, True, overwrite_big=True,
                                       grad_ready=self._early(fd))
+        del S12
         fd.reduce_rest_and_wait(self.dist)
         fd.adam()
         # ---- (2) generator: re-score the same fake batch with the updated D (:118-128)
@@ -438,22 +440,22 @@ class BetaVAEGANTrainer(_Base):
         b = data.shape[0]
         (errD_real, errD_fake, sum_dx, errG_fake, errG_recon, sim_loss, loss_dec, kld, loss_enc) = (
             _scalar(dev) for _ in range(9))
-        col_d = ops.im2col3(data, 1)  # the D-side and encoder-side im2col of `data` are reused within the step
-        col_e = ops.im2col3(data, 2)
+        col_e = ops.im2col3(data, 2)  # the encoder-side im2col of `data` is shared by the two encoder forwards
 
-        # ================= discriminator phase (:95-123)
+        # ================= discriminator phase (:95-123).  D(data) and D(fake.detach()) share every GEMM launch
+        # (stacked along the batch); BatchNorm statistics / running-stat updates stay per pass, real first.
         fd.zero_grad()
-        prob_r, _, S1 = engine.discriminator_forward(data, fd.P, fd.buffers, fd.cache, True, col=col_d)
-        d1 = self._bce(prob_r, real_label, errD_real, sum_dx)
+        nt = b * self.dist.world
         if noise is None:
             noise = torch.randn(b, 128, device=dev)
         fake, Sg1 = engine.decoder_forward(noise, feg.P, feg.buffers, feg.cache, True)
-        prob_f, _, S2 = engine.discriminator_forward(fake, fd.P, fd.buffers, fd.cache, True)
-        d2 = self._bce(prob_f, fake_label, errD_fake)
-        engine.discriminator_backward(S1, d1, None, fd.P, fd.G, fd.cache, False, True, overwrite_big=True)
-        engine.discriminator_backward(S2, d2, None, fd.P, fd.G, fd.cache, False, True,
+        prob, _, S12 = engine.discriminator_forward(torch.cat([data, fake]), fd.P, fd.buffers, fd.cache, True, groups=2)
+        dprob = torch.empty_like(prob)
+        ops.bce_const(prob[:b], real_label, errD_real, 1.0, n_total=nt, dprob=dprob[:b], stat=sum_dx)
+        ops.bce_const(prob[b:], fake_label, errD_fake, 1.0, n_total=nt, dprob=dprob[b:])
+        engine.discriminator_backward(S12, dprob, None, fd.P, fd.G, fd.cache, False, True, overwrite_big=True,
                                       grad_ready=self._early(fd))
-        del S1, S2
+        del S12
         fd.reduce_rest_and_wait(self.dist)
         fd.adam()
 
@@ -461,29 +463,33 @@ class BetaVAEGANTrainer(_Base):
         #   BCE(D(fake), real) + BCE(D(recon), real) + 0.5*||Dis_l(recon) - Dis_l(x)||^2 + ||recon - x||^2
         # w.r.t. ALL encoder and decoder parameters, D frozen at its updated value
         feg.zero_grad()
-        _, sim_real, S3 = engine.discriminator_forward(data, fd.P, fd.buffers, fd.cache, True, col=col_d)
-        del S3  # sim_real's path into D only produces discarded D gradients (:95)
         mu, logvar, Se = engine.encoder_forward(data, feg.P, feg.buffers, feg.cache, True, col=col_e)
         if eps_dec is None:
             eps_dec = torch.randn_like(mu)
         _, z16 = ops.reparam_forward(mu, logvar, eps_dec)
         recon, Sg2 = engine.decoder_forward(z16, feg.P, feg.buffers, feg.cache, True)
-        prob_f2, _, S4 = engine.discriminator_forward(fake, fd.P, fd.buffers, fd.cache, True)
-        prob_rc, sim_recon, S5 = engine.discriminator_forward(recon, fd.P, fd.buffers, fd.cache, True)
-        d4 = self._bce(prob_f2, real_label, errG_fake)
-        d5 = self._bce(prob_rc, real_label, errG_recon)
-        dsim = torch.empty_like(sim_recon)
-        ops.mse_sum(sim_recon, sim_real, sim_loss, 0.5, dsim, 0.5)
-        dfake = engine.discriminator_backward(S4, d4, None, fd.P, None, fd.cache, True, False)
+        # D(data) | D(fake) | D(recon) in one stacked pass (BatchNorm per pass, in the reference's order :129,147,150)
+        prob3, feat3, S345 = engine.discriminator_forward(torch.cat([data, fake, recon]), fd.P, fd.buffers, fd.cache,
+                                                          True, groups=3)
+        sim_real, sim_recon = feat3[:b], feat3[2 * b:]
+        dprob2 = torch.empty(2 * b, dtype=F32, device=dev)
+        ops.bce_const(prob3[b:2 * b], real_label, errG_fake, 1.0, n_total=nt, dprob=dprob2[:b])
+        ops.bce_const(prob3[2 * b:], real_label, errG_recon, 1.0, n_total=nt, dprob=dprob2[b:])
+        dfeat2 = torch.zeros((2 * b, 2048), dtype=F32, device=dev)
+        ops.mse_sum(sim_recon, sim_real, sim_loss, 0.5, dfeat2[b:], 0.5)
+        # back through D for the fake and recon passes only: sim_real's path into D (and every D weight gradient of
+        # this phase) is discarded by the reference's next netD.zero_grad() (:95)
+        dx = engine.discriminator_backward(S345, dprob2, dfeat2, fd.P, None, fd.cache, True, False, group_range=(1, 3))
+        del S345
+        dfake, drecon = dx[:b], dx[b:]
         engine.decoder_backward(Sg1, dfake, feg.P, feg.G, feg.cache, False, True, overwrite_big=True)
-        del S4, Sg1
-        drecon = engine.discriminator_backward(S5, d5, dsim, fd.P, None, fd.cache, True, False)
+        del Sg1
         ops.mse_sum(recon, data, loss_dec, 1.0, drecon, 1.0, accumulate=True)
         dz = engine.decoder_backward(Sg2, drecon, feg.P, feg.G, feg.cache, True, True)
         _, _, dmu, dlv = ops.reparam_backward(dz, logvar, eps_dec)
         engine.encoder_backward(Se, dmu, dlv, feg.P, feg.G, feg.cache, True, overwrite_big=True,
                                 grad_ready=self._early(feg))
-        del S5, Sg2, Se
+        del Sg2, Se
         feg.reduce_rest_and_wait(self.dist)
         feg.adam()
 

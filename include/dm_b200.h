@@ -124,7 +124,7 @@ int dm_act_backward(const float* dout, const float* out, long long rows, int c, 
 /* colsum[c] += sum_r x[r][c] */
 int dm_colsum(const void* x, int x_f32, long long rows, int c, float* partials, float* colsum, void* stream);
 
-/* fp32 NCHW [b,3,h,w] image -> bf16 im2col matrix [b*(h/s)*(w/s), 128], column c*25+kh*5+kw (75 valid):
+/* fp32 NCHW [b,3,h,w] image -> bf16 im2col matrix [b*(h/s)*(w/s), 80], column c*25+kh*5+kw (75 valid):
  * the A operand of the two 3-channel convolutions (model.py:449, 389) and of deconv4's input-gradient. */
 int dm_im2col3(const float* x_nchw, int batch, int h, int w, int stride, void* col_bf16, void* stream);
 /* fp32 NHWC(3) -> fp32 NCHW, optionally through nn.Tanh (model.py:509,565). */

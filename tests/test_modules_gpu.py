@@ -157,7 +157,7 @@ def test_per_layer_parity_discriminator(env):
     col = ops.im2col3(inp.detach().cuda(), 1)
     _, wu, wc = ops.pack_conv_weights(ref.convs[0].weight.detach().cuda(), 32, 3, True, True, True)
     b = inp.shape[0]
-    y = ops.gemm(ops.GEMM_NT, col, wc, b * 4096, 32, 128, out_dtype=torch.bfloat16, bias=ref.convs[0].bias.detach().cuda())
+    y = ops.gemm(ops.GEMM_NT, col, wc, b * 4096, 32, ops.COL_K, out_dtype=torch.bfloat16, bias=ref.convs[0].bias.detach().cuda())
     assert rel(from_nhwc(y.view(b, 64, 64, 32)), out) < TOL_LAYER
     dx = ops.conv_up(ops.geom(b, 64, 64, 32, 3, 1), nhwc16(out.grad), wu, out_f32=True)
     assert rel(from_nhwc(dx), inp.grad) < TOL_LAYER
@@ -194,7 +194,7 @@ def test_per_layer_parity_vae(env):
     y = ops.conv_up(ops.geom(b, 64, 64, 32, 3, 1), nhwc16(inp), wu, ref.deconv4.bias.detach().cuda(), out_f32=True)
     assert rel(from_nhwc(y), out) < TOL_LAYER
     col = ops.im2col3(out.grad.detach().cuda().contiguous(), 1)
-    dx = ops.gemm(ops.GEMM_NT, col, wc, b * 4096, 32, 128, out_dtype=torch.bfloat16)
+    dx = ops.gemm(ops.GEMM_NT, col, wc, b * 4096, 32, ops.COL_K, out_dtype=torch.bfloat16)
     assert rel(from_nhwc(dx.view(b, 64, 64, 32)), inp.grad) < TOL_LAYER
 
 
