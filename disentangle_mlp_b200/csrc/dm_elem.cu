@@ -487,7 +487,13 @@ __global__ void __launch_bounds__(256) pack_conv_kernel(const float* __restrict_
     if (w_up) {
       if (j < n_up) {
         const int s = static_cast<int>(j % cs), b = static_cast<int>((j / cs) % cb_pad), t = static_cast<int>(j / (static_cast<long long>(cs) * cb_pad));
-        w_up[j] = __float2bfloat16_rn(b < cb ? w[(static_cast<long long>(s) * cb + b) * 25 + t] : 0.f);
+        float v = 0.f;
+        if (cb == 3) {  // folded layout [kh][kw*3 + cb][cs] (t = kh < 5, b = kw*3 + cb < 15): see dm_conv_up
+          if (t < 5 && b < 15) v = w[(static_cast<long long>(s) * 3 + (b % 3)) * 25 + t * 5 + b / 3];
+        } else if (b < cb) {
+          v = w[(static_cast<long long>(s) * cb + b) * 25 + t];
+        }
+        w_up[j] = __float2bfloat16_rn(v);
         continue;
       }
       j -= n_up;

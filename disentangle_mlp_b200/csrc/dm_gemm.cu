@@ -69,6 +69,8 @@ struct alignas(64) GemmParams {
   void* out;
   const float* bias;
   int out_f32, out_atomic;
+  int fold_kw;  // FWD, stride-1 transposed conv to 3 channels: accumulator column = kw*3 + cb, epilogue sums the
+                // five horizontally shifted partial results (out[w] = sum_kw acc[w + 2 - kw][kw])
   // FWD epilogue: element offset of row (w,h,n) and column j
   long long os_w, os_h, os_n, os_col;
   long long phase_out_off[4];
@@ -144,6 +146,7 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
   uint64_t* tmem_full_bar = empty_bar + p.stages;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* fold_buf = reinterpret_cast<float*>(tmem_ptr_smem + 4);  // [128][17] fp32, fold_kw epilogue only
 
   // ---- one-time setup
   if (warp == 0 && lane == 0) {
@@ -295,7 +298,40 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
       const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * p.acc_stride);
       const int m_tile = w.m_tile, n_tile = w.n_tile;
 
-      if (p.mode == MODE_FWD) {
+      if (p.mode == MODE_FWD && p.fold_kw) {
+        // tile = bh full image rows of bw pixels; thread r = pixel (h, w').  acc[w'][kw*3+cb] holds the sum over kh
+        // and cs for UNSHIFTED w'; out[h][w][cb] = sum_kw acc[h][w + 2 - kw][kw*3 + cb] (zero outside the row).
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld_32x32(lane_addr, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 15; ++i) fold_buf[r * 17 + i] = __uint_as_float(v[i]);
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+        const int wq = r % p.bw, hq = r / p.bw;
+        const int h = (m_tile % p.tpi) * p.th_step + hq % p.bh;
+        const int n = (m_tile / p.tpi) * p.tn_step + hq / p.bh;
+        float o[3];
+#pragma unroll
+        for (int cb = 0; cb < 3; ++cb) o[cb] = p.bias ? __ldg(p.bias + cb) : 0.f;
+#pragma unroll
+        for (int kw = 0; kw < 5; ++kw) {
+          const int ws = wq + 2 - kw;
+          if (ws >= 0 && ws < p.bw) {
+            const float* src = fold_buf + (hq * p.bw + ws) * 17 + kw * 3;
+            o[0] += src[0];
+            o[1] += src[1];
+            o[2] += src[2];
+          }
+        }
+        if (n < p.n_lim) {
+          const long long off = wq * p.os_w + h * p.os_h + n * p.os_n;
+          outf[off] = o[0];
+          outf[off + 1] = o[1];
+          outf[off + 2] = o[2];
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // fold_buf is reused by the next tile
+      } else if (p.mode == MODE_FWD) {
         const int wx = m_tile * p.tw_step + r % p.bw;
         const int h = (m_tile % p.tpi) * p.th_step + (r / p.bw) % p.bh;
         const int n = (m_tile / p.tpi) * p.tn_step + r / (p.bw * p.bh);
@@ -536,7 +572,7 @@ static int launch(GemmParams& p, dim3 grid, cudaStream_t stream, double flops, i
   int stages = std::max(2, std::min(8, budget / stage_bytes));
   stages = static_cast<int>(std::max<long long>(1, std::min<long long>(stages, kb_stream)));
   p.stages = stages;
-  int smem = stages * stage_bytes + (2 * stages + 4) * 8 + 16 + 1024;
+  int smem = stages * stage_bytes + (2 * stages + 4) * 8 + 16 + 1024 + (p.fold_kw ? 128 * 17 * 4 : 0);
   // TMEM is 512 columns per SM: keep co-residency at <= 512 / tmem_cols CTAs by padding the smem request
   smem = std::max(smem, (two_per_sm ? 80 : 120) * 1024);
   static std::once_flag once;
@@ -835,7 +871,24 @@ extern "C" int dm_conv_up(const dm_conv_geom* g, const void* small, const void* 
   p.bn = pick_bn(cb_pad, env_int("DM_BN_CAP", 128));
   p.cpt = g->cs / p.kc;
   int nphase = 0, nt = 0;
-  if (g->stride == 1) {
+  const bool fold = (g->stride == 1 && g->cb == 3);
+  DM_REQUIRE(!fold || out_f32, "dm_conv_up: the 3-channel image side is written as fp32");
+  if (fold) {
+    // 5 k-blocks (one per kh) instead of 25: the A box is shifted vertically only, the 5 horizontal taps live in
+    // the N dimension (w_up for this layer is packed as [5][16 = kw*3+cb][32], see dm_pack_conv_weights)
+    p.fold_kw = 1;
+    p.bn = 16;
+    p.phase_tap_start[0] = 0;
+    for (int kh = 0; kh < 5; ++kh) {
+      Tap& t = p.taps[nt++];
+      t.dh = static_cast<int8_t>(2 - kh);
+      t.dw = 0;
+      t.wt = static_cast<uint8_t>(kh);
+    }
+    p.phase_tap_start[1] = nt;
+    nphase = 1;
+    p.os_w = g->cb; p.os_h = (long long)g->wb * g->cb;
+  } else if (g->stride == 1) {
     p.phase_tap_start[0] = 0;
     for (int kh = 0; kh < 5; ++kh)
       for (int kw = 0; kw < 5; ++kw) {
@@ -872,7 +925,7 @@ extern "C" int dm_conv_up(const dm_conv_geom* g, const void* small, const void* 
   p.w_lim = g->ws; p.n_lim = g->batch; p.n_valid = g->cb;
   uint32_t box[5] = {(uint32_t)p.kc, (uint32_t)pt.bw, 1, (uint32_t)pt.bh, (uint32_t)pt.bimg};
   if (int rc = encode_act_map(&p.map_a, small, g->batch, g->hs, g->ws, g->cs, 1, box, p.kc * 2)) return rc;
-  if (int rc = encode_w_map3(&p.map_b, w_up, 25, cb_pad, g->cs, g->cs, p.kc, p.bn, p.kc * 2)) return rc;
+  if (int rc = encode_w_map3(&p.map_b, w_up, fold ? 5 : 25, cb_pad, g->cs, g->cs, p.kc, p.bn, p.kc * 2)) return rc;
   p.num_n_tiles = (cb_pad + p.bn - 1) / p.bn;
   return launch(p, dim3(pt.tiles, p.num_n_tiles, nphase), stream, 50.0 * g->batch * g->hs * g->ws * g->cs * g->cb);
 }

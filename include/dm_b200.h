@@ -136,7 +136,8 @@ int dm_tanh_backward(const float* dout, const float* out, long long batch, int h
  * Linear layers are defined on (model.py:516-517, 540-543, 412-413). */
 int dm_transpose_bf16(const void* src, int batch, int rows, int cols, void* dst, void* stream);
 /* fp32 weight [cs][cb][5][5] -> bf16 operand packs: w_down [25][cs][cb], w_up [25][cb_pad][cs],
- * w_col [cs][128] (only when cb*25 <= 128).  Any output may be NULL. */
+ * w_col [cs][128] (only when cb*25 <= 128).  Any output may be NULL.  For cb == 3 the first 5 planes of w_up hold the
+ * kw-folded layout [kh][kw*3+cb][cs] that dm_conv_up uses for the 3-channel image side. */
 int dm_pack_conv_weights(const float* w, int cs, int cb, void* w_down, void* w_up, void* w_col, void* stream);
 int dm_cast_bf16(const float* src, long long n, void* dst, void* stream);
 

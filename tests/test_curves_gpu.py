@@ -1,0 +1,91 @@
+"""GPU: 200-step loss curves of the fused trainers against the oracle's golden curves (tests/golden/curves_*.json,
+written by oracle/gen_curves.py) with identical initial weights, data, labels, noise and eps.
+
+The north-star tolerance for bf16 is 1e-2 per layer.  A 200-step TRAJECTORY of a GAN is chaotic, so each curve is
+judged against the reference's own sensitivity: the golden file also holds the oracle re-run with its input images
+perturbed by 1e-3 ("perturbed").  The CUDA path must stay within max(stated tolerance, 3x that chaos floor) in
+the median over the 200 steps, and within the stated tolerance over the first 10 steps.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+# key -> (tolerance over the first 10 steps, tolerance on the 200-step median deviation)
+TOL = {
+    "vae": {"loss": (1e-2, 1e-2)},
+    "gan": {"errD": (5e-2, 1e-1), "errG": (5e-2, 1e-1)},
+    "betavaegan": {"recon_dec": (3e-2, 3e-2), "recon_enc": (5e-2, 3e-2), "kld": (1.5e-1, 5e-2), "sim": (1.0, 2e-1)},
+}
+
+
+def run_cuda(workload, doc):
+    from disentangle_mlp_b200 import model as dm
+    from disentangle_mlp_b200 import trainer as tr
+
+    meta = doc["meta"]
+    b, steps = meta["batch"], meta["steps"]
+    g = torch.Generator().manual_seed(meta["data_seed"])
+    x = (torch.rand(b, 3, 64, 64, generator=g) * 2 - 1).cuda()
+    torch.manual_seed(meta["seed"])
+    opt = dm.default_opt()
+    if workload == "vae":
+        m = dm.VAE(opt)
+        m.apply(dm.weights_init)
+        T, n = tr.VAETrainer(m.cuda(), lr=3e-4), 1
+    elif workload == "gan":
+        gen, d = dm.Generator_celeba(opt), dm.Discriminator_celeba(opt)
+        gen.apply(dm.weights_init)
+        d.apply(dm.weights_init)
+        T, n = tr.GANTrainer(gen.cuda(), d.cuda(), lr=3e-4), 1
+    else:
+        eg, d = dm.VAE(opt), dm.Discriminator_celeba(opt)
+        eg.apply(dm.weights_init)
+        d.apply(dm.weights_init)
+        T, n = tr.BetaVAEGANTrainer(eg.cuda(), d.cuda(), beta=25.0, lr=1e-3), 3
+    out = []
+    for s in range(steps):
+        gs = torch.Generator().manual_seed(10_000 + s)
+        r = [torch.randn(b, 128, generator=gs).cuda() for _ in range(n)]
+        real, fake = meta["labels"][s]
+        if workload == "vae":
+            m_ = T.step(x, r[0])
+        elif workload == "gan":
+            m_ = T.step(x, real, fake, r[0])
+        else:
+            m_ = T.step(x, real, fake, *r)
+        out.append({k: v.clone() for k, v in m_.items()})
+    return {k: [float(o[k]) for o in out] for k in out[0]}
+
+
+def deviations(a, ref):
+    a, ref = np.asarray(a), np.asarray(ref)
+    return np.abs(a - ref) / (np.abs(ref) + 1e-9)
+
+
+@pytest.mark.parametrize("workload", ["vae", "gan", "betavaegan"])
+def test_200_step_curves_track_oracle(workload):
+    path = os.path.join(GOLD, f"curves_{workload}.json")
+    if not os.path.exists(path):
+        pytest.skip("golden curves not generated")
+    doc = json.load(open(path))
+    mine = run_cuda(workload, doc)
+    report = {}
+    for key, (tol10, tol_med) in TOL[workload].items():
+        ref = doc["curves"][key]
+        dev = deviations(mine[key], ref)
+        floor = deviations(doc["perturbed"][key], ref)
+        report[key] = {"first10_max": float(dev[:10].max()), "median": float(np.median(dev)),
+                       "floor_median": float(np.median(floor)), "floor_first10_max": float(floor[:10].max())}
+        assert np.all(np.isfinite(mine[key])), key
+        assert dev[:10].max() <= max(tol10, 3 * floor[:10].max()), (workload, key, report[key])
+        assert np.median(dev) <= max(tol_med, 3 * np.median(floor)), (workload, key, report[key])
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/curve_report_{workload}.json", "w") as f:
+        json.dump(report, f, indent=1)
+    print(workload, json.dumps(report))

@@ -74,8 +74,12 @@ def test_pack_conv_weights(ops):
     wd, wu, wc = ops.pack_conv_weights(w, 64, 3, True, True, True)
     wb = w.bfloat16()
     assert torch.equal(wd, wb.reshape(64, 3, 25).permute(2, 0, 1).contiguous())
-    assert torch.equal(wu[:, :3, :], wb.reshape(64, 3, 25).permute(2, 1, 0).contiguous())
-    assert float(wu[:, 3:, :].float().abs().max()) == 0.0
+    # cb == 3: kw-folded layout wu[kh][kw*3 + cb][cs] = W[cs][cb][kh][kw]; everything else zero
+    assert torch.equal(wu[:5, :15, :], wb.permute(2, 3, 1, 0).reshape(5, 15, 64).contiguous())
+    assert float(wu[:5, 15:, :].float().abs().max()) == 0.0 and float(wu[5:].float().abs().max()) == 0.0
+    w2 = torch.randn(128, 32, 5, 5, device="cuda")
+    wd2, wu2, _ = ops.pack_conv_weights(w2, 128, 32)
+    assert torch.equal(wu2, w2.bfloat16().reshape(128, 32, 25).permute(2, 1, 0).contiguous())
     assert torch.equal(wc[:, :75], wb.reshape(64, 75)) and float(wc[:, 75:].float().abs().max()) == 0.0
 
 
