@@ -59,6 +59,9 @@ struct alignas(64) GemmParams {
   int num_units;    // MODE_WGRAD: tap units
   int total_tiles;  // persistent: CTAs grid-stride over [0, total_tiles)
   int acc_stride;   // TMEM columns between the two accumulator buffers
+  int cluster;      // 1, or 2: CTA pairs on adjacent M tiles (FWD) / tap units (WGRAD) share the B tile via multicast
+  int cg2;          // cluster == 2, FWD: ONE tcgen05.mma.cta_group::2 (M = 256) per CTA pair; each CTA holds its 128
+                    // A rows and half of the B rows, the leader CTA issues, both read their own TMEM half
   int cpt;     // MODE_FWD: channel chunks per tap
   int num_kb;  // MODE_WGRAD: total pixel-tile k-blocks
   // pixel-tile decode: tile j -> (w0, h0, n0); used for the M tile (FWD) or the K tile (WGRAD)
@@ -82,6 +85,7 @@ struct alignas(64) GemmParams {
   int m_valid;
   int wgrad_direct;    // host-only: conv wgrad writes the parameter layout directly
   int wgrad_tap_on_a;  // MODE_WGRAD: the tap shift applies to operand A (conv wgrad) instead of B
+  int dbg;             // timing experiments only (DM_DBG): 1 = skip the A loads, 2 = skip the B loads, 4 = skip the MMAs
 };
 
 constexpr int kThreads = 192;
@@ -97,13 +101,16 @@ struct TileWork {
   int m_tile, n_tile, phase, split, unit_tap, tap_begin, kb0, kb1;
 };
 
-__device__ __forceinline__ TileWork decode_tile(const GemmParams& p, int t) {
+// t indexes tiles (cluster == 1) or tile PAIRS (cluster == 2; `rank` = this CTA's rank in the pair).
+__device__ __forceinline__ TileWork decode_tile(const GemmParams& p, int t, int rank) {
   TileWork w;
   int total_kb;
   if (p.mode == MODE_FWD) {
     // order: m fastest, then n, then (phase, split): concurrently resident CTAs share one weight tile in L2
-    w.m_tile = t % p.num_m_tiles;
-    int r = t / p.num_m_tiles;
+    const int m_slots = (p.cluster == 2) ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles;
+    const int ms = t % m_slots;
+    w.m_tile = (p.cluster == 2) ? 2 * ms + rank : ms;  // may be a phantom tile (== num_m_tiles): rows are masked
+    int r = t / m_slots;
     w.n_tile = r % p.num_n_tiles;
     const int z = r / p.num_n_tiles;
     w.phase = z / p.num_splits;
@@ -113,11 +120,13 @@ __device__ __forceinline__ TileWork decode_tile(const GemmParams& p, int t) {
     total_kb = (p.phase_tap_start[w.phase + 1] - w.tap_begin) * p.cpt;
   } else {
     // order: (tap unit, n) fastest, then m, then split: concurrent CTAs share the pixel tiles, write disjoint outputs
-    const int units_n = p.num_units * p.num_n_tiles;
+    const int u_slots = (p.cluster == 2) ? (p.num_units + 1) / 2 : p.num_units;
+    const int units_n = u_slots * p.num_n_tiles;
     const int u = t % units_n;
     const int r = t / units_n;
-    w.unit_tap = u / p.num_n_tiles;
-    w.n_tile = u - w.unit_tap * p.num_n_tiles;
+    const int us = u / p.num_n_tiles;
+    w.unit_tap = (p.cluster == 2) ? 2 * us + rank : us;  // may be a phantom unit (== num_units): stores are skipped
+    w.n_tile = u - us * p.num_n_tiles;
     w.m_tile = r % p.num_m_tiles;
     w.split = r / p.num_m_tiles;
     w.phase = 0;
@@ -130,15 +139,21 @@ __device__ __forceinline__ TileWork decode_tile(const GemmParams& p, int t) {
   return w;
 }
 
+// kCG2 = true: CTA-pair instantiation (contains cta_group::2 instructions, so it MUST be launched with an even
+// cluster dimension); kCG2 = false: single-CTA MMA (optionally with multicast pairs).
+template <bool kCG2>
 __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int crank = (p.cluster == 2) ? static_cast<int>(cluster_ctarank()) : 0;
+  const int t_begin = (p.cluster == 2) ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int t_step = (p.cluster == 2) ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   const int a_bytes = p.a_mn ? 2 * kAtomBytes : 128 * p.kc * 2;
-  const int b_bytes = p.b_mn ? (p.bn >> 6) * kAtomBytes : p.bn * p.kc * 2;
+  const int b_bytes = p.b_mn ? (p.bn >> 6) * kAtomBytes : (kCG2 ? (p.bn >> 1) : p.bn) * p.kc * 2;
   const int stage_bytes = a_bytes + b_bytes;
 
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
@@ -153,132 +168,224 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
     tma_prefetch_desc(&p.map_a);
     tma_prefetch_desc(&p.map_b);
   }
+  if (kCG2) cluster_sync_all();  // both CTAs of the pair are resident before the paired TMEM allocation
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < p.stages; ++s) {
-        mbar_init(&full_bar[s], 1);
-        mbar_init(&empty_bar[s], 1);
+        // cg2: the leader's full barrier collects both CTAs' producers; every CTA's empty barrier is released by
+        // the leader's multicast commit.  multicast pairs: each CTA's MMA thread releases the stage in both CTAs.
+        mbar_init(&full_bar[s], kCG2 ? 2u : 1u);
+        mbar_init(&empty_bar[s], kCG2 ? 1u : static_cast<uint32_t>(p.cluster));
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(&tmem_full_bar[b], 1);
-        mbar_init(&tmem_empty_bar[b], 128);  // every epilogue thread arrives
+        mbar_init(&tmem_empty_bar[b], kCG2 ? 256u : 128u);  // every epilogue thread (of both CTAs) arrives
       }
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_ptr_smem, static_cast<uint32_t>(p.tmem_cols));
+    if constexpr (kCG2)
+      tmem_alloc_2sm(tmem_ptr_smem, static_cast<uint32_t>(p.tmem_cols));
+    else
+      tmem_alloc(tmem_ptr_smem, static_cast<uint32_t>(p.tmem_cols));
   }
   tc_fence_before();
-  __syncthreads();
+  if (p.cluster == 2)
+    cluster_sync_all();  // the peer's barriers must be initialised before anything is multicast at them
+  else
+    __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  // Both single-thread roles below are ISSUE-bound if careless: one lane retires roughly one dependent instruction
+  // every 4-6 cycles, and a 128x128x64 k-block is only 256 tensor-core cycles.  Everything that does not change per
+  // k-block is therefore hoisted into registers (barrier addresses, descriptor templates, tap coordinates), the
+  // k-block index is never divided, and the mode switches are resolved per tile, not per k-block.
+  const uint32_t full0 = smem_u32(full_bar);
+  const uint32_t empty0 = smem_u32(empty_bar);
+  const uint32_t smem0 = smem_u32(smem);
+  const int nstages = p.stages;
+
   if (warp == 0) {
-    // =========================================================== TMA producer (one thread)
-    if (lane == 0) {
+    // =========================================================== TMA producer
+    // The whole warp runs the (warp-uniform) loops so that addresses and coordinates live in uniform registers; one
+    // elected lane issues the barrier arrivals and the TMA loads.
+    {
+      const bool leader = elect_one();
       int stage = 0;
-      uint32_t parity = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const TileWork w = decode_tile(p, t);
-        if (w.kb0 >= w.kb1) continue;
+      uint32_t parity = 1;            // parity to wait for on the EMPTY barrier of `stage` (fresh barriers pass)
+      uint32_t sa = smem0;            // smem address of the current stage
+      const uint64_t map_a = reinterpret_cast<uint64_t>(&p.map_a);
+      const uint64_t map_b = reinterpret_cast<uint64_t>(&p.map_b);
+      const uint32_t tx_bytes = static_cast<uint32_t>(kCG2 ? 2 * stage_bytes : stage_bytes);
+      // the barrier that receives the complete_tx of this CTA's loads: its own, or (cta_group::2) the leader's
+      const uint32_t full_tx0 = kCG2 ? (full0 & kPeerBitMask) : full0;
+      const int kc = p.kc;
+      for (int t = t_begin; t < p.total_tiles; t += t_step) {
+        const TileWork w = decode_tile(p, t, crank);
+        int nkb = w.kb1 - w.kb0;
+        if (nkb <= 0) continue;
         if (p.mode == MODE_FWD) {
           const int w0 = w.m_tile * p.tw_step;
           const int h0 = (w.m_tile % p.tpi) * p.th_step;
           const int n0 = (w.m_tile / p.tpi) * p.tn_step;
-          const int ncol0 = w.n_tile * p.bn;
-          for (int kb = w.kb0; kb < w.kb1; ++kb) {
-            const int tt = kb / p.cpt;
-            const int chunk = kb - tt * p.cpt;
+          const int ncol0 = w.n_tile * p.bn + (kCG2 ? crank * (p.bn >> 1) : 0);
+          const int cpt = p.cpt;
+          int tt = w.kb0 / cpt;            // per tile, not per k-block
+          int chunk = w.kb0 - tt * cpt;
+          const int b_atoms = p.b_mn ? (p.bn >> 6) : 0;
+          while (nkb > 0) {
             const Tap tap = p.taps[w.tap_begin + tt];
-            uint8_t* sa = smem + stage * stage_bytes;
-            uint8_t* sb = sa + a_bytes;
-            mbar_wait(&empty_bar[stage], parity ^ 1u);
-            mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
-            tma_load_5d(sa, &p.map_a, &full_bar[stage], tap.dc + chunk * p.kc, w0 + tap.dw, tap.dp, h0 + tap.dh,
-                        n0);
-            if (!p.b_mn) {
-              tma_load_3d(sb, &p.map_b, &full_bar[stage], chunk * p.kc, ncol0, tap.wt);
-            } else {
-              for (int a = 0; a < (p.bn >> 6); ++a)
-                tma_load_3d(sb + a * kAtomBytes, &p.map_b, &full_bar[stage], ncol0 + a * 64, chunk * 64, tap.wt);
+            const int cw = w0 + tap.dw, cp = tap.dp, ch = h0 + tap.dh, wt = tap.wt;
+            int c0 = tap.dc + chunk * kc;
+            int kcol = chunk * kc;
+            const int nch = min(cpt - chunk, nkb);
+            for (int i = 0; i < nch; ++i) {
+              const uint32_t fb = full_tx0 + 8u * stage;
+              mbar_wait_u32(empty0 + 8u * stage, parity);
+              if (leader) {
+                if constexpr (kCG2) {
+                  if (crank == 0)
+                    mbar_arrive_expect_tx_u32(full0 + 8u * stage, tx_bytes);
+                  else
+                    mbar_arrive_remote_u32(full0 + 8u * stage, 0);
+                  tma_load_5d_2sm_u32(sa, map_a, fb, c0, cw, cp, ch, n0);
+                  tma_load_3d_2sm_u32(sa + a_bytes, map_b, fb, kcol, ncol0, wt);
+                } else {
+                  mbar_arrive_expect_tx_u32(fb, tx_bytes);
+                  tma_load_5d_u32(sa, map_a, fb, c0, cw, cp, ch, n0);
+                  if (b_atoms == 0) {
+                    tma_load_3d_u32(sa + a_bytes, map_b, fb, kcol, ncol0, wt);
+                  } else {
+                    for (int a = 0; a < b_atoms; ++a)
+                      tma_load_3d_u32(sa + a_bytes + a * kAtomBytes, map_b, fb, ncol0 + a * 64, kcol, wt);
+                  }
+                }
+              }
+              c0 += kc;
+              kcol += kc;
+              sa += stage_bytes;
+              if (++stage == nstages) {
+                stage = 0;
+                parity ^= 1u;
+                sa = smem0;
+              }
             }
-            if (++stage == p.stages) {
-              stage = 0;
-              parity ^= 1u;
-            }
+            nkb -= nch;
+            chunk = 0;
+            ++tt;
           }
         } else {
-          const Tap tap = p.taps[w.unit_tap];
+          const Tap tap = p.taps[min(w.unit_tap, p.num_units - 1)];
           const int mch0 = w.m_tile * 128;
           const int nch0 = w.n_tile * p.bn;
-          for (int kb = w.kb0; kb < w.kb1; ++kb) {
-            const int w0 = kb * p.tw_step;
-            const int h0 = (kb % p.tpi) * p.th_step;
-            const int n0 = (kb / p.tpi) * p.tn_step;
-            uint8_t* sa = smem + stage * stage_bytes;
-            uint8_t* sb = sa + a_bytes;
-            mbar_wait(&empty_bar[stage], parity ^ 1u);
-            mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
-            if (p.wgrad_tap_on_a) {
-              for (int a = 0; a < 2; ++a)
-                tma_load_5d(sa + a * kAtomBytes, &p.map_a, &full_bar[stage], mch0 + a * 64 + tap.dc, w0 + tap.dw,
-                            tap.dp, h0 + tap.dh, n0);
-              for (int a = 0; a < (p.bn >> 6); ++a)
-                tma_load_5d(sb + a * kAtomBytes, &p.map_b, &full_bar[stage], nch0 + a * 64, w0, 0, h0, n0);
-            } else {
-              for (int a = 0; a < 2; ++a)
-                tma_load_5d(sa + a * kAtomBytes, &p.map_a, &full_bar[stage], mch0 + a * 64, w0, 0, h0, n0);
-              for (int a = 0; a < (p.bn >> 6); ++a)
-                tma_load_5d(sb + a * kAtomBytes, &p.map_b, &full_bar[stage], nch0 + a * 64 + tap.dc, w0 + tap.dw,
-                            tap.dp, h0 + tap.dh, n0);
+          const int b_atoms = p.bn >> 6;
+          // pixel-tile coordinates of k-block kb: (w0, h0, n0) = (kb * tw_step, (kb % tpi) * th_step, (kb / tpi) *
+          // tn_step), advanced incrementally
+          int w0 = w.kb0 * p.tw_step;
+          int ti = w.kb0 % p.tpi;
+          int h0 = ti * p.th_step;
+          int n0 = (w.kb0 / p.tpi) * p.tn_step;
+          // the tap shift applies to A (conv wgrad) or to B (dense TN GEMM has a zero tap)
+          const int adc = p.wgrad_tap_on_a ? tap.dc : 0, adw = p.wgrad_tap_on_a ? tap.dw : 0;
+          const int adp = p.wgrad_tap_on_a ? tap.dp : 0, adh = p.wgrad_tap_on_a ? tap.dh : 0;
+          const int bdc = p.wgrad_tap_on_a ? 0 : tap.dc, bdw = p.wgrad_tap_on_a ? 0 : tap.dw;
+          const int bdp = p.wgrad_tap_on_a ? 0 : tap.dp, bdh = p.wgrad_tap_on_a ? 0 : tap.dh;
+          for (; nkb > 0; --nkb) {
+            const uint32_t fb = full0 + 8u * stage;
+            mbar_wait_u32(empty0 + 8u * stage, parity);
+            if (leader) {
+              mbar_arrive_expect_tx_u32(fb, tx_bytes);
+              tma_load_5d_u32(sa, map_a, fb, mch0 + adc, w0 + adw, adp, h0 + adh, n0);
+              tma_load_5d_u32(sa + kAtomBytes, map_a, fb, mch0 + 64 + adc, w0 + adw, adp, h0 + adh, n0);
+              for (int a = 0; a < b_atoms; ++a)
+                tma_load_5d_u32(sa + a_bytes + a * kAtomBytes, map_b, fb, nch0 + a * 64 + bdc, w0 + bdw, bdp,
+                                h0 + bdh, n0);
             }
-            if (++stage == p.stages) {
+            w0 += p.tw_step;
+            h0 += p.th_step;
+            if (++ti == p.tpi) {
+              ti = 0;
+              h0 = 0;
+              n0 += p.tn_step;
+            }
+            sa += stage_bytes;
+            if (++stage == nstages) {
               stage = 0;
               parity ^= 1u;
+              sa = smem0;
             }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // =========================================================== MMA issuer (one thread)
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128u, static_cast<uint32_t>(p.bn), p.a_mn, p.b_mn);
-      const uint32_t k_layout = (p.kc == 64) ? 2u : 4u;          // SWIZZLE_128B : SWIZZLE_64B
+    // =========================================================== MMA issuer (whole warp loops, one elected lane issues)
+    if (!kCG2 || crank == 0) {  // cta_group::2: the leader CTA issues for the pair
+      const bool leader = elect_one();
+      const uint32_t idesc = make_idesc_bf16(kCG2 ? 256u : 128u, static_cast<uint32_t>(p.bn), p.a_mn, p.b_mn);
+      const uint32_t k_layout = (p.kc == 64) ? 2u : 4u;            // SWIZZLE_128B : SWIZZLE_64B
       const uint32_t k_sbo = static_cast<uint32_t>(8 * p.kc * 2);  // 8 rows of one swizzle atom
-      const uint32_t a_step = p.a_mn ? 2048u : 32u;              // bytes per UMMA_K (16 elements of K)
-      const uint32_t b_step = p.b_mn ? 2048u : 32u;
-      const int nk = p.kc >> 4;
+      // descriptor templates (everything but the start address) and the per-UMMA_K advance of the start-address
+      // field (address >> 4; smem addresses stay below 2^18, so the 14-bit field never carries)
+      const uint64_t da_t = p.a_mn ? make_smem_desc(0u, kAtomBytes, 1024u, 2u) : make_smem_desc(0u, 0u, k_sbo, k_layout);
+      const uint64_t db_t = p.b_mn ? make_smem_desc(0u, kAtomBytes, 1024u, 2u) : make_smem_desc(0u, 0u, k_sbo, k_layout);
+      const uint32_t a_step = (p.a_mn ? 2048u : 32u) >> 4;  // per UMMA_K (16 elements of K)
+      const uint32_t b_step = (p.b_mn ? 2048u : 32u) >> 4;
+      const bool four = (p.kc == 64);
+      const uint32_t stage16 = static_cast<uint32_t>(stage_bytes) >> 4;
+      const uint32_t a16 = static_cast<uint32_t>(a_bytes) >> 4;
+      const uint32_t smem16 = smem0 >> 4;
+      const uint32_t tfull0 = smem_u32(tmem_full_bar), tempty0 = smem_u32(tmem_empty_bar);
       int stage = 0;
       uint32_t parity = 0;
+      uint32_t s16 = smem16;
       int it = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const TileWork w = decode_tile(p, t);
-        if (w.kb0 >= w.kb1) continue;
+      for (int t = t_begin; t < p.total_tiles; t += t_step) {
+        const TileWork w = decode_tile(p, t, crank);
+        int nkb = w.kb1 - w.kb0;
+        if (nkb <= 0) continue;
         const int buf = it & 1;
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * p.acc_stride);
-        mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1u);  // epilogue has drained this accumulator
+        mbar_wait_u32(tempty0 + 8u * buf, ((it >> 1) & 1) ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
-        for (int kb = w.kb0; kb < w.kb1; ++kb) {
-          mbar_wait(&full_bar[stage], parity);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
-          const uint32_t b_addr = a_addr + static_cast<uint32_t>(a_bytes);
-#pragma unroll 4
-          for (int k = 0; k < nk; ++k) {
-            const uint64_t da = p.a_mn ? make_smem_desc(a_addr + k * a_step, kAtomBytes, 1024u, 2u)
-                                       : make_smem_desc(a_addr + k * a_step, 0u, k_sbo, k_layout);
-            const uint64_t db = p.b_mn ? make_smem_desc(b_addr + k * b_step, kAtomBytes, 1024u, 2u)
-                                       : make_smem_desc(b_addr + k * b_step, 0u, k_sbo, k_layout);
-            umma_bf16(tmem_d, da, db, idesc, (kb > w.kb0 || k > 0) ? 1u : 0u);
+        uint32_t acc = 0;
+        for (; nkb > 0; --nkb) {
+          mbar_wait_u32(full0 + 8u * stage, parity);
+          const uint64_t da = da_t | s16;
+          const uint64_t db = db_t | (s16 + a16);
+          if (!leader) {
+          } else if constexpr (kCG2) {
+            umma_bf16_2sm(tmem_d, da, db, idesc, acc);
+            umma_bf16_2sm(tmem_d, da + a_step, db + b_step, idesc, 1u);
+            if (four) {
+              umma_bf16_2sm(tmem_d, da + 2 * a_step, db + 2 * b_step, idesc, 1u);
+              umma_bf16_2sm(tmem_d, da + 3 * a_step, db + 3 * b_step, idesc, 1u);
+            }
+            umma_commit_2sm_mc_u32(empty0 + 8u * stage, 0x3);  // releases this stage in both CTAs of the pair
+          } else {
+            umma_bf16(tmem_d, da, db, idesc, acc);
+            umma_bf16(tmem_d, da + a_step, db + b_step, idesc, 1u);
+            if (four) {
+              umma_bf16(tmem_d, da + 2 * a_step, db + 2 * b_step, idesc, 1u);
+              umma_bf16(tmem_d, da + 3 * a_step, db + 3 * b_step, idesc, 1u);
+            }
+            umma_commit_u32(empty0 + 8u * stage);  // frees this smem stage once the MMAs above retire
           }
-          umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above retire
-          if (++stage == p.stages) {
+          acc = 1u;
+          s16 += stage16;
+          if (++stage == nstages) {
             stage = 0;
             parity ^= 1u;
+            s16 = smem16;
           }
         }
-        umma_commit(&tmem_full_bar[buf]);  // accumulator complete -> epilogue
+        if (!leader) {
+        } else if constexpr (kCG2) {
+          umma_commit_2sm_mc_u32(tfull0 + 8u * buf, 0x3);  // each CTA's epilogue drains its own 128 TMEM lanes
+        } else {
+          umma_commit_u32(tfull0 + 8u * buf);  // accumulator complete -> epilogue
+        }
         ++it;
       }
     }
@@ -289,8 +396,8 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
     float* outf = reinterpret_cast<float*>(p.out);
     __nv_bfloat16* outh = reinterpret_cast<__nv_bfloat16*>(p.out);
     int it = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      const TileWork w = decode_tile(p, t);
+    for (int t = t_begin; t < p.total_tiles; t += t_step) {
+      const TileWork w = decode_tile(p, t, crank);
       if (w.kb0 >= w.kb1) continue;
       const int buf = it & 1;
       mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
@@ -382,9 +489,9 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
           }
         }
       } else {
-        const Tap tap = p.taps[w.unit_tap];
+        const Tap tap = p.taps[min(w.unit_tap, p.num_units - 1)];
         const int m = m_tile * 128 + r;
-        const bool row_ok = (m < p.m_valid) && (m < tap.mvalid);
+        const bool row_ok = (m < p.m_valid) && (m < tap.mvalid) && (w.unit_tap < p.num_units);
         const long long row_off = (m % p.mmod) * p.os_m + (m / p.mmod) * p.os_m2 + tap.out_off;
         const bool simple_n = p.nmod >= (1 << 30);  // column offset is affine: no div/mod per element
         const int ncols = min(p.bn, static_cast<int>(tap.nvalid) - n_tile * p.bn);
@@ -424,14 +531,25 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
       // this thread's TMEM reads of the accumulator are complete: hand the buffer back to the MMA issuer
       __syncwarp();
       tc_fence_before();
-      mbar_arrive(&tmem_empty_bar[buf]);
+      if (kCG2)
+        mbar_arrive_remote(&tmem_empty_bar[buf], 0);  // the leader's MMA thread waits for both CTAs' epilogues
+      else
+        mbar_arrive(&tmem_empty_bar[buf]);
       ++it;
     }
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+  if (p.cluster == 2)
+    cluster_sync_all();  // the peer may still multicast into this CTA's smem / arrive on its barriers
+  else
+    __syncthreads();
+  if (warp == 1) {
+    if constexpr (kCG2)
+      tmem_dealloc_2sm(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+    else
+      tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+  }
 }
 
 // ================================================================================ host side
@@ -554,20 +672,33 @@ static int num_sms() {
 // `grid` = logical tile space: x = m tiles, y = n tiles (FWD) or n tiles * tap units (WGRAD), z = phases*splits
 // (FWD) or splits (WGRAD).  The kernel is persistent: min(tiles, SMs * CTAs/SM) CTAs grid-stride over the tiles,
 // each with a double-buffered TMEM accumulator so that a tile's epilogue overlaps the next tile's main loop.
-static int launch(GemmParams& p, dim3 grid, cudaStream_t stream, double flops, int kb_per_cta = 1 << 30) {
+static int launch(GemmParams& p, dim3 grid, cudaStream_t stream, double flops, int kb_per_cta = 1 << 30,
+                  int cluster = 1) {
+  if (cluster != 2 || p.mode != MODE_FWD || p.b_mn) p.cg2 = 0;
   const int a_bytes = p.a_mn ? 2 * kAtomBytes : 128 * p.kc * 2;
-  const int b_bytes = p.b_mn ? (p.bn >> 6) * kAtomBytes : p.bn * p.kc * 2;
+  const int b_bytes = p.b_mn ? (p.bn >> 6) * kAtomBytes : (p.cg2 ? (p.bn >> 1) : p.bn) * p.kc * 2;
   const int stage_bytes = a_bytes + b_bytes;
+  p.cluster = cluster;
+  p.dbg = (cluster == 1 && p.mode == MODE_FWD && !p.b_mn) ? env_int("DM_DBG", 0) : 0;
   p.num_m_tiles = grid.x;
   if (p.mode == MODE_WGRAD) p.num_units = grid.y / p.num_n_tiles;
-  p.total_tiles = static_cast<int>(grid.x * grid.y * grid.z);
+  // work items: tiles, or tile pairs when CTA pairs share the B operand
+  if (cluster == 2) {
+    if (p.mode == MODE_FWD)
+      p.total_tiles = static_cast<int>(((grid.x + 1) / 2) * grid.y * grid.z);
+    else
+      p.total_tiles = static_cast<int>(grid.x * ((p.num_units + 1) / 2) * p.num_n_tiles * grid.z);
+  } else {
+    p.total_tiles = static_cast<int>(grid.x * grid.y * grid.z);
+  }
   p.acc_stride = (p.bn + 31) / 32 * 32;
   p.tmem_cols = pow2_cols(2 * p.acc_stride);
   const int sms = num_sms();
   // two CTAs per SM only if both their TMEM (2 x <=256 columns) and their smem rings fit
   const bool two_per_sm = p.tmem_cols <= 256 && stage_bytes <= 32768 && env_int("DM_ONE_CTA", 0) == 0;
   const int budget = two_per_sm ? env_int("DM_SMEM_BUDGET_SMALL", 98304) : env_int("DM_SMEM_BUDGET_BIG", 196608);
-  const int tiles_per_cta = (p.total_tiles + sms * (two_per_sm ? 2 : 1) - 1) / (sms * (two_per_sm ? 2 : 1));
+  const int slots = sms * (two_per_sm ? 2 : 1) / cluster;  // concurrently resident CTAs (or CTA pairs)
+  const int tiles_per_cta = (p.total_tiles + slots - 1) / slots;
   const long long kb_stream = static_cast<long long>(std::min(kb_per_cta, 1 << 20)) * tiles_per_cta;
   int stages = std::max(2, std::min(8, budget / stage_bytes));
   stages = static_cast<int>(std::max<long long>(1, std::min<long long>(stages, kb_stream)));
@@ -578,10 +709,12 @@ static int launch(GemmParams& p, dim3 grid, cudaStream_t stream, double flops, i
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(dm_tapgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_err = cudaFuncSetAttribute(dm_tapgemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(dm_tapgemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (attr_err != cudaSuccess) return set_error((int)attr_err, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
-  const int ctas = std::min(p.total_tiles, sms * (two_per_sm ? 2 : 1));
+  const int ctas = cluster * std::min(p.total_tiles, slots);
   g_last_grid[0] = grid.x; g_last_grid[1] = grid.y; g_last_grid[2] = grid.z;
   g_last_smem = smem; g_last_stages = stages;
   ProfRec rec;
@@ -603,13 +736,28 @@ static int launch(GemmParams& p, dim3 grid, cudaStream_t stream, double flops, i
     }
   }
   if (prof) cudaEventRecord(rec.e0, stream);
-  dm_tapgemm_kernel<<<ctas, kThreads, smem, stream>>>(p);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(ctas);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = cluster > 1 ? 1 : 0;
+  cudaError_t le = p.cg2 ? cudaLaunchKernelEx(&cfg, dm_tapgemm_kernel<true>, p)
+                         : cudaLaunchKernelEx(&cfg, dm_tapgemm_kernel<false>, p);
   if (prof) {
     cudaEventRecord(rec.e1, stream);
     std::lock_guard<std::mutex> lk(g_prof_mu);
     g_prof.push_back(rec);
   }
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  if (le != cudaSuccess) return set_error((int)le, "dm_tapgemm_kernel launch: %s", cudaGetErrorString(le));
   return check_launch("dm_tapgemm_kernel");
 }
 
@@ -851,9 +999,12 @@ extern "C" int dm_conv_down(const dm_conv_geom* g, const void* big, const void* 
   p.w_lim = g->ws; p.n_lim = g->batch; p.n_valid = g->cs;
   uint32_t box[5] = {(uint32_t)p.kc, (uint32_t)pt.bw, 1, (uint32_t)pt.bh, (uint32_t)pt.bimg};
   if (int rc = encode_act_map(&p.map_a, big, g->batch, g->hb, g->wb, g->cb, g->stride, box, p.kc * 2)) return rc;
-  if (int rc = encode_w_map3(&p.map_b, w_down, 25, g->cs, g->cb, g->cb, p.kc, p.bn, p.kc * 2)) return rc;
+  p.cg2 = (env_int("DM_CG2", 0) != 0 && pt.tiles >= 2 && p.bn >= 32) ? 1 : 0;
+  const int cluster = p.cg2 ? 2 : 1;
+  if (int rc = encode_w_map3(&p.map_b, w_down, 25, g->cs, g->cb, g->cb, p.kc, p.bn / cluster, p.kc * 2)) return rc;
   p.num_n_tiles = (g->cs + p.bn - 1) / p.bn;
-  return launch(p, dim3(pt.tiles, p.num_n_tiles, 1), stream, 50.0 * g->batch * g->hs * g->ws * g->cs * g->cb);
+  return launch(p, dim3(pt.tiles, p.num_n_tiles, 1), stream, 50.0 * g->batch * g->hs * g->ws * g->cs * g->cb, 1 << 30,
+                cluster);
 }
 
 extern "C" int dm_conv_up(const dm_conv_geom* g, const void* small, const void* w_up, const float* bias, void* out_big,
@@ -925,9 +1076,12 @@ extern "C" int dm_conv_up(const dm_conv_geom* g, const void* small, const void* 
   p.w_lim = g->ws; p.n_lim = g->batch; p.n_valid = g->cb;
   uint32_t box[5] = {(uint32_t)p.kc, (uint32_t)pt.bw, 1, (uint32_t)pt.bh, (uint32_t)pt.bimg};
   if (int rc = encode_act_map(&p.map_a, small, g->batch, g->hs, g->ws, g->cs, 1, box, p.kc * 2)) return rc;
-  if (int rc = encode_w_map3(&p.map_b, w_up, fold ? 5 : 25, cb_pad, g->cs, g->cs, p.kc, p.bn, p.kc * 2)) return rc;
+  p.cg2 = (!fold && env_int("DM_CG2", 0) != 0 && pt.tiles >= 2 && p.bn >= 32) ? 1 : 0;
+  const int cluster = p.cg2 ? 2 : 1;
+  if (int rc = encode_w_map3(&p.map_b, w_up, fold ? 5 : 25, cb_pad, g->cs, g->cs, p.kc, p.bn / cluster, p.kc * 2)) return rc;
   p.num_n_tiles = (cb_pad + p.bn - 1) / p.bn;
-  return launch(p, dim3(pt.tiles, p.num_n_tiles, nphase), stream, 50.0 * g->batch * g->hs * g->ws * g->cs * g->cb);
+  return launch(p, dim3(pt.tiles, p.num_n_tiles, nphase), stream, 50.0 * g->batch * g->hs * g->ws * g->cs * g->cb,
+                1 << 30, cluster);
 }
 
 extern "C" int dm_conv_wgrad(const dm_conv_geom* g, const void* small, const void* big, float* dw_packed,
@@ -998,6 +1152,7 @@ extern "C" int dm_conv_wgrad(const dm_conv_geom* g, const void* small, const voi
   if (splits <= 0) splits = std::max(1, std::min(p.num_kb, (env_int("DM_WGRAD_CTAS", 296) + base_ctas - 1) / base_ctas));
   splits = std::min(splits, p.num_kb);
   p.num_splits = splits;
+  const int cluster = 1;
   return launch(p, dim3(m_tiles, p.num_n_tiles * units, splits), stream,
-                50.0 * g->batch * g->hs * g->ws * g->cs * g->cb, (p.num_kb + splits - 1) / splits);
+                50.0 * g->batch * g->hs * g->ws * g->cs * g->cb, (p.num_kb + splits - 1) / splits, cluster);
 }

@@ -21,6 +21,19 @@ def test_case(name):
     assert rel < (4e-3 if bf16_out else 1e-4), (name, rel)
 
 
+@pytest.mark.parametrize("env", [{"DM_CG2": "1"}, {"DM_CLUSTER": "1"}])
+@pytest.mark.parametrize("name", [n for n in probe_gemm.CASES if n.startswith(("down_", "up_", "wgrad_"))])
+def test_cluster_modes(name, env, monkeypatch):
+    """The two thread-block-cluster modes of the kernel (off by default: measured neutral on this workload, see
+    DESIGN.md): DM_CG2=1 = one tcgen05.mma.cta_group::2 (M=256) per CTA pair, DM_CLUSTER=1 = 1-CTA MMAs with the
+    B tile TMA-multicast to both CTAs of a pair."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rel, _ = probe_gemm.CASES[name]()
+    bf16_out = name.startswith(("down_", "up_")) and "f32" not in name
+    assert rel < (4e-3 if bf16_out else 1e-4), (name, env, rel)
+
+
 def test_full_size_layers_linearity_and_batch_independence():
     """Full BASELINE sizes (batch 128): conv(x1 + x2) == conv(x1) + conv(x2) on bf16-exact inputs, and the
     result for image i does not depend on the other images in the batch."""

@@ -1,0 +1,73 @@
+"""GPU micro-benchmark of the tap-GEMM kernel on the training step's main layer shapes (CUDA events, warm caches):
+    python tools/perf_gemm.py [batch] ["ENV=V ENV2=V" ...]
+Each env set is applied in-process (the library reads its DM_* knobs at every launch)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from disentangle_mlp_b200 import ops
+
+
+def timeit(fn, reps=20):
+    for _ in range(min(3, reps)):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3  # us
+
+
+def cases(b):
+    dev = "cuda"
+    out = []
+    m, n, k = 8192, 4096, 4096
+    a = torch.randn(m, k, device=dev).bfloat16()
+    w = torch.randn(n, k, device=dev).bfloat16()
+    d = torch.empty(m, n, device=dev, dtype=torch.bfloat16)
+    out.append((f"gemm_nt {m}x{n}x{k}", 2.0 * m * n * k, lambda: ops.gemm(ops.GEMM_NT, a, w, m, n, k, out=d)))
+    for (hs, cs, cb, stride) in ((16, 256, 128, 2), (8, 256, 256, 2), (32, 128, 32, 2)):
+        wt = torch.randn(cs, cb, 5, 5, device=dev) * 0.05
+        small = torch.randn(b, hs, hs, cs, device=dev).bfloat16()
+        big = torch.randn(b, hs * stride, hs * stride, cb, device=dev).bfloat16()
+        w_down, w_up, _ = ops.pack_conv_weights(wt, cs, cb)
+        g = ops.geom(b, hs, hs, cs, cb, stride)
+        fl = 50.0 * b * hs * hs * cs * cb
+        o_s, o_b = torch.empty_like(small), torch.empty_like(big)
+        dw = torch.zeros(cs, cb, 5, 5, device=dev)
+        tag = f"{cb}->{cs} {hs * stride}->{hs}"
+        out.append((f"down  {tag}", fl, lambda g=g, big=big, w_down=w_down, o_s=o_s: ops.conv_down(g, big, w_down, None, out=o_s)))
+        out.append((f"up    {tag}", fl, lambda g=g, small=small, w_up=w_up, o_b=o_b: ops.conv_up(g, small, w_up, None, out=o_b)))
+        out.append((f"wgrad {tag}", fl, lambda g=g, small=small, big=big, dw=dw: ops.conv_wgrad(g, small, big, dw)))
+    return out
+
+
+def main():
+    only = os.environ.get("PERF_ONLY")     # substring filter on the case name
+    reps = int(os.environ.get("PERF_REPS", "20"))
+    b = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+    envsets = sys.argv[2:] or [""]
+    cs = [c for c in cases(b) if not only or only in c[0]]
+    print(f"batch {b}")
+    for es in envsets:
+        added = []
+        for kv in es.split():
+            k, v = kv.split("=")
+            os.environ[k] = v
+            added.append(k)
+        print(f"--- env [{es}]")
+        for name, fl, fn in cs:
+            us = timeit(fn, reps)
+            grid, smem, stages = ops.last_plan()
+            print(f"  {name:28s} {us:9.1f} us  {fl / us * 1e-6:8.1f} TFLOP/s   tiles {grid} stages {stages} smem {smem}")
+        for k in added:
+            del os.environ[k]
+
+
+if __name__ == "__main__":
+    main()
