@@ -39,7 +39,7 @@ struct Tap {
   uint8_t wt;      // weight tap index (B coordinate 2 in MODE_FWD)
   int16_t nvalid;  // MODE_WGRAD: valid columns of this tap unit
   int16_t mvalid;  // MODE_WGRAD: valid rows of this tap unit
-  int16_t pad_;
+  int16_t out_tap; // MODE_WGRAD, TMA epilogue: tap coordinate of this unit in the packed gradient [25][cs][cb]
   int32_t out_off; // MODE_WGRAD: element offset of this tap unit in the output
 };
 
@@ -85,6 +85,16 @@ struct alignas(64) GemmParams {
   int m_valid;
   int wgrad_direct;    // host-only: conv wgrad writes the parameter layout directly
   int wgrad_tap_on_a;  // MODE_WGRAD: the tap shift applies to operand A (conv wgrad) instead of B
+  // TMA epilogue (epi_tma != 0): each epilogue warp stages its 32 rows in smem and issues bulk tensor stores /
+  // reductions through map_out; out-of-bounds rows and columns are clipped by the TMA unit.
+  //   1 = rows: out[row][col], col contiguous (activations NHWC, plain matrices); box = {epi_cols, 32 rows as a
+  //       (epi_bw, epi_bh, 32/(epi_bw*epi_bh)) pixel sub-box}; bf16 or fp32; store or fp32 reduce-add (split-K)
+  //   2 = transposed reduce (conv weight gradient): packed dW[tap][n][m] += acc[m][n], box = {32 m, 32 n, 1 tap}
+  CUtensorMap map_out;
+  int epi_tma, epi_reduce, epi_cols, epi_swz, epi_bufs;
+  int epi_bw, epi_bh;    // mode 1: rows of the tile are pixels (w fastest, then h, then n) of an epi_bw x epi_bh x . box
+  int epi_row_step;      // mode 1: coordinate-1 origin of tile m (plain matrices: 128), 0 for pixel tiles
+  int phase_c[4], phase_p[4];  // mode 1, transposed-conv phases: channel-coordinate offset (pw * cb) and row parity ph
   int dbg;             // timing experiments only (DM_DBG): 1 = skip the A loads, 2 = skip the B loads, 4 = skip the MMAs
 };
 
@@ -143,8 +153,9 @@ __device__ __forceinline__ TileWork decode_tile(const GemmParams& p, int t, int 
 // cluster dimension); kCG2 = false: single-CTA MMA (optionally with multicast pairs).
 template <bool kCG2>
 __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_constant__ GemmParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();  // SWIZZLE_128B boxes need 1024-byte aligned stages
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -156,7 +167,8 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
   const int b_bytes = p.b_mn ? (p.bn >> 6) * kAtomBytes : (kCG2 ? (p.bn >> 1) : p.bn) * p.kc * 2;
   const int stage_bytes = a_bytes + b_bytes;
 
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint8_t* staging = smem + p.stages * stage_bytes;  // epi_bufs x 4 warps x 4 KB, TMA epilogue only
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + (p.epi_tma ? p.epi_bufs * 16384 : 0));
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full_bar = empty_bar + p.stages;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
@@ -396,6 +408,7 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
     float* outf = reinterpret_cast<float*>(p.out);
     __nv_bfloat16* outh = reinterpret_cast<__nv_bfloat16*>(p.out);
     int it = 0;
+    int ebuf = 0;  // TMA epilogue: staging buffer of the next box
     for (int t = t_begin; t < p.total_tiles; t += t_step) {
       const TileWork w = decode_tile(p, t, crank);
       if (w.kb0 >= w.kb1) continue;
@@ -405,7 +418,110 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
       const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * p.acc_stride);
       const int m_tile = w.m_tile, n_tile = w.n_tile;
 
-      if (p.mode == MODE_FWD && p.fold_kw) {
+      if (p.epi_tma == 1) {
+        // ---- rows: this warp's 32 rows -> smem (swizzled like the store map) -> one bulk tensor store per box
+        const uint64_t map_out = reinterpret_cast<uint64_t>(&p.map_out);
+        const int rq = q * 32;
+        const int cw = m_tile * p.epi_row_step + ((p.mode == MODE_FWD) ? m_tile * p.tw_step : 0) + rq % p.epi_bw;
+        const int chh = ((p.mode == MODE_FWD) ? (m_tile % p.tpi) * p.th_step : 0) + (rq / p.epi_bw) % p.epi_bh;
+        const int cn = ((p.mode == MODE_FWD) ? (m_tile / p.tpi) * p.tn_step : 0) + rq / (p.epi_bw * p.epi_bh);
+        const int cph = (p.mode == MODE_FWD) ? p.phase_p[w.phase] : 0;
+        const int cc0 = ((p.mode == MODE_FWD) ? p.phase_c[w.phase] : 0) + n_tile * p.bn;
+        const bool add_bias = (p.bias != nullptr) && (w.split == 0);
+        const uint32_t stg0 = smem_u32(staging) + static_cast<uint32_t>(q) * 4096u;
+        const int row_bytes = p.epi_cols * (p.out_f32 ? 4 : 2);          // 128 or 64
+        const uint32_t xr = (row_bytes == 128) ? (lane & 7) : ((lane >> 1) & 3);  // SWIZZLE_128B : SWIZZLE_64B
+        const uint32_t row_addr = static_cast<uint32_t>(lane * row_bytes);
+        int piece = 0;  // 16-byte piece index within the staging row
+        int boxc = 0;   // first column (within the tile) of the box being filled
+        for (int c0 = 0; c0 < p.bn; c0 += 32) {
+          uint32_t v[32];
+          __syncwarp();  // tcgen05.ld is warp-collective
+          tmem_ld_32x32(lane_addr + static_cast<uint32_t>(c0), v);
+          tmem_ld_wait();
+          if (add_bias) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (n_tile * p.bn + c0 + i < p.n_valid)
+                v[i] = __float_as_uint(__uint_as_float(v[i]) + __ldg(p.bias + n_tile * p.bn + c0 + i));
+          }
+          if (piece == 0) {
+            // the staging buffer about to be filled must have been read by the store issued epi_bufs boxes ago
+            if (lane == 0) {
+              if (p.epi_bufs == 2) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
+            }
+            __syncwarp();
+          }
+          const uint32_t stg = stg0 + static_cast<uint32_t>(ebuf) * 16384u + row_addr;
+          const int ncol = min(32, p.bn - c0);
+          if (p.out_f32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (4 * j < ncol)
+                st_shared_v4(stg + (((piece + j) ^ xr) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            piece += ncol >> 2;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (8 * j < ncol)
+                st_shared_v4(stg + (((piece + j) ^ xr) << 4),
+                             pack_bf16x2(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
+                             pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
+                             pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
+                             pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+            piece += ncol >> 3;
+          }
+          if (piece * 16 >= row_bytes || c0 + 32 >= p.bn) {
+            fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the bulk (async proxy) store
+            __syncwarp();
+            if (lane == 0) {
+              const uint32_t src = stg0 + static_cast<uint32_t>(ebuf) * 16384u;
+              if (p.epi_reduce)
+                tma_reduce_add_5d(map_out, src, cc0 + boxc, cw, cph, chh, cn);
+              else
+                tma_store_5d(map_out, src, cc0 + boxc, cw, cph, chh, cn);
+              bulk_commit_group();
+            }
+            piece = 0;
+            boxc = c0 + 32;
+            if (++ebuf == p.epi_bufs) ebuf = 0;
+          }
+        }
+      } else if (p.epi_tma == 2) {
+        // ---- conv weight gradient: acc[m = cb row][n = cs col] -> packed dW[tap][n][m]; staging [32 n][32 m] fp32
+        const uint64_t map_out = reinterpret_cast<uint64_t>(&p.map_out);
+        const Tap tap = p.taps[min(w.unit_tap, p.num_units - 1)];
+        const bool pair = p.mmod == 32;  // rows 0-31 / 32-63 belong to taps out_tap / out_tap + 1
+        const int m0 = pair ? 0 : m_tile * 128 + q * 32;
+        const int otap = tap.out_tap + (pair ? q : 0);
+        const bool warp_ok = (w.unit_tap < p.num_units) && (q * 32 < tap.mvalid) && (m_tile * 128 + q * 32 < p.m_valid);
+        const uint32_t stg0 = smem_u32(staging) + static_cast<uint32_t>(q) * 4096u;
+        const int ncols = min(p.bn, static_cast<int>(tap.nvalid) - n_tile * p.bn);
+        for (int c0 = 0; c0 < p.bn; c0 += 32) {
+          uint32_t v[32];
+          __syncwarp();
+          tmem_ld_32x32(lane_addr + static_cast<uint32_t>(c0), v);
+          tmem_ld_wait();
+          if (!warp_ok || c0 >= ncols) continue;
+          if (lane == 0) {
+            if (p.epi_bufs == 2) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
+          }
+          __syncwarp();
+          const uint32_t stg = stg0 + static_cast<uint32_t>(ebuf) * 16384u + static_cast<uint32_t>(lane) * 4u;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) st_shared_b32(stg + i * 128, v[i]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (p.epi_reduce)
+              tma_reduce_add_3d(map_out, stg0 + static_cast<uint32_t>(ebuf) * 16384u, m0, n_tile * p.bn + c0, otap);
+            else
+              tma_store_3d(map_out, stg0 + static_cast<uint32_t>(ebuf) * 16384u, m0, n_tile * p.bn + c0, otap);
+            bulk_commit_group();
+          }
+          if (++ebuf == p.epi_bufs) ebuf = 0;
+        }
+      } else if (p.mode == MODE_FWD && p.fold_kw) {
         // tile = bh full image rows of bw pixels; thread r = pixel (h, w').  acc[w'][kw*3+cb] holds the sum over kh
         // and cs for UNSHIFTED w'; out[h][w][cb] = sum_kw acc[h][w + 2 - kw][kw*3 + cb] (zero outside the row).
         uint32_t v[32];
@@ -537,6 +653,7 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
         mbar_arrive(&tmem_empty_bar[buf]);
       ++it;
     }
+    if (p.epi_tma && lane == 0) bulk_wait_group_all();  // smem must outlive the stores' reads; writes complete
   }
 
   tc_fence_before();
@@ -572,7 +689,7 @@ static EncodeTiledFn get_encode_fn() {
 
 // rank-`rank` bf16 tensor map; dims/box innermost first; strides in BYTES for dims 1..rank-1.
 static int encode_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides,
-                      const uint32_t* box, int swizzle_bytes) {
+                      const uint32_t* box, int swizzle_bytes, bool f32 = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(-2, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   cuuint64_t gdim[5], gstr[4];
@@ -585,7 +702,7 @@ static int encode_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t*
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides[i];
   CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                                : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(ptr), gdim,
+  CUresult r = fn(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(ptr), gdim,
                   gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -696,14 +813,17 @@ static int launch(GemmParams& p, dim3 grid, cudaStream_t stream, double flops, i
   const int sms = num_sms();
   // two CTAs per SM only if both their TMEM (2 x <=256 columns) and their smem rings fit
   const bool two_per_sm = p.tmem_cols <= 256 && stage_bytes <= 32768 && env_int("DM_ONE_CTA", 0) == 0;
-  const int budget = two_per_sm ? env_int("DM_SMEM_BUDGET_SMALL", 98304) : env_int("DM_SMEM_BUDGET_BIG", 196608);
+  // per-CTA ring budget: two CTAs per SM share 228 KB (1 KB of each is reserved); the TMA epilogue stages 16 KB (x2)
+  const int budget = two_per_sm ? env_int("DM_SMEM_BUDGET_SMALL", 98304)
+                                : env_int("DM_SMEM_BUDGET_BIG", 196608) - (p.epi_tma ? 16384 : 0);
   const int slots = sms * (two_per_sm ? 2 : 1) / cluster;  // concurrently resident CTAs (or CTA pairs)
   const int tiles_per_cta = (p.total_tiles + slots - 1) / slots;
   const long long kb_stream = static_cast<long long>(std::min(kb_per_cta, 1 << 20)) * tiles_per_cta;
   int stages = std::max(2, std::min(8, budget / stage_bytes));
   stages = static_cast<int>(std::max<long long>(1, std::min<long long>(stages, kb_stream)));
   p.stages = stages;
-  int smem = stages * stage_bytes + (2 * stages + 4) * 8 + 16 + 1024 + (p.fold_kw ? 128 * 17 * 4 : 0);
+  p.epi_bufs = p.epi_tma ? (two_per_sm ? 1 : 2) : 0;
+  int smem = stages * stage_bytes + p.epi_bufs * 16384 + (2 * stages + 4) * 8 + 16 + (p.fold_kw ? 128 * 17 * 4 : 0);
   // TMEM is 512 columns per SM: keep co-residency at <= 512 / tmem_cols CTAs by padding the smem request
   smem = std::max(smem, (two_per_sm ? 80 : 120) * 1024);
   static std::once_flag once;
@@ -785,6 +905,101 @@ static bool make_pix_tile(int P, int batch, int h, int w, PixTile* t) {
     t->tn_step = t->bimg;
     t->tiles = (batch + t->bimg - 1) / t->bimg;
   }
+  return true;
+}
+
+
+// ---- TMA epilogue set-up (GemmParams::epi_tma).  Returns false (legacy thread-store epilogue stays) when the
+// output cannot be described by a box store: odd leading dimensions, N tiles that are not whole boxes, ...
+static bool epi_common(GemmParams& p, const void* out, bool f32) {
+  if (env_int("DM_EPI_TMA", 1) == 0) return false;
+  if ((reinterpret_cast<uintptr_t>(out) & 15) != 0) return false;
+  const int full = f32 ? 32 : 64;           // columns of a 128-byte staging row
+  int cols = (p.bn % full == 0) ? full : ((p.bn % (full / 2) == 0 && p.bn == full / 2) ? full / 2 : 0);
+  if (cols == 0 || p.bn % 32 != 0) return false;
+  p.epi_cols = cols;
+  p.epi_swz = cols * (f32 ? 4 : 2);         // 128 or 64
+  return true;
+}
+
+// sub-box of 32 consecutive tile rows for a tile of bw x bh x bimg pixels (w fastest)
+static bool epi_sub_box(int bw, int bh, int bimg, uint32_t* sub) {
+  const int sw = std::min(bw, 32);
+  if (32 % sw != 0 || bw % sw != 0) return false;
+  const int sh = std::min(bh, 32 / sw);
+  if ((32 / sw) % sh != 0 || bh % sh != 0) return false;
+  const int sn = 32 / (sw * sh);
+  if (sn > bimg || bimg % sn != 0) return false;
+  sub[0] = sw; sub[1] = sh; sub[2] = sn;
+  return true;
+}
+
+// plain row-major matrix out[rows][cols] (leading dimension ld elements)
+static bool epi_rows_matrix(GemmParams& p, void* out, bool f32, long long rows, long long cols, long long ld,
+                            bool reduce, int row_step) {
+  if (!epi_common(p, out, f32)) return false;
+  const uint64_t es = f32 ? 4 : 2;
+  if ((ld * es) % 16 != 0) return false;
+  uint64_t dims[5] = {(uint64_t)cols, (uint64_t)rows, 1, 1, 1};
+  const uint64_t rs = (uint64_t)ld * es;
+  uint64_t str[4] = {rs, rs * rows, rs * rows, rs * rows};
+  uint32_t box[5] = {(uint32_t)p.epi_cols, 32, 1, 1, 1};
+  if (encode_map(&p.map_out, out, 5, dims, str, box, p.epi_swz, f32) != 0) return false;
+  p.epi_tma = 1; p.epi_reduce = reduce ? 1 : 0;
+  p.epi_bw = 128; p.epi_bh = 1; p.epi_row_step = row_step;
+  return true;
+}
+
+// NHWC activation out[b][h][w][c]; stride 2 = the four sub-pixel phases of a transposed convolution write the
+// parity-split view (2c, w/2, 2, h/2, b) at channel offset pw*c, parity ph
+static bool epi_rows_act(GemmParams& p, void* out, bool f32, int b, int h, int w, int c, int stride, const PixTile& pt) {
+  if (!epi_common(p, out, f32)) return false;
+  if (c % p.bn != 0) return false;  // a tile's columns must not spill into the other parity's channels
+  uint32_t sub[3];
+  if (!epi_sub_box(pt.bw, pt.bh, pt.bimg, sub)) return false;
+  const uint64_t e = f32 ? 4 : 2;
+  if ((c * e) % 16 != 0) return false;
+  uint64_t dims[5], str[4];
+  if (stride == 1) {
+    dims[0] = c; dims[1] = w; dims[2] = 1; dims[3] = h; dims[4] = b;
+    str[0] = c * e; str[1] = (uint64_t)w * c * e; str[2] = (uint64_t)w * c * e; str[3] = (uint64_t)h * w * c * e;
+  } else {
+    dims[0] = 2 * c; dims[1] = w / 2; dims[2] = 2; dims[3] = h / 2; dims[4] = b;
+    str[0] = 2 * c * e; str[1] = (uint64_t)w * c * e; str[2] = 2ull * w * c * e; str[3] = (uint64_t)h * w * c * e;
+  }
+  uint32_t box[5] = {(uint32_t)p.epi_cols, sub[0], 1, sub[1], sub[2]};
+  if (encode_map(&p.map_out, out, 5, dims, str, box, p.epi_swz, f32) != 0) return false;
+  p.epi_tma = 1; p.epi_reduce = 0;
+  p.epi_bw = pt.bw; p.epi_bh = pt.bh; p.epi_row_step = 0;
+  for (int ph = 0; ph < 2; ++ph)
+    for (int pw = 0; pw < 2; ++pw) {
+      p.phase_c[ph * 2 + pw] = (stride == 2) ? pw * c : 0;
+      p.phase_p[ph * 2 + pw] = (stride == 2) ? ph : 0;
+    }
+  return true;
+}
+
+// packed conv weight gradient dW[25][cs][cb] fp32 (cb contiguous): transposed reduce-add of [m = cb][n = cs] tiles
+static bool epi_wgrad_packed(GemmParams& p, float* dw, int cs, int cb) {
+  if (env_int("DM_EPI_TMA", 1) == 0) return false;
+  if ((reinterpret_cast<uintptr_t>(dw) & 15) != 0 || cb % 32 != 0 || cs % 32 != 0) return false;
+  uint64_t dims[3] = {(uint64_t)cb, (uint64_t)cs, 25};
+  uint64_t str[2] = {(uint64_t)cb * 4, (uint64_t)cb * cs * 4};
+  uint32_t box[3] = {32, 32, 1};
+  if (encode_map(&p.map_out, dw, 3, dims, str, box, 0, true) != 0) return false;
+  p.epi_tma = 2; p.epi_reduce = 1;
+  return true;
+}
+
+// dense out[n][m] fp32 with m contiguous (Linear weight gradient: rows of the accumulator are in-features)
+static bool epi_transposed_matrix(GemmParams& p, float* out, long long m, long long n, long long ld, bool reduce) {
+  if (env_int("DM_EPI_TMA", 1) == 0) return false;
+  if ((reinterpret_cast<uintptr_t>(out) & 15) != 0 || (ld * 4) % 16 != 0 || p.bn % 32 != 0 || n % 32 != 0) return false;
+  uint64_t dims[3] = {(uint64_t)m, (uint64_t)n, 1};
+  uint64_t str[2] = {(uint64_t)ld * 4, (uint64_t)ld * 4 * n};
+  uint32_t box[3] = {32, 32, 1};
+  if (encode_map(&p.map_out, out, 3, dims, str, box, 0, true) != 0) return false;
+  p.epi_tma = 2; p.epi_reduce = reduce ? 1 : 0;
   return true;
 }
 
@@ -912,6 +1127,7 @@ extern "C" int dm_gemm_bf16(const dm_gemm_desc* g, void* stream_) {
       rc = encode_w_map3(&p.map_b, g->b, 1, g->k, g->n, g->ldb, 64, 64, 128);
     if (rc) return rc;
     p.num_n_tiles = (g->n + p.bn - 1) / p.bn;
+    if (g->ldd_n == 1) epi_rows_matrix(p, g->d, g->d_f32 != 0, m_store, n_store, g->ldd_m, g->accumulate != 0, 0);
     DM_REQUIRE(splits <= p.cpt, "dm_gemm_bf16: splits %d > k-blocks %d", splits, p.cpt);
     grid = dim3((g->m + 127) / 128, p.num_n_tiles, splits);
   } else if (g->layout == DM_GEMM_TN) {
@@ -932,6 +1148,10 @@ extern "C" int dm_gemm_bf16(const dm_gemm_desc* g, void* stream_) {
     rc = encode_mat_map5(&p.map_b, g->b, g->k, g->n, g->ldb, 64, 64, 128);
     if (rc) return rc;
     p.num_n_tiles = (g->n + p.bn - 1) / p.bn;
+    if (g->ldd_n == 1)
+      epi_rows_matrix(p, g->d, true, m_store, n_store, g->ldd_m, g->accumulate != 0, 128);
+    else if (g->ldd_m == 1)
+      epi_transposed_matrix(p, static_cast<float*>(g->d), m_store, n_store, g->ldd_n, g->accumulate != 0);
     if (n_store > 32767) p.taps[0].nvalid = 32767;  // columns are bounded by n_tiles*bn anyway
     DM_REQUIRE(g->n <= 32767 || g->n % p.bn == 0, "dm_gemm_bf16: TN n too large for masked store");
     DM_REQUIRE(splits <= p.num_kb, "dm_gemm_bf16: splits %d > k-blocks %d", splits, p.num_kb);
@@ -1003,6 +1223,7 @@ extern "C" int dm_conv_down(const dm_conv_geom* g, const void* big, const void* 
   const int cluster = p.cg2 ? 2 : 1;
   if (int rc = encode_w_map3(&p.map_b, w_down, 25, g->cs, g->cb, g->cb, p.kc, p.bn / cluster, p.kc * 2)) return rc;
   p.num_n_tiles = (g->cs + p.bn - 1) / p.bn;
+  epi_rows_act(p, out_small, false, g->batch, g->hs, g->ws, g->cs, 1, pt);
   return launch(p, dim3(pt.tiles, p.num_n_tiles, 1), stream, 50.0 * g->batch * g->hs * g->ws * g->cs * g->cb, 1 << 30,
                 cluster);
 }
@@ -1080,6 +1301,7 @@ extern "C" int dm_conv_up(const dm_conv_geom* g, const void* small, const void* 
   const int cluster = p.cg2 ? 2 : 1;
   if (int rc = encode_w_map3(&p.map_b, w_up, fold ? 5 : 25, cb_pad, g->cs, g->cs, p.kc, p.bn / cluster, p.kc * 2)) return rc;
   p.num_n_tiles = (cb_pad + p.bn - 1) / p.bn;
+  if (!fold) epi_rows_act(p, out_big, out_f32 != 0, g->batch, g->hb, g->wb, g->cb, g->stride, pt);
   return launch(p, dim3(pt.tiles, p.num_n_tiles, nphase), stream, 50.0 * g->batch * g->hs * g->ws * g->cs * g->cb,
                 1 << 30, cluster);
 }
@@ -1119,6 +1341,7 @@ extern "C" int dm_conv_wgrad(const dm_conv_geom* g, const void* small, const voi
       p.taps[t].nvalid = static_cast<int16_t>(g->cs);
       p.taps[t].mvalid = static_cast<int16_t>(g->cb);
       p.taps[t].out_off = static_cast<int32_t>(t * tap_stride);
+      p.taps[t].out_tap = static_cast<int16_t>(t);
     }
     p.os_m = m_stride; p.os_m2 = 0; p.mmod = 1 << 30;
     p.m_valid = g->cb;
@@ -1138,6 +1361,7 @@ extern "C" int dm_conv_wgrad(const dm_conv_geom* g, const void* small, const voi
         t.nvalid = static_cast<int16_t>(g->cs);
         t.mvalid = static_cast<int16_t>(aw == 1 ? 32 : 64);
         t.out_off = static_cast<int32_t>((kh * 5 + 2 * aw + 2) * tap_stride);
+        t.out_tap = static_cast<int16_t>(kh * 5 + 2 * aw + 2);
       }
     p.os_m = m_stride; p.mmod = 32; p.os_m2 = tap_stride;
     p.m_valid = 64;
@@ -1147,6 +1371,7 @@ extern "C" int dm_conv_wgrad(const dm_conv_geom* g, const void* small, const voi
   if (int rc = encode_act_map(&p.map_a, big, g->batch, g->hb, g->wb, g->cb, g->stride, boxa, 128)) return rc;
   if (int rc = encode_act_map(&p.map_b, small, g->batch, g->hs, g->ws, g->cs, 1, boxa, 128)) return rc;
   p.wgrad_tap_on_a = 1;
+  if (!direct) epi_wgrad_packed(p, dw_packed, g->cs, g->cb);
   const int base_ctas = m_tiles * p.num_n_tiles * units;
   int splits = env_int("DM_WGRAD_SPLITS", 0);
   if (splits <= 0) splits = std::max(1, std::min(p.num_kb, (env_int("DM_WGRAD_CTAS", 296) + base_ctas - 1) / base_ctas));

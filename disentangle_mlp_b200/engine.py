@@ -152,6 +152,13 @@ def linear_wgrad(dy_bf16, x_bf16, batch, n_out, k_in, dw, overwrite=False):
 
 def conv_wgrad(g, small, big, dw, cache, name):
     """Conv / ConvT weight gradient through the tap-major packed scratch (persistent per weight, kept zeroed)."""
+    packed = getattr(cache, "packed_grads", None)
+    if packed is not None and (name + ".weight") in packed:
+        # fused trainers: the flat gradient buffer holds this weight's gradient in the packed layout already
+        gp = packed[name + ".weight"]
+        assert gp.data_ptr() == dw.data_ptr(), "packed gradient view does not alias the gradient handed in"
+        ops.conv_wgrad_packed(g, small, big, gp)
+        return
     if ops.WGRAD_DIRECT:
         ops.conv_wgrad(g, small, big, dw)
         return

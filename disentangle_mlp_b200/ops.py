@@ -70,7 +70,9 @@ def conv_up(g: ConvGeom, small, w_up, bias=None, out=None, out_f32=False):
     return out
 
 
-WGRAD_DIRECT = os.environ.get("DM_WGRAD_DIRECT", "1") != "0"
+# 0 (default): conv weight gradients are reduced into the tap-major packed layout [25][cs][cb] by bulk tensor
+# reductions (TMA) and unpacked once; 1: scattered 4-byte atomics straight into dw[cs][cb][5][5] (slower, kept for A/B)
+WGRAD_DIRECT = os.environ.get("DM_WGRAD_DIRECT", "0") != "0"
 
 
 def conv_wgrad_packed(g: ConvGeom, small, big, dw_packed):
@@ -220,8 +222,8 @@ def tanh_backward(dout, out, bias_grad=None):
     return dy
 
 
-def transpose(src, batch, rows, cols):
-    dst = torch.empty((batch, cols, rows), dtype=BF16, device=src.device)
+def transpose(src, batch, rows, cols, out=None):
+    dst = torch.empty((batch, cols, rows), dtype=BF16, device=src.device) if out is None else out
     _lib.check(_lib.load().dm_transpose_bf16(_p(src), batch, rows, cols, _p(dst), _stream()), "dm_transpose_bf16")
     return dst
 

@@ -52,14 +52,22 @@ class FlatParams:
         self.m = torch.zeros(off, dtype=F32, device=dev)
         self.v = torch.zeros(off, dtype=F32, device=dev)
         self.shadow = torch.zeros(off, dtype=BF16, device=dev)
-        self.P, self.G, self.W16 = {}, {}, {}
+        self.P, self.G, self.W16, self.GP = {}, {}, {}, {}
+        # 5x5 conv / deconv weights [cs][cb][5][5] with 32-aligned channel counts live in the flat buffers in the
+        # TAP-MAJOR layout [5][5][cs][cb]: that is the layout of the GEMM operand (the bf16 shadow IS w_down) and of
+        # the packed weight gradient the wgrad kernel reduces into (bulk tensor reductions need unit inner stride).
+        # The nn.Parameter becomes a permuted (non-contiguous) view with the reference shape; Adam is elementwise,
+        # so it does not care.
+        self.packed = {n for n, p in named if p.dim() == 4 and p.shape[0] % 32 == 0 and p.shape[1] % 32 == 0}
         for n, p in named:
             o, k = self.offsets[n], p.numel()
-            self.flat[o:o + k].copy_(p.data.reshape(-1))
-            p.data = self.flat[o:o + k].view(p.shape)
+            self._layout(self.flat, n, p.shape).copy_(p.data)
+            p.data = self._layout(self.flat, n, p.shape)
             self.P[n] = p
-            self.G[n] = self.grad[o:o + k].view(p.shape)
-            self.W16[n] = self.shadow[o:o + k].view(p.shape)
+            self.G[n] = self._layout(self.grad, n, p.shape)
+            self.W16[n] = self._layout(self.shadow, n, p.shape)
+            if n in self.packed:
+                self.GP[n] = self.grad[o:o + k].view(25, p.shape[0], p.shape[1])
         self.module = module
         self.buffers = dict(module.named_buffers())
         self.lr, self.betas, self.eps = lr, betas, eps
@@ -70,10 +78,17 @@ class FlatParams:
         # persistent bf16 operand packs of the conv / deconv weights ([cs][cb][5][5]), refreshed IN PLACE after every
         # update: no lazily rebuilt state, so a captured CUDA graph always reads current operands
         self.cache.static_packs = {}
+        self.cache.packed_grads = self.GP
         for n, p in named:
             if p.dim() == 4:
                 cs, cb = p.shape[0], p.shape[1]
-                self.cache.static_packs[n[:-len(".weight")]] = ops.pack_conv_weights(p.detach(), cs, cb, True, True, cb * 25 <= 128)
+                if n in self.packed:
+                    o, k = self.offsets[n], p.numel()
+                    w_down = self.shadow[o:o + k].view(25, cs, cb)
+                    w_up = torch.empty((25, cb, cs), dtype=BF16, device=dev)
+                    self.cache.static_packs[n[:-len(".weight")]] = (w_down, w_up, None)
+                else:
+                    self.cache.static_packs[n[:-len(".weight")]] = ops.pack_conv_weights(p.detach(), cs, cb, True, True, cb * 25 <= 128)
         # the big Linear weight gradients are written in "overwrite" mode by the first backward of a phase, so
         # zero_grad() only clears the rest of the flat gradient (8 % of it)
         big = sorted((self.offsets[n], self.offsets[n] + self.P[n].numel()) for n in self.names if n in BIG_LINEAR)
@@ -95,6 +110,15 @@ class FlatParams:
             self._late_ranges.append((lo, self.total))
         self.params_changed()
 
+    def _layout(self, buf, n, shape):
+        """View of parameter `n`'s slice of a flat buffer with the parameter's (reference) shape."""
+        o = self.offsets[n]
+        k = int(np.prod(shape)) if len(shape) else 1
+        if n in getattr(self, "packed", ()):
+            cs, cb = shape[0], shape[1]
+            return buf[o:o + k].view(5, 5, cs, cb).permute(2, 3, 0, 1)
+        return buf[o:o + k].view(shape)
+
     def reduce_early(self, reducer, name):
         o = self.offsets[name]
         reducer.allreduce_async(self.grad, o, o + self.P[name].numel())
@@ -107,7 +131,10 @@ class FlatParams:
     def refresh_packs(self):
         for name, packs in self.cache.static_packs.items():
             p = self.P[name + ".weight"]
-            ops.pack_conv_weights(p.detach(), p.shape[0], p.shape[1], out=packs)
+            if name + ".weight" in self.packed:  # w_down is the shadow itself; w_up = per-tap transpose of it
+                ops.transpose(packs[0], 25, p.shape[0], p.shape[1], out=packs[1])
+            else:
+                ops.pack_conv_weights(p.detach(), p.shape[0], p.shape[1], out=packs)
 
     def params_changed(self):
         """Call after the fp32 parameters were modified outside adam() (init, load_state_dict)."""
@@ -146,8 +173,8 @@ class FlatParams:
         for i, n in enumerate(self.names):
             o, k = self.offsets[n], self.P[n].numel()
             state[i] = {"step": torch.tensor(float(self.step_count)),
-                        "exp_avg": self.m[o:o + k].view(self.P[n].shape).clone(),
-                        "exp_avg_sq": self.v[o:o + k].view(self.P[n].shape).clone()}
+                        "exp_avg": self._layout(self.m, n, self.P[n].shape).contiguous().clone(),
+                        "exp_avg_sq": self._layout(self.v, n, self.P[n].shape).contiguous().clone()}
         group = {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": 0, "amsgrad": False,
                  "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
                  "decoupled_weight_decay": False, "params": list(range(len(self.names)))}
@@ -160,8 +187,8 @@ class FlatParams:
             if st is None:
                 continue
             o, k = self.offsets[n], self.P[n].numel()
-            self.m[o:o + k].copy_(st["exp_avg"].reshape(-1))
-            self.v[o:o + k].copy_(st["exp_avg_sq"].reshape(-1))
+            self._layout(self.m, n, self.P[n].shape).copy_(st["exp_avg"].view(self.P[n].shape))
+            self._layout(self.v, n, self.P[n].shape).copy_(st["exp_avg_sq"].view(self.P[n].shape))
             steps.add(int(st["step"]))
         if steps:
             assert len(steps) == 1, "per-parameter step counts differ; not representable"

@@ -2,9 +2,12 @@
 written by oracle/gen_curves.py) with identical initial weights, data, labels, noise and eps.
 
 The north-star tolerance for bf16 is 1e-2 per layer.  A 200-step TRAJECTORY of a GAN is chaotic, so each curve is
-judged against the reference's own sensitivity: the golden file also holds the oracle re-run with its input images
-perturbed by 1e-3 ("perturbed").  The CUDA path must stay within max(stated tolerance, 3x that chaos floor) in
-the median over the 200 steps, and within the stated tolerance over the first 10 steps.
+judged against the reference's own sensitivity.  The golden files hold, next to the fp32 oracle curve, two re-runs of
+the SAME oracle: "perturbed" (input images perturbed by 1e-3) and "bf16_emulated" (fp32 arithmetic with the outputs
+of every conv / Linear / BatchNorm, their gradients and the conv / Linear weights rounded to bf16 -- what any
+bf16-storage implementation of the reference costs on these trajectories).  The floor is the larger of the two
+deviations.  The CUDA path must stay within max(stated tolerance, 2x floor) in the median over the 200 steps and
+within max(stated tolerance, 3x floor) over the first 10 steps.
 """
 import json
 import os
@@ -17,15 +20,18 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 # key -> (tolerance over the first 10 steps, tolerance on the 200-step median deviation).
-# Measured on B200 (round 1): vae loss median 0.6 % (floor 0.14 %); gan errD median 3.3-3.7 % (floor 3.0 %);
-# beta-VAE-GAN recon_dec / recon_enc median 0.35-0.4 % (floor 0.26 %).  The first steps of the GAN-type loops are
-# a violent transient (the reference's own D saturates to BCE = 10 / 90 within 3 steps at lr 1e-3, Adam's first
-# updates are ~lr*sign(g)); two CUDA runs differ there by several per cent from fp32 atomics alone, hence the
-# looser first-10 bounds for those workloads.
+# Measured on B200 (round 1): vae loss median 0.4-0.6 % (bf16-emulated oracle: 0.84 %); gan errD median 2.6-3.7 %
+# (floor 3.0 %); beta-VAE-GAN recon_dec / recon_enc median 0.35-0.5 % (bf16-emulated oracle 0.35 %), kld median
+# 23-38 % (bf16-emulated oracle 24 %), sim median 10-17 % (bf16-emulated oracle 9.7 %).
+# The first steps of the GAN-type loops are a violent transient: the reference's own D saturates to BCE = 10 / 90
+# within 3 steps at lr 1e-3 and Adam's first updates are ~lr*sign(g), so gradient components below the rounding noise
+# flip their update direction.  `sim` at step 1 (D's feature distance right after D's first two updates) moves by
+# 40 % in the bf16-emulated oracle and by 70-180 % between two runs of this CUDA path that differ only in the
+# order of fp32 atomics; its first-10 bound is therefore only a sanity bound.
 TOL = {
     "vae": {"loss": (1e-2, 1e-2)},
     "gan": {"errD": (1e-1, 1e-1), "errG": (1e-1, 1e-1)},
-    "betavaegan": {"recon_dec": (2e-1, 3e-2), "recon_enc": (2e-1, 3e-2), "kld": (3e-1, 5e-2), "sim": (1.0, 2e-1)},
+    "betavaegan": {"recon_dec": (2e-1, 1e-2), "recon_enc": (2e-1, 1e-2), "kld": (5e-1, 5e-2), "sim": (2.5, 2e-1)},
 }
 
 
@@ -85,13 +91,15 @@ def test_200_step_curves_track_oracle(workload):
         ref = doc["curves"][key]
         dev = deviations(mine[key], ref)
         floor = deviations(doc["perturbed"][key], ref)
+        if "bf16_emulated" in doc:
+            floor = np.maximum(floor, deviations(doc["bf16_emulated"][key], ref))
         report[key] = {"first10_max": float(dev[:10].max()), "median": float(np.median(dev)),
                        "floor_median": float(np.median(floor)), "floor_first10_max": float(floor[:10].max())}
         if not np.all(np.isfinite(mine[key])):
             failures.append((key, "non-finite"))
         if not dev[:10].max() <= max(tol10, 3 * floor[:10].max()):
             failures.append((key, "first10", report[key]))
-        if not np.median(dev) <= max(tol_med, 3 * np.median(floor)):
+        if not np.median(dev) <= max(tol_med, 2 * np.median(floor)):
             failures.append((key, "median", report[key]))
     report["_first12"] = {k: {"cuda": mine[k][:12], "oracle": doc["curves"][k][:12]} for k in mine if k in doc["curves"]}
     os.makedirs("gpurun_out", exist_ok=True)

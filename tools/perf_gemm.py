@@ -44,6 +44,21 @@ def cases(b):
         out.append((f"down  {tag}", fl, lambda g=g, big=big, w_down=w_down, o_s=o_s: ops.conv_down(g, big, w_down, None, out=o_s)))
         out.append((f"up    {tag}", fl, lambda g=g, small=small, w_up=w_up, o_b=o_b: ops.conv_up(g, small, w_up, None, out=o_b)))
         out.append((f"wgrad {tag}", fl, lambda g=g, small=small, big=big, dw=dw: ops.conv_wgrad(g, small, big, dw)))
+        pk = torch.zeros(25, cs, cb, device=dev)
+        out.append((f"wgradP {tag}", fl, lambda g=g, small=small, big=big, pk=pk: ops.conv_wgrad_packed(g, small, big, pk)))
+    # the 16384 <-> 2048 Linear layers (weight-bandwidth bound): bytes-equivalent "TFLOP/s" column is not meaningful,
+    # read the microseconds: W is 67 MB in bf16 (10 us at 6.5 TB/s), dW 134 MB in fp32 (21 us)
+    from disentangle_mlp_b200 import engine
+    K, N = 16384, 2048
+    x = torch.randn(b, K, device=dev).bfloat16()
+    dy = torch.randn(b, N, device=dev).bfloat16()
+    wl = (torch.randn(N, K, device=dev) * 0.01).bfloat16()
+    bias = torch.zeros(N, device=dev)
+    dwl = torch.empty(N, K, device=dev)
+    dx = torch.empty(b, K, device=dev, dtype=torch.bfloat16)
+    out.append((f"lin_fwd  {b}x{N}x{K}", 2.0 * b * N * K, lambda: engine.linear_forward(x, wl, bias, b, N, K)))
+    out.append((f"lin_dgrad {b}x{K}x{N}", 2.0 * b * N * K, lambda: engine.linear_dgrad(dy, wl, b, N, K, out_dtype=torch.bfloat16)))
+    out.append((f"lin_wgrad {K}x{N}x{b}", 2.0 * b * N * K, lambda: engine.linear_wgrad(dy, x, b, N, K, dwl, overwrite=True)))
     return out
 
 
