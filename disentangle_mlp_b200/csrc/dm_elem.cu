@@ -373,30 +373,44 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, lo
 // ------------------------------------------------------------------------------------------ layout kernels
 // fp32 NCHW 3-channel image -> bf16 im2col matrix [batch*oh*ow, 80]; column = c*25 + kh*5 + kw (75 valid, 5 zero).
 // The GEMMs read it with K boxes of 32/64 columns: columns >= 80 are TMA out-of-bounds zero fill, never stored.
+// One block = one output row of one image: the 5 input rows x 3 channels it needs are staged in shared memory
+// (zero halo of 2 on each side), then the 160-byte rows of the matrix are written as coalesced 16-byte pieces.
 __global__ void __launch_bounds__(256) im2col3_kernel(const float* __restrict__ x, int batch, int h, int w,
                                                       int stride, __nv_bfloat16* __restrict__ col) {
+  extern __shared__ float patch[];  // [3 ch][5 kh][w + 4]
+  __shared__ int koff[80];          // column k -> offset of its tap in the patch (-1: zero column)
   const int oh = h / stride, ow = w / stride;
-  const long long total = static_cast<long long>(batch) * oh * ow * 10;  // 10 groups of 8 columns per pixel
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int grp = static_cast<int>(idx % 10);
-    const long long pix = idx / 10;
-    const int x0 = static_cast<int>(pix % ow);
-    const int y0 = static_cast<int>((pix / ow) % oh);
-    const int n = static_cast<int>(pix / (static_cast<long long>(ow) * oh));
-    float f[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int k = grp * 8 + i;
+  const int pw = w + 4;
+  if (threadIdx.x < 80) {
+    const int k = threadIdx.x;
+    const int ch = k / 25, t = k - ch * 25, kh = t / 5, kw = t - kh * 5;
+    koff[k] = (k < 75) ? (ch * 5 + kh) * pw + kw : -1;
+  }
+  for (long long row = blockIdx.x; row < static_cast<long long>(batch) * oh; row += gridDim.x) {
+    const int n = static_cast<int>(row / oh);
+    const int y0 = static_cast<int>(row - static_cast<long long>(n) * oh);
+    __syncthreads();  // previous row's readers are done (also orders the koff writes the first time)
+    for (int i = threadIdx.x; i < 15 * pw; i += blockDim.x) {
+      const int r = i / pw, px = i - r * pw;  // r = ch*5 + kh
+      const int ch = r / 5, kh = r - ch * 5;
+      const int iy = y0 * stride + kh - 2, ix = px - 2;
       float v = 0.f;
-      if (k < 75) {
-        const int ch = k / 25, t = k - ch * 25, kh = t / 5, kw = t - kh * 5;
-        const int iy = y0 * stride + kh - 2, ix = x0 * stride + kw - 2;
-        if (iy >= 0 && iy < h && ix >= 0 && ix < w) v = __ldg(x + ((static_cast<long long>(n) * 3 + ch) * h + iy) * w + ix);
-      }
-      f[i] = v;
+      if (iy >= 0 && iy < h && ix >= 0 && ix < w) v = __ldg(x + ((static_cast<long long>(n) * 3 + ch) * h + iy) * w + ix);
+      patch[i] = v;
     }
-    store8(col + pix * 80 + grp * 8, f);
+    __syncthreads();
+    __nv_bfloat16* dst = col + row * ow * 80;
+    for (int item = threadIdx.x; item < ow * 10; item += blockDim.x) {
+      const int x0 = item / 10, grp = item - x0 * 10;
+      const int base = x0 * stride;
+      float f[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int o = koff[grp * 8 + i];
+        f[i] = (o >= 0) ? patch[o + base] : 0.f;
+      }
+      store8(dst + item * 8, f);
+    }
   }
 }
 
@@ -855,7 +869,10 @@ extern "C" int dm_im2col3(const float* x_nchw, int batch, int h, int w, int stri
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   DM_REQUIRE(stride == 1 || stride == 2, "dm_im2col3: stride must be 1 or 2");
   const long long items = static_cast<long long>(batch) * (h / stride) * (w / stride) * 10;
-  im2col3_kernel<<<grid_for(items, 256, 148 * 32), 256, 0, s>>>(x_nchw, batch, h, w, stride, static_cast<bf16*>(col_bf16));
+  (void)items;
+  const long long out_rows = static_cast<long long>(batch) * (h / stride);
+  const int blocks = static_cast<int>(std::min<long long>(out_rows, 148 * 16));
+  im2col3_kernel<<<blocks, 256, 15 * (w + 4) * sizeof(float), s>>>(x_nchw, batch, h, w, stride, static_cast<bf16*>(col_bf16));
   DM_LAUNCHED("dm_im2col3");
 }
 

@@ -439,6 +439,14 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
           __syncwarp();  // tcgen05.ld is warp-collective
           tmem_ld_32x32(lane_addr + static_cast<uint32_t>(c0), v);
           tmem_ld_wait();
+          if (c0 + 32 >= p.bn) {
+            // all of this thread's TMEM reads of the tile are done: hand the accumulator back before the stores
+            tc_fence_before();
+            if (kCG2)
+              mbar_arrive_remote(&tmem_empty_bar[buf], 0);
+            else
+              mbar_arrive(&tmem_empty_bar[buf]);
+          }
           if (add_bias) {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
@@ -448,7 +456,9 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
           if (piece == 0) {
             // the staging buffer about to be filled must have been read by the store issued epi_bufs boxes ago
             if (lane == 0) {
-              if (p.epi_bufs == 2) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
+              if (p.epi_bufs == 4) bulk_wait_group_read<3>();
+              else if (p.epi_bufs == 2) bulk_wait_group_read<1>();
+              else bulk_wait_group_read<0>();
             }
             __syncwarp();
           }
@@ -502,9 +512,19 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
           __syncwarp();
           tmem_ld_32x32(lane_addr + static_cast<uint32_t>(c0), v);
           tmem_ld_wait();
+          if (c0 + 32 >= p.bn) {
+            // all of this thread's TMEM reads of the tile are done: hand the accumulator back before the stores
+            tc_fence_before();
+            if (kCG2)
+              mbar_arrive_remote(&tmem_empty_bar[buf], 0);
+            else
+              mbar_arrive(&tmem_empty_bar[buf]);
+          }
           if (!warp_ok || c0 >= ncols) continue;
           if (lane == 0) {
-            if (p.epi_bufs == 2) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
+            if (p.epi_bufs == 4) bulk_wait_group_read<3>();
+            else if (p.epi_bufs == 2) bulk_wait_group_read<1>();
+            else bulk_wait_group_read<0>();
           }
           __syncwarp();
           const uint32_t stg = stg0 + static_cast<uint32_t>(ebuf) * 16384u + static_cast<uint32_t>(lane) * 4u;
@@ -645,12 +665,15 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
         }
       }
       // this thread's TMEM reads of the accumulator are complete: hand the buffer back to the MMA issuer
+      // (the TMA epilogues did that already, right after their last tcgen05.ld)
       __syncwarp();
-      tc_fence_before();
-      if (kCG2)
-        mbar_arrive_remote(&tmem_empty_bar[buf], 0);  // the leader's MMA thread waits for both CTAs' epilogues
-      else
-        mbar_arrive(&tmem_empty_bar[buf]);
+      if (!p.epi_tma) {
+        tc_fence_before();
+        if (kCG2)
+          mbar_arrive_remote(&tmem_empty_bar[buf], 0);  // the leader's MMA thread waits for both CTAs' epilogues
+        else
+          mbar_arrive(&tmem_empty_bar[buf]);
+      }
       ++it;
     }
     if (p.epi_tma && lane == 0) bulk_wait_group_all();  // smem must outlive the stores' reads; writes complete
@@ -812,7 +835,9 @@ static int launch(GemmParams& p, dim3 grid, cudaStream_t stream, double flops, i
   p.tmem_cols = pow2_cols(2 * p.acc_stride);
   const int sms = num_sms();
   // two CTAs per SM only if both their TMEM (2 x <=256 columns) and their smem rings fit
-  const bool two_per_sm = p.tmem_cols <= 256 && stage_bytes <= 32768 && env_int("DM_ONE_CTA", 0) == 0;
+  // (and only if there are more tiles than SMs: otherwise one CTA per SM with a deeper ring hides more latency)
+  const bool two_per_sm = p.tmem_cols <= 256 && stage_bytes <= 32768 && env_int("DM_ONE_CTA", 0) == 0 &&
+                          p.total_tiles * cluster > sms;
   // per-CTA ring budget: two CTAs per SM share 228 KB (1 KB of each is reserved); the TMA epilogue stages 16 KB (x2)
   const int budget = two_per_sm ? env_int("DM_SMEM_BUDGET_SMALL", 98304)
                                 : env_int("DM_SMEM_BUDGET_BIG", 196608) - (p.epi_tma ? 16384 : 0);
@@ -822,8 +847,16 @@ static int launch(GemmParams& p, dim3 grid, cudaStream_t stream, double flops, i
   int stages = std::max(2, std::min(8, budget / stage_bytes));
   stages = static_cast<int>(std::max<long long>(1, std::min<long long>(stages, kb_stream)));
   p.stages = stages;
-  p.epi_bufs = p.epi_tma ? (two_per_sm ? 1 : 2) : 0;
-  int smem = stages * stage_bytes + p.epi_bufs * 16384 + (2 * stages + 4) * 8 + 16 + (p.fold_kw ? 128 * 17 * 4 : 0);
+  const int fixed = (2 * stages + 4) * 8 + 16 + (p.fold_kw ? 128 * 17 * 4 : 0);
+  p.epi_bufs = 0;
+  if (p.epi_tma) {
+    // per-CTA smem: 227 KB alone, or half of (228 KB - 2 x 1 KB reserved) when two CTAs share the SM
+    const int cap = two_per_sm ? (228 * 1024 - 2048) / 2 : 227 * 1024;
+    p.epi_bufs = 1;
+    for (int nb = 4; nb >= 2; nb >>= 1)
+      if (stages * stage_bytes + nb * 16384 + fixed <= cap) { p.epi_bufs = nb; break; }
+  }
+  int smem = stages * stage_bytes + p.epi_bufs * 16384 + fixed;
   // TMEM is 512 columns per SM: keep co-residency at <= 512 / tmem_cols CTAs by padding the smem request
   smem = std::max(smem, (two_per_sm ? 80 : 120) * 1024);
   static std::once_flag once;
@@ -1023,6 +1056,16 @@ static int pick_bn(int n, int cap) {
   return cap;
 }
 
+// Same, but halve the N tile (down to 64) while the launch would leave a quarter of the SMs without a tile:
+// `work` = number of 128-row tiles x phases that share one N tile.
+static int pick_bn_fill(int n, int cap, long long work) {
+  int bn = pick_bn(n, cap);
+  const int n16 = (n + 15) / 16 * 16;
+  while (bn >= 128 && (bn / 2) % 16 == 0 && n16 % (bn / 2) == 0 && work * ((n16 + bn - 1) / bn) < (num_sms() * 3) / 4)
+    bn /= 2;
+  return bn;
+}
+
 }  // namespace dm
 
 using namespace dm;
@@ -1207,7 +1250,7 @@ extern "C" int dm_conv_down(const dm_conv_geom* g, const void* big, const void* 
   init_params(p);
   p.mode = MODE_FWD;
   p.kc = (g->cb % 64 == 0) ? 64 : 32;
-  p.bn = pick_bn(g->cs, env_int("DM_BN_CAP", 128));
+  p.bn = pick_bn_fill(g->cs, env_int("DM_BN_CAP", 128), pt.tiles);
   p.cpt = g->cb / p.kc;
   p.phase_tap_start[0] = 0;
   p.phase_tap_start[1] = 25;
@@ -1240,7 +1283,7 @@ extern "C" int dm_conv_up(const dm_conv_geom* g, const void* small, const void* 
   init_params(p);
   p.mode = MODE_FWD;
   p.kc = (g->cs % 64 == 0) ? 64 : 32;
-  p.bn = pick_bn(cb_pad, env_int("DM_BN_CAP", 128));
+  p.bn = pick_bn_fill(cb_pad, env_int("DM_BN_CAP", 128), (g->stride == 2 ? 4ll : 1ll) * pt.tiles);
   p.cpt = g->cs / p.kc;
   int nphase = 0, nt = 0;
   const bool fold = (g->stride == 1 && g->cb == 3);
