@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <atomic>
+#include <mutex>
 #include <cstdint>
 
 #include "../../include/dm_b200.h"
@@ -158,15 +159,24 @@ __device__ __forceinline__ void sum_partials_block(const float* __restrict__ par
 template <typename T>
 __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ y, long long rows, int c,
                                                        long long rows_per_block, float* __restrict__ sums) {
+  // Shifted sums: sum (y - k) and sum (y - k)^2 with k = the channel's value in row 0.  E[(y-k)^2] - E[y-k]^2 does
+  // not cancel catastrophically when |mean| >> std (a BatchNorm1d feature that is nearly constant over a batch of
+  // 16), which the plain E[y^2] - E[y]^2 in fp32 does; torch uses a two-pass / Welford variance.
+  const int cv = blockIdx.x * blockDim.x + threadIdx.x;
+  float k[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (cv * 8 < c) load8(y + cv * 8, k);
   rows_reduce<T, 2>(rows, c, rows_per_block, sums, [&](long long r, int ch, float(&acc)[2][8]) {
     float f[8];
     load8(y + r * c + ch, f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      acc[0][i] += f[i];
-      acc[1][i] += f[i] * f[i];
+      const float d = f[i] - k[i];
+      acc[0][i] += d;
+      acc[1][i] += d * d;
     }
   });
+  // the shift travels with the partials: row gridDim.y of the [parts + 1][2][c] buffer
+  if (blockIdx.y == 0 && threadIdx.y == 0 && cv * 8 < c) store8(sums + 2ll * gridDim.y * c + cv * 8, k);
 }
 
 // Per-channel finalize: normalisation constants + running-stat update (momentum, unbiased running var),
@@ -180,13 +190,14 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
                                                             float* __restrict__ mean_invstd) {
   const int ch = blockIdx.x * 32 + threadIdx.x;
   float sum[2];
-  sum_partials_block<2>(partials, nparts, 2ll * c, ch, ch < c, c, sum);
+  sum_partials_block<2>(partials, nparts - 1, 2ll * c, ch, ch < c, c, sum);  // row nparts-1 = the shift k
   if (threadIdx.y != 0) return;
   if (ch == 0 && num_batches_tracked) *num_batches_tracked += 1;
   if (ch >= c) return;
   const double n = static_cast<double>(rows);
-  const double mean = sum[0] / n;
-  double var = sum[1] / n - mean * mean;
+  const double dmean = sum[0] / n;  // mean of (y - k)
+  const double mean = static_cast<double>(partials[2ll * (nparts - 1) * c + ch]) + dmean;
+  double var = sum[1] / n - dmean * dmean;
   if (var < 0.0) var = 0.0;
   const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
   const float sc = gamma[ch] * invstd;
@@ -304,6 +315,205 @@ __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __re
   sums[c + ch] = sum[1];
   if (dgamma) dgamma[ch] += sum[1];
   if (dbeta) dbeta[ch] += sum[0];
+}
+
+// ------------------------------------------------------------------------------------------ fused BatchNorm passes
+// One COOPERATIVE launch per BatchNorm application instead of three kernels: (1) every block reduces its rows into a
+// partial vector, (2) grid barrier, (3) every thread sums the gridDim.y partial vectors of ITS 8 channels (the ty
+// threads of a channel column split the partials and combine through shared memory) and derives the per-channel
+// constants, (4) every block normalises its rows (second read of y comes from L2: these tensors are far smaller than
+// the 126 MB L2).  Saves two launches + two pipeline drains per BatchNorm and the finalize kernel's serial tail.
+//
+// Grid barrier: sense-reversal on two words of a per-launch slot (launches on one stream are ordered, a captured
+// graph keeps its slot).  All blocks are co-resident because the kernel is launched cooperatively.
+__device__ __forceinline__ void grid_barrier(unsigned int* slot, unsigned int nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    volatile unsigned int* gen = slot + 1;
+    const unsigned int my_gen = *gen;
+    __threadfence();
+    if (atomicAdd(slot, 1u) == nblocks - 1u) {
+      slot[0] = 0u;
+      __threadfence();
+      atomicAdd(slot + 1, 1u);
+    } else {
+      while (*gen == my_gen) {
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// Totals of NACC accumulators for this thread's 8 channels from the gridDim.y block partials written by rows_reduce.
+template <int NACC>
+__device__ __forceinline__ void column_totals(const float* partials, int nparts, int c, int cv, bool live,
+                                              float (&tot)[NACC][8]) {
+  extern __shared__ float red[];  // [ty][tx*8*NACC] (reused: rows_reduce is done with it after the barrier)
+  const int tx = blockDim.x, ty = blockDim.y;
+  float acc[NACC][8];
+#pragma unroll
+  for (int a = 0; a < NACC; ++a)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[a][i] = 0.f;
+  if (live) {
+    for (int p = threadIdx.y; p < nparts; p += ty) {
+#pragma unroll
+      for (int a = 0; a < NACC; ++a) {
+        float f[8];
+        // plain (coherent) loads: the partials were written by other blocks of this same launch
+        const float4* src = reinterpret_cast<const float4*>(partials + (static_cast<long long>(p) * NACC + a) * c + cv * 8);
+        const float4 u = __ldcg(src), w = __ldcg(src + 1);
+        f[0] = u.x; f[1] = u.y; f[2] = u.z; f[3] = u.w; f[4] = w.x; f[5] = w.y; f[6] = w.z; f[7] = w.w;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[a][i] += f[i];
+      }
+    }
+  }
+  float* mine = red + (threadIdx.y * tx + threadIdx.x) * (8 * NACC);
+#pragma unroll
+  for (int a = 0; a < NACC; ++a)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mine[a * 8 + i] = acc[a][i];
+  __syncthreads();
+#pragma unroll
+  for (int a = 0; a < NACC; ++a)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float sum = 0.f;
+      for (int y = 0; y < ty; ++y) sum += red[(y * tx + threadIdx.x) * (8 * NACC) + a * 8 + i];
+      tot[a][i] = sum;
+    }
+  __syncthreads();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_fwd_fused_kernel(const T* __restrict__ y, long long rows, int c,
+                                                           long long rows_per_block, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float* __restrict__ running_mean,
+                                                           float* __restrict__ running_var,
+                                                           long long* __restrict__ num_batches_tracked, float momentum,
+                                                           float eps, int act, float slope, float* __restrict__ partials,
+                                                           float* __restrict__ scale_shift, float* __restrict__ mean_invstd,
+                                                           __nv_bfloat16* __restrict__ out, unsigned int* barrier) {
+  const int cv = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = cv * 8 < c;
+  float k[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // per-channel shift = row 0 (see bn_stats_kernel)
+  if (live) load8(y + cv * 8, k);
+  rows_reduce<T, 2>(rows, c, rows_per_block, partials, [&](long long r, int ch, float(&acc)[2][8]) {
+    float f[8];
+    load8(y + r * c + ch, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float d = f[i] - k[i];
+      acc[0][i] += d;
+      acc[1][i] += d * d;
+    }
+  });
+  grid_barrier(barrier, gridDim.x * gridDim.y);
+  float tot[2][8];
+  column_totals<2>(partials, gridDim.y, c, cv, live, tot);
+  if (!live) return;
+  float sc[8], sh[8], mu[8], is[8];
+  const double n = static_cast<double>(rows);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const double dmean = tot[0][i] / n;
+    const double mean = static_cast<double>(k[i]) + dmean;
+    double var = tot[1][i] / n - dmean * dmean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const int ch = cv * 8 + i;
+    sc[i] = gamma[ch] * invstd;
+    sh[i] = beta[ch] - static_cast<float>(mean) * sc[i];
+    mu[i] = static_cast<float>(mean);
+    is[i] = invstd;
+    if (blockIdx.y == 0 && threadIdx.y == 0 && running_mean) {
+      const double unbiased = rows > 1 ? var * n / (n - 1.0) : var;
+      running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * static_cast<float>(mean);
+      running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * static_cast<float>(unbiased);
+    }
+  }
+  if (blockIdx.y == 0 && threadIdx.y == 0) {
+    store8(scale_shift + cv * 8, sc);
+    store8(scale_shift + c + cv * 8, sh);
+    store8(mean_invstd + cv * 8, mu);
+    store8(mean_invstd + c + cv * 8, is);
+    if (cv == 0 && num_batches_tracked) *num_batches_tracked += 1;
+  }
+  const long long r0 = blockIdx.y * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+    float f[8];
+    load8(y + r * c + cv * 8, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = act_fwd(f[i] * sc[i] + sh[i], act, slope);
+    store8(out + r * c + cv * 8, f);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dout, const T* __restrict__ y,
+                                                           long long rows, int c, long long rows_per_block,
+                                                           const float* __restrict__ scale_shift,
+                                                           const float* __restrict__ mean_invstd, int act, float slope,
+                                                           float* __restrict__ partials, float* __restrict__ sums,
+                                                           __nv_bfloat16* __restrict__ dy, float* __restrict__ dgamma,
+                                                           float* __restrict__ dbeta, unsigned int* barrier) {
+  const int cv = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = cv * 8 < c;
+  float sc[8], sh[8], mu[8], is[8];
+  if (live) {
+    load8(scale_shift + cv * 8, sc);
+    load8(scale_shift + c + cv * 8, sh);
+    load8(mean_invstd + cv * 8, mu);
+    load8(mean_invstd + c + cv * 8, is);
+  }
+  rows_reduce<T, 2>(rows, c, rows_per_block, partials, [&](long long r, int ch, float(&acc)[2][8]) {
+    float f[8], g[8];
+    load8(y + r * c + ch, f);
+    load8(dout + r * c + ch, g);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float dz = g[i] * act_grad(f[i] * sc[i] + sh[i], act, slope);
+      acc[0][i] += dz;
+      acc[1][i] += dz * (f[i] - mu[i]) * is[i];
+    }
+  });
+  grid_barrier(barrier, gridDim.x * gridDim.y);
+  float tot[2][8];
+  column_totals<2>(partials, gridDim.y, c, cv, live, tot);
+  if (!live) return;
+  if (blockIdx.y == 0 && threadIdx.y == 0) {
+    store8(sums + cv * 8, tot[0]);
+    store8(sums + c + cv * 8, tot[1]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (dgamma) dgamma[cv * 8 + i] += tot[1][i];
+      if (dbeta) dbeta[cv * 8 + i] += tot[0][i];
+    }
+  }
+  const float inv_n = 1.f / static_cast<float>(rows);
+  float s0[8], s1[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    s0[i] = tot[0][i] * inv_n;
+    s1[i] = tot[1][i] * inv_n;
+  }
+  const long long r0 = blockIdx.y * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+    float f[8], g[8];
+    load8(y + r * c + cv * 8, f);
+    load8(dout + r * c + cv * 8, g);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float dz = g[i] * act_grad(f[i] * sc[i] + sh[i], act, slope);
+      const float xh = (f[i] - mu[i]) * is[i];
+      g[i] = sc[i] * (dz - s0[i] - xh * s1[i]);  // sc = gamma * invstd
+    }
+    store8(dy + r * c + cv * 8, g);
+  }
 }
 
 // out[i] (+)= sum_p partials[p][i]
@@ -771,7 +981,9 @@ typedef __nv_bfloat16 bf16;
 
 #define DM_CHECK_C8(c, who) DM_REQUIRE((c) % 8 == 0, who ": channel count %d must be a multiple of 8", (c))
 
-extern "C" int dm_bn_parts(long long rows, int c) { return make_row_layout(rows, c).gy; }
+// rows of the [parts][2][c] scratch handed to dm_bn_stats / dm_bn_finalize / dm_bn_forward / dm_bn_backward: one per
+// row block plus one that carries the per-channel shift of the shifted-sum statistics
+extern "C" int dm_bn_parts(long long rows, int c) { return make_row_layout(rows, c).gy + 1; }
 
 extern "C" int dm_bn_stats(const void* y, int y_f32, long long rows, int c, float* partials, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
@@ -807,6 +1019,105 @@ extern "C" int dm_bn_apply_act(const void* y, int y_f32, long long rows, int c, 
   DM_LAUNCHED("dm_bn_apply_act");
 }
 
+// ---- cooperative launches of the fused BatchNorm kernels
+// Barrier slots: 2 words per launch out of a small per-device pool (zeroed once); launches take slots round-robin, so
+// two fused launches that could overlap (different streams) practically never share one, and a captured graph keeps
+// the slots it was captured with.
+static unsigned int* barrier_slot() {
+  static std::mutex mu;
+  static unsigned int* pool[64] = {nullptr};
+  static std::atomic<unsigned int> next{0};
+  constexpr unsigned int kSlots = 4096;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return nullptr;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (!pool[dev]) {
+      unsigned int* p = nullptr;
+      if (cudaMalloc(&p, kSlots * 2 * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+      cudaMemset(p, 0, kSlots * 2 * sizeof(unsigned int));
+      cudaDeviceSynchronize();
+      pool[dev] = p;
+    }
+  }
+  return pool[dev] + 2 * (next.fetch_add(1, std::memory_order_relaxed) % kSlots);
+}
+
+template <typename K>
+static int max_coresident_blocks(K kernel, size_t smem) {
+  int per_sm = 0, dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem) != cudaSuccess) return 0;
+  return per_sm * sms;
+}
+
+template <typename K, typename... Args>
+static cudaError_t launch_coop(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
+// DM_BN_FUSED: unset / 0 = three-kernel paths (default), 1 = both passes as single cooperative launches, 2 = forward
+// only, 3 = backward only.  Measured on B200 (round 1, whole step in a CUDA graph, batch 64): the cooperative
+// launches cost ~27 us EACH more than the three plain kernels they replace (7.49 vs 5.70 ms/step), so the fused
+// kernels stay off; they are kept, tested, as the starting point for a non-cooperative variant.
+static bool fused_bn_enabled(bool forward = true) {
+  const char* e = getenv("DM_BN_FUSED");
+  if (!e) return false;
+  if (e[0] == '0') return false;
+  if (e[0] == '2') return forward;
+  if (e[0] == '3') return !forward;
+  return true;
+}
+
+// BatchNorm forward in one launch: statistics + running-stat update + normalise + activation.  `partials` is
+// [dm_bn_parts(rows, c)][2][c] scratch; scale_shift / mean_invstd ([2][c] each) are saved for the backward pass.
+extern "C" int dm_bn_forward(const void* y, int y_f32, long long rows, int c, const float* gamma, const float* beta,
+                             float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
+                             float eps, int act, float slope, float* partials, float* scale_shift, float* mean_invstd,
+                             void* out_bf16, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  DM_CHECK_C8(c, "dm_bn_forward");
+  RowLayout l = make_row_layout(rows, c);
+  const size_t sm = sizeof(float) * 256 * 16;
+  static int cap_f32 = -1, cap_bf16 = -1;
+  if (cap_f32 < 0) cap_f32 = max_coresident_blocks(bn_fwd_fused_kernel<float>, sm);
+  if (cap_bf16 < 0) cap_bf16 = max_coresident_blocks(bn_fwd_fused_kernel<bf16>, sm);
+  unsigned int* slot = fused_bn_enabled() ? barrier_slot() : nullptr;
+  const int cap = y_f32 ? cap_f32 : cap_bf16;
+  if (slot && l.gx * l.gy <= cap) {
+    cudaError_t e;
+    if (y_f32)
+      e = launch_coop(bn_fwd_fused_kernel<float>, dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s, static_cast<const float*>(y), rows, c,
+                      l.rows_per_block, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, act, slope,
+                      partials, scale_shift, mean_invstd, static_cast<bf16*>(out_bf16), slot);
+    else
+      e = launch_coop(bn_fwd_fused_kernel<bf16>, dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s, static_cast<const bf16*>(y), rows, c,
+                      l.rows_per_block, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, act, slope,
+                      partials, scale_shift, mean_invstd, static_cast<bf16*>(out_bf16), slot);
+    if (e != cudaSuccess) return set_error((int)e, "dm_bn_forward: cooperative launch: %s", cudaGetErrorString(e));
+    DM_LAUNCHED("dm_bn_forward");
+  }
+  // three-kernel path (grid too large to be co-resident, or DM_BN_FUSED=0)
+  if (int rc = dm_bn_stats(y, y_f32, rows, c, partials, stream_)) return rc;
+  if (int rc = dm_bn_finalize(partials, l.gy + 1, rows, c, gamma, beta, running_mean, running_var, num_batches_tracked, momentum,
+                              eps, scale_shift, mean_invstd, stream_))
+    return rc;
+  return dm_bn_apply_act(y, y_f32, rows, c, scale_shift, act, slope, out_bf16, stream_);
+}
+
 extern "C" int dm_bn_backward(const void* dout_bf16, const void* y, int y_f32, long long rows, int c,
                               const float* scale_shift, const float* mean_invstd, int act, float slope,
                               float* partials, float* sums, void* dy_bf16, float* dgamma, float* dbeta, void* stream_) {
@@ -815,6 +1126,25 @@ extern "C" int dm_bn_backward(const void* dout_bf16, const void* y, int y_f32, l
   RowLayout l = make_row_layout(rows, c);
   const size_t sm = sizeof(float) * 256 * 16;
   const bf16* d = static_cast<const bf16*>(dout_bf16);
+  {
+    static int cap_f32 = -1, cap_bf16 = -1;
+    if (cap_f32 < 0) cap_f32 = max_coresident_blocks(bn_bwd_fused_kernel<float>, sm);
+    if (cap_bf16 < 0) cap_bf16 = max_coresident_blocks(bn_bwd_fused_kernel<bf16>, sm);
+    unsigned int* slot = fused_bn_enabled(false) ? barrier_slot() : nullptr;
+    if (slot && l.gx * l.gy <= (y_f32 ? cap_f32 : cap_bf16)) {
+      cudaError_t e;
+      if (y_f32)
+        e = launch_coop(bn_bwd_fused_kernel<float>, dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s, d, static_cast<const float*>(y), rows, c,
+                        l.rows_per_block, scale_shift, mean_invstd, act, slope, partials, sums, static_cast<bf16*>(dy_bf16), dgamma,
+                        dbeta, slot);
+      else
+        e = launch_coop(bn_bwd_fused_kernel<bf16>, dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s, d, static_cast<const bf16*>(y), rows, c,
+                        l.rows_per_block, scale_shift, mean_invstd, act, slope, partials, sums, static_cast<bf16*>(dy_bf16), dgamma,
+                        dbeta, slot);
+      if (e != cudaSuccess) return set_error((int)e, "dm_bn_backward: cooperative launch: %s", cudaGetErrorString(e));
+      DM_LAUNCHED("dm_bn_backward");
+    }
+  }
   if (y_f32)
     bn_bwd_reduce_kernel<float><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s>>>(d, static_cast<const float*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, act, slope, partials);
   else

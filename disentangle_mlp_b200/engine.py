@@ -88,8 +88,10 @@ def bn_act_forward(y, rows, c, P, B, prefix, act, training=True, groups=1):
     for g in range(groups):
         ys = y2[g * rg:(g + 1) * rg]
         if training:
-            partials = ops.bn_stats(ys, rg, c)
-            ss, mi = ops.bn_finalize(partials, rg, c, gamma.detach(), beta.detach(), rm, rv, nbt, BN_MOMENTUM, BN_EPS)
+            _, ss, mi = ops.bn_forward(ys, rg, c, gamma.detach(), beta.detach(), rm, rv, nbt, act, LEAKY, BN_MOMENTUM, BN_EPS,
+                                       out=o2[g * rg:(g + 1) * rg])
+            states.append(BNState(ys, rg, c, ss, mi, act))
+            continue
         else:  # inference statistics (the reference scripts never call .eval(); kept for completeness)
             invstd = torch.rsqrt(rv + BN_EPS)
             sc = gamma.detach() * invstd

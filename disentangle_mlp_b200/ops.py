@@ -165,6 +165,19 @@ def bn_apply_act(y, rows, c, scale_shift, act, slope=0.2, out=None):
     return out
 
 
+def bn_forward(y, rows, c, gamma, beta, running_mean, running_var, nbt, act, slope=0.2, momentum=0.1, eps=1e-5, out=None):
+    """Training-mode BatchNorm + activation in one (cooperative) launch.  Returns (out, scale_shift, mean_invstd)."""
+    if out is None:
+        out = torch.empty(y.shape, dtype=BF16, device=y.device)
+    partials = torch.empty((bn_parts(rows, c), 2, c), dtype=F32, device=y.device)
+    scale_shift = torch.empty((2, c), dtype=F32, device=y.device)
+    mean_invstd = torch.empty((2, c), dtype=F32, device=y.device)
+    _lib.check(_lib.load().dm_bn_forward(_p(y), int(y.dtype == F32), rows, c, _p(gamma), _p(beta), _p(running_mean),
+                                         _p(running_var), _p(nbt), momentum, eps, act, slope, _p(partials),
+                                         _p(scale_shift), _p(mean_invstd), _p(out), _stream()), "dm_bn_forward")
+    return out, scale_shift, mean_invstd
+
+
 def bn_backward(dout, y, rows, c, scale_shift, mean_invstd, act, slope=0.2, dgamma=None, dbeta=None, out=None):
     assert dout.dtype == BF16
     dy = torch.empty(y.shape, dtype=BF16, device=y.device) if out is None else out

@@ -98,7 +98,9 @@ int dm_unpack_conv_grad(float* dw_packed, int cs, int cb, int accumulate, float*
  * Reductions over rows are two-level: every thread block writes one partial vector, the consumer kernel sums
  * them (no same-address atomics).  dm_bn_parts(rows, c) = number of partial vectors = leading dimension of the
  * caller-provided `partials` scratch ([parts][2][c] floats; [parts][c] for dm_act_backward / dm_colsum).
- *   dm_bn_stats    : partials[p][0][c] = sum_r y, partials[p][1][c] = sum_r y^2 over block p's rows
+ *   dm_bn_stats    : SHIFTED sums, k[c] = y[0][c]: partials[p][0][c] = sum_r (y - k), partials[p][1][c] = sum_r (y - k)^2
+ *                    over block p's rows; the LAST of the dm_bn_parts() rows carries k (E[(y-k)^2] - E[y-k]^2 does not
+ *                    cancel when |mean| >> std, unlike E[y^2] - E[y]^2 in fp32; torch computes a two-pass variance)
  *   dm_bn_finalize : scale = gamma*invstd, shift = beta - mean*scale; running stats updated with
  *                    `momentum` and the unbiased variance; num_batches_tracked += 1 (may be NULL)
  *   dm_bn_apply_act: out = act(y*scale + shift)   (the ReLU / LeakyReLU(0.2) that follows every BN)
@@ -111,6 +113,13 @@ int dm_bn_finalize(const float* partials, int nparts, long long rows, int c, con
                    float eps, float* scale_shift, float* mean_invstd, void* stream);
 int dm_bn_apply_act(const void* y, int y_f32, long long rows, int c, const float* scale_shift, int act,
                     float slope, void* out_bf16, void* stream);
+/* dm_bn_forward = dm_bn_stats + dm_bn_finalize + dm_bn_apply_act in ONE cooperative launch (grid barrier between the
+ * reduction and the normalisation; falls back to the three kernels when the grid cannot be co-resident).
+ * dm_bn_backward likewise runs its reduction, finalize and apply steps as one cooperative launch when it can. */
+int dm_bn_forward(const void* y, int y_f32, long long rows, int c, const float* gamma, const float* beta,
+                  float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
+                  int act, float slope, float* partials, float* scale_shift, float* mean_invstd, void* out_bf16,
+                  void* stream);
 int dm_bn_backward(const void* dout_bf16, const void* y, int y_f32, long long rows, int c,
                    const float* scale_shift, const float* mean_invstd, int act, float slope, float* partials,
                    float* sums, void* dy_bf16, float* dgamma, float* dbeta, void* stream);

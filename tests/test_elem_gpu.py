@@ -32,7 +32,7 @@ def test_batchnorm_forward_backward(ops, rows, c, dtype, act):
     sums = ops.bn_stats(y, rows, c)
     ss, mi = ops.bn_finalize(sums, rows, c, gamma, beta, rm, rv, nbt)
     out = ops.bn_apply_act(y, rows, c, ss, act, 0.2)
-    yr = y.float().requires_grad_(True)
+    yr = y.float().clone().requires_grad_(True)
     gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
     z = F.batch_norm(yr, rm_ref, rv_ref, gr, br, training=True, momentum=0.1, eps=1e-5)
     ref = {0: z, 1: F.relu(z), 2: F.leaky_relu(z, 0.2)}[act]
@@ -44,6 +44,37 @@ def test_batchnorm_forward_backward(ops, rows, c, dtype, act):
     dy, _ = ops.bn_backward(dout, y, rows, c, ss, mi, act, 0.2, dg, db)
     assert rel(dy, yr.grad) < 6e-3
     assert rel(dg, gr.grad) < 2e-3 and rel(db, br.grad) < 2e-3
+
+
+@pytest.mark.parametrize("fused", ["1", "0"])
+@pytest.mark.parametrize("rows,c,dtype,act", [(64 * 4096, 32, torch.bfloat16, 2), (4096, 256, torch.bfloat16, 1),
+                                             (64, 16384, torch.float32, 1), (1000, 64, torch.bfloat16, 0)])
+def test_batchnorm_single_launch(ops, rows, c, dtype, act, fused, monkeypatch):
+    """dm_bn_forward / dm_bn_backward: statistics, finalize and apply in ONE cooperative launch (grid barrier), and
+    the same entry points forced onto the three-kernel path (DM_BN_FUSED=0); twice in a row to exercise the barrier
+    slot's generation counter."""
+    monkeypatch.setenv("DM_BN_FUSED", fused)
+    torch.manual_seed(1)
+    y = (torch.randn(rows, c, device="cuda") * 1.3 - 0.2).to(dtype)
+    gamma = torch.randn(c, device="cuda") * 0.1 + 1
+    beta = torch.randn(c, device="cuda") * 0.1
+    for rep in range(2):
+        rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+        nbt = torch.zeros((), dtype=torch.long, device="cuda")
+        rm_ref, rv_ref = rm.clone(), rv.clone()
+        out, ss, mi = ops.bn_forward(y, rows, c, gamma, beta, rm, rv, nbt, act, 0.2)
+        yr = y.float().clone().requires_grad_(True)  # clone: y.float() aliases an fp32 y
+        gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+        z = F.batch_norm(yr, rm_ref, rv_ref, gr, br, training=True, momentum=0.1, eps=1e-5)
+        ref = {0: z, 1: F.relu(z), 2: F.leaky_relu(z, 0.2)}[act]
+        assert rel(out, ref) < 4e-3
+        assert rel(rm, rm_ref) < 1e-4 and rel(rv, rv_ref) < 1e-4 and int(nbt) == 1
+        dout = torch.randn(rows, c, device="cuda").bfloat16()
+        ref.backward(dout.float())
+        dg, db = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
+        dy, _ = ops.bn_backward(dout, y, rows, c, ss, mi, act, 0.2, dg, db)
+        assert rel(dy, yr.grad) < 6e-3
+        assert rel(dg, gr.grad) < 2e-3 and rel(db, br.grad) < 2e-3
 
 
 @pytest.mark.parametrize("stride", [1, 2])
