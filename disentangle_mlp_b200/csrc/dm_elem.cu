@@ -729,6 +729,28 @@ __global__ void __launch_bounds__(256) pack_conv_kernel(const float* __restrict_
   }
 }
 
+// Stride-2 transposed convolution with few output channels (cb = 32): the four sub-pixel phases share one GEMM.
+// w_upm[t = dhi*3 + dwi][n = (ph*2 + pw)*cb + c][cs] = w_up[kh*5 + kw][c][cs] with kh = ph + 2 - 2*dh, kw = pw + 2 - 2*dw
+// (dh = 1 - dhi, dw = 1 - dwi) when that filter tap exists, else 0: 9 input taps x N = 4*cb instead of 25 taps x N = cb.
+__global__ void __launch_bounds__(256) pack_up_merged_kernel(const __nv_bfloat16* __restrict__ w_up, int cs, int cb,
+                                                             __nv_bfloat16* __restrict__ w_upm) {
+  const long long total = 9ll * 4 * cb * cs;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % cs);
+    long long r = i / cs;
+    const int c = static_cast<int>(r % cb);
+    r /= cb;
+    const int phase = static_cast<int>(r % 4);
+    const int t = static_cast<int>(r / 4);
+    const int dh = 1 - t / 3, dw = 1 - t % 3, ph = phase >> 1, pw = phase & 1;
+    const int kh = ph + 2 - 2 * dh, kw = pw + 2 - 2 * dw;
+    __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+    if (kh >= 0 && kh < 5 && kw >= 0 && kw < 5) v = w_up[(static_cast<long long>(kh * 5 + kw) * cb + c) * cs + k];
+    w_upm[i] = v;
+  }
+}
+
 // tap-major packed conv gradient [25][n] -> master layout [n][25] (n = cs*cb); dw (+)= ; the packed buffer is
 // re-zeroed so that the next backward pass can accumulate into it again
 __global__ void __launch_bounds__(256) unpack_conv_grad_kernel(float* __restrict__ packed, long long n, int accumulate,
@@ -1233,6 +1255,13 @@ extern "C" int dm_pack_conv_weights(const float* w, int cs, int cb, void* w_down
   const long long total = 25ll * cs * cb + 25ll * cb_pad * cs + 128ll * cs;
   pack_conv_kernel<<<grid_for(total), 256, 0, s>>>(w, cs, cb, cb_pad, static_cast<bf16*>(w_down), static_cast<bf16*>(w_up), static_cast<bf16*>(w_col));
   DM_LAUNCHED("dm_pack_conv_weights");
+}
+
+extern "C" int dm_pack_up_merged(const void* w_up, int cs, int cb, void* w_upm, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  DM_REQUIRE(cb % 16 == 0, "dm_pack_up_merged: cb %d must be a multiple of 16", cb);
+  pack_up_merged_kernel<<<grid_for(36ll * cb * cs), 256, 0, s>>>(static_cast<const bf16*>(w_up), cs, cb, static_cast<bf16*>(w_upm));
+  DM_LAUNCHED("dm_pack_up_merged");
 }
 
 extern "C" int dm_unpack_conv_grad(float* packed, int cs, int cb, int accumulate, float* dw, void* stream_) {

@@ -93,6 +93,8 @@ struct alignas(64) GemmParams {
   CUtensorMap map_out;
   int epi_tma, epi_reduce, epi_cols, epi_swz, epi_bufs;
   int epi_bw, epi_bh;    // mode 1: rows of the tile are pixels (w fastest, then h, then n) of an epi_bw x epi_bh x . box
+  int epi_merge;         // mode 1, phase-merged transposed conv: 64-column box j goes to row parity j, channel 0
+  int bias_mod;          // != 0 (a power of two): bias index = column % bias_mod (phase-merged columns repeat the channels)
   int epi_row_step;      // mode 1: coordinate-1 origin of tile m (plain matrices: 128), 0 for pixel tiles
   int phase_c[4], phase_p[4];  // mode 1, transposed-conv phases: channel-coordinate offset (pw * cb) and row parity ph
   int dbg;             // timing experiments only (DM_DBG): 1 = skip the A loads, 2 = skip the B loads, 4 = skip the MMAs
@@ -428,6 +430,7 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
         const int cph = (p.mode == MODE_FWD) ? p.phase_p[w.phase] : 0;
         const int cc0 = ((p.mode == MODE_FWD) ? p.phase_c[w.phase] : 0) + n_tile * p.bn;
         const bool add_bias = (p.bias != nullptr) && (w.split == 0);
+        const int bias_mask = p.bias_mod ? p.bias_mod - 1 : 0x7fffffff;  // bias_mod is a power of two
         const uint32_t stg0 = smem_u32(staging) + static_cast<uint32_t>(q) * 4096u;
         const int row_bytes = p.epi_cols * (p.out_f32 ? 4 : 2);          // 128 or 64
         const uint32_t xr = (row_bytes == 128) ? (lane & 7) : ((lane >> 1) & 3);  // SWIZZLE_128B : SWIZZLE_64B
@@ -450,8 +453,10 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
           if (add_bias) {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (n_tile * p.bn + c0 + i < p.n_valid)
-                v[i] = __float_as_uint(__uint_as_float(v[i]) + __ldg(p.bias + n_tile * p.bn + c0 + i));
+              if (n_tile * p.bn + c0 + i < p.n_valid) {
+                const int bi = n_tile * p.bn + c0 + i;
+                v[i] = __float_as_uint(__uint_as_float(v[i]) + __ldg(p.bias + (bi & bias_mask)));
+              }
           }
           if (piece == 0) {
             // the staging buffer about to be filled must have been read by the store issued epi_bufs boxes ago
@@ -488,6 +493,8 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
               const uint32_t src = stg0 + static_cast<uint32_t>(ebuf) * 16384u;
               if (p.epi_reduce)
                 tma_reduce_add_5d(map_out, src, cc0 + boxc, cw, cph, chh, cn);
+              else if (p.epi_merge)
+                tma_store_5d(map_out, src, 0, cw, boxc >> 6, chh, cn);
               else
                 tma_store_5d(map_out, src, cc0 + boxc, cw, cph, chh, cn);
               bulk_commit_group();
@@ -1347,6 +1354,60 @@ extern "C" int dm_conv_up(const dm_conv_geom* g, const void* small, const void* 
   if (!fold) epi_rows_act(p, out_big, out_f32 != 0, g->batch, g->hb, g->wb, g->cb, g->stride, pt);
   return launch(p, dim3(pt.tiles, p.num_n_tiles, nphase), stream, 50.0 * g->batch * g->hs * g->ws * g->cs * g->cb,
                 1 << 30, cluster);
+}
+
+// Phase-merged stride-2 transposed convolution for cb == 32 (see dm_pack_up_merged): ONE GEMM with 9 input taps and
+// N = 4 * cb = 128 columns (column = (ph*2 + pw)*cb + c) instead of four phase GEMMs with N = 32.  An A tile is then
+// loaded 9 times instead of 25 and feeds 128-wide MMAs: the N = 32 form is bound by L2 -> smem operand traffic
+// (measured 15.6 TB/s, 21 % tensor-pipe), this one by the tensor pipe.  31 % of the MMA work multiplies zeros.
+extern "C" int dm_conv_up_merged(const dm_conv_geom* g, const void* small, const void* w_upm, const float* bias,
+                                 void* out_big, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (int rc = check_geom(g, "dm_conv_up_merged")) return rc;
+  DM_REQUIRE(g->stride == 2 && g->cb == 32, "dm_conv_up_merged: needs stride 2 and cb == 32");
+  DM_REQUIRE(g->cs % 64 == 0, "dm_conv_up_merged: cs %d must be a multiple of 64", g->cs);
+  PixTile pt;
+  DM_REQUIRE(make_pix_tile(128, g->batch, g->hs, g->ws, &pt), "dm_conv_up_merged: unsupported grid %dx%d", g->hs, g->ws);
+  GemmParams p;
+  init_params(p);
+  p.mode = MODE_FWD;
+  p.kc = 64;
+  p.bn = 4 * g->cb;
+  p.cpt = g->cs / p.kc;
+  int nt = 0;
+  p.phase_tap_start[0] = 0;
+  for (int dh = 1; dh >= -1; --dh)
+    for (int dw = 1; dw >= -1; --dw) {
+      Tap& t = p.taps[nt];
+      t.dh = static_cast<int8_t>(dh);
+      t.dw = static_cast<int8_t>(dw);
+      t.wt = static_cast<uint8_t>(nt);
+      ++nt;
+    }
+  p.phase_tap_start[1] = nt;
+  p.tw_step = 0; p.tpi = pt.tpi; p.th_step = pt.th_step; p.tn_step = pt.tn_step;
+  p.bw = pt.bw; p.bh = pt.bh;
+  p.out = out_big; p.bias = bias; p.out_f32 = 0; p.out_atomic = 0;
+  p.bias_mod = g->cb;
+  p.w_lim = g->ws; p.n_lim = g->batch; p.n_valid = p.bn;
+  uint32_t box[5] = {(uint32_t)p.kc, (uint32_t)pt.bw, 1, (uint32_t)pt.bh, (uint32_t)pt.bimg};
+  if (int rc = encode_act_map(&p.map_a, small, g->batch, g->hs, g->ws, g->cs, 1, box, p.kc * 2)) return rc;
+  if (int rc = encode_w_map3(&p.map_b, w_upm, 9, p.bn, g->cs, g->cs, p.kc, p.bn, p.kc * 2)) return rc;
+  p.num_n_tiles = 1;
+  // epilogue: 64-column box j = row parity ph = j of the parity-split output view (2cb, wb/2, 2, hb/2, b)
+  uint32_t sub[3];
+  DM_REQUIRE(epi_common(p, out_big, false) && epi_sub_box(pt.bw, pt.bh, pt.bimg, sub),
+             "dm_conv_up_merged: output not expressible as box stores");
+  {
+    const uint64_t e = 2, c = g->cb, w = g->wb, h = g->hb;
+    uint64_t dims[5] = {2 * c, w / 2, 2, h / 2, (uint64_t)g->batch};
+    uint64_t str[4] = {2 * c * e, w * c * e, 2 * w * c * e, h * w * c * e};
+    uint32_t obox[5] = {(uint32_t)p.epi_cols, sub[0], 1, sub[1], sub[2]};
+    if (int rc = encode_map(&p.map_out, out_big, 5, dims, str, obox, p.epi_swz, false)) return rc;
+  }
+  p.epi_tma = 1; p.epi_reduce = 0; p.epi_merge = 1;
+  p.epi_bw = pt.bw; p.epi_bh = pt.bh; p.epi_row_step = 0;
+  return launch(p, dim3(pt.tiles, 1, 1), stream, 50.0 * g->batch * g->hs * g->ws * g->cs * g->cb);
 }
 
 extern "C" int dm_conv_wgrad(const dm_conv_geom* g, const void* small, const void* big, float* dw_packed,

@@ -62,7 +62,27 @@ def conv_down(g: ConvGeom, big, w_down, bias=None, out=None):
     return out
 
 
+def up_merged(g_cb, stride) -> bool:
+    """Layers whose transposed convolution runs in the phase-merged form (dm_conv_up_merged)."""
+    return stride == 2 and g_cb == 32 and os.environ.get("DM_UP_MERGE", "1") != "0"
+
+
+def pack_up_merged(w_up, cs, cb, out=None):
+    """w_up [25][cb][cs] -> w_upm [9][4*cb][cs] (see dm_pack_up_merged)."""
+    if out is None:
+        out = torch.empty((9, 4 * cb, cs), dtype=BF16, device=w_up.device)
+    _lib.check(_lib.load().dm_pack_up_merged(_p(w_up), cs, cb, _p(out), _stream()), "dm_pack_up_merged")
+    return out
+
+
 def conv_up(g: ConvGeom, small, w_up, bias=None, out=None, out_f32=False):
+    if w_up.shape[0] == 9:  # phase-merged pack
+        assert not out_f32
+        if out is None:
+            out = torch.empty((g.batch, g.hb, g.wb, g.cb), dtype=BF16, device=small.device)
+        _lib.check(_lib.load().dm_conv_up_merged(C.byref(g), _p(small), _p(w_up), _p(bias), _p(out), _stream()),
+                   "dm_conv_up_merged")
+        return out
     if out is None:
         out = torch.empty((g.batch, g.hb, g.wb, g.cb), dtype=F32 if out_f32 else BF16, device=small.device)
     _lib.check(_lib.load().dm_conv_up(C.byref(g), _p(small), _p(w_up), _p(bias), _p(out), int(out.dtype == F32),
@@ -131,8 +151,16 @@ def pack_conv_weights(w, cs, cb, want_down=True, want_up=True, want_col=False, o
         w_down = torch.empty((25, cs, cb), dtype=BF16, device=dev) if want_down else None
         w_up = torch.empty((25, cb_pad, cs), dtype=BF16, device=dev) if want_up else None
         w_col = torch.empty((cs, 128), dtype=BF16, device=dev) if want_col else None
-    _lib.check(_lib.load().dm_pack_conv_weights(_p(w), cs, cb, _p(w_down), _p(w_up), _p(w_col), _stream()),
+    merged = want_up and up_merged(cb, 2)
+    w_up_std = w_up
+    if merged:  # conv_up consumes the phase-merged pack; the standard one is only an intermediate
+        w_up_std = torch.empty((25, cb_pad, cs), dtype=BF16, device=dev)
+        if w_up is None or w_up.shape[0] != 9:
+            w_up = torch.empty((9, 4 * cb, cs), dtype=BF16, device=dev)
+    _lib.check(_lib.load().dm_pack_conv_weights(_p(w), cs, cb, _p(w_down), _p(w_up_std), _p(w_col), _stream()),
                "dm_pack_conv_weights")
+    if merged:
+        pack_up_merged(w_up_std, cs, cb, out=w_up)
     return w_down, w_up, w_col
 
 

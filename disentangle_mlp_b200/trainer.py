@@ -78,6 +78,7 @@ class FlatParams:
         # persistent bf16 operand packs of the conv / deconv weights ([cs][cb][5][5]), refreshed IN PLACE after every
         # update: no lazily rebuilt state, so a captured CUDA graph always reads current operands
         self.cache.static_packs = {}
+        self._up_std = {}
         self.cache.packed_grads = self.GP
         for n, p in named:
             if p.dim() == 4:
@@ -86,6 +87,9 @@ class FlatParams:
                     o, k = self.offsets[n], p.numel()
                     w_down = self.shadow[o:o + k].view(25, cs, cb)
                     w_up = torch.empty((25, cb, cs), dtype=BF16, device=dev)
+                    if ops.up_merged(cb, 2):  # conv_up reads the phase-merged pack [9][4cb][cs]; w_up is its source
+                        self._up_std[n[:-len(".weight")]] = w_up
+                        w_up = torch.empty((9, 4 * cb, cs), dtype=BF16, device=dev)
                     self.cache.static_packs[n[:-len(".weight")]] = (w_down, w_up, None)
                 else:
                     self.cache.static_packs[n[:-len(".weight")]] = ops.pack_conv_weights(p.detach(), cs, cb, True, True, cb * 25 <= 128)
@@ -132,7 +136,11 @@ class FlatParams:
         for name, packs in self.cache.static_packs.items():
             p = self.P[name + ".weight"]
             if name + ".weight" in self.packed:  # w_down is the shadow itself; w_up = per-tap transpose of it
-                ops.transpose(packs[0], 25, p.shape[0], p.shape[1], out=packs[1])
+                if name in self._up_std:
+                    ops.transpose(packs[0], 25, p.shape[0], p.shape[1], out=self._up_std[name])
+                    ops.pack_up_merged(self._up_std[name], p.shape[0], p.shape[1], out=packs[1])
+                else:
+                    ops.transpose(packs[0], 25, p.shape[0], p.shape[1], out=packs[1])
             else:
                 ops.pack_conv_weights(p.detach(), p.shape[0], p.shape[1], out=packs)
 

@@ -78,6 +78,13 @@ int dm_conv_down(const dm_conv_geom* g, const void* big, const void* w_down, con
 int dm_conv_up(const dm_conv_geom* g, const void* small, const void* w_up, const float* bias,
                void* out_big, int out_f32, void* stream);
 
+/* Phase-merged form of dm_conv_up for stride 2, cb == 32 (ConvTranspose2d(128, 32), model.py:500 / the input
+ * gradient of Conv2d(32, 128), model.py:391): w_upm = dm_pack_up_merged(w_up) is [9][4*cb][cs]; one GEMM with N = 128
+ * computes the four sub-pixel phases from 9 shared input taps.  Output bf16 NHWC like dm_conv_up. */
+int dm_pack_up_merged(const void* w_up, int cs, int cb, void* w_upm, void* stream);
+int dm_conv_up_merged(const dm_conv_geom* g, const void* small, const void* w_upm, const float* bias, void* out_big,
+                      void* stream);
+
 /* Weight gradient of nn.Conv2d (small = grad_output, big = input) and of nn.ConvTranspose2d (small = input,
  * big = grad_output), fp32, accumulated atomically:
  *   direct_layout = 1: dw[cs][cb][kh][kw]          += sum_{b,h,w} small[b,h,w,cs] * big[b, s*h+kh-2, s*w+kw-2, cb]

@@ -100,7 +100,8 @@ def test_layout_kernels(ops):
     assert rel(dy, ref) < 1e-6 and rel(bg, ref.sum((0, 2, 3))) < 1e-4
 
 
-def test_pack_conv_weights(ops):
+def test_pack_conv_weights(ops, monkeypatch):
+    monkeypatch.setenv("DM_UP_MERGE", "0")  # the plain [25][cb][cs] transposed-conv pack (merged form: next test)
     w = torch.randn(64, 3, 5, 5, device="cuda")
     wd, wu, wc = ops.pack_conv_weights(w, 64, 3, True, True, True)
     wb = w.bfloat16()
@@ -112,6 +113,24 @@ def test_pack_conv_weights(ops):
     wd2, wu2, _ = ops.pack_conv_weights(w2, 128, 32)
     assert torch.equal(wu2, w2.bfloat16().reshape(128, 32, 25).permute(2, 1, 0).contiguous())
     assert torch.equal(wc[:, :75], wb.reshape(64, 75)) and float(wc[:, 75:].float().abs().max()) == 0.0
+
+
+def test_pack_up_merged(ops):
+    """cb == 32: conv_up consumes the phase-merged pack [9][4*cb][cs] (column = (ph*2+pw)*cb + c, tap = (dh, dw))."""
+    cs, cb = 128, 32
+    w = torch.randn(cs, cb, 5, 5, device="cuda")
+    _, wum, _ = ops.pack_conv_weights(w, cs, cb)
+    assert tuple(wum.shape) == (9, 4 * cb, cs)
+    ref = torch.zeros(9, 4, cb, cs, device="cuda", dtype=torch.bfloat16)
+    wb = w.bfloat16()
+    for t in range(9):
+        dh, dw = 1 - t // 3, 1 - t % 3
+        for ph in range(2):
+            for pw in range(2):
+                kh, kw = ph + 2 - 2 * dh, pw + 2 - 2 * dw
+                if 0 <= kh < 5 and 0 <= kw < 5:
+                    ref[t, ph * 2 + pw] = wb[:, :, kh, kw].t()
+    assert torch.equal(wum, ref.view(9, 4 * cb, cs))
 
 
 def test_bias_act_and_backward(ops):

@@ -34,6 +34,13 @@ def test_cluster_modes(name, env, monkeypatch):
     assert rel < (4e-3 if bf16_out else 1e-4), (name, env, rel)
 
 
+def test_conv_up_c32_unmerged(monkeypatch):
+    """The N = 32 four-phase form of the 128 -> 32 transposed convolution (default: phase-merged, N = 128)."""
+    monkeypatch.setenv("DM_UP_MERGE", "0")
+    rel, _ = probe_gemm.CASES["up_s2_c32"]()
+    assert rel < 4e-3, rel
+
+
 def test_full_size_layers_linearity_and_batch_independence():
     """Full BASELINE sizes (batch 128): conv(x1 + x2) == conv(x1) + conv(x2) on bf16-exact inputs, and the
     result for image i does not depend on the other images in the batch."""
