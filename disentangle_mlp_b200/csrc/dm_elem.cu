@@ -110,7 +110,7 @@ __device__ __forceinline__ void rows_reduce(long long rows, int c, long long row
   const long long r0 = blockIdx.y * rows_per_block;
   const long long r1 = min(rows, r0 + rows_per_block);
   if (live) {
-#pragma unroll 2
+#pragma unroll 4
     for (long long r = r0 + threadIdx.y; r < r1; r += ty) body(r, cv * 8, acc);
   }
   float* mine = red + (threadIdx.y * tx + threadIdx.x) * (8 * NACC);
@@ -224,6 +224,7 @@ __global__ void __launch_bounds__(256) bn_apply_act_kernel(const T* __restrict__
   load8(scale_shift + c + cv * 8, sh);
   const long long r0 = blockIdx.y * rows_per_block;
   const long long r1 = min(rows, r0 + rows_per_block);
+#pragma unroll 4
   for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
     float f[8];
     load8(y + r * c + cv * 8, f);
@@ -288,6 +289,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
   }
   const long long r0 = blockIdx.y * rows_per_block;
   const long long r1 = min(rows, r0 + rows_per_block);
+#pragma unroll 4
   for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
     float f[8], g[8];
     load8(y + r * c + cv * 8, f);
@@ -443,6 +445,7 @@ __global__ void __launch_bounds__(256) bn_fwd_fused_kernel(const T* __restrict__
   }
   const long long r0 = blockIdx.y * rows_per_block;
   const long long r1 = min(rows, r0 + rows_per_block);
+#pragma unroll 4
   for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
     float f[8];
     load8(y + r * c + cv * 8, f);
@@ -502,6 +505,7 @@ __global__ void __launch_bounds__(256) bn_bwd_fused_kernel(const __nv_bfloat16* 
   }
   const long long r0 = blockIdx.y * rows_per_block;
   const long long r1 = min(rows, r0 + rows_per_block);
+#pragma unroll 4
   for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
     float f[8], g[8];
     load8(y + r * c + cv * 8, f);
@@ -540,6 +544,7 @@ __global__ void __launch_bounds__(256) bias_act_kernel(const float* __restrict__
   if (bias) load8(bias + cv * 8, b);
   const long long r0 = blockIdx.y * rows_per_block;
   const long long r1 = min(rows, r0 + rows_per_block);
+#pragma unroll 4
   for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
     float f[8];
     load8(acc + r * c + cv * 8, f);

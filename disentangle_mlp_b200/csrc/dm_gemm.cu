@@ -1478,7 +1478,22 @@ extern "C" int dm_conv_wgrad(const dm_conv_geom* g, const void* small, const voi
   if (!direct) epi_wgrad_packed(p, dw_packed, g->cs, g->cb);
   const int base_ctas = m_tiles * p.num_n_tiles * units;
   int splits = env_int("DM_WGRAD_SPLITS", 0);
-  if (splits <= 0) splits = std::max(1, std::min(p.num_kb, (env_int("DM_WGRAD_CTAS", 296) + base_ctas - 1) / base_ctas));
+  if (splits <= 0) {
+    // split-K so that the persistent grid runs in WHOLE waves: cost(s) = waves(s) x (k-blocks per item + a fixed
+    // per-item epilogue/reduction cost, in k-block units); 300 items on 296 slots would take two rounds
+    const int acc_cols = (p.bn + 31) / 32 * 32;
+    const int stage_b = 2 * kAtomBytes + (p.bn >> 6) * kAtomBytes;
+    const bool two = pow2_cols(2 * acc_cols) <= 256 && stage_b <= 32768 && env_int("DM_ONE_CTA", 0) == 0;
+    const int slots = num_sms() * (two ? 2 : 1);
+    const int fixed = env_int("DM_WGRAD_FIXED_KB", 12);
+    long long best = -1;
+    for (int sp = 1; sp <= std::min(p.num_kb, 64); ++sp) {
+      const long long items = static_cast<long long>(base_ctas) * sp;
+      const long long waves = (items + slots - 1) / slots;
+      const long long cost = waves * ((p.num_kb + sp - 1) / sp + fixed);
+      if (best < 0 || cost < best) { best = cost; splits = sp; }
+    }
+  }
   splits = std::min(splits, p.num_kb);
   p.num_splits = splits;
   const int cluster = 1;

@@ -127,9 +127,13 @@ class FlatParams:
         o = self.offsets[name]
         reducer.allreduce_async(self.grad, o, o + self.P[name].numel())
 
-    def reduce_rest_and_wait(self, reducer):
+    def reduce_rest(self, reducer):
+        """Enqueue the all-reduce of everything not reduced early; the caller joins with reducer.wait()."""
         for lo, hi in self._late_ranges:
             reducer.allreduce_async(self.grad, lo, hi)
+
+    def reduce_rest_and_wait(self, reducer):
+        self.reduce_rest(reducer)
         reducer.wait()
 
     def refresh_packs(self):
@@ -491,18 +495,21 @@ class BetaVAEGANTrainer(_Base):
         engine.discriminator_backward(S12, dprob, None, fd.P, fd.G, fd.cache, False, True, overwrite_big=True,
                                       grad_ready=self._early(fd))
         del S12
-        fd.reduce_rest_and_wait(self.dist)
-        fd.adam()
+        fd.reduce_rest(self.dist)  # data parallel: D's gradient all-reduce runs on the NCCL stream ...
 
         # ================= "decoder" phase (:127-164): gradient of
         #   BCE(D(fake), real) + BCE(D(recon), real) + 0.5*||Dis_l(recon) - Dis_l(x)||^2 + ||recon - x||^2
         # w.r.t. ALL encoder and decoder parameters, D frozen at its updated value
+        # ... while the encoder / decoder forward of this phase, which does not read D, is computed; the D update
+        # (:123) lands before D is evaluated again, as in the reference
         feg.zero_grad()
         mu, logvar, Se = engine.encoder_forward(data, feg.P, feg.buffers, feg.cache, True, col=col_e)
         if eps_dec is None:
             eps_dec = torch.randn_like(mu)
         _, z16 = ops.reparam_forward(mu, logvar, eps_dec)
         recon, Sg2 = engine.decoder_forward(z16, feg.P, feg.buffers, feg.cache, True)
+        self.dist.wait()
+        fd.adam()
         # D(data) | D(fake) | D(recon) in one stacked pass (BatchNorm per pass, in the reference's order :129,147,150)
         prob3, feat3, S345 = engine.discriminator_forward(torch.cat([data, fake, recon]), fd.P, fd.buffers, fd.cache,
                                                           True, groups=3)
