@@ -47,9 +47,9 @@ _SIGS = {
                        c_float, c_void_p, c_void_p, c_void_p],
     "dm_bn_apply_act": [c_void_p, c_int, c_ll, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p],
     "dm_bn_forward": [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float,
-                      c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+                      c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "dm_bn_backward": [c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_int, c_float, c_void_p,
-                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+                       c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "dm_bias_act": [c_void_p, c_ll, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p],
     "dm_act_backward": [c_void_p, c_void_p, c_ll, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p],
     "dm_colsum": [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p],

@@ -11,6 +11,7 @@
 #include <atomic>
 #include <mutex>
 #include <cstdint>
+#include <cstdlib>
 
 #include "../../include/dm_b200.h"
 #include "dm_common.h"
@@ -85,7 +86,8 @@ static RowLayout make_row_layout(long long rows, int c) {
   if (l.tx < 1) l.tx = 1;
   l.ty = 256 / l.tx;
   l.gx = (cv + l.tx - 1) / l.tx;
-  long long want = std::max<long long>(1, (148ll * 2) / l.gx);  // ~2 fat blocks per SM: few partial vectors
+  static const int per_sm = [] { const char* e = getenv("DM_BN_BLOCKS_PER_SM"); return e ? std::max(1, atoi(e)) : 2; }();
+  long long want = std::max<long long>(1, (148ll * per_sm) / l.gx);  // blocks per SM: bytes in flight vs partial vectors
   long long rpb = (rows + want - 1) / want;
   rpb = std::max<long long>(l.ty, (rpb + l.ty - 1) / l.ty * l.ty);
   l.rows_per_block = rpb;
@@ -162,6 +164,9 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ y, 
   // Shifted sums: sum (y - k) and sum (y - k)^2 with k = the channel's value in row 0.  E[(y-k)^2] - E[y-k]^2 does
   // not cancel catastrophically when |mean| >> std (a BatchNorm1d feature that is nearly constant over a batch of
   // 16), which the plain E[y^2] - E[y]^2 in fp32 does; torch uses a two-pass / Welford variance.
+  // blockIdx.z = group: `gridDim.z` independent batches stacked along rows, each with its own partials block
+  y += static_cast<long long>(blockIdx.z) * rows * c;
+  sums += static_cast<long long>(blockIdx.z) * (gridDim.y + 1) * 2 * c;
   const int cv = blockIdx.x * blockDim.x + threadIdx.x;
   float k[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (cv * 8 < c) load8(y + cv * 8, k);
@@ -187,29 +192,36 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
                                                             float* __restrict__ running_var,
                                                             long long* __restrict__ num_batches_tracked, float momentum,
                                                             float eps, float* __restrict__ scale_shift,
-                                                            float* __restrict__ mean_invstd) {
+                                                            float* __restrict__ mean_invstd, int groups) {
   const int ch = blockIdx.x * 32 + threadIdx.x;
-  float sum[2];
-  sum_partials_block<2>(partials, nparts - 1, 2ll * c, ch, ch < c, c, sum);  // row nparts-1 = the shift k
-  if (threadIdx.y != 0) return;
-  if (ch == 0 && num_batches_tracked) *num_batches_tracked += 1;
-  if (ch >= c) return;
-  const double n = static_cast<double>(rows);
-  const double dmean = sum[0] / n;  // mean of (y - k)
-  const double mean = static_cast<double>(partials[2ll * (nparts - 1) * c + ch]) + dmean;
-  double var = sum[1] / n - dmean * dmean;
-  if (var < 0.0) var = 0.0;
-  const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-  const float sc = gamma[ch] * invstd;
-  scale_shift[ch] = sc;
-  scale_shift[c + ch] = beta[ch] - static_cast<float>(mean) * sc;
-  mean_invstd[ch] = static_cast<float>(mean);
-  mean_invstd[c + ch] = invstd;
-  if (running_mean) {
-    const double unbiased = rows > 1 ? var * n / (n - 1.0) : var;
-    running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * static_cast<float>(mean);
-    running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * static_cast<float>(unbiased);
+  // groups are finalized in order by the same thread: the running statistics see pass 0, then pass 1, ... exactly as
+  // separate forward calls would update them
+  for (int g = 0; g < groups; ++g) {
+    const float* part = partials + static_cast<long long>(g) * nparts * 2 * c;
+    float sum[2];
+    sum_partials_block<2>(part, nparts - 1, 2ll * c, ch, ch < c, c, sum);  // row nparts-1 = the shift k
+    __syncthreads();  // sum_partials_block's shared buffer is reused by the next group
+    if (threadIdx.y != 0 || ch >= c) continue;
+    const double n = static_cast<double>(rows);
+    const double dmean = sum[0] / n;  // mean of (y - k)
+    const double mean = static_cast<double>(part[2ll * (nparts - 1) * c + ch]) + dmean;
+    double var = sum[1] / n - dmean * dmean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float sc = gamma[ch] * invstd;
+    float* ss = scale_shift + static_cast<long long>(g) * 2 * c;
+    float* mi = mean_invstd + static_cast<long long>(g) * 2 * c;
+    ss[ch] = sc;
+    ss[c + ch] = beta[ch] - static_cast<float>(mean) * sc;
+    mi[ch] = static_cast<float>(mean);
+    mi[c + ch] = invstd;
+    if (running_mean) {
+      const double unbiased = rows > 1 ? var * n / (n - 1.0) : var;
+      running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * static_cast<float>(mean);
+      running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * static_cast<float>(unbiased);
+    }
   }
+  if (threadIdx.y == 0 && ch == 0 && num_batches_tracked) *num_batches_tracked += groups;
 }
 
 template <typename T>
@@ -219,6 +231,9 @@ __global__ void __launch_bounds__(256) bn_apply_act_kernel(const T* __restrict__
                                                            float slope, __nv_bfloat16* __restrict__ out) {
   const int cv = blockIdx.x * blockDim.x + threadIdx.x;
   if (cv * 8 >= c) return;
+  y += static_cast<long long>(blockIdx.z) * rows * c;  // group (see bn_stats_kernel)
+  out += static_cast<long long>(blockIdx.z) * rows * c;
+  scale_shift += static_cast<long long>(blockIdx.z) * 2 * c;
   float sc[8], sh[8];
   load8(scale_shift + cv * 8, sc);
   load8(scale_shift + c + cv * 8, sh);
@@ -242,6 +257,14 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
                                                             const float* __restrict__ scale_shift,
                                                             const float* __restrict__ mean_invstd, int act,
                                                             float slope, float* __restrict__ sums) {
+  {
+    const long long z = blockIdx.z;  // group
+    dout += z * rows * c;
+    y += z * rows * c;
+    scale_shift += z * 2 * c;
+    mean_invstd += z * 2 * c;
+    sums += z * (gridDim.y + 1) * 2 * c;
+  }
   const int cv0 = blockIdx.x * blockDim.x + threadIdx.x;
   float sc[8], sh[8], mu[8], is[8];
   if (cv0 * 8 < c) {
@@ -274,6 +297,15 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
                                                            __nv_bfloat16* __restrict__ dy) {
   const int cv = blockIdx.x * blockDim.x + threadIdx.x;
   if (cv * 8 >= c) return;
+  {
+    const long long z = blockIdx.z;  // group
+    dout += z * rows * c;
+    y += z * rows * c;
+    dy += z * rows * c;
+    scale_shift += z * 2 * c;
+    mean_invstd += z * 2 * c;
+    sums += z * 2 * c;
+  }
   float sc[8], sh[8], mu[8], is[8], s0[8], s1[8];
   load8(scale_shift + cv * 8, sc);
   load8(scale_shift + c + cv * 8, sh);
@@ -308,15 +340,19 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
 // (accumulating, like autograd's AccumulateGrad)
 __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __restrict__ partials, int nparts, int c,
                                                                 float* __restrict__ sums, float* __restrict__ dgamma,
-                                                                float* __restrict__ dbeta) {
+                                                                float* __restrict__ dbeta, int groups) {
   const int ch = blockIdx.x * 32 + threadIdx.x;
-  float sum[2];
-  sum_partials_block<2>(partials, nparts, 2ll * c, ch, ch < c, c, sum);
-  if (threadIdx.y != 0 || ch >= c) return;
-  sums[ch] = sum[0];
-  sums[c + ch] = sum[1];
-  if (dgamma) dgamma[ch] += sum[1];
-  if (dbeta) dbeta[ch] += sum[0];
+  for (int g = 0; g < groups; ++g) {
+    float sum[2];
+    // the partials block of a group has nparts + 1 rows (the last one is unused here: see dm_bn_parts)
+    sum_partials_block<2>(partials + static_cast<long long>(g) * (nparts + 1) * 2 * c, nparts, 2ll * c, ch, ch < c, c, sum);
+    __syncthreads();
+    if (threadIdx.y != 0 || ch >= c) continue;
+    sums[static_cast<long long>(g) * 2 * c + ch] = sum[0];
+    sums[static_cast<long long>(g) * 2 * c + c + ch] = sum[1];
+    if (dgamma) dgamma[ch] += sum[1];
+    if (dbeta) dbeta[ch] += sum[0];
+  }
 }
 
 // ------------------------------------------------------------------------------------------ fused BatchNorm passes
@@ -1012,38 +1048,52 @@ typedef __nv_bfloat16 bf16;
 // row block plus one that carries the per-channel shift of the shifted-sum statistics
 extern "C" int dm_bn_parts(long long rows, int c) { return make_row_layout(rows, c).gy + 1; }
 
-extern "C" int dm_bn_stats(const void* y, int y_f32, long long rows, int c, float* partials, void* stream_) {
+static int bn_stats_g(const void* y, int y_f32, long long rows, int c, float* partials, int groups, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   DM_CHECK_C8(c, "dm_bn_stats");
   RowLayout l = make_row_layout(rows, c);
   const size_t sm = sizeof(float) * 256 * 16;
   if (y_f32)
-    bn_stats_kernel<float><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s>>>(static_cast<const float*>(y), rows, c, l.rows_per_block, partials);
+    bn_stats_kernel<float><<<dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), sm, s>>>(static_cast<const float*>(y), rows, c, l.rows_per_block, partials);
   else
-    bn_stats_kernel<bf16><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s>>>(static_cast<const bf16*>(y), rows, c, l.rows_per_block, partials);
+    bn_stats_kernel<bf16><<<dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), sm, s>>>(static_cast<const bf16*>(y), rows, c, l.rows_per_block, partials);
   DM_LAUNCHED("dm_bn_stats");
 }
+extern "C" int dm_bn_stats(const void* y, int y_f32, long long rows, int c, float* partials, void* stream_) {
+  return bn_stats_g(y, y_f32, rows, c, partials, 1, stream_);
+}
 
+static int bn_finalize_g(const float* partials, int nparts, long long rows, int c, const float* gamma,
+                         const float* beta, float* running_mean, float* running_var,
+                         long long* num_batches_tracked, float momentum, float eps, float* scale_shift,
+                         float* mean_invstd, int groups, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  bn_finalize_kernel<<<(c + 31) / 32, dim3(32, 32), 0, s>>>(partials, nparts, rows, c, gamma, beta, running_mean, running_var,
+                                                     num_batches_tracked, momentum, eps, scale_shift, mean_invstd, groups);
+  DM_LAUNCHED("dm_bn_finalize");
+}
 extern "C" int dm_bn_finalize(const float* partials, int nparts, long long rows, int c, const float* gamma,
                               const float* beta, float* running_mean, float* running_var,
                               long long* num_batches_tracked, float momentum, float eps, float* scale_shift,
                               float* mean_invstd, void* stream_) {
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-  bn_finalize_kernel<<<(c + 31) / 32, dim3(32, 32), 0, s>>>(partials, nparts, rows, c, gamma, beta, running_mean, running_var,
-                                                     num_batches_tracked, momentum, eps, scale_shift, mean_invstd);
-  DM_LAUNCHED("dm_bn_finalize");
+  return bn_finalize_g(partials, nparts, rows, c, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps,
+                       scale_shift, mean_invstd, 1, stream_);
 }
 
-extern "C" int dm_bn_apply_act(const void* y, int y_f32, long long rows, int c, const float* scale_shift, int act,
-                               float slope, void* out_bf16, void* stream_) {
+static int bn_apply_act_g(const void* y, int y_f32, long long rows, int c, const float* scale_shift, int act,
+                          float slope, void* out_bf16, int groups, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   DM_CHECK_C8(c, "dm_bn_apply_act");
   RowLayout l = make_row_layout(rows, c);
   if (y_f32)
-    bn_apply_act_kernel<float><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), 0, s>>>(static_cast<const float*>(y), rows, c, l.rows_per_block, scale_shift, act, slope, static_cast<bf16*>(out_bf16));
+    bn_apply_act_kernel<float><<<dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), 0, s>>>(static_cast<const float*>(y), rows, c, l.rows_per_block, scale_shift, act, slope, static_cast<bf16*>(out_bf16));
   else
-    bn_apply_act_kernel<bf16><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), 0, s>>>(static_cast<const bf16*>(y), rows, c, l.rows_per_block, scale_shift, act, slope, static_cast<bf16*>(out_bf16));
+    bn_apply_act_kernel<bf16><<<dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), 0, s>>>(static_cast<const bf16*>(y), rows, c, l.rows_per_block, scale_shift, act, slope, static_cast<bf16*>(out_bf16));
   DM_LAUNCHED("dm_bn_apply_act");
+}
+extern "C" int dm_bn_apply_act(const void* y, int y_f32, long long rows, int c, const float* scale_shift, int act,
+                               float slope, void* out_bf16, void* stream_) {
+  return bn_apply_act_g(y, y_f32, rows, c, scale_shift, act, slope, out_bf16, 1, stream_);
 }
 
 // ---- cooperative launches of the fused BatchNorm kernels
@@ -1114,15 +1164,16 @@ static bool fused_bn_enabled(bool forward = true) {
 extern "C" int dm_bn_forward(const void* y, int y_f32, long long rows, int c, const float* gamma, const float* beta,
                              float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
                              float eps, int act, float slope, float* partials, float* scale_shift, float* mean_invstd,
-                             void* out_bf16, void* stream_) {
+                             void* out_bf16, int groups, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   DM_CHECK_C8(c, "dm_bn_forward");
+  DM_REQUIRE(groups >= 1, "dm_bn_forward: groups must be >= 1");
   RowLayout l = make_row_layout(rows, c);
   const size_t sm = sizeof(float) * 256 * 16;
   static int cap_f32 = -1, cap_bf16 = -1;
   if (cap_f32 < 0) cap_f32 = max_coresident_blocks(bn_fwd_fused_kernel<float>, sm);
   if (cap_bf16 < 0) cap_bf16 = max_coresident_blocks(bn_fwd_fused_kernel<bf16>, sm);
-  unsigned int* slot = fused_bn_enabled() ? barrier_slot() : nullptr;
+  unsigned int* slot = (groups == 1 && fused_bn_enabled()) ? barrier_slot() : nullptr;
   const int cap = y_f32 ? cap_f32 : cap_bf16;
   if (slot && l.gx * l.gy <= cap) {
     cudaError_t e;
@@ -1138,18 +1189,20 @@ extern "C" int dm_bn_forward(const void* y, int y_f32, long long rows, int c, co
     DM_LAUNCHED("dm_bn_forward");
   }
   // three-kernel path (grid too large to be co-resident, or DM_BN_FUSED=0)
-  if (int rc = dm_bn_stats(y, y_f32, rows, c, partials, stream_)) return rc;
-  if (int rc = dm_bn_finalize(partials, l.gy + 1, rows, c, gamma, beta, running_mean, running_var, num_batches_tracked, momentum,
-                              eps, scale_shift, mean_invstd, stream_))
+  if (int rc = bn_stats_g(y, y_f32, rows, c, partials, groups, stream_)) return rc;
+  if (int rc = bn_finalize_g(partials, l.gy + 1, rows, c, gamma, beta, running_mean, running_var, num_batches_tracked, momentum,
+                             eps, scale_shift, mean_invstd, groups, stream_))
     return rc;
-  return dm_bn_apply_act(y, y_f32, rows, c, scale_shift, act, slope, out_bf16, stream_);
+  return bn_apply_act_g(y, y_f32, rows, c, scale_shift, act, slope, out_bf16, groups, stream_);
 }
 
 extern "C" int dm_bn_backward(const void* dout_bf16, const void* y, int y_f32, long long rows, int c,
                               const float* scale_shift, const float* mean_invstd, int act, float slope,
-                              float* partials, float* sums, void* dy_bf16, float* dgamma, float* dbeta, void* stream_) {
+                              float* partials, float* sums, void* dy_bf16, float* dgamma, float* dbeta, int groups,
+                              void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   DM_CHECK_C8(c, "dm_bn_backward");
+  DM_REQUIRE(groups >= 1, "dm_bn_backward: groups must be >= 1");
   RowLayout l = make_row_layout(rows, c);
   const size_t sm = sizeof(float) * 256 * 16;
   const bf16* d = static_cast<const bf16*>(dout_bf16);
@@ -1157,7 +1210,7 @@ extern "C" int dm_bn_backward(const void* dout_bf16, const void* y, int y_f32, l
     static int cap_f32 = -1, cap_bf16 = -1;
     if (cap_f32 < 0) cap_f32 = max_coresident_blocks(bn_bwd_fused_kernel<float>, sm);
     if (cap_bf16 < 0) cap_bf16 = max_coresident_blocks(bn_bwd_fused_kernel<bf16>, sm);
-    unsigned int* slot = fused_bn_enabled(false) ? barrier_slot() : nullptr;
+    unsigned int* slot = (groups == 1 && fused_bn_enabled(false)) ? barrier_slot() : nullptr;
     if (slot && l.gx * l.gy <= (y_f32 ? cap_f32 : cap_bf16)) {
       cudaError_t e;
       if (y_f32)
@@ -1173,14 +1226,14 @@ extern "C" int dm_bn_backward(const void* dout_bf16, const void* y, int y_f32, l
     }
   }
   if (y_f32)
-    bn_bwd_reduce_kernel<float><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s>>>(d, static_cast<const float*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, act, slope, partials);
+    bn_bwd_reduce_kernel<float><<<dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), sm, s>>>(d, static_cast<const float*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, act, slope, partials);
   else
-    bn_bwd_reduce_kernel<bf16><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s>>>(d, static_cast<const bf16*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, act, slope, partials);
-  bn_bwd_finalize_kernel<<<(c + 31) / 32, dim3(32, 32), 0, s>>>(partials, l.gy, c, sums, dgamma, dbeta);
+    bn_bwd_reduce_kernel<bf16><<<dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), sm, s>>>(d, static_cast<const bf16*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, act, slope, partials);
+  bn_bwd_finalize_kernel<<<(c + 31) / 32, dim3(32, 32), 0, s>>>(partials, l.gy, c, sums, dgamma, dbeta, groups);
   if (y_f32)
-    bn_bwd_apply_kernel<float><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), 0, s>>>(d, static_cast<const float*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, sums, act, slope, static_cast<bf16*>(dy_bf16));
+    bn_bwd_apply_kernel<float><<<dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), 0, s>>>(d, static_cast<const float*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, sums, act, slope, static_cast<bf16*>(dy_bf16));
   else
-    bn_bwd_apply_kernel<bf16><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), 0, s>>>(d, static_cast<const bf16*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, sums, act, slope, static_cast<bf16*>(dy_bf16));
+    bn_bwd_apply_kernel<bf16><<<dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), 0, s>>>(d, static_cast<const bf16*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, sums, act, slope, static_cast<bf16*>(dy_bf16));
   g_launch_count.fetch_add(3, std::memory_order_relaxed);
   return check_launch("dm_bn_backward");
 }

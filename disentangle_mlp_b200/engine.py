@@ -77,29 +77,46 @@ def bn_act_forward(y, rows, c, P, B, prefix, act, training=True, groups=1):
 
     groups > 1: `y` holds `groups` independent batches stacked along rows (several forward passes of the same
     network pushed through each GEMM together); statistics, normalisation and the running-stat updates are done
-    per group, in order -- exactly what separate forward calls would do.  Returns (out, [BNState per group])."""
+    per group, in order -- exactly what separate forward calls would do -- by ONE set of kernel launches
+    (blockIdx.z = group).  Returns (out, [BNState per group])."""
     gamma, beta = P[prefix + ".weight"], P[prefix + ".bias"]
     rm, rv, nbt = B[prefix + ".running_mean"], B[prefix + ".running_var"], B[prefix + ".num_batches_tracked"]
     rg = rows // groups
     y2 = y.view(rows, c)
     out = torch.empty(y.shape, dtype=BF16, device=y.device)
     o2 = out.view(rows, c)
+    if training:
+        _, ss, mi = ops.bn_forward(y2, rg, c, gamma.detach(), beta.detach(), rm, rv, nbt, act, LEAKY, BN_MOMENTUM, BN_EPS,
+                                   out=o2, groups=groups)
+        if groups == 1:
+            ss, mi = ss.unsqueeze(0), mi.unsqueeze(0)
+        return out, [BNState(y2[g * rg:(g + 1) * rg], rg, c, ss[g], mi[g], act) for g in range(groups)]
     states = []
-    for g in range(groups):
+    for g in range(groups):  # inference statistics (the reference scripts never call .eval(); kept for completeness)
         ys = y2[g * rg:(g + 1) * rg]
-        if training:
-            _, ss, mi = ops.bn_forward(ys, rg, c, gamma.detach(), beta.detach(), rm, rv, nbt, act, LEAKY, BN_MOMENTUM, BN_EPS,
-                                       out=o2[g * rg:(g + 1) * rg])
-            states.append(BNState(ys, rg, c, ss, mi, act))
-            continue
-        else:  # inference statistics (the reference scripts never call .eval(); kept for completeness)
-            invstd = torch.rsqrt(rv + BN_EPS)
-            sc = gamma.detach() * invstd
-            ss = torch.stack([sc, beta.detach() - rm * sc]).contiguous()
-            mi = torch.stack([rm, invstd]).contiguous()
+        invstd = torch.rsqrt(rv + BN_EPS)
+        sc = gamma.detach() * invstd
+        ss = torch.stack([sc, beta.detach() - rm * sc]).contiguous()
+        mi = torch.stack([rm, invstd]).contiguous()
         ops.bn_apply_act(ys, rg, c, ss, act, LEAKY, out=o2[g * rg:(g + 1) * rg])
         states.append(BNState(ys, rg, c, ss, mi, act))
     return out, states
+
+
+def _stacked(states):
+    """True if the per-group states are adjacent slices of one stacked forward (same rows, consecutive memory)."""
+    s0 = states[0]
+    ye = s0.y.element_size()
+    for i, st in enumerate(states):
+        if st.rows != s0.rows or st.c != s0.c or st.act != s0.act:
+            return False
+        if st.y.data_ptr() != s0.y.data_ptr() + i * s0.rows * s0.c * ye:
+            return False
+        if st.scale_shift.data_ptr() != s0.scale_shift.data_ptr() + i * 2 * s0.c * 4:
+            return False
+        if st.mean_invstd.data_ptr() != s0.mean_invstd.data_ptr() + i * 2 * s0.c * 4:
+            return False
+    return True
 
 
 def bn_act_backward(dout, states, G, prefix):
@@ -112,6 +129,11 @@ def bn_act_backward(dout, states, G, prefix):
     d2 = dout.view(rows, c)
     dy = torch.empty(dout.shape, dtype=BF16, device=dout.device)
     y2 = dy.view(rows, c)
+    if len(states) > 1 and _stacked(states):
+        st = states[0]
+        ops.bn_backward(d2, st.y, st.rows, st.c, st.scale_shift, st.mean_invstd, st.act, LEAKY, dg, db, out=y2,
+                        groups=len(states))
+        return dy
     r0 = 0
     for st in states:
         ops.bn_backward(d2[r0:r0 + st.rows], st.y, st.rows, st.c, st.scale_shift, st.mean_invstd, st.act, LEAKY, dg, db,

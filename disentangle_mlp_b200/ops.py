@@ -193,28 +193,34 @@ def bn_apply_act(y, rows, c, scale_shift, act, slope=0.2, out=None):
     return out
 
 
-def bn_forward(y, rows, c, gamma, beta, running_mean, running_var, nbt, act, slope=0.2, momentum=0.1, eps=1e-5, out=None):
-    """Training-mode BatchNorm + activation in one (cooperative) launch.  Returns (out, scale_shift, mean_invstd)."""
+def bn_forward(y, rows, c, gamma, beta, running_mean, running_var, nbt, act, slope=0.2, momentum=0.1, eps=1e-5, out=None,
+               groups=1):
+    """Training-mode BatchNorm + activation (dm_bn_forward).  `y` holds `groups` stacked batches of `rows` rows each.
+    Returns (out, scale_shift [groups,2,c], mean_invstd [groups,2,c])."""
     if out is None:
         out = torch.empty(y.shape, dtype=BF16, device=y.device)
-    partials = torch.empty((bn_parts(rows, c), 2, c), dtype=F32, device=y.device)
-    scale_shift = torch.empty((2, c), dtype=F32, device=y.device)
-    mean_invstd = torch.empty((2, c), dtype=F32, device=y.device)
+    partials = torch.empty((groups, bn_parts(rows, c), 2, c), dtype=F32, device=y.device)
+    scale_shift = torch.empty((groups, 2, c), dtype=F32, device=y.device)
+    mean_invstd = torch.empty((groups, 2, c), dtype=F32, device=y.device)
     _lib.check(_lib.load().dm_bn_forward(_p(y), int(y.dtype == F32), rows, c, _p(gamma), _p(beta), _p(running_mean),
                                          _p(running_var), _p(nbt), momentum, eps, act, slope, _p(partials),
-                                         _p(scale_shift), _p(mean_invstd), _p(out), _stream()), "dm_bn_forward")
+                                         _p(scale_shift), _p(mean_invstd), _p(out), groups, _stream()), "dm_bn_forward")
+    if groups == 1:
+        return out, scale_shift[0], mean_invstd[0]
     return out, scale_shift, mean_invstd
 
 
-def bn_backward(dout, y, rows, c, scale_shift, mean_invstd, act, slope=0.2, dgamma=None, dbeta=None, out=None):
+def bn_backward(dout, y, rows, c, scale_shift, mean_invstd, act, slope=0.2, dgamma=None, dbeta=None, out=None, groups=1):
+    """`rows` per group; with groups > 1 dout / y / out are the stacked tensors and scale_shift / mean_invstd are
+    [groups,2,c]."""
     assert dout.dtype == BF16
     dy = torch.empty(y.shape, dtype=BF16, device=y.device) if out is None else out
-    partials = torch.empty((bn_parts(rows, c), 2, c), dtype=F32, device=y.device)
-    sums = torch.empty((2, c), dtype=F32, device=y.device)
+    partials = torch.empty((groups, bn_parts(rows, c), 2, c), dtype=F32, device=y.device)
+    sums = torch.empty((groups, 2, c), dtype=F32, device=y.device)
     _lib.check(_lib.load().dm_bn_backward(_p(dout), _p(y), int(y.dtype == F32), rows, c, _p(scale_shift),
                                           _p(mean_invstd), act, slope, _p(partials), _p(sums), _p(dy), _p(dgamma),
-                                          _p(dbeta), _stream()), "dm_bn_backward")
-    return dy, sums
+                                          _p(dbeta), groups, _stream()), "dm_bn_backward")
+    return dy, (sums[0] if groups == 1 else sums)
 
 
 def bias_act(acc, rows, c, bias, act, slope=0.2, want_f32=True, want_bf16=True):

@@ -122,14 +122,18 @@ int dm_bn_apply_act(const void* y, int y_f32, long long rows, int c, const float
                     float slope, void* out_bf16, void* stream);
 /* dm_bn_forward = dm_bn_stats + dm_bn_finalize + dm_bn_apply_act in ONE cooperative launch (grid barrier between the
  * reduction and the normalisation; falls back to the three kernels when the grid cannot be co-resident).
- * dm_bn_backward likewise runs its reduction, finalize and apply steps as one cooperative launch when it can. */
+ * dm_bn_backward likewise runs its reduction, finalize and apply steps as one cooperative launch when it can.
+ * groups > 1: y / out (dout / dy) hold `groups` independent batches of `rows` rows stacked along rows (several forward
+ * passes of one network pushed through each GEMM together); statistics, normalisation and running-stat updates are per
+ * group, in order; partials is [groups][dm_bn_parts][2][c], scale_shift / mean_invstd / sums are [groups][2][c];
+ * dgamma / dbeta accumulate over all groups. */
 int dm_bn_forward(const void* y, int y_f32, long long rows, int c, const float* gamma, const float* beta,
                   float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
                   int act, float slope, float* partials, float* scale_shift, float* mean_invstd, void* out_bf16,
-                  void* stream);
+                  int groups, void* stream);
 int dm_bn_backward(const void* dout_bf16, const void* y, int y_f32, long long rows, int c,
                    const float* scale_shift, const float* mean_invstd, int act, float slope, float* partials,
-                   float* sums, void* dy_bf16, float* dgamma, float* dbeta, void* stream);
+                   float* sums, void* dy_bf16, float* dgamma, float* dbeta, int groups, void* stream);
 
 /* out = act(acc + bias) after a split-K Linear (model.py:402-404); fp32 and/or bf16 outputs (NULL = skip). */
 int dm_bias_act(const float* acc, long long rows, int c, const float* bias, int act, float slope,

@@ -77,6 +77,34 @@ def test_batchnorm_single_launch(ops, rows, c, dtype, act, fused, monkeypatch):
         assert rel(dg, gr.grad) < 2e-3 and rel(db, br.grad) < 2e-3
 
 
+def test_batchnorm_groups(ops):
+    """groups = 3 stacked passes through one set of launches == three separate BatchNorm calls in order (per-pass
+    statistics, running stats updated pass by pass); backward over the sub-range of passes 1..2."""
+    torch.manual_seed(2)
+    rows, c, G = 2048, 64, 3
+    y = (torch.randn(G * rows, c, device="cuda") * torch.tensor([1.0, 2.0, 0.5], device="cuda").repeat_interleave(rows)[:, None]
+         + 0.4).bfloat16()
+    gamma = torch.randn(c, device="cuda") * 0.1 + 1
+    beta = torch.randn(c, device="cuda") * 0.1
+    rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    nbt = torch.zeros((), dtype=torch.long, device="cuda")
+    out, ss, mi = ops.bn_forward(y, rows, c, gamma, beta, rm, rv, nbt, 2, 0.2, groups=G)
+    rm_ref, rv_ref = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    yr = y.float().clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    refs = [F.leaky_relu(F.batch_norm(yr[g * rows:(g + 1) * rows], rm_ref, rv_ref, gr, br, training=True, momentum=0.1,
+                                      eps=1e-5), 0.2) for g in range(G)]
+    ref = torch.cat(refs)
+    assert rel(out, ref) < 4e-3
+    assert rel(rm, rm_ref) < 1e-4 and rel(rv, rv_ref) < 1e-4 and int(nbt) == G
+    dout = torch.randn(2 * rows, c, device="cuda").bfloat16()
+    torch.cat(refs[1:]).backward(dout.float())
+    dg, db = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
+    dy, _ = ops.bn_backward(dout, y[rows:], rows, c, ss[1:], mi[1:], 2, 0.2, dg, db, groups=2)
+    assert rel(dy, yr.grad[rows:]) < 6e-3
+    assert rel(dg, gr.grad) < 2e-3 and rel(db, br.grad) < 2e-3
+
+
 @pytest.mark.parametrize("stride", [1, 2])
 def test_im2col3(ops, stride):
     x = torch.rand(3, 3, 64, 64, device="cuda") * 2 - 1

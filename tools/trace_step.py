@@ -51,6 +51,11 @@ def main():
     gaps_pos = [g for g in gaps if g > 0]
     print(f"{len(ks)} kernels over {nsteps} steps; span {span / nsteps / 1e3:.3f} ms/step, busy {busy / nsteps / 1e3:.3f} ms/step, "
           f"gaps {sum(gaps_pos) / nsteps / 1e3:.3f} ms/step (median gap {np.median(gaps):.2f} us)")
+    show = os.environ.get("TRACE_SHOW")  # substring: list that kernel's individual launches (one step) in order
+    if show:
+        per = [(e - s_) for s_, e, n in ks if show in n]
+        per = per[: len(per) // nsteps]
+        print(f"{show}: " + " ".join(f"{d:.1f}" for d in per))
     for n, (c, t) in sorted(tot.items(), key=lambda kv: -kv[1][1])[:40]:
         print(f"{t / nsteps / 1e3:8.3f} ms/step  x{c / nsteps:6.1f}  avg {t / c:7.1f} us  {n}")
 
