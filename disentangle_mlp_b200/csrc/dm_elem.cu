@@ -980,7 +980,18 @@ __global__ void __launch_bounds__(256) bce_const_kernel(const float* __restrict_
 // optionally refreshing the bf16 shadow copy the GEMMs read.  28 B/param (+2 B shadow).
 __global__ void adam_count_kernel(int* step) { *step += 1; }
 
-__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+__device__ __forceinline__ float4 load_grad4(const float* g, long long i) { return reinterpret_cast<const float4*>(g)[i]; }
+__device__ __forceinline__ float4 load_grad4(const __nv_bfloat16* g, long long i) {
+  const uint2 u = reinterpret_cast<const uint2*>(g)[i];
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float load_grad1(const float* g, long long i) { return g[i]; }
+__device__ __forceinline__ float load_grad1(const __nv_bfloat16* g, long long i) { return __bfloat162float(g[i]); }
+
+template <typename GT>
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const GT* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, long long n,
                                                    float step_size, float beta1, float beta2, float omb1, float omb2,
                                                    float eps, float bc2_sqrt, float grad_scale, __nv_bfloat16* __restrict__ shadow,
@@ -1001,7 +1012,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nv;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
-    float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 gg = load_grad4(g, i);
     float4 mm = reinterpret_cast<float4*>(m)[i];
     float4 vv = reinterpret_cast<float4*>(v)[i];
     float* pf = &pp.x; float* gf = &gg.x; float* mf = &mm.x; float* vf = &vv.x;
@@ -1024,7 +1035,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   // tail (n not a multiple of 4)
   const long long t = nv * 4 + threadIdx.x;
   if (blockIdx.x == 0 && t < n) {
-    const float gr = g[t] * grad_scale;
+    const float gr = load_grad1(g, t) * grad_scale;
     m[t] = beta1 * m[t] + omb1 * gr;
     v[t] = beta2 * v[t] + omb2 * gr * gr;
     p[t] -= step_size * (m[t] / (sqrtf(v[t]) / bc2_sqrt + eps));
@@ -1387,25 +1398,40 @@ extern "C" int dm_bce_const(const float* p, int n, float n_total, float target, 
   DM_LAUNCHED("dm_bce_const");
 }
 
-extern "C" int dm_adam_step(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1,
-                            double beta2, double eps, int step, int* step_dev, float grad_scale, void* shadow_bf16,
-                            void* stream_) {
+extern "C" int dm_adam_step_ex(float* p, const void* g, int g_bf16, float* m, float* v, long long n, double lr,
+                               double beta1, double beta2, double eps, int step, int* step_dev, int count_step,
+                               float grad_scale, void* shadow_bf16, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   DM_REQUIRE(step >= 1 || step_dev != nullptr, "dm_adam_step: step must be >= 1 (or a device counter given)");
   // scalar arithmetic in double, then rounded to float once -- as torch.optim.Adam does with Python floats
   float step_size = 0.f, bc2s = 1.f;
   if (step_dev) {
-    adam_count_kernel<<<1, 1, 0, s>>>(step_dev);  // *step_dev += 1, then the update reads it
-    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    if (count_step) {  // *step_dev += 1, then the update reads it; later segments of the same step reuse the value
+      adam_count_kernel<<<1, 1, 0, s>>>(step_dev);
+      g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    }
   } else {
     const double bc1 = 1.0 - pow(beta1, step);
     const double bc2 = 1.0 - pow(beta2, step);
     step_size = static_cast<float>(lr / bc1);
     bc2s = static_cast<float>(sqrt(bc2));
   }
-  adam_kernel<<<grid_for(n / 4 + 1, 256, 148 * 8), 256, 0, s>>>(
-      p, g, m, v, n, step_size, static_cast<float>(beta1), static_cast<float>(beta2),
-      static_cast<float>(1.0 - beta1), static_cast<float>(1.0 - beta2), static_cast<float>(eps), bc2s, grad_scale,
-      static_cast<bf16*>(shadow_bf16), step_dev, lr, beta1, beta2);
+  const int grid = grid_for(n / 4 + 1, 256, 148 * 8);
+  if (g_bf16)
+    adam_kernel<bf16><<<grid, 256, 0, s>>>(p, static_cast<const bf16*>(g), m, v, n, step_size, static_cast<float>(beta1),
+                                           static_cast<float>(beta2), static_cast<float>(1.0 - beta1),
+                                           static_cast<float>(1.0 - beta2), static_cast<float>(eps), bc2s, grad_scale,
+                                           static_cast<bf16*>(shadow_bf16), step_dev, lr, beta1, beta2);
+  else
+    adam_kernel<float><<<grid, 256, 0, s>>>(p, static_cast<const float*>(g), m, v, n, step_size, static_cast<float>(beta1),
+                                            static_cast<float>(beta2), static_cast<float>(1.0 - beta1),
+                                            static_cast<float>(1.0 - beta2), static_cast<float>(eps), bc2s, grad_scale,
+                                            static_cast<bf16*>(shadow_bf16), step_dev, lr, beta1, beta2);
   DM_LAUNCHED("dm_adam_step");
+}
+
+extern "C" int dm_adam_step(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1,
+                            double beta2, double eps, int step, int* step_dev, float grad_scale, void* shadow_bf16,
+                            void* stream_) {
+  return dm_adam_step_ex(p, g, 0, m, v, n, lr, beta1, beta2, eps, step, step_dev, 1, grad_scale, shadow_bf16, stream_);
 }

@@ -534,9 +534,18 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
             else bulk_wait_group_read<0>();
           }
           __syncwarp();
-          const uint32_t stg = stg0 + static_cast<uint32_t>(ebuf) * 16384u + static_cast<uint32_t>(lane) * 4u;
+          if (p.out_f32) {
+            const uint32_t stg = stg0 + static_cast<uint32_t>(ebuf) * 16384u + static_cast<uint32_t>(lane) * 4u;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) st_shared_b32(stg + i * 128, v[i]);
+            for (int i = 0; i < 32; ++i) st_shared_b32(stg + i * 128, v[i]);
+          } else {  // bf16 output: staging rows of 32 m x 2 bytes
+            const uint32_t stg = stg0 + static_cast<uint32_t>(ebuf) * 16384u + static_cast<uint32_t>(lane) * 2u;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const __nv_bfloat16 h = __float2bfloat16_rn(__uint_as_float(v[i]));
+              asm volatile("st.shared.b16 [%0], %1;" ::"r"(stg + i * 64), "h"(*reinterpret_cast<const uint16_t*>(&h)) : "memory");
+            }
+          }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
@@ -1032,13 +1041,15 @@ static bool epi_wgrad_packed(GemmParams& p, float* dw, int cs, int cb) {
 }
 
 // dense out[n][m] fp32 with m contiguous (Linear weight gradient: rows of the accumulator are in-features)
-static bool epi_transposed_matrix(GemmParams& p, float* out, long long m, long long n, long long ld, bool reduce) {
-  if (env_int("DM_EPI_TMA", 1) == 0) return false;
-  if ((reinterpret_cast<uintptr_t>(out) & 15) != 0 || (ld * 4) % 16 != 0 || p.bn % 32 != 0 || n % 32 != 0) return false;
+static bool epi_transposed_matrix(GemmParams& p, void* out, bool f32, long long m, long long n, long long ld, bool reduce) {
+  if (env_int("DM_EPI_TMA", 1) == 0 && f32) return false;
+  const uint64_t es = f32 ? 4 : 2;
+  if ((reinterpret_cast<uintptr_t>(out) & 15) != 0 || (ld * es) % 16 != 0 || p.bn % 32 != 0 || n % 32 != 0) return false;
+  if (!f32 && reduce) return false;
   uint64_t dims[3] = {(uint64_t)m, (uint64_t)n, 1};
-  uint64_t str[2] = {(uint64_t)ld * 4, (uint64_t)ld * 4 * n};
+  uint64_t str[2] = {(uint64_t)ld * es, (uint64_t)ld * es * n};
   uint32_t box[3] = {32, 32, 1};
-  if (encode_map(&p.map_out, out, 3, dims, str, box, 0, true) != 0) return false;
+  if (encode_map(&p.map_out, out, 3, dims, str, box, 0, f32) != 0) return false;
   p.epi_tma = 2; p.epi_reduce = reduce ? 1 : 0;
   return true;
 }
@@ -1181,7 +1192,8 @@ extern "C" int dm_gemm_bf16(const dm_gemm_desc* g, void* stream_) {
     DM_REQUIRE(splits <= p.cpt, "dm_gemm_bf16: splits %d > k-blocks %d", splits, p.cpt);
     grid = dim3((g->m + 127) / 128, p.num_n_tiles, splits);
   } else if (g->layout == DM_GEMM_TN) {
-    DM_REQUIRE(g->d_f32, "dm_gemm_bf16: TN (weight-gradient) output is fp32");
+    DM_REQUIRE(g->d_f32 || (g->ldd_m == 1 && !g->accumulate),
+               "dm_gemm_bf16: TN (weight-gradient) output is fp32, or bf16 with unit row stride and no accumulation");
     DM_REQUIRE(g->bias == nullptr, "dm_gemm_bf16: TN has no bias");
     p.mode = MODE_WGRAD;
     p.a_mn = 1; p.b_mn = 1; p.kc = 64;
@@ -1201,7 +1213,8 @@ extern "C" int dm_gemm_bf16(const dm_gemm_desc* g, void* stream_) {
     if (g->ldd_n == 1)
       epi_rows_matrix(p, g->d, true, m_store, n_store, g->ldd_m, g->accumulate != 0, 128);
     else if (g->ldd_m == 1)
-      epi_transposed_matrix(p, static_cast<float*>(g->d), m_store, n_store, g->ldd_n, g->accumulate != 0);
+      epi_transposed_matrix(p, g->d, g->d_f32 != 0, m_store, n_store, g->ldd_n, g->accumulate != 0);
+    DM_REQUIRE(g->d_f32 || p.epi_tma == 2, "dm_gemm_bf16: bf16 TN output needs the bulk-store epilogue (alignment)");
     if (n_store > 32767) p.taps[0].nvalid = 32767;  // columns are bounded by n_tiles*bn anyway
     DM_REQUIRE(g->n <= 32767 || g->n % p.bn == 0, "dm_gemm_bf16: TN n too large for masked store");
     DM_REQUIRE(splits <= p.num_kb, "dm_gemm_bf16: splits %d > k-blocks %d", splits, p.num_kb);

@@ -171,6 +171,7 @@ def linear_dgrad(dy_bf16, w_bf16, batch, n_out, k_in, out_dtype=BF16, out=None):
 def linear_wgrad(dy_bf16, x_bf16, batch, n_out, k_in, dw, overwrite=False):
     """dw[n_out, k_in] (+)= dy^T @ x.  Computed as D[m = in-feature, n = out-feature] so that a warp's 32 rows are
     contiguous floats of dw (coalesced); `overwrite` stores instead of accumulating (dw need not be zeroed)."""
+    assert dw.dtype == F32 or overwrite, "a bf16 weight-gradient buffer is written once per phase (overwrite)"
     ops.gemm(GEMM_TN, x_bf16, dy_bf16, k_in, n_out, batch, out=dw, accumulate=not overwrite, ldd_m=1, ldd_n=k_in)
 
 

@@ -335,7 +335,10 @@ def bce_const(p, target, loss, w=1.0, n_total=None, dprob=None, accumulate=False
                "dm_bce_const")
 
 
-def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0, shadow=None, step_dev=None):
-    """step_dev: int32 CUDA tensor holding the step count; incremented on the device and used instead of `step`."""
-    _lib.check(_lib.load().dm_adam_step(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, step,
-                                        _p(step_dev), grad_scale, _p(shadow), _stream()), "dm_adam_step")
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0, shadow=None, step_dev=None, count_step=True):
+    """step_dev: int32 CUDA tensor holding the step count; incremented on the device (unless count_step is False: a
+    later segment of the same optimizer step) and used instead of `step`.  g: fp32 or bf16."""
+    assert g.dtype in (F32, BF16) and g.numel() == p.numel()
+    _lib.check(_lib.load().dm_adam_step_ex(_p(p), _p(g), int(g.dtype == BF16), _p(m), _p(v), p.numel(), lr, beta1, beta2,
+                                           eps, step, _p(step_dev), int(count_step), grad_scale, _p(shadow), _stream()),
+               "dm_adam_step")

@@ -191,6 +191,12 @@ int dm_bce_const(const float* p, int n, float n_total, float target, const float
 int dm_adam_step(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1,
                  double beta2, double eps, int step, int* step_dev, float grad_scale, void* shadow_bf16,
                  void* stream);
+/* Same on one SEGMENT of a flat buffer: g may be bf16 (g_bf16 != 0: the three 16384x2048 Linear weight gradients are
+ * stored, all-reduced and read in bf16); count_step == 0 reuses the device step counter that an earlier segment of
+ * the same optimizer step has already incremented. */
+int dm_adam_step_ex(float* p, const void* g, int g_bf16, float* m, float* v, long long n, double lr, double beta1,
+                    double beta2, double eps, int step, int* step_dev, int count_step, float grad_scale,
+                    void* shadow_bf16, void* stream);
 
 /* Per-launch CUDA-event timing of the GEMM-class kernel (bench.py roofline). dm_profile_read synchronises the
  * device and returns the summed launch durations, algorithmic FLOPs (2*M*N*K; convolutions: 2*25*b*hs*ws*cs*cb)

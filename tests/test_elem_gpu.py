@@ -243,3 +243,28 @@ def test_adam_matches_torch(ops):
     assert torch.equal(shadow, p.bfloat16())
     st = opt.state[ref]
     assert rel(m, st["exp_avg"]) < 1e-6 and rel(v, st["exp_avg_sq"]) < 1e-6
+
+
+def test_adam_segments_and_bf16_gradients(ops):
+    """dm_adam_step_ex: one optimizer step applied segment by segment (device step counter incremented once), with a
+    bf16 gradient on the middle segment -- equals torch.optim.Adam fed the same (bf16-rounded) gradient."""
+    torch.manual_seed(1)
+    n, a, b = 4096 + 40000 + 1003, 4096, 4096 + 40000
+    p = torch.randn(n, device="cuda")
+    ref = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-3)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    shadow = torch.empty(n, dtype=torch.bfloat16, device="cuda")
+    step_dev = torch.zeros((), dtype=torch.int32, device="cuda")
+    for _ in range(4):
+        g = torch.randn(n, device="cuda")
+        g16 = g[a:b].bfloat16()
+        gref = g.clone()
+        gref[a:b] = g16.float()
+        ref.grad = gref
+        opt.step()
+        for i, (lo, hi, gg) in enumerate(((0, a, g[0:a]), (a, b, g16), (b, n, g[b:n]))):
+            ops.adam_step(p[lo:hi], gg, m[lo:hi], v[lo:hi], 1e-3, 0.9, 0.999, 1e-8, 0, 1.0, shadow[lo:hi],
+                          step_dev=step_dev, count_step=(i == 0))
+    assert int(step_dev) == 4
+    assert rel(p, ref.detach()) < 1e-6 and torch.equal(shadow, p.bfloat16())

@@ -70,3 +70,19 @@ def test_full_size_layers_linearity_and_batch_independence():
     lhs, rhs = (y * s.double()).sum(), (x1.double() * up.double()).sum()
     # y carries one bf16 rounding (2^-9 relative per element); the sums cancel, so bound by the sum of magnitudes
     assert abs(float(lhs - rhs)) <= 2 ** -8 * float((y.abs() * s.abs().double()).sum())
+
+
+def test_tn_bf16_transposed_output():
+    """Linear weight gradient written as bf16 by the GEMM epilogue (D[n][m] = sum_k A[k][m] B[k][n], m contiguous)."""
+    import torch
+
+    from disentangle_mlp_b200 import ops
+
+    torch.manual_seed(0)
+    m, n, k = 1024, 256, 64
+    a = torch.randn(k, m, device="cuda").bfloat16()
+    b = torch.randn(k, n, device="cuda").bfloat16()
+    out = torch.zeros(n, m, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(ops.GEMM_TN, a, b, m, n, k, out=out, accumulate=False, ldd_m=1, ldd_n=m)
+    ref = b.float().t() @ a.float()
+    assert float((out.float() - ref).norm() / ref.norm()) < 4e-3
