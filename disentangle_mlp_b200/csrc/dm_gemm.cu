@@ -1282,7 +1282,7 @@ extern "C" int dm_conv_down(const dm_conv_geom* g, const void* big, const void* 
   p.w_lim = g->ws; p.n_lim = g->batch; p.n_valid = g->cs;
   uint32_t box[5] = {(uint32_t)p.kc, (uint32_t)pt.bw, 1, (uint32_t)pt.bh, (uint32_t)pt.bimg};
   if (int rc = encode_act_map(&p.map_a, big, g->batch, g->hb, g->wb, g->cb, g->stride, box, p.kc * 2)) return rc;
-  p.cg2 = (env_int("DM_CG2", 0) != 0 && pt.tiles >= 2 && p.bn >= 32) ? 1 : 0;
+  p.cg2 = (env_int("DM_CG2", 1) != 0 && pt.tiles >= 2 && p.bn >= 32) ? 1 : 0;
   const int cluster = p.cg2 ? 2 : 1;
   if (int rc = encode_w_map3(&p.map_b, w_down, 25, g->cs, g->cb, g->cb, p.kc, p.bn / cluster, p.kc * 2)) return rc;
   p.num_n_tiles = (g->cs + p.bn - 1) / p.bn;
@@ -1360,7 +1360,7 @@ extern "C" int dm_conv_up(const dm_conv_geom* g, const void* small, const void* 
   p.w_lim = g->ws; p.n_lim = g->batch; p.n_valid = g->cb;
   uint32_t box[5] = {(uint32_t)p.kc, (uint32_t)pt.bw, 1, (uint32_t)pt.bh, (uint32_t)pt.bimg};
   if (int rc = encode_act_map(&p.map_a, small, g->batch, g->hs, g->ws, g->cs, 1, box, p.kc * 2)) return rc;
-  p.cg2 = (!fold && env_int("DM_CG2", 0) != 0 && pt.tiles >= 2 && p.bn >= 32) ? 1 : 0;
+  p.cg2 = (!fold && env_int("DM_CG2", 1) != 0 && pt.tiles >= 2 && p.bn >= 32) ? 1 : 0;
   const int cluster = p.cg2 ? 2 : 1;
   if (int rc = encode_w_map3(&p.map_b, w_up, fold ? 5 : 25, cb_pad, g->cs, g->cs, p.kc, p.bn / cluster, p.kc * 2)) return rc;
   p.num_n_tiles = (cb_pad + p.bn - 1) / p.bn;
@@ -1405,7 +1405,9 @@ extern "C" int dm_conv_up_merged(const dm_conv_geom* g, const void* small, const
   p.w_lim = g->ws; p.n_lim = g->batch; p.n_valid = p.bn;
   uint32_t box[5] = {(uint32_t)p.kc, (uint32_t)pt.bw, 1, (uint32_t)pt.bh, (uint32_t)pt.bimg};
   if (int rc = encode_act_map(&p.map_a, small, g->batch, g->hs, g->ws, g->cs, 1, box, p.kc * 2)) return rc;
-  if (int rc = encode_w_map3(&p.map_b, w_upm, 9, p.bn, g->cs, g->cs, p.kc, p.bn, p.kc * 2)) return rc;
+  p.cg2 = (env_int("DM_CG2", 1) != 0 && pt.tiles >= 2) ? 1 : 0;
+  const int cluster = p.cg2 ? 2 : 1;
+  if (int rc = encode_w_map3(&p.map_b, w_upm, 9, p.bn, g->cs, g->cs, p.kc, p.bn / cluster, p.kc * 2)) return rc;
   p.num_n_tiles = 1;
   // epilogue: 64-column box j = row parity ph = j of the parity-split output view (2cb, wb/2, 2, hb/2, b)
   uint32_t sub[3];
@@ -1420,7 +1422,7 @@ extern "C" int dm_conv_up_merged(const dm_conv_geom* g, const void* small, const
   }
   p.epi_tma = 1; p.epi_reduce = 0; p.epi_merge = 1;
   p.epi_bw = pt.bw; p.epi_bh = pt.bh; p.epi_row_step = 0;
-  return launch(p, dim3(pt.tiles, 1, 1), stream, 50.0 * g->batch * g->hs * g->ws * g->cs * g->cb);
+  return launch(p, dim3(pt.tiles, 1, 1), stream, 50.0 * g->batch * g->hs * g->ws * g->cs * g->cb, 1 << 30, cluster);
 }
 
 extern "C" int dm_conv_wgrad(const dm_conv_geom* g, const void* small, const void* big, float* dw_packed,
