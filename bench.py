@@ -163,6 +163,16 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def profile_traffic(args):
+    """DRAM bytes (read + write) per launch of the GEMM-class kernel from the committed ncu capture of this workload
+    (profiles/r01_e_launches_vaegan_b64_final.txt: dram__bytes_read.sum + dram__bytes_write.sum over the 108 launches
+    of one step); None for configurations that were not captured."""
+    if args.workload == "betavaegan" and args.batch == 64:
+        return {"bytes_per_launch": 26.34e6, "launches": 108,
+                "source": "profiles/r01_e_launches_vaegan_b64_final.csv (ncu, one step, batch 64)"}
+    return None
+
+
 def workload_config(args, per_gpu_batch):
     names = {"betavaegan": f"VAE-GAN baseline (Larsen, Dis_l loss; experiments/new_betavaegan.py step, beta={args.beta:g})",
              "gan": "GAN (experiments/new_gan.py step)", "vae": "VAE (experiments/new_vae.py step)"}
@@ -318,10 +328,13 @@ def run_ours(args):
             "gpu_launches": int(launches), "cuda_graph": bool(graph_mode),
             "roofline": {"bound": "tensor", "kernel": "dm_tapgemm_kernel (all GEMM-class launches of the step)",
                          "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s",
-                         "frac": round(ach / peak, 4) if peak else None, "traffic": None,
+                         "frac": round(ach / peak, 4) if peak else None, "traffic": profile_traffic(args),
                          "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['src']})",
                          "launches_per_step": gemm_n / args.steps, "gemm_ms_per_step": round(gemm_ms / args.steps, 4),
-                         "gemm_share_of_step": round(gemm_ms / ms, 4),
+                         # both from the SAME eagerly launched pass (the graph replay has no per-kernel events);
+                         # the CUPTI timeline of the replay and the ncu launch list give 0.41-0.44 (profiles/)
+                         "gemm_share_of_step": round(gemm_ms / t_prof, 4),
+                         "timing": "CUDA events around every GEMM-class launch on the launching stream",
                          "step_frac_of_peak": round(ips / world * GFLOP_PER_IMG[args.workload] / 1e3 / peak, 4)},
             "cpu_baseline": cpu,
         }

@@ -51,6 +51,10 @@ def main():
     gaps_pos = [g for g in gaps if g > 0]
     print(f"{len(ks)} kernels over {nsteps} steps; span {span / nsteps / 1e3:.3f} ms/step, busy {busy / nsteps / 1e3:.3f} ms/step, "
           f"gaps {sum(gaps_pos) / nsteps / 1e3:.3f} ms/step (median gap {np.median(gaps):.2f} us)")
+    if os.environ.get("TRACE_GAPS"):
+        big = sorted(((ks[i + 1][0] - ks[i][1], i) for i in range(len(ks) - 1)), reverse=True)[:int(os.environ["TRACE_GAPS"])]
+        for g, i in big:
+            print(f"gap {g:8.1f} us after [{ks[i][2][:50]}] ({ks[i][1] - ks[i][0]:.1f} us) before [{ks[i + 1][2][:50]}]")
     show = os.environ.get("TRACE_SHOW")  # substring: list that kernel's individual launches (one step) in order
     if show:
         per = [(e - s_) for s_, e, n in ks if show in n]
