@@ -89,6 +89,10 @@ static RowLayout make_row_layout(long long rows, int c) {
   static const int per_sm = [] { const char* e = getenv("DM_BN_BLOCKS_PER_SM"); return e ? std::max(1, atoi(e)) : 2; }();
   long long want = std::max<long long>(1, (148ll * per_sm) / l.gx);  // blocks per SM: bytes in flight vs partial vectors
   long long rpb = (rows + want - 1) / want;
+  // DM_BN_MIN_SWEEPS > 1 gives small tensors fewer, fatter blocks (fewer partial vectors for the finalize kernels).
+  // Measured (batch 64): 1 is best -- the reduce / apply kernels lose more than the finalize kernels gain.
+  static const int mult = [] { const char* e = getenv("DM_BN_MIN_SWEEPS"); return e ? std::max(1, atoi(e)) : 1; }();
+  rpb = std::max<long long>(rpb, static_cast<long long>(mult) * l.ty);
   rpb = std::max<long long>(l.ty, (rpb + l.ty - 1) / l.ty * l.ty);
   l.rows_per_block = rpb;
   l.gy = static_cast<int>((rows + rpb - 1) / rpb);
