@@ -53,6 +53,7 @@ class FlatParams:
         self.v = torch.zeros(off, dtype=F32, device=dev)
         self.shadow = torch.zeros(off, dtype=BF16, device=dev)
         self.P, self.G, self.W16, self.GP = {}, {}, {}, {}
+        self._tail_done = None
         # 5x5 conv / deconv weights [cs][cb][5][5] with 32-aligned channel counts live in the flat buffers in the
         # TAP-MAJOR layout [5][5][cs][cb]: that is the layout of the GEMM operand (the bf16 shadow IS w_down) and of
         # the packed weight gradient the wgrad kernel reduces into (bulk tensor reductions need unit inner stride).
@@ -153,10 +154,25 @@ class FlatParams:
         o = self.offsets[name]
         reducer.allreduce_async(self.grad, o, o + self.P[name].numel())
 
+    def reduce_from(self, reducer, name):
+        """Data parallel: all-reduce the gradients of parameter `name` and everything after it in the flat buffer NOW
+        (they are final), on the side stream; reduce_rest() then skips that tail.  Used for the decoder parameters
+        (the tail of the VAE's parameter list), whose gradients are final before the encoder backward starts."""
+        if not reducer.on:
+            return
+        lo = self.offsets[name]
+        assert all(self.offsets[n] + self.P[n].numel() <= lo for n in self.names if n in EARLY_BUCKETS), \
+            "the separately reduced big gradients must lie before the early tail"
+        reducer.allreduce_async(self.grad, lo, self.total)
+        self._tail_done = lo
+
     def reduce_rest(self, reducer):
         """Enqueue the all-reduce of everything not reduced early; the caller joins with reducer.wait()."""
+        stop = self._tail_done if self._tail_done is not None else self.total
         for lo, hi in self._late_ranges:
-            reducer.allreduce_async(self.grad, lo, hi)
+            if lo < stop:
+                reducer.allreduce_async(self.grad, lo, min(hi, stop))
+        self._tail_done = None
 
     def reduce_rest_and_wait(self, reducer):
         self.reduce_rest(reducer)
@@ -418,6 +434,7 @@ class VAETrainer(_Base):
         dmu_kl, dlv_kl = torch.empty_like(mu), torch.empty_like(mu)
         ops.kl(mu, logvar, loss, self.beta, dmu_kl, dlv_kl)
         dz = engine.decoder_backward(Sg, drecon, fp.P, fp.G, fp.cache, True, True, overwrite_big=True)
+        fp.reduce_from(self.dist, "preprocess.0.weight")
         _, _, dmu, dlv = ops.reparam_backward(dz, logvar, eps, dmu_kl, dlv_kl)
         engine.encoder_backward(Se, dmu, dlv, fp.P, fp.G, fp.cache, True, overwrite_big=True,
                                 grad_ready=self._early(fp))
@@ -556,6 +573,7 @@ class BetaVAEGANTrainer(_Base):
         del Sg1
         ops.mse_sum(recon, data, loss_dec, 1.0, drecon, 1.0, accumulate=True)
         dz = engine.decoder_backward(Sg2, drecon, feg.P, feg.G, feg.cache, True, True)
+        feg.reduce_from(self.dist, "preprocess.0.weight")  # decoder gradients are final: reduce them under the encoder backward
         _, _, dmu, dlv = ops.reparam_backward(dz, logvar, eps_dec)
         engine.encoder_backward(Se, dmu, dlv, feg.P, feg.G, feg.cache, True, overwrite_big=True,
                                 grad_ready=self._early(feg))
@@ -575,6 +593,7 @@ class BetaVAEGANTrainer(_Base):
         dmu_kl, dlv_kl = torch.empty_like(mu), torch.empty_like(mu)
         ops.kl(mu, logvar, kld, self.beta, dmu_kl, dlv_kl)
         dz = engine.decoder_backward(Sg3, drecon, feg.P, feg.G, feg.cache, True, True, overwrite_big=True)
+        feg.reduce_from(self.dist, "preprocess.0.weight")
         _, _, dmu, dlv = ops.reparam_backward(dz, logvar, eps_enc, dmu_kl, dlv_kl)
         engine.encoder_backward(Se, dmu, dlv, feg.P, feg.G, feg.cache, True, overwrite_big=True,
                                 grad_ready=self._early(feg))
