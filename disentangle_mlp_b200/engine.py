@@ -11,6 +11,7 @@ Parameters are addressed by their reference state_dict names.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from types import SimpleNamespace
 
@@ -142,7 +143,10 @@ def bn_act_backward(dout, states, G, prefix):
     return dy
 
 
-def _splits_for(m_tiles, n_tiles, kblocks, target=296):
+def _splits_for(m_tiles, n_tiles, kblocks, target=None):
+    """Split-K factor of a skinny Linear GEMM: enough CTAs to keep the weight stream at HBM speed."""
+    if target is None:
+        target = int(os.environ.get("DM_LIN_CTAS", "296"))
     s = max(1, min(kblocks, target // max(1, m_tiles * n_tiles)))
     return s
 

@@ -343,6 +343,25 @@ class _Base:
         ops.bce_const(prob, target, loss, 1.0, n_total=b * self.dist.world, dprob=dprob, stat=stat)
         return dprob
 
+    def _fork_side(self, fn):
+        """Run fn() on a side stream ordered after the work queued so far; returns a token for _join_side().
+        (Inside graph capture this becomes a parallel branch of the graph.)  DM_SIDE_ADAM=0: run it inline."""
+        if os.environ.get("DM_SIDE_ADAM", "1") == "0":
+            fn()
+            return None
+        if getattr(self, "_side_stream", None) is None:
+            self._side_stream = torch.cuda.Stream()
+        cur = torch.cuda.current_stream()
+        self._side_stream.wait_stream(cur)
+        with torch.cuda.stream(self._side_stream):
+            fn()
+        return self._side_stream
+
+    @staticmethod
+    def _join_side(token):
+        if token is not None:
+            torch.cuda.current_stream().wait_stream(token)
+
     def _early(self, fp):
         """grad_ready hook: all-reduce a big gradient bucket as soon as the backward pass has finished writing it."""
         if not self.dist.on:
@@ -357,7 +376,7 @@ class _Base:
         dev = fps[0].flat.device
         self._gx = torch.zeros(batch, 3, 64, 64, device=dev)
         self._glabels = torch.zeros(2, device=dev)
-        self._glabels_host = torch.zeros(2).pin_memory()
+        self._glabels_ring = [(torch.zeros(2).pin_memory(), torch.cuda.Event()) for _ in range(16)]
         # random inputs of the step (noise / eps), drawn OUTSIDE the graph in the reference's order
         self._grands = [torch.zeros(batch, 128, device=dev) for _ in range(self.n_rands)]
         snaps = [fp.snapshot() for fp in fps]
@@ -388,8 +407,14 @@ class _Base:
     def _graph_step(self, data, real_label, fake_label):
         if real_label is None:
             real_label, fake_label = self.draw_labels()
-        self._glabels_host[0], self._glabels_host[1] = real_label, fake_label
-        self._glabels.copy_(self._glabels_host, non_blocking=True)
+        # the host may run several steps ahead of the GPU: each step's labels get their own pinned slot, reused only
+        # after the copy that read it has completed
+        k = self._glabel_slot = (getattr(self, "_glabel_slot", -1) + 1) % len(self._glabels_ring)
+        host, ev = self._glabels_ring[k]
+        ev.synchronize()
+        host[0], host[1] = real_label, fake_label
+        self._glabels.copy_(host, non_blocking=True)
+        ev.record()
         self._gx.copy_(data, non_blocking=True)
         for r in self._grands:
             r.normal_()
@@ -541,6 +566,9 @@ class BetaVAEGANTrainer(_Base):
                                       grad_ready=self._early(fd))
         del S12
         fd.reduce_rest(self.dist)  # data parallel: D's gradient all-reduce runs on the NCCL stream ...
+        # ... and D's Adam update (HBM-bound) runs on a side stream, both under the tensor-bound encoder / decoder
+        # forward below
+        fork = self._fork_side(lambda: (self.dist.wait(), fd.adam()))
 
         # ================= "decoder" phase (:127-164): gradient of
         #   BCE(D(fake), real) + BCE(D(recon), real) + 0.5*||Dis_l(recon) - Dis_l(x)||^2 + ||recon - x||^2
@@ -553,8 +581,7 @@ class BetaVAEGANTrainer(_Base):
             eps_dec = torch.randn_like(mu)
         _, z16 = ops.reparam_forward(mu, logvar, eps_dec)
         recon, Sg2 = engine.decoder_forward(z16, feg.P, feg.buffers, feg.cache, True)
-        self.dist.wait()
-        fd.adam()
+        self._join_side(fork)
         # D(data) | D(fake) | D(recon) in one stacked pass (BatchNorm per pass, in the reference's order :129,147,150)
         prob3, feat3, S345 = engine.discriminator_forward(torch.cat([data, fake, recon]), fd.P, fd.buffers, fd.cache,
                                                           True, groups=3)
