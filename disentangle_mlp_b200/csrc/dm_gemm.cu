@@ -797,8 +797,10 @@ static int g_last_smem = 0, g_last_stages = 0;
 struct ProfRec {
   cudaEvent_t e0, e1;
   double flops;
-  int gx, gy, gz, mode, bn, kc, stages, ctas, a_mn, b_mn;
+  int gx, gy, gz, mode, bn, kc, stages, ctas, a_mn, b_mn, kind;
 };
+// what the next launch computes (profile records only): 0 dense GEMM, 1 conv_down, 2 conv_up, 3 conv_wgrad
+static thread_local int t_kind = 0;
 static std::mutex g_prof_mu;
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
@@ -901,7 +903,7 @@ static int launch(GemmParams& p, dim3 grid, cudaStream_t stream, double flops, i
       }
       rec.flops = flops;
       rec.gx = grid.x; rec.gy = grid.y; rec.gz = grid.z; rec.mode = p.mode; rec.bn = p.bn; rec.kc = p.kc;
-      rec.stages = stages; rec.ctas = ctas; rec.a_mn = p.a_mn; rec.b_mn = p.b_mn;
+      rec.stages = stages; rec.ctas = ctas; rec.a_mn = p.a_mn; rec.b_mn = p.b_mn; rec.kind = t_kind;
     }
   }
   if (prof) cudaEventRecord(rec.e0, stream);
@@ -1122,12 +1124,12 @@ extern "C" int dm_profile_dump(const char* path) {
   FILE* f = fopen(path, "w");
   if (!f) return set_error(-1, "dm_profile_dump: cannot open %s", path);
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  fprintf(f, "idx,mode,a_mn,b_mn,tiles_m,tiles_n,tiles_z,bn,kc,stages,ctas,us,gflop\n");
+  fprintf(f, "idx,kind,mode,a_mn,b_mn,tiles_m,tiles_n,tiles_z,bn,kc,stages,ctas,us,gflop\n");
   int i = 0;
   for (auto& r : g_prof) {
     float t = 0.f;
     cudaEventElapsedTime(&t, r.e0, r.e1);
-    fprintf(f, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.3f,%.4f\n", i++, r.mode, r.a_mn, r.b_mn, r.gx, r.gy, r.gz, r.bn,
+    fprintf(f, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.3f,%.4f\n", i++, r.kind, r.mode, r.a_mn, r.b_mn, r.gx, r.gy, r.gz, r.bn,
             r.kc, r.stages, r.ctas, t * 1e3, r.flops * 1e-9);
     g_prof_pool.push_back(r);
   }
@@ -1147,6 +1149,7 @@ extern "C" int dm_debug_last_plan(int* grid_xyz, int* smem_bytes, int* stages) {
 extern "C" int dm_gemm_bf16(const dm_gemm_desc* g, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   DM_REQUIRE(g != nullptr, "dm_gemm_bf16: null descriptor");
+  t_kind = 0;
   DM_REQUIRE(g->m > 0 && g->n > 0 && g->k > 0, "dm_gemm_bf16: bad shape %d %d %d", g->m, g->n, g->k);
   DM_REQUIRE(g->lda % 8 == 0 && g->ldb % 8 == 0, "dm_gemm_bf16: lda/ldb must be multiples of 8 elements");
   DM_REQUIRE((reinterpret_cast<uintptr_t>(g->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(g->b) & 15) == 0,
@@ -1262,6 +1265,7 @@ extern "C" int dm_conv_down(const dm_conv_geom* g, const void* big, const void* 
                             void* out_small, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = check_geom(g, "dm_conv_down")) return rc;
+  t_kind = 1;
   DM_REQUIRE(g->cb % 32 == 0, "dm_conv_down: cb %d must be a multiple of 32", g->cb);
   DM_REQUIRE(g->cs % 16 == 0, "dm_conv_down: cs %d must be a multiple of 16", g->cs);
   PixTile pt;
@@ -1295,6 +1299,7 @@ extern "C" int dm_conv_up(const dm_conv_geom* g, const void* small, const void* 
                           int out_f32, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = check_geom(g, "dm_conv_up")) return rc;
+  t_kind = 2;
   DM_REQUIRE(g->cs % 32 == 0, "dm_conv_up: cs %d must be a multiple of 32", g->cs);
   const int cb_pad = std::max(16, (g->cb + 15) / 16 * 16);
   PixTile pt;
@@ -1377,6 +1382,7 @@ extern "C" int dm_conv_up_merged(const dm_conv_geom* g, const void* small, const
                                  void* out_big, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = check_geom(g, "dm_conv_up_merged")) return rc;
+  t_kind = 2;
   DM_REQUIRE(g->stride == 2 && g->cb == 32, "dm_conv_up_merged: needs stride 2 and cb == 32");
   DM_REQUIRE(g->cs % 64 == 0, "dm_conv_up_merged: cs %d must be a multiple of 64", g->cs);
   PixTile pt;
@@ -1431,6 +1437,7 @@ extern "C" int dm_conv_wgrad(const dm_conv_geom* g, const void* small, const voi
   // gradient dw_packed[25][cs][cb]: a warp's 32 rows (cb) are contiguous floats -> coalesced reductions.
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = check_geom(g, "dm_conv_wgrad")) return rc;
+  t_kind = 3;
   DM_REQUIRE(g->cs % 64 == 0, "dm_conv_wgrad: cs %d must be a multiple of 64", g->cs);
   const bool pair = (g->cb == 32 && g->stride == 2);
   DM_REQUIRE(g->cb % 64 == 0 || pair, "dm_conv_wgrad: cb %d must be a multiple of 64 (or 32 with stride 2)", g->cb);

@@ -39,7 +39,7 @@ def main():
     rows = list(csv.DictReader(open(path)))
     agg = defaultdict(lambda: [0, 0.0, 0.0])
     for r in rows:
-        k = (r["mode"], r["a_mn"] + r["b_mn"], r["tiles_m"], r["tiles_n"], r["tiles_z"], r["bn"], r["kc"], r["stages"], r["ctas"])
+        k = (r.get("kind", "?") + r["mode"], r["a_mn"] + r["b_mn"], r["tiles_m"], r["tiles_n"], r["tiles_z"], r["bn"], r["kc"], r["stages"], r["ctas"])
         agg[k][0] += 1
         agg[k][1] += float(r["us"])
         agg[k][2] += float(r["gflop"])
