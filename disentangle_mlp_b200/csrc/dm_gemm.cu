@@ -59,7 +59,7 @@ struct alignas(64) GemmParams {
   int num_units;    // MODE_WGRAD: tap units
   int total_tiles;  // persistent: CTAs grid-stride over [0, total_tiles)
   int acc_stride;   // TMEM columns between the two accumulator buffers
-  int cluster;      // 1, or 2: CTA pairs on adjacent M tiles (FWD) / tap units (WGRAD) share the B tile via multicast
+  int cluster;      // 1, or 2 = CTA pairs on adjacent M tiles (cg2)
   int cg2;          // cluster == 2, FWD: ONE tcgen05.mma.cta_group::2 (M = 256) per CTA pair; each CTA holds its 128
                     // A rows and half of the B rows, the leader CTA issues, both read their own TMEM half
   int cpt;     // MODE_FWD: channel chunks per tap
@@ -97,7 +97,6 @@ struct alignas(64) GemmParams {
   int bias_mod;          // != 0 (a power of two): bias index = column % bias_mod (phase-merged columns repeat the channels)
   int epi_row_step;      // mode 1: coordinate-1 origin of tile m (plain matrices: 128), 0 for pixel tiles
   int phase_c[4], phase_p[4];  // mode 1, transposed-conv phases: channel-coordinate offset (pw * cb) and row parity ph
-  int dbg;             // timing experiments only (DM_DBG): 1 = skip the A loads, 2 = skip the B loads, 4 = skip the MMAs
 };
 
 constexpr int kThreads = 192;
@@ -837,7 +836,6 @@ static int launch(GemmParams& p, dim3 grid, cudaStream_t stream, double flops, i
   const int b_bytes = p.b_mn ? (p.bn >> 6) * kAtomBytes : (p.cg2 ? (p.bn >> 1) : p.bn) * p.kc * 2;
   const int stage_bytes = a_bytes + b_bytes;
   p.cluster = cluster;
-  p.dbg = (cluster == 1 && p.mode == MODE_FWD && !p.b_mn) ? env_int("DM_DBG", 0) : 0;
   p.num_m_tiles = grid.x;
   if (p.mode == MODE_WGRAD) p.num_units = grid.y / p.num_n_tiles;
   // work items: tiles, or tile pairs when CTA pairs share the B operand
