@@ -76,5 +76,13 @@ def test_reference_checkpoint_roundtrip():
     assert len(st) == 42 and int(st[0]["step"]) == 6
     i = [n_ for n_, _ in fEG.named_parameters()].index("deconv2.weight")
     assert tuple(st[i]["exp_avg"].shape) == (256, 128, 5, 5)
+    # sampling / reconstruction under no_grad through the module API (utils/utils.py:13-32) on parameters
+    # that live, re-homed and tap-major, inside the trainer's flat buffers
+    code = torch.randn(8, 128, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        img, img_ref = mEG.decode(code.cuda()).cpu(), fEG.decode(code)
+        rec, mu, logvar = mEG(x.cuda())  # draws its own eps (models/model.py:534): only shapes are comparable
+    assert float((img - img_ref).norm() / img_ref.norm()) < 1.5e-2
+    assert tuple(rec.shape) == (b, 3, 64, 64) and tuple(mu.shape) == (b, 128) and bool(torch.isfinite(rec).all())
     # the imported moments continue training in stock torch without error
     steps.betavaegan_step(fEG, fD, fo, torch.optim.Adam(fD.parameters(), lr=1e-3), x, 25.0, 0.9, 0.1, *rands(3))
