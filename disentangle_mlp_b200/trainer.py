@@ -42,11 +42,16 @@ class FlatParams:
         self.names = [n for n, _ in named]
         dev = named[0][1].device
         assert dev.type == "cuda", "FlatParams needs the module on a CUDA device"
+        # placement in the flat buffers: everything in parameter order EXCEPT the three 33.5 M-element Linear weights,
+        # which go last -- the small parameters then form ONE contiguous range (one phase-end all-reduce instead of
+        # three), with the decoder's parameters as its tail (reduce_from)
         self.offsets, off = {}, 0
-        for n, p in named:
+        small = [(n, p) for n, p in named if n not in EARLY_BUCKETS]
+        for n, p in small + [(n, p) for n, p in named if n in EARLY_BUCKETS]:
             self.offsets[n] = off
             off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
         self.total = off
+        self._small_end = sum((p.numel() + ALIGN - 1) // ALIGN * ALIGN for _, p in small)
         self.flat = torch.zeros(off, dtype=F32, device=dev)
         self.grad = torch.zeros(off, dtype=F32, device=dev)
         self.m = torch.zeros(off, dtype=F32, device=dev)
@@ -136,6 +141,8 @@ class FlatParams:
         if lo < self.total:
             self._late_ranges.append((lo, self.total))
         self.params_changed()
+        # module.load_state_dict() copies into the re-homed fp32 masters: refresh the bf16 shadow / operand packs
+        module.register_load_state_dict_post_hook(lambda _m, _keys: self.params_changed())
 
     def _layout(self, buf, n, shape):
         """View of parameter `n`'s slice of a flat buffer with the parameter's (reference) shape."""
@@ -161,9 +168,8 @@ class FlatParams:
         if not reducer.on:
             return
         lo = self.offsets[name]
-        assert all(self.offsets[n] + self.P[n].numel() <= lo for n in self.names if n in EARLY_BUCKETS), \
-            "the separately reduced big gradients must lie before the early tail"
-        reducer.allreduce_async(self.grad, lo, self.total)
+        assert lo < self._small_end
+        reducer.allreduce_async(self.grad, lo, self._small_end)
         self._tail_done = lo
 
     def reduce_rest(self, reducer):
@@ -172,6 +178,8 @@ class FlatParams:
         for lo, hi in self._late_ranges:
             if lo < stop:
                 reducer.allreduce_async(self.grad, lo, min(hi, stop))
+            elif self._tail_done is not None and lo >= self._small_end:
+                reducer.allreduce_async(self.grad, lo, hi)  # (a late range behind the early tail: none today)
         self._tail_done = None
 
     def reduce_rest_and_wait(self, reducer):
