@@ -33,6 +33,62 @@ BIG_LINEAR = ("lth_features.0.weight", "x_to_mu.0.weight", "x_to_logvar.0.weight
 EARLY_BUCKETS = ("lth_features.0.weight", "x_to_mu.0.weight", "x_to_logvar.0.weight")  # all-reduced as soon as final
 
 
+def _complement(ranges, total):
+    """Sorted gaps of [0, total) not covered by the sorted, disjoint `ranges`."""
+    out, lo = [], 0
+    for a, b in sorted(ranges):
+        if a > lo:
+            out.append((lo, a))
+        lo = b
+    if lo < total:
+        out.append((lo, total))
+    return out
+
+
+def plan_layout(named_shapes, bf16_big=True):
+    """Placement of a module's parameters in the flat buffers and the ranges the optimizer / all-reduce work on.
+    Pure host logic (no tensors): `named_shapes` = [(name, shape)] in named_parameters() order.
+
+    Everything is placed in parameter order EXCEPT the three 33.5 M-element Linear weights (EARLY_BUCKETS), which go
+    last: the small parameters then form ONE contiguous range [0, small_end) -- one phase-end all-reduce instead of
+    three -- with the decoder's parameters as its tail (FlatParams.reduce_from)."""
+    numel = {n: int(np.prod(sh)) if len(sh) else 1 for n, sh in named_shapes}
+    al = lambda k: (k + ALIGN - 1) // ALIGN * ALIGN  # noqa: E731
+    names = [n for n, _ in named_shapes]
+    order = [n for n in names if n not in EARLY_BUCKETS] + [n for n in names if n in EARLY_BUCKETS]
+    offsets, off = {}, 0
+    for n in order:
+        offsets[n] = off
+        off += al(numel[n])
+    plan = {"names": names, "offsets": offsets, "total": off, "numel": numel,
+            "small_end": sum(al(numel[n]) for n in names if n not in EARLY_BUCKETS)}
+    # 5x5 conv / deconv weights [cs][cb][5][5] with 32-aligned channel counts: tap-major storage (see FlatParams)
+    plan["packed"] = {n for n, sh in named_shapes if len(sh) == 4 and sh[0] % 32 == 0 and sh[1] % 32 == 0}
+    # gradients kept, all-reduced and read by Adam in bf16
+    plan["big16"] = [n for n in names if n in EARLY_BUCKETS] if bf16_big else []
+    plan["off16"], o16 = {}, 0
+    for n in plan["big16"]:
+        plan["off16"][n] = o16
+        o16 += numel[n]
+    plan["total16"] = o16
+    # Adam runs per segment: fp32-gradient stretches of the flat buffer, and the bf16-gradient tensors
+    segs, lo = [], 0
+    for n in sorted(plan["big16"], key=lambda q: offsets[q]):
+        a, k = offsets[n], numel[n]
+        if a > lo:
+            segs.append((lo, a, None))
+        segs.append((a, a + k, plan["off16"][n]))
+        lo = a + k
+    if lo < off:
+        segs.append((lo, off, None))
+    plan["segments"] = segs
+    # zero_grad() skips the big Linear gradients (written in overwrite mode by the first backward of a phase)
+    plan["zero_ranges"] = _complement([(offsets[n], offsets[n] + numel[n]) for n in names if n in BIG_LINEAR], off)
+    # data parallel: the three 33.5 M-element gradients are all-reduced early, the remainder at phase end
+    plan["late_ranges"] = _complement([(offsets[n], offsets[n] + numel[n]) for n in names if n in EARLY_BUCKETS], off)
+    return plan
+
+
 class FlatParams:
     """Re-homes a module's parameters into ONE flat fp32 buffer (parameters become views), with matching
     flat gradient / Adam-moment buffers and a bf16 shadow that the GEMMs read."""
@@ -42,16 +98,9 @@ class FlatParams:
         self.names = [n for n, _ in named]
         dev = named[0][1].device
         assert dev.type == "cuda", "FlatParams needs the module on a CUDA device"
-        # placement in the flat buffers: everything in parameter order EXCEPT the three 33.5 M-element Linear weights,
-        # which go last -- the small parameters then form ONE contiguous range (one phase-end all-reduce instead of
-        # three), with the decoder's parameters as its tail (reduce_from)
-        self.offsets, off = {}, 0
-        small = [(n, p) for n, p in named if n not in EARLY_BUCKETS]
-        for n, p in small + [(n, p) for n, p in named if n in EARLY_BUCKETS]:
-            self.offsets[n] = off
-            off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
-        self.total = off
-        self._small_end = sum((p.numel() + ALIGN - 1) // ALIGN * ALIGN for _, p in small)
+        plan = plan_layout([(n, tuple(p.shape)) for n, p in named], os.environ.get("DM_BF16_BIGGRAD", "1") != "0")
+        self.offsets, self.total, self._small_end = plan["offsets"], plan["total"], plan["small_end"]
+        off = self.total
         self.flat = torch.zeros(off, dtype=F32, device=dev)
         self.grad = torch.zeros(off, dtype=F32, device=dev)
         self.m = torch.zeros(off, dtype=F32, device=dev)
@@ -64,7 +113,7 @@ class FlatParams:
         # the packed weight gradient the wgrad kernel reduces into (bulk tensor reductions need unit inner stride).
         # The nn.Parameter becomes a permuted (non-contiguous) view with the reference shape; Adam is elementwise,
         # so it does not care.
-        self.packed = {n for n, p in named if p.dim() == 4 and p.shape[0] % 32 == 0 and p.shape[1] % 32 == 0}
+        self.packed = plan["packed"]
         for n, p in named:
             o, k = self.offsets[n], p.numel()
             self._layout(self.flat, n, p.shape).copy_(p.data)
@@ -78,24 +127,11 @@ class FlatParams:
         # a GEMM whose epilogue can store bf16 directly: they are kept, all-reduced and read by Adam in bf16 (half the
         # NCCL bytes, 2 bytes less per parameter in the weight-gradient store and in the Adam read).  The fp32
         # accumulation happens in TMEM; one rounding to bf16 (2^-9) is far below the bf16 activation noise.
-        self.big16 = [n for n in self.names if n in EARLY_BUCKETS] if os.environ.get("DM_BF16_BIGGRAD", "1") != "0" else []
-        self.off16, o16 = {}, 0
-        for n in self.big16:
-            self.off16[n] = o16
-            o16 += self.P[n].numel()
-        self.grad16 = torch.zeros(max(o16, 1), dtype=BF16, device=dev)
+        self.big16, self.off16 = plan["big16"], plan["off16"]
+        self.grad16 = torch.zeros(max(plan["total16"], 1), dtype=BF16, device=dev)
         for n in self.big16:
             self.G[n] = self.grad16[self.off16[n]:self.off16[n] + self.P[n].numel()].view(self.P[n].shape)
-        # Adam runs per segment: fp32-gradient stretches of the flat buffer, and the bf16-gradient tensors in between
-        self._segments, lo = [], 0
-        for n in sorted(self.big16, key=lambda q: self.offsets[q]):
-            a, k = self.offsets[n], self.P[n].numel()
-            if a > lo:
-                self._segments.append((lo, a, None))
-            self._segments.append((a, a + k, self.off16[n]))
-            lo = a + k
-        if lo < self.total:
-            self._segments.append((lo, self.total, None))
+        self._segments = plan["segments"]  # Adam runs per segment (fp32-gradient stretches / bf16-gradient tensors)
         self.module = module
         self.buffers = dict(module.named_buffers())
         self.lr, self.betas, self.eps = lr, betas, eps
@@ -121,25 +157,7 @@ class FlatParams:
                     self.cache.static_packs[n[:-len(".weight")]] = (w_down, w_up, None)
                 else:
                     self.cache.static_packs[n[:-len(".weight")]] = ops.pack_conv_weights(p.detach(), cs, cb, True, True, cb * 25 <= 128)
-        # the big Linear weight gradients are written in "overwrite" mode by the first backward of a phase, so
-        # zero_grad() only clears the rest of the flat gradient (8 % of it)
-        big = sorted((self.offsets[n], self.offsets[n] + self.P[n].numel()) for n in self.names if n in BIG_LINEAR)
-        self._zero_ranges, lo = [], 0
-        for a, b in big:
-            if a > lo:
-                self._zero_ranges.append((lo, a))
-            lo = b
-        if lo < self.total:
-            self._zero_ranges.append((lo, self.total))
-        # data parallel: the three 33.5 M-element gradients are all-reduced early, the remainder at phase end
-        early = sorted((self.offsets[n], self.offsets[n] + self.P[n].numel()) for n in self.names if n in EARLY_BUCKETS)
-        self._late_ranges, lo = [], 0
-        for a, b in early:
-            if a > lo:
-                self._late_ranges.append((lo, a))
-            lo = b
-        if lo < self.total:
-            self._late_ranges.append((lo, self.total))
+        self._zero_ranges, self._late_ranges = plan["zero_ranges"], plan["late_ranges"]
         self.params_changed()
         # module.load_state_dict() copies into the re-homed fp32 masters: refresh the bf16 shadow / operand packs
         module.register_load_state_dict_post_hook(lambda _m, _keys: self.params_changed())

@@ -76,3 +76,80 @@ def test_bench_reference_arm_contract():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "img/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def _shell_flat_params(net, bf16_big=True):
+    """A FlatParams WITHOUT device buffers (CPU tensors, no kernels): only what the all-reduce scheduling touches."""
+    from types import SimpleNamespace
+
+    import torch
+
+    from disentangle_mlp_b200 import trainer as tr
+
+    named = [(n, tuple(p.shape)) for n, p in net.named_parameters()]
+    plan = tr.plan_layout(named, bf16_big)
+    fp = object.__new__(tr.FlatParams)
+    fp.names, fp.offsets, fp.total, fp._small_end = plan["names"], plan["offsets"], plan["total"], plan["small_end"]
+    fp.off16, fp._late_ranges, fp._tail_done = plan["off16"], plan["late_ranges"], None
+    fp.P = {n: SimpleNamespace(numel=lambda k=plan["numel"][n]: k) for n, _ in named}
+    fp.grad = torch.zeros(plan["total"])
+    fp.grad16 = torch.zeros(max(plan["total16"], 1), dtype=torch.bfloat16)
+    return fp, plan
+
+
+class _RecordingReducer:
+    on = True
+
+    def __init__(self):
+        self.calls = []
+
+    def allreduce_async(self, flat, lo=0, hi=None):
+        self.calls.append((flat.dtype, lo, flat.numel() if hi is None else hi))
+
+    def wait(self):
+        pass
+
+
+@pytest.mark.parametrize("bf16_big", [True, False])
+def test_flat_layout_and_reduce_schedule_cover_every_gradient_once(bf16_big):
+    """plan_layout + the trainer's all-reduce schedule (early big buckets, early decoder tail, phase-end rest): every
+    gradient element is reduced exactly once per phase, the big tensors in bf16 when enabled; Adam segments and the
+    zero ranges tile the flat buffer."""
+    import numpy as np
+    import torch
+
+    from disentangle_mlp_b200 import trainer as tr
+    from oracle import nets, steps
+
+    opt = steps.make_opt()
+    for net, early_names, tail in ((nets.VAE(opt), ("x_to_mu.0.weight", "x_to_logvar.0.weight"), "preprocess.0.weight"),
+                                   (nets.Discriminator_celeba(opt), ("lth_features.0.weight",), None),
+                                   (nets.Generator_celeba(opt), (), None)):
+        fp, plan = _shell_flat_params(net, bf16_big)
+        # layout: aligned, disjoint, big tensors last, small region contiguous
+        spans = sorted((plan["offsets"][n], plan["offsets"][n] + plan["numel"][n]) for n in plan["names"])
+        assert all(a % tr.ALIGN == 0 for a, _ in spans) and all(b <= c for (_, b), (c, _) in zip(spans, spans[1:]))
+        assert all(plan["offsets"][n] >= plan["small_end"] for n in early_names)
+        segs = plan["segments"]
+        assert segs[0][0] == 0 and segs[-1][1] == plan["total"] and all(a[1] == b[0] for a, b in zip(segs, segs[1:]))
+        assert [s[2] is not None for s in segs].count(True) == (len(early_names) if bf16_big else 0)
+        # one phase of the data-parallel schedule
+        red = _RecordingReducer()
+        for n in early_names:
+            fp.reduce_early(red, n)
+        if tail:
+            fp.reduce_from(red, tail)
+        fp.reduce_rest(red)
+        cover32 = np.zeros(plan["total"], dtype=np.int8)
+        cover16 = np.zeros(max(plan["total16"], 1), dtype=np.int8)
+        for dt, lo, hi in red.calls:
+            (cover16 if dt == torch.bfloat16 else cover32)[lo:hi] += 1
+        for n in plan["names"]:
+            o, k = plan["offsets"][n], plan["numel"][n]
+            if n in plan["off16"]:
+                o16 = plan["off16"][n]
+                assert (cover16[o16:o16 + k] == 1).all() and (cover32[o:o + k] == 0).all(), n
+            else:
+                assert (cover32[o:o + k] == 1).all(), n
+        assert len(red.calls) == len(early_names) + (1 if tail else 0) + 1
+        assert fp._tail_done is None  # reset for the next phase
