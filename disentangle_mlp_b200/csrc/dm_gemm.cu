@@ -1198,7 +1198,7 @@ extern "C" int dm_gemm_bf16(const dm_gemm_desc* g, void* stream_) {
     DM_REQUIRE(g->bias == nullptr, "dm_gemm_bf16: TN has no bias");
     p.mode = MODE_WGRAD;
     p.a_mn = 1; p.b_mn = 1; p.kc = 64;
-    p.bn = g->n >= 256 ? env_int("DM_BN_WGRAD", 256) : (g->n >= 128 ? 128 : 64);
+    p.bn = g->n >= 256 ? env_int("DM_BN_WGRAD", 128) : (g->n >= 128 ? 128 : 64);
     p.num_kb = (g->k + 63) / 64;
     p.tw_step = 64; p.tpi = 1 << 30; p.th_step = 0; p.tn_step = 0;
     p.taps[0].nvalid = static_cast<int16_t>(std::min(n_store, 32767));
@@ -1449,7 +1449,7 @@ extern "C" int dm_conv_wgrad(const dm_conv_geom* g, const void* small, const voi
   p.num_kb = pt.tiles;
   p.tw_step = 0; p.tpi = pt.tpi; p.th_step = pt.th_step; p.tn_step = pt.tn_step;
   p.out = dw_packed; p.out_f32 = 1; p.out_atomic = 1;
-  p.bn = g->cs >= 256 ? env_int("DM_BN_WGRAD", 256) : (g->cs >= 128 ? 128 : 64);
+  p.bn = g->cs >= 256 ? env_int("DM_BN_WGRAD", 128) : (g->cs >= 128 ? 128 : 64);
   p.num_n_tiles = g->cs / p.bn;
   // direct = 1: accumulate straight into the parameter layout dw[cs][cb][25] (scattered 4-byte reductions, no
   // unpack pass); direct = 0: tap-major packed layout [25][cs][cb] (coalesced reductions + dm_unpack_conv_grad)
