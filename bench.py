@@ -36,7 +36,7 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed regions run."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -48,7 +48,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -300,7 +300,6 @@ def run_ours(args):
     graph_mode = T._graph is not None
     if graph_mode:  # replayed kernels do not pass through the C ABI again: count what the graph holds
         launches = T.graph_launches_per_step * args.steps
-    clocks = sampler.stop() if rank == 0 else None
     for i in range(2):
         step_e2e(i)
     drain(0)
@@ -322,6 +321,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = float(t)
     assert len(sink) == args.steps + 2 and all(v == v for v in sink), "e2e: a loss was not read back (or is NaN)"
+    clocks = sampler.stop() if rank == 0 else None  # sampled across BOTH timed regions (device-resident and e2e)
 
     # roofline pass: same workload launched eagerly (events cannot be read back from a replayed graph), per-launch
     # CUDA events around every GEMM-class kernel on the launching stream
