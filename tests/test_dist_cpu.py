@@ -46,6 +46,73 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _worker_schedule(rank, world, port, q):
+    """The trainers' all-reduce schedule of one phase (early big buckets in bf16, early decoder tail, phase-end rest)
+    driven through the real GradReducer over gloo on a FlatParams shell with CPU buffers."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from types import SimpleNamespace
+
+    from disentangle_mlp_b200 import trainer as tr
+
+    # a scaled-down VAE-like parameter list (names matter: EARLY_BUCKETS / the decoder tail are found by name)
+    named = [("features.0.weight", (64, 3, 5, 5)), ("features.0.bias", (64,)), ("features.3.weight", (128, 64, 5, 5)),
+             ("x_to_mu.0.weight", (256, 1024)), ("x_to_mu.0.bias", (256,)), ("x_to_mu.3.weight", (128, 256)),
+             ("x_to_logvar.0.weight", (256, 1024)), ("x_to_logvar.3.weight", (128, 256)),
+             ("preprocess.0.weight", (1024, 128)), ("deconv1.weight", (64, 64, 5, 5)), ("deconv4.bias", (3,))]
+    plan = tr.plan_layout(named, True)
+    fp = object.__new__(tr.FlatParams)
+    fp.names, fp.offsets, fp.total, fp._small_end = plan["names"], plan["offsets"], plan["total"], plan["small_end"]
+    fp.off16, fp._late_ranges, fp._tail_done = plan["off16"], plan["late_ranges"], None
+    fp.P = {n: SimpleNamespace(numel=lambda k=plan["numel"][n]: k) for n, _ in named}
+    g = torch.Generator().manual_seed(100 + rank)
+    fp.grad = torch.randn(plan["total"], generator=g)
+    fp.grad16 = torch.randn(plan["total16"], generator=g).bfloat16()
+    mine32, mine16 = fp.grad.clone(), fp.grad16.clone()
+    red = tr.GradReducer()
+    ok = red.on
+    try:
+        for n in ("x_to_mu.0.weight", "x_to_logvar.0.weight"):
+            fp.reduce_early(red, n)
+        fp.reduce_from(red, "preprocess.0.weight")
+        fp.reduce_rest(red)
+        red.wait()
+        # expected: element-wise sums over the ranks (every element reduced exactly once)
+        all32 = [torch.zeros_like(mine32) for _ in range(world)]
+        all16 = [torch.zeros(mine16.numel()) for _ in range(world)]
+        dist.all_gather(all32, mine32)
+        dist.all_gather(all16, mine16.float())
+        exp32 = sum(all32)
+        for n, _ in named:
+            o, k = plan["offsets"][n], plan["numel"][n]
+            if n in plan["off16"]:
+                o16 = plan["off16"][n]
+                want = sum(a[o16:o16 + k] for a in all16)
+                ok = ok and torch.allclose(fp.grad16[o16:o16 + k].float(), want, rtol=2e-2, atol=2e-2)
+                ok = ok and torch.equal(fp.grad[o:o + k], mine32[o:o + k])  # its fp32 slot is not touched
+            else:
+                ok = ok and torch.allclose(fp.grad[o:o + k], exp32[o:o + k], rtol=1e-6, atol=1e-6)
+    except Exception as e:  # noqa: BLE001
+        print("schedule worker failed:", repr(e), flush=True)
+        ok = False
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_reduce_schedule_on_flat_buffers():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_schedule, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
+
+
 def test_gloo_world2_gradient_allreduce_and_scaling():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
