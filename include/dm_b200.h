@@ -88,8 +88,10 @@ int dm_conv_up_merged(const dm_conv_geom* g, const void* small, const void* w_up
 /* Weight gradient of nn.Conv2d (small = grad_output, big = input) and of nn.ConvTranspose2d (small = input,
  * big = grad_output), fp32, accumulated atomically:
  *   direct_layout = 1: dw[cs][cb][kh][kw]          += sum_{b,h,w} small[b,h,w,cs] * big[b, s*h+kh-2, s*w+kw-2, cb]
- *   direct_layout = 0: dw_packed[kh*5+kw][cs][cb]  += (same sum)   tap-major packed layout, coalesced reductions;
- *                      dm_unpack_conv_grad then moves it into the parameter layout.
+ *   direct_layout = 0: dw_packed[kh*5+kw][cs][cb]  += (same sum)   tap-major layout, reduced with bulk tensor reductions
+ *                      (cp.reduce.async.bulk.tensor, fp32 add) from a transposed smem staging tile.  The fused trainers
+ *                      keep conv weights, gradients and Adam state in this layout (no unpack); dm_unpack_conv_grad
+ *                      moves a packed scratch into the parameter layout for the drop-in modules.
  * Requires cs % 64 == 0 and cb % 64 == 0, or cb == 32 with stride 2. */
 int dm_conv_wgrad(const dm_conv_geom* g, const void* small, const void* big, float* dw, int direct_layout,
                   void* stream);
