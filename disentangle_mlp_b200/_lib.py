@@ -83,15 +83,17 @@ _lib = None
 
 
 def load():
-    """Load libdm_b200.so, building it first if the source tree is newer. Raises if impossible."""
+    """Load libdm_b200.so, (re)building it first when it is missing or its sources changed (content hash; the
+    build is serialised by a file lock, so concurrent ranks do not race).  Raises if impossible."""
     global _lib
     if _lib is not None:
         return _lib
-    path = Path(os.environ.get("DM_B200_LIB", LIB_PATH))
-    if not path.exists() or os.environ.get("DM_B200_REBUILD"):
+    if os.environ.get("DM_B200_LIB"):
+        path = Path(os.environ["DM_B200_LIB"])
+    else:
         from .build import build
 
-        path = build()
+        path = build(force=bool(os.environ.get("DM_B200_REBUILD")))
     lib = C.CDLL(str(path))
     lib.dm_last_error.restype = C.c_char_p
     lib.dm_last_error.argtypes = []

@@ -29,13 +29,27 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: cannot build libdm_b200.so")
 
 
-def _stale() -> bool:
-    if not LIB_PATH.exists():
-        return True
-    t = LIB_PATH.stat().st_mtime
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h"))
+HASH_PATH = LIB_DIR / "libdm_b200.so.srchash"
+
+
+def _source_hash() -> str:
+    """Digest of every source the library is built from (+ the flags).  Content, not mtimes: the repo snapshot that
+    travels to the GPU box does not preserve modification times."""
+    import hashlib
+
+    deps = sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")))
     deps.append(PKG_DIR.parent / "include" / "dm_b200.h")
-    return any(d.stat().st_mtime > t for d in deps)
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for d in deps:
+        h.update(d.name.encode())
+        h.update(d.read_bytes())
+    return h.hexdigest()
+
+
+def _stale() -> bool:
+    if not LIB_PATH.exists() or not HASH_PATH.exists():
+        return True
+    return HASH_PATH.read_text().strip() != _source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
@@ -43,8 +57,19 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not _stale():
         return LIB_PATH
     LIB_DIR.mkdir(exist_ok=True)
-    obj_dir = PKG_DIR / "build"
-    obj_dir.mkdir(exist_ok=True)
+    # one builder at a time (torchrun starts every rank at once): exclusive lock, then re-check
+    import fcntl
+
+    with open(LIB_DIR / ".build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not _stale():
+            return LIB_PATH
+        return _build_locked(verbose)
+
+
+def _build_locked(verbose: bool) -> Path:
+    obj_dir = PKG_DIR / "build" / f"pid{os.getpid()}"
+    obj_dir.mkdir(parents=True, exist_ok=True)
     nvcc = _nvcc()
     objs = []
     procs = []
@@ -61,12 +86,14 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
         if verbose and out.strip():
             print(out)
-    tmp = LIB_PATH.with_suffix(".so.tmp")
+    tmp = LIB_PATH.with_suffix(f".so.tmp{os.getpid()}")
     cmd = [nvcc, "-shared", "-o", str(tmp), *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
     os.replace(tmp, LIB_PATH)
+    HASH_PATH.write_text(_source_hash())
+    shutil.rmtree(obj_dir, ignore_errors=True)
     return LIB_PATH
 
 

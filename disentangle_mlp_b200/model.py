@@ -68,6 +68,9 @@ class _NetFn(torch.autograd.Function):
         B = dict(owner.named_buffers())
         cache = owner._operand_cache
         ctx.owner, ctx.kind, ctx.names, ctx.P = owner, kind, names, P
+        # backward re-derives the bf16 operands from the CURRENT parameters (they are not saved on ctx): remember
+        # their versions so that an in-place update between forward and backward raises, as stock autograd would
+        ctx.versions = [(p.data_ptr(), p._version) for p in params]
         x = x.detach()
         if kind == "disc":
             prob, feat, S = engine.discriminator_forward(x.float().contiguous(), P, B, cache, owner.training)
@@ -84,6 +87,10 @@ class _NetFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grads):
         P, names, cache = ctx.P, ctx.names, ctx.owner._operand_cache
+        if ctx.versions != [(P[n].data_ptr(), P[n]._version) for n in names]:
+            raise RuntimeError(f"{type(ctx.owner).__name__}: a parameter was modified in place between forward and "
+                               "backward (optimizer.step() before a retained-graph backward?); the kernels would "
+                               "back-propagate through the updated weights")
         need_w = any(ctx.needs_input_grad[3:])
         G = _alloc_grads(P) if need_w else None
         need_dx = ctx.needs_input_grad[2]
@@ -137,6 +144,12 @@ class _KernelBacked(nn.Module):
         names = self._param_names(kind)
         P = dict(self.named_parameters())
         return _NetFn.apply(self, kind, x, *[P[n] for n in names])
+
+    def apply(self, fn):  # .apply(weights_init) writes through `.data`: version counters do not move
+        out = super().apply(fn)
+        if hasattr(self, "_operand_cache"):
+            self._operand_cache.invalidate()
+        return out
 
     def _apply(self, fn, *a, **k):  # .to()/.cuda()/.float(): parameters move, derived operands are stale
         out = super()._apply(fn, *a, **k)

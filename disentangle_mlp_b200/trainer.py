@@ -216,10 +216,19 @@ class FlatParams:
             else:
                 ops.pack_conv_weights(p.detach(), p.shape[0], p.shape[1], out=packs)
 
+    def touch(self):
+        """The fp32 masters were updated through raw pointers (Adam kernel, graph replay, restore): nn.Parameter
+        version counters did not move, so the MODULE's own lazily built operand cache (engine.OperandCache, used by
+        the drop-in forward path: decode / model(x) sampling between training steps) must be dropped explicitly."""
+        c = getattr(self.module, "_operand_cache", None)
+        if c is not None:
+            c.invalidate()
+
     def params_changed(self):
         """Call after the fp32 parameters were modified outside adam() (init, load_state_dict)."""
         ops.cast_bf16(self.flat, self.shadow)
         self.refresh_packs()
+        self.touch()
 
     def zero_grad(self):
         for lo, hi in self._zero_ranges:
@@ -234,6 +243,7 @@ class FlatParams:
             ops.adam_step(self.flat[lo:hi], g, self.m[lo:hi], self.v[lo:hi], self.lr, self.betas[0], self.betas[1],
                           self.eps, 0, grad_scale, self.shadow[lo:hi], step_dev=self.step_dev, count_step=(i == 0))
         self.refresh_packs()  # bf16 conv operand packs follow the updated fp32 weights
+        self.touch()
 
     def snapshot(self):
         return {"flat": self.flat.clone(), "m": self.m.clone(), "v": self.v.clone(), "step": self.step_count,
@@ -430,7 +440,9 @@ class _Base:
         torch.cuda.set_rng_state(rng, dev)
         torch.cuda.synchronize()
 
-    def _graph_step(self, data, real_label, fake_label):
+    def _graph_step(self, data, real_label, fake_label, rands=None):
+        """Replay the captured step.  rands: optional list of `n_rands` [batch,128] tensors (noise / eps in the
+        reference's draw order) copied into the graph's static buffers instead of drawing them (parity tests)."""
         if real_label is None:
             real_label, fake_label = self.draw_labels()
         # the host may run several steps ahead of the GPU: each step's labels get their own pinned slot, reused only
@@ -442,11 +454,18 @@ class _Base:
         self._glabels.copy_(host, non_blocking=True)
         ev.record()
         self._gx.copy_(data, non_blocking=True)
-        for r in self._grands:
-            r.normal_()
+        if rands is None:
+            for r in self._grands:
+                r.normal_()
+        else:
+            assert len(rands) == len(self._grands) and all(r is not None for r in rands), \
+                "graph mode: inject all of the step's random inputs or none"
+            for dst, src in zip(self._grands, rands):
+                dst.copy_(src, non_blocking=True)
         self._graph.replay()
         for fp, n in zip(self.flat_params(), self._adams_per_step):
             fp.step_count += n
+            fp.touch()
         self.metrics = self._gmetrics
         return self.metrics
 
@@ -466,8 +485,8 @@ class VAETrainer(_Base):
         return [self.fp]
 
     def step(self, data, eps=None):
-        if self._graph is not None and eps is None:
-            return self._graph_step(data, 0.0, 0.0)
+        if self._graph is not None:
+            return self._graph_step(data, 0.0, 0.0, None if eps is None else [eps])
         return self._step_impl(data, None, None, eps=eps)
 
     def _step_impl(self, data, real_label=None, fake_label=None, eps=None):
@@ -510,8 +529,8 @@ class GANTrainer(_Base):
         return [self.fg, self.fd]
 
     def step(self, data, real_label=None, fake_label=None, noise=None):
-        if self._graph is not None and noise is None:
-            return self._graph_step(data, real_label, fake_label)
+        if self._graph is not None:
+            return self._graph_step(data, real_label, fake_label, None if noise is None else [noise])
         if real_label is None:
             real_label, fake_label = self.draw_labels()
         return self._step_impl(data, real_label, fake_label, noise=noise)
@@ -564,8 +583,9 @@ class BetaVAEGANTrainer(_Base):
         return [self.feg, self.fd]
 
     def step(self, data, real_label=None, fake_label=None, noise=None, eps_dec=None, eps_enc=None):
-        if self._graph is not None and noise is None and eps_dec is None and eps_enc is None:
-            return self._graph_step(data, real_label, fake_label)
+        if self._graph is not None:
+            rands = None if (noise is None and eps_dec is None and eps_enc is None) else [noise, eps_dec, eps_enc]
+            return self._graph_step(data, real_label, fake_label, rands)
         if real_label is None:
             real_label, fake_label = self.draw_labels()
         return self._step_impl(data, real_label, fake_label, noise, eps_dec, eps_enc)

@@ -72,3 +72,49 @@ class Loader:
                 u8 = torch.from_numpy(np.ascontiguousarray(self.data[i * self.b:(i + 1) * self.b]))
                 x = (u8.permute(0, 3, 1, 2).float() / 255.0 - 0.5) / 0.5
             yield x.pin_memory().to(self.dev, non_blocking=True)
+
+
+# ------------------------------------------------------------------------------------------ checkpoints
+# The reference's `model_<epoch>.tar` dictionaries, key for key.  The reference wraps some networks
+# in nn.DataParallel before calling .state_dict(), so THEIR keys carry a "module." prefix:
+#   new_betavaegan.py:222-228  encoder_decoder_model = netEG.module.state_dict() (no prefix),
+#                              discriminator_model = netD.state_dict()           ("module." prefix)
+#   new_gan.py:169-174         netG / netD = DataParallel state_dicts            ("module." prefix on both)
+#   new_vae.py:88-91           VAE_model = model.module.state_dict()             (no prefix)
+# Written here with the same prefixes, so either side loads the other's files; on load a prefix is accepted or not.
+CKPT_KEYS = {
+    "betavaegan": (("encoder_decoder_model", False, "encoder_decoder_optimizer"),
+                   ("discriminator_model", True, "discriminator_optimizer")),
+    "gan": (("netG", True, "G_trainer"), ("netD", True, "D_trainer")),
+    "vae": (("VAE_model", False, "optimizer"),),
+}
+
+
+def checkpoint_dict(kind, epoch, modules, flat_params):
+    """modules / flat_params: in the order of CKPT_KEYS[kind] (e.g. (netEG, netD), (T.feg, T.fd))."""
+    ck = {"epoch": epoch}
+    for (mk, prefixed, ok), mod, fp in zip(CKPT_KEYS[kind], modules, flat_params):
+        sd = mod.state_dict()
+        ck[mk] = {("module." + k if prefixed else k): v for k, v in sd.items()}
+        ck[ok] = fp.optimizer_state_dict()
+    return ck
+
+
+def save_checkpoint(kind, model_path, epoch, modules, flat_params):
+    os.makedirs(model_path, exist_ok=True)
+    path = os.path.join(model_path, f"model_{epoch}.tar")
+    torch.save(checkpoint_dict(kind, epoch, modules, flat_params), path)
+    return path
+
+
+def load_checkpoint_dict(kind, ck, modules, flat_params):
+    """Restore modules + fused optimizers from a reference-format dictionary; returns the epoch to resume from."""
+    for (mk, _prefixed, ok), mod, fp in zip(CKPT_KEYS[kind], modules, flat_params):
+        mod.load_state_dict({k.removeprefix("module."): v for k, v in ck[mk].items()})
+        fp.load_optimizer_state_dict(ck[ok])
+        fp.params_changed()
+    return int(ck["epoch"])
+
+
+def load_checkpoint(kind, path, modules, flat_params, dev):
+    return load_checkpoint_dict(kind, torch.load(path, map_location=dev, weights_only=False), modules, flat_params)

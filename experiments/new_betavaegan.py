@@ -5,12 +5,10 @@ disentangle_mlp_b200.trainer.BetaVAEGANTrainer.step.  lr is hard-coded to 1e-3 a
     python experiments/new_betavaegan.py --name run --beta 25 --batch_size_train 64
     torchrun --nproc-per-node 8 experiments/new_betavaegan.py --name run --beta 25 --batch_size_train 512
 """
-import os
-
 import numpy as np
 import torch
 
-from _common import Loader, parse, setup_dist
+from _common import Loader, load_checkpoint, parse, save_checkpoint, setup_dist
 
 from disentangle_mlp_b200 import model as dm
 from disentangle_mlp_b200.trainer import BetaVAEGANTrainer
@@ -26,15 +24,8 @@ def main():
     netD.apply(dm.weights_init)
     T = BetaVAEGANTrainer(netEG, netD, beta=opt.beta, lr=1e-3)
     start = 0
-    if opt.load_path:
-        ck = torch.load(opt.load_path, map_location=dev)
-        netEG.load_state_dict(ck["encoder_decoder_model"])
-        netD.load_state_dict({k.removeprefix("module."): v for k, v in ck["discriminator_model"].items()})
-        T.feg.load_optimizer_state_dict(ck["encoder_decoder_optimizer"])
-        T.fd.load_optimizer_state_dict(ck["discriminator_optimizer"])
-        T.feg.params_changed()
-        T.fd.params_changed()
-        start = ck["epoch"]
+    if opt.load_path:  # new_betavaegan.py:203-209
+        start = load_checkpoint("betavaegan", opt.load_path, (netEG, netD), (T.feg, T.fd), dev)
     torch.manual_seed(opt.seed + 7919 * (rank + 1))  # same initial weights on every rank, different noise / eps
     loader = Loader(opt, world, rank, dev)
     for epoch in range(start, opt.epochs):
@@ -48,13 +39,8 @@ def main():
         enc, dec, dx = (float(v) / loader.dataset_len * world for v in sums)
         if rank == 0:
             print(f"====> Epoch: {epoch} Avg Encoder Loss: {enc:.4f} Avg Decoder Loss: {dec:.4f} Dx: {dx:.4f}")
-            if opt.model_path:
-                os.makedirs(opt.model_path, exist_ok=True)
-                torch.save({"epoch": epoch + 1, "encoder_decoder_model": netEG.state_dict(),
-                            "discriminator_model": {"module." + k: v for k, v in netD.state_dict().items()},
-                            "encoder_decoder_optimizer": T.feg.optimizer_state_dict(),
-                            "discriminator_optimizer": T.fd.optimizer_state_dict()},
-                           os.path.join(opt.model_path, f"model_{epoch + 1}.tar"))
+            if opt.model_path:  # new_betavaegan.py:222-228
+                save_checkpoint("betavaegan", opt.model_path, epoch + 1, (netEG, netD), (T.feg, T.fd))
 
 
 if __name__ == "__main__":

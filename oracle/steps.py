@@ -144,3 +144,48 @@ def synthetic_batch(batch, seed, device="cpu"):
     """CelebA after Normalize(.5,.5) lies in [-1,1] (dataloader/dataset.py:12,38-43): i.i.d. U[-1,1] stand-in."""
     g = torch.Generator().manual_seed(seed)
     return (torch.rand(batch, 3, 64, 64, generator=g) * 2 - 1).to(device)
+
+
+class PerShard:
+    """Data-parallel restatement for the N-rank parity check: every call of the wrapped
+    module runs shard by shard over `world` equal slices of the batch -- so BatchNorm normalises each shard with
+    its own statistics, as each replica does under the reference's nn.DataParallel (new_betavaegan.py:40-42) and
+    as each rank does in the one-process-per-GPU scheme -- and the outputs are concatenated in rank order, so a
+    loss taken over the concatenated outputs back-propagates the SUM of the per-shard gradients.  Only shard 0's
+    forward updates the persistent BatchNorm buffers (DataParallel keeps device 0's; rank 0 is what the check
+    compares).  Pass instances of this class to the *_step functions above in place of the modules."""
+
+    def __init__(self, module, world):
+        self.module, self.world = module, world
+
+    def _run(self, fn, x):
+        outs = []
+        for s, xs in enumerate(x.chunk(self.world)):
+            saved = []
+            if s > 0:  # shards > 0 update throw-away copies of the BatchNorm buffers
+                for m in self.module.modules():
+                    for k, b in list(m._buffers.items()):
+                        if b is not None:
+                            saved.append((m, k, b))
+                            m._buffers[k] = b.clone()
+            o = fn(xs)
+            for m, k, b in saved:
+                m._buffers[k] = b
+            outs.append(o if isinstance(o, tuple) else (o,))
+        cat = tuple(torch.cat([o[i] for o in outs]) for i in range(len(outs[0])))
+        return cat if len(cat) > 1 else cat[0]
+
+    def __call__(self, x):
+        return self._run(self.module, x)
+
+    def encode(self, x):
+        return self._run(self.module.encode, x)
+
+    def decode(self, z):
+        return self._run(self.module.decode, z)
+
+    def zero_grad(self):
+        self.module.zero_grad()
+
+    def parameters(self):
+        return self.module.parameters()

@@ -85,3 +85,75 @@ def test_reference_checkpoint_roundtrip():
     assert tuple(rec.shape) == (b, 3, 64, 64) and tuple(mu.shape) == (b, 128) and bool(torch.isfinite(rec).all())
     # the imported moments continue training in stock torch without error
     steps.betavaegan_step(fEG, fD, fo, torch.optim.Adam(fD.parameters(), lr=1e-3), x, 25.0, 0.9, 0.1, *rands(3))
+
+
+@pytest.mark.parametrize("kind", ["gan", "vae", "betavaegan"])
+def test_checkpoint_key_sets_and_dataparallel_prefix(kind, tmp_path):
+    """The three scripts' `model_N.tar` formats, key for key, INCLUDING the "module." prefix the reference's
+    nn.DataParallel wrappers put on some state_dicts (new_gan.py:169-174 both nets; new_betavaegan.py:222-228 netD
+    only; new_vae.py:88-91 none): a reference-written file resumes here (--load_path) and a file written here loads
+    into the reference's DataParallel-wrapped modules."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "experiments"))
+    import _common as C
+    from disentangle_mlp_b200 import model as dm
+    from disentangle_mlp_b200 import trainer as tr
+    from oracle import nets, steps
+
+    b, opt = 8, steps.make_opt()
+    x = steps.synthetic_batch(b, 77)
+    torch.manual_seed(999)
+    if kind == "gan":
+        refs = (nets.Generator_celeba(opt), nets.Discriminator_celeba(opt))
+        mine = (dm.Generator_celeba(opt).cuda(), dm.Discriminator_celeba(opt).cuda())
+    elif kind == "vae":
+        refs = (nets.VAE(opt),)
+        mine = (dm.VAE(opt).cuda(),)
+    else:
+        refs = (nets.VAE(opt), nets.Discriminator_celeba(opt))
+        mine = (dm.VAE(opt).cuda(), dm.Discriminator_celeba(opt).cuda())
+    for r in refs:
+        r.apply(nets.weights_init)
+    ropts = [torch.optim.Adam(r.parameters(), lr=3e-4) for r in refs]
+    g = torch.Generator().manual_seed(8)
+    rands = [torch.randn(b, 128, generator=g) for _ in range(3)]
+    # the reference trains one step and writes its checkpoint the way ITS script does (DataParallel prefixes)
+    if kind == "gan":
+        steps.gan_step(refs[0], refs[1], ropts[0], ropts[1], x, 0.9, 0.1, rands[0])
+        T = tr.GANTrainer(*mine, lr=3e-4)
+        fps = (T.fg, T.fd)
+    elif kind == "vae":
+        steps.vae_step(refs[0], ropts[0], x, rands[0])
+        T = tr.VAETrainer(mine[0], lr=3e-4)
+        fps = (T.fp,)
+    else:
+        steps.betavaegan_step(refs[0], refs[1], ropts[0], ropts[1], x, 25.0, 0.9, 0.1, *rands)
+        T = tr.BetaVAEGANTrainer(*mine, beta=25.0, lr=3e-4)
+        fps = (T.feg, T.fd)
+    ck = {"epoch": 3}
+    for (mk, prefixed, ok), r, o in zip(C.CKPT_KEYS[kind], refs, ropts):
+        sd = torch.nn.DataParallel(r).state_dict() if prefixed else r.state_dict()
+        assert all(k.startswith("module.") for k in sd) == prefixed
+        ck[mk], ck[ok] = sd, o.state_dict()
+    path = tmp_path / "model_3.tar"
+    torch.save(ck, path)
+    # ---- resume here from the reference's file
+    assert C.load_checkpoint(kind, str(path), mine, fps, "cuda") == 3
+    for m, r in zip(mine, refs):
+        for (n, p), (_, q) in zip(m.state_dict().items(), r.state_dict().items()):
+            assert torch.equal(p.cpu(), q), n
+    for fp, o in zip(fps, ropts):
+        st = o.state_dict()["state"]
+        assert fp.step_count == int(st[0]["step"])
+    T.step(x.cuda()) if kind == "vae" else T.step(x.cuda(), 0.9, 0.1)  # training continues from it
+    # ---- and a file written here has the reference's key set and loads into ITS (DataParallel-wrapped) modules
+    out = C.save_checkpoint(kind, str(tmp_path / "out"), 4, mine, fps)
+    ck2 = torch.load(out, map_location="cpu", weights_only=False)
+    assert set(ck2) == set(ck)
+    for (mk, prefixed, ok), r in zip(C.CKPT_KEYS[kind], refs):
+        assert set(ck2[mk]) == set(ck[mk]), mk
+        target = torch.nn.DataParallel(r) if prefixed else r
+        target.load_state_dict(ck2[mk])  # strict: raises on any key mismatch
+        torch.optim.Adam(r.parameters(), lr=3e-4).load_state_dict(ck2[ok])

@@ -13,6 +13,14 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
+def _fp32_refs():
+    """torch references on CUDA must be true fp32: cudnn.allow_tf32 defaults to True (a ~1e-3 reference)."""
+    import torch
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
 def rel_err(got, ref):
     import torch
 
@@ -26,6 +34,7 @@ def case_gemm(layout, m, n, k, splits=1, out_bf16=False, bias=False, n_store=0, 
 
     from disentangle_mlp_b200 import ops
 
+    _fp32_refs()
     torch.manual_seed(0)
     dev = "cuda"
     if layout == "nt":
@@ -57,6 +66,7 @@ def case_gemm(layout, m, n, k, splits=1, out_bf16=False, bias=False, n_store=0, 
 def conv_refs(batch, hs, ws, cs, cb, stride, seed=0):
     import torch
 
+    _fp32_refs()
     torch.manual_seed(seed)
     dev = "cuda"
     w = (torch.randn(cs, cb, 5, 5, device=dev) * 0.05)
