@@ -13,6 +13,13 @@ from .build import LIB_PATH
 c_void_p, c_int, c_float, c_ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 
 
+class BnFuse(C.Structure):
+    """dm_bn_fuse: BatchNorm statistics + finalize fused into the producing kernel (scratch NULL = off)."""
+    _fields_ = [("scratch", c_void_p), ("groups", c_int), ("rows", c_ll), ("gamma", c_void_p), ("beta", c_void_p),
+                ("running_mean", c_void_p), ("running_var", c_void_p), ("num_batches_tracked", c_void_p),
+                ("momentum", c_float), ("eps", c_float), ("scale_shift", c_void_p), ("mean_invstd", c_void_p)]
+
+
 class GemmDesc(C.Structure):
     _fields_ = [
         ("layout", c_int), ("m", c_int), ("n", c_int), ("k", c_int),
@@ -20,6 +27,7 @@ class GemmDesc(C.Structure):
         ("d", c_void_p), ("ldd_m", c_ll), ("ldd_n", c_ll),
         ("d_f32", c_int), ("accumulate", c_int), ("bias", c_void_p),
         ("m_store", c_int), ("n_store", c_int), ("splits", c_int), ("k_alg", c_int),
+        ("bn", BnFuse),
     ]
 
 
@@ -33,8 +41,8 @@ GEMM_NT, GEMM_NN, GEMM_TN = 0, 1, 2
 # name -> argtypes (all return int except the first three)
 _SIGS = {
     "dm_gemm_bf16": [C.POINTER(GemmDesc), c_void_p],
-    "dm_conv_down": [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
-    "dm_conv_up": [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+    "dm_conv_down": [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_void_p, C.POINTER(BnFuse), c_void_p],
+    "dm_conv_up": [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_void_p, c_int, C.POINTER(BnFuse), c_void_p],
     "dm_conv_wgrad": [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "dm_unpack_conv_grad": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "dm_profile_enable": [c_int],
@@ -42,14 +50,13 @@ _SIGS = {
     "dm_profile_read": [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(c_ll)],
     "dm_debug_last_plan": [C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int)],
     "dm_bn_parts": [c_ll, c_int],
-    "dm_bn_stats": [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p],
-    "dm_bn_finalize": [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
-                       c_float, c_void_p, c_void_p, c_void_p],
-    "dm_bn_apply_act": [c_void_p, c_int, c_ll, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p],
+    "dm_bn_slots": [],
+    "dm_bn_stats": [c_void_p, c_int, c_int, C.POINTER(BnFuse), c_void_p],
+    "dm_bn_apply_act": [c_void_p, c_int, c_ll, c_int, c_void_p, c_int, c_float, c_void_p, c_int, c_void_p],
     "dm_bn_forward": [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float,
                       c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "dm_bn_backward": [c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_int, c_float, c_void_p,
-                       c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+                       c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "dm_bias_act": [c_void_p, c_ll, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p],
     "dm_act_backward": [c_void_p, c_void_p, c_ll, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p],
     "dm_colsum": [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p],
@@ -59,7 +66,7 @@ _SIGS = {
     "dm_transpose_bf16": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "dm_pack_conv_weights": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "dm_pack_up_merged": [c_void_p, c_int, c_int, c_void_p, c_void_p],
-    "dm_conv_up_merged": [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "dm_conv_up_merged": [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_void_p, C.POINTER(BnFuse), c_void_p],
     "dm_cast_bf16": [c_void_p, c_ll, c_void_p, c_void_p],
     "dm_reparam_forward": [c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_void_p],
     "dm_reparam_backward": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_void_p,
@@ -77,7 +84,7 @@ _SIGS = {
 }
 
 #: every symbol include/dm_b200.h declares
-EXPORTED = ["dm_last_error", "dm_version", "dm_launch_count", *list(_SIGS)]
+EXPORTED = ["dm_last_error", "dm_version", "dm_launch_count", "dm_bn_scratch_floats", *list(_SIGS)]
 
 _lib = None
 
@@ -99,6 +106,8 @@ def load():
     lib.dm_last_error.argtypes = []
     lib.dm_version.restype = c_int
     lib.dm_launch_count.restype = c_ll
+    lib.dm_bn_scratch_floats.restype = c_ll
+    lib.dm_bn_scratch_floats.argtypes = [c_int, c_int]
     for name, args in _SIGS.items():
         fn = getattr(lib, name)
         fn.argtypes = args

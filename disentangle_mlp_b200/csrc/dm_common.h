@@ -6,6 +6,9 @@
 
 namespace dm {
 
+// BatchNorm partial sums go to [group][kBnSlots][2][c] slot scratches (dm_elem.cu consumers, dm_gemm.cu epilogue)
+constexpr int kBnSlots = 8;
+
 // Thread-local last-error string returned by dm_last_error().
 char* last_error_buf();
 int set_error(int code, const char* fmt, ...);

@@ -15,6 +15,7 @@
 
 #include "../../include/dm_b200.h"
 #include "dm_common.h"
+#include "dm_bn_fin.cuh"
 
 namespace dm {
 extern std::atomic<long long> g_launch_count;
@@ -162,72 +163,93 @@ __device__ __forceinline__ void sum_partials_block(const float* __restrict__ par
   }
 }
 
+// ------------------------------------------------------------------------------------------ BatchNorm (training mode)
+// Two launches per application and direction, no finalize kernels (dm_bn_fin.cuh has the scheme): the producer of the
+// per-channel sums (the tcgen05 GEMM that writes the pre-BatchNorm tensor, in its epilogue -- dm_gemm.cu; or
+// bn_stats_kernel / bn_bwd_reduce_kernel here) adds its partial sums to a slot scratch with fp32 red.add; its LAST
+// block finalizes (constants for the consumer, running statistics / dgamma, dbeta) and re-zeroes the scratch; the
+// consumers are plain streaming kernels.  Tensors with at most kBn1dMaxRows rows (BatchNorm1d behind the Linear
+// layers: rows = batch) take a single-launch kernel with an exact two-pass variance.
+constexpr int kBn1dMaxRows = 256;
+
+// Row reduction into slots: every block reduces its row range, then adds its NACC x (tx*8) totals to slot
+// (blockIdx.y % kBnSlots) of `slots` = [kBnSlots][NACC][c].
+template <typename T, int NACC, typename F>
+__device__ __forceinline__ void rows_reduce_slots(long long rows, int c, long long rows_per_block, float* slots, F&& body) {
+  extern __shared__ float red[];  // [ty][tx*8*NACC]
+  const int tx = blockDim.x, ty = blockDim.y;
+  const int cv = blockIdx.x * tx + threadIdx.x;
+  const bool live = cv * 8 < c;
+  float acc[NACC][8];
+#pragma unroll
+  for (int a = 0; a < NACC; ++a)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[a][i] = 0.f;
+  const long long r0 = blockIdx.y * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  if (live) {
+#pragma unroll 4
+    for (long long r = r0 + threadIdx.y; r < r1; r += ty) body(r, cv * 8, acc);
+  }
+  float* mine = red + (threadIdx.y * tx + threadIdx.x) * (8 * NACC);
+#pragma unroll
+  for (int a = 0; a < NACC; ++a)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mine[a * 8 + i] = acc[a][i];
+  __syncthreads();
+  float* dst = slots + static_cast<long long>(blockIdx.y % kBnSlots) * NACC * c;
+  for (int j = threadIdx.y; j < 8 * NACC; j += ty) {
+    float s = 0.f;
+    for (int y = 0; y < ty; ++y) s += red[(y * tx + threadIdx.x) * (8 * NACC) + j];
+    if (live) atomicAdd(dst + static_cast<long long>(j / 8) * c + cv * 8 + (j % 8), s);
+  }
+}
+
+// Ticket: call when this block's partial sums have been added.  Returns true in every thread of the LAST block of the
+// grid to get here: all other blocks' red.adds are then visible (each published them with __threadfence first).
+__device__ __forceinline__ bool take_ticket(unsigned int* counter) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    const unsigned int n = gridDim.x * gridDim.y * gridDim.z;
+    s_last = (atomicAdd(counter, 1u) == n - 1u) ? 1 : 0;
+    __threadfence();
+  }
+  __syncthreads();
+  return s_last != 0;
+}
+
+// Forward producer for tensors no GEMM epilogue covers: shifted sums (k = running_mean) + finalize by the last block.
 template <typename T>
-__global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ y, long long rows, int c,
-                                                       long long rows_per_block, float* __restrict__ sums) {
-  // Shifted sums: sum (y - k) and sum (y - k)^2 with k = the channel's value in row 0.  E[(y-k)^2] - E[y-k]^2 does
-  // not cancel catastrophically when |mean| >> std (a BatchNorm1d feature that is nearly constant over a batch of
-  // 16), which the plain E[y^2] - E[y]^2 in fp32 does; torch uses a two-pass / Welford variance.
-  // blockIdx.z = group: `gridDim.z` independent batches stacked along rows, each with its own partials block
+__global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ y, int c, long long rows_per_block,
+                                                       const dm_bn_fuse f) {
+  // blockIdx.z = group: `gridDim.z` independent batches stacked along rows, each with its own slots
+  const long long rows = f.rows;
   y += static_cast<long long>(blockIdx.z) * rows * c;
-  sums += static_cast<long long>(blockIdx.z) * (gridDim.y + 1) * 2 * c;
+  float* slots = f.scratch + static_cast<long long>(blockIdx.z) * kBnSlots * 2 * c;
   const int cv = blockIdx.x * blockDim.x + threadIdx.x;
   float k[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (cv * 8 < c) load8(y + cv * 8, k);
-  rows_reduce<T, 2>(rows, c, rows_per_block, sums, [&](long long r, int ch, float(&acc)[2][8]) {
-    float f[8];
-    load8(y + r * c + ch, f);
+  if (f.running_mean && cv * 8 < c) {  // (plain loads: the last block of this launch rewrites running_mean)
+    const float4 u = __ldcg(reinterpret_cast<const float4*>(f.running_mean + cv * 8));
+    const float4 w = __ldcg(reinterpret_cast<const float4*>(f.running_mean + cv * 8) + 1);
+    k[0] = u.x; k[1] = u.y; k[2] = u.z; k[3] = u.w; k[4] = w.x; k[5] = w.y; k[6] = w.z; k[7] = w.w;
+  }
+  rows_reduce_slots<T, 2>(rows, c, rows_per_block, slots, [&](long long r, int ch, float(&acc)[2][8]) {
+    float v[8];
+    load8(y + r * c + ch, v);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float d = f[i] - k[i];
+      const float d = v[i] - k[i];
       acc[0][i] += d;
       acc[1][i] += d * d;
     }
   });
-  // the shift travels with the partials: row gridDim.y of the [parts + 1][2][c] buffer
-  if (blockIdx.y == 0 && threadIdx.y == 0 && cv * 8 < c) store8(sums + 2ll * gridDim.y * c + cv * 8, k);
+  if (!take_ticket(bn_ticket(f.scratch, c, f.groups))) return;
+  bn_forward_finalize(f, c, threadIdx.y * blockDim.x + threadIdx.x, blockDim.x * blockDim.y);
 }
 
-// Per-channel finalize: normalisation constants + running-stat update (momentum, unbiased running var),
-// matching torch.nn.BatchNorm{1,2}d in training mode (models/model.py:451-457,462,468,492,496-504,390-399).
-__global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ partials, int nparts, long long rows,
-                                                            int c, const float* __restrict__ gamma,
-                                                            const float* __restrict__ beta, float* __restrict__ running_mean,
-                                                            float* __restrict__ running_var,
-                                                            long long* __restrict__ num_batches_tracked, float momentum,
-                                                            float eps, float* __restrict__ scale_shift,
-                                                            float* __restrict__ mean_invstd, int groups) {
-  const int ch = blockIdx.x * 32 + threadIdx.x;
-  // groups are finalized in order by the same thread: the running statistics see pass 0, then pass 1, ... exactly as
-  // separate forward calls would update them
-  for (int g = 0; g < groups; ++g) {
-    const float* part = partials + static_cast<long long>(g) * nparts * 2 * c;
-    float sum[2];
-    sum_partials_block<2>(part, nparts - 1, 2ll * c, ch, ch < c, c, sum);  // row nparts-1 = the shift k
-    __syncthreads();  // sum_partials_block's shared buffer is reused by the next group
-    if (threadIdx.y != 0 || ch >= c) continue;
-    const double n = static_cast<double>(rows);
-    const double dmean = sum[0] / n;  // mean of (y - k)
-    const double mean = static_cast<double>(part[2ll * (nparts - 1) * c + ch]) + dmean;
-    double var = sum[1] / n - dmean * dmean;
-    if (var < 0.0) var = 0.0;
-    const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-    const float sc = gamma[ch] * invstd;
-    float* ss = scale_shift + static_cast<long long>(g) * 2 * c;
-    float* mi = mean_invstd + static_cast<long long>(g) * 2 * c;
-    ss[ch] = sc;
-    ss[c + ch] = beta[ch] - static_cast<float>(mean) * sc;
-    mi[ch] = static_cast<float>(mean);
-    mi[c + ch] = invstd;
-    if (running_mean) {
-      const double unbiased = rows > 1 ? var * n / (n - 1.0) : var;
-      running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * static_cast<float>(mean);
-      running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * static_cast<float>(unbiased);
-    }
-  }
-  if (threadIdx.y == 0 && ch == 0 && num_batches_tracked) *num_batches_tracked += groups;
-}
-
+// out = act(y * scale + shift) with given constants; blockIdx.z = group
 template <typename T>
 __global__ void __launch_bounds__(256) bn_apply_act_kernel(const T* __restrict__ y, long long rows, int c,
                                                            long long rows_per_block,
@@ -235,7 +257,7 @@ __global__ void __launch_bounds__(256) bn_apply_act_kernel(const T* __restrict__
                                                            float slope, __nv_bfloat16* __restrict__ out) {
   const int cv = blockIdx.x * blockDim.x + threadIdx.x;
   if (cv * 8 >= c) return;
-  y += static_cast<long long>(blockIdx.z) * rows * c;  // group (see bn_stats_kernel)
+  y += static_cast<long long>(blockIdx.z) * rows * c;
   out += static_cast<long long>(blockIdx.z) * rows * c;
   scale_shift += static_cast<long long>(blockIdx.z) * 2 * c;
   float sc[8], sh[8];
@@ -253,21 +275,23 @@ __global__ void __launch_bounds__(256) bn_apply_act_kernel(const T* __restrict__
   }
 }
 
-// Backward pass 1: sums[0][c] = sum dz, sums[1][c] = sum dz * xhat, dz = dout * act'(z)
+// Backward producer: slots[.][0][c] += sum dz, slots[.][1][c] += sum dz * xhat, dz = dout * act'(z); the last block
+// writes the per-group sums for bn_bwd_apply_kernel, accumulates dgamma / dbeta and re-zeroes the slots.
 template <typename T>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout,
                                                             const T* __restrict__ y, long long rows, int c,
                                                             long long rows_per_block,
                                                             const float* __restrict__ scale_shift,
                                                             const float* __restrict__ mean_invstd, int act,
-                                                            float slope, float* __restrict__ sums) {
+                                                            float slope, float* scratch, float* dgamma, float* dbeta) {
+  const int groups = gridDim.z;
+  float* slots = scratch + static_cast<long long>(blockIdx.z) * kBnSlots * 2 * c;
   {
     const long long z = blockIdx.z;  // group
     dout += z * rows * c;
     y += z * rows * c;
     scale_shift += z * 2 * c;
     mean_invstd += z * 2 * c;
-    sums += z * (gridDim.y + 1) * 2 * c;
   }
   const int cv0 = blockIdx.x * blockDim.x + threadIdx.x;
   float sc[8], sh[8], mu[8], is[8];
@@ -277,7 +301,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
     load8(mean_invstd + cv0 * 8, mu);
     load8(mean_invstd + c + cv0 * 8, is);
   }
-  rows_reduce<T, 2>(rows, c, rows_per_block, sums, [&](long long r, int ch, float(&acc)[2][8]) {
+  rows_reduce_slots<T, 2>(rows, c, rows_per_block, slots, [&](long long r, int ch, float(&acc)[2][8]) {
     float f[8], g[8];
     load8(y + r * c + ch, f);
     load8(dout + r * c + ch, g);
@@ -288,9 +312,12 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
       acc[1][i] += dz * (f[i] - mu[i]) * is[i];
     }
   });
+  if (!take_ticket(bn_ticket(scratch, c, groups))) return;
+  bn_backward_finalize(scratch, c, groups, dgamma, dbeta, threadIdx.y * blockDim.x + threadIdx.x,
+                       blockDim.x * blockDim.y);
 }
 
-// Backward pass 2: dy = gamma * invstd * (dz - mean(dz) - xhat * mean(dz * xhat))
+// Backward consumer: dy = gamma * invstd * (dz - mean(dz) - xhat * mean(dz * xhat)); sums = [groups][2][c]
 template <typename T>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout,
                                                            const T* __restrict__ y, long long rows, int c,
@@ -340,223 +367,166 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
   }
 }
 
-// sums[0][c] = sum dz, sums[1][c] = sum dz*xhat from the block partials; dgamma += sums[1], dbeta += sums[0]
-// (accumulating, like autograd's AccumulateGrad)
-__global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __restrict__ partials, int nparts, int c,
-                                                                float* __restrict__ sums, float* __restrict__ dgamma,
-                                                                float* __restrict__ dbeta, int groups) {
-  const int ch = blockIdx.x * 32 + threadIdx.x;
+// ---- small-row BatchNorm (rows <= kBn1dMaxRows; BatchNorm1d behind the Linear layers, model.py:462,468,492):
+// ONE launch, one block = 32 channels x all rows, exact two-pass variance (what torch computes), running statistics,
+// normalise + activation.  blockDim (4, 64): thread (x, y) holds rows y, y+64, y+128, y+192 of channels 8x .. 8x+7.
+// Groups (stacked passes) are processed in order by the same block.
+__device__ __forceinline__ void bn1d_block_sum(float (&v)[8], float (*red)[33], float* stat) {
+  // sum over the 64 y-threads of each of the block's 32 channels; result broadcast through stat[32]
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[threadIdx.y][threadIdx.x * 8 + i] = v[i];
+  __syncthreads();
+  const int tid = threadIdx.y * 4 + threadIdx.x;
+  if (tid < 32) {
+    float s = 0.f;
+#pragma unroll 8
+    for (int yy = 0; yy < 64; ++yy) s += red[yy][tid];
+    stat[tid] = s;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = stat[threadIdx.x * 8 + i];
+  __syncthreads();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn1d_fwd_kernel(const T* __restrict__ y, int rows, int c, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, float* running_mean,
+                                                       float* running_var, long long* num_batches_tracked, float momentum,
+                                                       float eps, int act, float slope, float* __restrict__ scale_shift,
+                                                       float* __restrict__ mean_invstd, __nv_bfloat16* __restrict__ out,
+                                                       int groups) {
+  __shared__ float red[64][33];
+  __shared__ float stat[32];
+  const int ch = (blockIdx.x * 4 + threadIdx.x) * 8;  // c is a multiple of 32: every thread is live
   for (int g = 0; g < groups; ++g) {
-    float sum[2];
-    // the partials block of a group has nparts + 1 rows (the last one is unused here: see dm_bn_parts)
-    sum_partials_block<2>(partials + static_cast<long long>(g) * (nparts + 1) * 2 * c, nparts, 2ll * c, ch, ch < c, c, sum);
-    __syncthreads();
-    if (threadIdx.y != 0 || ch >= c) continue;
-    sums[static_cast<long long>(g) * 2 * c + ch] = sum[0];
-    sums[static_cast<long long>(g) * 2 * c + c + ch] = sum[1];
-    if (dgamma) dgamma[ch] += sum[1];
-    if (dbeta) dbeta[ch] += sum[0];
-  }
-}
-
-// ------------------------------------------------------------------------------------------ fused BatchNorm passes
-// One COOPERATIVE launch per BatchNorm application instead of three kernels: (1) every block reduces its rows into a
-// partial vector, (2) grid barrier, (3) every thread sums the gridDim.y partial vectors of ITS 8 channels (the ty
-// threads of a channel column split the partials and combine through shared memory) and derives the per-channel
-// constants, (4) every block normalises its rows (second read of y comes from L2: these tensors are far smaller than
-// the 126 MB L2).  Saves two launches + two pipeline drains per BatchNorm and the finalize kernel's serial tail.
-//
-// Grid barrier: sense-reversal on two words of a per-launch slot (launches on one stream are ordered, a captured
-// graph keeps its slot).  All blocks are co-resident because the kernel is launched cooperatively.
-__device__ __forceinline__ void grid_barrier(unsigned int* slot, unsigned int nblocks) {
-  __syncthreads();
-  if (threadIdx.x == 0 && threadIdx.y == 0) {
-    volatile unsigned int* gen = slot + 1;
-    const unsigned int my_gen = *gen;
-    __threadfence();
-    if (atomicAdd(slot, 1u) == nblocks - 1u) {
-      slot[0] = 0u;
-      __threadfence();
-      atomicAdd(slot + 1, 1u);
-    } else {
-      while (*gen == my_gen) {
+    const T* yg = y + static_cast<long long>(g) * rows * c;
+    __nv_bfloat16* og = out + static_cast<long long>(g) * rows * c;
+    float v[4][8];
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = threadIdx.y + 64 * j;
+      if (r < rows) {
+        load8(yg + static_cast<long long>(r) * c + ch, v[j]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] += v[j][i];
       }
     }
-    __threadfence();
-  }
-  __syncthreads();
-}
-
-// Totals of NACC accumulators for this thread's 8 channels from the gridDim.y block partials written by rows_reduce.
-template <int NACC>
-__device__ __forceinline__ void column_totals(const float* partials, int nparts, int c, int cv, bool live,
-                                              float (&tot)[NACC][8]) {
-  extern __shared__ float red[];  // [ty][tx*8*NACC] (reused: rows_reduce is done with it after the barrier)
-  const int tx = blockDim.x, ty = blockDim.y;
-  float acc[NACC][8];
+    bn1d_block_sum(s, red, stat);
+    float mean[8], q[8];
 #pragma unroll
-  for (int a = 0; a < NACC; ++a)
+    for (int i = 0; i < 8; ++i) {
+      mean[i] = s[i] / static_cast<float>(rows);
+      q[i] = 0.f;
+    }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[a][i] = 0.f;
-  if (live) {
-    for (int p = threadIdx.y; p < nparts; p += ty) {
+    for (int j = 0; j < 4; ++j)
+      if (threadIdx.y + 64 * j < rows) {
 #pragma unroll
-      for (int a = 0; a < NACC; ++a) {
+        for (int i = 0; i < 8; ++i) {
+          const float d = v[j][i] - mean[i];
+          q[i] += d * d;
+        }
+      }
+    bn1d_block_sum(q, red, stat);
+    float sc[8], sh[8], is[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float var = q[i] / static_cast<float>(rows);
+      is[i] = rsqrtf(var + eps);
+      sc[i] = gamma[ch + i] * is[i];
+      sh[i] = beta[ch + i] - mean[i] * sc[i];
+      if (threadIdx.y == 0 && running_mean) {
+        const float unbiased = rows > 1 ? var * static_cast<float>(rows) / static_cast<float>(rows - 1) : var;
+        running_mean[ch + i] = (1.f - momentum) * running_mean[ch + i] + momentum * mean[i];
+        running_var[ch + i] = (1.f - momentum) * running_var[ch + i] + momentum * unbiased;
+      }
+    }
+    if (threadIdx.y == 0) {
+      float* ss = scale_shift + static_cast<long long>(g) * 2 * c;
+      float* mi = mean_invstd + static_cast<long long>(g) * 2 * c;
+      store8(ss + ch, sc);
+      store8(ss + c + ch, sh);
+      store8(mi + ch, mean);
+      store8(mi + c + ch, is);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = threadIdx.y + 64 * j;
+      if (r < rows) {
         float f[8];
-        // plain (coherent) loads: the partials were written by other blocks of this same launch
-        const float4* src = reinterpret_cast<const float4*>(partials + (static_cast<long long>(p) * NACC + a) * c + cv * 8);
-        const float4 u = __ldcg(src), w = __ldcg(src + 1);
-        f[0] = u.x; f[1] = u.y; f[2] = u.z; f[3] = u.w; f[4] = w.x; f[5] = w.y; f[6] = w.z; f[7] = w.w;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[a][i] += f[i];
+        for (int i = 0; i < 8; ++i) f[i] = act_fwd(v[j][i] * sc[i] + sh[i], act, slope);
+        store8(og + static_cast<long long>(r) * c + ch, f);
       }
     }
   }
-  float* mine = red + (threadIdx.y * tx + threadIdx.x) * (8 * NACC);
-#pragma unroll
-  for (int a = 0; a < NACC; ++a)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) mine[a * 8 + i] = acc[a][i];
-  __syncthreads();
-#pragma unroll
-  for (int a = 0; a < NACC; ++a)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float sum = 0.f;
-      for (int y = 0; y < ty; ++y) sum += red[(y * tx + threadIdx.x) * (8 * NACC) + a * 8 + i];
-      tot[a][i] = sum;
-    }
-  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0 && num_batches_tracked) *num_batches_tracked += groups;
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) bn_fwd_fused_kernel(const T* __restrict__ y, long long rows, int c,
-                                                           long long rows_per_block, const float* __restrict__ gamma,
-                                                           const float* __restrict__ beta, float* __restrict__ running_mean,
-                                                           float* __restrict__ running_var,
-                                                           long long* __restrict__ num_batches_tracked, float momentum,
-                                                           float eps, int act, float slope, float* __restrict__ partials,
-                                                           float* __restrict__ scale_shift, float* __restrict__ mean_invstd,
-                                                           __nv_bfloat16* __restrict__ out, unsigned int* barrier) {
-  const int cv = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = cv * 8 < c;
-  float k[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // per-channel shift = row 0 (see bn_stats_kernel)
-  if (live) load8(y + cv * 8, k);
-  rows_reduce<T, 2>(rows, c, rows_per_block, partials, [&](long long r, int ch, float(&acc)[2][8]) {
-    float f[8];
-    load8(y + r * c + ch, f);
+__global__ void __launch_bounds__(256) bn1d_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const T* __restrict__ y,
+                                                       int rows, int c, const float* __restrict__ scale_shift,
+                                                       const float* __restrict__ mean_invstd, int act, float slope,
+                                                       __nv_bfloat16* __restrict__ dy, float* dgamma, float* dbeta,
+                                                       int groups) {
+  __shared__ float red[64][33];
+  __shared__ float stat[32];
+  const int ch = (blockIdx.x * 4 + threadIdx.x) * 8;
+  float gsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int g = 0; g < groups; ++g) {
+    const long long off = static_cast<long long>(g) * rows * c;
+    const float* ss = scale_shift + static_cast<long long>(g) * 2 * c;
+    const float* mi = mean_invstd + static_cast<long long>(g) * 2 * c;
+    float sc[8], sh[8], mu[8], is[8];
+    load8(ss + ch, sc);
+    load8(ss + c + ch, sh);
+    load8(mi + ch, mu);
+    load8(mi + c + ch, is);
+    float dz[4][8], xh[4][8];
+    float a0[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, a1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = threadIdx.y + 64 * j;
+      if (r < rows) {
+        float f[8], gg[8];
+        load8(y + off + static_cast<long long>(r) * c + ch, f);
+        load8(dout + off + static_cast<long long>(r) * c + ch, gg);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          dz[j][i] = gg[i] * act_grad(f[i] * sc[i] + sh[i], act, slope);
+          xh[j][i] = (f[i] - mu[i]) * is[i];
+          a0[i] += dz[j][i];
+          a1[i] += dz[j][i] * xh[j][i];
+        }
+      }
+    }
+    bn1d_block_sum(a0, red, stat);
+    bn1d_block_sum(a1, red, stat);
+    const float inv_n = 1.f / static_cast<float>(rows);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float d = f[i] - k[i];
-      acc[0][i] += d;
-      acc[1][i] += d * d;
+      gsum[i] += a1[i];
+      bsum[i] += a0[i];
     }
-  });
-  grid_barrier(barrier, gridDim.x * gridDim.y);
-  float tot[2][8];
-  column_totals<2>(partials, gridDim.y, c, cv, live, tot);
-  if (!live) return;
-  float sc[8], sh[8], mu[8], is[8];
-  const double n = static_cast<double>(rows);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const double dmean = tot[0][i] / n;
-    const double mean = static_cast<double>(k[i]) + dmean;
-    double var = tot[1][i] / n - dmean * dmean;
-    if (var < 0.0) var = 0.0;
-    const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-    const int ch = cv * 8 + i;
-    sc[i] = gamma[ch] * invstd;
-    sh[i] = beta[ch] - static_cast<float>(mean) * sc[i];
-    mu[i] = static_cast<float>(mean);
-    is[i] = invstd;
-    if (blockIdx.y == 0 && threadIdx.y == 0 && running_mean) {
-      const double unbiased = rows > 1 ? var * n / (n - 1.0) : var;
-      running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * static_cast<float>(mean);
-      running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * static_cast<float>(unbiased);
+    for (int j = 0; j < 4; ++j) {
+      const int r = threadIdx.y + 64 * j;
+      if (r < rows) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = sc[i] * (dz[j][i] - a0[i] * inv_n - xh[j][i] * a1[i] * inv_n);
+        store8(dy + off + static_cast<long long>(r) * c + ch, o);
+      }
     }
   }
-  if (blockIdx.y == 0 && threadIdx.y == 0) {
-    store8(scale_shift + cv * 8, sc);
-    store8(scale_shift + c + cv * 8, sh);
-    store8(mean_invstd + cv * 8, mu);
-    store8(mean_invstd + c + cv * 8, is);
-    if (cv == 0 && num_batches_tracked) *num_batches_tracked += 1;
-  }
-  const long long r0 = blockIdx.y * rows_per_block;
-  const long long r1 = min(rows, r0 + rows_per_block);
-#pragma unroll 4
-  for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
-    float f[8];
-    load8(y + r * c + cv * 8, f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) f[i] = act_fwd(f[i] * sc[i] + sh[i], act, slope);
-    store8(out + r * c + cv * 8, f);
-  }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256) bn_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dout, const T* __restrict__ y,
-                                                           long long rows, int c, long long rows_per_block,
-                                                           const float* __restrict__ scale_shift,
-                                                           const float* __restrict__ mean_invstd, int act, float slope,
-                                                           float* __restrict__ partials, float* __restrict__ sums,
-                                                           __nv_bfloat16* __restrict__ dy, float* __restrict__ dgamma,
-                                                           float* __restrict__ dbeta, unsigned int* barrier) {
-  const int cv = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = cv * 8 < c;
-  float sc[8], sh[8], mu[8], is[8];
-  if (live) {
-    load8(scale_shift + cv * 8, sc);
-    load8(scale_shift + c + cv * 8, sh);
-    load8(mean_invstd + cv * 8, mu);
-    load8(mean_invstd + c + cv * 8, is);
-  }
-  rows_reduce<T, 2>(rows, c, rows_per_block, partials, [&](long long r, int ch, float(&acc)[2][8]) {
-    float f[8], g[8];
-    load8(y + r * c + ch, f);
-    load8(dout + r * c + ch, g);
+  if (threadIdx.y == 0) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float dz = g[i] * act_grad(f[i] * sc[i] + sh[i], act, slope);
-      acc[0][i] += dz;
-      acc[1][i] += dz * (f[i] - mu[i]) * is[i];
+      if (dgamma) dgamma[ch + i] += gsum[i];
+      if (dbeta) dbeta[ch + i] += bsum[i];
     }
-  });
-  grid_barrier(barrier, gridDim.x * gridDim.y);
-  float tot[2][8];
-  column_totals<2>(partials, gridDim.y, c, cv, live, tot);
-  if (!live) return;
-  if (blockIdx.y == 0 && threadIdx.y == 0) {
-    store8(sums + cv * 8, tot[0]);
-    store8(sums + c + cv * 8, tot[1]);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (dgamma) dgamma[cv * 8 + i] += tot[1][i];
-      if (dbeta) dbeta[cv * 8 + i] += tot[0][i];
-    }
-  }
-  const float inv_n = 1.f / static_cast<float>(rows);
-  float s0[8], s1[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    s0[i] = tot[0][i] * inv_n;
-    s1[i] = tot[1][i] * inv_n;
-  }
-  const long long r0 = blockIdx.y * rows_per_block;
-  const long long r1 = min(rows, r0 + rows_per_block);
-#pragma unroll 4
-  for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
-    float f[8], g[8];
-    load8(y + r * c + cv * 8, f);
-    load8(dout + r * c + cv * 8, g);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float dz = g[i] * act_grad(f[i] * sc[i] + sh[i], act, slope);
-      const float xh = (f[i] - mu[i]) * is[i];
-      g[i] = sc[i] * (dz - s0[i] - xh * s1[i]);  // sc = gamma * invstd
-    }
-    store8(dy + r * c + cv * 8, g);
   }
 }
 
@@ -1059,46 +1029,32 @@ typedef __nv_bfloat16 bf16;
 
 #define DM_CHECK_C8(c, who) DM_REQUIRE((c) % 8 == 0, who ": channel count %d must be a multiple of 8", (c))
 
-// rows of the [parts][2][c] scratch handed to dm_bn_stats / dm_bn_finalize / dm_bn_forward / dm_bn_backward: one per
-// row block plus one that carries the per-channel shift of the shifted-sum statistics
+// rows of the [parts][c] partial-sum scratch handed to dm_act_backward / dm_colsum (one per row block)
 extern "C" int dm_bn_parts(long long rows, int c) { return make_row_layout(rows, c).gy + 1; }
 
-static int bn_stats_g(const void* y, int y_f32, long long rows, int c, float* partials, int groups, void* stream_) {
+extern "C" int dm_bn_slots(void) { return kBnSlots; }
+extern "C" long long dm_bn_scratch_floats(int c, int groups) { return bn_scratch_floats(c, groups); }
+
+extern "C" int dm_bn_stats(const void* y, int y_f32, int c, const dm_bn_fuse* f, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   DM_CHECK_C8(c, "dm_bn_stats");
-  RowLayout l = make_row_layout(rows, c);
+  DM_REQUIRE(f != nullptr && f->scratch != nullptr && f->groups >= 1 && f->rows > 0 && f->gamma && f->beta &&
+                 f->scale_shift && f->mean_invstd,
+             "dm_bn_stats: incomplete dm_bn_fuse");
+  RowLayout l = make_row_layout(f->rows, c);
   const size_t sm = sizeof(float) * 256 * 16;
   if (y_f32)
-    bn_stats_kernel<float><<<dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), sm, s>>>(static_cast<const float*>(y), rows, c, l.rows_per_block, partials);
+    bn_stats_kernel<float><<<dim3(l.gx, l.gy, f->groups), dim3(l.tx, l.ty), sm, s>>>(static_cast<const float*>(y), c, l.rows_per_block, *f);
   else
-    bn_stats_kernel<bf16><<<dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), sm, s>>>(static_cast<const bf16*>(y), rows, c, l.rows_per_block, partials);
+    bn_stats_kernel<bf16><<<dim3(l.gx, l.gy, f->groups), dim3(l.tx, l.ty), sm, s>>>(static_cast<const bf16*>(y), c, l.rows_per_block, *f);
   DM_LAUNCHED("dm_bn_stats");
 }
-extern "C" int dm_bn_stats(const void* y, int y_f32, long long rows, int c, float* partials, void* stream_) {
-  return bn_stats_g(y, y_f32, rows, c, partials, 1, stream_);
-}
 
-static int bn_finalize_g(const float* partials, int nparts, long long rows, int c, const float* gamma,
-                         const float* beta, float* running_mean, float* running_var,
-                         long long* num_batches_tracked, float momentum, float eps, float* scale_shift,
-                         float* mean_invstd, int groups, void* stream_) {
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-  bn_finalize_kernel<<<(c + 31) / 32, dim3(32, 32), 0, s>>>(partials, nparts, rows, c, gamma, beta, running_mean, running_var,
-                                                     num_batches_tracked, momentum, eps, scale_shift, mean_invstd, groups);
-  DM_LAUNCHED("dm_bn_finalize");
-}
-extern "C" int dm_bn_finalize(const float* partials, int nparts, long long rows, int c, const float* gamma,
-                              const float* beta, float* running_mean, float* running_var,
-                              long long* num_batches_tracked, float momentum, float eps, float* scale_shift,
-                              float* mean_invstd, void* stream_) {
-  return bn_finalize_g(partials, nparts, rows, c, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps,
-                       scale_shift, mean_invstd, 1, stream_);
-}
-
-static int bn_apply_act_g(const void* y, int y_f32, long long rows, int c, const float* scale_shift, int act,
-                          float slope, void* out_bf16, int groups, void* stream_) {
+extern "C" int dm_bn_apply_act(const void* y, int y_f32, long long rows, int c, const float* scale_shift, int act,
+                               float slope, void* out_bf16, int groups, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   DM_CHECK_C8(c, "dm_bn_apply_act");
+  DM_REQUIRE(groups >= 1, "dm_bn_apply_act: groups must be >= 1");
   RowLayout l = make_row_layout(rows, c);
   if (y_f32)
     bn_apply_act_kernel<float><<<dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), 0, s>>>(static_cast<const float*>(y), rows, c, l.rows_per_block, scale_shift, act, slope, static_cast<bf16*>(out_bf16));
@@ -1106,150 +1062,72 @@ static int bn_apply_act_g(const void* y, int y_f32, long long rows, int c, const
     bn_apply_act_kernel<bf16><<<dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), 0, s>>>(static_cast<const bf16*>(y), rows, c, l.rows_per_block, scale_shift, act, slope, static_cast<bf16*>(out_bf16));
   DM_LAUNCHED("dm_bn_apply_act");
 }
-extern "C" int dm_bn_apply_act(const void* y, int y_f32, long long rows, int c, const float* scale_shift, int act,
-                               float slope, void* out_bf16, void* stream_) {
-  return bn_apply_act_g(y, y_f32, rows, c, scale_shift, act, slope, out_bf16, 1, stream_);
+
+static bool bn1d_ok(long long rows, int c) {
+  static const bool on = [] { const char* e = getenv("DM_BN1D"); return !e || e[0] != '0'; }();
+  return on && rows <= kBn1dMaxRows && c % 32 == 0;
 }
 
-// ---- cooperative launches of the fused BatchNorm kernels
-// Barrier slots: 2 words per launch out of a small per-device pool (zeroed once); launches take slots round-robin, so
-// two fused launches that could overlap (different streams) practically never share one, and a captured graph keeps
-// the slots it was captured with.
-static unsigned int* barrier_slot() {
-  static std::mutex mu;
-  static unsigned int* pool[64] = {nullptr};
-  static std::atomic<unsigned int> next{0};
-  constexpr unsigned int kSlots = 4096;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64) return nullptr;
-  {
-    std::lock_guard<std::mutex> lk(mu);
-    if (!pool[dev]) {
-      unsigned int* p = nullptr;
-      if (cudaMalloc(&p, kSlots * 2 * sizeof(unsigned int)) != cudaSuccess) return nullptr;
-      cudaMemset(p, 0, kSlots * 2 * sizeof(unsigned int));
-      cudaDeviceSynchronize();
-      pool[dev] = p;
-    }
-  }
-  return pool[dev] + 2 * (next.fetch_add(1, std::memory_order_relaxed) % kSlots);
-}
-
-template <typename K>
-static int max_coresident_blocks(K kernel, size_t smem) {
-  int per_sm = 0, dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem) != cudaSuccess) return 0;
-  return per_sm * sms;
-}
-
-template <typename K, typename... Args>
-static cudaError_t launch_coop(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;
-  attr[0].val.cooperative = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, args...);
-}
-
-// DM_BN_FUSED: unset / 0 = three-kernel paths (default), 1 = both passes as single cooperative launches, 2 = forward
-// only, 3 = backward only.  Measured on B200 (round 1, whole step in a CUDA graph, batch 64): the cooperative
-// launches cost ~27 us EACH more than the three plain kernels they replace (7.49 vs 5.70 ms/step), so the fused
-// kernels stay off; they are kept, tested, as the starting point for a non-cooperative variant.
-static bool fused_bn_enabled(bool forward = true) {
-  const char* e = getenv("DM_BN_FUSED");
-  if (!e) return false;
-  if (e[0] == '0') return false;
-  if (e[0] == '2') return forward;
-  if (e[0] == '3') return !forward;
-  return true;
-}
-
-// BatchNorm forward in one launch: statistics + running-stat update + normalise + activation.  `partials` is
-// [dm_bn_parts(rows, c)][2][c] scratch; scale_shift / mean_invstd ([2][c] each) are saved for the backward pass.
+// BatchNorm forward (training mode) + activation: statistics + normalisation + running-stat update.
+//   rows <= 256: ONE launch (bn1d_fwd_kernel, exact two-pass variance; `scratch` unused, may be NULL);
+//   otherwise:   bn_stats_kernel (slot partial sums, shift = running_mean, finalize by its last block) + bn_apply_act.
 extern "C" int dm_bn_forward(const void* y, int y_f32, long long rows, int c, const float* gamma, const float* beta,
                              float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
-                             float eps, int act, float slope, float* partials, float* scale_shift, float* mean_invstd,
+                             float eps, int act, float slope, float* scratch, float* scale_shift, float* mean_invstd,
                              void* out_bf16, int groups, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   DM_CHECK_C8(c, "dm_bn_forward");
   DM_REQUIRE(groups >= 1, "dm_bn_forward: groups must be >= 1");
-  RowLayout l = make_row_layout(rows, c);
-  const size_t sm = sizeof(float) * 256 * 16;
-  static int cap_f32 = -1, cap_bf16 = -1;
-  if (cap_f32 < 0) cap_f32 = max_coresident_blocks(bn_fwd_fused_kernel<float>, sm);
-  if (cap_bf16 < 0) cap_bf16 = max_coresident_blocks(bn_fwd_fused_kernel<bf16>, sm);
-  unsigned int* slot = (groups == 1 && fused_bn_enabled()) ? barrier_slot() : nullptr;
-  const int cap = y_f32 ? cap_f32 : cap_bf16;
-  if (slot && l.gx * l.gy <= cap) {
-    cudaError_t e;
+  if (bn1d_ok(rows, c)) {
     if (y_f32)
-      e = launch_coop(bn_fwd_fused_kernel<float>, dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s, static_cast<const float*>(y), rows, c,
-                      l.rows_per_block, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, act, slope,
-                      partials, scale_shift, mean_invstd, static_cast<bf16*>(out_bf16), slot);
+      bn1d_fwd_kernel<float><<<c / 32, dim3(4, 64), 0, s>>>(static_cast<const float*>(y), static_cast<int>(rows), c, gamma, beta,
+                                                           running_mean, running_var, num_batches_tracked, momentum, eps, act,
+                                                           slope, scale_shift, mean_invstd, static_cast<bf16*>(out_bf16), groups);
     else
-      e = launch_coop(bn_fwd_fused_kernel<bf16>, dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s, static_cast<const bf16*>(y), rows, c,
-                      l.rows_per_block, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, act, slope,
-                      partials, scale_shift, mean_invstd, static_cast<bf16*>(out_bf16), slot);
-    if (e != cudaSuccess) return set_error((int)e, "dm_bn_forward: cooperative launch: %s", cudaGetErrorString(e));
-    DM_LAUNCHED("dm_bn_forward");
+      bn1d_fwd_kernel<bf16><<<c / 32, dim3(4, 64), 0, s>>>(static_cast<const bf16*>(y), static_cast<int>(rows), c, gamma, beta,
+                                                          running_mean, running_var, num_batches_tracked, momentum, eps, act,
+                                                          slope, scale_shift, mean_invstd, static_cast<bf16*>(out_bf16), groups);
+    DM_LAUNCHED("dm_bn_forward(1d)");
   }
-  // three-kernel path (grid too large to be co-resident, or DM_BN_FUSED=0)
-  if (int rc = bn_stats_g(y, y_f32, rows, c, partials, groups, stream_)) return rc;
-  if (int rc = bn_finalize_g(partials, l.gy + 1, rows, c, gamma, beta, running_mean, running_var, num_batches_tracked, momentum,
-                             eps, scale_shift, mean_invstd, groups, stream_))
-    return rc;
-  return bn_apply_act_g(y, y_f32, rows, c, scale_shift, act, slope, out_bf16, groups, stream_);
+  DM_REQUIRE(scratch != nullptr, "dm_bn_forward: scratch required for rows > %d", kBn1dMaxRows);
+  dm_bn_fuse f;
+  f.scratch = scratch; f.groups = groups; f.rows = rows; f.gamma = gamma; f.beta = beta;
+  f.running_mean = running_mean; f.running_var = running_var; f.num_batches_tracked = num_batches_tracked;
+  f.momentum = momentum; f.eps = eps; f.scale_shift = scale_shift; f.mean_invstd = mean_invstd;
+  if (int rc = dm_bn_stats(y, y_f32, c, &f, stream_)) return rc;
+  return dm_bn_apply_act(y, y_f32, rows, c, scale_shift, act, slope, out_bf16, groups, stream_);
 }
 
 extern "C" int dm_bn_backward(const void* dout_bf16, const void* y, int y_f32, long long rows, int c,
                               const float* scale_shift, const float* mean_invstd, int act, float slope,
-                              float* partials, float* sums, void* dy_bf16, float* dgamma, float* dbeta, int groups,
+                              float* scratch, void* dy_bf16, float* dgamma, float* dbeta, int groups,
                               void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   DM_CHECK_C8(c, "dm_bn_backward");
   DM_REQUIRE(groups >= 1, "dm_bn_backward: groups must be >= 1");
+  const bf16* d = static_cast<const bf16*>(dout_bf16);
+  if (bn1d_ok(rows, c)) {
+    if (y_f32)
+      bn1d_bwd_kernel<float><<<c / 32, dim3(4, 64), 0, s>>>(d, static_cast<const float*>(y), static_cast<int>(rows), c, scale_shift,
+                                                           mean_invstd, act, slope, static_cast<bf16*>(dy_bf16), dgamma, dbeta, groups);
+    else
+      bn1d_bwd_kernel<bf16><<<c / 32, dim3(4, 64), 0, s>>>(d, static_cast<const bf16*>(y), static_cast<int>(rows), c, scale_shift,
+                                                          mean_invstd, act, slope, static_cast<bf16*>(dy_bf16), dgamma, dbeta, groups);
+    DM_LAUNCHED("dm_bn_backward(1d)");
+  }
+  DM_REQUIRE(scratch != nullptr, "dm_bn_backward: scratch required for rows > %d", kBn1dMaxRows);
   RowLayout l = make_row_layout(rows, c);
   const size_t sm = sizeof(float) * 256 * 16;
-  const bf16* d = static_cast<const bf16*>(dout_bf16);
-  {
-    static int cap_f32 = -1, cap_bf16 = -1;
-    if (cap_f32 < 0) cap_f32 = max_coresident_blocks(bn_bwd_fused_kernel<float>, sm);
-    if (cap_bf16 < 0) cap_bf16 = max_coresident_blocks(bn_bwd_fused_kernel<bf16>, sm);
-    unsigned int* slot = (groups == 1 && fused_bn_enabled(false)) ? barrier_slot() : nullptr;
-    if (slot && l.gx * l.gy <= (y_f32 ? cap_f32 : cap_bf16)) {
-      cudaError_t e;
-      if (y_f32)
-        e = launch_coop(bn_bwd_fused_kernel<float>, dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s, d, static_cast<const float*>(y), rows, c,
-                        l.rows_per_block, scale_shift, mean_invstd, act, slope, partials, sums, static_cast<bf16*>(dy_bf16), dgamma,
-                        dbeta, slot);
-      else
-        e = launch_coop(bn_bwd_fused_kernel<bf16>, dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s, d, static_cast<const bf16*>(y), rows, c,
-                        l.rows_per_block, scale_shift, mean_invstd, act, slope, partials, sums, static_cast<bf16*>(dy_bf16), dgamma,
-                        dbeta, slot);
-      if (e != cudaSuccess) return set_error((int)e, "dm_bn_backward: cooperative launch: %s", cudaGetErrorString(e));
-      DM_LAUNCHED("dm_bn_backward");
-    }
-  }
+  const float* sums = scratch + bn_slot_floats(c, groups) + 4;
   if (y_f32)
-    bn_bwd_reduce_kernel<float><<<dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), sm, s>>>(d, static_cast<const float*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, act, slope, partials);
+    bn_bwd_reduce_kernel<float><<<dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), sm, s>>>(d, static_cast<const float*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, act, slope, scratch, dgamma, dbeta);
   else
-    bn_bwd_reduce_kernel<bf16><<<dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), sm, s>>>(d, static_cast<const bf16*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, act, slope, partials);
-  bn_bwd_finalize_kernel<<<(c + 31) / 32, dim3(32, 32), 0, s>>>(partials, l.gy, c, sums, dgamma, dbeta, groups);
+    bn_bwd_reduce_kernel<bf16><<<dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), sm, s>>>(d, static_cast<const bf16*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, act, slope, scratch, dgamma, dbeta);
   if (y_f32)
     bn_bwd_apply_kernel<float><<<dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), 0, s>>>(d, static_cast<const float*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, sums, act, slope, static_cast<bf16*>(dy_bf16));
   else
     bn_bwd_apply_kernel<bf16><<<dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), 0, s>>>(d, static_cast<const bf16*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, sums, act, slope, static_cast<bf16*>(dy_bf16));
-  g_launch_count.fetch_add(3, std::memory_order_relaxed);
+  g_launch_count.fetch_add(2, std::memory_order_relaxed);
   return check_launch("dm_bn_backward");
 }
 

@@ -27,6 +27,7 @@
 
 #include "../../include/dm_b200.h"
 #include "dm_common.h"
+#include "dm_bn_fin.cuh"
 #include "dm_ptx.cuh"
 
 namespace dm {
@@ -97,6 +98,15 @@ struct alignas(64) GemmParams {
   int bias_mod;          // != 0 (a power of two): bias index = column % bias_mod (phase-merged columns repeat the channels)
   int epi_row_step;      // mode 1: coordinate-1 origin of tile m (plain matrices: 128), 0 for pixel tiles
   int phase_c[4], phase_p[4];  // mode 1, transposed-conv phases: channel-coordinate offset (pw * cb) and row parity ph
+  // BatchNorm statistics fused into the FWD / epi_tma == 1 epilogue: per-channel shifted sums of the tile's VALID rows
+  // (fp32 accumulator + bias, before the bf16 rounding), added to slot scratch [group][kBnSlots][2][stat_c]; the last
+  // CTA to finish finalizes (dm_bn_fin.cuh)
+  float* stat_out;           // nullptr = off (= stat_fin.scratch)
+  const float* stat_shift;   // k[stat_c] (the layer's running_mean) or nullptr
+  int stat_c;                // channels, a power of two; column j is channel j & (stat_c - 1) (phase-merged columns wrap)
+  int stat_tiles_per_group;  // M tiles per stacked pass
+  int stat_groups;
+  dm_bn_fuse stat_fin;
 };
 
 constexpr int kThreads = 192;
@@ -105,6 +115,21 @@ constexpr int kAtomBytes = 8192;  // one MN-major atom: 64 k-rows x 128 B
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// v[i] of lane l = element (row l, column i) of a 32 x 32 block -> returns in v[0] of lane l the sum of COLUMN l over
+// the 32 rows: a transpose-reduce butterfly, 16 + 8 + 4 + 2 + 1 = 31 shuffles instead of 32 x 5.
+__device__ __forceinline__ void warp_column_sums(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool hi = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = hi ? v[i] : v[i + s];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, s);
+      v[i] = (hi ? v[i + s] : v[i]) + recv;
+    }
+  }
 }
 
 // One unit of work: a 128 x BN output tile and the k-block range that feeds it.
@@ -410,6 +435,26 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
     __nv_bfloat16* outh = reinterpret_cast<__nv_bfloat16*>(p.out);
     int it = 0;
     int ebuf = 0;  // TMA epilogue: staging buffer of the next box
+    // fused BatchNorm statistics: lane l holds this warp's running sums of column (32 * chunk + l) of the current
+    // (group, N tile) run in registers (bn <= 128: at most 4 chunks, selected by predication -- no indexed register
+    // array, no shared memory: the smem budget decides how many CTAs share an SM); flushed with one coalesced red.add
+    // per 32 columns when the run ends
+    float st_s0 = 0.f, st_s1 = 0.f, st_s2 = 0.f, st_s3 = 0.f, st_q0 = 0.f, st_q1 = 0.f, st_q2 = 0.f, st_q3 = 0.f;
+    int stat_key = -1;
+    auto stat_flush = [&](int key) {
+      const int g = key / p.num_n_tiles, nt = key - g * p.num_n_tiles;
+      float* dst = p.stat_out + (static_cast<long long>(g) * kBnSlots + ((blockIdx.x * 4 + q) % kBnSlots)) * 2 * p.stat_c;
+      for (int ci = 0; ci * 32 < p.bn; ++ci) {
+        const int col = nt * p.bn + ci * 32 + lane;
+        const float vs = ci == 0 ? st_s0 : (ci == 1 ? st_s1 : (ci == 2 ? st_s2 : st_s3));
+        const float vq = ci == 0 ? st_q0 : (ci == 1 ? st_q1 : (ci == 2 ? st_q2 : st_q3));
+        if (col < p.n_valid) {
+          atomicAdd(dst + (col & (p.stat_c - 1)), vs);
+          atomicAdd(dst + p.stat_c + (col & (p.stat_c - 1)), vq);
+        }
+      }
+      st_s0 = st_s1 = st_s2 = st_s3 = st_q0 = st_q1 = st_q2 = st_q3 = 0.f;
+    };
     for (int t = t_begin; t < p.total_tiles; t += t_step) {
       const TileWork w = decode_tile(p, t, crank);
       if (w.kb0 >= w.kb1) continue;
@@ -436,6 +481,19 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
         const uint32_t row_addr = static_cast<uint32_t>(lane * row_bytes);
         int piece = 0;  // 16-byte piece index within the staging row
         int boxc = 0;   // first column (within the tile) of the box being filled
+        bool stat_row_ok = false;
+        if (p.stat_out) {
+          const int g = min(m_tile / p.stat_tiles_per_group, p.stat_groups - 1);
+          const int key = g * p.num_n_tiles + n_tile;
+          if (key != stat_key) {
+            if (stat_key >= 0) stat_flush(stat_key);
+            stat_key = key;
+          }
+          const int rr = rq + lane;  // this thread's row of the tile
+          const int wx = m_tile * p.tw_step + rr % p.bw;
+          const int nn = (m_tile / p.tpi) * p.tn_step + rr / (p.bw * p.bh);
+          stat_row_ok = (wx < p.w_lim) && (nn < p.n_lim);
+        }
         for (int c0 = 0; c0 < p.bn; c0 += 32) {
           uint32_t v[32];
           __syncwarp();  // tcgen05.ld is warp-collective
@@ -456,6 +514,25 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
                 const int bi = n_tile * p.bn + c0 + i;
                 v[i] = __float_as_uint(__uint_as_float(v[i]) + __ldg(p.bias + (bi & bias_mask)));
               }
+          }
+          if (p.stat_out) {
+            float d[32], d2[32];
+            const int smask = p.stat_c - 1;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int col = n_tile * p.bn + c0 + i;
+              const float kk = p.stat_shift ? __ldg(p.stat_shift + (col & smask)) : 0.f;
+              const float dv = (stat_row_ok && col < p.n_valid) ? __uint_as_float(v[i]) - kk : 0.f;
+              d[i] = dv;
+              d2[i] = dv * dv;
+            }
+            warp_column_sums(d, lane);
+            warp_column_sums(d2, lane);
+            const int ci = c0 >> 5;
+            st_s0 += ci == 0 ? d[0] : 0.f; st_q0 += ci == 0 ? d2[0] : 0.f;
+            st_s1 += ci == 1 ? d[0] : 0.f; st_q1 += ci == 1 ? d2[0] : 0.f;
+            st_s2 += ci == 2 ? d[0] : 0.f; st_q2 += ci == 2 ? d2[0] : 0.f;
+            st_s3 += ci == 3 ? d[0] : 0.f; st_q3 += ci == 3 ? d2[0] : 0.f;
           }
           if (piece == 0) {
             // the staging buffer about to be filled must have been read by the store issued epi_bufs boxes ago
@@ -690,6 +767,20 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
           mbar_arrive(&tmem_empty_bar[buf]);
       }
       ++it;
+    }
+    if (p.stat_out) {
+      // publish this CTA's partial sums, take a ticket; the LAST CTA of the grid finalizes the BatchNorm (constants for
+      // the consumer kernel, running statistics) and re-zeroes the scratch -- no finalize kernel
+      if (stat_key >= 0) stat_flush(stat_key);
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
+      if (q == 0 && lane == 0) {
+        const unsigned int tk = atomicAdd(bn_ticket(p.stat_out, p.stat_c, p.stat_groups), 1u);
+        tmem_ptr_smem[1] = (tk == gridDim.x - 1u) ? 1u : 0u;
+        __threadfence();
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (tmem_ptr_smem[1] != 0u) bn_forward_finalize(p.stat_fin, p.stat_c, q * 32 + lane, 128);
     }
     if (p.epi_tma && lane == 0) bulk_wait_group_all();  // smem must outlive the stores' reads; writes complete
   }
@@ -1054,6 +1145,26 @@ static bool epi_transposed_matrix(GemmParams& p, void* out, bool f32, long long 
   return true;
 }
 
+// Attach fused BatchNorm statistics (dm_bn_fuse) to a FWD launch whose epilogue is the row-store TMA path.
+// m_tiles = real M tiles; rows of a group must fill whole tiles.
+static int attach_stats(GemmParams& p, const dm_bn_fuse* bn, int channels, int m_tiles, const char* who) {
+  if (bn == nullptr || bn->scratch == nullptr) return 0;
+  DM_REQUIRE(bn->rows > 0 && bn->gamma && bn->beta && bn->scale_shift && bn->mean_invstd, "%s: incomplete dm_bn_fuse", who);
+  DM_REQUIRE(p.mode == MODE_FWD && p.epi_tma == 1 && p.num_splits == 1 && !p.fold_kw,
+             "%s: fused BatchNorm statistics need the row-store epilogue without split-K", who);
+  DM_REQUIRE(bn->groups >= 1 && m_tiles % bn->groups == 0, "%s: %d M tiles do not split into %d groups", who, m_tiles,
+             bn->groups);
+  DM_REQUIRE(channels > 0 && (channels & (channels - 1)) == 0, "%s: fused statistics need a power-of-two channel count", who);
+  DM_REQUIRE(p.bn <= 128, "%s: fused statistics support N tiles up to 128 columns", who);
+  p.stat_out = bn->scratch;
+  p.stat_shift = bn->running_mean;
+  p.stat_fin = *bn;
+  p.stat_c = channels;
+  p.stat_groups = bn->groups;
+  p.stat_tiles_per_group = m_tiles / bn->groups;
+  return 0;
+}
+
 static void init_params(GemmParams& p) {
   memset(&p, 0, sizeof(p));
   p.num_splits = 1;
@@ -1192,6 +1303,11 @@ extern "C" int dm_gemm_bf16(const dm_gemm_desc* g, void* stream_) {
     if (g->ldd_n == 1) epi_rows_matrix(p, g->d, g->d_f32 != 0, m_store, n_store, g->ldd_m, g->accumulate != 0, 0);
     DM_REQUIRE(splits <= p.cpt, "dm_gemm_bf16: splits %d > k-blocks %d", splits, p.cpt);
     grid = dim3((g->m + 127) / 128, p.num_n_tiles, splits);
+    if (g->bn.scratch) {
+      DM_REQUIRE(g->m % 128 == 0 && (g->m / 128) % std::max(1, g->bn.groups) == 0 && ((g->m / std::max(1, g->bn.groups)) % 128) == 0,
+                 "dm_gemm_bf16: fused statistics need whole 128-row tiles per group (m %d, groups %d)", g->m, g->bn.groups);
+      if (int rc2 = attach_stats(p, &g->bn, n_store, g->m / 128, "dm_gemm_bf16")) return rc2;
+    }
   } else if (g->layout == DM_GEMM_TN) {
     DM_REQUIRE(g->d_f32 || (g->ldd_m == 1 && !g->accumulate),
                "dm_gemm_bf16: TN (weight-gradient) output is fp32, or bf16 with unit row stride and no accumulation");
@@ -1259,8 +1375,15 @@ static void down_taps(const dm_conv_geom* g, Tap* taps) {
     }
 }
 
+// pixel tiles of a stacked batch split into `groups` passes of whole tiles?
+static bool groups_tile_aligned(const PixTile& pt, int batch, int groups) {
+  if (groups <= 1) return true;
+  if (batch % groups != 0 || pt.tiles % groups != 0) return false;
+  return pt.bimg <= 1 || (batch / groups) % pt.bimg == 0;
+}
+
 extern "C" int dm_conv_down(const dm_conv_geom* g, const void* big, const void* w_down, const float* bias,
-                            void* out_small, void* stream_) {
+                            void* out_small, const dm_bn_fuse* bn, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = check_geom(g, "dm_conv_down")) return rc;
   t_kind = 1;
@@ -1289,12 +1412,16 @@ extern "C" int dm_conv_down(const dm_conv_geom* g, const void* big, const void* 
   if (int rc = encode_w_map3(&p.map_b, w_down, 25, g->cs, g->cb, g->cb, p.kc, p.bn / cluster, p.kc * 2)) return rc;
   p.num_n_tiles = (g->cs + p.bn - 1) / p.bn;
   epi_rows_act(p, out_small, false, g->batch, g->hs, g->ws, g->cs, 1, pt);
+  if (bn && bn->scratch) {
+    DM_REQUIRE(groups_tile_aligned(pt, g->batch, bn->groups), "dm_conv_down: groups do not fall on tile boundaries");
+    if (int rc = attach_stats(p, bn, g->cs, pt.tiles, "dm_conv_down")) return rc;
+  }
   return launch(p, dim3(pt.tiles, p.num_n_tiles, 1), stream, 50.0 * g->batch * g->hs * g->ws * g->cs * g->cb, 1 << 30,
                 cluster);
 }
 
 extern "C" int dm_conv_up(const dm_conv_geom* g, const void* small, const void* w_up, const float* bias, void* out_big,
-                          int out_f32, void* stream_) {
+                          int out_f32, const dm_bn_fuse* bn, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = check_geom(g, "dm_conv_up")) return rc;
   t_kind = 2;
@@ -1368,6 +1495,11 @@ extern "C" int dm_conv_up(const dm_conv_geom* g, const void* small, const void* 
   if (int rc = encode_w_map3(&p.map_b, w_up, fold ? 5 : 25, cb_pad, g->cs, g->cs, p.kc, p.bn / cluster, p.kc * 2)) return rc;
   p.num_n_tiles = (cb_pad + p.bn - 1) / p.bn;
   if (!fold) epi_rows_act(p, out_big, out_f32 != 0, g->batch, g->hb, g->wb, g->cb, g->stride, pt);
+  if (bn && bn->scratch) {
+    DM_REQUIRE(groups_tile_aligned(pt, g->batch, bn->groups), "dm_conv_up: groups do not fall on tile boundaries");
+    DM_REQUIRE(cb_pad == g->cb, "dm_conv_up: fused statistics need cb %% 16 == 0");
+    if (int rc = attach_stats(p, bn, g->cb, pt.tiles, "dm_conv_up")) return rc;
+  }
   return launch(p, dim3(pt.tiles, p.num_n_tiles, nphase), stream, 50.0 * g->batch * g->hs * g->ws * g->cs * g->cb,
                 1 << 30, cluster);
 }
@@ -1377,7 +1509,7 @@ extern "C" int dm_conv_up(const dm_conv_geom* g, const void* small, const void* 
 // loaded 9 times instead of 25 and feeds 128-wide MMAs: the N = 32 form is bound by L2 -> smem operand traffic
 // (measured 15.6 TB/s, 21 % tensor-pipe), this one by the tensor pipe.  31 % of the MMA work multiplies zeros.
 extern "C" int dm_conv_up_merged(const dm_conv_geom* g, const void* small, const void* w_upm, const float* bias,
-                                 void* out_big, void* stream_) {
+                                 void* out_big, const dm_bn_fuse* bn, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = check_geom(g, "dm_conv_up_merged")) return rc;
   t_kind = 2;
@@ -1426,6 +1558,10 @@ extern "C" int dm_conv_up_merged(const dm_conv_geom* g, const void* small, const
   }
   p.epi_tma = 1; p.epi_reduce = 0; p.epi_merge = 1;
   p.epi_bw = pt.bw; p.epi_bh = pt.bh; p.epi_row_step = 0;
+  if (bn && bn->scratch) {  // the 128 columns are 4 phases x 32 channels: column j is channel j & 31
+    DM_REQUIRE(groups_tile_aligned(pt, g->batch, bn->groups), "dm_conv_up_merged: groups do not fall on tile boundaries");
+    if (int rc = attach_stats(p, bn, g->cb, pt.tiles, "dm_conv_up_merged")) return rc;
+  }
   return launch(p, dim3(pt.tiles, 1, 1), stream, 50.0 * g->batch * g->hs * g->ws * g->cs * g->cb, 1 << 30, cluster);
 }
 

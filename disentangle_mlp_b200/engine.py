@@ -31,6 +31,7 @@ class OperandCache:
     def __init__(self):
         self._c = {}
         self.wgrad_scratch = {}  # (weight name, device) -> zeroed [25][cs][cb] fp32 packed-gradient scratch
+        self.bn_scratch = {}  # (site, c, groups, device) -> BatchNorm slot scratch, zero between uses (ops.bn_scratch)
         self.static = False  # True: never rebuild implicitly (CUDA-graph mode); refresh() does it in place
 
     def get(self, key, param, builder):
@@ -73,13 +74,39 @@ class BNState:
     act: int
 
 
-def bn_act_forward(y, rows, c, P, B, prefix, act, training=True, groups=1):
+FUSE_BN_STATS = os.environ.get("DM_BN_FUSE_GEMM", "1") != "0"  # A/B: statistics in the producing GEMM's epilogue
+
+
+def _site_scratch(cache, site, c, groups, dev):
+    """The persistent slot scratch of one BatchNorm call site (zero between uses: the consumer kernel clears it)."""
+    key = (site, c, groups, str(dev))
+    sc = cache.bn_scratch.get(key)
+    if sc is None:
+        sc = cache.bn_scratch[key] = ops.bn_scratch(c, groups, dev)
+    return sc
+
+
+def bn_fuse(cache, P, B, prefix, c, groups, rows_per_group, dev, training=True, tile_rows=None):
+    """ops.BnSite for the GEMM that writes the pre-BatchNorm tensor of layer `prefix`, or None when the statistics
+    cannot ride in its epilogue (eval mode, passes that do not cover whole 128-row tiles, A/B switch).
+    rows_per_group: rows of the tensor per stacked pass; tile_rows: GEMM rows per pass if different (a transposed
+    convolution tiles its SMALL side: a quarter of the output pixels).
+    Pass the result to BOTH the GEMM (bn=...) and bn_act_forward (fused=...)."""
+    if not (training and FUSE_BN_STATS) or (tile_rows or rows_per_group) % 128 != 0:
+        return None
+    return ops.BnSite(_site_scratch(cache, prefix + "/f", c, groups, dev), groups, rows_per_group, c,
+                      P[prefix + ".weight"].detach(), P[prefix + ".bias"].detach(), B[prefix + ".running_mean"],
+                      B[prefix + ".running_var"], B[prefix + ".num_batches_tracked"], BN_MOMENTUM, BN_EPS)
+
+
+def bn_act_forward(y, rows, c, P, B, prefix, act, training=True, groups=1, cache=None, fused=None):
     """BatchNorm (batch statistics, running-stat update) + activation. P: params, B: buffers.
 
     groups > 1: `y` holds `groups` independent batches stacked along rows (several forward passes of the same
     network pushed through each GEMM together); statistics, normalisation and the running-stat updates are done
     per group, in order -- exactly what separate forward calls would do -- by ONE set of kernel launches
-    (blockIdx.z = group).  Returns (out, [BNState per group])."""
+    (blockIdx.z = group).  fused: the bn_fuse(...) site the producing GEMM was given (its epilogue produced the
+    statistics and its last CTA finalized them).  Returns (out, [BNState per group])."""
     gamma, beta = P[prefix + ".weight"], P[prefix + ".bias"]
     rm, rv, nbt = B[prefix + ".running_mean"], B[prefix + ".running_var"], B[prefix + ".num_batches_tracked"]
     rg = rows // groups
@@ -87,10 +114,17 @@ def bn_act_forward(y, rows, c, P, B, prefix, act, training=True, groups=1):
     out = torch.empty(y.shape, dtype=BF16, device=y.device)
     o2 = out.view(rows, c)
     if training:
-        _, ss, mi = ops.bn_forward(y2, rg, c, gamma.detach(), beta.detach(), rm, rv, nbt, act, LEAKY, BN_MOMENTUM, BN_EPS,
-                                   out=o2, groups=groups)
-        if groups == 1:
-            ss, mi = ss.unsqueeze(0), mi.unsqueeze(0)
+        if fused is not None:  # the GEMM's last CTA has already finalized: constants are in fused.scale_shift
+            ss, mi = fused.scale_shift, fused.mean_invstd
+            ops.bn_apply_act(y2, rg, c, ss, act, LEAKY, out=o2, groups=groups)
+        else:
+            sc = None
+            if rg > ops.BN1D_MAX_ROWS and cache is not None:
+                sc = _site_scratch(cache, prefix + "/f", c, groups, y.device)
+            _, ss, mi = ops.bn_forward(y2, rg, c, gamma.detach(), beta.detach(), rm, rv, nbt, act, LEAKY, BN_MOMENTUM,
+                                       BN_EPS, out=o2, groups=groups, scratch=sc)
+            if groups == 1:
+                ss, mi = ss.unsqueeze(0), mi.unsqueeze(0)
         return out, [BNState(y2[g * rg:(g + 1) * rg], rg, c, ss[g], mi[g], act) for g in range(groups)]
     states = []
     for g in range(groups):  # inference statistics (the reference scripts never call .eval(); kept for completeness)
@@ -120,7 +154,7 @@ def _stacked(states):
     return True
 
 
-def bn_act_backward(dout, states, G, prefix):
+def bn_act_backward(dout, states, G, prefix, cache=None):
     """Backward of bn_act_forward over the given per-group states (dout rows stacked in the same order).
     Returns dy (bf16); accumulates dgamma / dbeta into G when present."""
     dg = G.get(prefix + ".weight") if G is not None else None
@@ -130,15 +164,20 @@ def bn_act_backward(dout, states, G, prefix):
     d2 = dout.view(rows, c)
     dy = torch.empty(dout.shape, dtype=BF16, device=dout.device)
     y2 = dy.view(rows, c)
+    def scratch(groups, rows_g):
+        if rows_g <= ops.BN1D_MAX_ROWS or cache is None:
+            return None
+        return _site_scratch(cache, prefix + "/b", c, groups, dout.device)
+
     if len(states) > 1 and _stacked(states):
         st = states[0]
         ops.bn_backward(d2, st.y, st.rows, st.c, st.scale_shift, st.mean_invstd, st.act, LEAKY, dg, db, out=y2,
-                        groups=len(states))
+                        groups=len(states), scratch=scratch(len(states), st.rows))
         return dy
     r0 = 0
     for st in states:
         ops.bn_backward(d2[r0:r0 + st.rows], st.y, st.rows, st.c, st.scale_shift, st.mean_invstd, st.act, LEAKY, dg, db,
-                        out=y2[r0:r0 + st.rows])
+                        out=y2[r0:r0 + st.rows], scratch=scratch(1, st.rows))
         r0 += st.rows
     return dy
 
@@ -198,9 +237,9 @@ def conv_wgrad(g, small, big, dw, cache, name):
     ops.conv_wgrad(g, small, big, dw, ws[key])
 
 
-def col_conv_forward(col, w_col, bias, rows, cs):
+def col_conv_forward(col, w_col, bias, rows, cs, bn=None):
     """3-channel convolution as a GEMM over the im2col matrix: raw[rows, cs] (bf16)."""
-    return ops.gemm(GEMM_NT, col, w_col, rows, cs, ops.COL_K, out_dtype=BF16, bias=bias, k_alg=75)
+    return ops.gemm(GEMM_NT, col, w_col, rows, cs, ops.COL_K, out_dtype=BF16, bias=bias, k_alg=75, bn=bn)
 
 
 def col_conv_wgrad(col, dy, rows, cs, dw):
@@ -219,20 +258,25 @@ def discriminator_forward(x, P, B, cache: OperandCache, training=True, col=None,
     S = SimpleNamespace(b=b, groups=groups)
     S.col = ops.im2col3(x, 1) if col is None else col
     _, _, wc1 = _conv_pack(cache, "convs.0", P["convs.0.weight"], 32, 3)
-    raw1 = col_conv_forward(S.col, wc1, P["convs.0.bias"].detach(), b * 4096, 32)
-    S.a1, S.bn1 = bn_act_forward(raw1, b * 4096, 32, P, B, "convs.1", ACT_LEAKY, training, groups)
+    dev, bg = x.device, b // groups
+    f1 = bn_fuse(cache, P, B, "convs.1", 32, groups, bg * 4096, dev, training)
+    raw1 = col_conv_forward(S.col, wc1, P["convs.0.bias"].detach(), b * 4096, 32, bn=f1)
+    S.a1, S.bn1 = bn_act_forward(raw1, b * 4096, 32, P, B, "convs.1", ACT_LEAKY, training, groups, cache, f1)
     g2 = ops.geom(b, 32, 32, 128, 32, 2)
     wd2, _, _ = _conv_pack(cache, "convs.3", P["convs.3.weight"], 128, 32)
-    raw2 = ops.conv_down(g2, S.a1, wd2, P["convs.3.bias"].detach())
-    S.a2, S.bn2 = bn_act_forward(raw2, b * 1024, 128, P, B, "convs.4", ACT_LEAKY, training, groups)
+    f2 = bn_fuse(cache, P, B, "convs.4", 128, groups, bg * 1024, dev, training)
+    raw2 = ops.conv_down(g2, S.a1, wd2, P["convs.3.bias"].detach(), bn=f2)
+    S.a2, S.bn2 = bn_act_forward(raw2, b * 1024, 128, P, B, "convs.4", ACT_LEAKY, training, groups, cache, f2)
     g3 = ops.geom(b, 16, 16, 256, 128, 2)
     wd3, _, _ = _conv_pack(cache, "convs.6", P["convs.6.weight"], 256, 128)
-    raw3 = ops.conv_down(g3, S.a2, wd3, P["convs.6.bias"].detach())
-    S.a3, S.bn3 = bn_act_forward(raw3, b * 256, 256, P, B, "convs.7", ACT_LEAKY, training, groups)
+    f3 = bn_fuse(cache, P, B, "convs.7", 256, groups, bg * 256, dev, training)
+    raw3 = ops.conv_down(g3, S.a2, wd3, P["convs.6.bias"].detach(), bn=f3)
+    S.a3, S.bn3 = bn_act_forward(raw3, b * 256, 256, P, B, "convs.7", ACT_LEAKY, training, groups, cache, f3)
     g4 = ops.geom(b, 8, 8, 256, 256, 2)
     wd4, _, _ = _conv_pack(cache, "convs.9", P["convs.9.weight"], 256, 256)
-    raw4 = ops.conv_down(g4, S.a3, wd4, P["convs.9.bias"].detach())
-    a4, S.bn4 = bn_act_forward(raw4, b * 64, 256, P, B, "convs.10", ACT_LEAKY, training, groups)
+    f4 = bn_fuse(cache, P, B, "convs.10", 256, groups, bg * 64, dev, training)
+    raw4 = ops.conv_down(g4, S.a3, wd4, P["convs.9.bias"].detach(), bn=f4)
+    a4, S.bn4 = bn_act_forward(raw4, b * 64, 256, P, B, "convs.10", ACT_LEAKY, training, groups, cache, f4)
     S.flat = ops.transpose(a4, b, 64, 256)  # NHWC [b,64,256] -> NCHW flatten order [b,256*64]
     wl = _lin_w(cache, "lth_features.0", P["lth_features.0.weight"])
     acc = linear_forward(S.flat, wl, None, b, 2048, 16384)
@@ -282,28 +326,28 @@ def discriminator_backward(S, dprob, dfeat, P, G, cache: OperandCache, need_dx=T
     dflat = linear_dgrad(dpre, wl, b, 2048, 16384)
     da4 = ops.transpose(dflat, b, 256, 64)  # back to NHWC [b,64,256]
     # conv 4
-    dr4 = bn_act_backward(da4, S.bn4, wg, "convs.10")
+    dr4 = bn_act_backward(da4, S.bn4, wg, "convs.10", cache)
     g4 = ops.geom(b, 8, 8, 256, 256, 2)
     _, wu4, _ = _conv_pack(cache, "convs.9", P["convs.9.weight"], 256, 256)
     if wg:
         conv_wgrad(g4, dr4, S.a3, wg["convs.9.weight"], cache, "convs.9")
     da3 = ops.conv_up(g4, dr4, wu4)
     # conv 3
-    dr3 = bn_act_backward(da3, S.bn3, wg, "convs.7")
+    dr3 = bn_act_backward(da3, S.bn3, wg, "convs.7", cache)
     g3 = ops.geom(b, 16, 16, 256, 128, 2)
     _, wu3, _ = _conv_pack(cache, "convs.6", P["convs.6.weight"], 256, 128)
     if wg:
         conv_wgrad(g3, dr3, S.a2, wg["convs.6.weight"], cache, "convs.6")
     da2 = ops.conv_up(g3, dr3, wu3)
     # conv 2
-    dr2 = bn_act_backward(da2, S.bn2, wg, "convs.4")
+    dr2 = bn_act_backward(da2, S.bn2, wg, "convs.4", cache)
     g2 = ops.geom(b, 32, 32, 128, 32, 2)
     _, wu2, _ = _conv_pack(cache, "convs.3", P["convs.3.weight"], 128, 32)
     if wg:
         conv_wgrad(g2, dr2, S.a1, wg["convs.3.weight"], cache, "convs.3")
     da1 = ops.conv_up(g2, dr2, wu2)
     # conv 1 (3 input channels: im2col GEMM)
-    dr1 = bn_act_backward(da1, S.bn1, wg, "convs.1")
+    dr1 = bn_act_backward(da1, S.bn1, wg, "convs.1", cache)
     if wg:
         col_conv_wgrad(S.col, dr1, b * 4096, 32, wg["convs.0.weight"])
     if not need_dx:
@@ -321,23 +365,27 @@ def encoder_forward(x, P, B, cache: OperandCache, training=True, col=None):
     S = SimpleNamespace(b=b)
     S.col = ops.im2col3(x, 2) if col is None else col
     _, _, wc1 = _conv_pack(cache, "features.0", P["features.0.weight"], 64, 3)
-    raw1 = col_conv_forward(S.col, wc1, P["features.0.bias"].detach(), b * 1024, 64)
-    S.a1, S.bn1 = bn_act_forward(raw1, b * 1024, 64, P, B, "features.1", ACT_RELU, training)
+    dev = x.device
+    f1 = bn_fuse(cache, P, B, "features.1", 64, 1, b * 1024, dev, training)
+    raw1 = col_conv_forward(S.col, wc1, P["features.0.bias"].detach(), b * 1024, 64, bn=f1)
+    S.a1, S.bn1 = bn_act_forward(raw1, b * 1024, 64, P, B, "features.1", ACT_RELU, training, 1, cache, f1)
     g2 = ops.geom(b, 16, 16, 128, 64, 2)
     wd2, _, _ = _conv_pack(cache, "features.3", P["features.3.weight"], 128, 64)
-    raw2 = ops.conv_down(g2, S.a1, wd2, P["features.3.bias"].detach())
-    S.a2, S.bn2 = bn_act_forward(raw2, b * 256, 128, P, B, "features.4", ACT_RELU, training)
+    f2 = bn_fuse(cache, P, B, "features.4", 128, 1, b * 256, dev, training)
+    raw2 = ops.conv_down(g2, S.a1, wd2, P["features.3.bias"].detach(), bn=f2)
+    S.a2, S.bn2 = bn_act_forward(raw2, b * 256, 128, P, B, "features.4", ACT_RELU, training, 1, cache, f2)
     g3 = ops.geom(b, 8, 8, 256, 128, 2)
     wd3, _, _ = _conv_pack(cache, "features.6", P["features.6.weight"], 256, 128)
-    raw3 = ops.conv_down(g3, S.a2, wd3, P["features.6.bias"].detach())
-    a3, S.bn3 = bn_act_forward(raw3, b * 64, 256, P, B, "features.7", ACT_RELU, training)
+    f3 = bn_fuse(cache, P, B, "features.7", 256, 1, b * 64, dev, training)
+    raw3 = ops.conv_down(g3, S.a2, wd3, P["features.6.bias"].detach(), bn=f3)
+    a3, S.bn3 = bn_act_forward(raw3, b * 64, 256, P, B, "features.7", ACT_RELU, training, 1, cache, f3)
     S.flat = ops.transpose(a3, b, 64, 256)
     outs = []
     S.heads = {}
     for head in ("x_to_mu", "x_to_logvar"):
         w0 = _lin_w(cache, head + ".0", P[head + ".0.weight"])
         acc = linear_forward(S.flat, w0, P[head + ".0.bias"].detach(), b, 2048, 16384)
-        h1, bn = bn_act_forward(acc, b, 2048, P, B, head + ".1", ACT_RELU, training)
+        h1, bn = bn_act_forward(acc, b, 2048, P, B, head + ".1", ACT_RELU, training, 1, cache)
         w3 = _lin_w(cache, head + ".3", P[head + ".3.weight"])
         out = linear_forward(h1, w3, P[head + ".3.bias"].detach(), b, 128, 2048)
         S.heads[head] = SimpleNamespace(h1=h1, bn=bn)
@@ -363,7 +411,7 @@ def encoder_backward(S, dmu, dlogvar, P, G, cache: OperandCache, need_wgrad=True
             linear_wgrad(d16, H.h1, b, 128, 2048, wg[head + ".3.weight"])
         w3 = _lin_w(cache, head + ".3", P[head + ".3.weight"])
         dh1 = linear_dgrad(d16, w3, b, 128, 2048)
-        dacc = bn_act_backward(dh1, H.bn, wg, head + ".1")
+        dacc = bn_act_backward(dh1, H.bn, wg, head + ".1", cache)
         w0 = _lin_w(cache, head + ".0", P[head + ".0.weight"])
         if wg:
             linear_wgrad(dacc, S.flat, b, 2048, 16384, wg[head + ".0.weight"], overwrite_big)
@@ -371,19 +419,19 @@ def encoder_backward(S, dmu, dlogvar, P, G, cache: OperandCache, need_wgrad=True
                 grad_ready(head + ".0.weight")
         linear_dgrad(dacc, w0, b, 2048, 16384, out_dtype=F32, out=dflat)
     da3 = ops.transpose(ops.cast_bf16(dflat), b, 256, 64)
-    dr3 = bn_act_backward(da3, S.bn3, wg, "features.7")
+    dr3 = bn_act_backward(da3, S.bn3, wg, "features.7", cache)
     g3 = ops.geom(b, 8, 8, 256, 128, 2)
     _, wu3, _ = _conv_pack(cache, "features.6", P["features.6.weight"], 256, 128)
     if wg:
         conv_wgrad(g3, dr3, S.a2, wg["features.6.weight"], cache, "features.6")
     da2 = ops.conv_up(g3, dr3, wu3)
-    dr2 = bn_act_backward(da2, S.bn2, wg, "features.4")
+    dr2 = bn_act_backward(da2, S.bn2, wg, "features.4", cache)
     g2 = ops.geom(b, 16, 16, 128, 64, 2)
     _, wu2, _ = _conv_pack(cache, "features.3", P["features.3.weight"], 128, 64)
     if wg:
         conv_wgrad(g2, dr2, S.a1, wg["features.3.weight"], cache, "features.3")
     da1 = ops.conv_up(g2, dr2, wu2)
-    dr1 = bn_act_backward(da1, S.bn1, wg, "features.1")
+    dr1 = bn_act_backward(da1, S.bn1, wg, "features.1", cache)
     if wg:
         col_conv_wgrad(S.col, dr1, b * 1024, 64, wg["features.0.weight"])
     return None  # the encoder input is data: no input gradient on this path
@@ -398,20 +446,24 @@ def decoder_forward(code, P, B, cache: OperandCache, training=True):
     S.code16 = code if code.dtype == BF16 else ops.cast_bf16(code.contiguous())
     wp = _lin_w(cache, "preprocess.0", P["preprocess.0.weight"])
     acc = linear_forward(S.code16, wp, P["preprocess.0.bias"].detach(), b, 16384, 128)
-    h, S.bn0 = bn_act_forward(acc, b, 16384, P, B, "preprocess.1", ACT_RELU, training)
+    h, S.bn0 = bn_act_forward(acc, b, 16384, P, B, "preprocess.1", ACT_RELU, training, 1, cache)
     S.h0 = ops.transpose(h, b, 256, 64)  # NCHW flatten order -> NHWC [b,8,8,256]
+    dev = code.device
     g1 = ops.geom(b, 8, 8, 256, 256, 2)
     _, wu1, _ = _conv_pack(cache, "deconv1", P["deconv1.weight"], 256, 256)
-    raw1 = ops.conv_up(g1, S.h0, wu1, P["deconv1.bias"].detach())
-    S.a1, S.bn1 = bn_act_forward(raw1, b * 256, 256, P, B, "act1.0", ACT_RELU, training)
+    f1 = bn_fuse(cache, P, B, "act1.0", 256, 1, b * 256, dev, training, tile_rows=b * 64)
+    raw1 = ops.conv_up(g1, S.h0, wu1, P["deconv1.bias"].detach(), bn=f1)
+    S.a1, S.bn1 = bn_act_forward(raw1, b * 256, 256, P, B, "act1.0", ACT_RELU, training, 1, cache, f1)
     g2 = ops.geom(b, 16, 16, 256, 128, 2)
     _, wu2, _ = _conv_pack(cache, "deconv2", P["deconv2.weight"], 256, 128)
-    raw2 = ops.conv_up(g2, S.a1, wu2, P["deconv2.bias"].detach())
-    S.a2, S.bn2 = bn_act_forward(raw2, b * 1024, 128, P, B, "act2.0", ACT_RELU, training)
+    f2 = bn_fuse(cache, P, B, "act2.0", 128, 1, b * 1024, dev, training, tile_rows=b * 256)
+    raw2 = ops.conv_up(g2, S.a1, wu2, P["deconv2.bias"].detach(), bn=f2)
+    S.a2, S.bn2 = bn_act_forward(raw2, b * 1024, 128, P, B, "act2.0", ACT_RELU, training, 1, cache, f2)
     g3 = ops.geom(b, 32, 32, 128, 32, 2)
     _, wu3, _ = _conv_pack(cache, "deconv3", P["deconv3.weight"], 128, 32)
-    raw3 = ops.conv_up(g3, S.a2, wu3, P["deconv3.bias"].detach())
-    S.a3, S.bn3 = bn_act_forward(raw3, b * 4096, 32, P, B, "act3.0", ACT_RELU, training)
+    f3 = bn_fuse(cache, P, B, "act3.0", 32, 1, b * 4096, dev, training, tile_rows=b * 1024)
+    raw3 = ops.conv_up(g3, S.a2, wu3, P["deconv3.bias"].detach(), bn=f3)
+    S.a3, S.bn3 = bn_act_forward(raw3, b * 4096, 32, P, B, "act3.0", ACT_RELU, training, 1, cache, f3)
     g4 = ops.geom(b, 64, 64, 32, 3, 1)
     _, wu4, _ = _conv_pack(cache, "deconv4", P["deconv4.weight"], 32, 3)
     y4 = ops.conv_up(g4, S.a3, wu4, P["deconv4.bias"].detach(), out_f32=True)  # fp32 NHWC(3)
@@ -429,26 +481,26 @@ def decoder_backward(S, drecon, P, G, cache: OperandCache, need_dcode=True, need
         col_conv_wgrad(col4, S.a3, b * 4096, 32, wg["deconv4.weight"])
     _, _, wc4 = _conv_pack(cache, "deconv4", P["deconv4.weight"], 32, 3)
     da3 = col_conv_forward(col4, wc4, None, b * 4096, 32)  # ConvT input-gradient = conv of dy with the same weights
-    dr3 = bn_act_backward(da3, S.bn3, wg, "act3.0")
+    dr3 = bn_act_backward(da3, S.bn3, wg, "act3.0", cache)
     g3 = ops.geom(b, 32, 32, 128, 32, 2)
     wd3, _, _ = _conv_pack(cache, "deconv3", P["deconv3.weight"], 128, 32)
     if wg:
         conv_wgrad(g3, S.a2, dr3, wg["deconv3.weight"], cache, "deconv3")
     da2 = ops.conv_down(g3, dr3, wd3)
-    dr2 = bn_act_backward(da2, S.bn2, wg, "act2.0")
+    dr2 = bn_act_backward(da2, S.bn2, wg, "act2.0", cache)
     g2 = ops.geom(b, 16, 16, 256, 128, 2)
     wd2, _, _ = _conv_pack(cache, "deconv2", P["deconv2.weight"], 256, 128)
     if wg:
         conv_wgrad(g2, S.a1, dr2, wg["deconv2.weight"], cache, "deconv2")
     da1 = ops.conv_down(g2, dr2, wd2)
-    dr1 = bn_act_backward(da1, S.bn1, wg, "act1.0")
+    dr1 = bn_act_backward(da1, S.bn1, wg, "act1.0", cache)
     g1 = ops.geom(b, 8, 8, 256, 256, 2)
     wd1, _, _ = _conv_pack(cache, "deconv1", P["deconv1.weight"], 256, 256)
     if wg:
         conv_wgrad(g1, S.h0, dr1, wg["deconv1.weight"], cache, "deconv1")
     dh0 = ops.conv_down(g1, dr1, wd1)  # NHWC [b,8,8,256]
     dh = ops.transpose(dh0, b, 64, 256)  # -> [b, 256*64] flatten order
-    dacc = bn_act_backward(dh, S.bn0, wg, "preprocess.1")
+    dacc = bn_act_backward(dh, S.bn0, wg, "preprocess.1", cache)
     if wg:
         linear_wgrad(dacc, S.code16, b, 16384, 128, wg["preprocess.0.weight"], overwrite_big)
     if not need_dcode:

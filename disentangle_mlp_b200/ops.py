@@ -11,7 +11,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import GEMM_NN, GEMM_NT, GEMM_TN, ConvGeom, GemmDesc
+from ._lib import GEMM_NN, GEMM_NT, GEMM_TN, BnFuse, ConvGeom, GemmDesc
 
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 COL_K = 80  # stored columns of the 3-channel im2col matrix (75 valid); the GEMM's K boxes zero-fill beyond
@@ -35,9 +35,33 @@ def geom(batch, hs, ws, cs, cb, stride) -> ConvGeom:
 
 
 # ------------------------------------------------------------------------------------------ GEMM-class
+class BnSite:
+    """Everything the kernel that PRODUCES a pre-BatchNorm tensor needs to also produce its statistics and finalize
+    them (dm_bn_fuse): slot scratch, the layer's parameters / buffers, and the outputs scale_shift / mean_invstd
+    ([groups,2,c]) that the consumer (bn_apply_act) and the backward pass read."""
+
+    def __init__(self, scratch, groups, rows, c, gamma, beta, running_mean, running_var, nbt, momentum=0.1, eps=1e-5):
+        dev = scratch.device
+        self.scratch, self.groups, self.rows, self.c = scratch, int(groups), int(rows), int(c)
+        self.gamma, self.beta, self.running_mean, self.running_var, self.nbt = gamma, beta, running_mean, running_var, nbt
+        self.momentum, self.eps = momentum, eps
+        self.scale_shift = torch.empty((self.groups, 2, c), dtype=F32, device=dev)
+        self.mean_invstd = torch.empty((self.groups, 2, c), dtype=F32, device=dev)
+
+    def struct(self):
+        return BnFuse(_p(self.scratch), self.groups, self.rows, _p(self.gamma), _p(self.beta), _p(self.running_mean),
+                      _p(self.running_var), _p(self.nbt), self.momentum, self.eps, _p(self.scale_shift),
+                      _p(self.mean_invstd))
+
+
+def _bn_fuse(bn):
+    """bn: None or a BnSite -> dm_bn_fuse (or None)"""
+    return None if bn is None else bn.struct()
+
+
 def gemm(layout, a, b, m, n, k, *, out=None, out_dtype=F32, accumulate=False, bias=None, splits=1,
-         lda=None, ldb=None, ldd_m=None, ldd_n=1, m_store=0, n_store=0, k_alg=0):
-    """D = op(A) op(B) with bf16 operands; see dm_gemm_desc."""
+         lda=None, ldb=None, ldd_m=None, ldd_n=1, m_store=0, n_store=0, k_alg=0, bn=None):
+    """D = op(A) op(B) with bf16 operands; see dm_gemm_desc.  bn: a BnSite = fused BatchNorm statistics + finalize."""
     assert a.dtype == BF16 and b.dtype == BF16
     if out is None:
         out = (torch.zeros if accumulate else torch.empty)((m_store or m, n_store or n), dtype=out_dtype,
@@ -49,15 +73,20 @@ def gemm(layout, a, b, m, n, k, *, out=None, out_dtype=F32, accumulate=False, bi
     if ldd_m is None:
         ldd_m = out.stride(0) if out.dim() >= 2 else 1
     d = GemmDesc(layout, m, n, k, _p(a), lda, _p(b), ldb, _p(out), ldd_m, ldd_n, int(out.dtype == F32),
-                 int(accumulate), _p(bias), m_store, n_store, splits, k_alg)
+                 int(accumulate), _p(bias), m_store, n_store, splits, k_alg, _bn_fuse(bn) or BnFuse())
     _lib.check(_lib.load().dm_gemm_bf16(C.byref(d), _stream()), "dm_gemm_bf16")
     return out
 
 
-def conv_down(g: ConvGeom, big, w_down, bias=None, out=None):
+def _bn_ref(bn):
+    f = _bn_fuse(bn)
+    return None if f is None else C.byref(f)
+
+
+def conv_down(g: ConvGeom, big, w_down, bias=None, out=None, bn=None):
     if out is None:
         out = torch.empty((g.batch, g.hs, g.ws, g.cs), dtype=BF16, device=big.device)
-    _lib.check(_lib.load().dm_conv_down(C.byref(g), _p(big), _p(w_down), _p(bias), _p(out), _stream()),
+    _lib.check(_lib.load().dm_conv_down(C.byref(g), _p(big), _p(w_down), _p(bias), _p(out), _bn_ref(bn), _stream()),
                "dm_conv_down")
     return out
 
@@ -75,18 +104,18 @@ def pack_up_merged(w_up, cs, cb, out=None):
     return out
 
 
-def conv_up(g: ConvGeom, small, w_up, bias=None, out=None, out_f32=False):
+def conv_up(g: ConvGeom, small, w_up, bias=None, out=None, out_f32=False, bn=None):
     if w_up.shape[0] == 9:  # phase-merged pack
         assert not out_f32
         if out is None:
             out = torch.empty((g.batch, g.hb, g.wb, g.cb), dtype=BF16, device=small.device)
-        _lib.check(_lib.load().dm_conv_up_merged(C.byref(g), _p(small), _p(w_up), _p(bias), _p(out), _stream()),
-                   "dm_conv_up_merged")
+        _lib.check(_lib.load().dm_conv_up_merged(C.byref(g), _p(small), _p(w_up), _p(bias), _p(out), _bn_ref(bn),
+                                                 _stream()), "dm_conv_up_merged")
         return out
     if out is None:
         out = torch.empty((g.batch, g.hb, g.wb, g.cb), dtype=F32 if out_f32 else BF16, device=small.device)
     _lib.check(_lib.load().dm_conv_up(C.byref(g), _p(small), _p(w_up), _p(bias), _p(out), int(out.dtype == F32),
-                                      _stream()), "dm_conv_up")
+                                      _bn_ref(bn), _stream()), "dm_conv_up")
     return out
 
 
@@ -169,58 +198,66 @@ def bn_parts(rows, c) -> int:
     return int(_lib.load().dm_bn_parts(rows, c))
 
 
-def bn_stats(y, rows, c):
-    """Per-block partial sums [parts][2][c] of y and y^2 (summed by bn_finalize)."""
-    partials = torch.empty((bn_parts(rows, c), 2, c), dtype=F32, device=y.device)
-    _lib.check(_lib.load().dm_bn_stats(_p(y), int(y.dtype == F32), rows, c, _p(partials), _stream()), "dm_bn_stats")
-    return partials
+def bn_scratch(c, groups, device):
+    """A call site's slot scratch for the BatchNorm partial sums: zero on entry AND on exit of every use (the consumer
+    kernel's last block clears it), so it is allocated and zeroed once."""
+    return torch.zeros(int(_lib.load().dm_bn_scratch_floats(c, groups)), dtype=F32, device=device)
 
 
-def bn_finalize(partials, rows, c, gamma, beta, running_mean, running_var, nbt, momentum=0.1, eps=1e-5):
-    scale_shift = torch.empty((2, c), dtype=F32, device=partials.device)
-    mean_invstd = torch.empty((2, c), dtype=F32, device=partials.device)
-    _lib.check(_lib.load().dm_bn_finalize(_p(partials), partials.shape[0], rows, c, _p(gamma), _p(beta),
-                                          _p(running_mean), _p(running_var), _p(nbt), momentum, eps, _p(scale_shift),
-                                          _p(mean_invstd), _stream()), "dm_bn_finalize")
-    return scale_shift, mean_invstd
+def bn_slots() -> int:
+    return int(_lib.load().dm_bn_slots())
 
 
-def bn_apply_act(y, rows, c, scale_shift, act, slope=0.2, out=None):
+def bn_stats(y, c, site: BnSite):
+    """Producer + finalize for a tensor already in memory ([groups*rows, c]): fills site.scale_shift / mean_invstd,
+    updates the running statistics, leaves the scratch zeroed."""
+    f = site.struct()
+    _lib.check(_lib.load().dm_bn_stats(_p(y), int(y.dtype == F32), c, C.byref(f), _stream()), "dm_bn_stats")
+    return site.scale_shift, site.mean_invstd
+
+
+def bn_apply_act(y, rows, c, scale_shift, act, slope=0.2, out=None, groups=1):
+    """out = act(y * scale + shift) with given constants ([groups,2,c] or [2,c]); `rows` per group."""
     if out is None:
         out = torch.empty(y.shape, dtype=BF16, device=y.device)
     _lib.check(_lib.load().dm_bn_apply_act(_p(y), int(y.dtype == F32), rows, c, _p(scale_shift), act, slope, _p(out),
-                                           _stream()), "dm_bn_apply_act")
+                                           groups, _stream()), "dm_bn_apply_act")
     return out
 
 
+BN1D_MAX_ROWS = 256  # at most this many rows: single-launch kernels, no scratch
+
+
 def bn_forward(y, rows, c, gamma, beta, running_mean, running_var, nbt, act, slope=0.2, momentum=0.1, eps=1e-5, out=None,
-               groups=1):
+               groups=1, scratch=None):
     """Training-mode BatchNorm + activation (dm_bn_forward).  `y` holds `groups` stacked batches of `rows` rows each.
-    Returns (out, scale_shift [groups,2,c], mean_invstd [groups,2,c])."""
+    Returns (out, scale_shift [groups,2,c], mean_invstd [groups,2,c]) ([2,c] each when groups == 1)."""
     if out is None:
         out = torch.empty(y.shape, dtype=BF16, device=y.device)
-    partials = torch.empty((groups, bn_parts(rows, c), 2, c), dtype=F32, device=y.device)
+    if scratch is None and rows > BN1D_MAX_ROWS:
+        scratch = bn_scratch(c, groups, y.device)
     scale_shift = torch.empty((groups, 2, c), dtype=F32, device=y.device)
     mean_invstd = torch.empty((groups, 2, c), dtype=F32, device=y.device)
     _lib.check(_lib.load().dm_bn_forward(_p(y), int(y.dtype == F32), rows, c, _p(gamma), _p(beta), _p(running_mean),
-                                         _p(running_var), _p(nbt), momentum, eps, act, slope, _p(partials),
+                                         _p(running_var), _p(nbt), momentum, eps, act, slope, _p(scratch),
                                          _p(scale_shift), _p(mean_invstd), _p(out), groups, _stream()), "dm_bn_forward")
     if groups == 1:
         return out, scale_shift[0], mean_invstd[0]
     return out, scale_shift, mean_invstd
 
 
-def bn_backward(dout, y, rows, c, scale_shift, mean_invstd, act, slope=0.2, dgamma=None, dbeta=None, out=None, groups=1):
+def bn_backward(dout, y, rows, c, scale_shift, mean_invstd, act, slope=0.2, dgamma=None, dbeta=None, out=None, groups=1,
+                scratch=None):
     """`rows` per group; with groups > 1 dout / y / out are the stacked tensors and scale_shift / mean_invstd are
     [groups,2,c]."""
     assert dout.dtype == BF16
     dy = torch.empty(y.shape, dtype=BF16, device=y.device) if out is None else out
-    partials = torch.empty((groups, bn_parts(rows, c), 2, c), dtype=F32, device=y.device)
-    sums = torch.empty((groups, 2, c), dtype=F32, device=y.device)
+    if scratch is None and rows > BN1D_MAX_ROWS:
+        scratch = bn_scratch(c, groups, y.device)
     _lib.check(_lib.load().dm_bn_backward(_p(dout), _p(y), int(y.dtype == F32), rows, c, _p(scale_shift),
-                                          _p(mean_invstd), act, slope, _p(partials), _p(sums), _p(dy), _p(dgamma),
-                                          _p(dbeta), groups, _stream()), "dm_bn_backward")
-    return dy, (sums[0] if groups == 1 else sums)
+                                          _p(mean_invstd), act, slope, _p(scratch), _p(dy), _p(dgamma), _p(dbeta),
+                                          groups, _stream()), "dm_bn_backward")
+    return dy
 
 
 def bias_act(acc, rows, c, bias, act, slope=0.2, want_f32=True, want_bf16=True):

@@ -37,6 +37,27 @@ enum { DM_GEMM_NT = 0, /* D[m,n] = sum_k A[m,k] B[n,k]   (nn.Linear forward,  mo
        DM_GEMM_NN = 1, /* D[m,n] = sum_k A[m,k] B[k,n]   (nn.Linear backward wrt input)                     */
        DM_GEMM_TN = 2  /* D[m,n] = sum_k A[k,m] B[k,n]   (nn.Linear backward wrt weight)                    */ };
 
+/* BatchNorm statistics + finalize fused into the kernel that writes a pre-BatchNorm tensor (NT GEMM, dm_conv_down,
+ * dm_conv_up, dm_conv_up_merged with bf16 output and no split-K; or dm_bn_stats for tensors no GEMM epilogue covers).
+ * Producers add per-channel SHIFTED sums  sum (y - k), sum (y - k)^2  (k = running_mean; taken from the fp32 accumulator
+ * + bias before the bf16 rounding in the GEMM case) to a slot scratch with fp32 atomic adds; the LAST CTA to finish
+ * (ticket counter) sums the slots and writes scale_shift / mean_invstd for every stacked pass, updates the running
+ * statistics in pass order (momentum, unbiased variance; num_batches_tracked += groups) and re-zeroes the scratch.
+ * The consumer is then a plain dm_bn_apply_act(scale_shift).  scratch == NULL: off. */
+typedef struct dm_bn_fuse {
+  float* scratch;       /* dm_bn_scratch_floats(channels, groups) floats, ZERO on entry, left zero on exit */
+  int groups;           /* passes stacked along the batch / rows; each must cover whole 128-row tiles in the GEMMs */
+  long long rows;       /* rows (pixels) of ONE pass: the n of the statistics */
+  const float* gamma;   /* [channels] */
+  const float* beta;
+  float* running_mean;  /* [channels] or NULL; also the shift k of the sums */
+  float* running_var;
+  long long* num_batches_tracked; /* or NULL */
+  float momentum, eps;
+  float* scale_shift;   /* out [groups][2][channels]: gamma*invstd, beta - mean*gamma*invstd */
+  float* mean_invstd;   /* out [groups][2][channels]: saved for the backward pass */
+} dm_bn_fuse;
+
 typedef struct dm_gemm_desc {
   int layout;        /* DM_GEMM_* */
   int m, n, k;
@@ -54,6 +75,7 @@ typedef struct dm_gemm_desc {
   int n_store;       /* columns of D actually stored (0 = n) */
   int splits;        /* split-K factor (>= 1) */
   int k_alg;         /* algorithmic K for FLOP accounting when k is zero-padded (0 = k) */
+  dm_bn_fuse bn;     /* NT, bf16 D, splits == 1: fused BatchNorm statistics over the n_store columns (scratch NULL = off) */
 } dm_gemm_desc;
 
 int dm_gemm_bf16(const dm_gemm_desc* g, void* stream);
@@ -69,21 +91,21 @@ typedef struct dm_conv_geom {
  * = nn.Conv2d forward (model.py:449-457, 388-398) and nn.ConvTranspose2d input-gradient.
  * w_down: bf16 [25][cs][cb] (dm_pack_conv_weights).  Requires cb % 32 == 0, cs % 16 == 0. */
 int dm_conv_down(const dm_conv_geom* g, const void* big, const void* w_down, const float* bias,
-                 void* out_small, void* stream);
+                 void* out_small, const dm_bn_fuse* bn, void* stream);
 
 /* big[b, s*h+kh-2, s*w+kw-2, cb] += small[b,h,w,cs] * W[cs][cb][kh][kw]   (+ bias[cb])
  * = nn.ConvTranspose2d forward with output_padding = stride-1 (model.py:495-507, 555-563) and
  *   nn.Conv2d input-gradient.  w_up: bf16 [25][cb_pad][cs], cb_pad = max(cb,16) rounded up to 16.
  * out_big: bf16 NHWC [b,hb,wb,cb] or, when out_f32, fp32 NHWC (used for the 3-channel image side). */
 int dm_conv_up(const dm_conv_geom* g, const void* small, const void* w_up, const float* bias,
-               void* out_big, int out_f32, void* stream);
+               void* out_big, int out_f32, const dm_bn_fuse* bn, void* stream);
 
 /* Phase-merged form of dm_conv_up for stride 2, cb == 32 (ConvTranspose2d(128, 32), model.py:500 / the input
  * gradient of Conv2d(32, 128), model.py:391): w_upm = dm_pack_up_merged(w_up) is [9][4*cb][cs]; one GEMM with N = 128
  * computes the four sub-pixel phases from 9 shared input taps.  Output bf16 NHWC like dm_conv_up. */
 int dm_pack_up_merged(const void* w_up, int cs, int cb, void* w_upm, void* stream);
 int dm_conv_up_merged(const dm_conv_geom* g, const void* small, const void* w_upm, const float* bias, void* out_big,
-                      void* stream);
+                      const dm_bn_fuse* bn, void* stream);
 
 /* Weight gradient of nn.Conv2d (small = grad_output, big = input) and of nn.ConvTranspose2d (small = input,
  * big = grad_output), fp32, accumulated atomically:
@@ -103,39 +125,39 @@ int dm_unpack_conv_grad(float* dw_packed, int cs, int cb, int accumulate, float*
  * Linear output (rows = batch).  act: 0 none, 1 ReLU, 2 LeakyReLU(slope).
  * ---------------------------------------------------------------------------------------------- */
 
-/* nn.BatchNorm1d/2d, training mode (model.py:451,454,457,462,468,492,496,500,504,390,393,396,399).
- * Reductions over rows are two-level: every thread block writes one partial vector, the consumer kernel sums
- * them (no same-address atomics).  dm_bn_parts(rows, c) = number of partial vectors = leading dimension of the
- * caller-provided `partials` scratch ([parts][2][c] floats; [parts][c] for dm_act_backward / dm_colsum).
- *   dm_bn_stats    : SHIFTED sums, k[c] = y[0][c]: partials[p][0][c] = sum_r (y - k), partials[p][1][c] = sum_r (y - k)^2
- *                    over block p's rows; the LAST of the dm_bn_parts() rows carries k (E[(y-k)^2] - E[y-k]^2 does not
- *                    cancel when |mean| >> std, unlike E[y^2] - E[y]^2 in fp32; torch computes a two-pass variance)
- *   dm_bn_finalize : scale = gamma*invstd, shift = beta - mean*scale; running stats updated with
- *                    `momentum` and the unbiased variance; num_batches_tracked += 1 (may be NULL)
- *   dm_bn_apply_act: out = act(y*scale + shift)   (the ReLU / LeakyReLU(0.2) that follows every BN)
- *   dm_bn_backward : dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)), dz = dout*act'(z);
- *                    sums[2][c] = (sum dz, sum dz*xhat); dgamma += sums[1], dbeta += sums[0] (skipped when NULL) */
-int dm_bn_parts(long long rows, int c);
-int dm_bn_stats(const void* y, int y_f32, long long rows, int c, float* partials, void* stream);
-int dm_bn_finalize(const float* partials, int nparts, long long rows, int c, const float* gamma, const float* beta,
-                   float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
-                   float eps, float* scale_shift, float* mean_invstd, void* stream);
-int dm_bn_apply_act(const void* y, int y_f32, long long rows, int c, const float* scale_shift, int act,
-                    float slope, void* out_bf16, void* stream);
-/* dm_bn_forward = dm_bn_stats + dm_bn_finalize + dm_bn_apply_act in ONE cooperative launch (grid barrier between the
- * reduction and the normalisation; falls back to the three kernels when the grid cannot be co-resident).
- * dm_bn_backward likewise runs its reduction, finalize and apply steps as one cooperative launch when it can.
+/* nn.BatchNorm1d/2d, training mode (model.py:451,454,457,462,468,492,496,500,504,390,393,396,399), with the
+ * ReLU / LeakyReLU(0.2) that follows every BatchNorm folded in.  Two launches per application and direction, no
+ * finalize kernel:
+ *   producer : per-channel partial sums into a small SLOT scratch [groups][dm_bn_slots()][2][c] (fp32 atomic adds), then
+ *              the last block finalizes (see dm_bn_fuse above).  Forward: the GEMM that writes the tensor (dm_bn_fuse
+ *              argument of the GEMM-class entry points) or dm_bn_stats; backward: the first kernel of dm_bn_backward
+ *              (sum dz, sum dz*xhat, dz = dout*act'(z); dgamma / dbeta accumulated by its last block).
+ *   consumer : dm_bn_apply_act (out = act(y*scale + shift)) / the second kernel of dm_bn_backward
+ *              (dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat))).
+ * `scratch`: dm_bn_scratch_floats(c, groups) floats per call site, ZERO on entry and left zero on exit (allocate and
+ * clear once; never memset in the step).  scale_shift / mean_invstd: [groups][2][c].
  * groups > 1: y / out (dout / dy) hold `groups` independent batches of `rows` rows stacked along rows (several forward
  * passes of one network pushed through each GEMM together); statistics, normalisation and running-stat updates are per
- * group, in order; partials is [groups][dm_bn_parts][2][c], scale_shift / mean_invstd / sums are [groups][2][c];
- * dgamma / dbeta accumulate over all groups. */
+ * group, in order; dgamma / dbeta accumulate over all groups.
+ * Tensors with rows <= 256 (BatchNorm1d behind the Linear layers: rows = batch) take ONE launch with an exact two-pass
+ * variance inside dm_bn_forward / dm_bn_backward (scratch unused). */
+int dm_bn_slots(void);
+long long dm_bn_scratch_floats(int c, int groups);
+/* producer + finalize for a tensor already in memory; f->rows = rows of one pass */
+int dm_bn_stats(const void* y, int y_f32, int c, const dm_bn_fuse* f, void* stream);
+/* out = act(y*scale + shift) with given constants ([groups][2][c]); `rows` per group */
+int dm_bn_apply_act(const void* y, int y_f32, long long rows, int c, const float* scale_shift, int act,
+                    float slope, void* out_bf16, int groups, void* stream);
+/* = dm_bn_stats + dm_bn_apply_act, or the single-launch small-row kernel */
 int dm_bn_forward(const void* y, int y_f32, long long rows, int c, const float* gamma, const float* beta,
                   float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
-                  int act, float slope, float* partials, float* scale_shift, float* mean_invstd, void* out_bf16,
+                  int act, float slope, float* scratch, float* scale_shift, float* mean_invstd, void* out_bf16,
                   int groups, void* stream);
 int dm_bn_backward(const void* dout_bf16, const void* y, int y_f32, long long rows, int c,
-                   const float* scale_shift, const float* mean_invstd, int act, float slope, float* partials,
-                   float* sums, void* dy_bf16, float* dgamma, float* dbeta, int groups, void* stream);
+                   const float* scale_shift, const float* mean_invstd, int act, float slope, float* scratch,
+                   void* dy_bf16, float* dgamma, float* dbeta, int groups, void* stream);
+/* rows of the [parts][c] partial-sum scratch of dm_act_backward / dm_colsum */
+int dm_bn_parts(long long rows, int c);
 
 /* out = act(acc + bias) after a split-K Linear (model.py:402-404); fp32 and/or bf16 outputs (NULL = skip). */
 int dm_bias_act(const float* acc, long long rows, int c, const float* bias, int act, float slope,

@@ -45,16 +45,39 @@ def test_version_and_error_string(lib):
 def test_struct_layouts_match_c():
     from disentangle_mlp_b200 import _lib
 
-    # dm_gemm_desc: 4 ints, (ptr, ll) x2, ptr, 2 ll, 2 ints, ptr, 4 ints  -> natural alignment, no surprises
-    assert ctypes.sizeof(_lib.GemmDesc) == 16 + 16 + 16 + 24 + 8 + 8 + 16
+    # dm_bn_fuse: ptr, int (+pad), ll, 5 ptr, 2 float, 2 ptr; dm_gemm_desc: 4 ints, (ptr, ll) x2, ptr, 2 ll, 2 ints, ptr,
+    # 4 ints, dm_bn_fuse -> natural alignment (the numbers are what gcc's sizeof gives for include/dm_b200.h)
+    assert ctypes.sizeof(_lib.BnFuse) == 88
+    assert ctypes.sizeof(_lib.GemmDesc) == 16 + 16 + 16 + 24 + 8 + 8 + 16 + 88
     assert ctypes.sizeof(_lib.ConvGeom) == 32
+
+
+def test_struct_layouts_match_the_c_compiler(tmp_path):
+    """sizeof / offsetof as gcc sees include/dm_b200.h == the ctypes mirrors in _lib.py"""
+    from disentangle_mlp_b200 import _lib
+
+    src = tmp_path / "sz.c"
+    fields = [("dm_bn_fuse", f[0], _lib.BnFuse) for f in _lib.BnFuse._fields_] + \
+             [("dm_gemm_desc", f[0], _lib.GemmDesc) for f in _lib.GemmDesc._fields_] + \
+             [("dm_conv_geom", f[0], _lib.ConvGeom) for f in _lib.ConvGeom._fields_]
+    body = "".join(f'printf("%zu\\n", offsetof({t}, {n}));\n' for t, n, _ in fields)
+    src.write_text(f'#include <stdio.h>\n#include <stddef.h>\n#include "{ROOT}/include/dm_b200.h"\n'
+                   f'int main(void){{{body}printf("%zu %zu %zu\\n", sizeof(dm_bn_fuse), sizeof(dm_gemm_desc), '
+                   f'sizeof(dm_conv_geom));return 0;}}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    offs = [int(v) for v in out[:len(fields)]]
+    assert offs == [getattr(cls, n).offset for _, n, cls in fields]
+    assert [int(v) for v in out[len(fields):]] == [ctypes.sizeof(_lib.BnFuse), ctypes.sizeof(_lib.GemmDesc),
+                                                   ctypes.sizeof(_lib.ConvGeom)]
 
 
 def test_argument_errors_do_not_need_a_gpu(lib):
     from disentangle_mlp_b200 import _lib
 
     g = _lib.ConvGeom(4, 8, 8, 256, 17, 16, 256, 2)  # hb != hs*stride
-    rc = lib.dm_conv_down(ctypes.byref(g), None, None, None, None, None)
+    rc = lib.dm_conv_down(ctypes.byref(g), None, None, None, None, None, None)
     assert rc != 0 and b"stride x small" in lib.dm_last_error()
     d = _lib.GemmDesc(layout=7, m=1, n=1, k=1, lda=8, ldb=8)
     assert lib.dm_gemm_bf16(ctypes.byref(d), None) != 0

@@ -18,63 +18,117 @@ def ops():
     return o
 
 
-@pytest.mark.parametrize("rows,c,dtype,act", [(8 * 4096, 32, torch.bfloat16, 2), (4096, 256, torch.bfloat16, 1),
-                                             (16, 2048, torch.float32, 1), (16, 16384, torch.float32, 1),
-                                             (1000, 64, torch.bfloat16, 0)])
-def test_batchnorm_forward_backward(ops, rows, c, dtype, act):
-    torch.manual_seed(0)
-    y = (torch.randn(rows, c, device="cuda") * 1.7 + 0.3).to(dtype)
+def _bn_case(ops, rows, c, dtype, act, seed, mean_shift=0.3, use_scratch=None, reps=1, rm0=None):
+    torch.manual_seed(seed)
+    y = (torch.randn(rows, c, device="cuda") * 1.7 + mean_shift).to(dtype)
     gamma = torch.randn(c, device="cuda") * 0.1 + 1
     beta = torch.randn(c, device="cuda") * 0.1
-    rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
-    nbt = torch.zeros((), dtype=torch.long, device="cuda")
-    rm_ref, rv_ref = rm.clone(), rv.clone()
-    sums = ops.bn_stats(y, rows, c)
-    ss, mi = ops.bn_finalize(sums, rows, c, gamma, beta, rm, rv, nbt)
-    out = ops.bn_apply_act(y, rows, c, ss, act, 0.2)
-    yr = y.float().clone().requires_grad_(True)
-    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
-    z = F.batch_norm(yr, rm_ref, rv_ref, gr, br, training=True, momentum=0.1, eps=1e-5)
-    ref = {0: z, 1: F.relu(z), 2: F.leaky_relu(z, 0.2)}[act]
-    assert rel(out, ref) < 4e-3  # bf16 output rounding
-    assert rel(rm, rm_ref) < 1e-4 and rel(rv, rv_ref) < 1e-4 and int(nbt) == 1
-    dout = torch.randn(rows, c, device="cuda").bfloat16()
-    ref.backward(dout.float())
-    dg, db = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
-    dy, _ = ops.bn_backward(dout, y, rows, c, ss, mi, act, 0.2, dg, db)
-    assert rel(dy, yr.grad) < 6e-3
-    assert rel(dg, gr.grad) < 2e-3 and rel(db, br.grad) < 2e-3
-
-
-@pytest.mark.parametrize("fused", ["1", "0"])
-@pytest.mark.parametrize("rows,c,dtype,act", [(64 * 4096, 32, torch.bfloat16, 2), (4096, 256, torch.bfloat16, 1),
-                                             (64, 16384, torch.float32, 1), (1000, 64, torch.bfloat16, 0)])
-def test_batchnorm_single_launch(ops, rows, c, dtype, act, fused, monkeypatch):
-    """dm_bn_forward / dm_bn_backward: statistics, finalize and apply in ONE cooperative launch (grid barrier), and
-    the same entry points forced onto the three-kernel path (DM_BN_FUSED=0); twice in a row to exercise the barrier
-    slot's generation counter."""
-    monkeypatch.setenv("DM_BN_FUSED", fused)
-    torch.manual_seed(1)
-    y = (torch.randn(rows, c, device="cuda") * 1.3 - 0.2).to(dtype)
-    gamma = torch.randn(c, device="cuda") * 0.1 + 1
-    beta = torch.randn(c, device="cuda") * 0.1
-    for rep in range(2):
-        rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    for rep in range(reps):
+        rm = torch.zeros(c, device="cuda") if rm0 is None else rm0.clone()
+        rv = torch.ones(c, device="cuda")
         nbt = torch.zeros((), dtype=torch.long, device="cuda")
         rm_ref, rv_ref = rm.clone(), rv.clone()
-        out, ss, mi = ops.bn_forward(y, rows, c, gamma, beta, rm, rv, nbt, act, 0.2)
+        out, ss, mi = ops.bn_forward(y, rows, c, gamma, beta, rm, rv, nbt, act, 0.2, scratch=use_scratch)
         yr = y.float().clone().requires_grad_(True)  # clone: y.float() aliases an fp32 y
         gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
         z = F.batch_norm(yr, rm_ref, rv_ref, gr, br, training=True, momentum=0.1, eps=1e-5)
         ref = {0: z, 1: F.relu(z), 2: F.leaky_relu(z, 0.2)}[act]
-        assert rel(out, ref) < 4e-3
+        assert rel(out, ref) < 4e-3  # bf16 output rounding
         assert rel(rm, rm_ref) < 1e-4 and rel(rv, rv_ref) < 1e-4 and int(nbt) == 1
         dout = torch.randn(rows, c, device="cuda").bfloat16()
         ref.backward(dout.float())
         dg, db = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
-        dy, _ = ops.bn_backward(dout, y, rows, c, ss, mi, act, 0.2, dg, db)
+        dy = ops.bn_backward(dout, y, rows, c, ss, mi, act, 0.2, dg, db, scratch=use_scratch)
         assert rel(dy, yr.grad) < 6e-3
         assert rel(dg, gr.grad) < 2e-3 and rel(db, br.grad) < 2e-3
+        if use_scratch is not None:  # the producer's last block leaves slots + ticket zeroed for the next use
+            n0 = ops.bn_slots() * 2 * c + 4  # (behind them: the backward pass's per-group sums, overwritten per use)
+            assert float(use_scratch[:n0].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("rows,c,dtype,act", [(8 * 4096, 32, torch.bfloat16, 2), (4096, 256, torch.bfloat16, 1),
+                                             (16, 2048, torch.float32, 1), (16, 16384, torch.float32, 1),
+                                             (64, 16384, torch.float32, 1), (256, 2048, torch.float32, 1),
+                                             (1000, 64, torch.bfloat16, 0), (64 * 4096, 32, torch.bfloat16, 2),
+                                             (300, 2048, torch.float32, 1), (130, 256, torch.bfloat16, 1)])
+def test_batchnorm_forward_backward(ops, rows, c, dtype, act):
+    """dm_bn_forward / dm_bn_backward against torch fp32: rows <= 256 take the single-launch two-pass kernels, larger
+    tensors the producer (slot partial sums) + consumer (finalize prologue, last block cleans up) pair."""
+    _bn_case(ops, rows, c, dtype, act, seed=0)
+
+
+def test_batchnorm_scratch_is_reusable(ops):
+    """One persistent scratch per call site, zero on entry and on exit: three uses in a row without a memset."""
+    rows, c = 4096, 128
+    sc = ops.bn_scratch(c, 1, "cuda")
+    _bn_case(ops, rows, c, torch.bfloat16, 2, seed=3, use_scratch=sc, reps=3)
+
+
+def test_batchnorm_large_mean_small_std(ops):
+    """|mean| >> std: E[y^2] - E[y]^2 in fp32 would cancel; the shifted sums (k = running_mean, here close to the
+    batch mean as after a few training steps) and the two-pass small-row kernel must not."""
+    torch.manual_seed(5)
+    for rows, c in ((4096, 64), (64, 2048)):
+        y = (torch.randn(rows, c, device="cuda") * 1e-2 + 50.0)
+        gamma, beta = torch.ones(c, device="cuda"), torch.zeros(c, device="cuda")
+        rm, rv = torch.full((c,), 49.9, device="cuda"), torch.ones(c, device="cuda")
+        rm_ref, rv_ref = rm.clone(), rv.clone()
+        out, ss, mi = ops.bn_forward(y, rows, c, gamma, beta, rm, rv, None, 0, 0.2)
+        ref = F.batch_norm(y, rm_ref, rv_ref, gamma, beta, training=True, momentum=0.1, eps=1e-5)
+        assert rel(out, ref) < 8e-3, (rows, c, rel(out, ref))
+        assert rel(rv, rv_ref) < 1e-3
+
+
+@pytest.mark.parametrize("kind", ["gemm", "conv_down", "conv_up", "conv_up_merged"])
+def test_batchnorm_statistics_fused_into_gemm_epilogue(ops, kind):
+    """The statistics ride in the epilogue of the GEMM that writes the pre-BatchNorm tensor and its last CTA finalizes
+    them (dm_bn_fuse): dm_bn_apply_act with the constants it wrote must equal torch's batch_norm of the tensor the GEMM
+    wrote -- for 3 stacked passes (per-pass statistics, running stats in pass order)."""
+    torch.manual_seed(7)
+    G, dev = 3, "cuda"
+    if kind == "gemm":
+        m, n, k = G * 1024, 32, 80
+        a = torch.randn(m, k, device=dev).bfloat16()
+        a[1024:2048] *= 2.0
+        w = (torch.randn(n, 128, device=dev) * 0.1).bfloat16()
+        c, rows = n, m // G
+        run = lambda bn: ops.gemm(ops.GEMM_NT, a, w, m, n, k, out_dtype=torch.bfloat16,  # noqa: E731
+                                  bias=torch.linspace(-1, 1, n, device=dev), bn=bn)
+    else:
+        b = 2 * G
+        cs, cb, hs = {"conv_down": (128, 64, 16), "conv_up": (256, 128, 8), "conv_up_merged": (128, 32, 16)}[kind]
+        g = ops.geom(b, hs, hs, cs, cb, 2)
+        wt = torch.randn(cs, cb, 5, 5, device=dev) * 0.05
+        wd, wu, _ = ops.pack_conv_weights(wt, cs, cb)
+        if kind == "conv_down":
+            x = torch.randn(b, 2 * hs, 2 * hs, cb, device=dev).bfloat16()
+            x[2:4] *= 3.0
+            c, rows = cs, (b // G) * hs * hs
+            run = lambda bn: ops.conv_down(g, x, wd, torch.linspace(-1, 1, cs, device=dev), bn=bn)  # noqa: E731
+        else:
+            x = torch.randn(b, hs, hs, cs, device=dev).bfloat16()
+            x[2:4] *= 3.0
+            c, rows = cb, (b // G) * 4 * hs * hs
+            assert (wu.shape[0] == 9) == (kind == "conv_up_merged")
+            run = lambda bn: ops.conv_up(g, x, wu, torch.linspace(-1, 1, cb, device=dev), bn=bn)  # noqa: E731
+    gamma = torch.randn(c, device=dev) * 0.1 + 1
+    beta = torch.randn(c, device=dev) * 0.1
+    rm, rv = torch.randn(c, device=dev) * 0.1, torch.ones(c, device=dev)
+    nbt = torch.zeros((), dtype=torch.long, device=dev)
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    sc = ops.bn_scratch(c, G, dev)
+    for rep in range(2):  # twice: the scratch comes back zeroed
+        site = ops.BnSite(sc, G, rows, c, gamma, beta, rm, rv, nbt)
+        y = run(site)  # the GEMM's epilogue sums, its last CTA finalizes
+        y2 = y.view(G * rows, c)
+        out = ops.bn_apply_act(y2, rows, c, site.scale_shift, 2, 0.2, groups=G)
+        ref = torch.cat([F.leaky_relu(F.batch_norm(y2[i * rows:(i + 1) * rows].float(), rm_ref, rv_ref, gamma, beta,
+                                                   training=True, momentum=0.1, eps=1e-5), 0.2) for i in range(G)])
+        assert rel(out, ref) < 5e-3, (kind, rep, rel(out, ref))
+        assert rel(rm, rm_ref) < 2e-3 and rel(rv, rv_ref) < 2e-3 and int(nbt) == G * (rep + 1), (kind, rep)
+        assert float(sc[:G * ops.bn_slots() * 2 * c + 4].abs().max()) == 0.0
+    plain = run(None)
+    assert torch.equal(plain, y)  # the fused statistics do not change what the GEMM writes
 
 
 def test_batchnorm_groups(ops):
@@ -100,7 +154,7 @@ def test_batchnorm_groups(ops):
     dout = torch.randn(2 * rows, c, device="cuda").bfloat16()
     torch.cat(refs[1:]).backward(dout.float())
     dg, db = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
-    dy, _ = ops.bn_backward(dout, y[rows:], rows, c, ss[1:], mi[1:], 2, 0.2, dg, db, groups=2)
+    dy = ops.bn_backward(dout, y[rows:], rows, c, ss[1:], mi[1:], 2, 0.2, dg, db, groups=2)
     assert rel(dy, yr.grad[rows:]) < 6e-3
     assert rel(dg, gr.grad) < 2e-3 and rel(db, br.grad) < 2e-3
 

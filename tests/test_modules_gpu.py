@@ -124,12 +124,10 @@ def check_bn_layer(ops, bn, act, inp, out_act, tag):
     dev = "cuda"
     gamma, beta = bn.weight.detach().cuda(), bn.bias.detach().cuda()
     rm, rv = torch.zeros(c, device=dev), torch.ones(c, device=dev)
-    sums = ops.bn_stats(y, rows, c)
-    ss, mi = ops.bn_finalize(sums, rows, c, gamma, beta, rm, rv, None)
-    a = ops.bn_apply_act(y, rows, c, ss, act, 0.2)
+    a, ss, mi = ops.bn_forward(y, rows, c, gamma, beta, rm, rv, None, act, 0.2)
     dout = nhwc16(out_act.grad) if is2d else out_act.grad.detach().cuda().bfloat16().contiguous()
     dg, db = torch.zeros(c, device=dev), torch.zeros(c, device=dev)
-    dy, _ = ops.bn_backward(dout, y, rows, c, ss, mi, act, 0.2, dg, db)
+    dy = ops.bn_backward(dout, y, rows, c, ss, mi, act, 0.2, dg, db)
     # torch fp32 reference on the same rounded inputs
     yr = y.float().reshape(rows, c).clone().requires_grad_(True)
     gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)

@@ -55,6 +55,13 @@ def main():
         big = sorted(((ks[i + 1][0] - ks[i][1], i) for i in range(len(ks) - 1)), reverse=True)[:int(os.environ["TRACE_GAPS"])]
         for g, i in big:
             print(f"gap {g:8.1f} us after [{ks[i][2][:50]}] ({ks[i][1] - ks[i][0]:.1f} us) before [{ks[i + 1][2][:50]}]")
+    dump = os.environ.get("TRACE_DUMP")  # path: ordered list "start_us dur_us name" of ONE step's kernels
+    if dump:
+        per_step = len(ks) // nsteps
+        t0 = ks[0][0]
+        with open(dump, "w") as f:
+            for s_, e, n in ks[:per_step]:
+                f.write(f"{s_ - t0:10.1f} {e - s_:8.1f} {n[:90]}\n")
     show = os.environ.get("TRACE_SHOW")  # substring: list that kernel's individual launches (one step) in order
     if show:
         per = [(e - s_) for s_, e, n in ks if show in n]
