@@ -61,8 +61,13 @@ _SIGS = {
     "dm_act_backward": [c_void_p, c_void_p, c_ll, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p],
     "dm_colsum": [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p],
     "dm_im2col3": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
-    "dm_nhwc3_to_nchw": [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p],
-    "dm_tanh_backward": [c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p],
+    "dm_nhwc3_to_nchw": [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "dm_tanh_backward": [c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "dm_pad_image3": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "dm_pack_conv3_weights": [c_void_p, c_int, c_void_p, c_void_p],
+    "dm_conv3_fwd": [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_void_p, C.POINTER(BnFuse), c_void_p],
+    "dm_conv3_wgrad": [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_void_p],
+    "dm_unpack_conv3_grad": [c_void_p, c_int, c_void_p, c_void_p],
     "dm_transpose_bf16": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "dm_pack_conv_weights": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "dm_pack_up_merged": [c_void_p, c_int, c_int, c_void_p, c_void_p],
@@ -84,7 +89,7 @@ _SIGS = {
 }
 
 #: every symbol include/dm_b200.h declares
-EXPORTED = ["dm_last_error", "dm_version", "dm_launch_count", "dm_bn_scratch_floats", *list(_SIGS)]
+EXPORTED = ["dm_last_error", "dm_version", "dm_launch_count", "dm_bn_scratch_floats", "dm_pim_elems", *list(_SIGS)]
 
 _lib = None
 
@@ -108,6 +113,8 @@ def load():
     lib.dm_launch_count.restype = c_ll
     lib.dm_bn_scratch_floats.restype = c_ll
     lib.dm_bn_scratch_floats.argtypes = [c_int, c_int]
+    lib.dm_pim_elems.restype = c_ll
+    lib.dm_pim_elems.argtypes = [c_int]
     for name, args in _SIGS.items():
         fn = getattr(lib, name)
         fn.argtypes = args

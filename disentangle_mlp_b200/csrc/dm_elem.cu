@@ -639,39 +639,117 @@ __global__ void __launch_bounds__(256) im2col3_kernel(const float* __restrict__ 
   }
 }
 
-// fp32 NHWC(3) -> fp32 NCHW, optionally through tanh (decoder output, models/model.py:509,565)
+// ---- padded image ("pim"): the 3-channel image side of the three image-facing layers as a TMA-friendly operand.
+// bf16 [batch][kPimH = 68][kPimW = 72][8]: pixel (h, w) at [h + 2][w + 2], channels 3..7 and the 2-pixel border (+ 4
+// spare pixels per row) are zero.  A 5x5 filter ROW of output pixel (oh, ow) is then the 40 contiguous elements
+// starting at padded pixel (s*oh + kh, s*ow): the implicit GEMM reads it as a 64-element TMA box over a tensor map
+// whose pixel stride (16 B) is smaller than the box (overlapping windows) -- no im2col matrix (dm_gemm.cu: dm_conv3_*).
+constexpr int kPimH = 68, kPimW = 72;
+
+__device__ __forceinline__ void pim_store(__nv_bfloat16* pim, long long n, int h, int w, float r, float g, float b) {
+  bf16x8 v;
+  v.v[0] = __floats2bfloat162_rn(r, g);
+  v.v[1] = __floats2bfloat162_rn(b, 0.f);
+  v.v[2] = __floats2bfloat162_rn(0.f, 0.f);
+  v.v[3] = v.v[2];
+  *reinterpret_cast<bf16x8*>(pim + ((n * kPimH + h + 2) * kPimW + w + 2) * 8) = v;
+}
+
+// zero border of one padded image: rows 0,1,66,67 entirely, columns 0,1 and 66..71 of the other rows
+__device__ __forceinline__ void pim_zero_border(__nv_bfloat16* pim, long long n, int tid, int nt) {
+  bf16x8 z;
+  z.v[0] = z.v[1] = z.v[2] = z.v[3] = __floats2bfloat162_rn(0.f, 0.f);
+  bf16x8* base = reinterpret_cast<bf16x8*>(pim + n * kPimH * kPimW * 8);
+  for (int i = tid; i < 4 * kPimW; i += nt) {
+    const int r = i / kPimW, col = i - r * kPimW;
+    base[(r < 2 ? r : 64 + r) * kPimW + col] = z;
+  }
+  for (int i = tid; i < 64 * 8; i += nt) {
+    const int r = i >> 3, j = i & 7;
+    base[(r + 2) * kPimW + (j < 2 ? j : 64 + j)] = z;
+  }
+}
+
+// image -> pim.  src: fp32 NCHW [b,3,64,64] in [-1,1] (src_u8 == 0), or uint8 NHWC [b,64,64,3] (src_u8 != 0): the
+// reference's input pipeline ToTensor() + Normalize(.5,.5) (dataloader/dataset.py:37-43) = (u/255 - .5)/.5, fused here;
+// then dst_nchw (may be NULL) also receives the normalised fp32 NCHW image the losses read.  One block per image row.
+__global__ void __launch_bounds__(256) pad_image3_kernel(const void* __restrict__ src, int src_u8, int batch,
+                                                         __nv_bfloat16* __restrict__ pim, float* __restrict__ dst_nchw) {
+  for (long long row = blockIdx.x; row < static_cast<long long>(batch) * 64; row += gridDim.x) {
+    const long long n = row >> 6;
+    const int h = static_cast<int>(row & 63);
+    if (h == 0) pim_zero_border(pim, n, threadIdx.x, blockDim.x);
+    if (threadIdx.x < 64) {
+      const int w = threadIdx.x;
+      float v[3];
+      if (src_u8) {
+        const unsigned char* u = static_cast<const unsigned char*>(src) + ((n * 64 + h) * 64 + w) * 3;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) v[ch] = (static_cast<float>(u[ch]) / 255.f - 0.5f) / 0.5f;
+        if (dst_nchw) {
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) dst_nchw[((n * 3 + ch) * 64 + h) * 64 + w] = v[ch];
+        }
+      } else {
+        const float* f = static_cast<const float*>(src);
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) v[ch] = f[((n * 3 + ch) * 64 + h) * 64 + w];
+      }
+      pim_store(pim, n, h, w, v[0], v[1], v[2]);
+    }
+  }
+}
+
+// fp32 NHWC(3) -> fp32 NCHW, optionally through tanh (decoder output, models/model.py:509,565); pim (may be NULL, hw = 64*64
+// only) also receives the result as a padded bf16 image: the discriminator's input operand
 __global__ void __launch_bounds__(256) nhwc3_to_nchw_kernel(const float* __restrict__ src, long long batch, int hw,
-                                                            int apply_tanh, float* __restrict__ dst) {
+                                                            int apply_tanh, float* __restrict__ dst,
+                                                            __nv_bfloat16* __restrict__ pim) {
   const long long total = batch * hw;
   for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < total;
        p += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long n = p / hw;
     const int q = static_cast<int>(p - n * hw);
+    float v[3];
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
-      float v = src[p * 3 + ch];
-      if (apply_tanh) v = tanhf(v);
-      dst[(n * 3 + ch) * hw + q] = v;
+      v[ch] = src[p * 3 + ch];
+      if (apply_tanh) v[ch] = tanhf(v[ch]);
+      dst[(n * 3 + ch) * hw + q] = v[ch];
     }
+    if (pim) pim_store(pim, n, q >> 6, q & 63, v[0], v[1], v[2]);
+  }
+  if (pim) {  // borders: one block per image, strided
+    for (long long n = blockIdx.x; n < batch; n += gridDim.x) pim_zero_border(pim, n, threadIdx.x, blockDim.x);
   }
 }
 
-// dy = dout * (1 - out^2), all fp32 NCHW; bias_grad[c] += sum over batch and pixels of dy
+// dy = dout * (1 - out^2), fp32 NCHW in; bias_grad[c] += sum over batch and pixels of dy.  dy goes to fp32 NCHW (dy, may
+// be NULL) and / or to a padded bf16 image (pim, may be NULL): the operand of deconv4's input- and weight-gradient GEMMs.
+// One thread per pixel (3 channels).
 __global__ void __launch_bounds__(256) tanh_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out,
                                                        long long batch, int hw, float* __restrict__ dy,
-                                                       float* __restrict__ bias_grad) {
+                                                       float* __restrict__ bias_grad, __nv_bfloat16* __restrict__ pim) {
   __shared__ float red[3][8];
   float acc[3] = {0.f, 0.f, 0.f};
-  const long long total = batch * 3 * hw;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float o = out[i];
-    const float g = dout[i] * (1.f - o * o);
-    dy[i] = g;
-    const int ch = static_cast<int>((i / hw) % 3);
-    acc[0] += ch == 0 ? g : 0.f;
-    acc[1] += ch == 1 ? g : 0.f;
-    acc[2] += ch == 2 ? g : 0.f;
+  const long long total = batch * hw;
+  for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < total;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = p / hw;
+    const int q = static_cast<int>(p - n * hw);
+    float g[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const long long i = (n * 3 + ch) * hw + q;
+      const float o = out[i];
+      g[ch] = dout[i] * (1.f - o * o);
+      if (dy) dy[i] = g[ch];
+      acc[ch] += g[ch];
+    }
+    if (pim) pim_store(pim, n, q >> 6, q & 63, g[0], g[1], g[2]);
+  }
+  if (pim) {
+    for (long long n = blockIdx.x; n < batch; n += gridDim.x) pim_zero_border(pim, n, threadIdx.x, blockDim.x);
   }
   if (bias_grad == nullptr) return;
 #pragma unroll
@@ -685,6 +763,31 @@ __global__ void __launch_bounds__(256) tanh_bwd_kernel(const float* __restrict__
     float v = 0.f;
     for (int wv = 0; wv < 8; ++wv) v += red[threadIdx.x][wv];
     atomicAdd(bias_grad + threadIdx.x, v);
+  }
+}
+
+// fp32 weight [cs][3][5][5] -> bf16 window pack w_win[kh][cs][64]: element kw*8 + c (kw < 5, c < 3), zero elsewhere --
+// the K-major B operand matching a 64-element pim window
+__global__ void __launch_bounds__(256) pack_win_kernel(const float* __restrict__ w, int cs, __nv_bfloat16* __restrict__ w_win) {
+  const int total = 5 * cs * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int e = i & 63, n = (i >> 6) % cs, kh = i / (64 * cs);
+    const int kw = e >> 3, c = e & 7;
+    float v = 0.f;
+    if (kw < 5 && c < 3) v = w[((n * 3 + c) * 5 + kh) * 5 + kw];
+    w_win[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// window-layout weight gradient scratch [kh][cs][64] (fp32) -> dw[cs][3][5][5] += ; the scratch is re-zeroed
+__global__ void __launch_bounds__(256) unpack_win_grad_kernel(float* __restrict__ scratch, int cs, float* __restrict__ dw) {
+  const int total = 5 * cs * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int e = i & 63, n = (i >> 6) % cs, kh = i / (64 * cs);
+    const int kw = e >> 3, c = e & 7;
+    const float v = scratch[i];
+    scratch[i] = 0.f;
+    if (kw < 5 && c < 3) dw[((n * 3 + c) * 5 + kh) * 5 + kw] += v;
   }
 }
 
@@ -1179,17 +1282,43 @@ extern "C" int dm_im2col3(const float* x_nchw, int batch, int h, int w, int stri
   DM_LAUNCHED("dm_im2col3");
 }
 
-extern "C" int dm_nhwc3_to_nchw(const float* src, long long batch, int hw, int apply_tanh, float* dst, void* stream_) {
+extern "C" int dm_nhwc3_to_nchw(const float* src, long long batch, int hw, int apply_tanh, float* dst, void* pim_bf16,
+                                void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-  nhwc3_to_nchw_kernel<<<grid_for(batch * hw), 256, 0, s>>>(src, batch, hw, apply_tanh, dst);
+  DM_REQUIRE(pim_bf16 == nullptr || hw == 64 * 64, "dm_nhwc3_to_nchw: the padded-image output needs 64x64 images");
+  nhwc3_to_nchw_kernel<<<grid_for(batch * hw), 256, 0, s>>>(src, batch, hw, apply_tanh, dst, static_cast<bf16*>(pim_bf16));
   DM_LAUNCHED("dm_nhwc3_to_nchw");
 }
 
 extern "C" int dm_tanh_backward(const float* dout, const float* out, long long batch, int hw, float* dy,
-                                float* bias_grad, void* stream_) {
+                                float* bias_grad, void* pim_bf16, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-  tanh_bwd_kernel<<<grid_for(batch * 3 * hw, 256, 148 * 4), 256, 0, s>>>(dout, out, batch, hw, dy, bias_grad);
+  DM_REQUIRE(pim_bf16 == nullptr || hw == 64 * 64, "dm_tanh_backward: the padded-image output needs 64x64 images");
+  tanh_bwd_kernel<<<grid_for(batch * hw, 256, 148 * 4), 256, 0, s>>>(dout, out, batch, hw, dy, bias_grad, static_cast<bf16*>(pim_bf16));
   DM_LAUNCHED("dm_tanh_backward");
+}
+
+extern "C" long long dm_pim_elems(int batch) { return static_cast<long long>(batch) * kPimH * kPimW * 8; }
+
+extern "C" int dm_pad_image3(const void* src, int src_u8, int batch, void* pim_bf16, float* dst_nchw, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  DM_REQUIRE(batch > 0 && src != nullptr && pim_bf16 != nullptr, "dm_pad_image3: bad arguments");
+  DM_REQUIRE((reinterpret_cast<uintptr_t>(pim_bf16) & 127) == 0, "dm_pad_image3: pim must be 128-byte aligned");
+  const int blocks = static_cast<int>(std::min<long long>(static_cast<long long>(batch) * 64, 148 * 16));
+  pad_image3_kernel<<<blocks, 256, 0, s>>>(src, src_u8, batch, static_cast<bf16*>(pim_bf16), dst_nchw);
+  DM_LAUNCHED("dm_pad_image3");
+}
+
+extern "C" int dm_pack_conv3_weights(const float* w, int cs, void* w_win, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  pack_win_kernel<<<grid_for(5ll * cs * 64), 256, 0, s>>>(w, cs, static_cast<bf16*>(w_win));
+  DM_LAUNCHED("dm_pack_conv3_weights");
+}
+
+extern "C" int dm_unpack_conv3_grad(float* scratch, int cs, float* dw, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  unpack_win_grad_kernel<<<grid_for(5ll * cs * 64), 256, 0, s>>>(scratch, cs, dw);
+  DM_LAUNCHED("dm_unpack_conv3_grad");
 }
 
 extern "C" int dm_transpose_bf16(const void* src, int batch, int rows, int cols, void* dst, void* stream_) {

@@ -86,6 +86,8 @@ struct alignas(64) GemmParams {
   int m_valid;
   int wgrad_direct;    // host-only: conv wgrad writes the parameter layout directly
   int wgrad_tap_on_a;  // MODE_WGRAD: the tap shift applies to operand A (conv wgrad) instead of B
+  int wgrad_win;       // MODE_WGRAD over padded-image windows: unit u = filter rows (2u, 2u+1); the two 64-row A atoms
+                       // are the 64-element windows of taps[2u] and taps[2u+1] (same channel origin, different rows)
   // TMA epilogue (epi_tma != 0): each epilogue warp stages its 32 rows in smem and issues bulk tensor stores /
   // reductions through map_out; out-of-bounds rows and columns are clipped by the TMA unit.
   //   1 = rows: out[row][col], col contiguous (activations NHWC, plain matrices); box = {epi_cols, 32 rows as a
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
   const int t_step = (p.cluster == 2) ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   const int a_bytes = p.a_mn ? 2 * kAtomBytes : 128 * p.kc * 2;
-  const int b_bytes = p.b_mn ? (p.bn >> 6) * kAtomBytes : (kCG2 ? (p.bn >> 1) : p.bn) * p.kc * 2;
+  const int b_bytes = p.b_mn ? max(1, p.bn >> 6) * kAtomBytes : (kCG2 ? (p.bn >> 1) : p.bn) * p.kc * 2;
   const int stage_bytes = a_bytes + b_bytes;
 
   uint8_t* staging = smem + p.stages * stage_bytes;  // epi_bufs x 4 warps x 4 KB, TMA epilogue only
@@ -314,10 +316,12 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
             ++tt;
           }
         } else {
-          const Tap tap = p.taps[min(w.unit_tap, p.num_units - 1)];
+          const int ut = min(w.unit_tap, p.num_units - 1);
+          const Tap tap = p.taps[p.wgrad_win ? 2 * ut : ut];
+          const Tap tap2 = p.taps[p.wgrad_win ? 2 * ut + 1 : ut];  // second A atom (window mode only)
           const int mch0 = w.m_tile * 128;
           const int nch0 = w.n_tile * p.bn;
-          const int b_atoms = p.bn >> 6;
+          const int b_atoms = max(1, p.bn >> 6);  // (bn = 32: one 64-wide box whose upper half is out of bounds = zeros)
           // pixel-tile coordinates of k-block kb: (w0, h0, n0) = (kb * tw_step, (kb % tpi) * th_step, (kb / tpi) *
           // tn_step), advanced incrementally
           int w0 = w.kb0 * p.tw_step;
@@ -335,7 +339,10 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
             if (leader) {
               mbar_arrive_expect_tx_u32(fb, tx_bytes);
               tma_load_5d_u32(sa, map_a, fb, mch0 + adc, w0 + adw, adp, h0 + adh, n0);
-              tma_load_5d_u32(sa + kAtomBytes, map_a, fb, mch0 + 64 + adc, w0 + adw, adp, h0 + adh, n0);
+              if (p.wgrad_win)
+                tma_load_5d_u32(sa + kAtomBytes, map_a, fb, tap2.dc, w0 + tap2.dw, tap2.dp, h0 + tap2.dh, n0);
+              else
+                tma_load_5d_u32(sa + kAtomBytes, map_a, fb, mch0 + 64 + adc, w0 + adw, adp, h0 + adh, n0);
               for (int a = 0; a < b_atoms; ++a)
                 tma_load_5d_u32(sa + a_bytes + a * kAtomBytes, map_b, fb, nch0 + a * 64 + bdc, w0 + bdw, bdp,
                                 h0 + bdh, n0);
@@ -583,10 +590,11 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
       } else if (p.epi_tma == 2) {
         // ---- conv weight gradient: acc[m = cb row][n = cs col] -> packed dW[tap][n][m]; staging [32 n][32 m] fp32
         const uint64_t map_out = reinterpret_cast<uint64_t>(&p.map_out);
-        const Tap tap = p.taps[min(w.unit_tap, p.num_units - 1)];
+        const Tap tap = p.taps[p.wgrad_win ? 2 * min(w.unit_tap, p.num_units - 1) : min(w.unit_tap, p.num_units - 1)];
         const bool pair = p.mmod == 32;  // rows 0-31 / 32-63 belong to taps out_tap / out_tap + 1
-        const int m0 = pair ? 0 : m_tile * 128 + q * 32;
-        const int otap = tap.out_tap + (pair ? q : 0);
+        const bool pair64 = p.mmod == 64;  // window mode: rows 0-63 / 64-127 belong to filter rows out_tap / out_tap + 1
+        const int m0 = pair ? 0 : (pair64 ? (q & 1) * 32 : m_tile * 128 + q * 32);
+        const int otap = tap.out_tap + (pair ? q : (pair64 ? (q >> 1) : 0));
         const bool warp_ok = (w.unit_tap < p.num_units) && (q * 32 < tap.mvalid) && (m_tile * 128 + q * 32 < p.m_valid);
         const uint32_t stg0 = smem_u32(staging) + static_cast<uint32_t>(q) * 4096u;
         const int ncols = min(p.bn, static_cast<int>(tap.nvalid) - n_tile * p.bn);
@@ -924,7 +932,7 @@ static int launch(GemmParams& p, dim3 grid, cudaStream_t stream, double flops, i
                   int cluster = 1) {
   if (cluster != 2 || p.mode != MODE_FWD || p.b_mn) p.cg2 = 0;
   const int a_bytes = p.a_mn ? 2 * kAtomBytes : 128 * p.kc * 2;
-  const int b_bytes = p.b_mn ? (p.bn >> 6) * kAtomBytes : (p.cg2 ? (p.bn >> 1) : p.bn) * p.kc * 2;
+  const int b_bytes = p.b_mn ? std::max(1, p.bn >> 6) * kAtomBytes : (p.cg2 ? (p.bn >> 1) : p.bn) * p.kc * 2;
   const int stage_bytes = a_bytes + b_bytes;
   p.cluster = cluster;
   p.num_m_tiles = grid.x;
@@ -1655,4 +1663,137 @@ extern "C" int dm_conv_wgrad(const dm_conv_geom* g, const void* small, const voi
   const int cluster = 1;
   return launch(p, dim3(m_tiles, p.num_n_tiles * units, splits), stream,
                 50.0 * g->batch * g->hs * g->ws * g->cs * g->cb, (p.num_kb + splits - 1) / splits, cluster);
+}
+
+// ------------------------------------------------------------------------------------------ 3-channel image side
+// The three layers that touch the 3-channel image (Discriminator convs.0 / Encoder features.0 forward and weight
+// gradient, decoder deconv4 input- and weight-gradient) as implicit GEMMs over the PADDED IMAGE (dm_pad_image3):
+// bf16 [b][68][72][8], pixel (h, w) at [h+2][w+2], zero border / channels.  A filter row kh of output pixel (oh, ow) is
+// the contiguous run of 5 pixels x 8 channels starting at padded pixel (s*oh + kh, s*ow); the A operand of k-block kh
+// is a TMA box of 64 elements (8 pixels: the last 3 multiply zero weights) per output pixel over a tensor map whose
+// pixel stride (16 B) is smaller than the box -- overlapping windows.  K = 5 x 64 instead of 75, but no im2col matrix:
+// 16 B/pixel of image traffic instead of 160 B/pixel written + read.
+constexpr int kPimH = 68, kPimW = 72;
+
+// window view of the padded image: (e = 64 window elements, ow, row parity, oh', n)
+static int encode_pim_map(CUtensorMap* m, const void* pim, int batch, int stride, const uint32_t* box) {
+  const uint64_t px = 16, row = (uint64_t)kPimW * 16, img = (uint64_t)kPimH * row;
+  uint64_t dims[5], str[4];
+  if (stride == 1) {
+    dims[0] = 64; dims[1] = 64; dims[2] = 1; dims[3] = kPimH; dims[4] = batch;
+    str[0] = px; str[1] = row; str[2] = row; str[3] = img;
+  } else {
+    dims[0] = 64; dims[1] = 32; dims[2] = 2; dims[3] = kPimH / 2; dims[4] = batch;
+    str[0] = 2 * px; str[1] = row; str[2] = 2 * row; str[3] = img;
+  }
+  return encode_map(m, pim, 5, dims, str, box, 128);
+}
+
+// taps of filter row kh in the window view: padded row = s*oh + kh
+static void win_tap(Tap& t, int kh, int stride) {
+  memset(&t, 0, sizeof(t));
+  t.dh = static_cast<int8_t>(stride == 1 ? kh : kh / 2);
+  t.dp = static_cast<int8_t>(stride == 1 ? 0 : kh % 2);
+  t.wt = static_cast<uint8_t>(kh);
+}
+
+/* out[b,hs,ws,cs] (bf16 NHWC) = conv5x5(image, W) + bias, stride 1 or 2, from the padded image; w_win = bf16 [5][cs][64]
+ * (dm_pack_conv3_weights).  g: cb == 3, hb == wb == 64. */
+extern "C" int dm_conv3_fwd(const dm_conv_geom* g, const void* pim, const void* w_win, const float* bias, void* out_small,
+                            const dm_bn_fuse* bn, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (int rc = check_geom(g, "dm_conv3_fwd")) return rc;
+  t_kind = 1;
+  DM_REQUIRE(g->cb == 3 && g->hb == 64 && g->wb == 64, "dm_conv3_fwd: needs a 3-channel 64x64 image side");
+  DM_REQUIRE(g->cs % 32 == 0 && g->cs <= 128, "dm_conv3_fwd: cs %d must be 32, 64, 96 or 128", g->cs);
+  PixTile pt;
+  DM_REQUIRE(make_pix_tile(128, g->batch, g->hs, g->ws, &pt) && pt.bimg == 1, "dm_conv3_fwd: unsupported grid");
+  GemmParams p;
+  init_params(p);
+  p.mode = MODE_FWD;
+  p.kc = 64;
+  p.bn = g->cs;
+  p.cpt = 1;
+  p.phase_tap_start[0] = 0;
+  p.phase_tap_start[1] = 5;
+  for (int kh = 0; kh < 5; ++kh) win_tap(p.taps[kh], kh, g->stride);
+  p.tw_step = 0; p.tpi = pt.tpi; p.th_step = pt.th_step; p.tn_step = pt.tn_step;
+  p.bw = pt.bw; p.bh = pt.bh;
+  p.out = out_small; p.bias = bias; p.out_f32 = 0; p.out_atomic = 0;
+  p.os_w = g->cs; p.os_h = (long long)g->ws * g->cs; p.os_n = (long long)g->hs * g->ws * g->cs; p.os_col = 1;
+  p.w_lim = g->ws; p.n_lim = g->batch; p.n_valid = g->cs;
+  uint32_t box[5] = {64, (uint32_t)pt.bw, 1, (uint32_t)pt.bh, 1};
+  if (int rc = encode_pim_map(&p.map_a, pim, g->batch, g->stride, box)) return rc;
+  p.cg2 = (env_int("DM_CG2", 1) != 0 && pt.tiles >= 2) ? 1 : 0;
+  const int cluster = p.cg2 ? 2 : 1;
+  if (int rc = encode_w_map3(&p.map_b, w_win, 5, g->cs, 64, 64, 64, p.bn / cluster, 128)) return rc;
+  p.num_n_tiles = 1;
+  DM_REQUIRE(epi_rows_act(p, out_small, false, g->batch, g->hs, g->ws, g->cs, 1, pt), "dm_conv3_fwd: output not expressible as box stores");
+  if (bn && bn->scratch) {
+    DM_REQUIRE(groups_tile_aligned(pt, g->batch, bn->groups), "dm_conv3_fwd: groups do not fall on tile boundaries");
+    if (int rc = attach_stats(p, bn, g->cs, pt.tiles, "dm_conv3_fwd")) return rc;
+  }
+  return launch(p, dim3(pt.tiles, 1, 1), stream, 50.0 * g->batch * g->hs * g->ws * g->cs * g->cb, 1 << 30, cluster);
+}
+
+/* dw_win[5][cs][64] (fp32 window layout, dm_unpack_conv3_grad moves it to dw[cs][3][5][5]) +=
+ *   sum over pixels of small[b,h,w,cs] (bf16 NHWC: the output gradient of a Conv2d / the input of deconv4) x window.
+ * D[m = (filter row pair, window element)][n = cs], K = pixels. */
+extern "C" int dm_conv3_wgrad(const dm_conv_geom* g, const void* pim, const void* small, float* dw_win, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (int rc = check_geom(g, "dm_conv3_wgrad")) return rc;
+  t_kind = 3;
+  DM_REQUIRE(g->cb == 3 && g->hb == 64 && g->wb == 64, "dm_conv3_wgrad: needs a 3-channel 64x64 image side");
+  DM_REQUIRE(g->cs == 32 || g->cs == 64 || g->cs == 128, "dm_conv3_wgrad: cs %d must be 32, 64 or 128", g->cs);
+  PixTile pt;
+  DM_REQUIRE(make_pix_tile(64, g->batch, g->hs, g->ws, &pt) && pt.bimg == 1, "dm_conv3_wgrad: unsupported grid");
+  GemmParams p;
+  init_params(p);
+  p.mode = MODE_WGRAD;
+  p.a_mn = 1; p.b_mn = 1; p.kc = 64;
+  p.num_kb = pt.tiles;
+  p.tw_step = 0; p.tpi = pt.tpi; p.th_step = pt.th_step; p.tn_step = pt.tn_step;
+  p.out = dw_win; p.out_f32 = 1; p.out_atomic = 1;
+  p.bn = g->cs;
+  p.num_n_tiles = 1;
+  p.wgrad_win = 1;
+  p.wgrad_tap_on_a = 1;
+  for (int u = 0; u < 3; ++u) {
+    Tap& t = p.taps[2 * u];
+    win_tap(t, 2 * u, g->stride);
+    t.nvalid = static_cast<int16_t>(g->cs);
+    t.mvalid = static_cast<int16_t>(u == 2 ? 64 : 128);
+    t.out_tap = static_cast<int16_t>(2 * u);
+    Tap& t2 = p.taps[2 * u + 1];
+    win_tap(t2, 2 * u + 1, g->stride);
+    if (u == 2) t2.dh = 100;  // no sixth filter row: the box lies outside the tensor -> zero fill
+  }
+  p.mmod = 64; p.m_valid = 128;
+  uint32_t boxa[5] = {64, (uint32_t)pt.bw, 1, (uint32_t)pt.bh, 1};
+  if (int rc = encode_pim_map(&p.map_a, pim, g->batch, g->stride, boxa)) return rc;
+  // B = small [b,hs,ws,cs]: a 64-channel box; for cs == 32 its upper half is out of bounds = zeros (N = 32 is issued)
+  if (int rc = encode_act_map(&p.map_b, small, g->batch, g->hs, g->ws, g->cs, 1, boxa, 128)) return rc;
+  {  // transposed reduce-add into dw_win[5][cs][64]: box {32 m, 32 n, 1 filter row}
+    DM_REQUIRE((reinterpret_cast<uintptr_t>(dw_win) & 15) == 0, "dm_conv3_wgrad: dw_win must be 16-byte aligned");
+    uint64_t dims[3] = {64, (uint64_t)g->cs, 5};
+    uint64_t str[2] = {64 * 4, (uint64_t)g->cs * 64 * 4};
+    uint32_t box[3] = {32, 32, 1};
+    if (int rc = encode_map(&p.map_out, dw_win, 3, dims, str, box, 0, true)) return rc;
+    p.epi_tma = 2; p.epi_reduce = 1;
+  }
+  int splits = 1;
+  {  // split-K over the pixel tiles: whole waves of the persistent grid (as dm_conv_wgrad)
+    const int slots = num_sms() * 2;
+    const int fixed = env_int("DM_WGRAD_FIXED_KB", 12);
+    long long best = -1;
+    for (int sp = 1; sp <= std::min(p.num_kb, 128); ++sp) {
+      const long long items = 3ll * sp;
+      const long long waves = (items + slots - 1) / slots;
+      const long long cost = waves * ((p.num_kb + sp - 1) / sp + fixed);
+      if (best < 0 || cost < best) { best = cost; splits = sp; }
+    }
+  }
+  p.num_splits = splits;
+  return launch(p, dim3(1, 3, splits), stream, 50.0 * g->batch * g->hs * g->ws * g->cs * g->cb,
+                (p.num_kb + splits - 1) / splits, 1);
 }

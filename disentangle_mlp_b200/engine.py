@@ -55,12 +55,25 @@ def _lin_w(cache, name, p):
     return cache.get(("lin", name), p, lambda w: ops.cast_bf16(w.contiguous()))
 
 
+def pack3(w, out=None):
+    """operand packs of a 3-image-channel layer [cs][3][5][5]: (None, w_up kw-folded [25][16][cs] for the 32 -> 3
+    transposed direction, w_win [5][cs][64] for the GEMMs over the padded image)"""
+    cs = w.shape[0]
+    w = w.contiguous()
+    if out is None:
+        out = (None, torch.empty((25, 16, cs), dtype=BF16, device=w.device), None)
+    ops.pack_conv_weights(w, cs, 3, False, True, False, out=(None, out[1], None))
+    return (None, out[1], ops.pack_conv3_weights(w, out=out[2]))
+
+
 def _conv_pack(cache, name, p, cs, cb):
-    """(w_down [25][cs][cb], w_up [25][cb_pad][cs], w_col [cs][128] or None)"""
+    """(w_down [25][cs][cb], w_up [25][cb_pad][cs], None); for the three 3-channel layers (None, w_up, w_win): pack3"""
     static = getattr(cache, "static_packs", None)
     if static is not None:  # fused trainers: persistent buffers refreshed in place after every optimizer step
         return static[name]
-    return cache.get(("conv", name), p, lambda w: ops.pack_conv_weights(w.contiguous(), cs, cb, True, True, cb * 25 <= 128))
+    if cb == 3:
+        return cache.get(("conv", name), p, pack3)
+    return cache.get(("conv", name), p, lambda w: ops.pack_conv_weights(w.contiguous(), cs, cb, True, True, False))
 
 
 # ------------------------------------------------------------------------------------------ BatchNorm helper
@@ -237,30 +250,28 @@ def conv_wgrad(g, small, big, dw, cache, name):
     ops.conv_wgrad(g, small, big, dw, ws[key])
 
 
-def col_conv_forward(col, w_col, bias, rows, cs, bn=None):
-    """3-channel convolution as a GEMM over the im2col matrix: raw[rows, cs] (bf16)."""
-    return ops.gemm(GEMM_NT, col, w_col, rows, cs, ops.COL_K, out_dtype=BF16, bias=bias, k_alg=75, bn=bn)
-
-
-def col_conv_wgrad(col, dy, rows, cs, dw):
-    """dw[cs][3][5][5] (viewed [cs][75]) += dy^T @ col ; computed as D[k, cs] = col^T dy with a transposed store."""
-    splits = max(1, min(rows // 64, 296))
-    ops.gemm(GEMM_TN, col, dy.view(rows, cs), ops.COL_K, cs, rows, out=dw, accumulate=True, splits=splits, ldd_m=1, ldd_n=75, m_store=75,
-             n_store=cs)
+def conv3_wgrad(g, pim, small, dw, cache, name):
+    """Weight gradient of a 3-image-channel layer through its persistent window-layout scratch (kept zeroed)."""
+    ws = cache.wgrad_scratch
+    key = (name, "win", str(dw.device))
+    if key not in ws:
+        ws[key] = torch.zeros((5, g.cs, 64), dtype=F32, device=dw.device)
+    ops.conv3_wgrad(g, pim, small, dw, ws[key])
 
 
 # ------------------------------------------------------------------------------------------ Discriminator
-def discriminator_forward(x, P, B, cache: OperandCache, training=True, col=None, groups=1):
-    """Discriminator_celeba.forward (model.py:410-416). x: fp32 NCHW [b,3,64,64]. Returns prob [b], feat [b,2048].
-    groups > 1: x stacks `groups` separate batches (e.g. real | fake); every GEMM processes them together while
+def discriminator_forward(x, P, B, cache: OperandCache, training=True, groups=1, pim=None):
+    """Discriminator_celeba.forward (model.py:410-416). x: fp32 NCHW [b,3,64,64], or None with pim = the batch as a
+    padded bf16 image (ops.pad_image3 / the decoder's pim output).  Returns prob [b], feat [b,2048].
+    groups > 1: the batch stacks `groups` separate batches (e.g. real | fake); every GEMM processes them together while
     BatchNorm treats each group as its own forward pass (see bn_act_forward)."""
-    b = x.shape[0]
-    S = SimpleNamespace(b=b, groups=groups)
-    S.col = ops.im2col3(x, 1) if col is None else col
-    _, _, wc1 = _conv_pack(cache, "convs.0", P["convs.0.weight"], 32, 3)
-    dev, bg = x.device, b // groups
+    S = SimpleNamespace(groups=groups)
+    S.pim = ops.pad_image3(x) if pim is None else pim
+    b = S.b = S.pim.shape[0]
+    _, _, ww1 = _conv_pack(cache, "convs.0", P["convs.0.weight"], 32, 3)
+    dev, bg = S.pim.device, b // groups
     f1 = bn_fuse(cache, P, B, "convs.1", 32, groups, bg * 4096, dev, training)
-    raw1 = col_conv_forward(S.col, wc1, P["convs.0.bias"].detach(), b * 4096, 32, bn=f1)
+    raw1 = ops.conv3_fwd(ops.geom(b, 64, 64, 32, 3, 1), S.pim, ww1, P["convs.0.bias"].detach(), bn=f1)
     S.a1, S.bn1 = bn_act_forward(raw1, b * 4096, 32, P, B, "convs.1", ACT_LEAKY, training, groups, cache, f1)
     g2 = ops.geom(b, 32, 32, 128, 32, 2)
     wd2, _, _ = _conv_pack(cache, "convs.3", P["convs.3.weight"], 128, 32)
@@ -293,7 +304,7 @@ def _slice_disc(S, g0, g1):
     bg = S.b // S.groups
     i0, i1 = g0 * bg, g1 * bg
     V = SimpleNamespace(b=i1 - i0, groups=g1 - g0)
-    V.col = S.col[i0 * 4096:i1 * 4096]
+    V.pim = S.pim[i0:i1]
     V.a1, V.a2, V.a3 = S.a1[i0:i1], S.a2[i0:i1], S.a3[i0:i1]
     V.flat, V.feat, V.prob = S.flat[i0:i1], S.feat[i0:i1], S.prob[i0:i1]
     V.bn1, V.bn2, V.bn3, V.bn4 = S.bn1[g0:g1], S.bn2[g0:g1], S.bn3[g0:g1], S.bn4[g0:g1]
@@ -346,28 +357,29 @@ def discriminator_backward(S, dprob, dfeat, P, G, cache: OperandCache, need_dx=T
     if wg:
         conv_wgrad(g2, dr2, S.a1, wg["convs.3.weight"], cache, "convs.3")
     da1 = ops.conv_up(g2, dr2, wu2)
-    # conv 1 (3 input channels: im2col GEMM)
+    # conv 1 (3 input channels: GEMMs over the padded image)
     dr1 = bn_act_backward(da1, S.bn1, wg, "convs.1", cache)
+    g1 = ops.geom(b, 64, 64, 32, 3, 1)
     if wg:
-        col_conv_wgrad(S.col, dr1, b * 4096, 32, wg["convs.0.weight"])
+        conv3_wgrad(g1, S.pim, dr1, wg["convs.0.weight"], cache, "convs.0")
     if not need_dx:
         return None
-    g1 = ops.geom(b, 64, 64, 32, 3, 1)
     _, wu1, _ = _conv_pack(cache, "convs.0", P["convs.0.weight"], 32, 3)
     dx_nhwc = ops.conv_up(g1, dr1, wu1, out_f32=True)
     return ops.nhwc3_to_nchw(dx_nhwc, b, 64, 64, False)
 
 
 # ------------------------------------------------------------------------------------------ Encoder
-def encoder_forward(x, P, B, cache: OperandCache, training=True, col=None):
-    """VAE.encode (model.py:511-522). Returns mu, logvar fp32 [b,128]."""
-    b = x.shape[0]
-    S = SimpleNamespace(b=b)
-    S.col = ops.im2col3(x, 2) if col is None else col
-    _, _, wc1 = _conv_pack(cache, "features.0", P["features.0.weight"], 64, 3)
-    dev = x.device
+def encoder_forward(x, P, B, cache: OperandCache, training=True, pim=None):
+    """VAE.encode (model.py:511-522). x: fp32 NCHW, or None with pim = the batch as a padded bf16 image.
+    Returns mu, logvar fp32 [b,128]."""
+    S = SimpleNamespace()
+    S.pim = ops.pad_image3(x) if pim is None else pim
+    b = S.b = S.pim.shape[0]
+    _, _, ww1 = _conv_pack(cache, "features.0", P["features.0.weight"], 64, 3)
+    dev = S.pim.device
     f1 = bn_fuse(cache, P, B, "features.1", 64, 1, b * 1024, dev, training)
-    raw1 = col_conv_forward(S.col, wc1, P["features.0.bias"].detach(), b * 1024, 64, bn=f1)
+    raw1 = ops.conv3_fwd(ops.geom(b, 32, 32, 64, 3, 2), S.pim, ww1, P["features.0.bias"].detach(), bn=f1)
     S.a1, S.bn1 = bn_act_forward(raw1, b * 1024, 64, P, B, "features.1", ACT_RELU, training, 1, cache, f1)
     g2 = ops.geom(b, 16, 16, 128, 64, 2)
     wd2, _, _ = _conv_pack(cache, "features.3", P["features.3.weight"], 128, 64)
@@ -433,14 +445,15 @@ def encoder_backward(S, dmu, dlogvar, P, G, cache: OperandCache, need_wgrad=True
     da1 = ops.conv_up(g2, dr2, wu2)
     dr1 = bn_act_backward(da1, S.bn1, wg, "features.1", cache)
     if wg:
-        col_conv_wgrad(S.col, dr1, b * 1024, 64, wg["features.0.weight"])
+        conv3_wgrad(ops.geom(b, 32, 32, 64, 3, 2), S.pim, dr1, wg["features.0.weight"], cache, "features.0")
     return None  # the encoder input is data: no input gradient on this path
 
 
 # ------------------------------------------------------------------------------------------ Decoder
-def decoder_forward(code, P, B, cache: OperandCache, training=True):
+def decoder_forward(code, P, B, cache: OperandCache, training=True, pim_out=None):
     """VAE.decode / Generator_celeba.forward (model.py:537-566, 363-378). code: fp32 or bf16 [b,128].
-    Returns recon fp32 NCHW [b,3,64,64]."""
+    Returns recon fp32 NCHW [b,3,64,64]; pim_out (optional [b,68,72,8] bf16 buffer) also receives it as a padded image,
+    the form in which the discriminator reads it."""
     b = code.shape[0]
     S = SimpleNamespace(b=b)
     S.code16 = code if code.dtype == BF16 else ops.cast_bf16(code.contiguous())
@@ -467,7 +480,7 @@ def decoder_forward(code, P, B, cache: OperandCache, training=True):
     g4 = ops.geom(b, 64, 64, 32, 3, 1)
     _, wu4, _ = _conv_pack(cache, "deconv4", P["deconv4.weight"], 32, 3)
     y4 = ops.conv_up(g4, S.a3, wu4, P["deconv4.bias"].detach(), out_f32=True)  # fp32 NHWC(3)
-    S.recon = ops.nhwc3_to_nchw(y4, b, 64, 64, True)
+    S.recon = ops.nhwc3_to_nchw(y4, b, 64, 64, True, pim=pim_out)
     return S.recon, S
 
 
@@ -475,12 +488,14 @@ def decoder_backward(S, drecon, P, G, cache: OperandCache, need_dcode=True, need
     """drecon: fp32 NCHW gradient w.r.t. the decoder output. Returns dcode fp32 [b,128] or None."""
     b = S.b
     wg = G if need_wgrad else None
-    dy4 = ops.tanh_backward(drecon.contiguous(), S.recon, wg["deconv4.bias"] if wg else None)  # fp32 NCHW
-    col4 = ops.im2col3(dy4, 1)  # [b*4096, 128]
+    # gradient w.r.t. the pre-tanh image, written straight as a padded bf16 image: the operand of both GEMMs below
+    pim4 = ops.pim_empty(b, drecon.device)
+    ops.tanh_backward(drecon.contiguous(), S.recon, wg["deconv4.bias"] if wg else None, pim=pim4, want_dy=False)
+    g4 = ops.geom(b, 64, 64, 32, 3, 1)
     if wg:
-        col_conv_wgrad(col4, S.a3, b * 4096, 32, wg["deconv4.weight"])
-    _, _, wc4 = _conv_pack(cache, "deconv4", P["deconv4.weight"], 32, 3)
-    da3 = col_conv_forward(col4, wc4, None, b * 4096, 32)  # ConvT input-gradient = conv of dy with the same weights
+        conv3_wgrad(g4, pim4, S.a3, wg["deconv4.weight"], cache, "deconv4")
+    _, _, ww4 = _conv_pack(cache, "deconv4", P["deconv4.weight"], 32, 3)
+    da3 = ops.conv3_fwd(g4, pim4, ww4, None)  # ConvT input-gradient = conv of dy with the same weights
     dr3 = bn_act_backward(da3, S.bn3, wg, "act3.0", cache)
     g3 = ops.geom(b, 32, 32, 128, 32, 2)
     wd3, _, _ = _conv_pack(cache, "deconv3", P["deconv3.weight"], 128, 32)

@@ -291,17 +291,68 @@ def im2col3(x_nchw, stride, out=None):
     return out
 
 
-def nhwc3_to_nchw(src, batch, h, w, apply_tanh):
+PIM_H, PIM_W = 68, 72  # padded image: bf16 [b][68][72][8] (see dm_pad_image3)
+
+
+def pim_empty(batch, device):
+    """Uninitialised padded-image buffer for `batch` 64x64 images."""
+    return torch.empty((batch, PIM_H, PIM_W, 8), dtype=BF16, device=device)
+
+
+def pad_image3(x, pim=None, want_nchw=False):
+    """image batch -> padded bf16 image (the operand of the 3-channel GEMMs).  x: fp32 NCHW [b,3,64,64] in [-1,1], or
+    uint8 NHWC [b,64,64,3] (the reference's ToTensor + Normalize(.5,.5) is fused in; want_nchw then also returns the
+    normalised fp32 NCHW image).  Returns pim, or (pim, x_nchw)."""
+    u8 = x.dtype == torch.uint8
+    b = x.shape[0]
+    assert (tuple(x.shape[1:]) == (64, 64, 3)) if u8 else (tuple(x.shape[1:]) == (3, 64, 64) and x.dtype == F32)
+    if pim is None:
+        pim = pim_empty(b, x.device)
+    nchw = torch.empty((b, 3, 64, 64), dtype=F32, device=x.device) if (u8 and want_nchw) else None
+    _lib.check(_lib.load().dm_pad_image3(_p(x), int(u8), b, _p(pim), _p(nchw), _stream()), "dm_pad_image3")
+    return (pim, nchw if u8 else x) if want_nchw else pim
+
+
+def pack_conv3_weights(w, out=None):
+    """fp32 [cs][3][5][5] -> bf16 window pack [5][cs][64]"""
+    cs = w.shape[0]
+    if out is None:
+        out = torch.empty((5, cs, 64), dtype=BF16, device=w.device)
+    _lib.check(_lib.load().dm_pack_conv3_weights(_p(w), cs, _p(out), _stream()), "dm_pack_conv3_weights")
+    return out
+
+
+def conv3_fwd(g: ConvGeom, pim, w_win, bias=None, out=None, bn=None):
+    """bf16 NHWC [b,hs,ws,cs] = conv5x5(3-channel image, W) + bias from the padded image (stride g.stride)."""
+    if out is None:
+        out = torch.empty((g.batch, g.hs, g.ws, g.cs), dtype=BF16, device=pim.device)
+    _lib.check(_lib.load().dm_conv3_fwd(C.byref(g), _p(pim), _p(w_win), _p(bias), _p(out), _bn_ref(bn), _stream()),
+               "dm_conv3_fwd")
+    return out
+
+
+def conv3_wgrad(g: ConvGeom, pim, small, dw, scratch=None):
+    """dw[cs][3][5][5] (fp32) += sum_pixels small[b,h,w,cs] x 5x5 image patch.  scratch: zeroed fp32 [5][cs][64] window
+    gradient buffer (kept zeroed by the unpack kernel)."""
+    if scratch is None:
+        scratch = torch.zeros((5, g.cs, 64), dtype=F32, device=pim.device)
+    _lib.check(_lib.load().dm_conv3_wgrad(C.byref(g), _p(pim), _p(small), _p(scratch), _stream()), "dm_conv3_wgrad")
+    _lib.check(_lib.load().dm_unpack_conv3_grad(_p(scratch), g.cs, _p(dw), _stream()), "dm_unpack_conv3_grad")
+    return dw
+
+
+def nhwc3_to_nchw(src, batch, h, w, apply_tanh, pim=None):
     dst = torch.empty((batch, 3, h, w), dtype=F32, device=src.device)
-    _lib.check(_lib.load().dm_nhwc3_to_nchw(_p(src), batch, h * w, int(apply_tanh), _p(dst), _stream()),
+    _lib.check(_lib.load().dm_nhwc3_to_nchw(_p(src), batch, h * w, int(apply_tanh), _p(dst), _p(pim), _stream()),
                "dm_nhwc3_to_nchw")
     return dst
 
 
-def tanh_backward(dout, out, bias_grad=None):
+def tanh_backward(dout, out, bias_grad=None, pim=None, want_dy=True):
+    """dy = dout * (1 - out^2): as fp32 NCHW (want_dy) and / or as a padded bf16 image (pim)."""
     b, ch, h, w = out.shape
-    dy = torch.empty_like(out)
-    _lib.check(_lib.load().dm_tanh_backward(_p(dout), _p(out), b, h * w, _p(dy), _p(bias_grad), _stream()),
+    dy = torch.empty_like(out) if want_dy else None
+    _lib.check(_lib.load().dm_tanh_backward(_p(dout), _p(out), b, h * w, _p(dy), _p(bias_grad), _p(pim), _stream()),
                "dm_tanh_backward")
     return dy
 

@@ -156,7 +156,7 @@ class FlatParams:
                         w_up = torch.empty((9, 4 * cb, cs), dtype=BF16, device=dev)
                     self.cache.static_packs[n[:-len(".weight")]] = (w_down, w_up, None)
                 else:
-                    self.cache.static_packs[n[:-len(".weight")]] = ops.pack_conv_weights(p.detach(), cs, cb, True, True, cb * 25 <= 128)
+                    self.cache.static_packs[n[:-len(".weight")]] = engine.pack3(p.detach())
         self._zero_ranges, self._late_ranges = plan["zero_ranges"], plan["late_ranges"]
         self.params_changed()
         # module.load_state_dict() copies into the re-homed fp32 masters: refresh the bf16 shadow / operand packs
@@ -214,7 +214,7 @@ class FlatParams:
                 else:
                     ops.transpose(packs[0], 25, p.shape[0], p.shape[1], out=packs[1])
             else:
-                ops.pack_conv_weights(p.detach(), p.shape[0], p.shape[1], out=packs)
+                engine.pack3(p.detach(), out=packs)
 
     def touch(self):
         """The fp32 masters were updated through raw pointers (Adam kernel, graph replay, restore): nn.Parameter
@@ -398,6 +398,17 @@ class _Base:
         if token is not None:
             torch.cuda.current_stream().wait_stream(token)
 
+    @staticmethod
+    def _ingest(data, pim):
+        """The step's input batch -> (fp32 NCHW image the losses read, its padded bf16 image in `pim`).  data: fp32
+        NCHW in [-1,1] (what the reference's loader yields), or uint8 NHWC [b,64,64,3] straight from a pre-decoded shard:
+        the loader's ToTensor + Normalize(.5,.5) (dataloader/dataset.py:37-43) then runs inside the same kernel."""
+        if data.dtype == torch.uint8:
+            _, x = ops.pad_image3(data, pim, want_nchw=True)
+            return x
+        ops.pad_image3(data, pim)
+        return data
+
     def _early(self, fp):
         """grad_ready hook: all-reduce a big gradient bucket as soon as the backward pass has finished writing it."""
         if not self.dist.on:
@@ -405,23 +416,30 @@ class _Base:
         return lambda name: fp.reduce_early(self.dist, name)
 
     # ------------------------------------------------------------------ CUDA graph
-    def enable_graph(self, batch):
+    def enable_graph(self, batch, input_u8=False):
+        """input_u8: the step will be fed uint8 NHWC [batch,64,64,3] batches (normalisation fused into the first
+        kernel) instead of fp32 NCHW [-1,1] ones; the captured graph is specific to one input format."""
         if self.dist.on and os.environ.get("DM_GRAPH_DDP", "1") == "0":
             raise RuntimeError("graph capture with collectives disabled (DM_GRAPH_DDP=0)")
         fps = self.flat_params()
         dev = fps[0].flat.device
-        self._gx = torch.zeros(batch, 3, 64, 64, device=dev)
-        self._glabels = torch.zeros(2, device=dev)
-        self._glabels_ring = [(torch.zeros(2).pin_memory(), torch.cuda.Event()) for _ in range(16)]
-        # random inputs of the step (noise / eps), drawn OUTSIDE the graph in the reference's order
-        self._grands = [torch.zeros(batch, 128, device=dev) for _ in range(self.n_rands)]
+        self._gx = (torch.zeros(batch, 64, 64, 3, dtype=torch.uint8, device=dev) if input_u8
+                    else torch.zeros(batch, 3, 64, 64, device=dev))
+        if not hasattr(self, "_glabels"):  # labels / random inputs are shared by the graphs of both input formats
+            self._glabels = torch.zeros(2, device=dev)
+            self._glabels_ring = [(torch.zeros(2).pin_memory(), torch.cuda.Event()) for _ in range(16)]
+            # random inputs of the step (noise / eps), drawn OUTSIDE the graph in the reference's order (SURVEY Q5)
+            self._grands = [torch.zeros(batch, 128, device=dev) for _ in range(self.n_rands)]
         snaps = [fp.snapshot() for fp in fps]
         rng = torch.cuda.get_rng_state(dev)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):  # warm-up outside capture: lazy inits (func attributes, driver entry points)
             self._glabels.copy_(torch.tensor([0.9, 0.1]))
-            self._gx.uniform_(-1, 1)
+            if input_u8:
+                self._gx.random_(0, 256)
+            else:
+                self._gx.uniform_(-1, 1)
             for _ in range(2):
                 self._step_impl(self._gx, self._glabels[0:1], self._glabels[1:2], *self._grands)
         torch.cuda.current_stream().wait_stream(side)
@@ -439,6 +457,10 @@ class _Base:
             fp.restore(s)
         torch.cuda.set_rng_state(rng, dev)
         torch.cuda.synchronize()
+        # one captured graph per input format (fp32 NCHW / uint8 NHWC): _graph_step picks by the batch's dtype
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+        self._graphs[bool(input_u8)] = (self._graph, self._gx, self._gmetrics)
 
     def _graph_step(self, data, real_label, fake_label, rands=None):
         """Replay the captured step.  rands: optional list of `n_rands` [batch,128] tensors (noise / eps in the
@@ -453,7 +475,11 @@ class _Base:
         host[0], host[1] = real_label, fake_label
         self._glabels.copy_(host, non_blocking=True)
         ev.record()
-        self._gx.copy_(data, non_blocking=True)
+        graph, gx, gmetrics = self._graphs.get(data.dtype == torch.uint8) or (None, None, None)
+        if graph is None:
+            raise RuntimeError(f"no CUDA graph was captured for {data.dtype} input batches "
+                               f"(enable_graph(batch, input_u8={data.dtype == torch.uint8}))")
+        gx.copy_(data, non_blocking=True)
         if rands is None:
             for r in self._grands:
                 r.normal_()
@@ -462,11 +488,11 @@ class _Base:
                 "graph mode: inject all of the step's random inputs or none"
             for dst, src in zip(self._grands, rands):
                 dst.copy_(src, non_blocking=True)
-        self._graph.replay()
+        graph.replay()
         for fp, n in zip(self.flat_params(), self._adams_per_step):
             fp.step_count += n
             fp.touch()
-        self.metrics = self._gmetrics
+        self.metrics = gmetrics
         return self.metrics
 
 
@@ -494,7 +520,9 @@ class VAETrainer(_Base):
         b = data.shape[0]
         loss = _scalar(dev)
         fp.zero_grad()
-        mu, logvar, Se = engine.encoder_forward(data, fp.P, fp.buffers, fp.cache, True)
+        pim = ops.pim_empty(b, dev)
+        data = self._ingest(data, pim)
+        mu, logvar, Se = engine.encoder_forward(None, fp.P, fp.buffers, fp.cache, True, pim=pim)
         if eps is None:
             eps = torch.randn_like(mu)
         _, z16 = ops.reparam_forward(mu, logvar, eps)
@@ -544,8 +572,11 @@ class GANTrainer(_Base):
         fd.zero_grad()
         if noise is None:
             noise = torch.randn(b, 128, device=dev)
-        fake, Sg = engine.decoder_forward(noise, fg.P, fg.buffers, fg.cache, True)
-        prob, _, S12 = engine.discriminator_forward(torch.cat([data, fake]), fd.P, fd.buffers, fd.cache, True, groups=2)
+        # D's inputs as padded bf16 images, stacked [data | fake]: every producer writes its slice (no torch.cat)
+        pim = ops.pim_empty(2 * b, dev)
+        data = self._ingest(data, pim[:b])
+        fake, Sg = engine.decoder_forward(noise, fg.P, fg.buffers, fg.cache, True, pim_out=pim[b:])
+        prob, _, S12 = engine.discriminator_forward(None, fd.P, fd.buffers, fd.cache, True, groups=2, pim=pim)
         dprob = torch.empty_like(prob)
         nt = b * self.dist.world
         ops.bce_const(prob[:b], real_label, errD, 1.0, n_total=nt, dprob=dprob[:b], stat=sum_dx)
@@ -557,7 +588,7 @@ class GANTrainer(_Base):
         fd.adam()
         # ---- (2) generator: re-score the same fake batch with the updated D (:118-128)
         fg.zero_grad()
-        prob_g, _, S3 = engine.discriminator_forward(fake, fd.P, fd.buffers, fd.cache, True)
+        prob_g, _, S3 = engine.discriminator_forward(None, fd.P, fd.buffers, fd.cache, True, pim=pim[b:])
         d3 = self._bce(prob_g, real_label, errG, sum_dgz2)
         dfake = engine.discriminator_backward(S3, d3, None, fd.P, None, fd.cache, True, False)
         engine.decoder_backward(Sg, dfake, fg.P, fg.G, fg.cache, False, True, overwrite_big=True)
@@ -595,7 +626,10 @@ class BetaVAEGANTrainer(_Base):
         b = data.shape[0]
         (errD_real, errD_fake, sum_dx, errG_fake, errG_recon, sim_loss, loss_dec, kld, loss_enc) = (
             _scalar(dev) for _ in range(9))
-        col_e = ops.im2col3(data, 2)  # the encoder-side im2col of `data` is shared by the two encoder forwards
+        # every image the networks read, as padded bf16 images stacked [data | fake | recon]: each producer writes its
+        # slice once, D's stacked passes and the two encoder forwards read them in place (no torch.cat, no im2col)
+        pim = ops.pim_empty(3 * b, dev)
+        data = self._ingest(data, pim[:b])
 
         # ================= discriminator phase (:95-123).  D(data) and D(fake.detach()) share every GEMM launch
         # (stacked along the batch); BatchNorm statistics / running-stat updates stay per pass, real first.
@@ -603,8 +637,8 @@ class BetaVAEGANTrainer(_Base):
         nt = b * self.dist.world
         if noise is None:
             noise = torch.randn(b, 128, device=dev)
-        fake, Sg1 = engine.decoder_forward(noise, feg.P, feg.buffers, feg.cache, True)
-        prob, _, S12 = engine.discriminator_forward(torch.cat([data, fake]), fd.P, fd.buffers, fd.cache, True, groups=2)
+        fake, Sg1 = engine.decoder_forward(noise, feg.P, feg.buffers, feg.cache, True, pim_out=pim[b:2 * b])
+        prob, _, S12 = engine.discriminator_forward(None, fd.P, fd.buffers, fd.cache, True, groups=2, pim=pim[:2 * b])
         dprob = torch.empty_like(prob)
         ops.bce_const(prob[:b], real_label, errD_real, 1.0, n_total=nt, dprob=dprob[:b], stat=sum_dx)
         ops.bce_const(prob[b:], fake_label, errD_fake, 1.0, n_total=nt, dprob=dprob[b:])
@@ -622,15 +656,14 @@ class BetaVAEGANTrainer(_Base):
         # ... while the encoder / decoder forward of this phase, which does not read D, is computed; the D update
         # (:123) lands before D is evaluated again, as in the reference
         feg.zero_grad()
-        mu, logvar, Se = engine.encoder_forward(data, feg.P, feg.buffers, feg.cache, True, col=col_e)
+        mu, logvar, Se = engine.encoder_forward(None, feg.P, feg.buffers, feg.cache, True, pim=pim[:b])
         if eps_dec is None:
             eps_dec = torch.randn_like(mu)
         _, z16 = ops.reparam_forward(mu, logvar, eps_dec)
-        recon, Sg2 = engine.decoder_forward(z16, feg.P, feg.buffers, feg.cache, True)
+        recon, Sg2 = engine.decoder_forward(z16, feg.P, feg.buffers, feg.cache, True, pim_out=pim[2 * b:])
         self._join_side(fork)
         # D(data) | D(fake) | D(recon) in one stacked pass (BatchNorm per pass, in the reference's order :129,147,150)
-        prob3, feat3, S345 = engine.discriminator_forward(torch.cat([data, fake, recon]), fd.P, fd.buffers, fd.cache,
-                                                          True, groups=3)
+        prob3, feat3, S345 = engine.discriminator_forward(None, fd.P, fd.buffers, fd.cache, True, groups=3, pim=pim)
         sim_real, sim_recon = feat3[:b], feat3[2 * b:]
         dprob2 = torch.empty(2 * b, dtype=F32, device=dev)
         ops.bce_const(prob3[b:2 * b], real_label, errG_fake, 1.0, n_total=nt, dprob=dprob2[:b])
@@ -656,7 +689,7 @@ class BetaVAEGANTrainer(_Base):
 
         # ================= "encoder" phase (:167-193): gradient of beta*KL + ||recon - x||^2, fresh forward
         feg.zero_grad()
-        mu, logvar, Se = engine.encoder_forward(data, feg.P, feg.buffers, feg.cache, True, col=col_e)
+        mu, logvar, Se = engine.encoder_forward(None, feg.P, feg.buffers, feg.cache, True, pim=pim[:b])
         if eps_enc is None:
             eps_enc = torch.randn_like(mu)
         _, z16 = ops.reparam_forward(mu, logvar, eps_enc)

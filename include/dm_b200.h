@@ -171,11 +171,37 @@ int dm_colsum(const void* x, int x_f32, long long rows, int c, float* partials, 
 /* fp32 NCHW [b,3,h,w] image -> bf16 im2col matrix [b*(h/s)*(w/s), 80], column c*25+kh*5+kw (75 valid):
  * the A operand of the two 3-channel convolutions (model.py:449, 389) and of deconv4's input-gradient. */
 int dm_im2col3(const float* x_nchw, int batch, int h, int w, int stride, void* col_bf16, void* stream);
-/* fp32 NHWC(3) -> fp32 NCHW, optionally through nn.Tanh (model.py:509,565). */
-int dm_nhwc3_to_nchw(const float* src, long long batch, int hw, int apply_tanh, float* dst, void* stream);
-/* dy = dout*(1-out^2) (fp32 NCHW); bias_grad[3] += per-channel sums of dy (deconv4.bias gradient). */
+/* fp32 NHWC(3) -> fp32 NCHW, optionally through nn.Tanh (model.py:509,565); pim_bf16 (may be NULL; 64x64 only) also
+ * receives the result as a PADDED IMAGE (below): the discriminator's input operand. */
+int dm_nhwc3_to_nchw(const float* src, long long batch, int hw, int apply_tanh, float* dst, void* pim_bf16, void* stream);
+/* dy = dout*(1-out^2) (fp32 NCHW in); bias_grad[3] += per-channel sums of dy (deconv4.bias gradient).  dy is written as
+ * fp32 NCHW (dy, may be NULL) and / or as a padded image (pim_bf16, may be NULL): the operand of deconv4's gradient GEMMs. */
 int dm_tanh_backward(const float* dout, const float* out, long long batch, int hw, float* dy,
-                     float* bias_grad, void* stream);
+                     float* bias_grad, void* pim_bf16, void* stream);
+
+/* ---- the 3-channel image side as TMA-fed implicit GEMMs over a PADDED IMAGE ("pim"):
+ * bf16 [batch][68][72][8], pixel (h, w) of a 64x64 image at [h+2][w+2]; the 2-pixel border, 4 spare pixels per row and
+ * channels 3..7 are zero (dm_pim_elems(batch) elements, 128-byte aligned).  A 5x5 filter ROW of an output pixel is then
+ * 40 contiguous elements; the GEMMs read it as a 64-element box over a tensor map with overlapping pixel windows: no
+ * im2col matrix exists.
+ *   dm_pad_image3         image -> pim.  src fp32 NCHW [b,3,64,64] (src_u8 = 0), or uint8 NHWC [b,64,64,3] (src_u8 = 1):
+ *                         the reference's input transform ToTensor() + Normalize(.5,.5) = (u/255 - .5)/.5
+ *                         (dataloader/dataset.py:37-43) fused in; dst_nchw (may be NULL) then also gets the normalised
+ *                         fp32 NCHW image (what the losses read).
+ *   dm_pack_conv3_weights fp32 W[cs][3][5][5] -> bf16 w_win[5][cs][64] (element kw*8+c of filter row kh)
+ *   dm_conv3_fwd          out[b,hs,ws,cs] = conv5x5(image, W) + bias, stride 1 / 2: nn.Conv2d(3, cs) forward
+ *                         (model.py:449, 389) and the input-gradient of nn.ConvTranspose2d(cs, 3) (model.py:507);
+ *                         optional fused BatchNorm statistics (dm_bn_fuse)
+ *   dm_conv3_wgrad        dw_win[5][cs][64] (fp32) += sum_pixels small[b,h,w,cs] x window: weight gradient of those
+ *                         layers (small = grad_output of the Conv2d / input of deconv4); split-K, bulk tensor reductions
+ *   dm_unpack_conv3_grad  dw[cs][3][5][5] += dw_win; dw_win is re-zeroed */
+long long dm_pim_elems(int batch);
+int dm_pad_image3(const void* src, int src_u8, int batch, void* pim_bf16, float* dst_nchw, void* stream);
+int dm_pack_conv3_weights(const float* w, int cs, void* w_win, void* stream);
+int dm_conv3_fwd(const dm_conv_geom* g, const void* pim, const void* w_win, const float* bias, void* out_small,
+                 const dm_bn_fuse* bn, void* stream);
+int dm_conv3_wgrad(const dm_conv_geom* g, const void* pim, const void* small, float* dw_win, void* stream);
+int dm_unpack_conv3_grad(float* dw_win, int cs, float* dw, void* stream);
 /* bf16 [batch][rows][cols] -> [batch][cols][rows]: NHWC <-> the NCHW flatten order that the 16384-wide
  * Linear layers are defined on (model.py:516-517, 540-543, 412-413). */
 int dm_transpose_bf16(const void* src, int batch, int rows, int cols, void* dst, void* stream);

@@ -27,13 +27,22 @@ def update_rel(mine, ref, init):
 
 
 def bn_running_rel(mine, ref):
-    worst = 0.0
-    sm = mine.state_dict()
-    for k, v in ref.state_dict().items():
-        if "running" in k:
-            worst = max(worst, float((sm[k].cpu() - v).norm() / (v.norm() + 1e-30)))
-        if "tracked" in k:
-            assert int(sm[k]) == int(v), k
+    """worst relative L2 error over the BatchNorm running_mean / running_var buffers (running_mean relative to the
+    layer's running std: a mean near zero has no scale of its own)"""
+    worst, where = 0.0, None
+    sm, sr = mine.state_dict(), ref.state_dict()
+    for k, v in sr.items():
+        if k.endswith("running_var"):
+            e = float((sm[k].cpu() - v).norm() / (v.norm() + 1e-30))
+        elif k.endswith("running_mean"):
+            e = float((sm[k].cpu() - v).norm() / (sr[k.replace("running_mean", "running_var")].sqrt().norm() + 1e-30))
+        else:
+            if "tracked" in k:
+                assert int(sm[k]) == int(v), k
+            continue
+        if e > worst:
+            worst, where = e, k
+    print(f"BatchNorm running stats: worst relative error {worst:.3e} at {where}")
     return worst
 
 
@@ -43,8 +52,18 @@ TOL_FIRST = {"errD_real": 5e-3, "errD_fake": 5e-3, "D_x": 5e-3, "errG_fake": 2e-
              "recon_dec": 1e-2, "kld": 0.15, "recon_enc": 2e-2}
 
 
+def force_state(module, fp, ref_module, ref_opt):
+    """CUDA module + fused optimizer state := the oracle's (parameters, BatchNorm buffers, Adam moments and step)"""
+    module.load_state_dict(ref_module.state_dict())  # (post-hook refreshes the bf16 shadow / operand packs)
+    sd = ref_opt.state_dict()
+    if sd["state"]:
+        fp.load_optimizer_state_dict(sd)
+
+
 @pytest.mark.parametrize("batch", [64, 128])
 def test_betavaegan_graph_step_at_bench_batch(batch):
+    """Two replays of the captured step, each started from the oracle's exact state (teacher forcing: a free-running
+    second step of this GAN is chaotic in KL even in the oracle -- exp(logvar) after sign-like Adam updates)."""
     from disentangle_mlp_b200 import model as dm
     from disentangle_mlp_b200 import trainer as tr
     from oracle import nets, steps
@@ -56,10 +75,6 @@ def test_betavaegan_graph_step_at_bench_batch(batch):
     rEG.apply(nets.weights_init)
     rD.apply(nets.weights_init)
     mEG, mD = dm.VAE(opt).cuda(), dm.Discriminator_celeba(opt).cuda()
-    mEG.load_state_dict(rEG.state_dict())
-    mD.load_state_dict(rD.state_dict())
-    init_eg = torch.cat([p.detach().flatten().clone() for p in rEG.parameters()])
-    init_d = torch.cat([p.detach().flatten().clone() for p in rD.parameters()])
     # lr: the reference hard-codes 1e-3 (new_betavaegan.py:49-50), at which the very first Adam updates (+-lr on
     # every one of the 16384 inputs of a Linear row) throw logvar by O(10) and make exp(logvar) -- hence KL after the
     # first EG update -- chaotic in the oracle itself (an 11x KL difference at batch 128 from bf16 rounding alone).
@@ -71,24 +86,26 @@ def test_betavaegan_graph_step_at_bench_batch(batch):
     assert T._graph is not None
     xg = x.cuda()
     for s in range(2):
+        force_state(mEG, T.feg, rEG, oEG)
+        force_state(mD, T.fd, rD, oD)
+        init_eg = torch.cat([p.detach().flatten().clone() for p in rEG.parameters()])
+        init_d = torch.cat([p.detach().flatten().clone() for p in rD.parameters()])
         g = torch.Generator().manual_seed(50 + s)
         noise, e1, e2 = (torch.randn(batch, 128, generator=g) for _ in range(3))
         r = steps.betavaegan_step(rEG, rD, oEG, oD, x, 1.0, 0.9, 0.1, noise, e1, e2)
         m = {k: float(v) for k, v in T.step(xg, 0.9, 0.1, noise.cuda(), e1.cuda(), e2.cuda()).items()}
-        scale = 1.0 if s == 0 else 5.0  # the second replay inherits the first step's bf16 Adam updates
         for k, tol in TOL_FIRST.items():
-            assert abs(m[k] - r[k]) <= scale * tol * abs(r[k]), (batch, s, k, m[k], r[k])
-        if s == 0:
-            u_eg, u_d = update_rel(mEG, rEG, init_eg), update_rel(mD, rD, init_d)
-            print(f"batch {batch}: one-step update error EG {u_eg:.3e} D {u_d:.3e}")
-            # Adam's first update is -lr*sign(g) for EVERY element, however small its gradient: a fraction f of elements
-            # whose gradient is below the bf16 noise flips sign, and the relative L2 error of the update is 2*sqrt(f)
-            # (measured on B200, batch 64: EG 0.54 = 7 % of elements, D 0.21 = 1 %).  This bounds gross errors only; the
-            # per-layer gradients are bounded at 1e-2 in test_modules_gpu.py and the post-step parameters below.
-            assert u_eg < 0.8 and u_d < 0.4
+            assert abs(m[k] - r[k]) <= tol * abs(r[k]), (batch, s, k, m[k], r[k])
+        u_eg, u_d = update_rel(mEG, rEG, init_eg), update_rel(mD, rD, init_d)
+        print(f"batch {batch} step {s}: one-step update error EG {u_eg:.3e} D {u_d:.3e}")
+        # Adam's first updates are ~ -lr*sign(g) for EVERY element, however small its gradient: a fraction f of elements
+        # whose gradient is below the bf16 noise flips sign, and the relative L2 error of the update is 2*sqrt(f)
+        # (measured on B200: EG 0.35 = 3 % of elements, D 0.20 = 1 %).  This bounds gross errors only; the per-layer
+        # gradients are bounded at 1e-2 in test_modules_gpu.py, the post-step parameters below.
+        assert u_eg < 0.6 and u_d < 0.4
+        assert params_rel(mEG, rEG) < 1e-2 and params_rel(mD, rD) < 1e-2
+        assert bn_running_rel(mEG, rEG) < 2e-2 and bn_running_rel(mD, rD) < 2e-2
     assert T.fd.step_count == 2 and T.feg.step_count == 4
-    assert params_rel(mEG, rEG) < 5e-2 and params_rel(mD, rD) < 5e-2
-    assert bn_running_rel(mEG, rEG) < 2e-2 and bn_running_rel(mD, rD) < 2e-2
 
 
 def test_gan_graph_step_at_batch_256():

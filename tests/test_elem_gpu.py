@@ -168,6 +168,81 @@ def test_im2col3(ops, stride):
     assert col.shape[1] == 80 and float(col[:, 75:].abs().max()) == 0.0
 
 
+def _unpad(pim):
+    """padded bf16 image [b,68,72,8] -> (interior as fp32 NCHW [b,3,64,64], everything else)"""
+    inner = pim[:, 2:66, 2:66, :3].float().permute(0, 3, 1, 2)
+    rest = pim.clone()
+    rest[:, 2:66, 2:66, :3] = 0
+    return inner, rest
+
+
+def test_padded_image_producers(ops):
+    """dm_pad_image3 (fp32 NCHW and uint8 NHWC with the loader's ToTensor + Normalize(.5,.5) fused in,
+    dataloader/dataset.py:37-43), and the padded-image outputs of the decoder's tanh / tanh-backward kernels."""
+    torch.manual_seed(0)
+    x = torch.rand(5, 3, 64, 64, device="cuda") * 2 - 1
+    pim = ops.pad_image3(x, ops.pim_empty(5, "cuda").fill_(7.0))  # (pre-filled: borders must be ZEROED by the kernel)
+    inner, rest = _unpad(pim)
+    assert torch.equal(inner, x.bfloat16().float()) and float(rest.abs().max()) == 0.0
+    u8 = torch.randint(0, 256, (5, 64, 64, 3), dtype=torch.uint8, device="cuda")
+    pim, xn = ops.pad_image3(u8, ops.pim_empty(5, "cuda").fill_(7.0), want_nchw=True)
+    ref = ((u8.permute(0, 3, 1, 2).float() / 255.0) - 0.5) / 0.5  # transforms.ToTensor() + Normalize((.5,)*3, (.5,)*3)
+    assert float((xn - ref).abs().max()) < 1e-6
+    inner, rest = _unpad(pim)
+    assert torch.equal(inner, xn.bfloat16().float()) and float(rest.abs().max()) == 0.0
+    y = torch.randn(4, 64, 64, 3, device="cuda")
+    p2 = ops.pim_empty(4, "cuda").fill_(7.0)
+    out = ops.nhwc3_to_nchw(y, 4, 64, 64, True, pim=p2)
+    inner, rest = _unpad(p2)
+    assert torch.equal(inner, out.bfloat16().float()) and float(rest.abs().max()) == 0.0
+    dout = torch.randn_like(out)
+    p3 = ops.pim_empty(4, "cuda").fill_(7.0)
+    bg = torch.zeros(3, device="cuda")
+    assert ops.tanh_backward(dout, out, bg, pim=p3, want_dy=False) is None
+    dy = dout * (1 - out * out)
+    inner, rest = _unpad(p3)  # (the kernel's 1 - o*o is one fma: last-bit differences before the bf16 rounding)
+    assert rel(inner, dy) < 4e-3 and float((inner - dy.bfloat16().float()).abs().max()) < 0.05
+    assert float(rest.abs().max()) == 0.0
+    assert rel(bg, dy.sum(dim=(0, 2, 3))) < 1e-5
+
+
+@pytest.mark.parametrize("batch,cs,stride", [(6, 32, 1), (6, 64, 2), (64, 32, 1), (3, 64, 2), (1, 32, 1)])
+def test_conv3_window_gemms(ops, batch, cs, stride):
+    """The 3-channel layers as implicit GEMMs over the padded image (overlapping TMA windows) against torch fp32 on the
+    same bf16-rounded operands: forward + bias, weight gradient; with and without fused BatchNorm statistics."""
+    from disentangle_mlp_b200 import engine
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(batch + cs)
+    x = torch.rand(batch, 3, 64, 64, device="cuda") * 2 - 1
+    w = torch.randn(cs, 3, 5, 5, device="cuda") * 0.1
+    bias = torch.randn(cs, device="cuda") * 0.1
+    hs = 64 // stride
+    g = ops.geom(batch, hs, hs, cs, 3, stride)
+    pim = ops.pad_image3(x)
+    _, _, ww = engine.pack3(w)
+    y = ops.conv3_fwd(g, pim, ww, bias)
+    ref = F.conv2d(x.bfloat16().float(), w.bfloat16().float(), bias, stride=stride, padding=2)
+    assert rel(y.float().permute(0, 3, 1, 2), ref) < 4e-3
+    dy = torch.randn(batch, hs, hs, cs, device="cuda").bfloat16()
+    dw = torch.zeros_like(w)
+    sc = torch.zeros(5, cs, 64, device="cuda")
+    ops.conv3_wgrad(g, pim, dy, dw, sc)
+    ops.conv3_wgrad(g, pim, dy, dw, sc)  # accumulates; the scratch comes back zeroed
+    wr = w.clone().requires_grad_(True)
+    F.conv2d(x.bfloat16().float(), wr, None, stride=stride, padding=2).backward(dy.float().permute(0, 3, 1, 2))
+    assert rel(dw, 2 * wr.grad) < 4e-3 and float(sc.abs().max()) == 0.0
+    rows = batch * hs * hs
+    if rows % 128 == 0:
+        site = ops.BnSite(ops.bn_scratch(cs, 1, "cuda"), 1, rows, cs, torch.ones(cs, device="cuda"), torch.zeros(cs, device="cuda"),
+                          torch.zeros(cs, device="cuda"), torch.ones(cs, device="cuda"), None)
+        y2 = ops.conv3_fwd(g, pim, ww, bias, bn=site)
+        assert torch.equal(y2, y)
+        yf = y.float().view(rows, cs)
+        assert rel(site.mean_invstd[0, 0], yf.mean(0)) < 2e-3
+        assert rel(site.mean_invstd[0, 1], torch.rsqrt(yf.var(0, unbiased=False) + 1e-5)) < 2e-3
+
+
 def test_layout_kernels(ops):
     x = torch.randn(5, 64, 256, device="cuda").bfloat16()
     assert torch.equal(ops.transpose(x, 5, 64, 256), x.transpose(1, 2).contiguous())
@@ -177,7 +252,7 @@ def test_layout_kernels(ops):
     out = torch.tanh(y).permute(0, 3, 1, 2).contiguous()
     dout = torch.randn_like(out)
     bg = torch.zeros(3, device="cuda")
-    dy = ops.tanh_backward(dout, out, bg)
+    dy = ops.tanh_backward(dout, out, bg)  # (fp32 NCHW output; the padded-image form is tested above)
     ref = dout * (1 - out * out)
     assert rel(dy, ref) < 1e-6 and rel(bg, ref.sum((0, 2, 3))) < 1e-4
 

@@ -158,36 +158,36 @@ def check_linear_layer(ops, lin, inp, out, tag, dgrad_ref="own"):
 
 def check_conv3_layer(ops, conv, inp, out, stride, transposed, tag):
     """The three layers with 3 image channels (D convs.0, encoder features.0, decoder deconv4).  `inp` / `out` are the
-    oracle's layer input / output (with .grad).  Not transposed: forward from the fp32 NCHW image, weight gradient,
-    and (stride 1 only: the encoder's input needs none) the input gradient.  Transposed (deconv4): forward,
-    input-gradient (= a 3-channel convolution of the output gradient) and weight gradient."""
+    oracle's layer input / output (with .grad).  Not transposed: forward from the image (as a padded bf16 image),
+    weight gradient, and (stride 1 only: the encoder's input needs none) the input gradient.  Transposed (deconv4):
+    forward, input-gradient (= a 3-channel convolution of the output gradient) and weight gradient."""
     from disentangle_mlp_b200 import engine
 
     b = inp.shape[0]
     cs = conv.in_channels if transposed else conv.out_channels
     hs = 64 // stride
-    rows = b * hs * hs
     w = conv.weight.detach().cuda()
     bias = conv.bias.detach().cuda()
-    _, wu, wc = ops.pack_conv_weights(w, cs, 3, True, True, True)
+    _, wu, ww = engine.pack3(w)
+    g = ops.geom(b, hs, hs, cs, 3, stride)
     dw = torch.zeros_like(w)
     errs = {}
     if not transposed:
-        col = ops.im2col3(inp.detach().cuda().contiguous(), stride)
-        y = engine.col_conv_forward(col, wc, bias, rows, cs)
-        errs["fwd"] = rel(from_nhwc(y.view(b, hs, hs, cs)), out)
-        engine.col_conv_wgrad(col, nhwc16(out.grad).view(rows, cs), rows, cs, dw)
+        pim = ops.pad_image3(inp.detach().cuda().contiguous())
+        y = ops.conv3_fwd(g, pim, ww, bias)
+        errs["fwd"] = rel(from_nhwc(y), out)
+        ops.conv3_wgrad(g, pim, nhwc16(out.grad), dw)
         errs["wgrad"] = rel(dw, conv.weight.grad)
         if stride == 1:
-            dx = ops.conv_up(ops.geom(b, 64, 64, cs, 3, 1), nhwc16(out.grad), wu, out_f32=True)
+            dx = ops.conv_up(g, nhwc16(out.grad), wu, out_f32=True)
             errs["dgrad"] = rel(from_nhwc(dx), inp.grad)
     else:
-        y = ops.conv_up(ops.geom(b, 64, 64, cs, 3, 1), nhwc16(inp), wu, bias, out_f32=True)
+        y = ops.conv_up(g, nhwc16(inp), wu, bias, out_f32=True)
         errs["fwd"] = rel(from_nhwc(y), out)
-        col = ops.im2col3(out.grad.detach().cuda().contiguous(), 1)
-        dx = engine.col_conv_forward(col, wc, None, rows, cs)
-        errs["dgrad"] = rel(from_nhwc(dx.view(b, 64, 64, cs)), inp.grad)
-        engine.col_conv_wgrad(col, nhwc16(inp).view(rows, cs), rows, cs, dw)
+        pim = ops.pad_image3(out.grad.detach().cuda().contiguous())
+        dx = ops.conv3_fwd(g, pim, ww, None)
+        errs["dgrad"] = rel(from_nhwc(dx), inp.grad)
+        ops.conv3_wgrad(g, pim, nhwc16(inp), dw)
         errs["wgrad"] = rel(dw, conv.weight.grad)
     assert max(errs.values()) < TOL_LAYER, (tag, errs)
     return errs

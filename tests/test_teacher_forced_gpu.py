@@ -92,11 +92,13 @@ def test_teacher_forced_one_step_map(workload, nsteps):
     print(workload, json.dumps(report))
     # losses of the one-step map: north-star bf16 tolerance in the median over the trajectory, and a bound on the
     # 90th percentile (single steps where D sits at the BCE clamp or a loss crosses ~0 have large RELATIVE error)
+    # (measured on B200, round 2: medians <= 1e-3 for every quantity incl. KL 9e-5 and Dis_l 9e-4; worst single step 2.4e-2)
     for k, v in devs.items():
         assert np.all(np.isfinite(v)), k
         assert np.median(v) <= 1e-2, (k, report[k])
-        assert np.percentile(v, 90) <= 5e-2, (k, report[k])
+        assert np.percentile(v, 90) <= 1e-2, (k, report[k])
+        assert np.max(v) <= 1e-1, (k, report[k])
     # parameter update of one step (three Adam updates): Adam normalises every element's step to ~lr, so elements
     # whose gradient is at the bf16 noise level move in a noise-determined direction in the reference too
-    for k, v in upd.items():
-        assert np.median(v) <= 0.35, (k, report["update_rel_err"][k])
+    for k, v in upd.items():  # (measured medians: EG 0.03, D 1e-5)
+        assert np.median(v) <= 0.15, (k, report["update_rel_err"][k])
