@@ -260,7 +260,7 @@ def conv3_wgrad(g, pim, small, dw, cache, name):
 
 
 # ------------------------------------------------------------------------------------------ Discriminator
-def discriminator_forward(x, P, B, cache: OperandCache, training=True, groups=1, pim=None):
+def discriminator_forward(x, P, B, cache: OperandCache, training=True, groups=1, pim=None, before_linear=None):
     """Discriminator_celeba.forward (model.py:410-416). x: fp32 NCHW [b,3,64,64], or None with pim = the batch as a
     padded bf16 image (ops.pad_image3 / the decoder's pim output).  Returns prob [b], feat [b,2048].
     groups > 1: the batch stacks `groups` separate batches (e.g. real | fake); every GEMM processes them together while
@@ -289,6 +289,8 @@ def discriminator_forward(x, P, B, cache: OperandCache, training=True, groups=1,
     raw4 = ops.conv_down(g4, S.a3, wd4, P["convs.9.bias"].detach(), bn=f4)
     a4, S.bn4 = bn_act_forward(raw4, b * 64, 256, P, B, "convs.10", ACT_LEAKY, training, groups, cache, f4)
     S.flat = ops.transpose(a4, b, 64, 256)  # NHWC [b,64,256] -> NCHW flatten order [b,256*64]
+    if before_linear:  # data parallel, sharded Adam: the all-gather of the updated bf16 weight must have landed
+        before_linear()
     wl = _lin_w(cache, "lth_features.0", P["lth_features.0.weight"])
     acc = linear_forward(S.flat, wl, None, b, 2048, 16384)
     S.feat, _ = ops.bias_act(acc, b, 2048, P["lth_features.0.bias"].detach(), ACT_LEAKY, LEAKY, True, False)
@@ -370,7 +372,7 @@ def discriminator_backward(S, dprob, dfeat, P, G, cache: OperandCache, need_dx=T
 
 
 # ------------------------------------------------------------------------------------------ Encoder
-def encoder_forward(x, P, B, cache: OperandCache, training=True, pim=None):
+def encoder_forward(x, P, B, cache: OperandCache, training=True, pim=None, before_heads=None):
     """VAE.encode (model.py:511-522). x: fp32 NCHW, or None with pim = the batch as a padded bf16 image.
     Returns mu, logvar fp32 [b,128]."""
     S = SimpleNamespace()
@@ -392,6 +394,8 @@ def encoder_forward(x, P, B, cache: OperandCache, training=True, pim=None):
     raw3 = ops.conv_down(g3, S.a2, wd3, P["features.6.bias"].detach(), bn=f3)
     a3, S.bn3 = bn_act_forward(raw3, b * 64, 256, P, B, "features.7", ACT_RELU, training, 1, cache, f3)
     S.flat = ops.transpose(a3, b, 64, 256)
+    if before_heads:  # (see discriminator_forward)
+        before_heads()
     outs = []
     S.heads = {}
     for head in ("x_to_mu", "x_to_logvar"):

@@ -158,6 +158,7 @@ class FlatParams:
                 else:
                     self.cache.static_packs[n[:-len(".weight")]] = engine.pack3(p.detach())
         self._zero_ranges, self._late_ranges = plan["zero_ranges"], plan["late_ranges"]
+        self.reducer, self.shard, self._gather_pending = None, False, False
         self.params_changed()
         # module.load_state_dict() copies into the re-homed fp32 masters: refresh the bf16 shadow / operand packs
         module.register_load_state_dict_post_hook(lambda _m, _keys: self.params_changed())
@@ -171,10 +172,24 @@ class FlatParams:
             return buf[o:o + k].view(5, 5, cs, cb).permute(2, 3, 0, 1)
         return buf[o:o + k].view(shape)
 
+    def attach(self, reducer):
+        """Data parallel: the three 16384x2048 Linear weights (92 % of all parameters) get a SHARDED optimizer step
+        (ZeRO-1 on those tensors): their bf16 gradients are reduce-scattered, every rank runs Adam on 1/world of each
+        tensor (fp32 master, m, v of its chunk) and the bf16 shadow -- what the GEMMs read -- is all-gathered.  Same wire
+        bytes as the all-reduce it replaces, but Adam's HBM traffic drops by (world-1)/world on 92 % of the parameters.
+        The fp32 masters / moments of the other ranks' chunks go stale: gather_masters() before reading them
+        (checkpoints).  DM_SHARD_BIG=0: replicated Adam + all-reduce."""
+        self.reducer = reducer
+        self.shard = bool(reducer.on and self.big16 and os.environ.get("DM_SHARD_BIG", "1") != "0"
+                          and all(self.P[n].numel() % reducer.world == 0 for n in self.big16))
+
     def reduce_early(self, reducer, name):
         if name in self.off16:
             o = self.off16[name]
-            reducer.allreduce_async(self.grad16, o, o + self.P[name].numel())
+            if self.shard:
+                reducer.reduce_scatter_async(self.grad16, o, self.P[name].numel())
+            else:
+                reducer.allreduce_async(self.grad16, o, o + self.P[name].numel())
             return
         o = self.offsets[name]
         reducer.allreduce_async(self.grad, o, o + self.P[name].numel())
@@ -234,16 +249,58 @@ class FlatParams:
         for lo, hi in self._zero_ranges:
             self.grad[lo:hi].zero_()
 
-    def adam(self, grad_scale=1.0):
+    def adam(self, grad_scale=1.0, gather=True):
         """One Adam update; the step count lives on the device (incremented by the kernel) so that the call can be
-        replayed from a CUDA graph; the host mirror `step_count` is kept for the optimizer state dict."""
+        replayed from a CUDA graph; the host mirror `step_count` is kept for the optimizer state dict.
+        Sharded big tensors (attach()): only this rank's chunk is updated; gather=True launches the all-gather of the
+        bf16 shadows right away (asynchronously on the NCCL stream: reducer.wait() before their first use),
+        gather=False leaves it pending for gather_if_pending() -- e.g. at the start of the next step, under work that
+        does not read those weights."""
         self.step_count += 1
         for i, (lo, hi, o16) in enumerate(self._segments):
-            g = self.grad[lo:hi] if o16 is None else self.grad16[o16:o16 + (hi - lo)]
+            if o16 is not None and self.shard:
+                a, b = self.reducer.chunk(hi - lo)
+                g = self.grad16[o16 + a:o16 + b]
+                lo, hi = lo + a, lo + b
+            else:
+                g = self.grad[lo:hi] if o16 is None else self.grad16[o16:o16 + (hi - lo)]
             ops.adam_step(self.flat[lo:hi], g, self.m[lo:hi], self.v[lo:hi], self.lr, self.betas[0], self.betas[1],
                           self.eps, 0, grad_scale, self.shadow[lo:hi], step_dev=self.step_dev, count_step=(i == 0))
         self.refresh_packs()  # bf16 conv operand packs follow the updated fp32 weights
         self.touch()
+        if self.shard:
+            self._gather_pending = True
+            if gather:
+                self.gather_if_pending()
+
+    def gather_if_pending(self):
+        """All-gather the bf16 shadows of the sharded tensors (asynchronous, NCCL stream) if an update is pending."""
+        if not (self.shard and self._gather_pending):
+            return
+        for n in self.big16:
+            self.reducer.all_gather_async(self.shadow, self.offsets[n], self.P[n].numel())
+        self._gather_pending = False
+        self._gather_event = self.reducer.mark() if self.shadow.is_cuda else None
+
+    def wait_gathered(self):
+        """Order the current stream behind the last all-gather of this optimizer's bf16 shadows (and only that)."""
+        if not self.shard:
+            return
+        ev = getattr(self, "_gather_event", None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+        elif not self.shadow.is_cuda:
+            self.reducer.wait()
+
+    def gather_masters(self):
+        """Sharded tensors: make the fp32 masters and Adam moments complete on every rank (checkpoint / comparison)."""
+        if not self.shard:
+            return
+        self.gather_if_pending()
+        for n in self.big16:
+            for buf in (self.flat, self.m, self.v):
+                self.reducer.all_gather_async(buf, self.offsets[n], self.P[n].numel())
+        self.reducer.wait()
 
     def snapshot(self):
         return {"flat": self.flat.clone(), "m": self.m.clone(), "v": self.v.clone(), "step": self.step_count,
@@ -257,6 +314,7 @@ class FlatParams:
         self.step_dev.fill_(snap["step"])
         for k, b in self.buffers.items():
             b.copy_(snap["buffers"][k])
+        self._gather_pending = False
         self.params_changed()
 
     def optimizer_state_dict(self):
@@ -303,6 +361,7 @@ class GradReducer:
         self.dist = dist
         self.on = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self.world = dist.get_world_size() if self.on else 1
+        self.rank = dist.get_rank() if self.on else 0
         self.comm_stream = None
         self.handles = []
         self.cuda_pending = False
@@ -326,16 +385,60 @@ class GradReducer:
         hi = flat.numel() if hi is None else hi
         view = flat[lo:hi]
         if flat.is_cuda:
-            if self.comm_stream is None:
-                self.comm_stream = torch.cuda.Stream()
-            ev = torch.cuda.Event()
-            ev.record()
-            with torch.cuda.stream(self.comm_stream):
-                self.comm_stream.wait_event(ev)
-                self.dist.all_reduce(view, op=self.dist.ReduceOp.SUM)
-            self.cuda_pending = True
+            self._on_comm_stream(lambda: self.dist.all_reduce(view, op=self.dist.ReduceOp.SUM))
         else:
             self.handles.append(self.dist.all_reduce(view, op=self.dist.ReduceOp.SUM, async_op=True))
+
+    def _on_comm_stream(self, fn):
+        """Enqueue fn() on the NCCL side stream, ordered after the work already queued on the current stream."""
+        if self.comm_stream is None:
+            self.comm_stream = torch.cuda.Stream()
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(ev)
+            fn()
+        self.cuda_pending = True
+
+    def mark(self):
+        """An event on the NCCL stream behind everything enqueued so far: lets a consumer wait for THAT work only
+        (current_stream().wait_event), not for collectives enqueued later.  None without CUDA work."""
+        if self.comm_stream is None:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(self.comm_stream)
+        return ev
+
+    def chunk(self, n):
+        """This rank's slice [lo, hi) of a tensor of n elements split evenly over the ranks."""
+        c = n // self.world
+        return self.rank * c, (self.rank + 1) * c
+
+    def reduce_scatter_async(self, flat, lo, n):
+        """In place: this rank's chunk of flat[lo:lo+n] receives the SUM over ranks (the other chunks become garbage
+        nobody reads).  Half the wire bytes of an all-reduce; the other half is the all-gather of what Adam writes."""
+        if not self.on:
+            return
+        assert n % self.world == 0
+        view = flat[lo:lo + n]
+        a, b = self.chunk(n)
+        if flat.is_cuda:
+            self._on_comm_stream(lambda: self.dist.reduce_scatter_tensor(view[a:b], view, op=self.dist.ReduceOp.SUM))
+        else:  # gloo (CPU tests) has no reduce-scatter: all-reduce, the chunk is then what a reduce-scatter leaves
+            self.handles.append(self.dist.all_reduce(view, op=self.dist.ReduceOp.SUM, async_op=True))
+
+    def all_gather_async(self, flat, lo, n):
+        """In place: every rank's chunk of flat[lo:lo+n] is broadcast to all ranks."""
+        if not self.on:
+            return
+        assert n % self.world == 0
+        view = flat[lo:lo + n]
+        a, b = self.chunk(n)
+        if flat.is_cuda:
+            self._on_comm_stream(lambda: self.dist.all_gather_into_tensor(view, view[a:b]))
+        else:
+            mine = view[a:b].clone()
+            self.handles.append(self.dist.all_gather_into_tensor(view, mine, async_op=True))
 
     def wait(self):
         for h in self.handles:
@@ -364,6 +467,20 @@ class _Base:
 
     def flat_params(self):
         raise NotImplementedError
+
+    def _attach(self):
+        for fp in self.flat_params():
+            fp.attach(self.dist)
+
+    def sync(self, masters=False):
+        """Data parallel with sharded Adam: complete every pending all-gather (call before the modules are used
+        outside step(): sampling, evaluation); masters=True also gathers the fp32 masters / Adam moments (before
+        state_dict() / optimizer_state_dict(): checkpoints)."""
+        for fp in self.flat_params():
+            fp.gather_if_pending()
+            if masters:
+                fp.gather_masters()
+        self.dist.wait()
 
     @staticmethod
     def draw_labels():
@@ -449,8 +566,14 @@ class _Base:
 
         l0 = _lib.launch_count()
         self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
-            self._gmetrics = self._step_impl(self._gx, self._glabels[0:1], self._glabels[1:2], *self._grands)
+        try:
+            with torch.cuda.graph(self._graph):
+                self._gmetrics = self._step_impl(self._gx, self._glabels[0:1], self._glabels[1:2], *self._grands)
+        finally:
+            # events recorded while capturing belong to the graph: they must not be waited on by eager code afterwards
+            for fp in fps:
+                fp._gather_event = None
+            self.dist.cuda_pending = False
         self.graph_launches_per_step = _lib.launch_count() - l0  # libdm_b200 kernels captured in one step
         self._adams_per_step = [fp.step_count - c for fp, c in zip(fps, counts0)]
         for fp, s in zip(fps, snaps):  # undo the warm-up / capture-time bookkeeping: training state as before
@@ -492,6 +615,7 @@ class _Base:
         for fp, n in zip(self.flat_params(), self._adams_per_step):
             fp.step_count += n
             fp.touch()
+            fp._gather_pending = fp.shard  # the step's last sharded update is gathered at the start of the next replay
         self.metrics = gmetrics
         return self.metrics
 
@@ -504,6 +628,7 @@ class VAETrainer(_Base):
         self.model = model
         self.fp = FlatParams(model, lr)
         self.beta = beta
+        self._attach()
 
     n_rands = 1  # eps
 
@@ -520,9 +645,11 @@ class VAETrainer(_Base):
         b = data.shape[0]
         loss = _scalar(dev)
         fp.zero_grad()
+        fp.gather_if_pending()  # sharded Adam: the previous step's update reaches the other ranks under the encoder convs
         pim = ops.pim_empty(b, dev)
         data = self._ingest(data, pim)
-        mu, logvar, Se = engine.encoder_forward(None, fp.P, fp.buffers, fp.cache, True, pim=pim)
+        mu, logvar, Se = engine.encoder_forward(None, fp.P, fp.buffers, fp.cache, True, pim=pim,
+                                                before_heads=fp.wait_gathered if fp.shard else None)
         if eps is None:
             eps = torch.randn_like(mu)
         _, z16 = ops.reparam_forward(mu, logvar, eps)
@@ -537,7 +664,7 @@ class VAETrainer(_Base):
         engine.encoder_backward(Se, dmu, dlv, fp.P, fp.G, fp.cache, True, overwrite_big=True,
                                 grad_ready=self._early(fp))
         fp.reduce_rest_and_wait(self.dist)
-        fp.adam()
+        fp.adam(gather=False)
         self.metrics = {"loss": loss}
         return self.metrics
 
@@ -550,6 +677,7 @@ class GANTrainer(_Base):
         self.netG, self.netD = netG, netD
         self.fg = FlatParams(netG, lr)
         self.fd = FlatParams(netD, lr)
+        self._attach()
 
     n_rands = 1  # noise
 
@@ -588,7 +716,8 @@ class GANTrainer(_Base):
         fd.adam()
         # ---- (2) generator: re-score the same fake batch with the updated D (:118-128)
         fg.zero_grad()
-        prob_g, _, S3 = engine.discriminator_forward(None, fd.P, fd.buffers, fd.cache, True, pim=pim[b:])
+        prob_g, _, S3 = engine.discriminator_forward(None, fd.P, fd.buffers, fd.cache, True, pim=pim[b:],
+                                                     before_linear=fd.wait_gathered if fd.shard else None)
         d3 = self._bce(prob_g, real_label, errG, sum_dgz2)
         dfake = engine.discriminator_backward(S3, d3, None, fd.P, None, fd.cache, True, False)
         engine.decoder_backward(Sg, dfake, fg.P, fg.G, fg.cache, False, True, overwrite_big=True)
@@ -607,6 +736,7 @@ class BetaVAEGANTrainer(_Base):
         self.feg = FlatParams(netEG, lr)
         self.fd = FlatParams(netD, lr)
         self.beta = float(beta)
+        self._attach()
 
     n_rands = 3  # noise, eps of the decoder phase, eps of the encoder phase
 
@@ -628,6 +758,9 @@ class BetaVAEGANTrainer(_Base):
             _scalar(dev) for _ in range(9))
         # every image the networks read, as padded bf16 images stacked [data | fake | recon]: each producer writes its
         # slice once, D's stacked passes and the two encoder forwards read them in place (no torch.cat, no im2col)
+        # sharded Adam (data parallel): the encoder-phase update of the previous step reaches the other ranks now, under
+        # the discriminator phase, which does not read the encoder's weights
+        feg.gather_if_pending()
         pim = ops.pim_empty(3 * b, dev)
         data = self._ingest(data, pim[:b])
 
@@ -656,14 +789,16 @@ class BetaVAEGANTrainer(_Base):
         # ... while the encoder / decoder forward of this phase, which does not read D, is computed; the D update
         # (:123) lands before D is evaluated again, as in the reference
         feg.zero_grad()
-        mu, logvar, Se = engine.encoder_forward(None, feg.P, feg.buffers, feg.cache, True, pim=pim[:b])
+        mu, logvar, Se = engine.encoder_forward(None, feg.P, feg.buffers, feg.cache, True, pim=pim[:b],
+                                                before_heads=feg.wait_gathered if feg.shard else None)
         if eps_dec is None:
             eps_dec = torch.randn_like(mu)
         _, z16 = ops.reparam_forward(mu, logvar, eps_dec)
         recon, Sg2 = engine.decoder_forward(z16, feg.P, feg.buffers, feg.cache, True, pim_out=pim[2 * b:])
         self._join_side(fork)
         # D(data) | D(fake) | D(recon) in one stacked pass (BatchNorm per pass, in the reference's order :129,147,150)
-        prob3, feat3, S345 = engine.discriminator_forward(None, fd.P, fd.buffers, fd.cache, True, groups=3, pim=pim)
+        prob3, feat3, S345 = engine.discriminator_forward(None, fd.P, fd.buffers, fd.cache, True, groups=3, pim=pim,
+                                                          before_linear=fd.wait_gathered if fd.shard else None)
         sim_real, sim_recon = feat3[:b], feat3[2 * b:]
         dprob2 = torch.empty(2 * b, dtype=F32, device=dev)
         ops.bce_const(prob3[b:2 * b], real_label, errG_fake, 1.0, n_total=nt, dprob=dprob2[:b])
@@ -689,7 +824,8 @@ class BetaVAEGANTrainer(_Base):
 
         # ================= "encoder" phase (:167-193): gradient of beta*KL + ||recon - x||^2, fresh forward
         feg.zero_grad()
-        mu, logvar, Se = engine.encoder_forward(None, feg.P, feg.buffers, feg.cache, True, pim=pim[:b])
+        mu, logvar, Se = engine.encoder_forward(None, feg.P, feg.buffers, feg.cache, True, pim=pim[:b],
+                                                before_heads=feg.wait_gathered if feg.shard else None)
         if eps_enc is None:
             eps_enc = torch.randn_like(mu)
         _, z16 = ops.reparam_forward(mu, logvar, eps_enc)
@@ -704,7 +840,7 @@ class BetaVAEGANTrainer(_Base):
         engine.encoder_backward(Se, dmu, dlv, feg.P, feg.G, feg.cache, True, overwrite_big=True,
                                 grad_ready=self._early(feg))
         feg.reduce_rest_and_wait(self.dist)
-        feg.adam()
+        feg.adam(gather=False)  # (its all-gather rides under the next step's discriminator phase)
         self.metrics = {"errD_real": errD_real, "errD_fake": errD_fake, "D_x": sum_dx / b, "errG_fake": errG_fake,
                         "errG_recon": errG_recon, "sim": sim_loss, "recon_dec": loss_dec, "kld": kld,
                         "recon_enc": loss_enc}

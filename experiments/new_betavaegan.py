@@ -37,6 +37,7 @@ def main():
             if rank == 0 and i % opt.log_interval == 0:
                 print(f"epoch {epoch} step {i}: " + " ".join(f"{k}={float(v):.4f}" for k, v in m.items()), flush=True)
         enc, dec, dx = (float(v) / loader.dataset_len * world for v in sums)
+        T.sync(masters=True)  # (data parallel: complete the sharded optimizer state before it is read)
         if rank == 0:
             print(f"====> Epoch: {epoch} Avg Encoder Loss: {enc:.4f} Avg Decoder Loss: {dec:.4f} Dx: {dx:.4f}")
             if opt.model_path:  # new_betavaegan.py:222-228

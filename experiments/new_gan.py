@@ -30,6 +30,7 @@ def main():
                 print("[%d/%d][%d/%d]\tLoss_D: %.4f\tLoss_G: %.4f\tD(x): %.4f\tD(G(z)): %.4f / %.4f" % (
                     epoch, opt.epochs, i, len(loader), float(m["errD"]), float(m["errG"]), float(m["D_x"]),
                     float(m["D_G_z1"]), float(m["D_G_z2"])), flush=True)
+        T.sync(masters=True)  # (data parallel: complete the sharded optimizer state before it is read)
         if rank == 0 and opt.model_path:  # new_gan.py:169-174 (DataParallel state_dicts: "module." prefix)
             save_checkpoint("gan", opt.model_path, epoch + 1, (netG, netD), (T.fg, T.fd))
 

@@ -27,6 +27,7 @@ def main():
             total = m["loss"] if total is None else total + m["loss"]
             if rank == 0 and i % opt.log_interval == 0:
                 print(f"Train Epoch: {epoch} [{i}/{len(loader)}]\tLoss: {float(m['loss']) / data.shape[0]:.6f}", flush=True)
+        T.sync(masters=True)  # (data parallel: complete the sharded optimizer state before it is read)
         if rank == 0:
             print(f"====> Epoch: {epoch} Average loss: {float(total) / loader.dataset_len * world:.4f}")
             if opt.model_path:  # new_vae.py:88-91

@@ -65,6 +65,7 @@ def _worker_schedule(rank, world, port, q):
     fp = object.__new__(tr.FlatParams)
     fp.names, fp.offsets, fp.total, fp._small_end = plan["names"], plan["offsets"], plan["total"], plan["small_end"]
     fp.off16, fp._late_ranges, fp._tail_done = plan["off16"], plan["late_ranges"], None
+    fp.shard = False
     fp.P = {n: SimpleNamespace(numel=lambda k=plan["numel"][n]: k) for n, _ in named}
     g = torch.Generator().manual_seed(100 + rank)
     fp.grad = torch.randn(plan["total"], generator=g)
@@ -98,6 +99,79 @@ def _worker_schedule(rank, world, port, q):
         ok = False
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
+
+
+def _worker_sharded(rank, world, port, q):
+    """Sharded optimizer step of a big tensor (ZeRO-1 on the 16384x2048 Linear weights): reduce-scatter of the bf16
+    gradient, an Adam-like update of THIS rank's chunk only, all-gather of the bf16 shadow, and gather_masters() --
+    through the real GradReducer / FlatParams methods over gloo.  Every rank must end up with the shadow (and, after
+    gather_masters, the masters) that a replicated update on the summed gradient produces."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from types import SimpleNamespace
+
+    from disentangle_mlp_b200 import trainer as tr
+
+    ok = True
+    try:
+        n = 4096 * world
+        red = tr.GradReducer()
+        fp = object.__new__(tr.FlatParams)
+        fp.reducer, fp.shard, fp._gather_pending = red, True, False
+        fp.big16, fp.off16, fp.offsets = ["w"], {"w": 0}, {"w": 64}
+        fp.P = {"w": SimpleNamespace(numel=lambda: n)}
+        torch.manual_seed(7)
+        init = torch.randn(64 + n)
+        fp.flat, fp.m, fp.v = init.clone(), torch.zeros(64 + n), torch.zeros(64 + n)
+        fp.shadow = init.bfloat16()
+        g_all = [torch.randn(n, generator=torch.Generator().manual_seed(50 + r)).bfloat16() for r in range(world)]
+        fp.grad16 = g_all[rank].clone()
+        fp.reduce_early(red, "w")  # reduce-scatter (gloo: all-reduce)
+        red.wait()
+        a, b = red.chunk(n)
+        gsum = sum(g.float() for g in g_all)
+        ok = ok and torch.allclose(fp.grad16[a:b].float(), gsum[a:b], rtol=2e-2, atol=2e-2)
+        # "Adam" on the own chunk: p -= 0.1 * g ; shadow = bf16(p)
+        fp.flat[64 + a:64 + b] -= 0.1 * fp.grad16[a:b].float()
+        fp.m[64 + a:64 + b] = fp.grad16[a:b].float()
+        fp.shadow[64 + a:64 + b] = fp.flat[64 + a:64 + b].bfloat16()
+        stale = fp.flat.clone()
+        fp._gather_pending = True
+        fp.gather_if_pending()
+        fp.wait_gathered()
+        want = init.clone()
+        want[64:] -= 0.1 * gsum
+        ok = ok and torch.allclose(fp.shadow[64:].float(), want[64:], rtol=2e-2, atol=2e-2)
+        ok = ok and torch.equal(fp.shadow[:64], init[:64].bfloat16())  # neighbours untouched
+        # masters: other ranks' chunks are stale until gather_masters()
+        if world > 1:
+            oa = 64 + ((rank + 1) % world) * (n // world)
+            ok = ok and torch.equal(stale[oa:oa + 8], init[oa:oa + 8])
+        fp.gather_masters()
+        ok = ok and torch.allclose(fp.flat[64:], want[64:], rtol=2e-2, atol=2e-2)
+        ok = ok and torch.allclose(fp.m[64:], gsum, rtol=2e-2, atol=2e-2)
+    except Exception as e:  # noqa: BLE001
+        import traceback
+
+        traceback.print_exc()
+        print("sharded worker failed:", repr(e), flush=True)
+        ok = False
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_sharded_update_of_a_big_tensor():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_sharded, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
 
 
 def test_gloo_world2_reduce_schedule_on_flat_buffers():

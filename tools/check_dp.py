@@ -43,6 +43,7 @@ def main():
             x = (torch.rand(b, 3, 64, 64) * 2 - 1).cuda()
             for _ in range(3):
                 T.step(x)
+            T.sync(masters=True)  # sharded Adam: gather the other ranks' chunks of the big tensors before comparing
             worst = 0.0
             for fp in T.flat_params():
                 ref = fp.flat.clone()
