@@ -89,7 +89,8 @@ _SIGS = {
 }
 
 #: every symbol include/dm_b200.h declares
-EXPORTED = ["dm_last_error", "dm_version", "dm_launch_count", "dm_bn_scratch_floats", "dm_pim_elems", *list(_SIGS)]
+EXPORTED = ["dm_last_error", "dm_version", "dm_launch_count", "dm_bn_scratch_floats", "dm_pim_elems", "dm_workspace_bytes",
+            *list(_SIGS)]
 
 _lib = None
 
@@ -115,6 +116,8 @@ def load():
     lib.dm_bn_scratch_floats.argtypes = [c_int, c_int]
     lib.dm_pim_elems.restype = c_ll
     lib.dm_pim_elems.argtypes = [c_int]
+    lib.dm_workspace_bytes.restype = c_ll
+    lib.dm_workspace_bytes.argtypes = [c_int, C.POINTER(c_ll), c_int]
     for name, args in _SIGS.items():
         fn = getattr(lib, name)
         fn.argtypes = args

@@ -248,6 +248,17 @@ int dm_adam_step_ex(float* p, const void* g, int g_bf16, float* m, float* v, lon
                     double beta2, double eps, int step, int* step_dev, int count_step, float grad_scale,
                     void* shadow_bf16, void* stream);
 
+/* Workspace query: bytes of caller-owned scratch an op needs; all tensors -- inputs, outputs, saved-for-
+ * backward, scratch -- are allocated by the caller (PyTorch's caching allocator) and borrowed for the call; the library
+ * allocates nothing except cached tensor-map descriptors.  dims per op:
+ *   DM_WS_GEMM {m,n,k,splits} = 0 (split-K reduces into D); DM_WS_CONV_FWD / _DGRAD {..} = 0 (no im2col buffer);
+ *   DM_WS_CONV_WGRAD {cs,cb} packed-gradient scratch when dw is in the parameter layout; DM_WS_CONV3_WGRAD {cs};
+ *   DM_WS_BATCHNORM {c,groups} slot scratch (= 4 * dm_bn_scratch_floats); DM_WS_PADDED_IMAGE {batch};
+ *   DM_WS_COLSUM {rows,c} partial sums of dm_act_backward / dm_colsum.  Returns -1 for an unknown op. */
+enum { DM_WS_GEMM = 0, DM_WS_CONV_FWD = 1, DM_WS_CONV_DGRAD = 2, DM_WS_CONV_WGRAD = 3, DM_WS_CONV3_WGRAD = 4,
+       DM_WS_BATCHNORM = 5, DM_WS_PADDED_IMAGE = 6, DM_WS_COLSUM = 7 };
+long long dm_workspace_bytes(int op, const long long* dims, int ndims);
+
 /* Per-launch CUDA-event timing of the GEMM-class kernel (bench.py roofline). dm_profile_read synchronises the
  * device and returns the summed launch durations, algorithmic FLOPs (2*M*N*K; convolutions: 2*25*b*hs*ws*cs*cb)
  * and launch count since the previous read. */

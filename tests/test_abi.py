@@ -73,6 +73,20 @@ def test_struct_layouts_match_the_c_compiler(tmp_path):
                                                    ctypes.sizeof(_lib.ConvGeom)]
 
 
+def test_workspace_query(lib):
+    def ws(op, *dims):
+        arr = (ctypes.c_longlong * len(dims))(*dims)
+        return lib.dm_workspace_bytes(op, arr, len(dims))
+
+    assert ws(0, 64, 2048, 16384, 18) == 0 and ws(1, 64, 8, 8, 256, 256) == 0  # GEMM, implicit-GEMM convolutions
+    assert ws(3, 256, 128) == 25 * 256 * 128 * 4
+    assert ws(4, 32) == 5 * 32 * 64 * 4
+    assert ws(5, 256, 3) == 4 * lib.dm_bn_scratch_floats(256, 3)
+    assert ws(6, 192) == 2 * lib.dm_pim_elems(192)
+    assert ws(7, 64, 2048) == lib.dm_bn_parts(64, 2048) * 2048 * 4
+    assert ws(99) == -1 and b"unknown op" in lib.dm_last_error()
+
+
 def test_argument_errors_do_not_need_a_gpu(lib):
     from disentangle_mlp_b200 import _lib
 
