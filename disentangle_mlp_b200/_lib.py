@@ -44,6 +44,10 @@ _SIGS = {
     "dm_conv_down": [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_void_p, C.POINTER(BnFuse), c_void_p],
     "dm_conv_up": [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_void_p, c_int, C.POINTER(BnFuse), c_void_p],
     "dm_conv_wgrad": [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+    "dm_gemm_tf32": [C.POINTER(GemmDesc), c_void_p],
+    "dm_conv_down_tf32": [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "dm_conv_up_tf32": [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "dm_conv_wgrad_tf32": [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_void_p],
     "dm_unpack_conv_grad": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "dm_profile_enable": [c_int],
     "dm_profile_dump": [C.c_char_p],

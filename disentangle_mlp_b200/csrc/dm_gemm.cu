@@ -51,6 +51,7 @@ struct alignas(64) GemmParams {
   CUtensorMap map_b;
   int mode;
   int a_mn, b_mn;  // 0 = K-major, 1 = MN-major
+  int tf32;        // 1: fp32 operands read as TF32 (kind::tf32): kc = 32 elements (128 B), MN-major atoms 32 x 32
   int kc;          // K elements per k-block: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B, K-major only)
   int bn;          // N tile (multiple of 16, <= 256)
   int stages;
@@ -179,7 +180,9 @@ __device__ __forceinline__ TileWork decode_tile(const GemmParams& p, int t, int 
 
 // kCG2 = true: CTA-pair instantiation (contains cta_group::2 instructions, so it MUST be launched with an even
 // cluster dimension); kCG2 = false: single-CTA MMA (optionally with multicast pairs).
-template <bool kCG2>
+// kTF32 = true: fp32 operands read as TF32 (tcgen05.mma.kind::tf32, K = 8 per instruction): every k-block is 32 elements =
+// 128 bytes per row, so the K-major byte layout is identical to bf16's; MN-major atoms are 32 elements x 32 k-rows (4 KB).
+template <bool kCG2, bool kTF32 = false>
 __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
@@ -191,8 +194,11 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
   const int t_begin = (p.cluster == 2) ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int t_step = (p.cluster == 2) ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
-  const int a_bytes = p.a_mn ? 2 * kAtomBytes : 128 * p.kc * 2;
-  const int b_bytes = p.b_mn ? max(1, p.bn >> 6) * kAtomBytes : (kCG2 ? (p.bn >> 1) : p.bn) * p.kc * 2;
+  constexpr int kEsz = kTF32 ? 4 : 2;               // operand element size
+  constexpr int kAtomW = kTF32 ? 32 : 64;            // MN elements of one 128-byte MN-major atom row
+  constexpr int kAtomB = kTF32 ? 4096 : kAtomBytes;  // bytes of one MN-major atom (32 / 64 k-rows x 128 B)
+  const int a_bytes = p.a_mn ? (128 / kAtomW) * kAtomB : 128 * p.kc * kEsz;
+  const int b_bytes = p.b_mn ? max(1, p.bn / kAtomW) * kAtomB : (kCG2 ? (p.bn >> 1) : p.bn) * p.kc * kEsz;
   const int stage_bytes = a_bytes + b_bytes;
 
   uint8_t* staging = smem + p.stages * stage_bytes;  // epi_bufs x 4 warps x 4 KB, TMA epilogue only
@@ -273,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
           const int cpt = p.cpt;
           int tt = w.kb0 / cpt;            // per tile, not per k-block
           int chunk = w.kb0 - tt * cpt;
-          const int b_atoms = p.b_mn ? (p.bn >> 6) : 0;
+          const int b_atoms = p.b_mn ? (p.bn / kAtomW) : 0;
           while (nkb > 0) {
             const Tap tap = p.taps[w.tap_begin + tt];
             const int cw = w0 + tap.dw, cp = tap.dp, ch = h0 + tap.dh, wt = tap.wt;
@@ -298,7 +304,7 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
                     tma_load_3d_u32(sa + a_bytes, map_b, fb, kcol, ncol0, wt);
                   } else {
                     for (int a = 0; a < b_atoms; ++a)
-                      tma_load_3d_u32(sa + a_bytes + a * kAtomBytes, map_b, fb, ncol0 + a * 64, kcol, wt);
+                      tma_load_3d_u32(sa + a_bytes + a * kAtomB, map_b, fb, ncol0 + a * kAtomW, kcol, wt);
                   }
                 }
               }
@@ -321,7 +327,7 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
           const Tap tap2 = p.taps[p.wgrad_win ? 2 * ut + 1 : ut];  // second A atom (window mode only)
           const int mch0 = w.m_tile * 128;
           const int nch0 = w.n_tile * p.bn;
-          const int b_atoms = max(1, p.bn >> 6);  // (bn = 32: one 64-wide box whose upper half is out of bounds = zeros)
+          const int b_atoms = max(1, p.bn / kAtomW);  // (bf16, bn = 32: one 64-wide box, upper half out of bounds = zeros)
           // pixel-tile coordinates of k-block kb: (w0, h0, n0) = (kb * tw_step, (kb % tpi) * th_step, (kb / tpi) *
           // tn_step), advanced incrementally
           int w0 = w.kb0 * p.tw_step;
@@ -339,12 +345,15 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
             if (leader) {
               mbar_arrive_expect_tx_u32(fb, tx_bytes);
               tma_load_5d_u32(sa, map_a, fb, mch0 + adc, w0 + adw, adp, h0 + adh, n0);
-              if (p.wgrad_win)
-                tma_load_5d_u32(sa + kAtomBytes, map_a, fb, tap2.dc, w0 + tap2.dw, tap2.dp, h0 + tap2.dh, n0);
-              else
-                tma_load_5d_u32(sa + kAtomBytes, map_a, fb, mch0 + 64 + adc, w0 + adw, adp, h0 + adh, n0);
+              if (p.wgrad_win) {
+                tma_load_5d_u32(sa + kAtomB, map_a, fb, tap2.dc, w0 + tap2.dw, tap2.dp, h0 + tap2.dh, n0);
+              } else {
+#pragma unroll
+                for (int a = 1; a < 128 / kAtomW; ++a)
+                  tma_load_5d_u32(sa + a * kAtomB, map_a, fb, mch0 + a * kAtomW + adc, w0 + adw, adp, h0 + adh, n0);
+              }
               for (int a = 0; a < b_atoms; ++a)
-                tma_load_5d_u32(sa + a_bytes + a * kAtomBytes, map_b, fb, nch0 + a * 64 + bdc, w0 + bdw, bdp,
+                tma_load_5d_u32(sa + a_bytes + a * kAtomB, map_b, fb, nch0 + a * kAtomW + bdc, w0 + bdw, bdp,
                                 h0 + bdh, n0);
             }
             w0 += p.tw_step;
@@ -368,16 +377,22 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
     // =========================================================== MMA issuer (whole warp loops, one elected lane issues)
     if (!kCG2 || crank == 0) {  // cta_group::2: the leader CTA issues for the pair
       const bool leader = elect_one();
-      const uint32_t idesc = make_idesc_bf16(kCG2 ? 256u : 128u, static_cast<uint32_t>(p.bn), p.a_mn, p.b_mn);
-      const uint32_t k_layout = (p.kc == 64) ? 2u : 4u;            // SWIZZLE_128B : SWIZZLE_64B
-      const uint32_t k_sbo = static_cast<uint32_t>(8 * p.kc * 2);  // 8 rows of one swizzle atom
+      const uint32_t idesc = make_idesc_bf16(kCG2 ? 256u : 128u, static_cast<uint32_t>(p.bn), p.a_mn, p.b_mn, kTF32);
+      const uint32_t k_layout = (p.kc * kEsz == 128) ? 2u : 4u;       // SWIZZLE_128B : SWIZZLE_64B
+      const uint32_t k_sbo = static_cast<uint32_t>(8 * p.kc * kEsz);  // 8 rows of one swizzle atom
       // descriptor templates (everything but the start address) and the per-UMMA_K advance of the start-address
       // field (address >> 4; smem addresses stay below 2^18, so the 14-bit field never carries)
-      const uint64_t da_t = p.a_mn ? make_smem_desc(0u, kAtomBytes, 1024u, 2u) : make_smem_desc(0u, 0u, k_sbo, k_layout);
-      const uint64_t db_t = p.b_mn ? make_smem_desc(0u, kAtomBytes, 1024u, 2u) : make_smem_desc(0u, 0u, k_sbo, k_layout);
-      const uint32_t a_step = (p.a_mn ? 2048u : 32u) >> 4;  // per UMMA_K (16 elements of K)
-      const uint32_t b_step = (p.b_mn ? 2048u : 32u) >> 4;
-      const bool four = (p.kc == 64);
+      // MN-major: bf16 = SWIZZLE_128B atoms of 64 MN x 8 k-rows (SBO = 1024 B between 8-row groups); tf32 = the only
+      // layout 32-bit MN-major operands may use, SWIZZLE_128B_BASE32B (layout type 1; TMA: SWIZZLE_128B_ATOM_32B):
+      // atoms of 32 MN x 4 k-rows, 32-byte chunks XOR-ed with (row & 3) -> SBO = 512 B.  LBO = next MN atom (one box).
+      const uint64_t da_t = p.a_mn ? make_smem_desc(0u, kAtomB, kTF32 ? 512u : 1024u, kTF32 ? 1u : 2u)
+                                   : make_smem_desc(0u, 0u, k_sbo, k_layout);
+      const uint64_t db_t = p.b_mn ? make_smem_desc(0u, kAtomB, kTF32 ? 512u : 1024u, kTF32 ? 1u : 2u)
+                                   : make_smem_desc(0u, 0u, k_sbo, k_layout);
+      // per UMMA_K (16 bf16 / 8 tf32 elements of K): 32 bytes along a K-major row, 16 / 8 k-rows of an MN-major atom
+      const uint32_t a_step = (p.a_mn ? (kTF32 ? 1024u : 2048u) : 32u) >> 4;
+      const uint32_t b_step = (p.b_mn ? (kTF32 ? 1024u : 2048u) : 32u) >> 4;
+      const bool four = (p.kc * kEsz == 128);
       const uint32_t stage16 = static_cast<uint32_t>(stage_bytes) >> 4;
       const uint32_t a16 = static_cast<uint32_t>(a_bytes) >> 4;
       const uint32_t smem16 = smem0 >> 4;
@@ -408,6 +423,12 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
               umma_bf16_2sm(tmem_d, da + 3 * a_step, db + 3 * b_step, idesc, 1u);
             }
             umma_commit_2sm_mc_u32(empty0 + 8u * stage, 0x3);  // releases this stage in both CTAs of the pair
+          } else if constexpr (kTF32) {
+            umma_tf32(tmem_d, da, db, idesc, acc);
+            umma_tf32(tmem_d, da + a_step, db + b_step, idesc, 1u);
+            umma_tf32(tmem_d, da + 2 * a_step, db + 2 * b_step, idesc, 1u);
+            umma_tf32(tmem_d, da + 3 * a_step, db + 3 * b_step, idesc, 1u);
+            umma_commit_u32(empty0 + 8u * stage);
           } else {
             umma_bf16(tmem_d, da, db, idesc, acc);
             umma_bf16(tmem_d, da + a_step, db + b_step, idesc, 1u);
@@ -824,6 +845,8 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+constexpr int kSwz128Atom32 = 129;
+
 // rank-`rank` bf16 tensor map; dims/box innermost first; strides in BYTES for dims 1..rank-1.
 static int encode_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides,
                       const uint32_t* box, int swizzle_bytes, bool f32 = false) {
@@ -837,8 +860,10 @@ static int encode_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t*
     es[i] = 1;
   }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides[i];
-  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                               : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);
+  // swizzle_bytes: 128 / 64 / 0, or kSwz128Atom32 = 128-byte span with 32-byte chunks (MN-major fp32 operands)
+  CUtensorMapSwizzle sw = swizzle_bytes == kSwz128Atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                          : swizzle_bytes == 128         ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);
   CUresult r = fn(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(ptr), gdim,
                   gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -855,9 +880,9 @@ static int encode_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t*
 
 // NHWC bf16 activation [b,h,w,c] as the 5-D view (c, w, p, h, n); stride 2 -> parity-split view.
 static int encode_act_map(CUtensorMap* m, const void* ptr, int b, int h, int w, int c, int stride, const uint32_t* box,
-                          int swizzle_bytes) {
+                          int swizzle_bytes, bool f32 = false) {
   uint64_t dims[5], str[4];
-  const uint64_t e = 2;
+  const uint64_t e = f32 ? 4 : 2;
   if (stride == 1) {
     dims[0] = c; dims[1] = w; dims[2] = 1; dims[3] = h; dims[4] = b;
     str[0] = c * e; str[1] = (uint64_t)w * c * e; str[2] = (uint64_t)w * c * e; str[3] = (uint64_t)h * w * c * e;
@@ -865,26 +890,27 @@ static int encode_act_map(CUtensorMap* m, const void* ptr, int b, int h, int w, 
     dims[0] = 2 * c; dims[1] = w / 2; dims[2] = 2; dims[3] = h / 2; dims[4] = b;
     str[0] = 2 * c * e; str[1] = (uint64_t)w * c * e; str[2] = 2ull * w * c * e; str[3] = (uint64_t)h * w * c * e;
   }
-  return encode_map(m, ptr, 5, dims, str, box, swizzle_bytes);
+  return encode_map(m, ptr, 5, dims, str, box, swizzle_bytes, f32);
 }
 
-// Row-major bf16 matrix [rows, cols] (leading dimension ld) as the 5-D view (c=cols, w=rows, 1, 1, 1).
+// Row-major bf16 (fp32) matrix [rows, cols] (leading dimension ld) as the 5-D view (c=cols, w=rows, 1, 1, 1).
 static int encode_mat_map5(CUtensorMap* m, const void* ptr, long long rows, long long cols, long long ld,
-                           uint32_t box_c, uint32_t box_r, int swizzle_bytes) {
+                           uint32_t box_c, uint32_t box_r, int swizzle_bytes, bool f32 = false) {
   uint64_t dims[5] = {(uint64_t)cols, (uint64_t)rows, 1, 1, 1};
-  const uint64_t rs = (uint64_t)ld * 2;
+  const uint64_t rs = (uint64_t)ld * (f32 ? 4 : 2);
   uint64_t str[4] = {rs, rs * rows, rs * rows, rs * rows};
   uint32_t box[5] = {box_c, box_r, 1, 1, 1};
-  return encode_map(m, ptr, 5, dims, str, box, swizzle_bytes);
+  return encode_map(m, ptr, 5, dims, str, box, swizzle_bytes, f32);
 }
 
-// bf16 [t][rows][cols] as 3-D (cols, rows, t)
+// bf16 (fp32) [t][rows][cols] as 3-D (cols, rows, t)
 static int encode_w_map3(CUtensorMap* m, const void* ptr, long long t, long long rows, long long cols, long long ld,
-                         uint32_t box_c, uint32_t box_r, int swizzle_bytes) {
+                         uint32_t box_c, uint32_t box_r, int swizzle_bytes, bool f32 = false) {
+  const uint64_t e = f32 ? 4 : 2;
   uint64_t dims[3] = {(uint64_t)cols, (uint64_t)rows, (uint64_t)t};
-  uint64_t str[2] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * rows};
+  uint64_t str[2] = {(uint64_t)ld * e, (uint64_t)ld * e * rows};
   uint32_t box[3] = {box_c, box_r, 1};
-  return encode_map(m, ptr, 3, dims, str, box, swizzle_bytes);
+  return encode_map(m, ptr, 3, dims, str, box, swizzle_bytes, f32);
 }
 
 static int g_last_grid[3] = {0, 0, 0};
@@ -931,8 +957,10 @@ static int num_sms() {
 static int launch(GemmParams& p, dim3 grid, cudaStream_t stream, double flops, int kb_per_cta = 1 << 30,
                   int cluster = 1) {
   if (cluster != 2 || p.mode != MODE_FWD || p.b_mn) p.cg2 = 0;
-  const int a_bytes = p.a_mn ? 2 * kAtomBytes : 128 * p.kc * 2;
-  const int b_bytes = p.b_mn ? std::max(1, p.bn >> 6) * kAtomBytes : (p.cg2 ? (p.bn >> 1) : p.bn) * p.kc * 2;
+  if (p.tf32) p.cg2 = 0;
+  const int esz = p.tf32 ? 4 : 2, atom_w = p.tf32 ? 32 : 64, atom_b = p.tf32 ? 4096 : kAtomBytes;
+  const int a_bytes = p.a_mn ? (128 / atom_w) * atom_b : 128 * p.kc * esz;
+  const int b_bytes = p.b_mn ? std::max(1, p.bn / atom_w) * atom_b : (p.cg2 ? (p.bn >> 1) : p.bn) * p.kc * esz;
   const int stage_bytes = a_bytes + b_bytes;
   p.cluster = cluster;
   p.num_m_tiles = grid.x;
@@ -980,6 +1008,8 @@ static int launch(GemmParams& p, dim3 grid, cudaStream_t stream, double flops, i
     attr_err = cudaFuncSetAttribute(dm_tapgemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (attr_err == cudaSuccess)
       attr_err = cudaFuncSetAttribute(dm_tapgemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(dm_tapgemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (attr_err != cudaSuccess) return set_error((int)attr_err, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
   const int ctas = cluster * std::min(p.total_tiles, slots);
@@ -1017,8 +1047,9 @@ static int launch(GemmParams& p, dim3 grid, cudaStream_t stream, double flops, i
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = cluster > 1 ? 1 : 0;
-  cudaError_t le = p.cg2 ? cudaLaunchKernelEx(&cfg, dm_tapgemm_kernel<true>, p)
-                         : cudaLaunchKernelEx(&cfg, dm_tapgemm_kernel<false>, p);
+  cudaError_t le = p.tf32 ? cudaLaunchKernelEx(&cfg, dm_tapgemm_kernel<false, true>, p)
+                          : (p.cg2 ? cudaLaunchKernelEx(&cfg, dm_tapgemm_kernel<true>, p)
+                                   : cudaLaunchKernelEx(&cfg, dm_tapgemm_kernel<false>, p));
   if (prof) {
     cudaEventRecord(rec.e1, stream);
     std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -1263,12 +1294,15 @@ extern "C" int dm_debug_last_plan(int* grid_xyz, int* smem_bytes, int* stages) {
 }
 
 // ------------------------------------------------------------------------------------------ dense GEMM
-extern "C" int dm_gemm_bf16(const dm_gemm_desc* g, void* stream_) {
+static int gemm_impl(const dm_gemm_desc* g, bool tf32, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   DM_REQUIRE(g != nullptr, "dm_gemm_bf16: null descriptor");
   t_kind = 0;
   DM_REQUIRE(g->m > 0 && g->n > 0 && g->k > 0, "dm_gemm_bf16: bad shape %d %d %d", g->m, g->n, g->k);
-  DM_REQUIRE(g->lda % 8 == 0 && g->ldb % 8 == 0, "dm_gemm_bf16: lda/ldb must be multiples of 8 elements");
+  const int ld_align = tf32 ? 4 : 8;
+  DM_REQUIRE(g->lda % ld_align == 0 && g->ldb % ld_align == 0, "dm_gemm: lda/ldb must be multiples of 16 bytes");
+  const int kc_mn = tf32 ? 32 : 64;   // k-rows of an MN-major k-block = elements of a 128-byte K-major row
+  const int aw = tf32 ? 32 : 64;      // MN elements of one MN-major atom
   DM_REQUIRE((reinterpret_cast<uintptr_t>(g->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(g->b) & 15) == 0,
              "dm_gemm_bf16: operands must be 16-byte aligned");
   const int splits = std::max(1, g->splits);
@@ -1276,6 +1310,7 @@ extern "C" int dm_gemm_bf16(const dm_gemm_desc* g, void* stream_) {
   DM_REQUIRE(!g->accumulate || g->d_f32, "dm_gemm_bf16: accumulate needs fp32 output");
   GemmParams p;
   init_params(p);
+  p.tf32 = tf32 ? 1 : 0;
   p.out = g->d;
   p.bias = g->bias;
   p.out_f32 = g->d_f32;
@@ -1291,6 +1326,7 @@ extern "C" int dm_gemm_bf16(const dm_gemm_desc* g, void* stream_) {
     p.b_mn = (g->layout == DM_GEMM_NN);
     p.kc = (g->k % 64 == 0 || p.b_mn) ? 64 : 32;
     if (!p.b_mn && g->k < 64 && g->k % 32 == 0) p.kc = 32;
+    if (tf32) p.kc = 32;
     DM_REQUIRE(g->k % p.kc == 0 || g->k > p.kc, "dm_gemm_bf16: unsupported k %d", g->k);
     p.bn = p.b_mn ? (g->n >= 128 ? 128 : 64) : pick_bn(g->n, env_int("DM_BN_CAP", 128));
     p.cpt = (g->k + p.kc - 1) / p.kc;
@@ -1300,12 +1336,13 @@ extern "C" int dm_gemm_bf16(const dm_gemm_desc* g, void* stream_) {
     p.bw = 128; p.bh = 1;
     p.os_w = g->ldd_m; p.os_col = g->ldd_n;
     p.w_lim = m_store; p.n_lim = 1; p.n_valid = n_store;
-    rc = encode_mat_map5(&p.map_a, g->a, g->m, g->k, g->lda, p.kc, 128, p.kc * 2);
+    const int esz = tf32 ? 4 : 2;
+    rc = encode_mat_map5(&p.map_a, g->a, g->m, g->k, g->lda, p.kc, 128, p.kc * esz, tf32);
     if (rc) return rc;
     if (!p.b_mn)
-      rc = encode_w_map3(&p.map_b, g->b, 1, g->n, g->k, g->ldb, p.kc, p.bn, p.kc * 2);
+      rc = encode_w_map3(&p.map_b, g->b, 1, g->n, g->k, g->ldb, p.kc, p.bn, p.kc * esz, tf32);
     else
-      rc = encode_w_map3(&p.map_b, g->b, 1, g->k, g->n, g->ldb, 64, 64, 128);
+      rc = encode_w_map3(&p.map_b, g->b, 1, g->k, g->n, g->ldb, aw, kc_mn, tf32 ? kSwz128Atom32 : 128, tf32);
     if (rc) return rc;
     p.num_n_tiles = (g->n + p.bn - 1) / p.bn;
     if (g->ldd_n == 1) epi_rows_matrix(p, g->d, g->d_f32 != 0, m_store, n_store, g->ldd_m, g->accumulate != 0, 0);
@@ -1321,18 +1358,18 @@ extern "C" int dm_gemm_bf16(const dm_gemm_desc* g, void* stream_) {
                "dm_gemm_bf16: TN (weight-gradient) output is fp32, or bf16 with unit row stride and no accumulation");
     DM_REQUIRE(g->bias == nullptr, "dm_gemm_bf16: TN has no bias");
     p.mode = MODE_WGRAD;
-    p.a_mn = 1; p.b_mn = 1; p.kc = 64;
+    p.a_mn = 1; p.b_mn = 1; p.kc = kc_mn;
     p.bn = g->n >= 256 ? env_int("DM_BN_WGRAD", 128) : (g->n >= 128 ? 128 : 64);
-    p.num_kb = (g->k + 63) / 64;
-    p.tw_step = 64; p.tpi = 1 << 30; p.th_step = 0; p.tn_step = 0;
+    p.num_kb = (g->k + kc_mn - 1) / kc_mn;
+    p.tw_step = kc_mn; p.tpi = 1 << 30; p.th_step = 0; p.tn_step = 0;
     p.taps[0].nvalid = static_cast<int16_t>(std::min(n_store, 32767));
     p.taps[0].mvalid = 32767;
     p.os_m = g->ldd_m; p.os_n1 = g->ldd_n; p.os_n2 = 0; p.nmod = 1 << 30;
     p.m_valid = m_store;
     // A stored [k][m]: (c = m, w = k rows); B stored [k][n]
-    rc = encode_mat_map5(&p.map_a, g->a, g->k, g->m, g->lda, 64, 64, 128);
+    rc = encode_mat_map5(&p.map_a, g->a, g->k, g->m, g->lda, aw, kc_mn, tf32 ? kSwz128Atom32 : 128, tf32);
     if (rc) return rc;
-    rc = encode_mat_map5(&p.map_b, g->b, g->k, g->n, g->ldb, 64, 64, 128);
+    rc = encode_mat_map5(&p.map_b, g->b, g->k, g->n, g->ldb, aw, kc_mn, tf32 ? kSwz128Atom32 : 128, tf32);
     if (rc) return rc;
     p.num_n_tiles = (g->n + p.bn - 1) / p.bn;
     if (g->ldd_n == 1)
@@ -1350,6 +1387,13 @@ extern "C" int dm_gemm_bf16(const dm_gemm_desc* g, void* stream_) {
   const double k_alg = g->k_alg > 0 ? g->k_alg : g->k;
   const int kb_total = (p.mode == MODE_FWD) ? p.cpt : p.num_kb;
   return launch(p, grid, stream, 2.0 * m_store * n_store * k_alg, (kb_total + splits - 1) / splits);
+}
+
+extern "C" int dm_gemm_bf16(const dm_gemm_desc* g, void* stream_) { return gemm_impl(g, false, stream_); }
+// fp32 operands and (usually) fp32 D, TF32 tensor-core arithmetic with fp32 accumulation: the TF32 precision mode
+extern "C" int dm_gemm_tf32(const dm_gemm_desc* g, void* stream_) {
+  DM_REQUIRE(g == nullptr || g->bn.scratch == nullptr, "dm_gemm_tf32: fused BatchNorm statistics are bf16-path only");
+  return gemm_impl(g, true, stream_);
 }
 
 // ------------------------------------------------------------------------------------------ convolutions
@@ -1390,8 +1434,8 @@ static bool groups_tile_aligned(const PixTile& pt, int batch, int groups) {
   return pt.bimg <= 1 || (batch / groups) % pt.bimg == 0;
 }
 
-extern "C" int dm_conv_down(const dm_conv_geom* g, const void* big, const void* w_down, const float* bias,
-                            void* out_small, const dm_bn_fuse* bn, void* stream_) {
+static int conv_down_impl(const dm_conv_geom* g, const void* big, const void* w_down, const float* bias,
+                          void* out_small, const dm_bn_fuse* bn, bool tf32, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = check_geom(g, "dm_conv_down")) return rc;
   t_kind = 1;
@@ -1402,7 +1446,9 @@ extern "C" int dm_conv_down(const dm_conv_geom* g, const void* big, const void* 
   GemmParams p;
   init_params(p);
   p.mode = MODE_FWD;
-  p.kc = (g->cb % 64 == 0) ? 64 : 32;
+  p.tf32 = tf32 ? 1 : 0;
+  const int esz = tf32 ? 4 : 2;
+  p.kc = (g->cb % 64 == 0 && !tf32) ? 64 : 32;
   p.bn = pick_bn_fill(g->cs, env_int("DM_BN_CAP", 128), pt.tiles);
   p.cpt = g->cb / p.kc;
   p.phase_tap_start[0] = 0;
@@ -1410,16 +1456,16 @@ extern "C" int dm_conv_down(const dm_conv_geom* g, const void* big, const void* 
   down_taps(g, p.taps);
   p.tw_step = 0; p.tpi = pt.tpi; p.th_step = pt.th_step; p.tn_step = pt.tn_step;
   p.bw = pt.bw; p.bh = pt.bh;
-  p.out = out_small; p.bias = bias; p.out_f32 = 0; p.out_atomic = 0;
+  p.out = out_small; p.bias = bias; p.out_f32 = tf32 ? 1 : 0; p.out_atomic = 0;
   p.os_w = g->cs; p.os_h = (long long)g->ws * g->cs; p.os_n = (long long)g->hs * g->ws * g->cs; p.os_col = 1;
   p.w_lim = g->ws; p.n_lim = g->batch; p.n_valid = g->cs;
   uint32_t box[5] = {(uint32_t)p.kc, (uint32_t)pt.bw, 1, (uint32_t)pt.bh, (uint32_t)pt.bimg};
-  if (int rc = encode_act_map(&p.map_a, big, g->batch, g->hb, g->wb, g->cb, g->stride, box, p.kc * 2)) return rc;
-  p.cg2 = (env_int("DM_CG2", 1) != 0 && pt.tiles >= 2 && p.bn >= 32) ? 1 : 0;
+  if (int rc = encode_act_map(&p.map_a, big, g->batch, g->hb, g->wb, g->cb, g->stride, box, p.kc * esz, tf32)) return rc;
+  p.cg2 = (!tf32 && env_int("DM_CG2", 1) != 0 && pt.tiles >= 2 && p.bn >= 32) ? 1 : 0;
   const int cluster = p.cg2 ? 2 : 1;
-  if (int rc = encode_w_map3(&p.map_b, w_down, 25, g->cs, g->cb, g->cb, p.kc, p.bn / cluster, p.kc * 2)) return rc;
+  if (int rc = encode_w_map3(&p.map_b, w_down, 25, g->cs, g->cb, g->cb, p.kc, p.bn / cluster, p.kc * esz, tf32)) return rc;
   p.num_n_tiles = (g->cs + p.bn - 1) / p.bn;
-  epi_rows_act(p, out_small, false, g->batch, g->hs, g->ws, g->cs, 1, pt);
+  epi_rows_act(p, out_small, tf32, g->batch, g->hs, g->ws, g->cs, 1, pt);
   if (bn && bn->scratch) {
     DM_REQUIRE(groups_tile_aligned(pt, g->batch, bn->groups), "dm_conv_down: groups do not fall on tile boundaries");
     if (int rc = attach_stats(p, bn, g->cs, pt.tiles, "dm_conv_down")) return rc;
@@ -1428,8 +1474,18 @@ extern "C" int dm_conv_down(const dm_conv_geom* g, const void* big, const void* 
                 cluster);
 }
 
-extern "C" int dm_conv_up(const dm_conv_geom* g, const void* small, const void* w_up, const float* bias, void* out_big,
-                          int out_f32, const dm_bn_fuse* bn, void* stream_) {
+extern "C" int dm_conv_down(const dm_conv_geom* g, const void* big, const void* w_down, const float* bias,
+                            void* out_small, const dm_bn_fuse* bn, void* stream_) {
+  return conv_down_impl(g, big, w_down, bias, out_small, bn, false, stream_);
+}
+// TF32 precision mode: big / w_down / out_small are fp32 (same layouts), tensor-core arithmetic in TF32, fp32 accumulate
+extern "C" int dm_conv_down_tf32(const dm_conv_geom* g, const void* big, const void* w_down, const float* bias,
+                                 void* out_small, void* stream_) {
+  return conv_down_impl(g, big, w_down, bias, out_small, nullptr, true, stream_);
+}
+
+static int conv_up_impl(const dm_conv_geom* g, const void* small, const void* w_up, const float* bias, void* out_big,
+                        int out_f32, const dm_bn_fuse* bn, bool tf32, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = check_geom(g, "dm_conv_up")) return rc;
   t_kind = 2;
@@ -1440,11 +1496,15 @@ extern "C" int dm_conv_up(const dm_conv_geom* g, const void* small, const void* 
   GemmParams p;
   init_params(p);
   p.mode = MODE_FWD;
-  p.kc = (g->cs % 64 == 0) ? 64 : 32;
+  p.tf32 = tf32 ? 1 : 0;
+  const int esz = tf32 ? 4 : 2;
+  p.kc = (g->cs % 64 == 0 && !tf32) ? 64 : 32;
   p.bn = pick_bn_fill(cb_pad, env_int("DM_BN_CAP", 128), (g->stride == 2 ? 4ll : 1ll) * pt.tiles);
   p.cpt = g->cs / p.kc;
   int nphase = 0, nt = 0;
   const bool fold = (g->stride == 1 && g->cb == 3);
+  DM_REQUIRE(!(tf32 && fold), "dm_conv_up_tf32: the 3-channel kw-folded layer is bf16-path only");
+  if (tf32) out_f32 = 1;
   DM_REQUIRE(!fold || out_f32, "dm_conv_up: the 3-channel image side is written as fp32");
   if (fold) {
     // 5 k-blocks (one per kh) instead of 25: the A box is shifted vertically only, the 5 horizontal taps live in
@@ -1497,10 +1557,10 @@ extern "C" int dm_conv_up(const dm_conv_geom* g, const void* small, const void* 
   p.out = out_big; p.bias = bias; p.out_f32 = out_f32; p.out_atomic = 0;
   p.w_lim = g->ws; p.n_lim = g->batch; p.n_valid = g->cb;
   uint32_t box[5] = {(uint32_t)p.kc, (uint32_t)pt.bw, 1, (uint32_t)pt.bh, (uint32_t)pt.bimg};
-  if (int rc = encode_act_map(&p.map_a, small, g->batch, g->hs, g->ws, g->cs, 1, box, p.kc * 2)) return rc;
-  p.cg2 = (!fold && env_int("DM_CG2", 1) != 0 && pt.tiles >= 2 && p.bn >= 32) ? 1 : 0;
+  if (int rc = encode_act_map(&p.map_a, small, g->batch, g->hs, g->ws, g->cs, 1, box, p.kc * esz, tf32)) return rc;
+  p.cg2 = (!tf32 && !fold && env_int("DM_CG2", 1) != 0 && pt.tiles >= 2 && p.bn >= 32) ? 1 : 0;
   const int cluster = p.cg2 ? 2 : 1;
-  if (int rc = encode_w_map3(&p.map_b, w_up, fold ? 5 : 25, cb_pad, g->cs, g->cs, p.kc, p.bn / cluster, p.kc * 2)) return rc;
+  if (int rc = encode_w_map3(&p.map_b, w_up, fold ? 5 : 25, cb_pad, g->cs, g->cs, p.kc, p.bn / cluster, p.kc * esz, tf32)) return rc;
   p.num_n_tiles = (cb_pad + p.bn - 1) / p.bn;
   if (!fold) epi_rows_act(p, out_big, out_f32 != 0, g->batch, g->hb, g->wb, g->cb, g->stride, pt);
   if (bn && bn->scratch) {
@@ -1510,6 +1570,15 @@ extern "C" int dm_conv_up(const dm_conv_geom* g, const void* small, const void* 
   }
   return launch(p, dim3(pt.tiles, p.num_n_tiles, nphase), stream, 50.0 * g->batch * g->hs * g->ws * g->cs * g->cb,
                 1 << 30, cluster);
+}
+
+extern "C" int dm_conv_up(const dm_conv_geom* g, const void* small, const void* w_up, const float* bias, void* out_big,
+                          int out_f32, const dm_bn_fuse* bn, void* stream_) {
+  return conv_up_impl(g, small, w_up, bias, out_big, out_f32, bn, false, stream_);
+}
+extern "C" int dm_conv_up_tf32(const dm_conv_geom* g, const void* small, const void* w_up, const float* bias,
+                               void* out_big, void* stream_) {
+  return conv_up_impl(g, small, w_up, bias, out_big, 1, nullptr, true, stream_);
 }
 
 // Phase-merged stride-2 transposed convolution for cb == 32 (see dm_pack_up_merged): ONE GEMM with 9 input taps and
@@ -1573,23 +1642,27 @@ extern "C" int dm_conv_up_merged(const dm_conv_geom* g, const void* small, const
   return launch(p, dim3(pt.tiles, 1, 1), stream, 50.0 * g->batch * g->hs * g->ws * g->cs * g->cb, 1 << 30, cluster);
 }
 
-extern "C" int dm_conv_wgrad(const dm_conv_geom* g, const void* small, const void* big, float* dw_packed,
-                             int direct_layout, void* stream_) {
+static int conv_wgrad_impl(const dm_conv_geom* g, const void* small, const void* big, float* dw_packed,
+                           int direct_layout, bool tf32, void* stream_) {
   // D_t[m = cb][n = cs] = sum_pixels big_tap_t[pix][cb] * small[pix][cs], accumulated into the tap-major packed
   // gradient dw_packed[25][cs][cb]: a warp's 32 rows (cb) are contiguous floats -> coalesced reductions.
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = check_geom(g, "dm_conv_wgrad")) return rc;
   t_kind = 3;
   DM_REQUIRE(g->cs % 64 == 0, "dm_conv_wgrad: cs %d must be a multiple of 64", g->cs);
-  const bool pair = (g->cb == 32 && g->stride == 2);
-  DM_REQUIRE(g->cb % 64 == 0 || pair, "dm_conv_wgrad: cb %d must be a multiple of 64 (or 32 with stride 2)", g->cb);
+  const bool pair = (!tf32 && g->cb == 32 && g->stride == 2);
+  DM_REQUIRE(g->cb % 64 == 0 || pair || (tf32 && g->cb % 32 == 0),
+             "dm_conv_wgrad: cb %d must be a multiple of 64 (or 32 with stride 2)", g->cb);
+  const int kpix = tf32 ? 32 : 64;   // pixels (k-rows) per k-block = height of an MN-major atom
+  const int aw = tf32 ? 32 : 64;     // channels of one atom
   PixTile pt;
-  DM_REQUIRE(make_pix_tile(64, g->batch, g->hs, g->ws, &pt), "dm_conv_wgrad: unsupported grid %dx%d", g->hs, g->ws);
+  DM_REQUIRE(make_pix_tile(kpix, g->batch, g->hs, g->ws, &pt), "dm_conv_wgrad: unsupported grid %dx%d", g->hs, g->ws);
   GemmParams p;
   init_params(p);
+  p.tf32 = tf32 ? 1 : 0;
   p.wgrad_direct = direct_layout;
   p.mode = MODE_WGRAD;
-  p.a_mn = 1; p.b_mn = 1; p.kc = 64;
+  p.a_mn = 1; p.b_mn = 1; p.kc = kpix;
   p.num_kb = pt.tiles;
   p.tw_step = 0; p.tpi = pt.tpi; p.th_step = pt.th_step; p.tn_step = pt.tn_step;
   p.out = dw_packed; p.out_f32 = 1; p.out_atomic = 1;
@@ -1634,10 +1707,11 @@ extern "C" int dm_conv_wgrad(const dm_conv_geom* g, const void* small, const voi
     p.os_m = m_stride; p.mmod = 32; p.os_m2 = tap_stride;
     p.m_valid = 64;
   }
-  uint32_t boxa[5] = {64, (uint32_t)pt.bw, 1, (uint32_t)pt.bh, (uint32_t)pt.bimg};
+  uint32_t boxa[5] = {(uint32_t)aw, (uint32_t)pt.bw, 1, (uint32_t)pt.bh, (uint32_t)pt.bimg};
   // operand roles: A = big (tap-shifted, M = cb), B = small (N = cs)
-  if (int rc = encode_act_map(&p.map_a, big, g->batch, g->hb, g->wb, g->cb, g->stride, boxa, 128)) return rc;
-  if (int rc = encode_act_map(&p.map_b, small, g->batch, g->hs, g->ws, g->cs, 1, boxa, 128)) return rc;
+  const int swz = tf32 ? kSwz128Atom32 : 128;
+  if (int rc = encode_act_map(&p.map_a, big, g->batch, g->hb, g->wb, g->cb, g->stride, boxa, swz, tf32)) return rc;
+  if (int rc = encode_act_map(&p.map_b, small, g->batch, g->hs, g->ws, g->cs, 1, boxa, swz, tf32)) return rc;
   p.wgrad_tap_on_a = 1;
   if (!direct) epi_wgrad_packed(p, dw_packed, g->cs, g->cb);
   const int base_ctas = m_tiles * p.num_n_tiles * units;
@@ -1663,6 +1737,16 @@ extern "C" int dm_conv_wgrad(const dm_conv_geom* g, const void* small, const voi
   const int cluster = 1;
   return launch(p, dim3(m_tiles, p.num_n_tiles * units, splits), stream,
                 50.0 * g->batch * g->hs * g->ws * g->cs * g->cb, (p.num_kb + splits - 1) / splits, cluster);
+}
+
+extern "C" int dm_conv_wgrad(const dm_conv_geom* g, const void* small, const void* big, float* dw_packed,
+                             int direct_layout, void* stream_) {
+  return conv_wgrad_impl(g, small, big, dw_packed, direct_layout, false, stream_);
+}
+// TF32 precision mode: small / big are fp32 NHWC; dw_packed[25][cs][cb] fp32 (tap-major), accumulated
+extern "C" int dm_conv_wgrad_tf32(const dm_conv_geom* g, const void* small, const void* big, float* dw_packed,
+                                  void* stream_) {
+  return conv_wgrad_impl(g, small, big, dw_packed, 0, true, stream_);
 }
 
 // ------------------------------------------------------------------------------------------ 3-channel image side

@@ -142,6 +142,20 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 }
 
 
+// Same with fp32 operands in shared memory read as TF32 (kind::tf32: K = 8 per instruction, fp32 accumulation)
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // ---------------------------------------------------------------- raw-address variants for the single-thread hot loops
 // (32-bit shared-window addresses and the tensor map's generic address are computed once, outside the k loop)
 __device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
@@ -294,11 +308,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32 (cute::UMMA::InstrDescriptor bit layout):
 //   [4,6) c_format=1 (F32)  [7,10) a_format=1 (BF16)  [10,13) b_format=1 (BF16)
 //   [15] a_major  [16] b_major (0 = K-major, 1 = MN-major)  [17,23) N>>3  [24,29) M>>4
-__host__ __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t m, uint32_t n, uint32_t a_mn, uint32_t b_mn) {
+//   kind::tf32: a_format = b_format = 2 (TF32)
+__host__ __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t m, uint32_t n, uint32_t a_mn, uint32_t b_mn,
+                                                            bool tf32 = false) {
   uint32_t d = 0;
   d |= 1u << 4;
-  d |= 1u << 7;
-  d |= 1u << 10;
+  d |= (tf32 ? 2u : 1u) << 7;
+  d |= (tf32 ? 2u : 1u) << 10;
   d |= (a_mn & 1u) << 15;
   d |= (b_mn & 1u) << 16;
   d |= ((n >> 3) & 0x3Fu) << 17;

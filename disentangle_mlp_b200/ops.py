@@ -151,6 +151,55 @@ def conv_wgrad(g: ConvGeom, small, big, dw, packed=None, direct=None):
     return unpack_conv_grad(packed, g.cs, g.cb, dw, True)
 
 
+# ------------------------------------------------------------------------------------------ TF32 precision mode
+def gemm_tf32(layout, a, b, m, n, k, *, out=None, accumulate=False, bias=None, splits=1, ldd_m=None, ldd_n=1,
+              m_store=0, n_store=0):
+    """D = op(A) op(B), fp32 operands read by the tensor cores as TF32, fp32 accumulate / output (dm_gemm_tf32)."""
+    assert a.dtype == F32 and b.dtype == F32
+    if out is None:
+        out = (torch.zeros if accumulate else torch.empty)((m_store or m, n_store or n), dtype=F32, device=a.device)
+    if ldd_m is None:
+        ldd_m = out.stride(0) if out.dim() >= 2 else 1
+    d = GemmDesc(layout, m, n, k, _p(a), a.stride(0), _p(b), b.stride(0), _p(out), ldd_m, ldd_n, 1, int(accumulate),
+                 _p(bias), m_store, n_store, splits, 0, BnFuse())
+    _lib.check(_lib.load().dm_gemm_tf32(C.byref(d), _stream()), "dm_gemm_tf32")
+    return out
+
+
+def pack_conv_weights_f32(w):
+    """fp32 [cs][cb][5][5] -> fp32 (w_down [25][cs][cb], w_up [25][cb][cs]): the TF32 path's operand packs."""
+    cs, cb = w.shape[0], w.shape[1]
+    w_down = w.permute(2, 3, 0, 1).reshape(25, cs, cb).contiguous()
+    w_up = w.permute(2, 3, 1, 0).reshape(25, cb, cs).contiguous()
+    return w_down, w_up
+
+
+def conv_down_tf32(g: ConvGeom, big, w_down, bias=None):
+    assert big.dtype == F32 and w_down.dtype == F32
+    out = torch.empty((g.batch, g.hs, g.ws, g.cs), dtype=F32, device=big.device)
+    _lib.check(_lib.load().dm_conv_down_tf32(C.byref(g), _p(big), _p(w_down), _p(bias), _p(out), _stream()),
+               "dm_conv_down_tf32")
+    return out
+
+
+def conv_up_tf32(g: ConvGeom, small, w_up, bias=None):
+    assert small.dtype == F32 and w_up.dtype == F32
+    out = torch.empty((g.batch, g.hb, g.wb, g.cb), dtype=F32, device=small.device)
+    _lib.check(_lib.load().dm_conv_up_tf32(C.byref(g), _p(small), _p(w_up), _p(bias), _p(out), _stream()),
+               "dm_conv_up_tf32")
+    return out
+
+
+def conv_wgrad_tf32(g: ConvGeom, small, big, dw_packed=None):
+    """dw_packed [25][cs][cb] fp32 (tap-major) += small^T * shifted(big); returns it viewed as [cs][cb][5][5]."""
+    assert small.dtype == F32 and big.dtype == F32
+    if dw_packed is None:
+        dw_packed = torch.zeros((25, g.cs, g.cb), dtype=F32, device=small.device)
+    _lib.check(_lib.load().dm_conv_wgrad_tf32(C.byref(g), _p(small), _p(big), _p(dw_packed), _stream()),
+               "dm_conv_wgrad_tf32")
+    return dw_packed.view(5, 5, g.cs, g.cb).permute(2, 3, 0, 1)
+
+
 def profile_enable(on: bool):
     _lib.load().dm_profile_enable(int(on))
 

@@ -120,6 +120,19 @@ int dm_conv_wgrad(const dm_conv_geom* g, const void* small, const void* big, flo
 /* dw[cs][cb][5][5] (+)= dw_packed[25][cs][cb]; dw_packed is zeroed for the next accumulation. */
 int dm_unpack_conv_grad(float* dw_packed, int cs, int cb, int accumulate, float* dw, void* stream);
 
+/* ---- TF32 precision mode (north-star: "bf16/TF32 with fp32 accumulation", tolerance 1e-3 per layer).
+ * The same tcgen05 kernel instantiated for tcgen05.mma.kind::tf32: operands are FP32 in memory (activations fp32 NHWC,
+ * weights fp32 in the same packed layouts: w_down [25][cs][cb], w_up [25][cb][cs], Linear [out][in]), read by the tensor
+ * cores as TF32 (10-bit mantissa), accumulated in fp32 in TMEM, written as fp32.  The reference's layers are fp32
+ * (model.py:388-408, 449-509); this is the mode that tracks them to 1e-3.  Requires channel counts % 32 == 0 (the three
+ * 3-channel layers stay on the bf16 path); dw_packed of dm_conv_wgrad_tf32 is the tap-major [25][cs][cb] layout. */
+int dm_gemm_tf32(const dm_gemm_desc* g, void* stream);
+int dm_conv_down_tf32(const dm_conv_geom* g, const void* big, const void* w_down, const float* bias, void* out_small,
+                      void* stream);
+int dm_conv_up_tf32(const dm_conv_geom* g, const void* small, const void* w_up, const float* bias, void* out_big,
+                    void* stream);
+int dm_conv_wgrad_tf32(const dm_conv_geom* g, const void* small, const void* big, float* dw_packed, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * HBM-bound ops.  "rows x c" = channel-innermost matrix view of an NHWC activation (rows = b*h*w) or of a
  * Linear output (rows = batch).  act: 0 none, 1 ReLU, 2 LeakyReLU(slope).
