@@ -1073,7 +1073,8 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    float step_size, float beta1, float beta2, float omb1, float omb2,
                                                    float eps, float bc2_sqrt, float grad_scale, __nv_bfloat16* __restrict__ shadow,
                                                    const int* __restrict__ step_dev, double lr_d, double beta1_d,
-                                                   double beta2_d) {
+                                                   double beta2_d, const int* __restrict__ enable) {
+  if (enable && *enable == 0) return;  // a deferred update whose gradient has not been produced yet (or was applied)
   if (step_dev) {  // CUDA-graph mode: bias corrections from the device-side step counter (same double arithmetic)
     __shared__ float sh[2];
     if (threadIdx.x == 0) {
@@ -1409,9 +1410,9 @@ extern "C" int dm_bce_const(const float* p, int n, float n_total, float target, 
   DM_LAUNCHED("dm_bce_const");
 }
 
-extern "C" int dm_adam_step_ex(float* p, const void* g, int g_bf16, float* m, float* v, long long n, double lr,
-                               double beta1, double beta2, double eps, int step, int* step_dev, int count_step,
-                               float grad_scale, void* shadow_bf16, void* stream_) {
+static int adam_impl(float* p, const void* g, int g_bf16, float* m, float* v, long long n, double lr,
+                     double beta1, double beta2, double eps, int step, int* step_dev, int count_step,
+                     float grad_scale, void* shadow_bf16, const int* enable_dev, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   DM_REQUIRE(step >= 1 || step_dev != nullptr, "dm_adam_step: step must be >= 1 (or a device counter given)");
   // scalar arithmetic in double, then rounded to float once -- as torch.optim.Adam does with Python floats
@@ -1432,13 +1433,31 @@ extern "C" int dm_adam_step_ex(float* p, const void* g, int g_bf16, float* m, fl
     adam_kernel<bf16><<<grid, 256, 0, s>>>(p, static_cast<const bf16*>(g), m, v, n, step_size, static_cast<float>(beta1),
                                            static_cast<float>(beta2), static_cast<float>(1.0 - beta1),
                                            static_cast<float>(1.0 - beta2), static_cast<float>(eps), bc2s, grad_scale,
-                                           static_cast<bf16*>(shadow_bf16), step_dev, lr, beta1, beta2);
+                                           static_cast<bf16*>(shadow_bf16), step_dev, lr, beta1, beta2, enable_dev);
   else
     adam_kernel<float><<<grid, 256, 0, s>>>(p, static_cast<const float*>(g), m, v, n, step_size, static_cast<float>(beta1),
                                             static_cast<float>(beta2), static_cast<float>(1.0 - beta1),
                                             static_cast<float>(1.0 - beta2), static_cast<float>(eps), bc2s, grad_scale,
-                                            static_cast<bf16*>(shadow_bf16), step_dev, lr, beta1, beta2);
+                                            static_cast<bf16*>(shadow_bf16), step_dev, lr, beta1, beta2, enable_dev);
   DM_LAUNCHED("dm_adam_step");
+}
+
+extern "C" int dm_adam_step_ex(float* p, const void* g, int g_bf16, float* m, float* v, long long n, double lr,
+                               double beta1, double beta2, double eps, int step, int* step_dev, int count_step,
+                               float grad_scale, void* shadow_bf16, void* stream_) {
+  return adam_impl(p, g, g_bf16, m, v, n, lr, beta1, beta2, eps, step, step_dev, count_step, grad_scale, shadow_bf16,
+                   nullptr, stream_);
+}
+
+// Same, gated by a device-side flag: the launch is a no-op when *enable_dev == 0.  Lets a CUDA graph contain the DEFERRED
+// update of a tensor (applied at the start of the next step, under work that does not read it): the flag says whether
+// the gradient buffer holds an unapplied gradient.
+extern "C" int dm_adam_step_gated(float* p, const void* g, int g_bf16, float* m, float* v, long long n, double lr,
+                                  double beta1, double beta2, double eps, int* step_dev, float grad_scale,
+                                  void* shadow_bf16, const int* enable_dev, void* stream_) {
+  DM_REQUIRE(step_dev != nullptr && enable_dev != nullptr, "dm_adam_step_gated: device step counter and flag required");
+  return adam_impl(p, g, g_bf16, m, v, n, lr, beta1, beta2, eps, 0, step_dev, 0, grad_scale, shadow_bf16, enable_dev,
+                   stream_);
 }
 
 extern "C" int dm_adam_step(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1,

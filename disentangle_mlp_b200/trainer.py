@@ -159,7 +159,13 @@ class FlatParams:
                     self.cache.static_packs[n[:-len(".weight")]] = engine.pack3(p.detach())
         self._zero_ranges, self._late_ranges = plan["zero_ranges"], plan["late_ranges"]
         self.reducer, self.shard, self._gather_pending = None, False, False
+        # deferred update of the big bf16-gradient tensors (adam(big="defer")): device flag "grad16 holds an unapplied
+        # gradient" (read by the gated Adam launch inside the step graph) + its host mirror
+        self.big_valid = torch.zeros((), dtype=torch.int32, device=dev)
+        self._big_pending, self._big_event = False, None
         self.params_changed()
+        module.register_load_state_dict_pre_hook(lambda *_a, **_k: self.flush())
+        module.register_state_dict_pre_hook(lambda *_a, **_k: self.flush())  # (direct .parameters() reads: T.sync() first)
         # module.load_state_dict() copies into the re-homed fp32 masters: refresh the bf16 shadow / operand packs
         module.register_load_state_dict_post_hook(lambda _m, _keys: self.params_changed())
 
@@ -249,15 +255,22 @@ class FlatParams:
         for lo, hi in self._zero_ranges:
             self.grad[lo:hi].zero_()
 
-    def adam(self, grad_scale=1.0, gather=True):
+    def adam(self, grad_scale=1.0, gather=True, big="now", side=None):
         """One Adam update; the step count lives on the device (incremented by the kernel) so that the call can be
         replayed from a CUDA graph; the host mirror `step_count` is kept for the optimizer state dict.
         Sharded big tensors (attach()): only this rank's chunk is updated; gather=True launches the all-gather of the
         bf16 shadows right away (asynchronously on the NCCL stream: reducer.wait() before their first use),
         gather=False leaves it pending for gather_if_pending() -- e.g. at the start of the next step, under work that
-        does not read those weights."""
+        does not read those weights.
+        big (not sharded): what to do with the big bf16-gradient tensors (2 x 33.5 M elements = 2/3 of this call's HBM
+        traffic for the VAE): "now" = inline; "side" = on the stream `side` right away, wait_big() before their first
+        use; "defer" = leave the gradient in place, flagged valid, and apply it in finish_big() -- at the start of the
+        next step on a side stream, under work that does not read those weights (flush() applies it immediately)."""
         self.step_count += 1
+        split = big != "now" and not self.shard and bool(self.big16)
         for i, (lo, hi, o16) in enumerate(self._segments):
+            if o16 is not None and split:
+                continue
             if o16 is not None and self.shard:
                 a, b = self.reducer.chunk(hi - lo)
                 g = self.grad16[o16 + a:o16 + b]
@@ -272,6 +285,50 @@ class FlatParams:
             self._gather_pending = True
             if gather:
                 self.gather_if_pending()
+        if split:
+            self.big_valid.fill_(1)
+            self._big_pending = True
+            if big == "side":
+                self.finish_big(side)
+
+    def finish_big(self, side=None):
+        """Apply the pending update of the big tensors (gated by the device flag, so the launches are safe to capture
+        and replay): on stream `side` when given (asynchronous; wait_big() orders a consumer behind it), else inline."""
+        if not self.big16 or self.shard:
+            return
+
+        def run():
+            for lo, hi, o16 in self._segments:
+                if o16 is not None:
+                    ops.adam_step(self.flat[lo:hi], self.grad16[o16:o16 + (hi - lo)], self.m[lo:hi], self.v[lo:hi], self.lr,
+                                  self.betas[0], self.betas[1], self.eps, 0, 1.0, self.shadow[lo:hi],
+                                  step_dev=self.step_dev, enable=self.big_valid)
+
+        if side is None:
+            run()
+            self._big_event = None
+        else:
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                run()
+                self._big_event = torch.cuda.Event()
+                self._big_event.record(side)
+        self._big_pending = False
+        self.touch()
+
+    def wait_big(self):
+        """Order the current stream behind the last side-stream update of the big tensors."""
+        if self._big_event is not None:
+            torch.cuda.current_stream().wait_event(self._big_event)
+
+    def flush(self):
+        """Apply any deferred update NOW (before the parameters / moments are read or replaced from outside)."""
+        if self._big_pending or self._big_event is not None:
+            self.wait_big()
+            if self._big_pending:
+                self.finish_big()
+            self.big_valid.zero_()  # a captured step graph must not apply this gradient again
+            self._big_event = None
 
     def gather_if_pending(self):
         """All-gather the bf16 shadows of the sharded tensors (asynchronous, NCCL stream) if an update is pending."""
@@ -303,6 +360,7 @@ class FlatParams:
         self.reducer.wait()
 
     def snapshot(self):
+        self.flush()
         return {"flat": self.flat.clone(), "m": self.m.clone(), "v": self.v.clone(), "step": self.step_count,
                 "buffers": {k: b.clone() for k, b in self.buffers.items()}}
 
@@ -315,10 +373,13 @@ class FlatParams:
         for k, b in self.buffers.items():
             b.copy_(snap["buffers"][k])
         self._gather_pending = False
+        self._big_pending, self._big_event = False, None
+        self.big_valid.zero_()
         self.params_changed()
 
     def optimizer_state_dict(self):
         """torch.optim.Adam-compatible state (exp_avg / exp_avg_sq / step per parameter)."""
+        self.flush()
         state = {}
         for i, n in enumerate(self.names):
             o, k = self.offsets[n], self.P[n].numel()
@@ -331,6 +392,7 @@ class FlatParams:
         return {"state": state, "param_groups": [group]}
 
     def load_optimizer_state_dict(self, sd):
+        self.flush()
         steps = set()
         for i, n in enumerate(self.names):
             st = sd["state"].get(i)
@@ -468,6 +530,26 @@ class _Base:
     def flat_params(self):
         raise NotImplementedError
 
+    DEFER = os.environ.get("DM_DEFER_BIG", "1") != "0"  # A/B: big-tensor Adam off the critical path
+
+    def _deferred(self):
+        """FlatParams whose step-final Adam leaves the big tensors to the start of the next step"""
+        return []
+
+    def _side(self):
+        if getattr(self, "_side_stream", None) is None:
+            self._side_stream = torch.cuda.Stream()
+        return self._side_stream
+
+    @staticmethod
+    def _before_use(fp):
+        """engine hook: order the stream behind whatever still updates fp's big Linear weights (the all-gather of a
+        sharded update, or a side-stream / deferred Adam) right before a network first reads them"""
+        def wait():
+            fp.wait_gathered()
+            fp.wait_big()
+        return wait
+
     def _attach(self):
         for fp in self.flat_params():
             fp.attach(self.dist)
@@ -477,6 +559,7 @@ class _Base:
         outside step(): sampling, evaluation); masters=True also gathers the fp32 masters / Adam moments (before
         state_dict() / optimizer_state_dict(): checkpoints)."""
         for fp in self.flat_params():
+            fp.flush()
             fp.gather_if_pending()
             if masters:
                 fp.gather_masters()
@@ -573,6 +656,7 @@ class _Base:
             # events recorded while capturing belong to the graph: they must not be waited on by eager code afterwards
             for fp in fps:
                 fp._gather_event = None
+                fp._big_event = None
             self.dist.cuda_pending = False
         self.graph_launches_per_step = _lib.launch_count() - l0  # libdm_b200 kernels captured in one step
         self._adams_per_step = [fp.step_count - c for fp, c in zip(fps, counts0)]
@@ -616,6 +700,7 @@ class _Base:
             fp.step_count += n
             fp.touch()
             fp._gather_pending = fp.shard  # the step's last sharded update is gathered at the start of the next replay
+            fp._big_pending = fp in self._deferred()  # ... and a deferred big-tensor update is applied there
         self.metrics = gmetrics
         return self.metrics
 
@@ -635,6 +720,9 @@ class VAETrainer(_Base):
     def flat_params(self):
         return [self.fp]
 
+    def _deferred(self):
+        return [self.fp] if (self.DEFER and not self.fp.shard) else []
+
     def step(self, data, eps=None):
         if self._graph is not None:
             return self._graph_step(data, 0.0, 0.0, None if eps is None else [eps])
@@ -646,10 +734,12 @@ class VAETrainer(_Base):
         loss = _scalar(dev)
         fp.zero_grad()
         fp.gather_if_pending()  # sharded Adam: the previous step's update reaches the other ranks under the encoder convs
+        if self.DEFER:  # ... single GPU: the previous step's update of the two big Linear weights runs under them
+            fp.finish_big(self._side())
         pim = ops.pim_empty(b, dev)
         data = self._ingest(data, pim)
         mu, logvar, Se = engine.encoder_forward(None, fp.P, fp.buffers, fp.cache, True, pim=pim,
-                                                before_heads=fp.wait_gathered if fp.shard else None)
+                                                before_heads=self._before_use(fp))
         if eps is None:
             eps = torch.randn_like(mu)
         _, z16 = ops.reparam_forward(mu, logvar, eps)
@@ -664,7 +754,7 @@ class VAETrainer(_Base):
         engine.encoder_backward(Se, dmu, dlv, fp.P, fp.G, fp.cache, True, overwrite_big=True,
                                 grad_ready=self._early(fp))
         fp.reduce_rest_and_wait(self.dist)
-        fp.adam(gather=False)
+        fp.adam(gather=False, big="defer" if self.DEFER else "now")
         self.metrics = {"loss": loss}
         return self.metrics
 
@@ -743,6 +833,9 @@ class BetaVAEGANTrainer(_Base):
     def flat_params(self):
         return [self.feg, self.fd]
 
+    def _deferred(self):
+        return [self.feg] if (self.DEFER and not self.feg.shard) else []
+
     def step(self, data, real_label=None, fake_label=None, noise=None, eps_dec=None, eps_enc=None):
         if self._graph is not None:
             rands = None if (noise is None and eps_dec is None and eps_enc is None) else [noise, eps_dec, eps_enc]
@@ -761,6 +854,8 @@ class BetaVAEGANTrainer(_Base):
         # sharded Adam (data parallel): the encoder-phase update of the previous step reaches the other ranks now, under
         # the discriminator phase, which does not read the encoder's weights
         feg.gather_if_pending()
+        if self.DEFER:  # single GPU: the same for the Adam update of the encoder's two 33.5 M-element Linear weights
+            feg.finish_big(self._side())
         pim = ops.pim_empty(3 * b, dev)
         data = self._ingest(data, pim[:b])
 
@@ -790,7 +885,7 @@ class BetaVAEGANTrainer(_Base):
         # (:123) lands before D is evaluated again, as in the reference
         feg.zero_grad()
         mu, logvar, Se = engine.encoder_forward(None, feg.P, feg.buffers, feg.cache, True, pim=pim[:b],
-                                                before_heads=feg.wait_gathered if feg.shard else None)
+                                                before_heads=self._before_use(feg))
         if eps_dec is None:
             eps_dec = torch.randn_like(mu)
         _, z16 = ops.reparam_forward(mu, logvar, eps_dec)
@@ -820,12 +915,13 @@ class BetaVAEGANTrainer(_Base):
                                 grad_ready=self._early(feg))
         del Sg2, Se
         feg.reduce_rest_and_wait(self.dist)
-        feg.adam()
+        # (big Linear weights on the side stream: the encoder convolutions of the next phase do not read them)
+        feg.adam(big="side" if self.DEFER else "now", side=self._side())
 
         # ================= "encoder" phase (:167-193): gradient of beta*KL + ||recon - x||^2, fresh forward
         feg.zero_grad()
         mu, logvar, Se = engine.encoder_forward(None, feg.P, feg.buffers, feg.cache, True, pim=pim[:b],
-                                                before_heads=feg.wait_gathered if feg.shard else None)
+                                                before_heads=self._before_use(feg))
         if eps_enc is None:
             eps_enc = torch.randn_like(mu)
         _, z16 = ops.reparam_forward(mu, logvar, eps_enc)
@@ -840,7 +936,9 @@ class BetaVAEGANTrainer(_Base):
         engine.encoder_backward(Se, dmu, dlv, feg.P, feg.G, feg.cache, True, overwrite_big=True,
                                 grad_ready=self._early(feg))
         feg.reduce_rest_and_wait(self.dist)
-        feg.adam(gather=False)  # (its all-gather rides under the next step's discriminator phase)
+        # (sharded: its all-gather rides under the next step's discriminator phase; single GPU: so does the update of the
+        # two big Linear weights itself)
+        feg.adam(gather=False, big="defer" if self.DEFER else "now")
         self.metrics = {"errD_real": errD_real, "errD_fake": errD_fake, "D_x": sum_dx / b, "errG_fake": errG_fake,
                         "errG_recon": errG_recon, "sim": sim_loss, "recon_dec": loss_dec, "kld": kld,
                         "recon_enc": loss_enc}

@@ -272,6 +272,14 @@ enum { DM_WS_GEMM = 0, DM_WS_CONV_FWD = 1, DM_WS_CONV_DGRAD = 2, DM_WS_CONV_WGRA
        DM_WS_BATCHNORM = 5, DM_WS_PADDED_IMAGE = 6, DM_WS_COLSUM = 7 };
 long long dm_workspace_bytes(int op, const long long* dims, int ndims);
 
+/* Same, as a DEFERRED update inside a CUDA graph: no-op when *enable_dev == 0 (device int: "the gradient buffer holds an
+ * unapplied gradient"); uses the device step counter without incrementing it.  The fused trainers apply the update of
+ * the two 33.5 M-element encoder Linear weights at the START of the next step on a side stream, under the discriminator
+ * phase, which does not read them. */
+int dm_adam_step_gated(float* p, const void* g, int g_bf16, float* m, float* v, long long n, double lr, double beta1,
+                       double beta2, double eps, int* step_dev, float grad_scale, void* shadow_bf16,
+                       const int* enable_dev, void* stream);
+
 /* Per-launch CUDA-event timing of the GEMM-class kernel (bench.py roofline). dm_profile_read synchronises the
  * device and returns the summed launch durations, algorithmic FLOPs (2*M*N*K; convolutions: 2*25*b*hs*ws*cs*cb)
  * and launch count since the previous read. */

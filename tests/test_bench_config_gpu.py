@@ -96,6 +96,7 @@ def test_betavaegan_graph_step_at_bench_batch(batch):
         m = {k: float(v) for k, v in T.step(xg, 0.9, 0.1, noise.cuda(), e1.cuda(), e2.cuda()).items()}
         for k, tol in TOL_FIRST.items():
             assert abs(m[k] - r[k]) <= tol * abs(r[k]), (batch, s, k, m[k], r[k])
+        T.sync()  # the step leaves the update of the two big encoder Linear weights to the start of the next replay
         u_eg, u_d = update_rel(mEG, rEG, init_eg), update_rel(mD, rD, init_d)
         print(f"batch {batch} step {s}: one-step update error EG {u_eg:.3e} D {u_d:.3e}")
         # Adam's first updates are ~ -lr*sign(g) for EVERY element, however small its gradient: a fraction f of elements
@@ -137,6 +138,7 @@ def test_gan_graph_step_at_batch_256():
         for k, tol in (("errD", 5e-3), ("D_x", 5e-3), ("D_G_z1", 5e-3), ("errG", 2e-2), ("D_G_z2", 3e-2)):
             sc = 1.0 if s == 0 else 3.0
             assert abs(m[k] - r[k]) <= sc * tol * abs(r[k]), (s, k, m[k], r[k])
+    T.sync()
     assert params_rel(mG, rG) < 2e-2 and params_rel(mD, rD) < 5e-2
     assert bn_running_rel(mG, rG) < 2e-2 and bn_running_rel(mD, rD) < 2e-2
     assert int(mD.convs[1].num_batches_tracked) == 6

@@ -38,6 +38,7 @@ def test_vae_trainer_tracks_oracle(mods):
         r = steps.vae_step(ref, o, x, eps)
         m = float(T.step(x.cuda(), eps.cuda())["loss"])
         assert abs(m - r["loss"]) <= 1e-2 * r["loss"], (s, m, r["loss"])
+    T.sync()  # (apply the deferred update of the big Linear weights before reading the parameters)
     assert params_rel(mine, ref) < 3e-2
     assert int(mine.features[1].num_batches_tracked) == 5
 
@@ -63,6 +64,7 @@ def test_gan_trainer_tracks_oracle(mods):
         m = {k: float(v) for k, v in T.step(x.cuda(), real, fake, noise.cuda()).items()}
         assert abs(m["errD"] - r["errD"]) <= 3e-2 * abs(r["errD"]), (s, m, r)
         assert abs(m["errG"] - r["errG"]) <= 3e-2 * abs(r["errG"]), (s, m, r)
+    T.sync()
     assert params_rel(mG, rG) < 2e-2 and params_rel(mD, rD) < 5e-2
     assert int(mD.convs[1].num_batches_tracked) == 9  # three D forwards per step
 
@@ -91,6 +93,7 @@ def test_betavaegan_trainer_first_step_and_counters(mods):
     for k, tol in (("errG_fake", 2e-2), ("errG_recon", 2e-2), ("sim", 5e-2), ("recon_dec", 2e-2), ("kld", 0.15),
                    ("recon_enc", 5e-2)):
         assert abs(m[k] - r[k]) <= tol * abs(r[k]), (k, m[k], r[k])
+    T.sync()
     # update order / counts: D stepped once, EG twice; BN running stats D 5x, encoder 2x, decoder 3x
     assert T.fd.step_count == 1 and T.feg.step_count == 2
     assert int(mD.convs[1].num_batches_tracked) == 5
@@ -127,6 +130,7 @@ def test_cuda_graph_step_matches_eager(mods):
         first = {k: float(v) for k, v in T.step(x, 0.9, 0.1).items()}
         for s in range(2):
             T.step(x, 0.9, 0.1)
+        T.sync()
         outs.append((torch.cat([p.detach().flatten() for p in eg.parameters()]).clone(),
                      torch.cat([p.detach().flatten() for p in d.parameters()]).clone(),
                      first, T.feg.step_count, int(T.feg.step_dev), T.fd.step_count,

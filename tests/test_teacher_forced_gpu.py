@@ -72,6 +72,7 @@ def _run(workload, nsteps, b):
         m = {k: float(v) for k, v in T.step(xg, real, fake, *[t.cuda() for t in rands]).items()}
         for k in r:
             devs.setdefault(k, []).append(abs(m[k] - r[k]) / (abs(r[k]) + 1e-9))
+        T.sync()  # (apply the deferred big-tensor update before the parameters are read)
         for key, mm, rr, p0 in (("a", ma, ra, pa0), ("d", md, rd, pd0)):
             du_ref = _flat(rr) - p0
             du = _flat(mm) - p0
