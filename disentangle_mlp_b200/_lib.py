@@ -68,10 +68,10 @@ _SIGS = {
     "dm_nhwc3_to_nchw": [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "dm_tanh_backward": [c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "dm_pad_image3": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p],
-    "dm_pack_conv3_weights": [c_void_p, c_int, c_void_p, c_void_p],
+    "dm_pack_conv3_weights": [c_void_p, c_int, c_int, c_void_p, c_void_p],
     "dm_conv3_fwd": [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_void_p, C.POINTER(BnFuse), c_void_p],
     "dm_conv3_wgrad": [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_void_p],
-    "dm_unpack_conv3_grad": [c_void_p, c_int, c_void_p, c_void_p],
+    "dm_unpack_conv3_grad": [c_void_p, c_int, c_int, c_void_p, c_void_p],
     "dm_transpose_bf16": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "dm_pack_conv_weights": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "dm_pack_up_merged": [c_void_p, c_int, c_int, c_void_p, c_void_p],

@@ -42,14 +42,14 @@ extern "C" long long dm_workspace_bytes(int op, const long long* dims, int ndims
       return 0;
     case DM_WS_CONV_WGRAD:  // cs, cb: tap-major packed gradient [25][cs][cb] fp32 (only when dw is NOT already tap-major)
       return 25ll * d(0) * d(1) * 4;
-    case DM_WS_CONV3_WGRAD:  // cs: window-layout gradient [5][cs][64] fp32 (zero on entry / exit)
-      return 5ll * d(0) * 64 * 4;
+    case DM_WS_CONV3_WGRAD:  // cs, stride: window-layout gradient [5][cs or 2*cs][64] fp32 (zero on entry / exit)
+      return 5ll * d(0) * (d(1) == 1 ? 2 : 1) * 64 * 4;
     case DM_WS_BATCHNORM: {  // c, groups: slot scratch (zero on entry / exit)
       const long long c = d(0), g = d(1) > 0 ? d(1) : 1;
       return (g * dm::kBnSlots * 2 * c + 4 + 2 * g * c) * 4;
     }
-    case DM_WS_PADDED_IMAGE:  // batch: bf16 [batch][68][72][8]
-      return d(0) * 68 * 72 * 8 * 2;
+    case DM_WS_PADDED_IMAGE:  // batch: bf16 [batch][68][72][4] + 64 elements of slack
+      return (d(0) * 68 * 72 * 4 + 64) * 2;
     case DM_WS_COLSUM: {  // rows, c: [dm_bn_parts(rows, c)][c] fp32 partial sums (dm_act_backward / dm_colsum)
       return static_cast<long long>(dm_bn_parts(d(0), static_cast<int>(d(1)))) * d(1) * 4;
     }

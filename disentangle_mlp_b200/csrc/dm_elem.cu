@@ -640,33 +640,33 @@ __global__ void __launch_bounds__(256) im2col3_kernel(const float* __restrict__ 
 }
 
 // ---- padded image ("pim"): the 3-channel image side of the three image-facing layers as a TMA-friendly operand.
-// bf16 [batch][kPimH = 68][kPimW = 72][8]: pixel (h, w) at [h + 2][w + 2], channels 3..7 and the 2-pixel border (+ 4
-// spare pixels per row) are zero.  A 5x5 filter ROW of output pixel (oh, ow) is then the 40 contiguous elements
-// starting at padded pixel (s*oh + kh, s*ow): the implicit GEMM reads it as a 64-element TMA box over a tensor map
-// whose pixel stride (16 B) is smaller than the box (overlapping windows) -- no im2col matrix (dm_gemm.cu: dm_conv3_*).
+// bf16 [batch][kPimH = 68][kPimW = 72][4]: pixel (h, w) at [h + 2][w + 2]; channel 3, the 2-pixel border and 4 spare
+// pixels per row are zero.  A 5x5 filter ROW of an output pixel is then 5 pixels x 4 channels = 20 contiguous elements.
+// TMA strides must be multiples of 16 bytes = TWO pixels, so the implicit GEMM (dm_gemm.cu: dm_conv3_*) reads a window
+// of 8 pixels (32 elements, 64 B) starting at an EVEN pixel per output-pixel PAIR (stride 1) or per output pixel
+// (stride 2), over a tensor map whose position stride (16 B) is smaller than the box: overlapping windows, no im2col.
 constexpr int kPimH = 68, kPimW = 72;
 
 __device__ __forceinline__ void pim_store(__nv_bfloat16* pim, long long n, int h, int w, float r, float g, float b) {
-  bf16x8 v;
-  v.v[0] = __floats2bfloat162_rn(r, g);
-  v.v[1] = __floats2bfloat162_rn(b, 0.f);
-  v.v[2] = __floats2bfloat162_rn(0.f, 0.f);
-  v.v[3] = v.v[2];
-  *reinterpret_cast<bf16x8*>(pim + ((n * kPimH + h + 2) * kPimW + w + 2) * 8) = v;
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(r, g), hi = __floats2bfloat162_rn(b, 0.f);
+  uint2 v;
+  v.x = *reinterpret_cast<const uint32_t*>(&lo);
+  v.y = *reinterpret_cast<const uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(pim + ((n * kPimH + h + 2) * kPimW + w + 2) * 4) = v;
 }
 
-// zero border of one padded image: rows 0,1,66,67 entirely, columns 0,1 and 66..71 of the other rows
+// zero border of one padded image: rows 0,1,66,67 entirely, pixels 0,1 and 66..71 of the other rows (16 B = 2 pixels)
 __device__ __forceinline__ void pim_zero_border(__nv_bfloat16* pim, long long n, int tid, int nt) {
-  bf16x8 z;
-  z.v[0] = z.v[1] = z.v[2] = z.v[3] = __floats2bfloat162_rn(0.f, 0.f);
-  bf16x8* base = reinterpret_cast<bf16x8*>(pim + n * kPimH * kPimW * 8);
-  for (int i = tid; i < 4 * kPimW; i += nt) {
-    const int r = i / kPimW, col = i - r * kPimW;
-    base[(r < 2 ? r : 64 + r) * kPimW + col] = z;
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  uint4* base = reinterpret_cast<uint4*>(pim + n * kPimH * kPimW * 4);
+  constexpr int kRow16 = kPimW / 2;  // 16-byte pieces per row
+  for (int i = tid; i < 4 * kRow16; i += nt) {
+    const int r = i / kRow16, col = i - r * kRow16;
+    base[(r < 2 ? r : 64 + r) * kRow16 + col] = z;
   }
-  for (int i = tid; i < 64 * 8; i += nt) {
-    const int r = i >> 3, j = i & 7;
-    base[(r + 2) * kPimW + (j < 2 ? j : 64 + j)] = z;
+  for (int i = tid; i < 64 * 4; i += nt) {
+    const int r = i >> 2, j = i & 3;
+    base[(r + 2) * kRow16 + (j == 0 ? 0 : 32 + j)] = z;  // pixels 0-1, 66-67, 68-69, 70-71
   }
 }
 
@@ -766,28 +766,36 @@ __global__ void __launch_bounds__(256) tanh_bwd_kernel(const float* __restrict__
   }
 }
 
-// fp32 weight [cs][3][5][5] -> bf16 window pack w_win[kh][cs][64]: element kw*8 + c (kw < 5, c < 3), zero elsewhere --
-// the K-major B operand matching a 64-element pim window
-__global__ void __launch_bounds__(256) pack_win_kernel(const float* __restrict__ w, int cs, __nv_bfloat16* __restrict__ w_win) {
-  const int total = 5 * cs * 64;
+// fp32 weight [cs][3][5][5] -> bf16 window pack: the K-major B operand matching a 32-element pim window (8 pixels x 4
+// channels, element j*4 + c).  stride 2 (window starts at the output pixel's own first tap): w_win[kh][cs][32], kw = j.
+// stride 1 (one window per output-pixel PAIR, starting at the even pixel): w_win[kh][pw*cs + n][32], kw = j - pw.
+__global__ void __launch_bounds__(256) pack_win_kernel(const float* __restrict__ w, int cs, int stride,
+                                                       __nv_bfloat16* __restrict__ w_win) {
+  const int nn = stride == 1 ? 2 * cs : cs;
+  const int total = 5 * nn * 32;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int e = i & 63, n = (i >> 6) % cs, kh = i / (64 * cs);
-    const int kw = e >> 3, c = e & 7;
+    const int e = i & 31, row = (i >> 5) % nn, kh = i / (32 * nn);
+    const int pw = row / cs, n = row - pw * cs;
+    const int j = e >> 2, c = e & 3, kw = j - pw;
     float v = 0.f;
-    if (kw < 5 && c < 3) v = w[((n * 3 + c) * 5 + kh) * 5 + kw];
+    if (kw >= 0 && kw < 5 && c < 3) v = w[((n * 3 + c) * 5 + kh) * 5 + kw];
     w_win[i] = __float2bfloat16_rn(v);
   }
 }
 
-// window-layout weight gradient scratch [kh][cs][64] (fp32) -> dw[cs][3][5][5] += ; the scratch is re-zeroed
-__global__ void __launch_bounds__(256) unpack_win_grad_kernel(float* __restrict__ scratch, int cs, float* __restrict__ dw) {
-  const int total = 5 * cs * 64;
+// window-layout weight gradient scratch [kh][nn][64] (fp32; nn = cs, or 2*cs = (pw, n) for stride 1; element j*4 + c of
+// a 16-pixel window) -> dw[cs][3][5][5] += ; the scratch is re-zeroed
+__global__ void __launch_bounds__(256) unpack_win_grad_kernel(float* __restrict__ scratch, int cs, int stride,
+                                                              float* __restrict__ dw) {
+  const int nn = stride == 1 ? 2 * cs : cs;
+  const int total = 5 * nn * 64;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int e = i & 63, n = (i >> 6) % cs, kh = i / (64 * cs);
-    const int kw = e >> 3, c = e & 7;
+    const int e = i & 63, row = (i >> 6) % nn, kh = i / (64 * nn);
+    const int pw = row / cs, n = row - pw * cs;
+    const int j = e >> 2, c = e & 3, kw = j - pw;
     const float v = scratch[i];
     scratch[i] = 0.f;
-    if (kw < 5 && c < 3) dw[((n * 3 + c) * 5 + kh) * 5 + kw] += v;
+    if (kw >= 0 && kw < 5 && c < 3) atomicAdd(dw + ((n * 3 + c) * 5 + kh) * 5 + kw, v);  // (two pw rows share a dw entry)
   }
 }
 
@@ -1299,7 +1307,9 @@ extern "C" int dm_tanh_backward(const float* dout, const float* out, long long b
   DM_LAUNCHED("dm_tanh_backward");
 }
 
-extern "C" long long dm_pim_elems(int batch) { return static_cast<long long>(batch) * kPimH * kPimW * 8; }
+// elements of a padded-image buffer for `batch` images: [batch][68][72][4] plus 64 elements of slack (the 16-pixel windows
+// of the weight-gradient GEMM read up to 48 bytes past the last row of the last image; what they read is discarded)
+extern "C" long long dm_pim_elems(int batch) { return static_cast<long long>(batch) * kPimH * kPimW * 4 + 64; }
 
 extern "C" int dm_pad_image3(const void* src, int src_u8, int batch, void* pim_bf16, float* dst_nchw, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
@@ -1310,15 +1320,17 @@ extern "C" int dm_pad_image3(const void* src, int src_u8, int batch, void* pim_b
   DM_LAUNCHED("dm_pad_image3");
 }
 
-extern "C" int dm_pack_conv3_weights(const float* w, int cs, void* w_win, void* stream_) {
+extern "C" int dm_pack_conv3_weights(const float* w, int cs, int stride, void* w_win, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-  pack_win_kernel<<<grid_for(5ll * cs * 64), 256, 0, s>>>(w, cs, static_cast<bf16*>(w_win));
+  DM_REQUIRE(stride == 1 || stride == 2, "dm_pack_conv3_weights: stride must be 1 or 2");
+  pack_win_kernel<<<grid_for(5ll * cs * 64), 256, 0, s>>>(w, cs, stride, static_cast<bf16*>(w_win));
   DM_LAUNCHED("dm_pack_conv3_weights");
 }
 
-extern "C" int dm_unpack_conv3_grad(float* scratch, int cs, float* dw, void* stream_) {
+extern "C" int dm_unpack_conv3_grad(float* scratch, int cs, int stride, float* dw, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-  unpack_win_grad_kernel<<<grid_for(5ll * cs * 64), 256, 0, s>>>(scratch, cs, dw);
+  DM_REQUIRE(stride == 1 || stride == 2, "dm_unpack_conv3_grad: stride must be 1 or 2");
+  unpack_win_grad_kernel<<<grid_for(5ll * cs * 128), 256, 0, s>>>(scratch, cs, stride, dw);
   DM_LAUNCHED("dm_unpack_conv3_grad");
 }
 

@@ -1752,25 +1752,30 @@ extern "C" int dm_conv_wgrad_tf32(const dm_conv_geom* g, const void* small, cons
 // ------------------------------------------------------------------------------------------ 3-channel image side
 // The three layers that touch the 3-channel image (Discriminator convs.0 / Encoder features.0 forward and weight
 // gradient, decoder deconv4 input- and weight-gradient) as implicit GEMMs over the PADDED IMAGE (dm_pad_image3):
-// bf16 [b][68][72][8], pixel (h, w) at [h+2][w+2], zero border / channels.  A filter row kh of output pixel (oh, ow) is
-// the contiguous run of 5 pixels x 8 channels starting at padded pixel (s*oh + kh, s*ow); the A operand of k-block kh
-// is a TMA box of 64 elements (8 pixels: the last 3 multiply zero weights) per output pixel over a tensor map whose
-// pixel stride (16 B) is smaller than the box -- overlapping windows.  K = 5 x 64 instead of 75, but no im2col matrix:
-// 16 B/pixel of image traffic instead of 160 B/pixel written + read.
+// bf16 [b][68][72][4], pixel (h, w) at [h+2][w+2], zero border / 4th channel.  A filter row kh of an output pixel is
+// the contiguous run of 5 pixels x 4 channels starting at padded pixel (s*oh + kh, s*ow).  TMA strides are multiples
+// of 16 B = two pixels, so the A operand of k-block kh is a box of 32 elements (8 pixels) starting at an EVEN pixel:
+//   stride 2: one window per output pixel (2*ow is even): M = pixels, N = cs, weights w_win[kh][cs][32];
+//   stride 1: one window per output-pixel PAIR (2*w2, 2*w2+1), the pair's two pixels as 2*cs output COLUMNS
+//             (pw*cs + n) with weights shifted by pw pixels: M = pairs, N = 2*cs -- and [pairs][2*cs] IS the NHWC tensor.
+// The tensor map's position stride (16 B) is smaller than the box (64 B): overlapping windows.  K = 5 x 32 instead of
+// 75, but no im2col matrix: 8 B/pixel of image instead of a 160 B/pixel matrix written and read.
 constexpr int kPimH = 68, kPimW = 72;
 
-// window view of the padded image: (e = 64 window elements, ow, row parity, oh', n)
-static int encode_pim_map(CUtensorMap* m, const void* pim, int batch, int stride, const uint32_t* box) {
-  const uint64_t px = 16, row = (uint64_t)kPimW * 16, img = (uint64_t)kPimH * row;
+// window view of the padded image: (e = `inner` window elements, position, row parity, row, n)
+static int encode_pim_map(CUtensorMap* m, const void* pim, int batch, int stride, const uint32_t* box, int inner) {
+  const uint64_t pos = 16, row = (uint64_t)kPimW * 8, img = (uint64_t)kPimH * row;
   uint64_t dims[5], str[4];
+  dims[0] = inner; dims[1] = 32; dims[4] = batch;
+  str[0] = pos; str[3] = img;
   if (stride == 1) {
-    dims[0] = 64; dims[1] = 64; dims[2] = 1; dims[3] = kPimH; dims[4] = batch;
-    str[0] = px; str[1] = row; str[2] = row; str[3] = img;
+    dims[2] = 1; dims[3] = kPimH;
+    str[1] = row; str[2] = row;
   } else {
-    dims[0] = 64; dims[1] = 32; dims[2] = 2; dims[3] = kPimH / 2; dims[4] = batch;
-    str[0] = 2 * px; str[1] = row; str[2] = 2 * row; str[3] = img;
+    dims[2] = 2; dims[3] = kPimH / 2;
+    str[1] = row; str[2] = 2 * row;
   }
-  return encode_map(m, pim, 5, dims, str, box, 128);
+  return encode_map(m, pim, 5, dims, str, box, inner * 2);  // 64 elements: SWIZZLE_128B, 32: SWIZZLE_64B
 }
 
 // taps of filter row kh in the window view: padded row = s*oh + kh
@@ -1781,22 +1786,23 @@ static void win_tap(Tap& t, int kh, int stride) {
   t.wt = static_cast<uint8_t>(kh);
 }
 
-/* out[b,hs,ws,cs] (bf16 NHWC) = conv5x5(image, W) + bias, stride 1 or 2, from the padded image; w_win = bf16 [5][cs][64]
- * (dm_pack_conv3_weights).  g: cb == 3, hb == wb == 64. */
+/* out[b,hs,ws,cs] (bf16 NHWC) = conv5x5(image, W) + bias, stride 1 or 2, from the padded image; w_win from
+ * dm_pack_conv3_weights(stride).  g: cb == 3, hb == wb == 64. */
 extern "C" int dm_conv3_fwd(const dm_conv_geom* g, const void* pim, const void* w_win, const float* bias, void* out_small,
                             const dm_bn_fuse* bn, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = check_geom(g, "dm_conv3_fwd")) return rc;
   t_kind = 1;
   DM_REQUIRE(g->cb == 3 && g->hb == 64 && g->wb == 64, "dm_conv3_fwd: needs a 3-channel 64x64 image side");
-  DM_REQUIRE(g->cs % 32 == 0 && g->cs <= 128, "dm_conv3_fwd: cs %d must be 32, 64, 96 or 128", g->cs);
-  PixTile pt;
-  DM_REQUIRE(make_pix_tile(128, g->batch, g->hs, g->ws, &pt) && pt.bimg == 1, "dm_conv3_fwd: unsupported grid");
+  DM_REQUIRE(g->cs == 32 || g->cs == 64, "dm_conv3_fwd: cs %d must be 32 or 64", g->cs);
+  const int nn = g->stride == 1 ? 2 * g->cs : g->cs;  // GEMM columns: (pixel of the pair, channel) or channel
+  PixTile pt;  // tiles of 128 window positions on the (hs rows) x (32 positions) grid
+  DM_REQUIRE(make_pix_tile(128, g->batch, g->hs, 32, &pt) && pt.bimg == 1, "dm_conv3_fwd: unsupported grid");
   GemmParams p;
   init_params(p);
   p.mode = MODE_FWD;
-  p.kc = 64;
-  p.bn = g->cs;
+  p.kc = 32;
+  p.bn = nn;
   p.cpt = 1;
   p.phase_tap_start[0] = 0;
   p.phase_tap_start[1] = 5;
@@ -1804,15 +1810,17 @@ extern "C" int dm_conv3_fwd(const dm_conv_geom* g, const void* pim, const void* 
   p.tw_step = 0; p.tpi = pt.tpi; p.th_step = pt.th_step; p.tn_step = pt.tn_step;
   p.bw = pt.bw; p.bh = pt.bh;
   p.out = out_small; p.bias = bias; p.out_f32 = 0; p.out_atomic = 0;
-  p.os_w = g->cs; p.os_h = (long long)g->ws * g->cs; p.os_n = (long long)g->hs * g->ws * g->cs; p.os_col = 1;
-  p.w_lim = g->ws; p.n_lim = g->batch; p.n_valid = g->cs;
-  uint32_t box[5] = {64, (uint32_t)pt.bw, 1, (uint32_t)pt.bh, 1};
-  if (int rc = encode_pim_map(&p.map_a, pim, g->batch, g->stride, box)) return rc;
+  p.bias_mod = g->cs;  // (stride 1: the 2*cs columns repeat the channels)
+  p.os_w = nn; p.os_h = 32ll * nn; p.os_n = (long long)g->hs * 32 * nn; p.os_col = 1;
+  p.w_lim = 32; p.n_lim = g->batch; p.n_valid = nn;
+  uint32_t box[5] = {32, (uint32_t)pt.bw, 1, (uint32_t)pt.bh, 1};
+  if (int rc = encode_pim_map(&p.map_a, pim, g->batch, g->stride, box, 32)) return rc;
   p.cg2 = (env_int("DM_CG2", 1) != 0 && pt.tiles >= 2) ? 1 : 0;
   const int cluster = p.cg2 ? 2 : 1;
-  if (int rc = encode_w_map3(&p.map_b, w_win, 5, g->cs, 64, 64, 64, p.bn / cluster, 128)) return rc;
+  if (int rc = encode_w_map3(&p.map_b, w_win, 5, nn, 32, 32, 32, p.bn / cluster, 64)) return rc;
   p.num_n_tiles = 1;
-  DM_REQUIRE(epi_rows_act(p, out_small, false, g->batch, g->hs, g->ws, g->cs, 1, pt), "dm_conv3_fwd: output not expressible as box stores");
+  // the output as the NHWC tensor [b][hs][32 positions][nn]
+  DM_REQUIRE(epi_rows_act(p, out_small, false, g->batch, g->hs, 32, nn, 1, pt), "dm_conv3_fwd: output not expressible as box stores");
   if (bn && bn->scratch) {
     DM_REQUIRE(groups_tile_aligned(pt, g->batch, bn->groups), "dm_conv3_fwd: groups do not fall on tile boundaries");
     if (int rc = attach_stats(p, bn, g->cs, pt.tiles, "dm_conv3_fwd")) return rc;
@@ -1820,17 +1828,19 @@ extern "C" int dm_conv3_fwd(const dm_conv_geom* g, const void* pim, const void* 
   return launch(p, dim3(pt.tiles, 1, 1), stream, 50.0 * g->batch * g->hs * g->ws * g->cs * g->cb, 1 << 30, cluster);
 }
 
-/* dw_win[5][cs][64] (fp32 window layout, dm_unpack_conv3_grad moves it to dw[cs][3][5][5]) +=
- *   sum over pixels of small[b,h,w,cs] (bf16 NHWC: the output gradient of a Conv2d / the input of deconv4) x window.
- * D[m = (filter row pair, window element)][n = cs], K = pixels. */
+/* dw_win[5][nn][64] (fp32 window layout, nn = cs or 2*cs; dm_unpack_conv3_grad moves it to dw[cs][3][5][5]) +=
+ *   sum over window positions of small (bf16 NHWC, viewed [positions][nn]: the output gradient of a Conv2d / the input
+ *   of deconv4) x 16-pixel window.  D[m = (filter row pair, window element)][n], K = positions. */
 extern "C" int dm_conv3_wgrad(const dm_conv_geom* g, const void* pim, const void* small, float* dw_win, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = check_geom(g, "dm_conv3_wgrad")) return rc;
   t_kind = 3;
   DM_REQUIRE(g->cb == 3 && g->hb == 64 && g->wb == 64, "dm_conv3_wgrad: needs a 3-channel 64x64 image side");
-  DM_REQUIRE(g->cs == 32 || g->cs == 64 || g->cs == 128, "dm_conv3_wgrad: cs %d must be 32, 64 or 128", g->cs);
-  PixTile pt;
-  DM_REQUIRE(make_pix_tile(64, g->batch, g->hs, g->ws, &pt) && pt.bimg == 1, "dm_conv3_wgrad: unsupported grid");
+  DM_REQUIRE((g->cs == 32 && g->stride == 1) || (g->cs == 64 && g->stride == 2),
+             "dm_conv3_wgrad: supports cs 32 / stride 1 and cs 64 / stride 2 (64 GEMM columns)");
+  const int nn = g->stride == 1 ? 2 * g->cs : g->cs;
+  PixTile pt;  // k-blocks of 64 window positions
+  DM_REQUIRE(make_pix_tile(64, g->batch, g->hs, 32, &pt) && pt.bimg == 1, "dm_conv3_wgrad: unsupported grid");
   GemmParams p;
   init_params(p);
   p.mode = MODE_WGRAD;
@@ -1838,14 +1848,14 @@ extern "C" int dm_conv3_wgrad(const dm_conv_geom* g, const void* pim, const void
   p.num_kb = pt.tiles;
   p.tw_step = 0; p.tpi = pt.tpi; p.th_step = pt.th_step; p.tn_step = pt.tn_step;
   p.out = dw_win; p.out_f32 = 1; p.out_atomic = 1;
-  p.bn = g->cs;
+  p.bn = nn;
   p.num_n_tiles = 1;
   p.wgrad_win = 1;
   p.wgrad_tap_on_a = 1;
   for (int u = 0; u < 3; ++u) {
     Tap& t = p.taps[2 * u];
     win_tap(t, 2 * u, g->stride);
-    t.nvalid = static_cast<int16_t>(g->cs);
+    t.nvalid = static_cast<int16_t>(nn);
     t.mvalid = static_cast<int16_t>(u == 2 ? 64 : 128);
     t.out_tap = static_cast<int16_t>(2 * u);
     Tap& t2 = p.taps[2 * u + 1];
@@ -1854,19 +1864,19 @@ extern "C" int dm_conv3_wgrad(const dm_conv_geom* g, const void* pim, const void
   }
   p.mmod = 64; p.m_valid = 128;
   uint32_t boxa[5] = {64, (uint32_t)pt.bw, 1, (uint32_t)pt.bh, 1};
-  if (int rc = encode_pim_map(&p.map_a, pim, g->batch, g->stride, boxa)) return rc;
-  // B = small [b,hs,ws,cs]: a 64-channel box; for cs == 32 its upper half is out of bounds = zeros (N = 32 is issued)
-  if (int rc = encode_act_map(&p.map_b, small, g->batch, g->hs, g->ws, g->cs, 1, boxa, 128)) return rc;
-  {  // transposed reduce-add into dw_win[5][cs][64]: box {32 m, 32 n, 1 filter row}
+  if (int rc = encode_pim_map(&p.map_a, pim, g->batch, g->stride, boxa, 64)) return rc;
+  // B = small viewed as [b][hs][32 positions][nn = 64]
+  if (int rc = encode_act_map(&p.map_b, small, g->batch, g->hs, 32, nn, 1, boxa, 128)) return rc;
+  {  // transposed reduce-add into dw_win[5][nn][64]: box {32 m, 32 n, 1 filter row}
     DM_REQUIRE((reinterpret_cast<uintptr_t>(dw_win) & 15) == 0, "dm_conv3_wgrad: dw_win must be 16-byte aligned");
-    uint64_t dims[3] = {64, (uint64_t)g->cs, 5};
-    uint64_t str[2] = {64 * 4, (uint64_t)g->cs * 64 * 4};
+    uint64_t dims[3] = {64, (uint64_t)nn, 5};
+    uint64_t str[2] = {64 * 4, (uint64_t)nn * 64 * 4};
     uint32_t box[3] = {32, 32, 1};
     if (int rc = encode_map(&p.map_out, dw_win, 3, dims, str, box, 0, true)) return rc;
     p.epi_tma = 2; p.epi_reduce = 1;
   }
   int splits = 1;
-  {  // split-K over the pixel tiles: whole waves of the persistent grid (as dm_conv_wgrad)
+  {  // split-K over the position tiles: whole waves of the persistent grid (as dm_conv_wgrad)
     const int slots = num_sms() * 2;
     const int fixed = env_int("DM_WGRAD_FIXED_KB", 12);
     long long best = -1;

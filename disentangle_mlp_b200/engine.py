@@ -55,15 +55,18 @@ def _lin_w(cache, name, p):
     return cache.get(("lin", name), p, lambda w: ops.cast_bf16(w.contiguous()))
 
 
-def pack3(w, out=None):
+CONV3_STRIDE = {"convs.0": 1, "features.0": 2, "deconv4": 1}  # the three layers on the 3-channel image side
+
+
+def pack3(w, stride, out=None):
     """operand packs of a 3-image-channel layer [cs][3][5][5]: (None, w_up kw-folded [25][16][cs] for the 32 -> 3
-    transposed direction, w_win [5][cs][64] for the GEMMs over the padded image)"""
+    transposed direction, w_win for the GEMMs over the padded image (ops.pack_conv3_weights))"""
     cs = w.shape[0]
     w = w.contiguous()
     if out is None:
         out = (None, torch.empty((25, 16, cs), dtype=BF16, device=w.device), None)
     ops.pack_conv_weights(w, cs, 3, False, True, False, out=(None, out[1], None))
-    return (None, out[1], ops.pack_conv3_weights(w, out=out[2]))
+    return (None, out[1], ops.pack_conv3_weights(w, stride, out=out[2]))
 
 
 def _conv_pack(cache, name, p, cs, cb):
@@ -72,7 +75,7 @@ def _conv_pack(cache, name, p, cs, cb):
     if static is not None:  # fused trainers: persistent buffers refreshed in place after every optimizer step
         return static[name]
     if cb == 3:
-        return cache.get(("conv", name), p, pack3)
+        return cache.get(("conv", name), p, lambda w: pack3(w, CONV3_STRIDE[name]))
     return cache.get(("conv", name), p, lambda w: ops.pack_conv_weights(w.contiguous(), cs, cb, True, True, False))
 
 
@@ -255,7 +258,7 @@ def conv3_wgrad(g, pim, small, dw, cache, name):
     ws = cache.wgrad_scratch
     key = (name, "win", str(dw.device))
     if key not in ws:
-        ws[key] = torch.zeros((5, g.cs, 64), dtype=F32, device=dw.device)
+        ws[key] = torch.zeros((5, ops.conv3_cols(g.cs, g.stride), 64), dtype=F32, device=dw.device)
     ops.conv3_wgrad(g, pim, small, dw, ws[key])
 
 

@@ -340,12 +340,14 @@ def im2col3(x_nchw, stride, out=None):
     return out
 
 
-PIM_H, PIM_W = 68, 72  # padded image: bf16 [b][68][72][8] (see dm_pad_image3)
+PIM_H, PIM_W, PIM_C = 68, 72, 4  # padded image: bf16 [b][68][72][4] (see dm_pad_image3)
 
 
 def pim_empty(batch, device):
-    """Uninitialised padded-image buffer for `batch` 64x64 images."""
-    return torch.empty((batch, PIM_H, PIM_W, 8), dtype=BF16, device=device)
+    """Uninitialised padded-image buffer for `batch` 64x64 images: a [batch,68,72,4] view of an allocation with the 64
+    elements of slack the weight-gradient GEMM's 16-pixel windows may read (and discard) past the last image."""
+    flat = torch.empty(int(_lib.load().dm_pim_elems(batch)), dtype=BF16, device=device)
+    return flat[:batch * PIM_H * PIM_W * PIM_C].view(batch, PIM_H, PIM_W, PIM_C)
 
 
 def pad_image3(x, pim=None, want_nchw=False):
@@ -362,12 +364,17 @@ def pad_image3(x, pim=None, want_nchw=False):
     return (pim, nchw if u8 else x) if want_nchw else pim
 
 
-def pack_conv3_weights(w, out=None):
-    """fp32 [cs][3][5][5] -> bf16 window pack [5][cs][64]"""
+def conv3_cols(cs, stride):
+    """GEMM columns of a 3-image-channel layer: cs, or 2*cs = (pixel of the output pair, channel) for stride 1"""
+    return 2 * cs if stride == 1 else cs
+
+
+def pack_conv3_weights(w, stride, out=None):
+    """fp32 [cs][3][5][5] -> bf16 window pack [5][cs or 2*cs][32] (dm_pack_conv3_weights)"""
     cs = w.shape[0]
     if out is None:
-        out = torch.empty((5, cs, 64), dtype=BF16, device=w.device)
-    _lib.check(_lib.load().dm_pack_conv3_weights(_p(w), cs, _p(out), _stream()), "dm_pack_conv3_weights")
+        out = torch.empty((5, conv3_cols(cs, stride), 32), dtype=BF16, device=w.device)
+    _lib.check(_lib.load().dm_pack_conv3_weights(_p(w), cs, stride, _p(out), _stream()), "dm_pack_conv3_weights")
     return out
 
 
@@ -381,12 +388,13 @@ def conv3_fwd(g: ConvGeom, pim, w_win, bias=None, out=None, bn=None):
 
 
 def conv3_wgrad(g: ConvGeom, pim, small, dw, scratch=None):
-    """dw[cs][3][5][5] (fp32) += sum_pixels small[b,h,w,cs] x 5x5 image patch.  scratch: zeroed fp32 [5][cs][64] window
-    gradient buffer (kept zeroed by the unpack kernel)."""
+    """dw[cs][3][5][5] (fp32) += sum_pixels small[b,h,w,cs] x 5x5 image patch.  scratch: zeroed fp32
+    [5][conv3_cols(cs, stride)][64] window gradient buffer (kept zeroed by the unpack kernel)."""
     if scratch is None:
-        scratch = torch.zeros((5, g.cs, 64), dtype=F32, device=pim.device)
+        scratch = torch.zeros((5, conv3_cols(g.cs, g.stride), 64), dtype=F32, device=pim.device)
+    assert scratch.numel() == 5 * conv3_cols(g.cs, g.stride) * 64
     _lib.check(_lib.load().dm_conv3_wgrad(C.byref(g), _p(pim), _p(small), _p(scratch), _stream()), "dm_conv3_wgrad")
-    _lib.check(_lib.load().dm_unpack_conv3_grad(_p(scratch), g.cs, _p(dw), _stream()), "dm_unpack_conv3_grad")
+    _lib.check(_lib.load().dm_unpack_conv3_grad(_p(scratch), g.cs, g.stride, _p(dw), _stream()), "dm_unpack_conv3_grad")
     return dw
 
 

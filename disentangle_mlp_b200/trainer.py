@@ -156,7 +156,8 @@ class FlatParams:
                         w_up = torch.empty((9, 4 * cb, cs), dtype=BF16, device=dev)
                     self.cache.static_packs[n[:-len(".weight")]] = (w_down, w_up, None)
                 else:
-                    self.cache.static_packs[n[:-len(".weight")]] = engine.pack3(p.detach())
+                    self.cache.static_packs[n[:-len(".weight")]] = engine.pack3(
+                        p.detach(), engine.CONV3_STRIDE[n[:-len(".weight")]])
         self._zero_ranges, self._late_ranges = plan["zero_ranges"], plan["late_ranges"]
         self.reducer, self.shard, self._gather_pending = None, False, False
         # deferred update of the big bf16-gradient tensors (adam(big="defer")): device flag "grad16 holds an unapplied
@@ -235,7 +236,7 @@ class FlatParams:
                 else:
                     ops.transpose(packs[0], 25, p.shape[0], p.shape[1], out=packs[1])
             else:
-                engine.pack3(p.detach(), out=packs)
+                engine.pack3(p.detach(), engine.CONV3_STRIDE[name], out=packs)
 
     def touch(self):
         """The fp32 masters were updated through raw pointers (Adam kernel, graph replay, restore): nn.Parameter

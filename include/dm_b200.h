@@ -193,28 +193,30 @@ int dm_tanh_backward(const float* dout, const float* out, long long batch, int h
                      float* bias_grad, void* pim_bf16, void* stream);
 
 /* ---- the 3-channel image side as TMA-fed implicit GEMMs over a PADDED IMAGE ("pim"):
- * bf16 [batch][68][72][8], pixel (h, w) of a 64x64 image at [h+2][w+2]; the 2-pixel border, 4 spare pixels per row and
- * channels 3..7 are zero (dm_pim_elems(batch) elements, 128-byte aligned).  A 5x5 filter ROW of an output pixel is then
- * 40 contiguous elements; the GEMMs read it as a 64-element box over a tensor map with overlapping pixel windows: no
- * im2col matrix exists.
+ * bf16 [batch][68][72][4], pixel (h, w) of a 64x64 image at [h+2][w+2]; the 2-pixel border, 4 spare pixels per row and
+ * the 4th channel are zero (dm_pim_elems(batch) elements incl. 64 of slack, 128-byte aligned).  A 5x5 filter ROW of an
+ * output pixel is then 20 contiguous elements; the GEMMs read 8-pixel (16-pixel: weight gradient) windows starting at
+ * even pixels over a tensor map with overlapping positions (TMA strides are multiples of 16 B = 2 pixels): one window
+ * per output pixel for stride 2, one per output-pixel PAIR for stride 1 (the pair = 2*cs GEMM columns).  No im2col matrix.
  *   dm_pad_image3         image -> pim.  src fp32 NCHW [b,3,64,64] (src_u8 = 0), or uint8 NHWC [b,64,64,3] (src_u8 = 1):
  *                         the reference's input transform ToTensor() + Normalize(.5,.5) = (u/255 - .5)/.5
  *                         (dataloader/dataset.py:37-43) fused in; dst_nchw (may be NULL) then also gets the normalised
  *                         fp32 NCHW image (what the losses read).
- *   dm_pack_conv3_weights fp32 W[cs][3][5][5] -> bf16 w_win[5][cs][64] (element kw*8+c of filter row kh)
+ *   dm_pack_conv3_weights fp32 W[cs][3][5][5] -> bf16 w_win: stride 2 [5][cs][32] (element kw*4+c of filter row kh),
+ *                         stride 1 [5][2*cs][32] (row pw*cs+n holds the filter shifted by pw pixels)
  *   dm_conv3_fwd          out[b,hs,ws,cs] = conv5x5(image, W) + bias, stride 1 / 2: nn.Conv2d(3, cs) forward
  *                         (model.py:449, 389) and the input-gradient of nn.ConvTranspose2d(cs, 3) (model.py:507);
  *                         optional fused BatchNorm statistics (dm_bn_fuse)
- *   dm_conv3_wgrad        dw_win[5][cs][64] (fp32) += sum_pixels small[b,h,w,cs] x window: weight gradient of those
+ *   dm_conv3_wgrad        dw_win[5][cs or 2*cs][64] (fp32) += sum_positions small x window: weight gradient of those
  *                         layers (small = grad_output of the Conv2d / input of deconv4); split-K, bulk tensor reductions
  *   dm_unpack_conv3_grad  dw[cs][3][5][5] += dw_win; dw_win is re-zeroed */
 long long dm_pim_elems(int batch);
 int dm_pad_image3(const void* src, int src_u8, int batch, void* pim_bf16, float* dst_nchw, void* stream);
-int dm_pack_conv3_weights(const float* w, int cs, void* w_win, void* stream);
+int dm_pack_conv3_weights(const float* w, int cs, int stride, void* w_win, void* stream);
 int dm_conv3_fwd(const dm_conv_geom* g, const void* pim, const void* w_win, const float* bias, void* out_small,
                  const dm_bn_fuse* bn, void* stream);
 int dm_conv3_wgrad(const dm_conv_geom* g, const void* pim, const void* small, float* dw_win, void* stream);
-int dm_unpack_conv3_grad(float* dw_win, int cs, float* dw, void* stream);
+int dm_unpack_conv3_grad(float* dw_win, int cs, int stride, float* dw, void* stream);
 /* bf16 [batch][rows][cols] -> [batch][cols][rows]: NHWC <-> the NCHW flatten order that the 16384-wide
  * Linear layers are defined on (model.py:516-517, 540-543, 412-413). */
 int dm_transpose_bf16(const void* src, int batch, int rows, int cols, void* dst, void* stream);
@@ -265,8 +267,8 @@ int dm_adam_step_ex(float* p, const void* g, int g_bf16, float* m, float* v, lon
  * backward, scratch -- are allocated by the caller (PyTorch's caching allocator) and borrowed for the call; the library
  * allocates nothing except cached tensor-map descriptors.  dims per op:
  *   DM_WS_GEMM {m,n,k,splits} = 0 (split-K reduces into D); DM_WS_CONV_FWD / _DGRAD {..} = 0 (no im2col buffer);
- *   DM_WS_CONV_WGRAD {cs,cb} packed-gradient scratch when dw is in the parameter layout; DM_WS_CONV3_WGRAD {cs};
- *   DM_WS_BATCHNORM {c,groups} slot scratch (= 4 * dm_bn_scratch_floats); DM_WS_PADDED_IMAGE {batch};
+ *   DM_WS_CONV_WGRAD {cs,cb} packed-gradient scratch when dw is in the parameter layout; DM_WS_CONV3_WGRAD {cs,stride};
+ *   DM_WS_BATCHNORM {c,groups} slot scratch (= 4 * dm_bn_scratch_floats); DM_WS_PADDED_IMAGE {batch} (= 2 * dm_pim_elems);
  *   DM_WS_COLSUM {rows,c} partial sums of dm_act_backward / dm_colsum.  Returns -1 for an unknown op. */
 enum { DM_WS_GEMM = 0, DM_WS_CONV_FWD = 1, DM_WS_CONV_DGRAD = 2, DM_WS_CONV_WGRAD = 3, DM_WS_CONV3_WGRAD = 4,
        DM_WS_BATCHNORM = 5, DM_WS_PADDED_IMAGE = 6, DM_WS_COLSUM = 7 };

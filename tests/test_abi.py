@@ -80,7 +80,7 @@ def test_workspace_query(lib):
 
     assert ws(0, 64, 2048, 16384, 18) == 0 and ws(1, 64, 8, 8, 256, 256) == 0  # GEMM, implicit-GEMM convolutions
     assert ws(3, 256, 128) == 25 * 256 * 128 * 4
-    assert ws(4, 32) == 5 * 32 * 64 * 4
+    assert ws(4, 32, 1) == 5 * 64 * 64 * 4 and ws(4, 64, 2) == 5 * 64 * 64 * 4
     assert ws(5, 256, 3) == 4 * lib.dm_bn_scratch_floats(256, 3)
     assert ws(6, 192) == 2 * lib.dm_pim_elems(192)
     assert ws(7, 64, 2048) == lib.dm_bn_parts(64, 2048) * 2048 * 4

@@ -169,7 +169,7 @@ def test_im2col3(ops, stride):
 
 
 def _unpad(pim):
-    """padded bf16 image [b,68,72,8] -> (interior as fp32 NCHW [b,3,64,64], everything else)"""
+    """padded bf16 image [b,68,72,4] -> (interior as fp32 NCHW [b,3,64,64], everything else)"""
     inner = pim[:, 2:66, 2:66, :3].float().permute(0, 3, 1, 2)
     rest = pim.clone()
     rest[:, 2:66, 2:66, :3] = 0
@@ -220,13 +220,13 @@ def test_conv3_window_gemms(ops, batch, cs, stride):
     hs = 64 // stride
     g = ops.geom(batch, hs, hs, cs, 3, stride)
     pim = ops.pad_image3(x)
-    _, _, ww = engine.pack3(w)
+    _, _, ww = engine.pack3(w, stride)
     y = ops.conv3_fwd(g, pim, ww, bias)
     ref = F.conv2d(x.bfloat16().float(), w.bfloat16().float(), bias, stride=stride, padding=2)
     assert rel(y.float().permute(0, 3, 1, 2), ref) < 4e-3
     dy = torch.randn(batch, hs, hs, cs, device="cuda").bfloat16()
     dw = torch.zeros_like(w)
-    sc = torch.zeros(5, cs, 64, device="cuda")
+    sc = torch.zeros(5, ops.conv3_cols(cs, stride), 64, device="cuda")
     ops.conv3_wgrad(g, pim, dy, dw, sc)
     ops.conv3_wgrad(g, pim, dy, dw, sc)  # accumulates; the scratch comes back zeroed
     wr = w.clone().requires_grad_(True)

@@ -168,7 +168,7 @@ def check_conv3_layer(ops, conv, inp, out, stride, transposed, tag):
     hs = 64 // stride
     w = conv.weight.detach().cuda()
     bias = conv.bias.detach().cuda()
-    _, wu, ww = engine.pack3(w)
+    _, wu, ww = engine.pack3(w, stride)
     g = ops.geom(b, hs, hs, cs, 3, stride)
     dw = torch.zeros_like(w)
     errs = {}
