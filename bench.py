@@ -248,11 +248,12 @@ def run_reference(args):
 
 def profile_traffic(args):
     """DRAM bytes (read + write) per launch of the GEMM-class kernel from the committed ncu capture of this workload
-    (profiles/r01_e_launches_vaegan_b64_final.txt: dram__bytes_read.sum + dram__bytes_write.sum over the 108 launches
-    of one step); None for configurations that were not captured."""
-    if args.workload == "betavaegan" and args.batch == 64:
-        return {"bytes_per_launch": 26.34e6, "launches": 108,
-                "source": "profiles/r01_e_launches_vaegan_b64_final.csv (ncu, one step, batch 64)"}
+    (profiles/r02_traffic.json, written by tools/summarize_ncu_metrics.py from the ncu launch list of one step:
+    dram__bytes_read.sum + dram__bytes_write.sum over the GEMM-class launches); None for configurations not captured."""
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get(f"{args.workload}_b{args.batch}")
     return None
 
 
@@ -430,7 +431,8 @@ def run_ours(args):
     gemm_ms = sum(float(r["us"]) for r in recs) / 1e3
     gemm_flops = sum(float(r["gflop"]) for r in recs) * 1e9
     gemm_n = len(recs)
-    conv = [r for r in recs if r["kind"] != "0"]
+    conv = [r for r in recs if r["kind"] in ("1", "2", "3")]  # the >= 32-channel 5x5 layers (tensor-bound)
+    conv3 = [r for r in recs if r["kind"] == "4"]  # the three 3-image-channel layers (TMA-row / HBM bound)
     conv_ms = sum(float(r["us"]) for r in conv) / 1e3
     conv_flops = sum(float(r["gflop"]) for r in conv) * 1e9
     ops.profile_enable(False)
@@ -483,8 +485,14 @@ def run_ours(args):
                                         "frac": round(conv_flops / (conv_ms / 1e3) / 1e12 / peak, 4) if conv_ms > 0 else None,
                                         "launches_per_step": len(conv) / args.steps,
                                         "ms_per_step": round(conv_ms / args.steps, 4),
-                                        "note": "the 5x5 conv / transposed-conv / weight-gradient launches only "
-                                                "(north-star: fraction of dense-bf16 peak on the conv GEMMs)"},
+                                        "note": "the 5x5 conv / transposed-conv / weight-gradient launches of the layers "
+                                                "with >= 32 channels on both sides (north-star: fraction of dense-bf16 "
+                                                "peak on the conv GEMMs); the 3-image-channel layers are listed apart"},
+                         "conv3_gemms": {"launches_per_step": len(conv3) / args.steps,
+                                         "ms_per_step": round(sum(float(r["us"]) for r in conv3) / 1e3 / args.steps, 4),
+                                         "gflop_per_step": round(sum(float(r["gflop"]) for r in conv3) / args.steps, 2),
+                                         "note": "convs.0 / features.0 / deconv4 gradients: window GEMMs over the padded "
+                                                 "3-channel image, 0.4 % of the step's FLOPs, bound by TMA rows and HBM"},
                          "step_frac_of_peak": round(ips / world * GFLOP_PER_IMG[args.workload] / 1e3 / peak, 4)},
             "cpu_baseline": cpu,
             "torch_gpu_baseline": torch_gpu,

@@ -89,7 +89,7 @@ _SIGS = {
     "dm_adam_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, C.c_double, C.c_double, C.c_double, C.c_double, c_int,
                      c_void_p, c_float, c_void_p, c_void_p],
     "dm_adam_step_gated": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_ll, C.c_double, C.c_double, C.c_double,
-                           C.c_double, c_void_p, c_float, c_void_p, c_void_p, c_void_p],
+                           C.c_double, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p],
     "dm_adam_step_ex": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_ll, C.c_double, C.c_double, C.c_double,
                         C.c_double, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p],
 }

@@ -171,6 +171,7 @@ __device__ __forceinline__ void sum_partials_block(const float* __restrict__ par
 // consumers are plain streaming kernels.  Tensors with at most kBn1dMaxRows rows (BatchNorm1d behind the Linear
 // layers: rows = batch) take a single-launch kernel with an exact two-pass variance.
 constexpr int kBn1dMaxRows = 256;
+constexpr int kBnUnroll = 8;  // rows in flight per thread of the streaming BatchNorm kernels (16-byte loads each)
 
 // Row reduction into slots: every block reduces its row range, then adds its NACC x (tx*8) totals to slot
 // (blockIdx.y % kBnSlots) of `slots` = [kBnSlots][NACC][c].
@@ -188,7 +189,7 @@ __device__ __forceinline__ void rows_reduce_slots(long long rows, int c, long lo
   const long long r0 = blockIdx.y * rows_per_block;
   const long long r1 = min(rows, r0 + rows_per_block);
   if (live) {
-#pragma unroll 4
+#pragma unroll kBnUnroll
     for (long long r = r0 + threadIdx.y; r < r1; r += ty) body(r, cv * 8, acc);
   }
   float* mine = red + (threadIdx.y * tx + threadIdx.x) * (8 * NACC);
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(256) bn_apply_act_kernel(const T* __restrict__
   load8(scale_shift + c + cv * 8, sh);
   const long long r0 = blockIdx.y * rows_per_block;
   const long long r1 = min(rows, r0 + rows_per_block);
-#pragma unroll 4
+#pragma unroll kBnUnroll
   for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
     float f[8];
     load8(y + r * c + cv * 8, f);
@@ -352,7 +353,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
   }
   const long long r0 = blockIdx.y * rows_per_block;
   const long long r1 = min(rows, r0 + rows_per_block);
-#pragma unroll 4
+#pragma unroll kBnUnroll
   for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
     float f[8], g[8];
     load8(y + r * c + cv * 8, f);
@@ -1081,12 +1082,12 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    float step_size, float beta1, float beta2, float omb1, float omb2,
                                                    float eps, float bc2_sqrt, float grad_scale, __nv_bfloat16* __restrict__ shadow,
                                                    const int* __restrict__ step_dev, double lr_d, double beta1_d,
-                                                   double beta2_d, const int* __restrict__ enable) {
+                                                   double beta2_d, const int* __restrict__ enable, int step_offset) {
   if (enable && *enable == 0) return;  // a deferred update whose gradient has not been produced yet (or was applied)
   if (step_dev) {  // CUDA-graph mode: bias corrections from the device-side step counter (same double arithmetic)
     __shared__ float sh[2];
     if (threadIdx.x == 0) {
-      const int st = *step_dev;
+      const int st = *step_dev + step_offset;
       sh[0] = static_cast<float>(lr_d / (1.0 - pow(beta1_d, static_cast<double>(st))));
       sh[1] = static_cast<float>(sqrt(1.0 - pow(beta2_d, static_cast<double>(st))));
     }
@@ -1424,7 +1425,7 @@ extern "C" int dm_bce_const(const float* p, int n, float n_total, float target, 
 
 static int adam_impl(float* p, const void* g, int g_bf16, float* m, float* v, long long n, double lr,
                      double beta1, double beta2, double eps, int step, int* step_dev, int count_step,
-                     float grad_scale, void* shadow_bf16, const int* enable_dev, void* stream_) {
+                     float grad_scale, void* shadow_bf16, const int* enable_dev, int step_offset, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   DM_REQUIRE(step >= 1 || step_dev != nullptr, "dm_adam_step: step must be >= 1 (or a device counter given)");
   // scalar arithmetic in double, then rounded to float once -- as torch.optim.Adam does with Python floats
@@ -1445,12 +1446,12 @@ static int adam_impl(float* p, const void* g, int g_bf16, float* m, float* v, lo
     adam_kernel<bf16><<<grid, 256, 0, s>>>(p, static_cast<const bf16*>(g), m, v, n, step_size, static_cast<float>(beta1),
                                            static_cast<float>(beta2), static_cast<float>(1.0 - beta1),
                                            static_cast<float>(1.0 - beta2), static_cast<float>(eps), bc2s, grad_scale,
-                                           static_cast<bf16*>(shadow_bf16), step_dev, lr, beta1, beta2, enable_dev);
+                                           static_cast<bf16*>(shadow_bf16), step_dev, lr, beta1, beta2, enable_dev, step_offset);
   else
     adam_kernel<float><<<grid, 256, 0, s>>>(p, static_cast<const float*>(g), m, v, n, step_size, static_cast<float>(beta1),
                                             static_cast<float>(beta2), static_cast<float>(1.0 - beta1),
                                             static_cast<float>(1.0 - beta2), static_cast<float>(eps), bc2s, grad_scale,
-                                            static_cast<bf16*>(shadow_bf16), step_dev, lr, beta1, beta2, enable_dev);
+                                            static_cast<bf16*>(shadow_bf16), step_dev, lr, beta1, beta2, enable_dev, step_offset);
   DM_LAUNCHED("dm_adam_step");
 }
 
@@ -1458,18 +1459,18 @@ extern "C" int dm_adam_step_ex(float* p, const void* g, int g_bf16, float* m, fl
                                double beta1, double beta2, double eps, int step, int* step_dev, int count_step,
                                float grad_scale, void* shadow_bf16, void* stream_) {
   return adam_impl(p, g, g_bf16, m, v, n, lr, beta1, beta2, eps, step, step_dev, count_step, grad_scale, shadow_bf16,
-                   nullptr, stream_);
+                   nullptr, 0, stream_);
 }
 
 // Same, gated by a device-side flag: the launch is a no-op when *enable_dev == 0.  Lets a CUDA graph contain the DEFERRED
 // update of a tensor (applied at the start of the next step, under work that does not read it): the flag says whether
 // the gradient buffer holds an unapplied gradient.
 extern "C" int dm_adam_step_gated(float* p, const void* g, int g_bf16, float* m, float* v, long long n, double lr,
-                                  double beta1, double beta2, double eps, int* step_dev, float grad_scale,
-                                  void* shadow_bf16, const int* enable_dev, void* stream_) {
-  DM_REQUIRE(step_dev != nullptr && enable_dev != nullptr, "dm_adam_step_gated: device step counter and flag required");
+                                  double beta1, double beta2, double eps, int* step_dev, int step_offset,
+                                  float grad_scale, void* shadow_bf16, const int* enable_dev, void* stream_) {
+  DM_REQUIRE(step_dev != nullptr, "dm_adam_step_gated: device step counter required");
   return adam_impl(p, g, g_bf16, m, v, n, lr, beta1, beta2, eps, 0, step_dev, 0, grad_scale, shadow_bf16, enable_dev,
-                   stream_);
+                   step_offset, stream_);
 }
 
 extern "C" int dm_adam_step(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1,

@@ -923,7 +923,8 @@ struct ProfRec {
   double flops;
   int gx, gy, gz, mode, bn, kc, stages, ctas, a_mn, b_mn, kind;
 };
-// what the next launch computes (profile records only): 0 dense GEMM, 1 conv_down, 2 conv_up, 3 conv_wgrad
+// what the next launch computes (profile records only): 0 dense GEMM, 1 conv_down, 2 conv_up, 3 conv_wgrad,
+// 4 = the 3-image-channel layers (window GEMMs over the padded image: bound by TMA rows / HBM, not by the tensor pipe)
 static thread_local int t_kind = 0;
 static std::mutex g_prof_mu;
 static bool g_prof_on = false;
@@ -1792,7 +1793,7 @@ extern "C" int dm_conv3_fwd(const dm_conv_geom* g, const void* pim, const void* 
                             const dm_bn_fuse* bn, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = check_geom(g, "dm_conv3_fwd")) return rc;
-  t_kind = 1;
+  t_kind = 4;
   DM_REQUIRE(g->cb == 3 && g->hb == 64 && g->wb == 64, "dm_conv3_fwd: needs a 3-channel 64x64 image side");
   DM_REQUIRE(g->cs == 32 || g->cs == 64, "dm_conv3_fwd: cs %d must be 32 or 64", g->cs);
   const int nn = g->stride == 1 ? 2 * g->cs : g->cs;  // GEMM columns: (pixel of the pair, channel) or channel
@@ -1834,7 +1835,7 @@ extern "C" int dm_conv3_fwd(const dm_conv_geom* g, const void* pim, const void* 
 extern "C" int dm_conv3_wgrad(const dm_conv_geom* g, const void* pim, const void* small, float* dw_win, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = check_geom(g, "dm_conv3_wgrad")) return rc;
-  t_kind = 3;
+  t_kind = 4;
   DM_REQUIRE(g->cb == 3 && g->hb == 64 && g->wb == 64, "dm_conv3_wgrad: needs a 3-channel 64x64 image side");
   DM_REQUIRE((g->cs == 32 && g->stride == 1) || (g->cs == 64 && g->stride == 2),
              "dm_conv3_wgrad: supports cs 32 / stride 1 and cs 64 / stride 2 (64 GEMM columns)");

@@ -413,8 +413,10 @@ def encoder_forward(x, P, B, cache: OperandCache, training=True, pim=None, befor
 
 
 def encoder_backward(S, dmu, dlogvar, P, G, cache: OperandCache, need_wgrad=True, overwrite_big=False,
-                     grad_ready=None):
-    """dmu / dlogvar: fp32 [b,128] gradients w.r.t. the encoder outputs."""
+                     grad_ready=None, heads_done=None):
+    """dmu / dlogvar: fp32 [b,128] gradients w.r.t. the encoder outputs.
+    heads_done: called once both heads are back-propagated -- the two 16384x2048 weight gradients are final and the
+    weights themselves are not read again in this pass (their optimizer update may start)."""
     b = S.b
     dev = S.flat.device
     wg = G if need_wgrad else None
@@ -437,6 +439,8 @@ def encoder_backward(S, dmu, dlogvar, P, G, cache: OperandCache, need_wgrad=True
             if grad_ready:
                 grad_ready(head + ".0.weight")
         linear_dgrad(dacc, w0, b, 2048, 16384, out_dtype=F32, out=dflat)
+    if heads_done:
+        heads_done()
     da3 = ops.transpose(ops.cast_bf16(dflat), b, 256, 64)
     dr3 = bn_act_backward(da3, S.bn3, wg, "features.7", cache)
     g3 = ops.geom(b, 8, 8, 256, 128, 2)

@@ -481,15 +481,17 @@ def bce_const(p, target, loss, w=1.0, n_total=None, dprob=None, accumulate=False
 
 
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0, shadow=None, step_dev=None, count_step=True,
-              enable=None):
+              enable=None, step_offset=None):
     """step_dev: int32 CUDA tensor holding the step count; incremented on the device (unless count_step is False: a
     later segment of the same optimizer step) and used instead of `step`.  g: fp32 or bf16.
-    enable: int32 CUDA scalar gating a DEFERRED update (no-op when 0); implies count_step=False."""
+    enable: int32 CUDA scalar gating a DEFERRED update (no-op when 0); step_offset: an EARLY update that runs before
+    the step counter of its optimizer step has been incremented (uses step_dev + step_offset).  Either implies
+    count_step=False."""
     assert g.dtype in (F32, BF16) and g.numel() == p.numel()
-    if enable is not None:
+    if enable is not None or step_offset is not None:
         _lib.check(_lib.load().dm_adam_step_gated(_p(p), _p(g), int(g.dtype == BF16), _p(m), _p(v), p.numel(), lr, beta1,
-                                                  beta2, eps, _p(step_dev), grad_scale, _p(shadow), _p(enable), _stream()),
-                   "dm_adam_step_gated")
+                                                  beta2, eps, _p(step_dev), int(step_offset or 0), grad_scale, _p(shadow),
+                                                  _p(enable), _stream()), "dm_adam_step_gated")
         return
     _lib.check(_lib.load().dm_adam_step_ex(_p(p), _p(g), int(g.dtype == BF16), _p(m), _p(v), p.numel(), lr, beta1, beta2,
                                            eps, step, _p(step_dev), int(count_step), grad_scale, _p(shadow), _stream()),

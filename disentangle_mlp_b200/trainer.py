@@ -268,7 +268,12 @@ class FlatParams:
         use; "defer" = leave the gradient in place, flagged valid, and apply it in finish_big() -- at the start of the
         next step on a side stream, under work that does not read those weights (flush() applies it immediately)."""
         self.step_count += 1
-        split = big != "now" and not self.shard and bool(self.big16)
+        early = getattr(self, "_big_early", False)  # adam_big_early() has already updated them in this step
+        self._big_early = False
+        if early:  # join the side stream (the update had the rest of the backward pass to finish)
+            self.wait_big()
+            self._big_event = None
+        split = (big != "now" or early) and not self.shard and bool(self.big16)
         for i, (lo, hi, o16) in enumerate(self._segments):
             if o16 is not None and split:
                 continue
@@ -286,11 +291,28 @@ class FlatParams:
             self._gather_pending = True
             if gather:
                 self.gather_if_pending()
-        if split:
+        if split and not early:
             self.big_valid.fill_(1)
             self._big_pending = True
             if big == "side":
                 self.finish_big(side)
+
+    def adam_big_early(self, side):
+        """The update of the big bf16-gradient tensors, launched as soon as their gradients are final (the encoder's
+        heads have been back-propagated) on stream `side`, under the rest of the backward pass; the adam() call that
+        ends the phase then covers everything else.  Uses step counter + 1: adam() has not incremented it yet."""
+        if not self.big16 or self.shard:
+            return
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for lo, hi, o16 in self._segments:
+                if o16 is not None:
+                    ops.adam_step(self.flat[lo:hi], self.grad16[o16:o16 + (hi - lo)], self.m[lo:hi], self.v[lo:hi], self.lr,
+                                  self.betas[0], self.betas[1], self.eps, 0, 1.0, self.shadow[lo:hi],
+                                  step_dev=self.step_dev, step_offset=1)
+            self._big_event = torch.cuda.Event()
+            self._big_event.record(side)
+        self._big_early = True
 
     def finish_big(self, side=None):
         """Apply the pending update of the big tensors (gated by the device flag, so the launches are safe to capture
@@ -531,7 +553,17 @@ class _Base:
     def flat_params(self):
         raise NotImplementedError
 
-    DEFER = os.environ.get("DM_DEFER_BIG", "1") != "0"  # A/B: big-tensor Adam off the critical path
+    # where the Adam update of the encoder's two 33.5 M-element Linear weights runs (single GPU / unsharded):
+    #   "early" (default) on a side stream as soon as their gradients are final, under the encoder's conv backward;
+    #   "defer" the phase-final one at the start of the next step under the discriminator phase (needs sync() before
+    #   the parameters are read); "now" inline.  Measured in profiles/ (r02 A/B).
+    BIG_ADAM = os.environ.get("DM_BIG_ADAM", "early")
+    DEFER = BIG_ADAM == "defer"
+
+    def _heads_done(self, fp):
+        if self.BIG_ADAM != "early" or fp.shard:
+            return None
+        return lambda: fp.adam_big_early(self._side())
 
     def _deferred(self):
         """FlatParams whose step-final Adam leaves the big tensors to the start of the next step"""
@@ -753,7 +785,7 @@ class VAETrainer(_Base):
         fp.reduce_from(self.dist, "preprocess.0.weight")
         _, _, dmu, dlv = ops.reparam_backward(dz, logvar, eps, dmu_kl, dlv_kl)
         engine.encoder_backward(Se, dmu, dlv, fp.P, fp.G, fp.cache, True, overwrite_big=True,
-                                grad_ready=self._early(fp))
+                                grad_ready=self._early(fp), heads_done=self._heads_done(fp))
         fp.reduce_rest_and_wait(self.dist)
         fp.adam(gather=False, big="defer" if self.DEFER else "now")
         self.metrics = {"loss": loss}
@@ -913,7 +945,7 @@ class BetaVAEGANTrainer(_Base):
         feg.reduce_from(self.dist, "preprocess.0.weight")  # decoder gradients are final: reduce them under the encoder backward
         _, _, dmu, dlv = ops.reparam_backward(dz, logvar, eps_dec)
         engine.encoder_backward(Se, dmu, dlv, feg.P, feg.G, feg.cache, True, overwrite_big=True,
-                                grad_ready=self._early(feg))
+                                grad_ready=self._early(feg), heads_done=self._heads_done(feg))
         del Sg2, Se
         feg.reduce_rest_and_wait(self.dist)
         # (big Linear weights on the side stream: the encoder convolutions of the next phase do not read them)
@@ -935,7 +967,7 @@ class BetaVAEGANTrainer(_Base):
         feg.reduce_from(self.dist, "preprocess.0.weight")
         _, _, dmu, dlv = ops.reparam_backward(dz, logvar, eps_enc, dmu_kl, dlv_kl)
         engine.encoder_backward(Se, dmu, dlv, feg.P, feg.G, feg.cache, True, overwrite_big=True,
-                                grad_ready=self._early(feg))
+                                grad_ready=self._early(feg), heads_done=self._heads_done(feg))
         feg.reduce_rest_and_wait(self.dist)
         # (sharded: its all-gather rides under the next step's discriminator phase; single GPU: so does the update of the
         # two big Linear weights itself)

@@ -274,12 +274,16 @@ enum { DM_WS_GEMM = 0, DM_WS_CONV_FWD = 1, DM_WS_CONV_DGRAD = 2, DM_WS_CONV_WGRA
        DM_WS_BATCHNORM = 5, DM_WS_PADDED_IMAGE = 6, DM_WS_COLSUM = 7 };
 long long dm_workspace_bytes(int op, const long long* dims, int ndims);
 
-/* Same, as a DEFERRED update inside a CUDA graph: no-op when *enable_dev == 0 (device int: "the gradient buffer holds an
- * unapplied gradient"); uses the device step counter without incrementing it.  The fused trainers apply the update of
- * the two 33.5 M-element encoder Linear weights at the START of the next step on a side stream, under the discriminator
- * phase, which does not read them. */
+/* Same on a segment whose update runs OUT OF ORDER with the rest of its optimizer step, off the critical path:
+ *   EARLY    (step_offset = 1, enable_dev NULL): the two 33.5 M-element encoder Linear weight gradients are final as soon
+ *            as the heads have been back-propagated; their Adam update (2/3 of the step's Adam traffic) runs on a side
+ *            stream under the encoder's convolution backward, before the rest of the step has incremented the device
+ *            step counter -- hence the offset;
+ *   DEFERRED (step_offset = 0, enable_dev = device int "the gradient buffer holds an unapplied gradient"): applied at
+ *            the start of the next step; a no-op when *enable_dev == 0.
+ * Never increments the step counter. */
 int dm_adam_step_gated(float* p, const void* g, int g_bf16, float* m, float* v, long long n, double lr, double beta1,
-                       double beta2, double eps, int* step_dev, float grad_scale, void* shadow_bf16,
+                       double beta2, double eps, int* step_dev, int step_offset, float grad_scale, void* shadow_bf16,
                        const int* enable_dev, void* stream);
 
 /* Per-launch CUDA-event timing of the GEMM-class kernel (bench.py roofline). dm_profile_read synchronises the
