@@ -417,6 +417,7 @@ def run_ours(args):
     # roofline pass: same workload launched eagerly (events cannot be read back from a replayed graph), per-launch
     # CUDA events around every GEMM-class kernel on the launching stream
     saved_graph, T._graph = T._graph, None
+    T.BIG_ADAM = "now"  # (no side-stream Adam under the GEMMs while they are being timed one by one)
     ops.profile_enable(True)
     ops.profile_read()
     t_prof = timed(step_resident, args.steps)
@@ -435,6 +436,23 @@ def run_ours(args):
     conv3 = [r for r in recs if r["kind"] == "4"]  # the three 3-image-channel layers (TMA-row / HBM bound)
     conv_ms = sum(float(r["us"]) for r in conv) / 1e3
     conv_flops = sum(float(r["gflop"]) for r in conv) * 1e9
+    # the same pass with the BatchNorm statistics in their own kernels instead of the GEMM epilogues: isolates the
+    # tensor-core part of the GEMM-class kernel (the timed runs above use the fused form: it is the faster STEP)
+    from disentangle_mlp_b200 import engine as _engine
+
+    nofuse = None
+    if _engine.FUSE_BN_STATS:
+        _engine.FUSE_BN_STATS = False
+        timed(step_resident, 2)
+        ops.profile_read()
+        timed(step_resident, args.steps)
+        with tempfile.NamedTemporaryFile("r", suffix=".csv") as tf:
+            _lib.check(_lib.load().dm_profile_dump(tf.name.encode()), "dm_profile_dump")
+            recs2 = list(csv.DictReader(open(tf.name)))
+        _engine.FUSE_BN_STATS = True
+        conv2 = [r for r in recs2 if r["kind"] in ("1", "2", "3")]
+        nofuse = {"gemm_ms": sum(float(r["us"]) for r in recs2) / 1e3, "gemm_flops": sum(float(r["gflop"]) for r in recs2) * 1e9,
+                  "conv_ms": sum(float(r["us"]) for r in conv2) / 1e3, "conv_flops": sum(float(r["gflop"]) for r in conv2) * 1e9}
     ops.profile_enable(False)
     T._graph = saved_graph
 
@@ -493,6 +511,17 @@ def run_ours(args):
                                          "gflop_per_step": round(sum(float(r["gflop"]) for r in conv3) / args.steps, 2),
                                          "note": "convs.0 / features.0 / deconv4 gradients: window GEMMs over the padded "
                                                  "3-channel image, 0.4 % of the step's FLOPs, bound by TMA rows and HBM"},
+                         "bn_stats_in_epilogue": bool(nofuse is not None),
+                         "without_fused_bn_stats": None if nofuse is None else {
+                             "note": "same eager pass with the BatchNorm statistics + finalize in separate kernels "
+                                     "(DM_BN_FUSE_GEMM=0): the GEMM-class kernel's tensor-core part alone; the fused form "
+                                     "above carries that HBM-bound work inside the GEMM launches and is the faster step",
+                             "achieved": round(nofuse["gemm_flops"] / (nofuse["gemm_ms"] / 1e3) / 1e12, 2),
+                             "frac": round(nofuse["gemm_flops"] / (nofuse["gemm_ms"] / 1e3) / 1e12 / peak, 4),
+                             "gemm_ms_per_step": round(nofuse["gemm_ms"] / args.steps, 4),
+                             "conv_gemms": {"achieved": round(nofuse["conv_flops"] / (nofuse["conv_ms"] / 1e3) / 1e12, 2),
+                                            "frac": round(nofuse["conv_flops"] / (nofuse["conv_ms"] / 1e3) / 1e12 / peak, 4),
+                                            "ms_per_step": round(nofuse["conv_ms"] / args.steps, 4)}},
                          "step_frac_of_peak": round(ips / world * GFLOP_PER_IMG[args.workload] / 1e3 / peak, 4)},
             "cpu_baseline": cpu,
             "torch_gpu_baseline": torch_gpu,

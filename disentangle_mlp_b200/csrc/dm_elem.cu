@@ -961,16 +961,18 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__
   if ((threadIdx.x & 31) == 0) prob[row] = 1.f / (1.f + expf(-(s + b[0])));
 }
 // dlogit = dprob * p * (1-p); dfeat[r][:] = dfeat_ext[r][:] + dlogit[r] * w;  dw += sum_r dlogit[r] feat[r][:]; db += sum dlogit
+// grid (k / 256 column blocks, row chunks of kHeadRows): the weight / bias gradients are combined with fp32 atomics
+constexpr int kHeadRows = 16;
 __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ dprob, const float* __restrict__ prob,
                                                        const float* __restrict__ feat, const float* __restrict__ dfeat_ext,
                                                        int rows, int k, const float* __restrict__ w,
                                                        float* __restrict__ dfeat, float* __restrict__ dw,
                                                        float* __restrict__ db) {
-  // one block per 256 columns; loops over rows
   const int col = blockIdx.x * 256 + threadIdx.x;
+  const int r0 = blockIdx.y * kHeadRows, r1 = min(rows, r0 + kHeadRows);
   float accw = 0.f, accb = 0.f;
   const float wv = col < k ? w[col] : 0.f;
-  for (int r = 0; r < rows; ++r) {
+  for (int r = r0; r < r1; ++r) {
     const float p = prob[r];
     const float dl = dprob[r] * p * (1.f - p);
     accb += dl;
@@ -980,8 +982,8 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
       accw += dl * feat[o];
     }
   }
-  if (col < k && dw) dw[col] += accw;
-  if (col == 0 && db) db[0] += accb;
+  if (col < k && dw) atomicAdd(dw + col, accw);
+  if (col == 0 && db) atomicAdd(db, accb);
 }
 
 // ------------------------------------------------------------------------------------------ loss reductions
@@ -1398,7 +1400,7 @@ extern "C" int dm_head_forward(const float* feat, int rows, int k, const float* 
 extern "C" int dm_head_backward(const float* dprob, const float* prob, const float* feat, const float* dfeat_ext,
                                 int rows, int k, const float* w, float* dfeat, float* dw, float* db, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-  head_bwd_kernel<<<(k + 255) / 256, 256, 0, s>>>(dprob, prob, feat, dfeat_ext, rows, k, w, dfeat, dw, db);
+  head_bwd_kernel<<<dim3((k + 255) / 256, (rows + kHeadRows - 1) / kHeadRows), 256, 0, s>>>(dprob, prob, feat, dfeat_ext, rows, k, w, dfeat, dw, db);
   DM_LAUNCHED("dm_head_backward");
 }
 

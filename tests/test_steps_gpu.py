@@ -138,7 +138,7 @@ def test_cuda_graph_step_matches_eager(mods):
     (eg0, d0, m0, c0, cd0, dd0, n0), (eg1, d1, m1, c1, cd1, dd1, n1) = outs
     assert c0 == c1 == cd0 == cd1 == 6 and dd0 == dd1 == 3 and n0 == n1 == 15
     for k in ("errD_real", "errD_fake", "D_x"):  # (BatchNorm partial sums are fp32 atomics: summation order varies)
-        assert abs(m0[k] - m1[k]) <= 2e-4 * abs(m0[k]), (k, m0[k], m1[k])
+        assert abs(m0[k] - m1[k]) <= 2e-3 * abs(m0[k]), (k, m0[k], m1[k])
     for k in ("errG_fake", "errG_recon", "sim", "recon_dec"):
         assert abs(m0[k] - m1[k]) <= 1e-2 * abs(m0[k]), (k, m0[k], m1[k])
     for k in ("kld", "recon_enc"):
