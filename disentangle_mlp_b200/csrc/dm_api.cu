@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/dm_b200.h"
 #include "dm_common.h"
@@ -21,6 +22,12 @@ int set_error(int code, const char* fmt, ...) {
   vsnprintf(last_error_buf(), 512, fmt, ap);
   va_end(ap);
   return code == 0 ? -1 : code;
+}
+
+// read at every launch (a CUDA graph keeps whatever was in force when it was captured)
+bool pdl_enabled() {
+  const char* v = getenv("DM_PDL");
+  return !(v && v[0] == '0');
 }
 
 }  // namespace dm

@@ -225,6 +225,7 @@ __device__ __forceinline__ bool take_ticket(unsigned int* counter) {
 template <typename T>
 __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ y, int c, long long rows_per_block,
                                                        const dm_bn_fuse f) {
+  pdl_sync();
   // blockIdx.z = group: `gridDim.z` independent batches stacked along rows, each with its own slots
   const long long rows = f.rows;
   y += static_cast<long long>(blockIdx.z) * rows * c;
@@ -256,6 +257,7 @@ __global__ void __launch_bounds__(256) bn_apply_act_kernel(const T* __restrict__
                                                            long long rows_per_block,
                                                            const float* __restrict__ scale_shift, int act,
                                                            float slope, __nv_bfloat16* __restrict__ out) {
+  pdl_sync();
   const int cv = blockIdx.x * blockDim.x + threadIdx.x;
   if (cv * 8 >= c) return;
   y += static_cast<long long>(blockIdx.z) * rows * c;
@@ -285,6 +287,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
                                                             const float* __restrict__ scale_shift,
                                                             const float* __restrict__ mean_invstd, int act,
                                                             float slope, float* scratch, float* dgamma, float* dbeta) {
+  pdl_sync();
   const int groups = gridDim.z;
   float* slots = scratch + static_cast<long long>(blockIdx.z) * kBnSlots * 2 * c;
   {
@@ -327,6 +330,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
                                                            const float* __restrict__ mean_invstd,
                                                            const float* __restrict__ sums, int act, float slope,
                                                            __nv_bfloat16* __restrict__ dy) {
+  pdl_sync();
   const int cv = blockIdx.x * blockDim.x + threadIdx.x;
   if (cv * 8 >= c) return;
   {
@@ -397,6 +401,7 @@ __global__ void __launch_bounds__(256) bn1d_fwd_kernel(const T* __restrict__ y, 
                                                        float eps, int act, float slope, float* __restrict__ scale_shift,
                                                        float* __restrict__ mean_invstd, __nv_bfloat16* __restrict__ out,
                                                        int groups) {
+  pdl_sync();
   __shared__ float red[64][33];
   __shared__ float stat[32];
   const int ch = (blockIdx.x * 4 + threadIdx.x) * 8;  // c is a multiple of 32: every thread is live
@@ -472,6 +477,7 @@ __global__ void __launch_bounds__(256) bn1d_bwd_kernel(const __nv_bfloat16* __re
                                                        const float* __restrict__ mean_invstd, int act, float slope,
                                                        __nv_bfloat16* __restrict__ dy, float* dgamma, float* dbeta,
                                                        int groups) {
+  pdl_sync();
   __shared__ float red[64][33];
   __shared__ float stat[32];
   const int ch = (blockIdx.x * 4 + threadIdx.x) * 8;
@@ -534,6 +540,7 @@ __global__ void __launch_bounds__(256) bn1d_bwd_kernel(const __nv_bfloat16* __re
 // out[i] (+)= sum_p partials[p][i]
 __global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __restrict__ partials, int nparts, int n,
                                                                 int accumulate, float* __restrict__ out) {
+  pdl_sync();
   const int i = blockIdx.x * 32 + threadIdx.x;
   float sum[1];
   sum_partials_block<1>(partials, nparts, n, i, i < n, 0, sum);
@@ -547,6 +554,7 @@ __global__ void __launch_bounds__(256) bias_act_kernel(const float* __restrict__
                                                        long long rows_per_block, const float* __restrict__ bias,
                                                        int act, float slope, float* __restrict__ out_f32,
                                                        __nv_bfloat16* __restrict__ out_bf16) {
+  pdl_sync();
   const int cv = blockIdx.x * blockDim.x + threadIdx.x;
   if (cv * 8 >= c) return;
   float b[8];
@@ -572,6 +580,7 @@ __global__ void __launch_bounds__(256) act_bwd_colsum_kernel(const float* __rest
                                                              long long rows_per_block, int act, float slope,
                                                              __nv_bfloat16* __restrict__ dpre,
                                                              float* __restrict__ colsum) {
+  pdl_sync();
   rows_reduce<float, 1>(rows, c, rows_per_block, colsum, [&](long long r, int ch, float(&acc)[1][8]) {
     float g[8], o[8];
     load8(dout + r * c + ch, g);
@@ -588,6 +597,7 @@ __global__ void __launch_bounds__(256) act_bwd_colsum_kernel(const float* __rest
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long rows, int c,
                                                      long long rows_per_block, float* __restrict__ colsum) {
+  pdl_sync();
   rows_reduce<T, 1>(rows, c, rows_per_block, colsum, [&](long long r, int ch, float(&acc)[1][8]) {
     float f[8];
     load8(x + r * c + ch, f);
@@ -603,6 +613,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, lo
 // (zero halo of 2 on each side), then the 160-byte rows of the matrix are written as coalesced 16-byte pieces.
 __global__ void __launch_bounds__(256) im2col3_kernel(const float* __restrict__ x, int batch, int h, int w,
                                                       int stride, __nv_bfloat16* __restrict__ col) {
+  pdl_sync();
   extern __shared__ float patch[];  // [3 ch][5 kh][w + 4]
   __shared__ int koff[80];          // column k -> offset of its tap in the patch (-1: zero column)
   const int oh = h / stride, ow = w / stride;
@@ -676,6 +687,7 @@ __device__ __forceinline__ void pim_zero_border(__nv_bfloat16* pim, long long n,
 // then dst_nchw (may be NULL) also receives the normalised fp32 NCHW image the losses read.  One block per image row.
 __global__ void __launch_bounds__(256) pad_image3_kernel(const void* __restrict__ src, int src_u8, int batch,
                                                          __nv_bfloat16* __restrict__ pim, float* __restrict__ dst_nchw) {
+  pdl_sync();
   for (long long row = blockIdx.x; row < static_cast<long long>(batch) * 64; row += gridDim.x) {
     const long long n = row >> 6;
     const int h = static_cast<int>(row & 63);
@@ -706,6 +718,7 @@ __global__ void __launch_bounds__(256) pad_image3_kernel(const void* __restrict_
 __global__ void __launch_bounds__(256) nhwc3_to_nchw_kernel(const float* __restrict__ src, long long batch, int hw,
                                                             int apply_tanh, float* __restrict__ dst,
                                                             __nv_bfloat16* __restrict__ pim) {
+  pdl_sync();
   const long long total = batch * hw;
   for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < total;
        p += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -731,6 +744,7 @@ __global__ void __launch_bounds__(256) nhwc3_to_nchw_kernel(const float* __restr
 __global__ void __launch_bounds__(256) tanh_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out,
                                                        long long batch, int hw, float* __restrict__ dy,
                                                        float* __restrict__ bias_grad, __nv_bfloat16* __restrict__ pim) {
+  pdl_sync();
   __shared__ float red[3][8];
   float acc[3] = {0.f, 0.f, 0.f};
   const long long total = batch * hw;
@@ -772,6 +786,7 @@ __global__ void __launch_bounds__(256) tanh_bwd_kernel(const float* __restrict__
 // stride 1 (one window per output-pixel PAIR, starting at the even pixel): w_win[kh][pw*cs + n][32], kw = j - pw.
 __global__ void __launch_bounds__(256) pack_win_kernel(const float* __restrict__ w, int cs, int stride,
                                                        __nv_bfloat16* __restrict__ w_win) {
+  pdl_sync();
   const int nn = stride == 1 ? 2 * cs : cs;
   const int total = 5 * nn * 32;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -788,6 +803,7 @@ __global__ void __launch_bounds__(256) pack_win_kernel(const float* __restrict__
 // a 16-pixel window) -> dw[cs][3][5][5] += ; the scratch is re-zeroed
 __global__ void __launch_bounds__(256) unpack_win_grad_kernel(float* __restrict__ scratch, int cs, int stride,
                                                               float* __restrict__ dw) {
+  pdl_sync();
   const int nn = stride == 1 ? 2 * cs : cs;
   const int total = 5 * nn * 64;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -803,6 +819,7 @@ __global__ void __launch_bounds__(256) unpack_win_grad_kernel(float* __restrict_
 // bf16 [b][r][c] -> [b][c][r] through a 32x32 (+1 pad) shared-memory tile
 __global__ void __launch_bounds__(256) transpose_kernel(const __nv_bfloat16* __restrict__ src, int rows, int cols,
                                                         __nv_bfloat16* __restrict__ dst) {
+  pdl_sync();
   __shared__ __nv_bfloat16 tile[32][33];
   const long long base = static_cast<long long>(blockIdx.z) * rows * cols;
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -822,6 +839,7 @@ __global__ void __launch_bounds__(256) pack_conv_kernel(const float* __restrict_
                                                         __nv_bfloat16* __restrict__ w_down,
                                                         __nv_bfloat16* __restrict__ w_up,
                                                         __nv_bfloat16* __restrict__ w_col) {
+  pdl_sync();
   const long long n_down = 25ll * cs * cb, n_up = 25ll * cb_pad * cs, n_col = w_col ? 128ll * cs : 0;
   const long long total = (w_down ? n_down : 0) + (w_up ? n_up : 0) + n_col;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -861,6 +879,7 @@ __global__ void __launch_bounds__(256) pack_conv_kernel(const float* __restrict_
 // (dh = 1 - dhi, dw = 1 - dwi) when that filter tap exists, else 0: 9 input taps x N = 4*cb instead of 25 taps x N = cb.
 __global__ void __launch_bounds__(256) pack_up_merged_kernel(const __nv_bfloat16* __restrict__ w_up, int cs, int cb,
                                                              __nv_bfloat16* __restrict__ w_upm) {
+  pdl_sync();
   const long long total = 9ll * 4 * cb * cs;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -882,6 +901,7 @@ __global__ void __launch_bounds__(256) pack_up_merged_kernel(const __nv_bfloat16
 // re-zeroed so that the next backward pass can accumulate into it again
 __global__ void __launch_bounds__(256) unpack_conv_grad_kernel(float* __restrict__ packed, long long n, int accumulate,
                                                                float* __restrict__ dw) {
+  pdl_sync();
   constexpr int W = 128;  // elements of n per block
   __shared__ float tile[25][W + 1];
   const long long i0 = static_cast<long long>(blockIdx.x) * W;
@@ -906,6 +926,7 @@ __global__ void __launch_bounds__(256) unpack_conv_grad_kernel(float* __restrict
 
 __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src, long long n,
                                                         __nv_bfloat16* __restrict__ dst) {
+  pdl_sync();
   const long long nv = n / 8;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nv;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -921,6 +942,7 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
 __global__ void reparam_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ logvar,
                                    const float* __restrict__ eps, long long n, float* __restrict__ z_f32,
                                    __nv_bfloat16* __restrict__ z_bf16) {
+  pdl_sync();
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   const float z = mu[i] + eps[i] * expf(0.5f * logvar[i]);
@@ -933,6 +955,7 @@ __global__ void reparam_bwd_kernel(const float* __restrict__ dz, const float* __
                                    const float* __restrict__ dlogvar_ext, long long n,
                                    __nv_bfloat16* __restrict__ dmu, __nv_bfloat16* __restrict__ dlogvar,
                                    float* __restrict__ dmu_f32, float* __restrict__ dlogvar_f32) {
+  pdl_sync();
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   const float g = dz ? dz[i] : 0.f;
@@ -949,6 +972,7 @@ __global__ void reparam_bwd_kernel(const float* __restrict__ dz, const float* __
 __global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__ feat, int rows, int k,
                                                        const float* __restrict__ w, const float* __restrict__ b,
                                                        float* __restrict__ prob) {
+  pdl_sync();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   float s = 0.f;
@@ -968,6 +992,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
                                                        int rows, int k, const float* __restrict__ w,
                                                        float* __restrict__ dfeat, float* __restrict__ dw,
                                                        float* __restrict__ db) {
+  pdl_sync();
   const int col = blockIdx.x * 256 + threadIdx.x;
   const int r0 = blockIdx.y * kHeadRows, r1 = min(rows, r0 + kHeadRows);
   float accw = 0.f, accb = 0.f;
@@ -1006,6 +1031,7 @@ __device__ __forceinline__ float block_sum(float v) {
 __global__ void __launch_bounds__(256) mse_sum_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                       long long n, float wloss, float* __restrict__ loss,
                                                       float wgrad, int grad_accumulate, float* __restrict__ grad) {
+  pdl_sync();
   float acc = 0.f;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -1023,6 +1049,7 @@ __global__ void __launch_bounds__(256) kl_kernel(const float* __restrict__ mu, c
                                                  long long n, float w, float* __restrict__ loss,
                                                  int grad_accumulate, float* __restrict__ dmu,
                                                  float* __restrict__ dlogvar) {
+  pdl_sync();
   float acc = 0.f;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -1042,6 +1069,7 @@ __global__ void __launch_bounds__(256) bce_const_kernel(const float* __restrict_
                                                         const float* __restrict__ target_dev, float w,
                                                         float* __restrict__ loss, int grad_accumulate,
                                                         float* __restrict__ dprob, float* __restrict__ stat) {
+  pdl_sync();
   if (target_dev) target = *target_dev;  // CUDA-graph mode: the per-step label lives in device memory
   float acc = 0.f, accp = 0.f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -1066,7 +1094,8 @@ __global__ void __launch_bounds__(256) bce_const_kernel(const float* __restrict_
 // ------------------------------------------------------------------------------------------ Adam
 // torch.optim.Adam (betas, eps, no weight decay, no amsgrad; experiments/new_betavaegan.py:49-50) on a flat buffer,
 // optionally refreshing the bf16 shadow copy the GEMMs read.  28 B/param (+2 B shadow).
-__global__ void adam_count_kernel(int* step) { *step += 1; }
+__global__ void adam_count_kernel(int* step) {
+  pdl_sync(); *step += 1; }
 
 __device__ __forceinline__ float4 load_grad4(const float* g, long long i) { return reinterpret_cast<const float4*>(g)[i]; }
 __device__ __forceinline__ float4 load_grad4(const __nv_bfloat16* g, long long i) {
@@ -1085,6 +1114,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    float eps, float bc2_sqrt, float grad_scale, __nv_bfloat16* __restrict__ shadow,
                                                    const int* __restrict__ step_dev, double lr_d, double beta1_d,
                                                    double beta2_d, const int* __restrict__ enable, int step_offset) {
+  pdl_sync();
   if (enable && *enable == 0) return;  // a deferred update whose gradient has not been produced yet (or was applied)
   if (step_dev) {  // CUDA-graph mode: bias corrections from the device-side step counter (same double arithmetic)
     __shared__ float sh[2];
@@ -1159,9 +1189,9 @@ extern "C" int dm_bn_stats(const void* y, int y_f32, int c, const dm_bn_fuse* f,
   RowLayout l = make_row_layout(f->rows, c);
   const size_t sm = sizeof(float) * 256 * 16;
   if (y_f32)
-    bn_stats_kernel<float><<<dim3(l.gx, l.gy, f->groups), dim3(l.tx, l.ty), sm, s>>>(static_cast<const float*>(y), c, l.rows_per_block, *f);
+    launch_pdl(bn_stats_kernel<float>, dim3(l.gx, l.gy, f->groups), dim3(l.tx, l.ty), sm, s, static_cast<const float*>(y), c, l.rows_per_block, *f);
   else
-    bn_stats_kernel<bf16><<<dim3(l.gx, l.gy, f->groups), dim3(l.tx, l.ty), sm, s>>>(static_cast<const bf16*>(y), c, l.rows_per_block, *f);
+    launch_pdl(bn_stats_kernel<bf16>, dim3(l.gx, l.gy, f->groups), dim3(l.tx, l.ty), sm, s, static_cast<const bf16*>(y), c, l.rows_per_block, *f);
   DM_LAUNCHED("dm_bn_stats");
 }
 
@@ -1172,9 +1202,9 @@ extern "C" int dm_bn_apply_act(const void* y, int y_f32, long long rows, int c, 
   DM_REQUIRE(groups >= 1, "dm_bn_apply_act: groups must be >= 1");
   RowLayout l = make_row_layout(rows, c);
   if (y_f32)
-    bn_apply_act_kernel<float><<<dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), 0, s>>>(static_cast<const float*>(y), rows, c, l.rows_per_block, scale_shift, act, slope, static_cast<bf16*>(out_bf16));
+    launch_pdl(bn_apply_act_kernel<float>, dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), 0, s, static_cast<const float*>(y), rows, c, l.rows_per_block, scale_shift, act, slope, static_cast<bf16*>(out_bf16));
   else
-    bn_apply_act_kernel<bf16><<<dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), 0, s>>>(static_cast<const bf16*>(y), rows, c, l.rows_per_block, scale_shift, act, slope, static_cast<bf16*>(out_bf16));
+    launch_pdl(bn_apply_act_kernel<bf16>, dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), 0, s, static_cast<const bf16*>(y), rows, c, l.rows_per_block, scale_shift, act, slope, static_cast<bf16*>(out_bf16));
   DM_LAUNCHED("dm_bn_apply_act");
 }
 
@@ -1195,11 +1225,11 @@ extern "C" int dm_bn_forward(const void* y, int y_f32, long long rows, int c, co
   DM_REQUIRE(groups >= 1, "dm_bn_forward: groups must be >= 1");
   if (bn1d_ok(rows, c)) {
     if (y_f32)
-      bn1d_fwd_kernel<float><<<c / 32, dim3(4, 64), 0, s>>>(static_cast<const float*>(y), static_cast<int>(rows), c, gamma, beta,
+      launch_pdl(bn1d_fwd_kernel<float>, c / 32, dim3(4, 64), 0, s, static_cast<const float*>(y), static_cast<int>(rows), c, gamma, beta,
                                                            running_mean, running_var, num_batches_tracked, momentum, eps, act,
                                                            slope, scale_shift, mean_invstd, static_cast<bf16*>(out_bf16), groups);
     else
-      bn1d_fwd_kernel<bf16><<<c / 32, dim3(4, 64), 0, s>>>(static_cast<const bf16*>(y), static_cast<int>(rows), c, gamma, beta,
+      launch_pdl(bn1d_fwd_kernel<bf16>, c / 32, dim3(4, 64), 0, s, static_cast<const bf16*>(y), static_cast<int>(rows), c, gamma, beta,
                                                           running_mean, running_var, num_batches_tracked, momentum, eps, act,
                                                           slope, scale_shift, mean_invstd, static_cast<bf16*>(out_bf16), groups);
     DM_LAUNCHED("dm_bn_forward(1d)");
@@ -1223,10 +1253,10 @@ extern "C" int dm_bn_backward(const void* dout_bf16, const void* y, int y_f32, l
   const bf16* d = static_cast<const bf16*>(dout_bf16);
   if (bn1d_ok(rows, c)) {
     if (y_f32)
-      bn1d_bwd_kernel<float><<<c / 32, dim3(4, 64), 0, s>>>(d, static_cast<const float*>(y), static_cast<int>(rows), c, scale_shift,
+      launch_pdl(bn1d_bwd_kernel<float>, c / 32, dim3(4, 64), 0, s, d, static_cast<const float*>(y), static_cast<int>(rows), c, scale_shift,
                                                            mean_invstd, act, slope, static_cast<bf16*>(dy_bf16), dgamma, dbeta, groups);
     else
-      bn1d_bwd_kernel<bf16><<<c / 32, dim3(4, 64), 0, s>>>(d, static_cast<const bf16*>(y), static_cast<int>(rows), c, scale_shift,
+      launch_pdl(bn1d_bwd_kernel<bf16>, c / 32, dim3(4, 64), 0, s, d, static_cast<const bf16*>(y), static_cast<int>(rows), c, scale_shift,
                                                           mean_invstd, act, slope, static_cast<bf16*>(dy_bf16), dgamma, dbeta, groups);
     DM_LAUNCHED("dm_bn_backward(1d)");
   }
@@ -1235,13 +1265,13 @@ extern "C" int dm_bn_backward(const void* dout_bf16, const void* y, int y_f32, l
   const size_t sm = sizeof(float) * 256 * 16;
   const float* sums = scratch + bn_slot_floats(c, groups) + 4;
   if (y_f32)
-    bn_bwd_reduce_kernel<float><<<dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), sm, s>>>(d, static_cast<const float*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, act, slope, scratch, dgamma, dbeta);
+    launch_pdl(bn_bwd_reduce_kernel<float>, dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), sm, s, d, static_cast<const float*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, act, slope, scratch, dgamma, dbeta);
   else
-    bn_bwd_reduce_kernel<bf16><<<dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), sm, s>>>(d, static_cast<const bf16*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, act, slope, scratch, dgamma, dbeta);
+    launch_pdl(bn_bwd_reduce_kernel<bf16>, dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), sm, s, d, static_cast<const bf16*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, act, slope, scratch, dgamma, dbeta);
   if (y_f32)
-    bn_bwd_apply_kernel<float><<<dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), 0, s>>>(d, static_cast<const float*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, sums, act, slope, static_cast<bf16*>(dy_bf16));
+    launch_pdl(bn_bwd_apply_kernel<float>, dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), 0, s, d, static_cast<const float*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, sums, act, slope, static_cast<bf16*>(dy_bf16));
   else
-    bn_bwd_apply_kernel<bf16><<<dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), 0, s>>>(d, static_cast<const bf16*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, sums, act, slope, static_cast<bf16*>(dy_bf16));
+    launch_pdl(bn_bwd_apply_kernel<bf16>, dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), 0, s, d, static_cast<const bf16*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, sums, act, slope, static_cast<bf16*>(dy_bf16));
   g_launch_count.fetch_add(2, std::memory_order_relaxed);
   return check_launch("dm_bn_backward");
 }
@@ -1251,7 +1281,7 @@ extern "C" int dm_bias_act(const float* acc, long long rows, int c, const float*
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   DM_CHECK_C8(c, "dm_bias_act");
   RowLayout l = make_row_layout(rows, c);
-  bias_act_kernel<<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), 0, s>>>(acc, rows, c, l.rows_per_block, bias, act, slope, out_f32, static_cast<bf16*>(out_bf16));
+  launch_pdl(bias_act_kernel, dim3(l.gx, l.gy), dim3(l.tx, l.ty), 0, s, acc, rows, c, l.rows_per_block, bias, act, slope, out_f32, static_cast<bf16*>(out_bf16));
   DM_LAUNCHED("dm_bias_act");
 }
 
@@ -1260,10 +1290,10 @@ extern "C" int dm_act_backward(const float* dout, const float* out, long long ro
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   DM_CHECK_C8(c, "dm_act_backward");
   RowLayout l = make_row_layout(rows, c);
-  act_bwd_colsum_kernel<<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), sizeof(float) * 256 * 8, s>>>(dout, out, rows, c, l.rows_per_block, act, slope, static_cast<bf16*>(dpre_bf16), partials);
+  launch_pdl(act_bwd_colsum_kernel, dim3(l.gx, l.gy), dim3(l.tx, l.ty), sizeof(float) * 256 * 8, s, dout, out, rows, c, l.rows_per_block, act, slope, static_cast<bf16*>(dpre_bf16), partials);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   if (colsum) {
-    reduce_partials_kernel<<<(c + 31) / 32, dim3(32, 32), 0, s>>>(partials, l.gy, c, 1, colsum);
+    launch_pdl(reduce_partials_kernel, (c + 31) / 32, dim3(32, 32), 0, s, partials, l.gy, c, 1, colsum);
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
   }
   return check_launch("dm_act_backward");
@@ -1275,10 +1305,10 @@ extern "C" int dm_colsum(const void* x, int x_f32, long long rows, int c, float*
   RowLayout l = make_row_layout(rows, c);
   const size_t sm = sizeof(float) * 256 * 8;
   if (x_f32)
-    colsum_kernel<float><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s>>>(static_cast<const float*>(x), rows, c, l.rows_per_block, partials);
+    launch_pdl(colsum_kernel<float>, dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s, static_cast<const float*>(x), rows, c, l.rows_per_block, partials);
   else
-    colsum_kernel<bf16><<<dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s>>>(static_cast<const bf16*>(x), rows, c, l.rows_per_block, partials);
-  reduce_partials_kernel<<<(c + 31) / 32, dim3(32, 32), 0, s>>>(partials, l.gy, c, 1, colsum);
+    launch_pdl(colsum_kernel<bf16>, dim3(l.gx, l.gy), dim3(l.tx, l.ty), sm, s, static_cast<const bf16*>(x), rows, c, l.rows_per_block, partials);
+  launch_pdl(reduce_partials_kernel, (c + 31) / 32, dim3(32, 32), 0, s, partials, l.gy, c, 1, colsum);
   g_launch_count.fetch_add(2, std::memory_order_relaxed);
   return check_launch("dm_colsum");
 }
@@ -1290,7 +1320,7 @@ extern "C" int dm_im2col3(const float* x_nchw, int batch, int h, int w, int stri
   (void)items;
   const long long out_rows = static_cast<long long>(batch) * (h / stride);
   const int blocks = static_cast<int>(std::min<long long>(out_rows, 148 * 16));
-  im2col3_kernel<<<blocks, 256, 15 * (w + 4) * sizeof(float), s>>>(x_nchw, batch, h, w, stride, static_cast<bf16*>(col_bf16));
+  launch_pdl(im2col3_kernel, blocks, 256, 15 * (w + 4) * sizeof(float), s, x_nchw, batch, h, w, stride, static_cast<bf16*>(col_bf16));
   DM_LAUNCHED("dm_im2col3");
 }
 
@@ -1298,7 +1328,7 @@ extern "C" int dm_nhwc3_to_nchw(const float* src, long long batch, int hw, int a
                                 void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   DM_REQUIRE(pim_bf16 == nullptr || hw == 64 * 64, "dm_nhwc3_to_nchw: the padded-image output needs 64x64 images");
-  nhwc3_to_nchw_kernel<<<grid_for(batch * hw), 256, 0, s>>>(src, batch, hw, apply_tanh, dst, static_cast<bf16*>(pim_bf16));
+  launch_pdl(nhwc3_to_nchw_kernel, grid_for(batch * hw), 256, 0, s, src, batch, hw, apply_tanh, dst, static_cast<bf16*>(pim_bf16));
   DM_LAUNCHED("dm_nhwc3_to_nchw");
 }
 
@@ -1306,7 +1336,7 @@ extern "C" int dm_tanh_backward(const float* dout, const float* out, long long b
                                 float* bias_grad, void* pim_bf16, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   DM_REQUIRE(pim_bf16 == nullptr || hw == 64 * 64, "dm_tanh_backward: the padded-image output needs 64x64 images");
-  tanh_bwd_kernel<<<grid_for(batch * hw, 256, 148 * 4), 256, 0, s>>>(dout, out, batch, hw, dy, bias_grad, static_cast<bf16*>(pim_bf16));
+  launch_pdl(tanh_bwd_kernel, grid_for(batch * hw, 256, 148 * 4), 256, 0, s, dout, out, batch, hw, dy, bias_grad, static_cast<bf16*>(pim_bf16));
   DM_LAUNCHED("dm_tanh_backward");
 }
 
@@ -1319,27 +1349,27 @@ extern "C" int dm_pad_image3(const void* src, int src_u8, int batch, void* pim_b
   DM_REQUIRE(batch > 0 && src != nullptr && pim_bf16 != nullptr, "dm_pad_image3: bad arguments");
   DM_REQUIRE((reinterpret_cast<uintptr_t>(pim_bf16) & 127) == 0, "dm_pad_image3: pim must be 128-byte aligned");
   const int blocks = static_cast<int>(std::min<long long>(static_cast<long long>(batch) * 64, 148 * 16));
-  pad_image3_kernel<<<blocks, 256, 0, s>>>(src, src_u8, batch, static_cast<bf16*>(pim_bf16), dst_nchw);
+  launch_pdl(pad_image3_kernel, blocks, 256, 0, s, src, src_u8, batch, static_cast<bf16*>(pim_bf16), dst_nchw);
   DM_LAUNCHED("dm_pad_image3");
 }
 
 extern "C" int dm_pack_conv3_weights(const float* w, int cs, int stride, void* w_win, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   DM_REQUIRE(stride == 1 || stride == 2, "dm_pack_conv3_weights: stride must be 1 or 2");
-  pack_win_kernel<<<grid_for(5ll * cs * 64), 256, 0, s>>>(w, cs, stride, static_cast<bf16*>(w_win));
+  launch_pdl(pack_win_kernel, grid_for(5ll * cs * 64), 256, 0, s, w, cs, stride, static_cast<bf16*>(w_win));
   DM_LAUNCHED("dm_pack_conv3_weights");
 }
 
 extern "C" int dm_unpack_conv3_grad(float* scratch, int cs, int stride, float* dw, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   DM_REQUIRE(stride == 1 || stride == 2, "dm_unpack_conv3_grad: stride must be 1 or 2");
-  unpack_win_grad_kernel<<<grid_for(5ll * cs * 128), 256, 0, s>>>(scratch, cs, stride, dw);
+  launch_pdl(unpack_win_grad_kernel, grid_for(5ll * cs * 128), 256, 0, s, scratch, cs, stride, dw);
   DM_LAUNCHED("dm_unpack_conv3_grad");
 }
 
 extern "C" int dm_transpose_bf16(const void* src, int batch, int rows, int cols, void* dst, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-  transpose_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32, batch), dim3(32, 8), 0, s>>>(static_cast<const bf16*>(src), rows, cols, static_cast<bf16*>(dst));
+  launch_pdl(transpose_kernel, dim3((cols + 31) / 32, (rows + 31) / 32, batch), dim3(32, 8), 0, s, static_cast<const bf16*>(src), rows, cols, static_cast<bf16*>(dst));
   DM_LAUNCHED("dm_transpose_bf16");
 }
 
@@ -1349,35 +1379,35 @@ extern "C" int dm_pack_conv_weights(const float* w, int cs, int cb, void* w_down
   DM_REQUIRE(w_col == nullptr || cb * 25 <= 128, "dm_pack_conv_weights: col form needs cb*25 <= 128");
   const int cb_pad = std::max(16, (cb + 15) / 16 * 16);
   const long long total = 25ll * cs * cb + 25ll * cb_pad * cs + 128ll * cs;
-  pack_conv_kernel<<<grid_for(total), 256, 0, s>>>(w, cs, cb, cb_pad, static_cast<bf16*>(w_down), static_cast<bf16*>(w_up), static_cast<bf16*>(w_col));
+  launch_pdl(pack_conv_kernel, grid_for(total), 256, 0, s, w, cs, cb, cb_pad, static_cast<bf16*>(w_down), static_cast<bf16*>(w_up), static_cast<bf16*>(w_col));
   DM_LAUNCHED("dm_pack_conv_weights");
 }
 
 extern "C" int dm_pack_up_merged(const void* w_up, int cs, int cb, void* w_upm, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   DM_REQUIRE(cb % 16 == 0, "dm_pack_up_merged: cb %d must be a multiple of 16", cb);
-  pack_up_merged_kernel<<<grid_for(36ll * cb * cs), 256, 0, s>>>(static_cast<const bf16*>(w_up), cs, cb, static_cast<bf16*>(w_upm));
+  launch_pdl(pack_up_merged_kernel, grid_for(36ll * cb * cs), 256, 0, s, static_cast<const bf16*>(w_up), cs, cb, static_cast<bf16*>(w_upm));
   DM_LAUNCHED("dm_pack_up_merged");
 }
 
 extern "C" int dm_unpack_conv_grad(float* packed, int cs, int cb, int accumulate, float* dw, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   const long long n = static_cast<long long>(cs) * cb;
-  unpack_conv_grad_kernel<<<static_cast<unsigned>((n + 127) / 128), 256, 0, s>>>(packed, n, accumulate, dw);
+  launch_pdl(unpack_conv_grad_kernel, static_cast<unsigned>((n + 127) / 128), 256, 0, s, packed, n, accumulate, dw);
   DM_LAUNCHED("dm_unpack_conv_grad");
 }
 
 extern "C" int dm_cast_bf16(const float* src, long long n, void* dst, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   DM_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0, "dm_cast_bf16: pointers must be 16-byte aligned");
-  cast_bf16_kernel<<<grid_for(n / 8 + 1), 256, 0, s>>>(src, n, static_cast<bf16*>(dst));
+  launch_pdl(cast_bf16_kernel, grid_for(n / 8 + 1), 256, 0, s, src, n, static_cast<bf16*>(dst));
   DM_LAUNCHED("dm_cast_bf16");
 }
 
 extern "C" int dm_reparam_forward(const float* mu, const float* logvar, const float* eps, long long n, float* z_f32,
                                   void* z_bf16, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-  reparam_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(mu, logvar, eps, n, z_f32, static_cast<bf16*>(z_bf16));
+  launch_pdl(reparam_fwd_kernel, (unsigned)((n + 255) / 256), 256, 0, s, mu, logvar, eps, n, z_f32, static_cast<bf16*>(z_bf16));
   DM_LAUNCHED("dm_reparam_forward");
 }
 
@@ -1385,7 +1415,7 @@ extern "C" int dm_reparam_backward(const float* dz, const float* logvar, const f
                                    const float* dlogvar_ext, long long n, void* dmu_bf16, void* dlogvar_bf16,
                                    float* dmu_f32, float* dlogvar_f32, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-  reparam_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dz, logvar, eps, dmu_ext, dlogvar_ext, n, static_cast<bf16*>(dmu_bf16), static_cast<bf16*>(dlogvar_bf16), dmu_f32, dlogvar_f32);
+  launch_pdl(reparam_bwd_kernel, (unsigned)((n + 255) / 256), 256, 0, s, dz, logvar, eps, dmu_ext, dlogvar_ext, n, static_cast<bf16*>(dmu_bf16), static_cast<bf16*>(dlogvar_bf16), dmu_f32, dlogvar_f32);
   DM_LAUNCHED("dm_reparam_backward");
 }
 
@@ -1393,35 +1423,35 @@ extern "C" int dm_head_forward(const float* feat, int rows, int k, const float* 
                                void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   DM_REQUIRE(k % 4 == 0, "dm_head_forward: k must be a multiple of 4");
-  head_fwd_kernel<<<(rows + 7) / 8, 256, 0, s>>>(feat, rows, k, w, b, prob);
+  launch_pdl(head_fwd_kernel, (rows + 7) / 8, 256, 0, s, feat, rows, k, w, b, prob);
   DM_LAUNCHED("dm_head_forward");
 }
 
 extern "C" int dm_head_backward(const float* dprob, const float* prob, const float* feat, const float* dfeat_ext,
                                 int rows, int k, const float* w, float* dfeat, float* dw, float* db, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-  head_bwd_kernel<<<dim3((k + 255) / 256, (rows + kHeadRows - 1) / kHeadRows), 256, 0, s>>>(dprob, prob, feat, dfeat_ext, rows, k, w, dfeat, dw, db);
+  launch_pdl(head_bwd_kernel, dim3((k + 255) / 256, (rows + kHeadRows - 1) / kHeadRows), 256, 0, s, dprob, prob, feat, dfeat_ext, rows, k, w, dfeat, dw, db);
   DM_LAUNCHED("dm_head_backward");
 }
 
 extern "C" int dm_mse_sum(const float* a, const float* b, long long n, float wloss, float* loss, float wgrad,
                           int grad_accumulate, float* grad, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-  mse_sum_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, s>>>(a, b, n, wloss, loss, wgrad, grad_accumulate, grad);
+  launch_pdl(mse_sum_kernel, grid_for(n, 256, 148 * 4), 256, 0, s, a, b, n, wloss, loss, wgrad, grad_accumulate, grad);
   DM_LAUNCHED("dm_mse_sum");
 }
 
 extern "C" int dm_kl(const float* mu, const float* logvar, long long n, float w, float* loss, int grad_accumulate,
                      float* dmu, float* dlogvar, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-  kl_kernel<<<grid_for(n, 256, 148), 256, 0, s>>>(mu, logvar, n, w, loss, grad_accumulate, dmu, dlogvar);
+  launch_pdl(kl_kernel, grid_for(n, 256, 148), 256, 0, s, mu, logvar, n, w, loss, grad_accumulate, dmu, dlogvar);
   DM_LAUNCHED("dm_kl");
 }
 
 extern "C" int dm_bce_const(const float* p, int n, float n_total, float target, const float* target_dev, float w,
                             float* loss, int grad_accumulate, float* dprob, float* stat, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-  bce_const_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(p, n, n_total, target, target_dev, w, loss, grad_accumulate, dprob, stat);
+  launch_pdl(bce_const_kernel, grid_for(n, 256, 8), 256, 0, s, p, n, n_total, target, target_dev, w, loss, grad_accumulate, dprob, stat);
   DM_LAUNCHED("dm_bce_const");
 }
 
@@ -1434,7 +1464,7 @@ static int adam_impl(float* p, const void* g, int g_bf16, float* m, float* v, lo
   float step_size = 0.f, bc2s = 1.f;
   if (step_dev) {
     if (count_step) {  // *step_dev += 1, then the update reads it; later segments of the same step reuse the value
-      adam_count_kernel<<<1, 1, 0, s>>>(step_dev);
+      launch_pdl(adam_count_kernel, 1, 1, 0, s, step_dev);
       g_launch_count.fetch_add(1, std::memory_order_relaxed);
     }
   } else {
@@ -1445,12 +1475,12 @@ static int adam_impl(float* p, const void* g, int g_bf16, float* m, float* v, lo
   }
   const int grid = grid_for(n / 4 + 1, 256, 148 * 8);
   if (g_bf16)
-    adam_kernel<bf16><<<grid, 256, 0, s>>>(p, static_cast<const bf16*>(g), m, v, n, step_size, static_cast<float>(beta1),
+    launch_pdl(adam_kernel<bf16>, grid, 256, 0, s, p, static_cast<const bf16*>(g), m, v, n, step_size, static_cast<float>(beta1),
                                            static_cast<float>(beta2), static_cast<float>(1.0 - beta1),
                                            static_cast<float>(1.0 - beta2), static_cast<float>(eps), bc2s, grad_scale,
                                            static_cast<bf16*>(shadow_bf16), step_dev, lr, beta1, beta2, enable_dev, step_offset);
   else
-    adam_kernel<float><<<grid, 256, 0, s>>>(p, static_cast<const float*>(g), m, v, n, step_size, static_cast<float>(beta1),
+    launch_pdl(adam_kernel<float>, grid, 256, 0, s, p, static_cast<const float*>(g), m, v, n, step_size, static_cast<float>(beta1),
                                             static_cast<float>(beta2), static_cast<float>(1.0 - beta1),
                                             static_cast<float>(1.0 - beta2), static_cast<float>(eps), bc2s, grad_scale,
                                             static_cast<bf16*>(shadow_bf16), step_dev, lr, beta1, beta2, enable_dev, step_offset);

@@ -110,7 +110,23 @@ struct alignas(64) GemmParams {
   int stat_tiles_per_group;  // M tiles per stacked pass
   int stat_groups;
   dm_bn_fuse stat_fin;
+#ifdef DM_STAMPS
+  unsigned long long* stamps;  // debug build only: [cta][16] %globaltimer stamps of the kernel's phases
+#endif
 };
+
+#ifdef DM_STAMPS
+#define DM_STAMP(i)                                                      \
+  do {                                                                   \
+    if (p.stamps) {                                                      \
+      unsigned long long t_;                                             \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));             \
+      p.stamps[blockIdx.x * 16 + (i)] = t_;                              \
+    }                                                                    \
+  } while (0)
+#else
+#define DM_STAMP(i)
+#endif
 
 constexpr int kThreads = 192;
 constexpr int kAtomBytes = 8192;  // one MN-major atom: 64 k-rows x 128 B
@@ -186,6 +202,7 @@ template <bool kCG2, bool kTF32 = false>
 __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
+  if (threadIdx.x == 0) DM_STAMP(0);
   if ((smem_u32(smem) & 1023u) != 0u) __trap();  // SWIZZLE_128B boxes need 1024-byte aligned stages
 
   const int warp = threadIdx.x >> 5;
@@ -242,6 +259,11 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
     __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (threadIdx.x == 0) DM_STAMP(1);
+  // everything above (barriers, TMEM, descriptor prefetch) ran while the previous kernel of the stream was still
+  // finishing; from here on its results are needed, and the next kernel may start its own prologue
+  pdl_sync();
+  if (threadIdx.x == 0) DM_STAMP(2);
 
   // Both single-thread roles below are ISSUE-bound if careless: one lane retires roughly one dependent instruction
   // every 4-6 cycles, and a 128x128x64 k-block is only 256 tensor-core cycles.  Everything that does not change per
@@ -267,6 +289,9 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
       // the barrier that receives the complete_tx of this CTA's loads: its own, or (cta_group::2) the leader's
       const uint32_t full_tx0 = kCG2 ? (full0 & kPeerBitMask) : full0;
       const int kc = p.kc;
+#ifdef DM_STAMPS
+      bool stamped_first = false;
+#endif
       for (int t = t_begin; t < p.total_tiles; t += t_step) {
         const TileWork w = decode_tile(p, t, crank);
         int nkb = w.kb1 - w.kb0;
@@ -297,6 +322,9 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
                     mbar_arrive_remote_u32(full0 + 8u * stage, 0);
                   tma_load_5d_2sm_u32(sa, map_a, fb, c0, cw, cp, ch, n0);
                   tma_load_3d_2sm_u32(sa + a_bytes, map_b, fb, kcol, ncol0, wt);
+#ifdef DM_STAMPS
+                  if (!stamped_first) { DM_STAMP(3); stamped_first = true; }
+#endif
                 } else {
                   mbar_arrive_expect_tx_u32(fb, tx_bytes);
                   tma_load_5d_u32(sa, map_a, fb, c0, cw, cp, ch, n0);
@@ -307,6 +335,9 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
                       tma_load_3d_u32(sa + a_bytes + a * kAtomB, map_b, fb, ncol0 + a * kAtomW, kcol, wt);
                   }
                 }
+#ifdef DM_STAMPS
+                if (!stamped_first) { DM_STAMP(3); stamped_first = true; }
+#endif
               }
               c0 += kc;
               kcol += kc;
@@ -355,6 +386,9 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
               for (int a = 0; a < b_atoms; ++a)
                 tma_load_5d_u32(sa + a_bytes + a * kAtomB, map_b, fb, nch0 + a * kAtomW + bdc, w0 + bdw, bdp,
                                 h0 + bdh, n0);
+#ifdef DM_STAMPS
+              if (!stamped_first) { DM_STAMP(3); stamped_first = true; }
+#endif
             }
             w0 += p.tw_step;
             h0 += p.th_step;
@@ -372,6 +406,7 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
           }
         }
       }
+      if (leader) DM_STAMP(11);
     }
   } else if (warp == 1) {
     // =========================================================== MMA issuer (whole warp loops, one elected lane issues)
@@ -412,6 +447,9 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
         uint32_t acc = 0;
         for (; nkb > 0; --nkb) {
           mbar_wait_u32(full0 + 8u * stage, parity);
+#ifdef DM_STAMPS
+          if (leader && it == 0 && acc == 0) DM_STAMP(4);
+#endif
           const uint64_t da = da_t | s16;
           const uint64_t db = db_t | (s16 + a16);
           if (!leader) {
@@ -454,6 +492,7 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
         }
         ++it;
       }
+      if (leader) DM_STAMP(5);
     }
   } else {
     // =========================================================== epilogue (4 warps, 128 TMEM lanes)
@@ -489,6 +528,12 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
       const int buf = it & 1;
       mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
       tc_fence_after();
+#ifdef DM_STAMPS
+      if (q == 0 && lane == 0) {
+        if (it == 0) DM_STAMP(6);
+        DM_STAMP(7);
+      }
+#endif
       const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * p.acc_stride);
       const int m_tile = w.m_tile, n_tile = w.n_tile;
 
@@ -797,6 +842,7 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
       }
       ++it;
     }
+    if (q == 0 && lane == 0) DM_STAMP(8);
     if (p.stat_out) {
       // publish this CTA's partial sums, take a ticket; the LAST CTA of the grid finalizes the BatchNorm (constants for
       // the consumer kernel, running statistics) and re-zeroes the scratch -- no finalize kernel
@@ -811,7 +857,9 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (tmem_ptr_smem[1] != 0u) bn_forward_finalize(p.stat_fin, p.stat_c, q * 32 + lane, 128);
     }
+    if (q == 0 && lane == 0) DM_STAMP(9);
     if (p.epi_tma && lane == 0) bulk_wait_group_all();  // smem must outlive the stores' reads; writes complete
+    if (q == 0 && lane == 0) DM_STAMP(10);
   }
 
   tc_fence_before();
@@ -825,6 +873,7 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
     else
       tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
   }
+  if (threadIdx.x == 0) DM_STAMP(12);
 }
 
 // ================================================================================ host side
@@ -913,6 +962,13 @@ static int encode_w_map3(CUtensorMap* m, const void* ptr, long long t, long long
   return encode_map(m, ptr, 3, dims, str, box, swizzle_bytes, f32);
 }
 
+#ifdef DM_STAMPS
+static unsigned long long* g_stamps = nullptr;
+extern "C" int dm_debug_set_stamps(void* dev_buf) {
+  g_stamps = static_cast<unsigned long long*>(dev_buf);
+  return 0;
+}
+#endif
 static int g_last_grid[3] = {0, 0, 0};
 static int g_last_smem = 0, g_last_stages = 0;
 
@@ -1035,19 +1091,31 @@ static int launch(GemmParams& p, dim3 grid, cudaStream_t stream, double flops, i
     }
   }
   if (prof) cudaEventRecord(rec.e0, stream);
+#ifdef DM_STAMPS
+  p.stamps = g_stamps;
+#endif
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(ctas);
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int nattr = 0;
+  if (cluster > 1) {
+    attr[nattr].id = cudaLaunchAttributeClusterDimension;
+    attr[nattr].val.clusterDim.x = cluster;
+    attr[nattr].val.clusterDim.y = 1;
+    attr[nattr].val.clusterDim.z = 1;
+    ++nattr;
+  }
+  if (pdl_enabled()) {
+    attr[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[nattr].val.programmaticStreamSerializationAllowed = 1;
+    ++nattr;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = cluster > 1 ? 1 : 0;
+  cfg.numAttrs = nattr;
   cudaError_t le = p.tf32 ? cudaLaunchKernelEx(&cfg, dm_tapgemm_kernel<false, true>, p)
                           : (p.cg2 ? cudaLaunchKernelEx(&cfg, dm_tapgemm_kernel<true>, p)
                                    : cudaLaunchKernelEx(&cfg, dm_tapgemm_kernel<false>, p));

@@ -234,8 +234,48 @@ def linear_wgrad(dy_bf16, x_bf16, batch, n_out, k_in, dw, overwrite=False):
     ops.gemm(GEMM_TN, x_bf16, dy_bf16, k_in, n_out, batch, out=dw, accumulate=not overwrite, ldd_m=1, ldd_n=k_in)
 
 
+class WgradSide:
+    """Convolution weight gradients on a side stream.  Inside one network's backward pass the weight gradient of a layer
+    and the rest of the chain (input gradient -> BatchNorm backward -> next layer) only share their inputs, and nothing
+    reads the weight gradient before the optimizer: with `stream` set (the fused trainers do, DM_WGRAD_STREAM=1) every
+    conv weight-gradient launch forks off the current stream, and `join()` -- called at the end of each backward
+    pass -- brings it back.  The tail of each GEMM (last tiles, epilogue, drain: ~5 us of a 20-40 us launch at batch
+    64) then overlaps another kernel's work instead of idling the SMs.  Works the same inside a CUDA-graph capture
+    (fork / join become graph edges)."""
+    stream = None
+    keep = []      # operands of the in-flight side-stream launches: alive until join()
+    pending = False
+
+    @classmethod
+    def run(cls, fn, *args):
+        s = cls.stream
+        if s is None:
+            fn(*args)
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        s.wait_event(ev)
+        with torch.cuda.stream(s):
+            fn(*args)
+        cls.keep.append(args)
+        cls.pending = True
+
+    @classmethod
+    def join(cls):
+        if cls.pending:
+            ev = torch.cuda.Event()
+            ev.record(cls.stream)
+            torch.cuda.current_stream().wait_event(ev)
+            cls.keep.clear()
+            cls.pending = False
+
+
 def conv_wgrad(g, small, big, dw, cache, name):
     """Conv / ConvT weight gradient through the tap-major packed scratch (persistent per weight, kept zeroed)."""
+    WgradSide.run(_conv_wgrad, g, small, big, dw, cache, name)
+
+
+def _conv_wgrad(g, small, big, dw, cache, name):
     packed = getattr(cache, "packed_grads", None)
     if packed is not None and (name + ".weight") in packed:
         # fused trainers: the flat gradient buffer holds this weight's gradient in the packed layout already
@@ -255,6 +295,10 @@ def conv_wgrad(g, small, big, dw, cache, name):
 
 def conv3_wgrad(g, pim, small, dw, cache, name):
     """Weight gradient of a 3-image-channel layer through its persistent window-layout scratch (kept zeroed)."""
+    WgradSide.run(_conv3_wgrad, g, pim, small, dw, cache, name)
+
+
+def _conv3_wgrad(g, pim, small, dw, cache, name):
     ws = cache.wgrad_scratch
     key = (name, "win", str(dw.device))
     if key not in ws:
@@ -317,10 +361,12 @@ def _slice_disc(S, g0, g1):
 
 
 def discriminator_backward(S, dprob, dfeat, P, G, cache: OperandCache, need_dx=True, need_wgrad=True,
-                           overwrite_big=False, grad_ready=None, group_range=None):
+                           overwrite_big=False, grad_ready=None, group_range=None, linear_done=None):
     """Backward of discriminator_forward. dprob [b] / dfeat [b,2048] fp32 (either may be None).
     G: dict name -> fp32 grad tensor (accumulated) or None. Returns dx fp32 NCHW or None.
-    group_range=(g0, g1): back-propagate only through those groups of a grouped forward (b = their images)."""
+    group_range=(g0, g1): back-propagate only through those groups of a grouped forward (b = their images).
+    linear_done: called once the 16384x2048 Linear is back-propagated -- its weight gradient is final and the weight is
+    not read again in this pass (its optimizer update may start, see encoder_backward's heads_done)."""
     if group_range is not None:
         S = _slice_disc(S, *group_range)
     b = S.b
@@ -340,6 +386,8 @@ def discriminator_backward(S, dprob, dfeat, P, G, cache: OperandCache, need_dx=T
         if grad_ready:  # the 33.5 M-element gradient is final: its all-reduce can overlap the conv backward below
             grad_ready("lth_features.0.weight")
     dflat = linear_dgrad(dpre, wl, b, 2048, 16384)
+    if linear_done:
+        linear_done()
     da4 = ops.transpose(dflat, b, 256, 64)  # back to NHWC [b,64,256]
     # conv 4
     dr4 = bn_act_backward(da4, S.bn4, wg, "convs.10", cache)
@@ -368,10 +416,13 @@ def discriminator_backward(S, dprob, dfeat, P, G, cache: OperandCache, need_dx=T
     if wg:
         conv3_wgrad(g1, S.pim, dr1, wg["convs.0.weight"], cache, "convs.0")
     if not need_dx:
+        WgradSide.join()
         return None
     _, wu1, _ = _conv_pack(cache, "convs.0", P["convs.0.weight"], 32, 3)
     dx_nhwc = ops.conv_up(g1, dr1, wu1, out_f32=True)
-    return ops.nhwc3_to_nchw(dx_nhwc, b, 64, 64, False)
+    dx = ops.nhwc3_to_nchw(dx_nhwc, b, 64, 64, False)
+    WgradSide.join()
+    return dx
 
 
 # ------------------------------------------------------------------------------------------ Encoder
@@ -457,37 +508,41 @@ def encoder_backward(S, dmu, dlogvar, P, G, cache: OperandCache, need_wgrad=True
     dr1 = bn_act_backward(da1, S.bn1, wg, "features.1", cache)
     if wg:
         conv3_wgrad(ops.geom(b, 32, 32, 64, 3, 2), S.pim, dr1, wg["features.0.weight"], cache, "features.0")
+    WgradSide.join()
     return None  # the encoder input is data: no input gradient on this path
 
 
 # ------------------------------------------------------------------------------------------ Decoder
-def decoder_forward(code, P, B, cache: OperandCache, training=True, pim_out=None):
+def decoder_forward(code, P, B, cache: OperandCache, training=True, pim_out=None, groups=1):
     """VAE.decode / Generator_celeba.forward (model.py:537-566, 363-378). code: fp32 or bf16 [b,128].
     Returns recon fp32 NCHW [b,3,64,64]; pim_out (optional [b,68,72,8] bf16 buffer) also receives it as a padded image,
-    the form in which the discriminator reads it."""
+    the form in which the discriminator reads it.
+    groups > 1: `code` stacks that many separate decode() calls (e.g. decode(noise) | decode(z)); every GEMM processes
+    them together, BatchNorm treats each group as its own forward pass, in order (see bn_act_forward)."""
     b = code.shape[0]
-    S = SimpleNamespace(b=b)
+    bg = b // groups
+    S = SimpleNamespace(b=b, groups=groups)
     S.code16 = code if code.dtype == BF16 else ops.cast_bf16(code.contiguous())
     wp = _lin_w(cache, "preprocess.0", P["preprocess.0.weight"])
     acc = linear_forward(S.code16, wp, P["preprocess.0.bias"].detach(), b, 16384, 128)
-    h, S.bn0 = bn_act_forward(acc, b, 16384, P, B, "preprocess.1", ACT_RELU, training, 1, cache)
+    h, S.bn0 = bn_act_forward(acc, b, 16384, P, B, "preprocess.1", ACT_RELU, training, groups, cache)
     S.h0 = ops.transpose(h, b, 256, 64)  # NCHW flatten order -> NHWC [b,8,8,256]
     dev = code.device
     g1 = ops.geom(b, 8, 8, 256, 256, 2)
     _, wu1, _ = _conv_pack(cache, "deconv1", P["deconv1.weight"], 256, 256)
-    f1 = bn_fuse(cache, P, B, "act1.0", 256, 1, b * 256, dev, training, tile_rows=b * 64)
+    f1 = bn_fuse(cache, P, B, "act1.0", 256, groups, bg * 256, dev, training, tile_rows=bg * 64)
     raw1 = ops.conv_up(g1, S.h0, wu1, P["deconv1.bias"].detach(), bn=f1)
-    S.a1, S.bn1 = bn_act_forward(raw1, b * 256, 256, P, B, "act1.0", ACT_RELU, training, 1, cache, f1)
+    S.a1, S.bn1 = bn_act_forward(raw1, b * 256, 256, P, B, "act1.0", ACT_RELU, training, groups, cache, f1)
     g2 = ops.geom(b, 16, 16, 256, 128, 2)
     _, wu2, _ = _conv_pack(cache, "deconv2", P["deconv2.weight"], 256, 128)
-    f2 = bn_fuse(cache, P, B, "act2.0", 128, 1, b * 1024, dev, training, tile_rows=b * 256)
+    f2 = bn_fuse(cache, P, B, "act2.0", 128, groups, bg * 1024, dev, training, tile_rows=bg * 256)
     raw2 = ops.conv_up(g2, S.a1, wu2, P["deconv2.bias"].detach(), bn=f2)
-    S.a2, S.bn2 = bn_act_forward(raw2, b * 1024, 128, P, B, "act2.0", ACT_RELU, training, 1, cache, f2)
+    S.a2, S.bn2 = bn_act_forward(raw2, b * 1024, 128, P, B, "act2.0", ACT_RELU, training, groups, cache, f2)
     g3 = ops.geom(b, 32, 32, 128, 32, 2)
     _, wu3, _ = _conv_pack(cache, "deconv3", P["deconv3.weight"], 128, 32)
-    f3 = bn_fuse(cache, P, B, "act3.0", 32, 1, b * 4096, dev, training, tile_rows=b * 1024)
+    f3 = bn_fuse(cache, P, B, "act3.0", 32, groups, bg * 4096, dev, training, tile_rows=bg * 1024)
     raw3 = ops.conv_up(g3, S.a2, wu3, P["deconv3.bias"].detach(), bn=f3)
-    S.a3, S.bn3 = bn_act_forward(raw3, b * 4096, 32, P, B, "act3.0", ACT_RELU, training, 1, cache, f3)
+    S.a3, S.bn3 = bn_act_forward(raw3, b * 4096, 32, P, B, "act3.0", ACT_RELU, training, groups, cache, f3)
     g4 = ops.geom(b, 64, 64, 32, 3, 1)
     _, wu4, _ = _conv_pack(cache, "deconv4", P["deconv4.weight"], 32, 3)
     y4 = ops.conv_up(g4, S.a3, wu4, P["deconv4.bias"].detach(), out_f32=True)  # fp32 NHWC(3)
@@ -496,7 +551,8 @@ def decoder_forward(code, P, B, cache: OperandCache, training=True, pim_out=None
 
 
 def decoder_backward(S, drecon, P, G, cache: OperandCache, need_dcode=True, need_wgrad=True, overwrite_big=False):
-    """drecon: fp32 NCHW gradient w.r.t. the decoder output. Returns dcode fp32 [b,128] or None."""
+    """drecon: fp32 NCHW gradient w.r.t. the decoder output (all groups of a grouped forward, stacked).
+    Returns dcode fp32 [b,128] or None."""
     b = S.b
     wg = G if need_wgrad else None
     # gradient w.r.t. the pre-tanh image, written straight as a padded bf16 image: the operand of both GEMMs below
@@ -530,6 +586,9 @@ def decoder_backward(S, drecon, P, G, cache: OperandCache, need_dcode=True, need
     if wg:
         linear_wgrad(dacc, S.code16, b, 16384, 128, wg["preprocess.0.weight"], overwrite_big)
     if not need_dcode:
+        WgradSide.join()
         return None
     wp = _lin_w(cache, "preprocess.0", P["preprocess.0.weight"])
-    return linear_dgrad(dacc, wp, b, 16384, 128, out_dtype=F32)
+    dcode = linear_dgrad(dacc, wp, b, 16384, 128, out_dtype=F32)
+    WgradSide.join()
+    return dcode

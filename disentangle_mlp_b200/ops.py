@@ -427,9 +427,9 @@ def cast_bf16(src, dst=None):
     return dst
 
 
-def reparam_forward(mu, logvar, eps):
+def reparam_forward(mu, logvar, eps, out_bf16=None):
     z = torch.empty_like(mu)
-    zb = torch.empty(mu.shape, dtype=BF16, device=mu.device)
+    zb = torch.empty(mu.shape, dtype=BF16, device=mu.device) if out_bf16 is None else out_bf16
     _lib.check(_lib.load().dm_reparam_forward(_p(mu), _p(logvar), _p(eps), mu.numel(), _p(z), _p(zb), _stream()),
                "dm_reparam_forward")
     return z, zb

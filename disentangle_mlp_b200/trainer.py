@@ -549,6 +549,8 @@ class _Base:
         self.dist = GradReducer()
         self.metrics = {}
         self._graph = None
+        if os.environ.get("DM_WGRAD_STREAM", "1") != "0" and engine.WgradSide.stream is None and torch.cuda.is_available():
+            engine.WgradSide.stream = torch.cuda.Stream()
 
     def flat_params(self):
         raise NotImplementedError
@@ -877,6 +879,13 @@ class BetaVAEGANTrainer(_Base):
             real_label, fake_label = self.draw_labels()
         return self._step_impl(data, real_label, fake_label, noise, eps_dec, eps_enc)
 
+    # DM_STACK_DEC=1 (default): the encoder / decoder forward of the "decoder" phase is computed at the START of the step.
+    # It reads only the encoder / decoder parameters, which the discriminator phase does not change, so decode(noise)
+    # (discriminator phase) and decode(z) (decoder phase) go through every decoder GEMM TOGETHER as one stacked
+    # two-group pass (BatchNorm per group, noise first: the reference's order of running-stat updates), and so do their
+    # two backward passes.  =0: the reference's literal order, two separate decoder passes each way.
+    STACK_DEC = os.environ.get("DM_STACK_DEC", "1") != "0"
+
     def _step_impl(self, data, real_label, fake_label, noise=None, eps_dec=None, eps_enc=None):
         feg, fd, dev = self.feg, self.fd, data.device
         b = data.shape[0]
@@ -891,42 +900,64 @@ class BetaVAEGANTrainer(_Base):
             feg.finish_big(self._side())
         pim = ops.pim_empty(3 * b, dev)
         data = self._ingest(data, pim[:b])
+        nt = b * self.dist.world
+        if noise is None:
+            noise = torch.randn(b, 128, device=dev)
+        stack = self.STACK_DEC
+
+        if stack:
+            # ---- encoder forward + BOTH decoder forwards of the discriminator / decoder phases (:97 fake, :127 recon)
+            feg.zero_grad()
+            mu, logvar, Se = engine.encoder_forward(None, feg.P, feg.buffers, feg.cache, True, pim=pim[:b],
+                                                    before_heads=self._before_use(feg))
+            if eps_dec is None:
+                eps_dec = torch.randn_like(mu)
+            code = torch.empty((2 * b, 128), dtype=BF16, device=dev)
+            ops.cast_bf16(noise.contiguous(), code[:b])
+            ops.reparam_forward(mu, logvar, eps_dec, out_bf16=code[b:])
+            both, Sg12 = engine.decoder_forward(code, feg.P, feg.buffers, feg.cache, True, pim_out=pim[b:], groups=2)
+            recon = both[b:]
 
         # ================= discriminator phase (:95-123).  D(data) and D(fake.detach()) share every GEMM launch
         # (stacked along the batch); BatchNorm statistics / running-stat updates stay per pass, real first.
         fd.zero_grad()
-        nt = b * self.dist.world
-        if noise is None:
-            noise = torch.randn(b, 128, device=dev)
-        fake, Sg1 = engine.decoder_forward(noise, feg.P, feg.buffers, feg.cache, True, pim_out=pim[b:2 * b])
+        if not stack:
+            fake, Sg1 = engine.decoder_forward(noise, feg.P, feg.buffers, feg.cache, True, pim_out=pim[b:2 * b])
         prob, _, S12 = engine.discriminator_forward(None, fd.P, fd.buffers, fd.cache, True, groups=2, pim=pim[:2 * b])
         dprob = torch.empty_like(prob)
         ops.bce_const(prob[:b], real_label, errD_real, 1.0, n_total=nt, dprob=dprob[:b], stat=sum_dx)
         ops.bce_const(prob[b:], fake_label, errD_fake, 1.0, n_total=nt, dprob=dprob[b:])
+        # (stacked order: nothing independent follows the discriminator's backward pass, so the update of its
+        # 33.5 M-element Linear weight starts on the side stream as soon as that layer is back-propagated)
         engine.discriminator_backward(S12, dprob, None, fd.P, fd.G, fd.cache, False, True, overwrite_big=True,
-                                      grad_ready=self._early(fd))
+                                      grad_ready=self._early(fd), linear_done=self._heads_done(fd) if stack else None)
         del S12
         fd.reduce_rest(self.dist)  # data parallel: D's gradient all-reduce runs on the NCCL stream ...
-        # ... and D's Adam update (HBM-bound) runs on a side stream, both under the tensor-bound encoder / decoder
-        # forward below
-        fork = self._fork_side(lambda: (self.dist.wait(), fd.adam()))
+        if stack:
+            self.dist.wait()
+            fd.adam()
+        else:
+            # ... and D's Adam update (HBM-bound) runs on a side stream, both under the tensor-bound encoder / decoder
+            # forward below
+            fork = self._fork_side(lambda: (self.dist.wait(), fd.adam()))
 
         # ================= "decoder" phase (:127-164): gradient of
         #   BCE(D(fake), real) + BCE(D(recon), real) + 0.5*||Dis_l(recon) - Dis_l(x)||^2 + ||recon - x||^2
         # w.r.t. ALL encoder and decoder parameters, D frozen at its updated value
-        # ... while the encoder / decoder forward of this phase, which does not read D, is computed; the D update
-        # (:123) lands before D is evaluated again, as in the reference
-        feg.zero_grad()
-        mu, logvar, Se = engine.encoder_forward(None, feg.P, feg.buffers, feg.cache, True, pim=pim[:b],
-                                                before_heads=self._before_use(feg))
-        if eps_dec is None:
-            eps_dec = torch.randn_like(mu)
-        _, z16 = ops.reparam_forward(mu, logvar, eps_dec)
-        recon, Sg2 = engine.decoder_forward(z16, feg.P, feg.buffers, feg.cache, True, pim_out=pim[2 * b:])
-        self._join_side(fork)
+        if not stack:
+            # ... while the encoder / decoder forward of this phase, which does not read D, is computed; the D update
+            # (:123) lands before D is evaluated again, as in the reference
+            feg.zero_grad()
+            mu, logvar, Se = engine.encoder_forward(None, feg.P, feg.buffers, feg.cache, True, pim=pim[:b],
+                                                    before_heads=self._before_use(feg))
+            if eps_dec is None:
+                eps_dec = torch.randn_like(mu)
+            _, z16 = ops.reparam_forward(mu, logvar, eps_dec)
+            recon, Sg2 = engine.decoder_forward(z16, feg.P, feg.buffers, feg.cache, True, pim_out=pim[2 * b:])
+            self._join_side(fork)
         # D(data) | D(fake) | D(recon) in one stacked pass (BatchNorm per pass, in the reference's order :129,147,150)
         prob3, feat3, S345 = engine.discriminator_forward(None, fd.P, fd.buffers, fd.cache, True, groups=3, pim=pim,
-                                                          before_linear=fd.wait_gathered if fd.shard else None)
+                                                          before_linear=self._before_use(fd))
         sim_real, sim_recon = feat3[:b], feat3[2 * b:]
         dprob2 = torch.empty(2 * b, dtype=F32, device=dev)
         ops.bce_const(prob3[b:2 * b], real_label, errG_fake, 1.0, n_total=nt, dprob=dprob2[:b])
@@ -938,15 +969,21 @@ class BetaVAEGANTrainer(_Base):
         dx = engine.discriminator_backward(S345, dprob2, dfeat2, fd.P, None, fd.cache, True, False, group_range=(1, 3))
         del S345
         dfake, drecon = dx[:b], dx[b:]
-        engine.decoder_backward(Sg1, dfake, feg.P, feg.G, feg.cache, False, True, overwrite_big=True)
-        del Sg1
-        ops.mse_sum(recon, data, loss_dec, 1.0, drecon, 1.0, accumulate=True)
-        dz = engine.decoder_backward(Sg2, drecon, feg.P, feg.G, feg.cache, True, True)
+        if stack:
+            ops.mse_sum(recon, data, loss_dec, 1.0, drecon, 1.0, accumulate=True)
+            dz = engine.decoder_backward(Sg12, dx, feg.P, feg.G, feg.cache, True, True, overwrite_big=True)[b:]
+            del Sg12
+        else:
+            engine.decoder_backward(Sg1, dfake, feg.P, feg.G, feg.cache, False, True, overwrite_big=True)
+            del Sg1
+            ops.mse_sum(recon, data, loss_dec, 1.0, drecon, 1.0, accumulate=True)
+            dz = engine.decoder_backward(Sg2, drecon, feg.P, feg.G, feg.cache, True, True)
+            del Sg2
         feg.reduce_from(self.dist, "preprocess.0.weight")  # decoder gradients are final: reduce them under the encoder backward
         _, _, dmu, dlv = ops.reparam_backward(dz, logvar, eps_dec)
         engine.encoder_backward(Se, dmu, dlv, feg.P, feg.G, feg.cache, True, overwrite_big=True,
                                 grad_ready=self._early(feg), heads_done=self._heads_done(feg))
-        del Sg2, Se
+        del Se
         feg.reduce_rest_and_wait(self.dist)
         # (big Linear weights on the side stream: the encoder convolutions of the next phase do not read them)
         feg.adam(big="side" if self.DEFER else "now", side=self._side())

@@ -31,6 +31,12 @@ def cases(b):
     w = torch.randn(n, k, device=dev).bfloat16()
     d = torch.empty(m, n, device=dev, dtype=torch.bfloat16)
     out.append((f"gemm_nt {m}x{n}x{k}", 2.0 * m * n * k, lambda: ops.gemm(ops.GEMM_NT, a, w, m, n, k, out=d)))
+    for (tm, tn, tk) in ((b, 128, 2048), (b, 16384, 128)):
+        ta = torch.randn(tm, tk, device=dev).bfloat16()
+        tw = torch.randn(tn, tk, device=dev).bfloat16()
+        td = torch.empty(tm, tn, device=dev, dtype=torch.bfloat16)
+        out.append((f"gemm_nt {tm}x{tn}x{tk}", 2.0 * tm * tn * tk,
+                    lambda ta=ta, tw=tw, td=td, tm=tm, tn=tn, tk=tk: ops.gemm(ops.GEMM_NT, ta, tw, tm, tn, tk, out=td)))
     for (hs, cs, cb, stride) in ((16, 256, 128, 2), (8, 256, 256, 2), (32, 128, 32, 2)):
         wt = torch.randn(cs, cb, 5, 5, device=dev) * 0.05
         small = torch.randn(b, hs, hs, cs, device=dev).bfloat16()
