@@ -372,6 +372,108 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
   }
 }
 
+// Backward in ONE launch: reduce -> grid-wide barrier -> apply.  The barrier is the ticket of the two-launch scheme
+// plus a flag the finalizing block raises; every block of the grid must be resident at once, so the host caps the
+// grid at two blocks per SM (dm_bn_backward falls back to the two-launch form otherwise).  Waiting blocks only wait for
+// blocks of this same kernel, which depend on nothing but earlier kernels: other kernels sharing the SMs can delay the
+// barrier but not deadlock it.  The apply phase re-reads this block's own rows (L2 hits for the tensors of this model)
+// -- no second launch, no second ramp-up.  Scratch words after the slots: [0] ticket, [1] flag, [2] exit ticket.
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dout,
+                                                           const T* __restrict__ y, long long rows, int c,
+                                                           long long rows_per_block,
+                                                           const float* __restrict__ scale_shift,
+                                                           const float* __restrict__ mean_invstd, int act,
+                                                           float slope, float* scratch, float* dgamma, float* dbeta,
+                                                           __nv_bfloat16* __restrict__ dy) {
+  pdl_sync();
+  const int groups = gridDim.z;
+  float* slots = scratch + static_cast<long long>(blockIdx.z) * kBnSlots * 2 * c;
+  const float* sums = scratch + bn_slot_floats(c, groups) + 4 + static_cast<long long>(blockIdx.z) * 2 * c;
+  {
+    const long long z = blockIdx.z;  // group
+    dout += z * rows * c;
+    y += z * rows * c;
+    dy += z * rows * c;
+    scale_shift += z * 2 * c;
+    mean_invstd += z * 2 * c;
+  }
+  const int cv = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = cv * 8 < c;
+  float sc[8], sh[8], mu[8], is[8];
+  if (live) {
+    load8(scale_shift + cv * 8, sc);
+    load8(scale_shift + c + cv * 8, sh);
+    load8(mean_invstd + cv * 8, mu);
+    load8(mean_invstd + c + cv * 8, is);
+  }
+  rows_reduce_slots<T, 2>(rows, c, rows_per_block, slots, [&](long long r, int ch, float(&acc)[2][8]) {
+    float f[8], g[8];
+    load8(y + r * c + ch, f);
+    load8(dout + r * c + ch, g);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float dz = g[i] * act_grad(f[i] * sc[i] + sh[i], act, slope);
+      acc[0][i] += dz;
+      acc[1][i] += dz * (f[i] - mu[i]) * is[i];
+    }
+  });
+  unsigned int* words = bn_ticket(scratch, c, groups);
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  if (take_ticket(words)) {
+    bn_backward_finalize(scratch, c, groups, dgamma, dbeta, tid, blockDim.x * blockDim.y);
+    __threadfence();  // every finalizing thread publishes its sums ...
+    __syncthreads();
+    if (tid == 0) atomicExch(words + 1, 1u);  // ... before the flag goes up
+  }
+  if (tid == 0) {
+    unsigned int f;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(words + 1) : "memory");
+    } while (f == 0u);
+  }
+  __syncthreads();
+  if (live) {
+    float s0[8], s1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s0[i] = __ldcg(sums + cv * 8 + i);
+      s1[i] = __ldcg(sums + c + cv * 8 + i);
+    }
+    const float inv_n = 1.f / static_cast<float>(rows);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s0[i] *= inv_n;
+      s1[i] *= inv_n;
+    }
+    const long long r0 = blockIdx.y * rows_per_block;
+    const long long r1 = min(rows, r0 + rows_per_block);
+#pragma unroll kBnUnroll
+    for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+      float f[8], g[8];
+      load8(y + r * c + cv * 8, f);
+      load8(dout + r * c + cv * 8, g);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float dz = g[i] * act_grad(f[i] * sc[i] + sh[i], act, slope);
+        const float xh = (f[i] - mu[i]) * is[i];
+        g[i] = sc[i] * (dz - s0[i] - xh * s1[i]);  // sc = gamma * invstd
+      }
+      store8(dy + r * c + cv * 8, g);
+    }
+  }
+  // the last block past the barrier lowers the flag for the next launch
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int n = gridDim.x * gridDim.y * gridDim.z;
+    if (atomicAdd(words + 2, 1u) == n - 1u) {
+      words[2] = 0u;
+      __threadfence();
+      atomicExch(words + 1, 0u);
+    }
+  }
+}
+
 // ---- small-row BatchNorm (rows <= kBn1dMaxRows; BatchNorm1d behind the Linear layers, model.py:462,468,492):
 // ONE launch, one block = 32 channels x all rows, exact two-pass variance (what torch computes), running statistics,
 // normalise + activation.  blockDim (4, 64): thread (x, y) holds rows y, y+64, y+128, y+192 of channels 8x .. 8x+7.
@@ -1263,6 +1365,35 @@ extern "C" int dm_bn_backward(const void* dout_bf16, const void* y, int y_f32, l
   DM_REQUIRE(scratch != nullptr, "dm_bn_backward: scratch required for rows > %d", kBn1dMaxRows);
   RowLayout l = make_row_layout(rows, c);
   const size_t sm = sizeof(float) * 256 * 16;
+  {
+    // single-launch form: the whole grid must be resident (grid barrier) -> at most two blocks per SM, all groups included
+    // OFF by default: measured 4.90 vs 4.61 ms per batch-64 step (profiles/r02b_ab_bn_bwd_fused.txt) -- the barrier makes
+    // every block wait for the last one to get an SM slot, and the side-stream weight-gradient GEMMs hold those slots
+    static const bool fused_on = [] { const char* e = getenv("DM_BN_BWD_FUSED"); return e && e[0] == '1'; }();
+    static const int occ = [sm] {
+      int a = 0, b = 0, sms = 0, dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, bn_bwd_fused_kernel<bf16>, 256, sm);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, bn_bwd_fused_kernel<float>, 256, sm);
+      return std::min(a, b) >= 2 ? 2 * sms : 0;
+    }();
+    const long long per_group = occ / std::max(1, l.gx * groups);
+    if (fused_on && per_group >= 1) {
+      RowLayout f = l;
+      long long rpb = (rows + per_group - 1) / per_group;
+      rpb = std::max<long long>(f.ty, (rpb + f.ty - 1) / f.ty * f.ty);
+      f.rows_per_block = rpb;
+      f.gy = static_cast<int>((rows + rpb - 1) / rpb);
+      if (static_cast<long long>(f.gx) * f.gy * groups <= occ) {
+        if (y_f32)
+          launch_pdl(bn_bwd_fused_kernel<float>, dim3(f.gx, f.gy, groups), dim3(f.tx, f.ty), sm, s, d, static_cast<const float*>(y), rows, c, f.rows_per_block, scale_shift, mean_invstd, act, slope, scratch, dgamma, dbeta, static_cast<bf16*>(dy_bf16));
+        else
+          launch_pdl(bn_bwd_fused_kernel<bf16>, dim3(f.gx, f.gy, groups), dim3(f.tx, f.ty), sm, s, d, static_cast<const bf16*>(y), rows, c, f.rows_per_block, scale_shift, mean_invstd, act, slope, scratch, dgamma, dbeta, static_cast<bf16*>(dy_bf16));
+        DM_LAUNCHED("dm_bn_backward(fused)");
+      }
+    }
+  }
   const float* sums = scratch + bn_slot_floats(c, groups) + 4;
   if (y_f32)
     launch_pdl(bn_bwd_reduce_kernel<float>, dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), sm, s, d, static_cast<const float*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, act, slope, scratch, dgamma, dbeta);

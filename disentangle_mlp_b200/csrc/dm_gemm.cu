@@ -567,11 +567,20 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
           const int nn = (m_tile / p.tpi) * p.tn_step + rr / (p.bw * p.bh);
           stat_row_ok = (wx < p.w_lim) && (nn < p.n_lim);
         }
+#ifdef DM_STAMPS
+        long long ld_clk = 0, wait_clk = 0, pack_clk = 0, epi_t0 = clock64();
+#endif
         for (int c0 = 0; c0 < p.bn; c0 += 32) {
           uint32_t v[32];
           __syncwarp();  // tcgen05.ld is warp-collective
+#ifdef DM_STAMPS
+          const long long t_ld = clock64();
+#endif
           tmem_ld_32x32(lane_addr + static_cast<uint32_t>(c0), v);
           tmem_ld_wait();
+#ifdef DM_STAMPS
+          ld_clk += clock64() - t_ld;
+#endif
           if (c0 + 32 >= p.bn) {
             // all of this thread's TMEM reads of the tile are done: hand the accumulator back before the stores
             tc_fence_before();
@@ -607,6 +616,9 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
             st_s2 += ci == 2 ? d[0] : 0.f; st_q2 += ci == 2 ? d2[0] : 0.f;
             st_s3 += ci == 3 ? d[0] : 0.f; st_q3 += ci == 3 ? d2[0] : 0.f;
           }
+#ifdef DM_STAMPS
+          const long long t_w = clock64();
+#endif
           if (piece == 0) {
             // the staging buffer about to be filled must have been read by the store issued epi_bufs boxes ago
             if (lane == 0) {
@@ -616,6 +628,10 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
             }
             __syncwarp();
           }
+#ifdef DM_STAMPS
+          wait_clk += clock64() - t_w;
+          const long long t_p = clock64();
+#endif
           const uint32_t stg = stg0 + static_cast<uint32_t>(ebuf) * 16384u + row_addr;
           const int ncol = min(32, p.bn - c0);
           if (p.out_f32) {
@@ -635,6 +651,9 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
                              pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
             piece += ncol >> 3;
           }
+#ifdef DM_STAMPS
+          pack_clk += clock64() - t_p;
+#endif
           if (piece * 16 >= row_bytes || c0 + 32 >= p.bn) {
             fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the bulk (async proxy) store
             __syncwarp();
@@ -653,6 +672,13 @@ __global__ void __launch_bounds__(kThreads, 1) dm_tapgemm_kernel(const __grid_co
             if (++ebuf == p.epi_bufs) ebuf = 0;
           }
         }
+#ifdef DM_STAMPS
+        if (q == 0 && lane == 0 && p.stamps) {
+          p.stamps[blockIdx.x * 16 + 13] = static_cast<unsigned long long>(ld_clk);
+          p.stamps[blockIdx.x * 16 + 15] = static_cast<unsigned long long>(wait_clk) * 100000ull + static_cast<unsigned long long>(pack_clk);
+          p.stamps[blockIdx.x * 16 + 14] = static_cast<unsigned long long>(clock64() - epi_t0);
+        }
+#endif
       } else if (p.epi_tma == 2) {
         // ---- conv weight gradient: acc[m = cb row][n = cs col] -> packed dW[tap][n][m]; staging [32 n][32 m] fp32
         const uint64_t map_out = reinterpret_cast<uint64_t>(&p.map_out);

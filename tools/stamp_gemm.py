@@ -52,7 +52,10 @@ def main():
                 cols.append("   -   ")
             else:
                 cols.append(f"{(np.median(v) - t0) / 1e3:5.1f}/{(v.max() - t0) / 1e3:5.1f}")
-        print(f"{name:28s} {us:6.1f} us  ctas {len(st):4d} entry {cols[0]} | " + " ".join(cols[1:]))
+        extra = ""
+        if (st[:, 14] > 0).any():
+            extra = f" | last tile epilogue: {np.median(st[:, 14][st[:, 14] > 0]):.0f} clk, of which tcgen05.ld+wait {np.median(st[:, 13][st[:, 14] > 0]):.0f} clk, staging-buffer wait {np.median(st[:, 15][st[:, 14] > 0] // 100000):.0f}, pack + st.shared {np.median(st[:, 15][st[:, 14] > 0] % 100000):.0f}"
+        print(f"{name:28s} {us:6.1f} us  ctas {len(st):4d} entry {cols[0]} | " + " ".join(cols[1:]) + extra)
 
 
 if __name__ == "__main__":

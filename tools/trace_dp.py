@@ -58,6 +58,28 @@ def main():
               f"{sum(e - s for s, e in comp) / nsteps / 1e3:.3f} ms/step")
         for s, e in nccl[: len(nccl) // nsteps]:
             print(f"   nccl kernel {(e - s):8.1f} us")
+        # idle time of the compute side: gaps between consecutive compute kernels (union of intervals), largest first
+        merged = []
+        for cs, ce in comp:
+            if merged and cs <= merged[-1][1]:
+                merged[-1][1] = max(merged[-1][1], ce)
+            else:
+                merged.append([cs, ce])
+        gaps = sorted(((merged[i + 1][0] - merged[i][1], merged[i][1]) for i in range(len(merged) - 1)), reverse=True)
+        print(f"compute idle (no non-NCCL kernel running) {sum(g for g, _ in gaps) / nsteps / 1e3:.3f} ms/step; largest gaps:")
+        by_end = sorted(evs, key=lambda t: t[1])
+        for g, at in gaps[:24]:
+            prev = [n for s_, e_, n in evs if abs(e_ - at) < 0.01 and "nccl" not in n.lower()]
+            nxt = [n for s_, e_, n in evs if abs(s_ - (at + g)) < 0.01 and "nccl" not in n.lower()]
+            during = [f"{n[:28]}({e_ - s_:.0f}us)" for s_, e_, n in evs if "nccl" in n.lower() and s_ < at + g and e_ > at]
+            print(f"   {g:7.1f} us after [{(prev or ['?'])[0][:40]}] before [{(nxt or ['?'])[0][:40]}] nccl: {during}")
+        dump = os.environ.get("TRACE_DUMP")
+        if dump:
+            ks = sorted(evs)
+            t0 = ks[0][0]
+            with open(dump, "w") as f:
+                for s_, e_, n in ks[: len(ks) // nsteps]:
+                    f.write(f"{s_ - t0:10.1f} {e_ - s_:8.1f} {n[:90]}\n")
     dist.barrier()
     torch.cuda.synchronize()
     os._exit(0)
