@@ -78,7 +78,7 @@ struct RowLayout {
   int tx, ty, gx, gy;
   long long rows_per_block;
 };
-static RowLayout make_row_layout(long long rows, int c) {
+static RowLayout make_row_layout(long long rows, int c, bool streaming = false, int groups = 1) {
   RowLayout l;
   int cv = c / 8;
   l.tx = 1;
@@ -87,8 +87,15 @@ static RowLayout make_row_layout(long long rows, int c) {
   if (l.tx < 1) l.tx = 1;
   l.ty = 256 / l.tx;
   l.gx = (cv + l.tx - 1) / l.tx;
-  static const int per_sm = [] { const char* e = getenv("DM_BN_BLOCKS_PER_SM"); return e ? std::max(1, atoi(e)) : 2; }();
-  long long want = std::max<long long>(1, (148ll * per_sm) / l.gx);  // blocks per SM: bytes in flight vs partial vectors
+  // blocks per SM: bytes in flight vs fixed cost per block.  3 = what the register budget of these kernels lets an SM hold
+  // (one full wave).  Reducing kernels and pure streaming kernels (apply) have separate knobs.
+  static const int per_sm_red = [] { const char* e = getenv("DM_BN_BLOCKS_PER_SM"); return e ? std::max(1, atoi(e)) : 3; }();
+  static const int per_sm_str = [] { const char* e = getenv("DM_BN_APPLY_BLOCKS_PER_SM"); return e ? std::max(1, atoi(e)) : 4; }();
+  const int per_sm = streaming ? per_sm_str : per_sm_red;
+  // (stacked passes multiply the grid by `groups`: DM_BN_GROUP_AWARE=1 divides the per-group block count accordingly)
+  static const bool group_aware = [] { const char* e = getenv("DM_BN_GROUP_AWARE"); return e && e[0] == '1'; }();
+  const int gdiv = group_aware ? std::max(1, groups) : 1;
+  long long want = std::max<long long>(1, (148ll * per_sm) / (l.gx * gdiv));  // blocks per SM: bytes in flight vs partial vectors
   long long rpb = (rows + want - 1) / want;
   // DM_BN_MIN_SWEEPS > 1 gives small tensors fewer, fatter blocks (fewer partial vectors for the finalize kernels).
   // Measured (batch 64): 1 is best -- the reduce / apply kernels lose more than the finalize kernels gain.
@@ -1288,7 +1295,7 @@ extern "C" int dm_bn_stats(const void* y, int y_f32, int c, const dm_bn_fuse* f,
   DM_REQUIRE(f != nullptr && f->scratch != nullptr && f->groups >= 1 && f->rows > 0 && f->gamma && f->beta &&
                  f->scale_shift && f->mean_invstd,
              "dm_bn_stats: incomplete dm_bn_fuse");
-  RowLayout l = make_row_layout(f->rows, c);
+  RowLayout l = make_row_layout(f->rows, c, false, f->groups);
   const size_t sm = sizeof(float) * 256 * 16;
   if (y_f32)
     launch_pdl(bn_stats_kernel<float>, dim3(l.gx, l.gy, f->groups), dim3(l.tx, l.ty), sm, s, static_cast<const float*>(y), c, l.rows_per_block, *f);
@@ -1302,7 +1309,7 @@ extern "C" int dm_bn_apply_act(const void* y, int y_f32, long long rows, int c, 
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   DM_CHECK_C8(c, "dm_bn_apply_act");
   DM_REQUIRE(groups >= 1, "dm_bn_apply_act: groups must be >= 1");
-  RowLayout l = make_row_layout(rows, c);
+  RowLayout l = make_row_layout(rows, c, true, groups);
   if (y_f32)
     launch_pdl(bn_apply_act_kernel<float>, dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), 0, s, static_cast<const float*>(y), rows, c, l.rows_per_block, scale_shift, act, slope, static_cast<bf16*>(out_bf16));
   else
@@ -1363,7 +1370,8 @@ extern "C" int dm_bn_backward(const void* dout_bf16, const void* y, int y_f32, l
     DM_LAUNCHED("dm_bn_backward(1d)");
   }
   DM_REQUIRE(scratch != nullptr, "dm_bn_backward: scratch required for rows > %d", kBn1dMaxRows);
-  RowLayout l = make_row_layout(rows, c);
+  RowLayout l = make_row_layout(rows, c, false, groups);
+  const RowLayout la = make_row_layout(rows, c, true, groups);
   const size_t sm = sizeof(float) * 256 * 16;
   {
     // single-launch form: the whole grid must be resident (grid barrier) -> at most two blocks per SM, all groups included
@@ -1400,9 +1408,9 @@ extern "C" int dm_bn_backward(const void* dout_bf16, const void* y, int y_f32, l
   else
     launch_pdl(bn_bwd_reduce_kernel<bf16>, dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), sm, s, d, static_cast<const bf16*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, act, slope, scratch, dgamma, dbeta);
   if (y_f32)
-    launch_pdl(bn_bwd_apply_kernel<float>, dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), 0, s, d, static_cast<const float*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, sums, act, slope, static_cast<bf16*>(dy_bf16));
+    launch_pdl(bn_bwd_apply_kernel<float>, dim3(la.gx, la.gy, groups), dim3(la.tx, la.ty), 0, s, d, static_cast<const float*>(y), rows, c, la.rows_per_block, scale_shift, mean_invstd, sums, act, slope, static_cast<bf16*>(dy_bf16));
   else
-    launch_pdl(bn_bwd_apply_kernel<bf16>, dim3(l.gx, l.gy, groups), dim3(l.tx, l.ty), 0, s, d, static_cast<const bf16*>(y), rows, c, l.rows_per_block, scale_shift, mean_invstd, sums, act, slope, static_cast<bf16*>(dy_bf16));
+    launch_pdl(bn_bwd_apply_kernel<bf16>, dim3(la.gx, la.gy, groups), dim3(la.tx, la.ty), 0, s, d, static_cast<const bf16*>(y), rows, c, la.rows_per_block, scale_shift, mean_invstd, sums, act, slope, static_cast<bf16*>(dy_bf16));
   g_launch_count.fetch_add(2, std::memory_order_relaxed);
   return check_launch("dm_bn_backward");
 }

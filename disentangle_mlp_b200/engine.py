@@ -243,12 +243,14 @@ class WgradSide:
     64) then overlaps another kernel's work instead of idling the SMs.  Works the same inside a CUDA-graph capture
     (fork / join become graph edges)."""
     stream = None
+    big_stream = None  # second side stream: the 16384x2048 Linear weight gradients (HBM-latency-bound, like the
+                       # input-gradient GEMM they now run beside) and, behind them, the early Adam update of those weights
     keep = []      # operands of the in-flight side-stream launches: alive until join()
-    pending = False
+    pending = set()
 
     @classmethod
-    def run(cls, fn, *args):
-        s = cls.stream
+    def run(cls, fn, *args, big=False):
+        s = cls.big_stream if big else cls.stream
         if s is None:
             fn(*args)
             return
@@ -258,16 +260,16 @@ class WgradSide:
         with torch.cuda.stream(s):
             fn(*args)
         cls.keep.append(args)
-        cls.pending = True
+        cls.pending.add(s)
 
     @classmethod
     def join(cls):
-        if cls.pending:
+        for s in cls.pending:
             ev = torch.cuda.Event()
-            ev.record(cls.stream)
+            ev.record(s)
             torch.cuda.current_stream().wait_event(ev)
-            cls.keep.clear()
-            cls.pending = False
+        cls.pending.clear()
+        cls.keep.clear()
 
 
 def conv_wgrad(g, small, big, dw, cache, name):
@@ -382,9 +384,11 @@ def discriminator_backward(S, dprob, dfeat, P, G, cache: OperandCache, need_dx=T
     dpre = ops.act_backward(dfeat_t, S.feat, b, 2048, ACT_LEAKY, LEAKY, colsum)
     wl = _lin_w(cache, "lth_features.0", P["lth_features.0.weight"])
     if wg:
-        linear_wgrad(dpre, S.flat, b, 2048, 16384, wg["lth_features.0.weight"], overwrite_big)
-        if grad_ready:  # the 33.5 M-element gradient is final: its all-reduce can overlap the conv backward below
-            grad_ready("lth_features.0.weight")
+        def big_wgrad(dpre_, flat_, dw_):
+            linear_wgrad(dpre_, flat_, b, 2048, 16384, dw_, overwrite_big)
+            if grad_ready:  # the 33.5 M-element gradient is final: its all-reduce can overlap the conv backward below
+                grad_ready("lth_features.0.weight")
+        WgradSide.run(big_wgrad, dpre, S.flat, wg["lth_features.0.weight"], big=True)
     dflat = linear_dgrad(dpre, wl, b, 2048, 16384)
     if linear_done:
         linear_done()
@@ -486,9 +490,11 @@ def encoder_backward(S, dmu, dlogvar, P, G, cache: OperandCache, need_wgrad=True
         dacc = bn_act_backward(dh1, H.bn, wg, head + ".1", cache)
         w0 = _lin_w(cache, head + ".0", P[head + ".0.weight"])
         if wg:
-            linear_wgrad(dacc, S.flat, b, 2048, 16384, wg[head + ".0.weight"], overwrite_big)
-            if grad_ready:
-                grad_ready(head + ".0.weight")
+            def big_wgrad(dacc_, flat_, dw_, head_=head):
+                linear_wgrad(dacc_, flat_, b, 2048, 16384, dw_, overwrite_big)
+                if grad_ready:
+                    grad_ready(head_ + ".0.weight")
+            WgradSide.run(big_wgrad, dacc, S.flat, wg[head + ".0.weight"], big=True)
         linear_dgrad(dacc, w0, b, 2048, 16384, out_dtype=F32, out=dflat)
     if heads_done:
         heads_done()

@@ -551,6 +551,9 @@ class _Base:
         self._graph = None
         if os.environ.get("DM_WGRAD_STREAM", "1") != "0" and engine.WgradSide.stream is None and torch.cuda.is_available():
             engine.WgradSide.stream = torch.cuda.Stream()
+        if (os.environ.get("DM_BIG_WGRAD_STREAM", "0") != "0" and engine.WgradSide.big_stream is None
+                and torch.cuda.is_available()):
+            engine.WgradSide.big_stream = torch.cuda.Stream()
 
     def flat_params(self):
         raise NotImplementedError
@@ -572,6 +575,10 @@ class _Base:
         return []
 
     def _side(self):
+        # ONE side stream per process for the big Linear weights: their weight gradients (engine.WgradSide.big_stream)
+        # and the early / deferred Adam updates that consume them are ordered by being on the same stream
+        if engine.WgradSide.big_stream is not None:
+            return engine.WgradSide.big_stream
         if getattr(self, "_side_stream", None) is None:
             self._side_stream = torch.cuda.Stream()
         return self._side_stream
