@@ -91,6 +91,7 @@ def _shell_flat_params(net, bf16_big=True):
     fp = object.__new__(tr.FlatParams)
     fp.names, fp.offsets, fp.total, fp._small_end = plan["names"], plan["offsets"], plan["total"], plan["small_end"]
     fp.off16, fp._late_ranges, fp._tail_done = plan["off16"], plan["late_ranges"], None
+    fp.shard = False  # (the sharded reduce-scatter path of the big tensors is covered by tests/test_dist_cpu.py)
     fp.P = {n: SimpleNamespace(numel=lambda k=plan["numel"][n]: k) for n, _ in named}
     fp.grad = torch.zeros(plan["total"])
     fp.grad16 = torch.zeros(max(plan["total16"], 1), dtype=torch.bfloat16)
