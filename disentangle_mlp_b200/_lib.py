@@ -75,6 +75,8 @@ _SIGS = {
     "dm_transpose_bf16": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "dm_pack_conv_weights": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "dm_pack_up_merged": [c_void_p, c_int, c_int, c_void_p, c_void_p],
+    "dm_pack_down_pairs": [c_void_p, c_int, c_int, c_void_p, c_void_p],
+    "dm_conv_down_paired": [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_void_p, C.POINTER(BnFuse), c_void_p],
     "dm_conv_up_merged": [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_void_p, C.POINTER(BnFuse), c_void_p],
     "dm_cast_bf16": [c_void_p, c_ll, c_void_p, c_void_p],
     "dm_reparam_forward": [c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_void_p],

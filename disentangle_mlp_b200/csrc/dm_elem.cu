@@ -1006,6 +1006,25 @@ __global__ void __launch_bounds__(256) pack_up_merged_kernel(const __nv_bfloat16
   }
 }
 
+// w_pair[kh*3 + j][n][p*cb + c] = w_down[kh*5 + 2j + p][n][c] (zero where 2j + p = 5): the K = 2*cb operand rows of
+// dm_conv_down_paired (two filter columns per k-block)
+__global__ void __launch_bounds__(256) pack_down_pairs_kernel(const __nv_bfloat16* __restrict__ w_down, int cs, int cb,
+                                                              __nv_bfloat16* __restrict__ w_pair) {
+  pdl_sync();
+  const long long total = 15ll * cs * 2 * cb;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % (2 * cb));
+    long long r = i / (2 * cb);
+    const int n = static_cast<int>(r % cs);
+    const int t = static_cast<int>(r / cs);
+    const int kh = t / 3, kw = 2 * (t % 3) + k / cb, c = k % cb;
+    __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+    if (kw < 5) v = w_down[(static_cast<long long>(kh * 5 + kw) * cs + n) * cb + c];
+    w_pair[i] = v;
+  }
+}
+
 // tap-major packed conv gradient [25][n] -> master layout [n][25] (n = cs*cb); dw (+)= ; the packed buffer is
 // re-zeroed so that the next backward pass can accumulate into it again
 __global__ void __launch_bounds__(256) unpack_conv_grad_kernel(float* __restrict__ packed, long long n, int accumulate,
@@ -1527,6 +1546,13 @@ extern "C" int dm_pack_up_merged(const void* w_up, int cs, int cb, void* w_upm, 
   DM_REQUIRE(cb % 16 == 0, "dm_pack_up_merged: cb %d must be a multiple of 16", cb);
   launch_pdl(pack_up_merged_kernel, grid_for(36ll * cb * cs), 256, 0, s, static_cast<const bf16*>(w_up), cs, cb, static_cast<bf16*>(w_upm));
   DM_LAUNCHED("dm_pack_up_merged");
+}
+
+extern "C" int dm_pack_down_pairs(const void* w_down, int cs, int cb, void* w_pair, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  DM_REQUIRE(cb == 32, "dm_pack_down_pairs: cb %d must be 32 (64-element paired rows)", cb);
+  launch_pdl(pack_down_pairs_kernel, grid_for(30ll * cs * cb), 256, 0, s, static_cast<const bf16*>(w_down), cs, cb, static_cast<bf16*>(w_pair));
+  DM_LAUNCHED("dm_pack_down_pairs");
 }
 
 extern "C" int dm_unpack_conv_grad(float* packed, int cs, int cb, int accumulate, float* dw, void* stream_) {

@@ -1529,8 +1529,12 @@ static bool groups_tile_aligned(const PixTile& pt, int batch, int groups) {
   return pt.bimg <= 1 || (batch / groups) % pt.bimg == 0;
 }
 
+// paired = true (stride 2, cb = 32, bf16): w_down is the PAIRED pack [15][cs][64] of dm_pack_down_pairs -- a k-block is
+// one 128-byte row of the parity view (both w-parities x 32 channels) = the two filter columns (2j, 2j+1) of one
+// filter row; 15 k-blocks of K = 64 instead of 25 of K = 32.  The TMA unit delivers ~0.7 box rows per clock per SM
+// whatever the row length, so 64-byte rows feed the tensor cores at half the rate of 128-byte rows.
 static int conv_down_impl(const dm_conv_geom* g, const void* big, const void* w_down, const float* bias,
-                          void* out_small, const dm_bn_fuse* bn, bool tf32, void* stream_) {
+                          void* out_small, const dm_bn_fuse* bn, bool tf32, void* stream_, bool paired = false) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = check_geom(g, "dm_conv_down")) return rc;
   t_kind = 1;
@@ -1543,12 +1547,28 @@ static int conv_down_impl(const dm_conv_geom* g, const void* big, const void* w_
   p.mode = MODE_FWD;
   p.tf32 = tf32 ? 1 : 0;
   const int esz = tf32 ? 4 : 2;
-  p.kc = (g->cb % 64 == 0 && !tf32) ? 64 : 32;
+  if (paired) DM_REQUIRE(g->stride == 2 && g->cb == 32 && !tf32, "dm_conv_down_paired: stride 2, cb = 32, bf16 only");
+  p.kc = ((g->cb % 64 == 0 || paired) && !tf32) ? 64 : 32;
   p.bn = pick_bn_fill(g->cs, env_int("DM_BN_CAP", 128), pt.tiles);
-  p.cpt = g->cb / p.kc;
+  p.cpt = paired ? 1 : g->cb / p.kc;
   p.phase_tap_start[0] = 0;
-  p.phase_tap_start[1] = 25;
-  down_taps(g, p.taps);
+  p.phase_tap_start[1] = paired ? 15 : 25;
+  if (paired) {
+    for (int kh = 0; kh < 5; ++kh)
+      for (int j = 0; j < 3; ++j) {  // filter columns (2j, 2j+1): input w = 2*ow + 2j - 2 (+1) -> parity 0 (1), w/2 = ow + j - 1
+        Tap& t = p.taps[kh * 3 + j];
+        memset(&t, 0, sizeof(t));
+        t.wt = static_cast<uint8_t>(kh * 3 + j);
+        const int eh = kh - 2;
+        const int ah = (eh >= 0) ? eh / 2 : -((-eh + 1) / 2);
+        t.dh = static_cast<int8_t>(ah);
+        t.dp = static_cast<int8_t>(eh - 2 * ah);
+        t.dw = static_cast<int8_t>(j - 1);
+        t.dc = 0;
+      }
+  } else {
+    down_taps(g, p.taps);
+  }
   p.tw_step = 0; p.tpi = pt.tpi; p.th_step = pt.th_step; p.tn_step = pt.tn_step;
   p.bw = pt.bw; p.bh = pt.bh;
   p.out = out_small; p.bias = bias; p.out_f32 = tf32 ? 1 : 0; p.out_atomic = 0;
@@ -1558,7 +1578,11 @@ static int conv_down_impl(const dm_conv_geom* g, const void* big, const void* w_
   if (int rc = encode_act_map(&p.map_a, big, g->batch, g->hb, g->wb, g->cb, g->stride, box, p.kc * esz, tf32)) return rc;
   p.cg2 = (!tf32 && env_int("DM_CG2", 1) != 0 && pt.tiles >= 2 && p.bn >= 32) ? 1 : 0;
   const int cluster = p.cg2 ? 2 : 1;
-  if (int rc = encode_w_map3(&p.map_b, w_down, 25, g->cs, g->cb, g->cb, p.kc, p.bn / cluster, p.kc * esz, tf32)) return rc;
+  if (paired) {
+    if (int rc = encode_w_map3(&p.map_b, w_down, 15, g->cs, 64, 64, 64, p.bn / cluster, 128, false)) return rc;
+  } else {
+    if (int rc = encode_w_map3(&p.map_b, w_down, 25, g->cs, g->cb, g->cb, p.kc, p.bn / cluster, p.kc * esz, tf32)) return rc;
+  }
   p.num_n_tiles = (g->cs + p.bn - 1) / p.bn;
   epi_rows_act(p, out_small, tf32, g->batch, g->hs, g->ws, g->cs, 1, pt);
   if (bn && bn->scratch) {
@@ -1574,6 +1598,11 @@ extern "C" int dm_conv_down(const dm_conv_geom* g, const void* big, const void* 
   return conv_down_impl(g, big, w_down, bias, out_small, bn, false, stream_);
 }
 // TF32 precision mode: big / w_down / out_small are fp32 (same layouts), tensor-core arithmetic in TF32, fp32 accumulate
+extern "C" int dm_conv_down_paired(const dm_conv_geom* g, const void* big, const void* w_pair, const float* bias,
+                                  void* out_small, const dm_bn_fuse* bn, void* stream_) {
+  return conv_down_impl(g, big, w_pair, bias, out_small, bn, false, stream_, true);
+}
+
 extern "C" int dm_conv_down_tf32(const dm_conv_geom* g, const void* big, const void* w_down, const float* bias,
                                  void* out_small, void* stream_) {
   return conv_down_impl(g, big, w_down, bias, out_small, nullptr, true, stream_);

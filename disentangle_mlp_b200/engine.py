@@ -70,13 +70,24 @@ def pack3(w, stride, out=None):
 
 
 def _conv_pack(cache, name, p, cs, cb):
-    """(w_down [25][cs][cb], w_up [25][cb_pad][cs], None); for the three 3-channel layers (None, w_up, w_win): pack3"""
+    """(w_down [25][cs][cb], w_up [25][cb_pad][cs], w_pair [15][cs][64] for cb = 32 else None); for the three 3-channel
+    layers (None, w_up, w_win): pack3"""
     static = getattr(cache, "static_packs", None)
     if static is not None:  # fused trainers: persistent buffers refreshed in place after every optimizer step
         return static[name]
     if cb == 3:
         return cache.get(("conv", name), p, lambda w: pack3(w, CONV3_STRIDE[name]))
-    return cache.get(("conv", name), p, lambda w: ops.pack_conv_weights(w.contiguous(), cs, cb, True, True, False))
+
+    def build(w):
+        w_down, w_up, _ = ops.pack_conv_weights(w.contiguous(), cs, cb, True, True, False)
+        return (w_down, w_up, ops.pack_down_pairs(w_down, cs, cb) if ops.down_paired(cb, 2) else None)
+
+    return cache.get(("conv", name), p, build)
+
+
+def _down_w(packs):
+    """the conv_down operand of a _conv_pack() triple: the paired pack [15][cs][64] where the layer has one"""
+    return packs[0] if packs[2] is None else packs[2]
 
 
 # ------------------------------------------------------------------------------------------ BatchNorm helper
@@ -323,7 +334,7 @@ def discriminator_forward(x, P, B, cache: OperandCache, training=True, groups=1,
     raw1 = ops.conv3_fwd(ops.geom(b, 64, 64, 32, 3, 1), S.pim, ww1, P["convs.0.bias"].detach(), bn=f1)
     S.a1, S.bn1 = bn_act_forward(raw1, b * 4096, 32, P, B, "convs.1", ACT_LEAKY, training, groups, cache, f1)
     g2 = ops.geom(b, 32, 32, 128, 32, 2)
-    wd2, _, _ = _conv_pack(cache, "convs.3", P["convs.3.weight"], 128, 32)
+    wd2 = _down_w(_conv_pack(cache, "convs.3", P["convs.3.weight"], 128, 32))
     f2 = bn_fuse(cache, P, B, "convs.4", 128, groups, bg * 1024, dev, training)
     raw2 = ops.conv_down(g2, S.a1, wd2, P["convs.3.bias"].detach(), bn=f2)
     S.a2, S.bn2 = bn_act_forward(raw2, b * 1024, 128, P, B, "convs.4", ACT_LEAKY, training, groups, cache, f2)
@@ -571,7 +582,7 @@ def decoder_backward(S, drecon, P, G, cache: OperandCache, need_dcode=True, need
     da3 = ops.conv3_fwd(g4, pim4, ww4, None)  # ConvT input-gradient = conv of dy with the same weights
     dr3 = bn_act_backward(da3, S.bn3, wg, "act3.0", cache)
     g3 = ops.geom(b, 32, 32, 128, 32, 2)
-    wd3, _, _ = _conv_pack(cache, "deconv3", P["deconv3.weight"], 128, 32)
+    wd3 = _down_w(_conv_pack(cache, "deconv3", P["deconv3.weight"], 128, 32))
     if wg:
         conv_wgrad(g3, S.a2, dr3, wg["deconv3.weight"], cache, "deconv3")
     da2 = ops.conv_down(g3, dr3, wd3)

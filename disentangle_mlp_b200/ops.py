@@ -83,9 +83,26 @@ def _bn_ref(bn):
     return None if f is None else C.byref(f)
 
 
+def down_paired(g_cb, stride) -> bool:
+    """Layers whose stride-2 convolution runs with two filter columns per k-block (dm_conv_down_paired)."""
+    return stride == 2 and g_cb == 32 and os.environ.get("DM_DOWN_PAIR", "1") != "0"
+
+
+def pack_down_pairs(w_down, cs, cb, out=None):
+    """w_down [25][cs][cb = 32] -> w_pair [15][cs][64] (see dm_pack_down_pairs)."""
+    if out is None:
+        out = torch.empty((15, cs, 2 * cb), dtype=BF16, device=w_down.device)
+    _lib.check(_lib.load().dm_pack_down_pairs(_p(w_down), cs, cb, _p(out), _stream()), "dm_pack_down_pairs")
+    return out
+
+
 def conv_down(g: ConvGeom, big, w_down, bias=None, out=None, bn=None):
     if out is None:
         out = torch.empty((g.batch, g.hs, g.ws, g.cs), dtype=BF16, device=big.device)
+    if w_down.shape[0] == 15:  # paired pack
+        _lib.check(_lib.load().dm_conv_down_paired(C.byref(g), _p(big), _p(w_down), _p(bias), _p(out), _bn_ref(bn),
+                                                   _stream()), "dm_conv_down_paired")
+        return out
     _lib.check(_lib.load().dm_conv_down(C.byref(g), _p(big), _p(w_down), _p(bias), _p(out), _bn_ref(bn), _stream()),
                "dm_conv_down")
     return out

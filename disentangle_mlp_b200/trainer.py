@@ -154,7 +154,8 @@ class FlatParams:
                     if ops.up_merged(cb, 2):  # conv_up reads the phase-merged pack [9][4cb][cs]; w_up is its source
                         self._up_std[n[:-len(".weight")]] = w_up
                         w_up = torch.empty((9, 4 * cb, cs), dtype=BF16, device=dev)
-                    self.cache.static_packs[n[:-len(".weight")]] = (w_down, w_up, None)
+                    w_pair = torch.empty((15, cs, 64), dtype=BF16, device=dev) if ops.down_paired(cb, 2) else None
+                    self.cache.static_packs[n[:-len(".weight")]] = (w_down, w_up, w_pair)
                 else:
                     self.cache.static_packs[n[:-len(".weight")]] = engine.pack3(
                         p.detach(), engine.CONV3_STRIDE[n[:-len(".weight")]])
@@ -235,6 +236,8 @@ class FlatParams:
                     ops.pack_up_merged(self._up_std[name], p.shape[0], p.shape[1], out=packs[1])
                 else:
                     ops.transpose(packs[0], 25, p.shape[0], p.shape[1], out=packs[1])
+                if packs[2] is not None:
+                    ops.pack_down_pairs(packs[0], p.shape[0], p.shape[1], out=packs[2])
             else:
                 engine.pack3(p.detach(), engine.CONV3_STRIDE[name], out=packs)
 

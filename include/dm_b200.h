@@ -104,6 +104,14 @@ int dm_conv_up(const dm_conv_geom* g, const void* small, const void* w_up, const
  * gradient of Conv2d(32, 128), model.py:391): w_upm = dm_pack_up_merged(w_up) is [9][4*cb][cs]; one GEMM with N = 128
  * computes the four sub-pixel phases from 9 shared input taps.  Output bf16 NHWC like dm_conv_up. */
 int dm_pack_up_merged(const void* w_up, int cs, int cb, void* w_upm, void* stream);
+
+/* The stride-2 convolution with 32 input channels (Conv2d(32, 128), model.py:391; the input-gradient of
+ * ConvTranspose2d(128, 32), model.py:500) with TWO filter columns per k-block: w_pair = dm_pack_down_pairs(w_down) is
+ * [15][cs][64] (filter row kh, column pair j: columns 2j, 2j+1; the sixth column is zero); the A operand row is one
+ * 128-byte run of the NHWC tensor (two adjacent pixels x 32 channels).  Same arguments as dm_conv_down otherwise. */
+int dm_pack_down_pairs(const void* w_down, int cs, int cb, void* w_pair, void* stream);
+int dm_conv_down_paired(const dm_conv_geom* g, const void* big, const void* w_pair, const float* bias, void* out_small,
+                        const dm_bn_fuse* bn, void* stream);
 int dm_conv_up_merged(const dm_conv_geom* g, const void* small, const void* w_upm, const float* bias, void* out_big,
                       const dm_bn_fuse* bn, void* stream);
 

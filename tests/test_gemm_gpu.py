@@ -40,6 +40,41 @@ def test_conv_up_c32_unmerged(monkeypatch):
     assert rel < 4e-3, rel
 
 
+@pytest.mark.parametrize("batch,groups", [(4, 1), (64, 1), (96, 3)])
+def test_conv_down_paired_c32(batch, groups):
+    """Conv2d(32, 128, 5, stride 2, pad 2) (model.py:391) with two filter columns per k-block (dm_conv_down_paired,
+    K = 64 rows of the parity view) against torch on the same bf16 operands, and against the one-column form."""
+    import torch
+    import torch.nn.functional as F
+
+    from disentangle_mlp_b200 import ops
+
+    torch.manual_seed(3)
+    cs, cb, hs = 128, 32, 32
+    x = torch.randn(batch, cb, 2 * hs, 2 * hs, device="cuda").bfloat16()
+    w = (torch.randn(cs, cb, 5, 5, device="cuda") * 0.05).bfloat16()
+    bias = torch.randn(cs, device="cuda") * 0.1
+    ref = F.conv2d(x.float(), w.float(), bias, stride=2, padding=2).permute(0, 2, 3, 1)
+    g = ops.geom(batch, hs, hs, cs, cb, 2)
+    wd, _, _ = ops.pack_conv_weights(w.float(), cs, cb)
+    wp = ops.pack_down_pairs(wd, cs, cb)
+    assert wp.shape == (15, cs, 64)
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    y_pair = ops.conv_down(g, xn, wp, bias).float()
+    y_one = ops.conv_down(g, xn, wd, bias).float()
+    rel = float((y_pair - ref).norm() / ref.norm())
+    assert rel < 4e-3, rel
+    assert float((y_pair - y_one).norm() / y_one.norm()) < 4e-3
+    if groups > 1 or batch >= 64:  # statistics in the epilogue ride along unchanged
+        site = ops.BnSite(ops.bn_scratch(cs, groups, "cuda"), groups, batch // groups * hs * hs, cs,
+                          torch.ones(cs, device="cuda"), torch.zeros(cs, device="cuda"), torch.zeros(cs, device="cuda"),
+                          torch.ones(cs, device="cuda"), torch.zeros((), dtype=torch.int64, device="cuda"), 0.1, 1e-5)
+        ops.conv_down(g, xn, wp, bias, bn=site)
+        mean = ref.reshape(groups, -1, cs).mean(1)
+        got = site.mean_invstd.view(groups, 2, cs)[:, 0]
+        assert float((got - mean).abs().max()) < 2e-3 * float(ref.abs().max())
+
+
 def test_full_size_layers_linearity_and_batch_independence():
     """Full BASELINE sizes (batch 128): conv(x1 + x2) == conv(x1) + conv(x2) on bf16-exact inputs, and the
     result for image i does not depend on the other images in the batch."""

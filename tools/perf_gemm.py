@@ -48,6 +48,9 @@ def cases(b):
         dw = torch.zeros(cs, cb, 5, 5, device=dev)
         tag = f"{cb}->{cs} {hs * stride}->{hs}"
         out.append((f"down  {tag}", fl, lambda g=g, big=big, w_down=w_down, o_s=o_s: ops.conv_down(g, big, w_down, None, out=o_s)))
+        if cb == 32 and stride == 2:
+            w_pair = ops.pack_down_pairs(w_down, cs, cb)
+            out.append((f"downP {tag}", fl, lambda g=g, big=big, w_pair=w_pair, o_s=o_s: ops.conv_down(g, big, w_pair, None, out=o_s)))
         out.append((f"up    {tag}", fl, lambda g=g, small=small, w_up=w_up, o_b=o_b: ops.conv_up(g, small, w_up, None, out=o_b)))
         out.append((f"wgrad {tag}", fl, lambda g=g, small=small, big=big, dw=dw: ops.conv_wgrad(g, small, big, dw)))
         pk = torch.zeros(25, cs, cb, device=dev)
