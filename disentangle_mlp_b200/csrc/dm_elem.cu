@@ -509,13 +509,18 @@ __global__ void __launch_bounds__(256) bn1d_fwd_kernel(const T* __restrict__ y, 
                                                        float* running_var, long long* num_batches_tracked, float momentum,
                                                        float eps, int act, float slope, float* __restrict__ scale_shift,
                                                        float* __restrict__ mean_invstd, __nv_bfloat16* __restrict__ out,
-                                                       int groups) {
+                                                       int groups, long long ld_y, const float* __restrict__ pre_bias) {
+  // ld_y: row stride of y (>= c: y may be a column block of a wider matrix, e.g. one head of a fused two-head GEMM);
+  // pre_bias: the Linear bias the producing GEMM did NOT add: normalised as if y + pre_bias had been stored, while the
+  // saved constants (mean, shift) are expressed for the stored y, which is what the backward pass reads
   pdl_sync();
   __shared__ float red[64][33];
   __shared__ float stat[32];
   const int ch = (blockIdx.x * 4 + threadIdx.x) * 8;  // c is a multiple of 32: every thread is live
+  float pb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (pre_bias) load8(pre_bias + ch, pb);
   for (int g = 0; g < groups; ++g) {
-    const T* yg = y + static_cast<long long>(g) * rows * c;
+    const T* yg = y + static_cast<long long>(g) * rows * ld_y;
     __nv_bfloat16* og = out + static_cast<long long>(g) * rows * c;
     float v[4][8];
     float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -523,7 +528,7 @@ __global__ void __launch_bounds__(256) bn1d_fwd_kernel(const T* __restrict__ y, 
     for (int j = 0; j < 4; ++j) {
       const int r = threadIdx.y + 64 * j;
       if (r < rows) {
-        load8(yg + static_cast<long long>(r) * c + ch, v[j]);
+        load8(yg + static_cast<long long>(r) * ld_y + ch, v[j]);
 #pragma unroll
         for (int i = 0; i < 8; ++i) s[i] += v[j][i];
       }
@@ -551,10 +556,10 @@ __global__ void __launch_bounds__(256) bn1d_fwd_kernel(const T* __restrict__ y, 
       const float var = q[i] / static_cast<float>(rows);
       is[i] = rsqrtf(var + eps);
       sc[i] = gamma[ch + i] * is[i];
-      sh[i] = beta[ch + i] - mean[i] * sc[i];
+      sh[i] = beta[ch + i] - mean[i] * sc[i];  // (mean of the STORED y: the bias cancels in the normalisation)
       if (threadIdx.y == 0 && running_mean) {
         const float unbiased = rows > 1 ? var * static_cast<float>(rows) / static_cast<float>(rows - 1) : var;
-        running_mean[ch + i] = (1.f - momentum) * running_mean[ch + i] + momentum * mean[i];
+        running_mean[ch + i] = (1.f - momentum) * running_mean[ch + i] + momentum * (mean[i] + pb[i]);
         running_var[ch + i] = (1.f - momentum) * running_var[ch + i] + momentum * unbiased;
       }
     }
@@ -585,7 +590,8 @@ __global__ void __launch_bounds__(256) bn1d_bwd_kernel(const __nv_bfloat16* __re
                                                        int rows, int c, const float* __restrict__ scale_shift,
                                                        const float* __restrict__ mean_invstd, int act, float slope,
                                                        __nv_bfloat16* __restrict__ dy, float* dgamma, float* dbeta,
-                                                       int groups) {
+                                                       int groups, long long ld_y, long long ld_dy) {
+  // ld_y / ld_dy: row strides of y and dy (>= c: column blocks of wider matrices); dout is dense [rows, c]
   pdl_sync();
   __shared__ float red[64][33];
   __shared__ float stat[32];
@@ -607,7 +613,7 @@ __global__ void __launch_bounds__(256) bn1d_bwd_kernel(const __nv_bfloat16* __re
       const int r = threadIdx.y + 64 * j;
       if (r < rows) {
         float f[8], gg[8];
-        load8(y + off + static_cast<long long>(r) * c + ch, f);
+        load8(y + static_cast<long long>(g) * rows * ld_y + static_cast<long long>(r) * ld_y + ch, f);
         load8(dout + off + static_cast<long long>(r) * c + ch, gg);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -633,7 +639,7 @@ __global__ void __launch_bounds__(256) bn1d_bwd_kernel(const __nv_bfloat16* __re
         float o[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = sc[i] * (dz[j][i] - a0[i] * inv_n - xh[j][i] * a1[i] * inv_n);
-        store8(dy + off + static_cast<long long>(r) * c + ch, o);
+        store8(dy + static_cast<long long>(g) * rows * ld_dy + static_cast<long long>(r) * ld_dy + ch, o);
       }
     }
   }
@@ -1355,11 +1361,13 @@ extern "C" int dm_bn_forward(const void* y, int y_f32, long long rows, int c, co
     if (y_f32)
       launch_pdl(bn1d_fwd_kernel<float>, c / 32, dim3(4, 64), 0, s, static_cast<const float*>(y), static_cast<int>(rows), c, gamma, beta,
                                                            running_mean, running_var, num_batches_tracked, momentum, eps, act,
-                                                           slope, scale_shift, mean_invstd, static_cast<bf16*>(out_bf16), groups);
+                                                           slope, scale_shift, mean_invstd, static_cast<bf16*>(out_bf16), groups,
+                                                           static_cast<long long>(c), static_cast<const float*>(nullptr));
     else
       launch_pdl(bn1d_fwd_kernel<bf16>, c / 32, dim3(4, 64), 0, s, static_cast<const bf16*>(y), static_cast<int>(rows), c, gamma, beta,
                                                           running_mean, running_var, num_batches_tracked, momentum, eps, act,
-                                                          slope, scale_shift, mean_invstd, static_cast<bf16*>(out_bf16), groups);
+                                                          slope, scale_shift, mean_invstd, static_cast<bf16*>(out_bf16), groups,
+                                                          static_cast<long long>(c), static_cast<const float*>(nullptr));
     DM_LAUNCHED("dm_bn_forward(1d)");
   }
   DM_REQUIRE(scratch != nullptr, "dm_bn_forward: scratch required for rows > %d", kBn1dMaxRows);
@@ -1369,6 +1377,33 @@ extern "C" int dm_bn_forward(const void* y, int y_f32, long long rows, int c, co
   f.momentum = momentum; f.eps = eps; f.scale_shift = scale_shift; f.mean_invstd = mean_invstd;
   if (int rc = dm_bn_stats(y, y_f32, c, &f, stream_)) return rc;
   return dm_bn_apply_act(y, y_f32, rows, c, scale_shift, act, slope, out_bf16, groups, stream_);
+}
+
+// Small-row BatchNorm (rows <= 256) on a COLUMN BLOCK of a wider fp32 matrix: y = base + column offset, row stride ld_y.
+// Used for the encoder's two heads computed by one N = 4096 GEMM (model.py:460-471): pre_bias = the head's Linear bias,
+// which that GEMM does not add.  One pass (groups = 1).
+extern "C" int dm_bn1d_forward(const float* y, long long ld_y, int rows, int c, const float* pre_bias, const float* gamma,
+                               const float* beta, float* running_mean, float* running_var,
+                               long long* num_batches_tracked, float momentum, float eps, int act, float slope,
+                               float* scale_shift, float* mean_invstd, void* out_bf16, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  DM_REQUIRE(bn1d_ok(rows, c) && ld_y >= c && ld_y % 8 == 0, "dm_bn1d_forward: rows %d (<= %d), c %d (%% 32), ld %lld", rows,
+             kBn1dMaxRows, c, ld_y);
+  launch_pdl(bn1d_fwd_kernel<float>, c / 32, dim3(4, 64), 0, s, y, rows, c, gamma, beta, running_mean, running_var,
+             num_batches_tracked, momentum, eps, act, slope, scale_shift, mean_invstd, static_cast<bf16*>(out_bf16), 1, ld_y,
+             pre_bias);
+  DM_LAUNCHED("dm_bn1d_forward");
+}
+
+extern "C" int dm_bn1d_backward(const void* dout_bf16, const float* y, long long ld_y, int rows, int c,
+                                const float* scale_shift, const float* mean_invstd, int act, float slope, void* dy_bf16,
+                                long long ld_dy, float* dgamma, float* dbeta, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  DM_REQUIRE(bn1d_ok(rows, c) && ld_y >= c && ld_dy >= c && ld_y % 8 == 0 && ld_dy % 8 == 0,
+             "dm_bn1d_backward: rows %d (<= %d), c %d (%% 32), ld %lld / %lld", rows, kBn1dMaxRows, c, ld_y, ld_dy);
+  launch_pdl(bn1d_bwd_kernel<float>, c / 32, dim3(4, 64), 0, s, static_cast<const bf16*>(dout_bf16), y, rows, c, scale_shift,
+             mean_invstd, act, slope, static_cast<bf16*>(dy_bf16), dgamma, dbeta, 1, ld_y, ld_dy);
+  DM_LAUNCHED("dm_bn1d_backward");
 }
 
 extern "C" int dm_bn_backward(const void* dout_bf16, const void* y, int y_f32, long long rows, int c,
@@ -1382,10 +1417,12 @@ extern "C" int dm_bn_backward(const void* dout_bf16, const void* y, int y_f32, l
   if (bn1d_ok(rows, c)) {
     if (y_f32)
       launch_pdl(bn1d_bwd_kernel<float>, c / 32, dim3(4, 64), 0, s, d, static_cast<const float*>(y), static_cast<int>(rows), c, scale_shift,
-                                                           mean_invstd, act, slope, static_cast<bf16*>(dy_bf16), dgamma, dbeta, groups);
+                                                           mean_invstd, act, slope, static_cast<bf16*>(dy_bf16), dgamma, dbeta, groups,
+                                                           static_cast<long long>(c), static_cast<long long>(c));
     else
       launch_pdl(bn1d_bwd_kernel<bf16>, c / 32, dim3(4, 64), 0, s, d, static_cast<const bf16*>(y), static_cast<int>(rows), c, scale_shift,
-                                                          mean_invstd, act, slope, static_cast<bf16*>(dy_bf16), dgamma, dbeta, groups);
+                                                          mean_invstd, act, slope, static_cast<bf16*>(dy_bf16), dgamma, dbeta, groups,
+                                                          static_cast<long long>(c), static_cast<long long>(c));
     DM_LAUNCHED("dm_bn_backward(1d)");
   }
   DM_REQUIRE(scratch != nullptr, "dm_bn_backward: scratch required for rows > %d", kBn1dMaxRows);

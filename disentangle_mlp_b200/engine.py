@@ -55,6 +55,29 @@ def _lin_w(cache, name, p):
     return cache.get(("lin", name), p, lambda w: ops.cast_bf16(w.contiguous()))
 
 
+FUSE_HEADS = os.environ.get("DM_FUSE_HEADS", "1") != "0"
+HEADS = ("x_to_mu", "x_to_logvar")
+
+
+def _stacked_rows(a, b):
+    """[a; b] as ONE matrix when b's rows follow a's in the same buffer (views of a flat parameter / gradient buffer),
+    else None."""
+    if a is None or b is None or a.dtype != b.dtype or a.shape != b.shape or not (a.is_contiguous() and b.is_contiguous()):
+        return None
+    if b.data_ptr() != a.data_ptr() + a.numel() * a.element_size():
+        return None
+    return a.as_strided((2 * a.shape[0], a.shape[1]), (a.shape[1], 1))
+
+
+def _heads_weight(cache, P):
+    """The two heads' 16384 -> 2048 weights as one [4096, 16384] bf16 operand (fused trainers: adjacent in the optimizer's
+    bf16 shadow), or None (module path: separate casts)."""
+    views = getattr(cache, "lin_views", None)
+    if not FUSE_HEADS or views is None:
+        return None
+    return _stacked_rows(views.get(HEADS[0] + ".0.weight"), views.get(HEADS[1] + ".0.weight"))
+
+
 CONV3_STRIDE = {"convs.0": 1, "features.0": 2, "deconv4": 1}  # the three layers on the 3-channel image side
 
 
@@ -467,10 +490,23 @@ def encoder_forward(x, P, B, cache: OperandCache, training=True, pim=None, befor
         before_heads()
     outs = []
     S.heads = {}
-    for head in ("x_to_mu", "x_to_logvar"):
-        w0 = _lin_w(cache, head + ".0", P[head + ".0.weight"])
-        acc = linear_forward(S.flat, w0, P[head + ".0.bias"].detach(), b, 2048, 16384)
-        h1, bn = bn_act_forward(acc, b, 2048, P, B, head + ".1", ACT_RELU, training, 1, cache)
+    wcat = _heads_weight(cache, P) if (training and b <= ops.BN1D_MAX_ROWS) else None
+    S.acc_cat = None
+    if wcat is not None:
+        # both heads' first Linear as ONE GEMM over their stacked weights (N = 4096): one pass over the activations, half
+        # the launches; the per-head BatchNorm1d reads its column block and adds the head's Linear bias itself
+        S.acc_cat = linear_forward(S.flat, wcat, None, b, 4096, 16384)
+    for i, head in enumerate(HEADS):
+        if wcat is not None:
+            h1, ss, mi = ops.bn1d_forward_cols(S.acc_cat, i * 2048, 2048, P[head + ".0.bias"].detach(),
+                                               P[head + ".1.weight"].detach(), P[head + ".1.bias"].detach(),
+                                               B[head + ".1.running_mean"], B[head + ".1.running_var"],
+                                               B[head + ".1.num_batches_tracked"], ACT_RELU, LEAKY, BN_MOMENTUM, BN_EPS)
+            bn = SimpleNamespace(scale_shift=ss, mean_invstd=mi)
+        else:
+            w0 = _lin_w(cache, head + ".0", P[head + ".0.weight"])
+            acc = linear_forward(S.flat, w0, P[head + ".0.bias"].detach(), b, 2048, 16384)
+            h1, bn = bn_act_forward(acc, b, 2048, P, B, head + ".1", ACT_RELU, training, 1, cache)
         w3 = _lin_w(cache, head + ".3", P[head + ".3.weight"])
         out = linear_forward(h1, w3, P[head + ".3.bias"].detach(), b, 128, 2048)
         S.heads[head] = SimpleNamespace(h1=h1, bn=bn)
@@ -486,8 +522,14 @@ def encoder_backward(S, dmu, dlogvar, P, G, cache: OperandCache, need_wgrad=True
     b = S.b
     dev = S.flat.device
     wg = G if need_wgrad else None
-    dflat = torch.zeros((b, 16384), dtype=F32, device=dev)
-    for head, d in (("x_to_mu", dmu), ("x_to_logvar", dlogvar)):
+    fused = getattr(S, "acc_cat", None) is not None
+    wcat = _heads_weight(cache, P) if fused else None
+    gcat = _stacked_rows(wg[HEADS[0] + ".0.weight"], wg[HEADS[1] + ".0.weight"]) if (fused and wg) else None
+    assert not fused or (wcat is not None and (gcat is not None or not wg)), \
+        "fused heads: the two 16384x2048 weights / gradients must be adjacent in the flat buffers"
+    dflat = None if fused else torch.zeros((b, 16384), dtype=F32, device=dev)
+    dacc_cat = torch.empty((b, 4096), dtype=BF16, device=dev) if fused else None
+    for i, (head, d) in enumerate((("x_to_mu", dmu), ("x_to_logvar", dlogvar))):
         H = S.heads[head]
         if d is None:
             d = torch.zeros((b, 128), dtype=F32, device=dev)
@@ -498,6 +540,10 @@ def encoder_backward(S, dmu, dlogvar, P, G, cache: OperandCache, need_wgrad=True
             linear_wgrad(d16, H.h1, b, 128, 2048, wg[head + ".3.weight"])
         w3 = _lin_w(cache, head + ".3", P[head + ".3.weight"])
         dh1 = linear_dgrad(d16, w3, b, 128, 2048)
+        if fused:
+            ops.bn1d_backward_cols(dh1, S.acc_cat, i * 2048, 2048, H.bn.scale_shift, H.bn.mean_invstd, ACT_RELU, LEAKY,
+                                   dacc_cat, wg[head + ".1.weight"] if wg else None, wg[head + ".1.bias"] if wg else None)
+            continue
         dacc = bn_act_backward(dh1, H.bn, wg, head + ".1", cache)
         w0 = _lin_w(cache, head + ".0", P[head + ".0.weight"])
         if wg:
@@ -507,9 +553,22 @@ def encoder_backward(S, dmu, dlogvar, P, G, cache: OperandCache, need_wgrad=True
                     grad_ready(head_ + ".0.weight")
             WgradSide.run(big_wgrad, dacc, S.flat, wg[head + ".0.weight"], big=True)
         linear_dgrad(dacc, w0, b, 2048, 16384, out_dtype=F32, out=dflat)
+    if fused:
+        # one weight-gradient GEMM into the two (adjacent) gradients, one input-gradient GEMM over K = 4096 written
+        # straight in bf16 (no fp32 accumulation buffer, no cast)
+        if wg:
+            def big_wgrad(dacc_, flat_, dw_):
+                linear_wgrad(dacc_, flat_, b, 4096, 16384, dw_, overwrite_big)
+                if grad_ready:
+                    for head in HEADS:
+                        grad_ready(head + ".0.weight")
+            WgradSide.run(big_wgrad, dacc_cat, S.flat, gcat, big=True)
+        dflat16 = linear_dgrad(dacc_cat, wcat, b, 4096, 16384)
+    else:
+        dflat16 = None
     if heads_done:
         heads_done()
-    da3 = ops.transpose(ops.cast_bf16(dflat), b, 256, 64)
+    da3 = ops.transpose(dflat16 if fused else ops.cast_bf16(dflat), b, 256, 64)
     dr3 = bn_act_backward(da3, S.bn3, wg, "features.7", cache)
     g3 = ops.geom(b, 8, 8, 256, 128, 2)
     _, wu3, _ = _conv_pack(cache, "features.6", P["features.6.weight"], 256, 128)

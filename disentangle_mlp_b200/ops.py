@@ -326,6 +326,31 @@ def bn_backward(dout, y, rows, c, scale_shift, mean_invstd, act, slope=0.2, dgam
     return dy
 
 
+def bn1d_forward_cols(acc, col0, c, pre_bias, gamma, beta, running_mean, running_var, nbt, act, slope=0.2, momentum=0.1,
+                      eps=1e-5):
+    """BatchNorm1d + activation of columns [col0, col0 + c) of the fp32 matrix acc [rows, ld] (dm_bn1d_forward).
+    Returns (out bf16 [rows, c], scale_shift [2,c], mean_invstd [2,c]) -- constants for the STORED (bias-less) values."""
+    rows, ld = acc.shape
+    assert acc.dtype == F32 and acc.is_contiguous() and rows <= BN1D_MAX_ROWS
+    out = torch.empty((rows, c), dtype=BF16, device=acc.device)
+    ss = torch.empty((2, c), dtype=F32, device=acc.device)
+    mi = torch.empty((2, c), dtype=F32, device=acc.device)
+    _lib.check(_lib.load().dm_bn1d_forward(acc.data_ptr() + 4 * col0, ld, rows, c, _p(pre_bias), _p(gamma), _p(beta),
+                                           _p(running_mean), _p(running_var), _p(nbt), momentum, eps, act, slope, _p(ss),
+                                           _p(mi), _p(out), _stream()), "dm_bn1d_forward")
+    return out, ss, mi
+
+
+def bn1d_backward_cols(dout, acc, col0, c, scale_shift, mean_invstd, act, slope, dy, dgamma=None, dbeta=None):
+    """Backward of bn1d_forward_cols: dout bf16 [rows, c] dense; dy bf16 [rows, ld_dy] receives columns [col0, col0+c)."""
+    rows, ld = acc.shape
+    assert dout.dtype == BF16 and dout.is_contiguous() and dy.dtype == BF16 and dy.is_contiguous()
+    _lib.check(_lib.load().dm_bn1d_backward(_p(dout), acc.data_ptr() + 4 * col0, ld, rows, c, _p(scale_shift),
+                                            _p(mean_invstd), act, slope, dy.data_ptr() + 2 * col0, dy.shape[1], _p(dgamma),
+                                            _p(dbeta), _stream()), "dm_bn1d_backward")
+    return dy
+
+
 def bias_act(acc, rows, c, bias, act, slope=0.2, want_f32=True, want_bf16=True):
     out_f32 = torch.empty((rows, c), dtype=F32, device=acc.device) if want_f32 else None
     out_bf16 = torch.empty((rows, c), dtype=BF16, device=acc.device) if want_bf16 else None

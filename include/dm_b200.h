@@ -174,6 +174,17 @@ int dm_bn_forward(const void* y, int y_f32, long long rows, int c, const float* 
                   float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
                   int act, float slope, float* scratch, float* scale_shift, float* mean_invstd, void* out_bf16,
                   int groups, void* stream);
+/* nn.BatchNorm1d (training) + activation on a COLUMN BLOCK of a wider fp32 matrix (row stride ld_y), rows <= 256: the
+ * two heads x_to_mu / x_to_logvar (model.py:460-471) computed by ONE GEMM over their stacked weights [4096][16384].
+ * pre_bias: the head's Linear bias, which that GEMM does not add (it only moves running_mean).  dy of the backward
+ * form goes to a column block of a [rows][ld_dy] matrix (the A operand of the fused input-gradient GEMM). */
+int dm_bn1d_forward(const float* y, long long ld_y, int rows, int c, const float* pre_bias, const float* gamma,
+                    const float* beta, float* running_mean, float* running_var, long long* num_batches_tracked,
+                    float momentum, float eps, int act, float slope, float* scale_shift, float* mean_invstd,
+                    void* out_bf16, void* stream);
+int dm_bn1d_backward(const void* dout_bf16, const float* y, long long ld_y, int rows, int c, const float* scale_shift,
+                     const float* mean_invstd, int act, float slope, void* dy_bf16, long long ld_dy, float* dgamma,
+                     float* dbeta, void* stream);
 int dm_bn_backward(const void* dout_bf16, const void* y, int y_f32, long long rows, int c,
                    const float* scale_shift, const float* mean_invstd, int act, float slope, float* scratch,
                    void* dy_bf16, float* dgamma, float* dbeta, int groups, void* stream);

@@ -397,3 +397,39 @@ def test_adam_segments_and_bf16_gradients(ops):
                           step_dev=step_dev, count_step=(i == 0))
     assert int(step_dev) == 4
     assert rel(p, ref.detach()) < 1e-6 and torch.equal(shadow, p.bfloat16())
+
+
+@pytest.mark.parametrize("rows", [8, 64, 200])
+def test_bn1d_on_column_blocks_with_pre_bias(ops, rows):
+    """dm_bn1d_forward / dm_bn1d_backward: BatchNorm1d + ReLU of one 2048-column block of a wider fp32 matrix whose
+    producing GEMM did not add the Linear bias (the encoder's two heads from one N = 4096 GEMM, model.py:460-471),
+    against torch.nn.functional.batch_norm on (block + bias)."""
+    import torch.nn.functional as F
+
+    torch.manual_seed(rows)
+    c, ld = 2048, 4096
+    acc = torch.randn(rows, ld, device="cuda") * 2 + 0.5
+    for head in range(2):
+        col0 = head * c
+        bias = torch.randn(c, device="cuda")
+        gamma, beta = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda") * 0.1
+        rm, rv = torch.randn(c, device="cuda") * 0.1, torch.rand(c, device="cuda") + 0.5
+        nbt = torch.zeros((), dtype=torch.int64, device="cuda")
+        x = (acc[:, col0:col0 + c] + bias).clone().requires_grad_(True)
+        gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+        rm_ref, rv_ref = rm.clone(), rv.clone()
+        ref = F.relu(F.batch_norm(x, rm_ref, rv_ref, gr, br, True, 0.1, 1e-5))
+        out, ss, mi = ops.bn1d_forward_cols(acc, col0, c, bias, gamma, beta, rm, rv, nbt, 1)
+        assert float((out.float() - ref).norm() / ref.norm()) < 4e-3
+        assert torch.allclose(rm, rm_ref, atol=1e-5, rtol=1e-4) and torch.allclose(rv, rv_ref, atol=1e-5, rtol=1e-4)
+        assert int(nbt) == 1
+        dout = torch.randn(rows, c, device="cuda").bfloat16()
+        ref.backward(dout.float())
+        dy = torch.full((rows, ld), 7.0, device="cuda", dtype=torch.bfloat16)
+        dg, db = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
+        ops.bn1d_backward_cols(dout, acc, col0, c, ss, mi, 1, 0.2, dy, dg, db)
+        got = dy[:, col0:col0 + c].float()
+        assert float((got - x.grad).norm() / x.grad.norm()) < 6e-3
+        other = dy[:, (1 - head) * c:(2 - head) * c]
+        assert bool((other == 7.0).all())  # the other head's columns are untouched
+        assert float((dg - gr.grad).norm() / gr.grad.norm()) < 2e-3 and float((db - br.grad).norm() / br.grad.norm()) < 2e-3
