@@ -541,6 +541,12 @@ def _scalar(dev):
     return torch.zeros((), dtype=F32, device=dev)
 
 
+def _scalars(n, dev):
+    """n zeroed fp32 device scalars from ONE fill (4-byte aligned 0-dim views, which is all the loss kernels need)"""
+    buf = torch.zeros(n, dtype=F32, device=dev)
+    return tuple(buf[i] for i in range(n))
+
+
 class _Base:
     """Common trainer plumbing: label stream, BCE helper, optional whole-step CUDA-graph capture.
 
@@ -829,7 +835,7 @@ class GANTrainer(_Base):
     def _step_impl(self, data, real_label, fake_label, noise=None):
         fg, fd, dev = self.fg, self.fd, data.device
         b = data.shape[0]
-        errD, errG, sum_dx, sum_dgz1, sum_dgz2 = (_scalar(dev) for _ in range(5))
+        errD, errG, sum_dx, sum_dgz1, sum_dgz2 = _scalars(5, dev)
         # ---- (1) discriminator: real batch, then detached fake batch (:84-113).  Both forward passes go through every
         # GEMM together (stacked along the batch); BatchNorm statistics / running stats stay per pass, real first.
         fd.zero_grad()
@@ -899,8 +905,7 @@ class BetaVAEGANTrainer(_Base):
     def _step_impl(self, data, real_label, fake_label, noise=None, eps_dec=None, eps_enc=None):
         feg, fd, dev = self.feg, self.fd, data.device
         b = data.shape[0]
-        (errD_real, errD_fake, sum_dx, errG_fake, errG_recon, sim_loss, loss_dec, kld, loss_enc) = (
-            _scalar(dev) for _ in range(9))
+        (errD_real, errD_fake, sum_dx, errG_fake, errG_recon, sim_loss, loss_dec, kld, loss_enc) = _scalars(9, dev)
         # every image the networks read, as padded bf16 images stacked [data | fake | recon]: each producer writes its
         # slice once, D's stacked passes and the two encoder forwards read them in place (no torch.cat, no im2col)
         # sharded Adam (data parallel): the encoder-phase update of the previous step reaches the other ranks now, under
