@@ -277,9 +277,15 @@ class FlatParams:
             self.wait_big()
             self._big_event = None
         split = (big != "now" or early) and not self.shard and bool(self.big16)
-        for i, (lo, hi, o16) in enumerate(self._segments):
+        # sharded: the big tensors' chunks first, each followed at once by the all-gather of its bf16 shadow -- the NCCL
+        # stream then works under the rest of this call (small tensors, operand packs) and the next phase's convolutions
+        order = sorted(range(len(self._segments)), key=lambda i: (self._segments[i][2] is None) if self.shard else i)
+        eager_gather = self.shard and gather and self.shadow.is_cuda and os.environ.get("DM_EAGER_GATHER", "1") != "0"
+        for k, i in enumerate(order):
+            lo, hi, o16 = self._segments[i]
             if o16 is not None and split:
                 continue
+            full = (lo, hi)
             if o16 is not None and self.shard:
                 a, b = self.reducer.chunk(hi - lo)
                 g = self.grad16[o16 + a:o16 + b]
@@ -287,10 +293,15 @@ class FlatParams:
             else:
                 g = self.grad[lo:hi] if o16 is None else self.grad16[o16:o16 + (hi - lo)]
             ops.adam_step(self.flat[lo:hi], g, self.m[lo:hi], self.v[lo:hi], self.lr, self.betas[0], self.betas[1],
-                          self.eps, 0, grad_scale, self.shadow[lo:hi], step_dev=self.step_dev, count_step=(i == 0))
+                          self.eps, 0, grad_scale, self.shadow[lo:hi], step_dev=self.step_dev, count_step=(k == 0))
+            if o16 is not None and eager_gather:
+                self.reducer.all_gather_async(self.shadow, full[0], full[1] - full[0])
+        if eager_gather:
+            self._gather_pending = False
+            self._gather_event = self.reducer.mark()
         self.refresh_packs()  # bf16 conv operand packs follow the updated fp32 weights
         self.touch()
-        if self.shard:
+        if self.shard and not eager_gather:
             self._gather_pending = True
             if gather:
                 self.gather_if_pending()
