@@ -196,6 +196,7 @@ class FlatParams:
             o = self.off16[name]
             if self.shard:
                 reducer.reduce_scatter_async(self.grad16, o, self.P[name].numel())
+                self._rs_event = reducer.mark() if self.grad16.is_cuda else None
             else:
                 reducer.allreduce_async(self.grad16, o, o + self.P[name].numel())
             return
@@ -224,8 +225,17 @@ class FlatParams:
         self._tail_done = None
 
     def reduce_rest_and_wait(self, reducer):
+        """All-reduce what is still unreduced and order the stream behind the collectives the following adam() needs.
+        Sharded: only behind the reduce-scatters of the big gradients -- adam() updates those chunks first and waits for
+        the small gradients' all-reduce (which then ran under that HBM-bound work) right before it needs them."""
         self.reduce_rest(reducer)
-        reducer.wait()
+        ev = getattr(self, "_rs_event", None)
+        if self.shard and ev is not None and os.environ.get("DM_SPLIT_WAIT", "1") != "0":
+            torch.cuda.current_stream().wait_event(ev)
+            self._rs_event = None
+            self._wait_rest = reducer.mark()  # (an event behind the all-reduce just enqueued, not behind later gathers)
+        else:
+            reducer.wait()
 
     def refresh_packs(self):
         for name, packs in self.cache.static_packs.items():
@@ -281,10 +291,14 @@ class FlatParams:
         # stream then works under the rest of this call (small tensors, operand packs) and the next phase's convolutions
         order = sorted(range(len(self._segments)), key=lambda i: (self._segments[i][2] is None) if self.shard else i)
         eager_gather = self.shard and gather and self.shadow.is_cuda and os.environ.get("DM_EAGER_GATHER", "1") != "0"
+        wait_rest, self._wait_rest = getattr(self, "_wait_rest", None), None
         for k, i in enumerate(order):
             lo, hi, o16 = self._segments[i]
             if o16 is not None and split:
                 continue
+            if o16 is None and wait_rest is not None:  # (reduce_rest_and_wait: the small gradients are needed from here)
+                torch.cuda.current_stream().wait_event(wait_rest)
+                wait_rest = None
             full = (lo, hi)
             if o16 is not None and self.shard:
                 a, b = self.reducer.chunk(hi - lo)
@@ -296,6 +310,8 @@ class FlatParams:
                           self.eps, 0, grad_scale, self.shadow[lo:hi], step_dev=self.step_dev, count_step=(k == 0))
             if o16 is not None and eager_gather:
                 self.reducer.all_gather_async(self.shadow, full[0], full[1] - full[0])
+        if wait_rest is not None:
+            torch.cuda.current_stream().wait_event(wait_rest)
         if eager_gather:
             self._gather_pending = False
             self._gather_event = self.reducer.mark()
@@ -719,6 +735,8 @@ class _Base:
             for fp in fps:
                 fp._gather_event = None
                 fp._big_event = None
+                fp._rs_event = None
+                fp._wait_rest = None
             self.dist.cuda_pending = False
         self.graph_launches_per_step = _lib.launch_count() - l0  # libdm_b200 kernels captured in one step
         self._adams_per_step = [fp.step_count - c for fp, c in zip(fps, counts0)]
@@ -958,11 +976,11 @@ class BetaVAEGANTrainer(_Base):
         engine.discriminator_backward(S12, dprob, None, fd.P, fd.G, fd.cache, False, True, overwrite_big=True,
                                       grad_ready=self._early(fd), linear_done=self._heads_done(fd) if stack else None)
         del S12
-        fd.reduce_rest(self.dist)  # data parallel: D's gradient all-reduce runs on the NCCL stream ...
         if stack:
-            self.dist.wait()
+            fd.reduce_rest_and_wait(self.dist)  # data parallel: D's gradient all-reduce runs on the NCCL stream
             fd.adam()
         else:
+            fd.reduce_rest(self.dist)
             # ... and D's Adam update (HBM-bound) runs on a side stream, both under the tensor-bound encoder / decoder
             # forward below
             fork = self._fork_side(lambda: (self.dist.wait(), fd.adam()))
