@@ -154,3 +154,20 @@ def test_flat_layout_and_reduce_schedule_cover_every_gradient_once(bf16_big):
                 assert (cover32[o:o + k] == 1).all(), n
         assert len(red.calls) == len(early_names) + (1 if tail else 0) + 1
         assert fp._tail_done is None  # reset for the next phase
+
+
+def test_the_two_head_weights_are_adjacent_in_the_flat_buffers():
+    """engine.encoder_forward / encoder_backward run x_to_mu | x_to_logvar as ONE N = 4096 GEMM over the two 16384x2048
+    weights (and one weight-gradient GEMM into their gradients): that needs them back to back, mu first, in the fp32
+    flat buffer (= the bf16 shadow) and in the bf16 gradient buffer."""
+    from disentangle_mlp_b200 import trainer as tr
+    from oracle import nets, steps
+
+    net = nets.VAE(steps.make_opt())
+    named = [(n, tuple(p.shape)) for n, p in net.named_parameters()]
+    for bf16_big in (True, False):
+        plan = tr.plan_layout(named, bf16_big)
+        a, b = "x_to_mu.0.weight", "x_to_logvar.0.weight"
+        assert plan["offsets"][b] == plan["offsets"][a] + plan["numel"][a]
+        if bf16_big:
+            assert plan["off16"][b] == plan["off16"][a] + plan["numel"][a]
