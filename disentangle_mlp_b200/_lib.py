@@ -59,6 +59,8 @@ _SIGS = {
     "dm_bn_apply_act": [c_void_p, c_int, c_ll, c_int, c_void_p, c_int, c_float, c_void_p, c_int, c_void_p],
     "dm_bn_forward": [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float,
                       c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+    "dm_linear_pair_forward": [c_void_p] * 6 + [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "dm_linear_pair_backward": [c_void_p] * 6 + [c_int, c_int, c_int] + [c_void_p] * 7,
     "dm_bn1d_forward": [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                         c_float, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p],
     "dm_bn1d_backward": [c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_int, c_float, c_void_p, c_ll,

@@ -1102,6 +1102,115 @@ __global__ void reparam_bwd_kernel(const float* __restrict__ dz, const float* __
   if (dlogvar_f32) dlogvar_f32[i] = b;
 }
 
+// The SECOND Linear of the encoder's two heads (model.py:464,470: Linear(2048, 128) of x_to_mu and x_to_logvar) for
+// BOTH heads in one launch.  These are 17 MFLOP problems: a tensor-core launch per head costs its fixed ~10 us (plus
+// a zero fill, a bf16 cast, a column-sum pair ...), a SIMT kernel over both heads a few.  PairPtrs: [0] = mu, [1] = logvar.
+struct PairPtrs {
+  const void* x[2];   // bf16 [rows][k]   inputs of the Linear (h1)
+  const void* w[2];   // bf16 [n][k]      weights (optimizer's bf16 shadow)
+  const float* b[2];  // fp32 [n]         biases (forward)
+  const float* d[2];  // fp32 [rows][n]   output gradients (backward)
+  float* out[2];      // fp32 [rows][n]   forward outputs
+  void* dx[2];        // bf16 [rows][k]   input gradients
+  float* dw[2];       // fp32 [n][k]      weight gradients (accumulated)
+  float* db[2];       // fp32 [n]         bias gradients (accumulated)
+};
+
+// out[r][nn] = sum_j x[r][j] w[nn][j] + b[nn]: block = 8 rows x 8 output columns (one column per warp), lanes split k.
+// All nine 16-byte loads of an iteration are issued before the first FMA (guarded loads interleaved with their FMAs
+// serialise on the L2 latency: 118 us instead of a few).
+__global__ void __launch_bounds__(256) linear_pair_fwd_kernel(const PairPtrs p, int rows, int n, int k) {
+  pdl_sync();
+  const int head = blockIdx.z, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nn = blockIdx.x * 8 + warp;
+  const int r0 = blockIdx.y * 8;
+  if (nn >= n) return;
+  const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(p.x[head]);
+  const __nv_bfloat16* w = static_cast<const __nv_bfloat16*>(p.w[head]) + static_cast<long long>(nn) * k;
+  float* out = p.out[head];
+  const float bias = p.b[head] ? p.b[head][nn] : 0.f;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int j = lane * 8; j < k; j += 256) {
+    float wf[8], xf[8][8];
+    load8(w + j, wf);
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) {
+      const int r = min(r0 + rr, rows - 1);  // (clamped: rows past the end are computed and not stored)
+      load8(x + static_cast<long long>(r) * k + j, xf[rr]);
+    }
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[rr] = fmaf(xf[rr][i], wf[i], acc[rr]);
+  }
+#pragma unroll
+  for (int rr = 0; rr < 8; ++rr) {
+    float v = acc[rr];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0 && r0 + rr < rows) out[static_cast<long long>(r0 + rr) * n + nn] = v + bias;
+  }
+}
+
+// dx[r][j] = sum_kk d[r][kk] w[kk][j]: block = 8 rows x 256 columns, thread = one column j; n <= 128
+__global__ void __launch_bounds__(256) linear_pair_dgrad_kernel(const PairPtrs p, int rows, int n, int k) {
+  pdl_sync();
+  __shared__ float d_s[8][128];
+  const int head = blockIdx.z;
+  const int r0 = blockIdx.y * 8;
+  for (int i = threadIdx.x; i < 8 * n; i += 256) {
+    const int rr = i / n, kk = i - rr * n;
+    d_s[rr][kk] = (r0 + rr < rows) ? p.d[head][static_cast<long long>(r0 + rr) * n + kk] : 0.f;
+  }
+  __syncthreads();
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= k) return;
+  const __nv_bfloat16* w = static_cast<const __nv_bfloat16*>(p.w[head]);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+  for (int kk = 0; kk < n; ++kk) {
+    const float wv = __bfloat162float(w[static_cast<long long>(kk) * k + j]);
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) acc[rr] = fmaf(d_s[rr][kk], wv, acc[rr]);
+  }
+  __nv_bfloat16* dx = static_cast<__nv_bfloat16*>(p.dx[head]);
+#pragma unroll
+  for (int rr = 0; rr < 8; ++rr)
+    if (r0 + rr < rows) dx[static_cast<long long>(r0 + rr) * k + j] = __float2bfloat16_rn(acc[rr]);
+}
+
+// dw[kk][j] += sum_r d[r][kk] x[r][j]; db[kk] += sum_r d[r][kk]: block = 16 output features x 256 columns; rows <= 256
+__global__ void __launch_bounds__(256) linear_pair_wgrad_kernel(const PairPtrs p, int rows, int n, int k) {
+  pdl_sync();
+  __shared__ float d_s[256][16];
+  const int head = blockIdx.z;
+  const int k0 = blockIdx.y * 16;
+  for (int i = threadIdx.x; i < rows * 16; i += 256) {
+    const int r = i >> 4, kk = i & 15;
+    d_s[r][kk] = (k0 + kk < n) ? p.d[head][static_cast<long long>(r) * n + k0 + kk] : 0.f;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x < 16 && k0 + threadIdx.x < n && p.db[head]) {
+    float sb = 0.f;
+    for (int r = 0; r < rows; ++r) sb += d_s[r][threadIdx.x];
+    p.db[head][k0 + threadIdx.x] += sb;
+  }
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= k) return;
+  const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(p.x[head]);
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+#pragma unroll 4
+  for (int r = 0; r < rows; ++r) {
+    const float xv = __bfloat162float(x[static_cast<long long>(r) * k + j]);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = fmaf(d_s[r][i], xv, acc[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    if (k0 + i < n) p.dw[head][static_cast<long long>(k0 + i) * k + j] += acc[i];
+}
+
 // Discriminator head Linear(k,1)+Sigmoid (models/model.py:406-408): one warp per row
 __global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__ feat, int rows, int k,
                                                        const float* __restrict__ w, const float* __restrict__ b,
@@ -1627,6 +1736,33 @@ extern "C" int dm_head_forward(const float* feat, int rows, int k, const float* 
   DM_REQUIRE(k % 4 == 0, "dm_head_forward: k must be a multiple of 4");
   launch_pdl(head_fwd_kernel, (rows + 7) / 8, 256, 0, s, feat, rows, k, w, b, prob);
   DM_LAUNCHED("dm_head_forward");
+}
+
+extern "C" int dm_linear_pair_forward(const void* x0, const void* x1, const void* w0, const void* w1, const float* b0,
+                                      const float* b1, int rows, int n, int k, float* out0, float* out1, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  DM_REQUIRE(k % 256 == 0 && n % 8 == 0 && rows >= 1, "dm_linear_pair_forward: k %d (%% 256), n %d (%% 8)", k, n);
+  PairPtrs p = {};
+  p.x[0] = x0; p.x[1] = x1; p.w[0] = w0; p.w[1] = w1; p.b[0] = b0; p.b[1] = b1; p.out[0] = out0; p.out[1] = out1;
+  launch_pdl(linear_pair_fwd_kernel, dim3(n / 8, (rows + 7) / 8, 2), 256, 0, s, p, rows, n, k);
+  DM_LAUNCHED("dm_linear_pair_forward");
+}
+
+extern "C" int dm_linear_pair_backward(const float* d0, const float* d1, const void* x0, const void* x1, const void* w0,
+                                       const void* w1, int rows, int n, int k, void* dx0, void* dx1, float* dw0,
+                                       float* dw1, float* db0, float* db1, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  DM_REQUIRE(k % 256 == 0 && n <= 128 && n % 16 == 0 && rows >= 1 && rows <= 256,
+             "dm_linear_pair_backward: k %d (%% 256), n %d (<= 128, %% 16), rows %d (<= 256)", k, n, rows);
+  PairPtrs p = {};
+  p.d[0] = d0; p.d[1] = d1; p.x[0] = x0; p.x[1] = x1; p.w[0] = w0; p.w[1] = w1;
+  p.dx[0] = dx0; p.dx[1] = dx1; p.dw[0] = dw0; p.dw[1] = dw1; p.db[0] = db0; p.db[1] = db1;
+  launch_pdl(linear_pair_dgrad_kernel, dim3(k / 256, (rows + 7) / 8, 2), 256, 0, s, p, rows, n, k);
+  if (dw0 && dw1) {
+    launch_pdl(linear_pair_wgrad_kernel, dim3(k / 256, n / 16, 2), 256, 0, s, p, rows, n, k);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  }
+  DM_LAUNCHED("dm_linear_pair_backward");
 }
 
 extern "C" int dm_head_backward(const float* dprob, const float* prob, const float* feat, const float* dfeat_ext,

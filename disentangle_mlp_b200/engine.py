@@ -56,6 +56,7 @@ def _lin_w(cache, name, p):
 
 
 FUSE_HEADS = os.environ.get("DM_FUSE_HEADS", "1") != "0"
+PAIR_HEADS = os.environ.get("DM_PAIR_HEADS", "0") != "0"  # measured slower than the two tensor-core launches (4.46 vs 4.42 ms): off
 HEADS = ("x_to_mu", "x_to_logvar")
 
 
@@ -507,10 +508,13 @@ def encoder_forward(x, P, B, cache: OperandCache, training=True, pim=None, befor
             w0 = _lin_w(cache, head + ".0", P[head + ".0.weight"])
             acc = linear_forward(S.flat, w0, P[head + ".0.bias"].detach(), b, 2048, 16384)
             h1, bn = bn_act_forward(acc, b, 2048, P, B, head + ".1", ACT_RELU, training, 1, cache)
-        w3 = _lin_w(cache, head + ".3", P[head + ".3.weight"])
-        out = linear_forward(h1, w3, P[head + ".3.bias"].detach(), b, 128, 2048)
         S.heads[head] = SimpleNamespace(h1=h1, bn=bn)
-        outs.append(out)
+    w3 = [_lin_w(cache, head + ".3", P[head + ".3.weight"]) for head in HEADS]
+    b3 = [P[head + ".3.bias"].detach() for head in HEADS]
+    if PAIR_HEADS:  # both heads' Linear(2048, 128) in one SIMT launch (17 MFLOP each: a tensor-core launch is all overhead)
+        outs = ops.linear_pair_forward(S.heads[HEADS[0]].h1, S.heads[HEADS[1]].h1, w3[0], w3[1], b3[0], b3[1])
+    else:
+        outs = [linear_forward(S.heads[head].h1, w3[i], b3[i], b, 128, 2048) for i, head in enumerate(HEADS)]
     return outs[0], outs[1], S
 
 
@@ -529,17 +533,24 @@ def encoder_backward(S, dmu, dlogvar, P, G, cache: OperandCache, need_wgrad=True
         "fused heads: the two 16384x2048 weights / gradients must be adjacent in the flat buffers"
     dflat = None if fused else torch.zeros((b, 16384), dtype=F32, device=dev)
     dacc_cat = torch.empty((b, 4096), dtype=BF16, device=dev) if fused else None
-    for i, (head, d) in enumerate((("x_to_mu", dmu), ("x_to_logvar", dlogvar))):
+    ds = [torch.zeros((b, 128), dtype=F32, device=dev) if d is None else d.contiguous() for d in (dmu, dlogvar)]
+    pair = PAIR_HEADS and b <= 256
+    if pair:  # both heads' Linear(2048, 128): input gradient, weight gradient and bias gradient in two SIMT launches
+        w3 = [_lin_w(cache, head + ".3", P[head + ".3.weight"]) for head in HEADS]
+        dh1s = ops.linear_pair_backward(ds[0], ds[1], S.heads[HEADS[0]].h1, S.heads[HEADS[1]].h1, w3[0], w3[1],
+                                        *([wg[h + ".3.weight"] for h in HEADS] + [wg[h + ".3.bias"] for h in HEADS]
+                                          if wg else [None] * 4))
+    for i, (head, d) in enumerate(zip(HEADS, ds)):
         H = S.heads[head]
-        if d is None:
-            d = torch.zeros((b, 128), dtype=F32, device=dev)
-        d = d.contiguous()
-        d16 = ops.cast_bf16(d)
-        if wg:
-            ops.colsum(d, b, 128, wg[head + ".3.bias"])
-            linear_wgrad(d16, H.h1, b, 128, 2048, wg[head + ".3.weight"])
-        w3 = _lin_w(cache, head + ".3", P[head + ".3.weight"])
-        dh1 = linear_dgrad(d16, w3, b, 128, 2048)
+        if pair:
+            dh1 = dh1s[i]
+        else:
+            d16 = ops.cast_bf16(d)
+            if wg:
+                ops.colsum(d, b, 128, wg[head + ".3.bias"])
+                linear_wgrad(d16, H.h1, b, 128, 2048, wg[head + ".3.weight"])
+            w3 = _lin_w(cache, head + ".3", P[head + ".3.weight"])
+            dh1 = linear_dgrad(d16, w3, b, 128, 2048)
         if fused:
             ops.bn1d_backward_cols(dh1, S.acc_cat, i * 2048, 2048, H.bn.scale_shift, H.bn.mean_invstd, ACT_RELU, LEAKY,
                                    dacc_cat, wg[head + ".1.weight"] if wg else None, wg[head + ".1.bias"] if wg else None)

@@ -326,6 +326,28 @@ def bn_backward(dout, y, rows, c, scale_shift, mean_invstd, act, slope=0.2, dgam
     return dy
 
 
+def linear_pair_forward(x0, x1, w0, w1, b0, b1):
+    """(x0 @ w0^T + b0, x1 @ w1^T + b1) in one launch: x bf16 [rows, k], w bf16 [n, k] -> fp32 [rows, n] each."""
+    rows, k = x0.shape
+    n = w0.shape[0]
+    out = torch.empty((2, rows, n), dtype=F32, device=x0.device)
+    _lib.check(_lib.load().dm_linear_pair_forward(_p(x0), _p(x1), _p(w0), _p(w1), _p(b0), _p(b1), rows, n, k, _p(out[0]),
+                                                  _p(out[1]), _stream()), "dm_linear_pair_forward")
+    return out[0], out[1]
+
+
+def linear_pair_backward(d0, d1, x0, x1, w0, w1, dw0=None, dw1=None, db0=None, db1=None):
+    """Backward of linear_pair_forward: d fp32 [rows, n] -> (dx0, dx1) bf16 [rows, k]; dw / db accumulated when given."""
+    rows, k = x0.shape
+    n = w0.shape[0]
+    assert d0.dtype == F32 and d1.dtype == F32
+    dx = torch.empty((2, rows, k), dtype=BF16, device=x0.device)
+    _lib.check(_lib.load().dm_linear_pair_backward(_p(d0), _p(d1), _p(x0), _p(x1), _p(w0), _p(w1), rows, n, k, _p(dx[0]),
+                                                   _p(dx[1]), _p(dw0), _p(dw1), _p(db0), _p(db1), _stream()),
+               "dm_linear_pair_backward")
+    return dx[0], dx[1]
+
+
 def bn1d_forward_cols(acc, col0, c, pre_bias, gamma, beta, running_mean, running_var, nbt, act, slope=0.2, momentum=0.1,
                       eps=1e-5):
     """BatchNorm1d + activation of columns [col0, col0 + c) of the fp32 matrix acc [rows, ld] (dm_bn1d_forward).

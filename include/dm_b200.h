@@ -252,6 +252,16 @@ int dm_reparam_backward(const float* dz, const float* logvar, const float* eps, 
                         const float* dlogvar_ext, long long n, void* dmu_bf16, void* dlogvar_bf16,
                         float* dmu_f32, float* dlogvar_f32, void* stream);
 
+/* The second Linear of the encoder's two heads (Linear(2048, 128) of x_to_mu and x_to_logvar, model.py:464,470) for BOTH
+ * heads in one launch (SIMT: 17 MFLOP each).  x bf16 [rows][k], w bf16 [n][k], out / d fp32 [rows][n].
+ * backward: dx bf16 [rows][k] = d w;  dw fp32 [n][k] += d^T x and db fp32 [n] += column sums of d (skipped when dw0 or
+ * dw1 is NULL).  k % 256 == 0; backward: n <= 128, n % 16 == 0, rows <= 256. */
+int dm_linear_pair_forward(const void* x0, const void* x1, const void* w0, const void* w1, const float* b0, const float* b1,
+                           int rows, int n, int k, float* out0, float* out1, void* stream);
+int dm_linear_pair_backward(const float* d0, const float* d1, const void* x0, const void* x1, const void* w0,
+                            const void* w1, int rows, int n, int k, void* dx0, void* dx1, float* dw0, float* dw1,
+                            float* db0, float* db1, void* stream);
+
 /* Discriminator head Linear(k,1)+Sigmoid (model.py:406-408) and its backward. */
 int dm_head_forward(const float* feat, int rows, int k, const float* w, const float* b, float* prob,
                     void* stream);

@@ -433,3 +433,31 @@ def test_bn1d_on_column_blocks_with_pre_bias(ops, rows):
         other = dy[:, (1 - head) * c:(2 - head) * c]
         assert bool((other == 7.0).all())  # the other head's columns are untouched
         assert float((dg - gr.grad).norm() / gr.grad.norm()) < 2e-3 and float((db - br.grad).norm() / br.grad.norm()) < 2e-3
+
+
+@pytest.mark.parametrize("rows", [5, 64, 256])
+def test_linear_pair_kernels(ops, rows):
+    """dm_linear_pair_forward / backward: Linear(2048, 128) of both encoder heads (model.py:464,470) in one launch against
+    torch on the same bf16 operands (fp32 accumulation)."""
+    torch.manual_seed(rows)
+    n, k = 128, 2048
+    xs = [torch.randn(rows, k, device="cuda").bfloat16() for _ in range(2)]
+    ws = [(torch.randn(n, k, device="cuda") * 0.03).bfloat16() for _ in range(2)]
+    bs = [torch.randn(n, device="cuda") for _ in range(2)]
+    o0, o1 = ops.linear_pair_forward(xs[0], xs[1], ws[0], ws[1], bs[0], bs[1])
+    for o, x, w, b in zip((o0, o1), xs, ws, bs):
+        ref = x.float() @ w.float().t() + b
+        assert float((o - ref).norm() / ref.norm()) < 1e-5
+    ds = [torch.randn(rows, n, device="cuda") for _ in range(2)]
+    dws = [torch.full((n, k), 0.5, device="cuda") for _ in range(2)]  # accumulated into
+    dbs = [torch.full((n,), -1.0, device="cuda") for _ in range(2)]
+    dx0, dx1 = ops.linear_pair_backward(ds[0], ds[1], xs[0], xs[1], ws[0], ws[1], dws[0], dws[1], dbs[0], dbs[1])
+    for dx, d, x, w, dw, db in zip((dx0, dx1), ds, xs, ws, dws, dbs):
+        ref_dx = d @ w.float()
+        assert float((dx.float() - ref_dx).norm() / ref_dx.norm()) < 4e-3  # one bf16 rounding of the result
+        ref_dw = d.t() @ x.float() + 0.5
+        assert float((dw - ref_dw).norm() / ref_dw.norm()) < 1e-5
+        assert torch.allclose(db, d.sum(0) - 1.0, atol=1e-4, rtol=1e-5)
+    # input gradient only (the discarded-weight-gradient phases): dw / db untouched
+    dx0b, _ = ops.linear_pair_backward(ds[0], ds[1], xs[0], xs[1], ws[0], ws[1])
+    assert torch.equal(dx0b, dx0)

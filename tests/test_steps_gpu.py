@@ -37,7 +37,12 @@ def test_vae_trainer_tracks_oracle(mods):
         eps = torch.randn(b, 128, generator=torch.Generator().manual_seed(90 + s))
         r = steps.vae_step(ref, o, x, eps)
         m = float(T.step(x.cuda(), eps.cuda())["loss"])
-        assert abs(m - r["loss"]) <= 1e-2 * r["loss"], (s, m, r["loss"])
+        # step 0 runs on the initial parameters: bf16 forward error only.  Later steps follow Adam's first updates
+        # (~lr*sign(g) per element): identical runs of THIS path already differ from each other by up to 1.2e-2 there
+        # (fp32 atomic order -> sign flips of near-zero gradients; tools/flake_hunt.py, profiles/r02b_run_to_run_spread.txt),
+        # so the free-running bound is 3e-2; the per-step error is bounded at 1e-3 by the teacher-forced tests
+        tol = 2e-3 if s == 0 else 3e-2
+        assert abs(m - r["loss"]) <= tol * r["loss"], (s, m, r["loss"])
     T.sync()  # (apply the deferred update of the big Linear weights before reading the parameters)
     assert params_rel(mine, ref) < 3e-2
     assert int(mine.features[1].num_batches_tracked) == 5
